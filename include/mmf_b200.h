@@ -1,0 +1,144 @@
+/*
+ * mmf_b200.h -- C ABI of libmmf_b200.so: the B200-native (sm_100a) generation hot path of
+ * dfaroughy/Multimodal-flows.  Plain pointers and sizes only; no torch types cross this boundary.
+ *
+ * Every entry point replaces one piece of the reference's PyTorch hot path (paths relative to
+ * /root/reference/multimodal_flows):
+ *
+ *   mmf_model_create / destroy   MODEL_REGISTRY[config.model](config) + load_state_dict
+ *                                networks/registry.py:4-9, model/MMF.py:30, model/CFM.py:23
+ *   mmf_encoder_forward          ParticleFormer.forward       networks/ParticleTransformers.py:62-122
+ *                                FusedParticleFormer.forward  networks/ParticleTransformers.py:177-210
+ *                                EPiC.forward                 networks/EPiC.py:38-62
+ *   mmf_hybrid_step              HybridSolver.tauleap_step    model/solvers.py:22-60   (after the model call)
+ *                                RandomTelegraphBridge.rate   model/MJB.py:163-195
+ *   mmf_euler_step               ContinuousSolver.euler_step  model/solvers.py:139-143 (after the model call)
+ *   mmf_generate[_host]          MultiModalFlowBridge.simulate_dynamics  model/MMF.py:172-200
+ *                                ConditionalFlowMatching.simulate_dynamics  model/CFM.py:133-154
+ *
+ * Conventions
+ *   - all functions return 0 on success, non-zero on failure; mmf_last_error() gives a thread-local message.
+ *   - "device" pointers are CUDA device pointers on the model's device, "host" pointers are host memory.
+ *   - tensors are contiguous, row-major:  x (B,D,3) float32,  k (B,D) int64,  mask (B,D) int64 (non-zero = real
+ *     particle),  t (B,) float32,  logits / rates / u (B,D,V) float32.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls are asynchronous with respect
+ *     to the host except where noted; they never allocate or free caller memory.
+ *   - outputs at padded slots (mask == 0) are zero.  The reference lets padded slots evolve and zeroes them in
+ *     FlowGeneratorCallback (utils/callbacks.py:57); real slots never depend on them.
+ *   - a handle is bound to one device and is not thread-safe; different handles are independent.
+ */
+#ifndef MMF_B200_H
+#define MMF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMF_ABI_VERSION 1
+
+typedef struct MmfModel MmfModel;
+
+enum MmfArch { MMF_ARCH_PARTICLEFORMER = 0, MMF_ARCH_FUSED_PARTICLEFORMER = 1, MMF_ARCH_EPIC = 2 };
+
+/* Hyper-parameters read by the hot path (reference scripts/train_mmf.py:42-56). */
+typedef struct MmfModelDesc {
+    int32_t arch;               /* enum MmfArch */
+    int32_t vocab_size;         /* V, 9 */
+    int32_t dim_continuous;     /* 3 */
+    int32_t n_embd;             /* 256 */
+    int32_t n_inner;            /* 512 */
+    int32_t n_head;             /* 4 */
+    int32_t n_layer;            /* 5 */
+    int32_t n_layer_fused;      /* 6 (ParticleFormer only) */
+    int32_t n_embd_glob;        /* 16 (EPiC only) */
+    int32_t qk_layernorm;       /* 1 */
+    int32_t max_num_particles;  /* D, 150 */
+} MmfModelDesc;
+
+/* One named fp32 parameter of the reference state_dict (host memory, row-major). */
+typedef struct MmfWeightRef {
+    const char* name;           /* e.g. "transformer.blocks_x.0.attn.c_attn.weight" */
+    const float* data;
+    int32_t ndim;
+    int64_t shape[4];
+} MmfWeightRef;
+
+/* Per-call sampling options (reference config.temperature/top_k/top_p/beta/use_final_max_rates). */
+typedef struct MmfStepOptions {
+    float temperature;          /* logits / T when T != 1 */
+    float beta;                 /* telegraph stochasticity */
+    int32_t top_k;              /* <= 0: off */
+    float top_p;                /* <= 0: off */
+    int32_t use_final_max_rates;
+    uint64_t seed;              /* Philox key when no uniforms are supplied */
+    uint64_t first_global_jet;  /* global index of jet 0 of this call: draws depend on (seed, global slot, step) only */
+} MmfStepOptions;
+
+int mmf_abi_version(void);
+const char* mmf_last_error(void);
+
+/* Packs the checkpoint for the device (bf16 K-major matrices, folded tables) and allocates nothing else until
+ * the first forward.  Fails on hyper-parameters outside the accelerated envelope (n_embd 256, n_inner 512,
+ * n_head 4, D <= 160, V <= 16); there is no fallback path.  Synchronous. */
+int mmf_model_create(const MmfModelDesc* desc, const MmfWeightRef* weights, int32_t n_weights, int32_t device,
+                     MmfModel** out);
+void mmf_model_destroy(MmfModel* model);
+
+/* One encoder forward.  Device pointers.  t is per jet.  logits_out may be NULL for EPiC (k is ignored then).
+ * Synchronises once internally (multiplicities are read back to plan the packed layout). */
+int mmf_encoder_forward(MmfModel* model, const float* x, const int64_t* k, const int64_t* mask, const float* t,
+                        int32_t B, int32_t D, float* vt_out, float* logits_out, void* stream);
+
+/* The fused hybrid step on device tensors, in place on x and k: Euler update of x, telegraph tau-leap of k.
+ * u: (B,D,V) uniforms in [0,1) or NULL (Philox from opts->seed, opts->first_global_jet, step_index).
+ * rates_out: (B,D,V) or NULL.  No model handle needed; `device` selects the GPU. */
+int mmf_hybrid_step(const float* vt, const float* logits, float* x, int64_t* k, const float* t, float dt,
+                    const MmfStepOptions* opts, const float* u, uint32_t step_index, int32_t B, int32_t D,
+                    int32_t V, float* rates_out, int32_t device, void* stream);
+
+/* x += vt * dt on n floats (EPiC / ContinuousSolver carrier). */
+int mmf_euler_step(const float* vt, float* x, float dt, int64_t n, int32_t device, void* stream);
+
+/* The whole N-step sampler on device tensors.
+ *   t_grid      host array of the N time points (the caller builds torch.linspace(eps, 1-eps, N) so that it is
+ *               bit-identical to the reference), dt = (t[N-1]-t[0])/(N-1) likewise
+ *   u           device (N,B,D,V) supplied uniforms or NULL
+ *   forced_k    device (N,B,D) uint8 teacher-forced tokens applied after each step, or NULL
+ *   rates_out   device (B,D,V) rates of the last step, or NULL
+ * k0 / k_out / opts may be NULL for EPiC.  x_out may alias x0, k_out may alias k0. */
+int mmf_generate(MmfModel* model, const float* x0, const int64_t* k0, const int64_t* mask, int32_t B, int32_t D,
+                 const float* t_grid, int32_t N, float dt, const MmfStepOptions* opts, const float* u,
+                 const uint8_t* forced_k, float* x_out, int64_t* k_out, float* rates_out, void* stream);
+
+/* Same with HOST buffers: stages inputs to the device, runs, copies results back and waits. */
+int mmf_generate_host(MmfModel* model, const float* x0, const int64_t* k0, const int64_t* mask, int32_t B, int32_t D,
+                      const float* t_grid, int32_t N, float dt, const MmfStepOptions* opts, float* x_out,
+                      int64_t* k_out);
+
+/* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
+int64_t mmf_launch_count(const MmfModel* model);
+
+/* ---- diagnostics: the building-block kernels, exposed so that tests can check each against torch ---- */
+/* out = epilogue(A[M,K] * W[N,K]^T + bias); device pointers; A, W bf16; M multiple of 128, K multiple of 64.
+ * mode 0: bf16 out (act 0 none / 1 GELU); mode 1: fp32 out (N multiple of 128) */
+int mmf_dbg_gemm(const void* A_bf16, const void* W_bf16, const float* bias, int32_t M, int32_t N, int32_t K,
+                 int32_t mode, int32_t act, void* out, int32_t device, void* stream);
+/* residual[M,C] += A*W^T + bias (+ temb[0,:]); act_out[M,C] = bf16(LayerNorm(residual)); C in {128,256} */
+int mmf_dbg_gemm_resln(const void* A_bf16, const void* W_bf16, const float* bias, const float* temb,
+                       const float* ln_g, const float* ln_b, int32_t M, int32_t C, int32_t K, float* residual,
+                       void* act_out_bf16, int32_t device, void* stream);
+/* fused QKV projection: q,k [M,C] bf16 with per-head LayerNorm, vT [C,M] bf16 */
+int mmf_dbg_gemm_qkv(const void* A_bf16, const void* W_bf16, const float* bias, const float* q_g, const float* q_b,
+                     const float* k_g, const float* k_b, int32_t M, int32_t C, int32_t hs, void* q_out, void* k_out,
+                     void* vT_out, int32_t device, void* stream);
+/* masked attention over packed jets: q,k [M,C] bf16, vT [C,M] bf16, jet_n host array of n_jets multiplicities
+ * (rows are the jets back to back); out [M,C] bf16.  Synchronous. */
+int mmf_dbg_attention(const void* q, const void* k, const void* vT, const int32_t* jet_n, int32_t n_jets, int32_t M,
+                      int32_t C, int32_t hs, void* out, int32_t device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMF_B200_H */

@@ -1,0 +1,450 @@
+// CUDA-core kernels of the hot path: the fused hybrid step, packing, the K=3 input embedding, row
+// LayerNorms that sit between streams, and the tiny output projections fused with the step.
+// All are memory-bound: one coalesced, vectorised pass over the data.
+#include "mmf_internal.h"
+#include "mmf_simt.h"
+
+namespace mmf {
+
+namespace {
+
+__device__ __forceinline__ float gelu_erf_simt(float x) {
+    const float z = fabsf(x) * 0.70710678f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.0f - p * t * exp2f(-1.44269504f * z * z);
+    return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1. fused hybrid step on the padded (B, D) layout  -- north_star kernel (2)
+//    reads vt(12) logits(4V) x(12) k(8) [u(4V)]  writes x(12) k(8) [rates(4V)]  bytes per particle
+// ---------------------------------------------------------------------------------------------
+constexpr int kStepThreads = 256;
+
+// cooperative, coalesced copy of `count` floats between global and shared memory (float4 when aligned)
+__device__ __forceinline__ void block_load(float* s, const float* g, int count, int valid) {
+    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0 && valid == count) {
+        const float4* g4 = reinterpret_cast<const float4*>(g);
+        float4* s4 = reinterpret_cast<float4*>(s);
+        for (int i = threadIdx.x; i < count / 4; i += blockDim.x) s4[i] = __ldcs(g4 + i);
+        for (int i = (count / 4) * 4 + threadIdx.x; i < count; i += blockDim.x) s[i] = __ldcs(g + i);
+    } else {
+        for (int i = threadIdx.x; i < valid; i += blockDim.x) s[i] = __ldcs(g + i);
+    }
+}
+__device__ __forceinline__ void block_store(float* g, const float* s, int count, int valid) {
+    if ((reinterpret_cast<uintptr_t>(g) & 15) == 0 && valid == count) {
+        float4* g4 = reinterpret_cast<float4*>(g);
+        const float4* s4 = reinterpret_cast<const float4*>(s);
+        for (int i = threadIdx.x; i < count / 4; i += blockDim.x) __stcs(g4 + i, s4[i]);
+        for (int i = (count / 4) * 4 + threadIdx.x; i < count; i += blockDim.x) __stcs(g + i, s[i]);
+    } else {
+        for (int i = threadIdx.x; i < valid; i += blockDim.x) __stcs(g + i, s[i]);
+    }
+}
+
+template <int V>
+__global__ void __launch_bounds__(kStepThreads)
+hybrid_step_kernel(const float* __restrict__ vt, const float* __restrict__ logits, float* __restrict__ x,
+                   long long* __restrict__ k, const float* __restrict__ t, long long n_particles, int D,
+                   const StepLaunch sl, float* __restrict__ rates_out) {
+    __shared__ __align__(16) float s_lg[kStepThreads * V];      // logits in, rates out
+    __shared__ __align__(16) float s_u[kStepThreads * V];
+    __shared__ __align__(16) float s_x[kStepThreads * 3];
+    __shared__ __align__(16) float s_v[kStepThreads * 3];
+
+    const long long base = static_cast<long long>(blockIdx.x) * kStepThreads;
+    const long long remain = n_particles - base;
+    const int nval = remain < kStepThreads ? static_cast<int>(remain) : kStepThreads;
+    block_load(s_lg, logits + base * V, kStepThreads * V, nval * V);
+    if (sl.u) block_load(s_u, sl.u + base * V, kStepThreads * V, nval * V);
+    block_load(s_x, x + base * 3, kStepThreads * 3, nval * 3);
+    block_load(s_v, vt + base * 3, kStepThreads * 3, nval * 3);
+    __syncthreads();
+
+    const int tid = threadIdx.x;
+    const long long i = base + tid;
+    if (tid < nval) {
+        float lg[V], u[V], rates[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) lg[v] = s_lg[tid * V + v];
+        if (sl.u) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) u[v] = s_u[tid * V + v];
+        } else {
+            philox_uniforms(sl.seed, sl.slot0 + static_cast<uint64_t>(i), sl.step, V, u);
+        }
+        long long kc = k[i];
+        if (kc < 0 || kc >= V) { atomicOr(sl.err_flag, 2); kc = 0; }
+        float w, coef;
+        det_thermostat(__ldg(t + i / D), sl.sp.beta, V, &w, &coef);
+        const int kn = step_particle<V>(lg, static_cast<int>(kc), w, coef, sl.sp, u, rates_out ? rates : nullptr);
+        k[i] = kn;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s_x[tid * 3 + c] = euler_update(s_x[tid * 3 + c], s_v[tid * 3 + c], sl.sp.dt);
+        if (rates_out) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) s_lg[tid * V + v] = rates[v];
+        }
+    }
+    __syncthreads();
+    block_store(x + base * 3, s_x, kStepThreads * 3, nval * 3);
+    if (rates_out) block_store(rates_out + base * V, s_lg, kStepThreads * V, nval * V);
+}
+
+__global__ void euler_kernel(const float* __restrict__ vt, float* __restrict__ x, float dt, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = euler_update(x[i], vt[i], dt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. packing: (B, D, .) with prefix-or-arbitrary masks  <->  [rows, .] over real particles only
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_kernel(const float* __restrict__ x0, const long long* __restrict__ k0,
+                            const int* __restrict__ row_slot, int rows, int V, float* __restrict__ xs,
+                            int* __restrict__ ks, int* err_flag) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const long long s = row_slot[r];
+    xs[r * 3 + 0] = x0[s * 3 + 0];
+    xs[r * 3 + 1] = x0[s * 3 + 1];
+    xs[r * 3 + 2] = x0[s * 3 + 2];
+    int kk = 0;
+    if (k0) {
+        const long long kv = k0[s];
+        if (kv < 0 || kv >= V) atomicOr(err_flag, 2); else kk = static_cast<int>(kv);
+    }
+    ks[r] = kk;
+}
+
+__global__ void unpack_kernel(const float* __restrict__ xs, const int* __restrict__ ks,
+                              const int* __restrict__ row_slot, int rows, float* __restrict__ x_out,
+                              long long* __restrict__ k_out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const long long s = row_slot[r];
+    x_out[s * 3 + 0] = xs[r * 3 + 0];
+    x_out[s * 3 + 1] = xs[r * 3 + 1];
+    x_out[s * 3 + 2] = xs[r * 3 + 2];
+    if (k_out) k_out[s] = ks[r];
+}
+
+__global__ void force_tokens_kernel(const unsigned char* __restrict__ forced, const int* __restrict__ row_slot,
+                                    int rows, int* __restrict__ ks) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) ks[r] = forced[row_slot[r]];
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. input embedding, first layer: h = GELU(W0 x + b0), K = 3 -> CUDA cores   (wxe.0 / epic.wxe)
+//    one thread produces 8 consecutive features of one row (one 16-byte bf16 store)
+// ---------------------------------------------------------------------------------------------
+__global__ void embed_x_kernel(const float* __restrict__ xs, int rows, const float* __restrict__ w0 /*[E][3]*/,
+                               const float* __restrict__ b0, int E, int apply_gelu, bf16* __restrict__ out, int ld_out) {
+    const int per_row = E / 8;
+    const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int r = static_cast<int>(idx / per_row), c0 = static_cast<int>(idx % per_row) * 8;
+    if (r >= rows) return;
+    const float a = xs[r * 3 + 0], b = xs[r * 3 + 1], c = xs[r * 3 + 2];
+    uint32_t packed[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float h[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int f = c0 + j * 2 + q;
+            float v = fmaf(__ldg(w0 + f * 3 + 2), c, fmaf(__ldg(w0 + f * 3 + 1), b, fmaf(__ldg(w0 + f * 3), a, __ldg(b0 + f))));
+            h[q] = apply_gelu ? gelu_erf_simt(v) : v;
+        }
+        __nv_bfloat162 p = __floats2bfloat162_rn(h[0], h[1]);
+        packed[j] = *reinterpret_cast<uint32_t*>(&p);
+    }
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(r) * ld_out + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. row kernels on the 256-wide residual stream, one warp per row, lane owns 8 consecutive columns.
+//    LayerNorm groups are either two halves of 128 (ParticleFormer's x | y streams) or the full 256.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float group_sum(float v, int group_width) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    if (group_width == 256) v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+}
+// v[8] = this lane's columns [lane*8, lane*8+8).  Normalises in place over the lane's group.
+__device__ __forceinline__ void warp_layernorm(float* v, int lane, int group_width, const float* g, const float* b) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    const float mean = group_sum(s, group_width) / group_width;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(group_sum(q, group_width) / group_width + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf((v[i] - mean) * rstd, __ldg(g + lane * 8 + i), b ? __ldg(b + lane * 8 + i) : 0.f);
+}
+__device__ __forceinline__ void load8(const float* p, float* v) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8_bf16(bf16* p, const float* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// after the wxe.2 GEMM:  x-half = LN_ln1x(raw) + temb ;  y-half = Ytab[k] + temb ;  keep a copy as the skip
+// stream; emit the first block's LayerNorm as the bf16 GEMM operand.
+__global__ void embed_finish_kernel(EmbedFinishArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= a.rows) return;
+    const int row = warp;
+    float v[8], yv[8];
+    const float* tb = a.temb + static_cast<size_t>(a.row_jet ? a.row_jet[row] : 0) * a.temb_ld + lane * 8;
+    if (lane < 16) {
+        load8(a.resid + static_cast<size_t>(row) * 256 + lane * 8, v);
+    } else {
+        load8(a.ytab + a.ks[row] * 128 + (lane - 16) * 8, yv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = yv[i];
+    }
+    // all 32 lanes take part in the shuffles; the upper half-warp's result is discarded
+    warp_layernorm(v, lane & 15, 128, a.ln1x_g, a.ln1x_b);
+    if (lane >= 16) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = yv[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += __ldg(tb + i);
+    store8(a.resid + static_cast<size_t>(row) * 256 + lane * 8, v);
+    store8(a.skip + static_cast<size_t>(row) * 256 + lane * 8, v);
+    warp_layernorm(v, lane, a.next_ln_width, a.next_g, a.next_b);
+    store8_bf16(a.act + static_cast<size_t>(row) * 256 + lane * 8, v);
+}
+
+// stream junctions: v = resid + skip ; LN_1 (groups) ; + temb2 ; [write resid] ; [LN_2] ; bf16 operand out
+__global__ void add_ln_kernel(AddLnArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= a.rows) return;
+    const int row = warp;
+    float v[8], s[8];
+    load8(a.resid + static_cast<size_t>(row) * 256 + lane * 8, v);
+    load8(a.skip + static_cast<size_t>(row) * 256 + lane * 8, s);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += s[i];
+    warp_layernorm(v, lane, a.ln1_width, a.ln1_g, a.ln1_b);
+    if (a.temb) {
+        const float* tb = a.temb + static_cast<size_t>(a.row_jet ? a.row_jet[row] : 0) * a.temb_ld + lane * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += __ldg(tb + i);
+    }
+    if (a.write_resid) store8(a.resid + static_cast<size_t>(row) * 256 + lane * 8, v);
+    if (a.ln2_g) warp_layernorm(v, lane, a.ln2_width, a.ln2_g, a.ln2_b);
+    store8_bf16(a.act + static_cast<size_t>(row) * 256 + lane * 8, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 5. output projections (512 -> 3 and 512 -> V) fused with the hybrid step        (head_x.2, head_y.2)
+//    one warp per row: lane owns 16 hidden units of each head, 3 + V dot products, xor-reduce, then lane 0
+//    takes the Euler + telegraph step for the particle (or writes vt / logits for the forward-only API).
+// ---------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256)
+head_out_kernel(HeadOutArgs a) {
+    extern __shared__ float s_w[];            // [3 + V][512] fp32 weights, then [3 + V] biases
+    constexpr int NO = 3 + V;
+    for (int i = threadIdx.x; i < NO * 512; i += blockDim.x) s_w[i] = i < 3 * 512 ? a.wx[i] : a.wy[i - 3 * 512];
+    for (int i = threadIdx.x; i < NO; i += blockDim.x) s_w[NO * 512 + i] = i < 3 ? a.bx[i] : a.by[i - 3];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < a.rows; row += warps_per_grid) {
+        float acc[NO];
+#pragma unroll
+        for (int o = 0; o < NO; ++o) acc[o] = 0.f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {            // 0: head_x hidden, 1: head_y hidden
+            const uint4* src = reinterpret_cast<const uint4*>(a.hidden + static_cast<size_t>(row) * a.ld_hidden + half * 512 + lane * 16);
+            float h[16];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const uint4 raw = __ldg(src + q);
+                const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&w4[j]);
+                    h[q * 8 + j * 2] = __low2float(p);
+                    h[q * 8 + j * 2 + 1] = __high2float(p);
+                }
+            }
+            const int o0 = half == 0 ? 0 : 3, o1 = half == 0 ? 3 : NO;
+#pragma unroll
+            for (int o = 0; o < NO; ++o) {
+                if (o >= o0 && o < o1) {
+                    const float* w = s_w + o * 512 + lane * 16;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[o] = fmaf(h[j], w[j], acc[o]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < NO; ++o) {
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], m);
+            acc[o] += s_w[NO * 512 + o];
+        }
+        if (lane == 0) {
+            const long long slot = a.row_slot[row];
+            if (a.vt_out) {                       // forward-only API: padded (B, D, .) outputs
+                for (int c = 0; c < 3; ++c) a.vt_out[slot * 3 + c] = acc[c];
+                for (int v = 0; v < V; ++v) a.logits_out[slot * V + v] = acc[3 + v];
+            }
+            if (a.do_step) {
+                float u[V], rates[V];
+                if (a.sl.u) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) u[v] = __ldg(a.sl.u + slot * V + v);
+                } else {
+                    philox_uniforms(a.sl.seed, a.sl.slot0 + static_cast<uint64_t>(slot), a.sl.step, V, u);
+                }
+                const int kn = step_particle<V>(acc + 3, a.ks[row], a.w, a.coef, a.sl.sp, u, a.rates_out ? rates : nullptr);
+                a.ks[row] = a.forced ? static_cast<int>(a.forced[slot]) : kn;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) a.xs[row * 3 + c] = euler_update(a.xs[row * 3 + c], acc[c], a.sl.sp.dt);
+                if (a.rates_out) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) a.rates_out[slot * V + v] = rates[v];
+                }
+                if (a.argmax_out) {               // use_final_max_rates (reference model/MMF.py:193-196)
+                    int best = 0;
+#pragma unroll
+                    for (int v = 1; v < V; ++v) best = rates[v] > rates[best] ? v : best;
+                    a.ks[row] = best;
+                }
+            }
+        }
+    }
+}
+
+template <int V>
+int launch_head_out_t(const HeadOutArgs& a, cudaStream_t stream) {
+    const int smem = ((3 + V) * 512 + (3 + V)) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        MMF_CUDA_OK(cudaFuncSetAttribute(head_out_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    int blocks = (a.rows + 7) / 8;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks < 1) blocks = 1;
+    head_out_kernel<V><<<blocks, 256, smem, stream>>>(a);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+#define MMF_DISPATCH_V(V_, CALL)                                        \
+    switch (V_) {                                                       \
+        case 2: { constexpr int VV = 2; CALL; } break;                  \
+        case 3: { constexpr int VV = 3; CALL; } break;                  \
+        case 4: { constexpr int VV = 4; CALL; } break;                  \
+        case 5: { constexpr int VV = 5; CALL; } break;                  \
+        case 6: { constexpr int VV = 6; CALL; } break;                  \
+        case 7: { constexpr int VV = 7; CALL; } break;                  \
+        case 8: { constexpr int VV = 8; CALL; } break;                  \
+        case 9: { constexpr int VV = 9; CALL; } break;                  \
+        case 10: { constexpr int VV = 10; CALL; } break;                \
+        case 12: { constexpr int VV = 12; CALL; } break;                \
+        case 16: { constexpr int VV = 16; CALL; } break;                \
+        default:                                                        \
+            set_last_error("vocab_size must be one of 2..10, 12, 16");  \
+            return 2;                                                   \
+    }
+
+int launch_hybrid_step(const float* vt, const float* logits, float* x, long long* k, const float* t, int B, int D,
+                       const StepLaunch& sl, float* rates_out, cudaStream_t stream) {
+    const long long n = static_cast<long long>(B) * D;
+    if (n == 0) return 0;
+    const unsigned blocks = static_cast<unsigned>((n + kStepThreads - 1) / kStepThreads);
+    MMF_DISPATCH_V(sl.sp.vocab, (hybrid_step_kernel<VV><<<blocks, kStepThreads, 0, stream>>>(vt, logits, x, k, t, n, D, sl, rates_out)));
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_euler(const float* vt, float* x, float dt, long long n, cudaStream_t stream) {
+    if (n == 0) return 0;
+    euler_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(vt, x, dt, n);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_pack(const float* x0, const long long* k0, const int* row_slot, int rows, int V, float* xs, int* ks,
+                int* err_flag, cudaStream_t stream) {
+    if (rows == 0) return 0;
+    pack_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(x0, k0, row_slot, rows, V, xs, ks, err_flag);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_unpack(const float* xs, const int* ks, const int* row_slot, int rows, float* x_out, long long* k_out,
+                  cudaStream_t stream) {
+    if (rows == 0) return 0;
+    unpack_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(xs, ks, row_slot, rows, x_out, k_out);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_force_tokens(const unsigned char* forced, const int* row_slot, int rows, int* ks, cudaStream_t stream) {
+    if (rows == 0) return 0;
+    force_tokens_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(forced, row_slot, rows, ks);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_embed_x(const float* xs, int rows, const float* w0, const float* b0, int E, int apply_gelu, bf16* out,
+                   int ld_out, cudaStream_t stream) {
+    if (rows == 0) return 0;
+    const long long threads = static_cast<long long>(rows) * (E / 8);
+    embed_x_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(xs, rows, w0, b0, E, apply_gelu, out, ld_out);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_embed_finish(const EmbedFinishArgs& a, cudaStream_t stream) {
+    if (a.rows == 0) return 0;
+    embed_finish_kernel<<<(a.rows + 7) / 8, 256, 0, stream>>>(a);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_add_ln(const AddLnArgs& a, cudaStream_t stream) {
+    if (a.rows == 0) return 0;
+    add_ln_kernel<<<(a.rows + 7) / 8, 256, 0, stream>>>(a);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_head_out(const HeadOutArgs& a, int V, cudaStream_t stream) {
+    if (a.rows == 0) return 0;
+    MMF_DISPATCH_V(V, return launch_head_out_t<VV>(a, stream));
+    return 0;
+}
+
+}  // namespace mmf

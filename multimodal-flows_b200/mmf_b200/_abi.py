@@ -1,0 +1,234 @@
+"""ctypes binding of ``libmmf_b200.so`` (C ABI declared in ``include/mmf_b200.h``).
+
+This is the only place Python touches the native library.  PyTorch is used for
+device memory and streams; tensors cross the boundary as raw pointers.  There is
+no fallback: if the library is missing or a call fails, a ``RuntimeError`` is
+raised with ``mmf_last_error()``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_uint32, c_uint64, c_void_p
+from typing import Dict, Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmf_b200.so")
+
+ARCH = {"ParticleFormer": 0, "FusedParticleFormer": 1, "EPiC": 2}
+
+
+class MmfModelDesc(ctypes.Structure):
+    _fields_ = [(n, c_int32) for n in (
+        "arch", "vocab_size", "dim_continuous", "n_embd", "n_inner", "n_head", "n_layer", "n_layer_fused",
+        "n_embd_glob", "qk_layernorm", "max_num_particles")]
+
+
+class MmfWeightRef(ctypes.Structure):
+    _fields_ = [("name", c_char_p), ("data", c_void_p), ("ndim", c_int32), ("shape", c_int64 * 4)]
+
+
+class MmfStepOptions(ctypes.Structure):
+    _fields_ = [("temperature", c_float), ("beta", c_float), ("top_k", c_int32), ("top_p", c_float),
+                ("use_final_max_rates", c_int32), ("seed", c_uint64), ("first_global_jet", c_uint64)]
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+EXPORTS = [
+    "mmf_abi_version", "mmf_last_error", "mmf_model_create", "mmf_model_destroy", "mmf_encoder_forward",
+    "mmf_hybrid_step", "mmf_euler_step", "mmf_generate", "mmf_generate_host", "mmf_launch_count",
+    "mmf_dbg_gemm", "mmf_dbg_gemm_resln", "mmf_dbg_gemm_qkv", "mmf_dbg_attention",
+]
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python multimodal-flows_b200/build.py` "
+            "(there is no CPU or PyTorch fallback for the accelerated path)")
+    L = ctypes.CDLL(LIB_PATH)
+    L.mmf_abi_version.restype = c_int32
+    L.mmf_last_error.restype = c_char_p
+    L.mmf_model_create.argtypes = [POINTER(MmfModelDesc), POINTER(MmfWeightRef), c_int32, c_int32, POINTER(c_void_p)]
+    L.mmf_model_destroy.argtypes = [c_void_p]
+    L.mmf_model_destroy.restype = None
+    L.mmf_launch_count.argtypes = [c_void_p]
+    L.mmf_launch_count.restype = c_int64
+    L.mmf_encoder_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
+                                      c_void_p, c_void_p]
+    L.mmf_hybrid_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, POINTER(MmfStepOptions),
+                                  c_void_p, c_uint32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]
+    L.mmf_euler_step.argtypes = [c_void_p, c_void_p, c_float, c_int64, c_int32, c_void_p]
+    L.mmf_generate.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_float,
+                               POINTER(MmfStepOptions), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.mmf_generate_host.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32,
+                                    c_float, POINTER(MmfStepOptions), c_void_p, c_void_p]
+    L.mmf_dbg_gemm.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                               c_int32, c_void_p]
+    L.mmf_dbg_gemm_resln.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                     c_int32, c_void_p, c_void_p, c_int32, c_void_p]
+    L.mmf_dbg_gemm_qkv.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                   c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
+    L.mmf_dbg_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                    c_void_p, c_int32, c_void_p]
+    for name in EXPORTS:
+        if name not in ("mmf_last_error", "mmf_model_destroy", "mmf_launch_count", "mmf_abi_version"):
+            getattr(L, name).restype = c_int32
+    if L.mmf_abi_version() != 1:
+        raise RuntimeError("libmmf_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().mmf_last_error()
+        raise RuntimeError(f"libmmf_b200: {msg.decode() if msg else 'unknown error'} (status {rc})")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_handle(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def step_options(cfg, seed: int = 0, first_global_jet: int = 0) -> MmfStepOptions:
+    return MmfStepOptions(
+        temperature=float(cfg.temperature if cfg.temperature is not None else 1.0), beta=float(cfg.beta),
+        top_k=int(cfg.top_k or 0), top_p=float(cfg.top_p or 0.0),
+        use_final_max_rates=int(bool(getattr(cfg, "use_final_max_rates", False))),
+        seed=int(seed), first_global_jet=int(first_global_jet))
+
+
+class NativeModel:
+    """Owns one ``MmfModel*`` built from a reference-layout fp32 state_dict."""
+
+    def __init__(self, cfg, state_dict: Dict[str, torch.Tensor], device: torch.device):
+        L = lib()
+        if device.type != "cuda":
+            raise RuntimeError("the accelerated path runs on a CUDA device only (no CPU fallback)")
+        self.device = device
+        self.index = device.index if device.index is not None else torch.cuda.current_device()
+        desc = MmfModelDesc(
+            arch=ARCH[cfg.model], vocab_size=cfg.vocab_size, dim_continuous=cfg.dim_continuous, n_embd=cfg.n_embd,
+            n_inner=cfg.n_inner if cfg.n_inner is not None else 4 * cfg.n_embd, n_head=cfg.n_head,
+            n_layer=cfg.n_layer, n_layer_fused=getattr(cfg, "n_layer_fused", 0) or 0,
+            n_embd_glob=getattr(cfg, "n_embd_glob", 0) or 0, qk_layernorm=int(bool(cfg.qk_layernorm)),
+            max_num_particles=cfg.max_num_particles)
+        keep = []
+        refs = (MmfWeightRef * len(state_dict))()
+        for i, (name, t) in enumerate(state_dict.items()):
+            t = t.detach().to("cpu", torch.float32).contiguous()
+            keep.append(t)
+            shape = (c_int64 * 4)(*(list(t.shape) + [1] * (4 - t.dim())))
+            refs[i] = MmfWeightRef(name.encode(), t.data_ptr(), t.dim(), shape)
+        handle = c_void_p()
+        check(L.mmf_model_create(ctypes.byref(desc), refs, len(state_dict), self.index, ctypes.byref(handle)))
+        self.handle = handle
+        self.vocab_size = cfg.vocab_size
+        self.is_epic = cfg.model == "EPiC"
+
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            lib().mmf_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self) -> int:
+        return int(lib().mmf_launch_count(self.handle))
+
+    def forward(self, x, k, mask, t):
+        """(B,D,3) f32, (B,D[,1]) i64, (B,D[,1]) i64, (B,) f32 -> vt (B,D,3), logits (B,D,V) (None for EPiC)."""
+        B, D = x.shape[:2]
+        x = x.contiguous().float()
+        mask = mask.reshape(B, D).contiguous().long()
+        t = t.contiguous().float()
+        vt = torch.empty(B, D, 3, device=self.device, dtype=torch.float32)
+        logits = None
+        if not self.is_epic:
+            k = k.reshape(B, D).contiguous().long()
+            logits = torch.empty(B, D, self.vocab_size, device=self.device, dtype=torch.float32)
+        check(lib().mmf_encoder_forward(self.handle, ptr(x), ptr(k) if not self.is_epic else None, ptr(mask), ptr(t),
+                                        B, D, ptr(vt), ptr(logits), stream_handle(self.device)))
+        return vt, logits
+
+    def generate(self, x0, k0, mask, t_grid, dt, opts: Optional[MmfStepOptions], u=None, forced_k=None,
+                 want_rates=False):
+        B, D = x0.shape[:2]
+        N = int(t_grid.numel())
+        x0 = x0.contiguous().float()
+        mask = mask.reshape(B, D).contiguous().long()
+        tg = t_grid.detach().to("cpu", torch.float32).contiguous()
+        x_out = torch.empty_like(x0)
+        k_out = rates = None
+        if not self.is_epic:
+            k0 = k0.reshape(B, D).contiguous().long()
+            k_out = torch.empty_like(k0)
+            if want_rates:
+                rates = torch.empty(B, D, self.vocab_size, device=self.device, dtype=torch.float32)
+        if u is not None:
+            u = u.contiguous().float()
+            assert u.shape == (N, B, D, self.vocab_size)
+        if forced_k is not None:
+            forced_k = forced_k.reshape(N, B, D).contiguous().to(torch.uint8)
+        check(lib().mmf_generate(self.handle, ptr(x0), ptr(k0) if not self.is_epic else None, ptr(mask), B, D,
+                                 tg.data_ptr(), N, float(dt), ctypes.byref(opts) if opts is not None else None,
+                                 ptr(u), ptr(forced_k), ptr(x_out), ptr(k_out), ptr(rates),
+                                 stream_handle(self.device)))
+        return x_out, k_out, rates
+
+    def generate_host(self, x0, k0, mask, t_grid, dt, opts: Optional[MmfStepOptions]):
+        """Host tensors in, host tensors out (pinned or pageable); copies are inside the call."""
+        B, D = x0.shape[:2]
+        N = int(t_grid.numel())
+        assert x0.device.type == "cpu" and mask.device.type == "cpu"
+        x0 = x0.contiguous().float()
+        mask = mask.reshape(B, D).contiguous().long()
+        tg = t_grid.detach().to("cpu", torch.float32).contiguous()
+        x_out = torch.empty_like(x0).pin_memory()
+        k_out = None
+        if not self.is_epic:
+            k0 = k0.reshape(B, D).contiguous().long()
+            k_out = torch.empty_like(k0).pin_memory()
+        check(lib().mmf_generate_host(self.handle, ptr(x0), ptr(k0) if not self.is_epic else None, ptr(mask), B, D,
+                                      tg.data_ptr(), N, float(dt), ctypes.byref(opts) if opts is not None else None,
+                                      ptr(x_out), ptr(k_out)))
+        return x_out, k_out
+
+
+def hybrid_step(vt, logits, x, k, t, dt, opts: MmfStepOptions, u=None, step_index=0, want_rates=True):
+    """In-place fused step on device tensors: x (B,D,3) f32, k (B,D) i64 (both contiguous)."""
+    B, D = x.shape[:2]
+    V = logits.shape[-1]
+    assert x.is_cuda and x.is_contiguous() and k.is_contiguous() and k.dtype == torch.int64
+    rates = torch.empty(B, D, V, device=x.device, dtype=torch.float32) if want_rates else None
+    vt = vt.contiguous().float()
+    logits = logits.contiguous().float()
+    t = t.contiguous().float()
+    if u is not None:
+        u = u.contiguous().float()
+    idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    check(lib().mmf_hybrid_step(ptr(vt), ptr(logits), ptr(x), ptr(k), ptr(t), float(dt), ctypes.byref(opts), ptr(u),
+                                int(step_index), B, D, V, ptr(rates), idx, stream_handle(x.device)))
+    return rates
+
+
+def euler_step(vt, x, dt):
+    assert x.is_cuda and x.is_contiguous()
+    vt = vt.contiguous().float()
+    idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    check(lib().mmf_euler_step(ptr(vt), ptr(x), float(dt), x.numel(), idx, stream_handle(x.device)))

@@ -1,0 +1,79 @@
+"""Encoder forward and the N-step sampler through the C ABI vs the committed reference goldens and the oracle.
+
+Tolerances: the CUDA path computes with bf16 tensor-core operands and fp32
+accumulation against an fp32 reference, so on real particles
+    rel-L2 <= 2e-2  and  max-abs <= 3e-2 * max|ref|.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REL_L2 = 2e-2
+MAX_ABS = 3e-2
+
+
+def _setup(model, flavor, seed):
+    from mmf_b200 import _abi, synthetic
+    from mmf_b200.param_spec import make_config
+    cfg = make_config(model)
+    sd = synthetic.make_state_dict(cfg, flavor=flavor, seed=seed)
+    return cfg, sd, _abi.NativeModel(cfg, sd, torch.device("cuda:0")), synthetic
+
+
+def _errs(out, ref, real):
+    o, r = out[real].float(), ref[real].float()
+    return float((o - r).norm() / r.norm()), float((o - r).abs().max() / r.abs().max())
+
+
+@pytest.mark.parametrize("model", ["FusedParticleFormer", "ParticleFormer"])
+@pytest.mark.parametrize("flavor", ["default", "wide"])
+def test_encoder_forward_matches_reference_golden(model, flavor, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"encoder_{model}_{flavor}.npz"))
+    cfg, sd, nm, synthetic = _setup(model, flavor, int(g["weight_seed"]))
+    assert abs(synthetic.state_dict_checksum(sd) - float(g["weight_checksum"])) < 1e-6 * abs(float(g["weight_checksum"])) + 1e-9
+    dev = torch.device("cuda:0")
+    T = lambda n: torch.from_numpy(g[n]).to(dev)
+    vt, logits = nm.forward(T("continuous"), T("discrete"), T("mask"), T("time"))
+    torch.cuda.synchronize()
+    real = T("mask").bool().squeeze(-1)
+    e_vt = _errs(vt, T("vt"), real)
+    e_lg = _errs(logits, T("logits"), real)
+    assert torch.isfinite(vt).all() and torch.isfinite(logits).all()
+    assert (vt[~real] == 0).all() and (logits[~real] == 0).all()
+    assert e_vt[0] < REL_L2 and e_vt[1] < MAX_ABS, ("vt", e_vt)
+    assert e_lg[0] < REL_L2 and e_lg[1] < MAX_ABS, ("logits", e_lg)
+
+
+@pytest.mark.parametrize("model", ["FusedParticleFormer", "ParticleFormer"])
+def test_generate_teacher_forced_matches_reference_trajectory(model, golden_dir):
+    """Full N=100 loop with the reference's token trajectory forced after each step: x_N within tolerance."""
+    from mmf_b200 import _abi
+    from oracle import mmf_oracle as orc
+    g = np.load(os.path.join(golden_dir, f"traj_{model}.npz"))
+    cfg, sd, nm, synthetic = _setup(model, "wide", int(g["weight_seed"]))
+    cfg.num_timesteps = int(g["num_timesteps"])
+    dev = torch.device("cuda:0")
+    x0 = torch.from_numpy(g["x0"]).to(dev); k0 = torch.from_numpy(g["k0"]).long().to(dev); mask = torch.from_numpy(g["mask"]).to(dev)
+    B, D = x0.shape[:2]
+    u = synthetic.uniform_draws(cfg.num_timesteps, B, D, cfg.vocab_size, seed=int(g["u_seed"]))
+    assert abs(float(u.double().sum()) - float(g["u_checksum"])) < 1e-6
+    ts, dt = orc.time_grid(cfg)
+    opts = _abi.step_options(cfg)
+    forced = torch.from_numpy(g["traj_k"]).to(dev)
+    x, k, _ = nm.generate(x0, k0, mask, ts, float(dt), opts, u=u.to(dev), forced_k=forced)
+    torch.cuda.synchronize()
+    real = mask.bool().squeeze(-1)
+    xr = torch.from_numpy(g["x_out"]).to(dev)
+    rel, mx = _errs(x, xr, real)
+    assert rel < REL_L2, (rel, mx)
+    assert torch.equal(k[real], torch.from_numpy(g["k_out"]).long().to(dev).reshape(B, D)[real])
+    # free-running (no forcing): jump decisions stay close to the reference trajectory early on
+    x2, k2, _ = nm.generate(x0, k0, mask, ts, float(dt), opts, u=u.to(dev))
+    torch.cuda.synchronize()
+    agree = (k2[real] == torch.from_numpy(g["k_out"]).long().to(dev).reshape(B, D)[real]).float().mean().item()
+    assert agree > 0.6, agree
+    assert (x2[~real] == 0).all() and (k2[~real] == 0).all()

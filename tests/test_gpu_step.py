@@ -1,0 +1,105 @@
+"""The fused hybrid step kernel through the C ABI.
+
+Bit-exact targets: the C oracle (same deterministic arithmetic) on any input, and the reference's own
+outputs on the committed tie-free golden vectors.  Rates vs the reference: 1e-6 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_cuda(vt, logits, x, k, t, dt, u, T, top_k, top_p, beta=0.075, want_rates=True):
+    from mmf_b200 import _abi
+    dev = torch.device("cuda:0")
+    opts = _abi.MmfStepOptions(temperature=T, beta=beta, top_k=int(top_k or 0), top_p=float(top_p or 0.0),
+                               use_final_max_rates=0, seed=0, first_global_jet=0)
+    xd = x.clone().to(dev).contiguous()
+    kd = k.reshape(x.shape[0], x.shape[1]).long().clone().to(dev).contiguous()
+    rates = _abi.hybrid_step(vt.to(dev), logits.to(dev), xd, kd, t.to(dev), dt, opts, u=u.to(dev) if u is not None else None,
+                             want_rates=want_rates)
+    torch.cuda.synchronize()
+    return xd.cpu(), kd.cpu(), rates.cpu() if rates is not None else None
+
+
+def test_step_matches_reference_goldens(golden_dir):
+    g = np.load(os.path.join(golden_dir, "step_cases.npz"))
+    for ci in range(int(g["num_cases"])):
+        p = f"c{ci}_"
+        T = lambda n: torch.from_numpy(g[p + n])
+        top_k = int(g[p + "top_k"]) or None
+        top_p = float(g[p + "top_p"]) or None
+        x, k, rates = _run_cuda(T("vt"), T("logits"), T("x"), T("k"), T("t"), float(g[p + "dt"]), T("u"),
+                                float(g[p + "T"]), top_k, top_p)
+        k_ref = T("k_out").long().reshape(k.shape)
+        assert int((k != k_ref).sum()) == 0, f"case {ci}: {int((k != k_ref).sum())} token mismatches"
+        assert torch.equal(x, T("x_out")), f"case {ci}: continuous update not bit-exact"
+        rel = ((rates - T("rates")).abs() / T("rates").abs()).max().item()
+        assert rel < 1e-6, f"case {ci}: rates rel err {rel}"
+
+
+@pytest.mark.parametrize("T,top_k,top_p", [(1.0, None, None), (0.8, None, None), (1.2, 5, None), (1.0, None, 0.9), (0.9, 3, 0.7)])
+def test_step_bit_exact_vs_c_oracle(T, top_k, top_p):
+    from oracle import step_oracle
+    B, D, V = 64, 150, 9
+    g = torch.Generator().manual_seed(7)
+    vt = torch.randn(B, D, 3, generator=g) * 2
+    logits = torch.randn(B, D, V, generator=g) * 2.5
+    x = torch.randn(B, D, 3, generator=g)
+    k = torch.randint(0, V, (B, D, 1), generator=g)
+    t = torch.linspace(1e-5, 1 - 1e-5, B)
+    u = torch.rand(B, D, V, generator=g)          # NOT tie-filtered: same arithmetic must give same decisions
+    dt = 0.010100808
+    xo, ko, ro = step_oracle.hybrid_step(vt, logits, x, k, t, dt, u, temperature=T, top_k=top_k, top_p=top_p)
+    xc, kc, rc = _run_cuda(vt, logits, x, k, t, dt, u, T, top_k, top_p)
+    assert torch.equal(kc, ko.reshape(kc.shape)), int((kc != ko.reshape(kc.shape)).sum())
+    assert torch.equal(xc, xo)
+    assert torch.equal(rc, ro), (rc - ro).abs().max().item()
+
+
+def test_step_philox_statistics_and_invariance():
+    """In-kernel draws: jump statistics agree with supplied uniforms, and draws depend on the global slot only."""
+    from mmf_b200 import _abi
+    dev = torch.device("cuda:0")
+    B, D, V = 512, 150, 9
+    g = torch.Generator().manual_seed(11)
+    vt = torch.randn(B, D, 3, generator=g).to(dev)
+    logits = (torch.randn(B, D, V, generator=g) * 2).to(dev)
+    x0 = torch.randn(B, D, 3, generator=g).to(dev)
+    k0 = torch.randint(0, V, (B, D), generator=g).to(dev)
+    t = torch.full((B,), 0.5).to(dev)
+    opts = _abi.MmfStepOptions(1.0, 0.075, 0, 0.0, 0, 1234, 0)
+    ka = k0.clone(); xa = x0.clone()
+    _abi.hybrid_step(vt, logits, xa, ka, t, 0.0101, opts, u=None, step_index=3, want_rates=False)
+    # same jets presented as the second half of a larger launch starting at global jet 0
+    opts2 = _abi.MmfStepOptions(1.0, 0.075, 0, 0.0, 0, 1234, B // 2)
+    kb = k0[B // 2:].clone().contiguous(); xb = x0[B // 2:].clone().contiguous()
+    _abi.hybrid_step(vt[B // 2:].contiguous(), logits[B // 2:].contiguous(), xb, kb, t[B // 2:].contiguous(), 0.0101, opts2,
+                     u=None, step_index=3, want_rates=False)
+    torch.cuda.synchronize()
+    assert torch.equal(ka[B // 2:], kb), "draws must depend on (seed, global slot, step) only"
+    u = torch.rand(B, D, V, generator=g).to(dev)
+    kc = k0.clone(); xc = x0.clone()
+    _abi.hybrid_step(vt, logits, xc, kc, t, 0.0101, opts, u=u, want_rates=False)
+    fa = (ka != k0).float().mean().item(); fc = (kc != k0).float().mean().item()
+    assert abs(fa - fc) < 0.01, (fa, fc)
+    ha = torch.bincount(ka.flatten(), minlength=V).float() / ka.numel()
+    hc = torch.bincount(kc.flatten(), minlength=V).float() / kc.numel()
+    assert (ha - hc).abs().max().item() < 0.01
+
+
+def test_step_rejects_out_of_range_tokens_only_in_flag():
+    """Tokens outside [0,V) are clamped and flagged (the reference asserts, MJB.py:177-182); no crash."""
+    from mmf_b200 import _abi
+    dev = torch.device("cuda:0")
+    B, D, V = 2, 8, 9
+    vt = torch.zeros(B, D, 3, device=dev); logits = torch.zeros(B, D, V, device=dev)
+    x = torch.zeros(B, D, 3, device=dev); k = torch.full((B, D), 11, device=dev, dtype=torch.int64)
+    t = torch.full((B,), 0.3, device=dev)
+    opts = _abi.MmfStepOptions(1.0, 0.075, 0, 0.0, 0, 0, 0)
+    _abi.hybrid_step(vt, logits, x, k, t, 0.01, opts, u=torch.rand(B, D, V, device=dev), want_rates=False)
+    torch.cuda.synchronize()
+    assert int(k.max()) < V
