@@ -81,7 +81,7 @@ const char* mmf_last_error(void);
 
 /* Packs the checkpoint for the device (bf16 K-major matrices, folded tables) and allocates nothing else until
  * the first forward.  Fails on hyper-parameters outside the accelerated envelope (n_embd 256, n_inner 512,
- * n_head 4, D <= 160, V <= 16); there is no fallback path.  Synchronous. */
+ * n_head 4, D <= 152, V <= 16); there is no fallback path.  Synchronous. */
 int mmf_model_create(const MmfModelDesc* desc, const MmfWeightRef* weights, int32_t n_weights, int32_t device,
                      MmfModel** out);
 void mmf_model_destroy(MmfModel* model);

@@ -356,10 +356,17 @@ int ensure_workspace(MmfModel* m, int rows, int slots, int trows, int n_items) {
 // ---------------------------------------------------------------------------------------------
 // planning: packed row layout + attention work items from the (host) mask
 // ---------------------------------------------------------------------------------------------
+// TMA needs the innermost coordinate (the token index of V^T) on a 16-byte boundary, so the key window of an
+// item starts at the jet's first row rounded down to a multiple of 8; the few foreign rows in front are masked
+// by the per-row segment bounds like any other jet in the window.
 void plan_attention_items(const std::vector<int>& jet_start, const std::vector<int>& jet_n, std::vector<AttnItem>* items) {
     int g_start = -1, g_rows = 0;
+    auto window = [](int q_row0, int nq, int first_key, int end_key) {
+        const int k0 = first_key & ~7;
+        return AttnItem{q_row0, nq, k0, end_key - k0};
+    };
     auto flush = [&]() {
-        if (g_rows > 0) items->push_back(AttnItem{g_start, g_rows, g_start, g_rows});
+        if (g_rows > 0) items->push_back(window(g_start, g_rows, g_start, g_start + g_rows));
         g_start = -1; g_rows = 0;
     };
     for (size_t j = 0; j < jet_n.size(); ++j) {
@@ -367,8 +374,8 @@ void plan_attention_items(const std::vector<int>& jet_start, const std::vector<i
         if (n == 0) continue;
         if (n > kTileM) {
             flush();
-            items->push_back(AttnItem{s, kTileM, s, n});
-            items->push_back(AttnItem{s + kTileM, n - kTileM, s, n});
+            items->push_back(window(s, kTileM, s, s + n));
+            items->push_back(window(s + kTileM, n - kTileM, s, s + n));
             continue;
         }
         if (g_rows + n > kTileM) flush();
@@ -388,7 +395,7 @@ int build_plan(const int64_t* mask, int B, int D, Plan* p) {
         for (int d = 0; d < D; ++d)
             if (mask[static_cast<size_t>(b) * D + d] != 0) { p->row_slot.push_back(b * D + d); p->row_jet.push_back(b); ++rows; }
         jet_n[b] = rows - jet_start[b];
-        MMF_REQUIRE(jet_n[b] <= kMaxKeys, "a jet has more than 160 real particles");
+        MMF_REQUIRE(jet_n[b] <= kMaxKeys - 8, "a jet has more than 152 real particles");
         for (int i = 0; i < jet_n[b]; ++i) { p->seg_beg.push_back(jet_start[b]); p->seg_end.push_back(rows); }
     }
     p->rows = rows;
@@ -637,7 +644,7 @@ int mmf_model_create(const MmfModelDesc* desc, const MmfWeightRef* weights, int3
     MMF_REQUIRE(desc->n_embd == 256 && desc->n_inner == 512 && desc->n_head == 4 && desc->dim_continuous == 3,
                 "accelerated path is built for n_embd=256, n_inner=512, n_head=4, dim_continuous=3");
     MMF_REQUIRE(desc->vocab_size >= 2 && desc->vocab_size <= kMaxV, "vocab_size must be in [2,16]");
-    MMF_REQUIRE(desc->max_num_particles >= 1 && desc->max_num_particles <= kMaxKeys, "max_num_particles must be <= 160");
+    MMF_REQUIRE(desc->max_num_particles >= 1 && desc->max_num_particles <= kMaxKeys - 8, "max_num_particles must be <= 152");
     MMF_REQUIRE(desc->n_layer >= 1 && (desc->arch != MMF_ARCH_PARTICLEFORMER || desc->n_layer_fused >= 1), "need at least one block");
     int ndev = 0;
     MMF_CUDA_OK(cudaGetDeviceCount(&ndev));
@@ -819,7 +826,7 @@ int mmf_dbg_attention(const void* q, const void* k, const void* vT, const int32_
     std::vector<int> start(n_jets), n(n_jets), seg_beg, seg_end;
     int rows = 0;
     for (int j = 0; j < n_jets; ++j) {
-        MMF_REQUIRE(jet_n[j] >= 0 && jet_n[j] <= kMaxKeys, "dbg_attention: jet too long");
+        MMF_REQUIRE(jet_n[j] >= 0 && jet_n[j] <= kMaxKeys - 8, "dbg_attention: jet too long");
         start[j] = rows; n[j] = jet_n[j]; rows += jet_n[j];
         for (int i = 0; i < jet_n[j]; ++i) { seg_beg.push_back(start[j]); seg_end.push_back(start[j] + jet_n[j]); }
     }
