@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""Headline benchmark: generated jets / second at 100 steps (ParticleFormer, <=150 particles).
+
+Contract (see the task description): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line on rank 0.
+  step      = one pass of the hot path over one batch: the whole 100-timestep sampler on 256 synthetic
+              AOJ-shaped jets per GPU (BASELINE.json configs[1])
+  value     = whole-job jets/s with inputs resident in HBM when the timed region starts (CUDA events, max over ranks)
+  e2e       = same metric through the drop-in API with HOST buffers (H2D and D2H copies inside the timed region)
+  roofline  = the dominant kernel class, timed live with CUDA events, against MEASURED_PEAKS.json
+  cpu_baseline = the oracle port (torch fp32, reference algorithm) timed on this box's host cores, bounded sample
+`--impl reference` times that CPU port as the reference arm (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "multimodal-flows_b200"))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "generated jets/sec @100 steps (ParticleFormer, 150 particles)"
+FLOPS_PER_PARTICLE = {"ParticleFormer": 10_630_656, "FusedParticleFormer": 5_649_920}
+FLOPS_PER_JET_CONST = {"ParticleFormer": 65_536, "FusedParticleFormer": 0}
+ATTN_FLOPS_PER_N2 = {"ParticleFormer": 11_264, "FusedParticleFormer": 5_120}
+TC_CLASSES = ("gemm_embed", "gemm_qkv", "attention", "gemm_attn_proj_resln", "gemm_mlp_fc_gelu", "gemm_mlp_out_resln",
+              "gemm_head_fc_gelu")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="ParticleFormer", choices=["ParticleFormer", "FusedParticleFormer"])
+    ap.add_argument("--batch", type=int, default=256, help="jets per GPU per step")
+    ap.add_argument("--timesteps", type=int, default=100)
+    ap.add_argument("--temperature", type=float, default=1.0)
+    ap.add_argument("--dense", action="store_true", help="every jet has 150 particles (worst case)")
+    ap.add_argument("--cpu-sample-jets", type=int, default=32)
+    ap.add_argument("--cpu-sample-timesteps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-step-roofline", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6), ("sw_power_cap", 7)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median over the upper half: samples taken between launches idle down
+        load = sm[len(sm) // 2:] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_flops_per_timestep(model: str, n: torch.Tensor) -> float:
+    nf = n.double()
+    return float((FLOPS_PER_PARTICLE[model] * nf + FLOPS_PER_JET_CONST[model] + ATTN_FLOPS_PER_N2[model] * nf * nf).sum())
+
+
+def cpu_port_rate(args, cfg, sd, sample_jets, sample_timesteps, repeats=1):
+    """jets/s at `timesteps` steps of the CPU oracle port, extrapolated from `sample_timesteps` timesteps."""
+    from mmf_b200 import synthetic
+    from oracle import mmf_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    src = synthetic.source_state(sample_jets, cfg.max_num_particles, cfg.vocab_size, dense=args.dense)
+    u = synthetic.uniform_draws(sample_timesteps + 1, sample_jets, cfg.max_num_particles, cfg.vocab_size)
+    orc.simulate_dynamics(sd, cfg, src.continuous, src.discrete, src.mask, u=u, max_steps=1)          # warm-up
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.simulate_dynamics(sd, cfg, src.continuous, src.discrete, src.mask, u=u[1:], max_steps=sample_timesteps)
+        dt = (time.perf_counter() - t0) / sample_timesteps
+        best = dt if best is None else min(best, dt)
+    return sample_jets / (best * cfg.num_timesteps), best
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    from mmf_b200 import synthetic
+    from mmf_b200.param_spec import make_config
+    cfg = make_config(args.model, num_timesteps=args.timesteps, temperature=args.temperature)
+    sd = synthetic.make_state_dict(cfg, flavor="wide", seed=0)
+    cores = os.cpu_count() or 1
+    # one "step" = a bounded sample (sample_jets x sample_timesteps) of the same workload, extrapolated to the full step
+    for _ in range(max(args.warmup, 0)):
+        cpu_port_rate(args, cfg, sd, args.cpu_sample_jets, 1)
+    t0 = time.perf_counter()
+    rates = [cpu_port_rate(args, cfg, sd, args.cpu_sample_jets, args.cpu_sample_timesteps)[0] for _ in range(max(args.steps, 1))]
+    wall = time.perf_counter() - t0
+    value = sum(rates) / len(rates)
+    sample = (f"{args.cpu_sample_jets} jets x {args.cpu_sample_timesteps} of {args.timesteps} timesteps per step, oracle port "
+              f"(torch fp32, {cores} threads), extrapolated linearly to {args.timesteps} timesteps")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "jets/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * args.batch / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "wall_s": wall},
+        "cpu_baseline": {"value": value, "unit": "jets/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "jets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_name(args):
+    return (f"{args.model} sampler, batch {args.batch} jets/GPU x {args.timesteps} timesteps, D=150, V=9, "
+            + ("dense n=150" if args.dense else "AOJ-shaped n~clamp(round(55+18z),1,150)") + f", T={args.temperature}")
+
+
+def step_kernel_roofline(peaks, dev):
+    """Standalone fused step kernel on a batch larger than L2: 65536 jets x 150 slots."""
+    from mmf_b200 import _abi
+    B, D, V = 65536, 150, 9
+    g = torch.Generator(device=dev).manual_seed(3)
+    vt = torch.randn(B, D, 3, device=dev, generator=g)
+    logits = torch.randn(B, D, V, device=dev, generator=g)
+    x = torch.randn(B, D, 3, device=dev, generator=g)
+    k = torch.randint(0, V, (B, D), device=dev, generator=g)
+    t = torch.full((B,), 0.5, device=dev)
+    opts = _abi.MmfStepOptions(1.0, 0.075, 0, 0.0, 0, 1, 0)
+    out = {}
+    for mode, u in (("philox", None), ("supplied_u", torch.rand(B, D, V, device=dev, generator=g))):
+        for _ in range(3):
+            _abi.hybrid_step(vt, logits, x, k, t, 0.0101, opts, u=u, want_rates=False)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for i in range(reps):
+            _abi.hybrid_step(vt, logits, x, k, t, 0.0101, opts, u=u, step_index=i, want_rates=False)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        bytes_per_particle = 12 + 36 + 12 + 8 + 12 + 8 + (36 if u is not None else 0)
+        gbs = B * D * bytes_per_particle / (ms * 1e-3) / 1e9
+        out[mode] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                     "traffic": None, "bytes_per_particle": bytes_per_particle, "ms_per_launch": ms, "particles": B * D}
+        del u
+    return out
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the accelerated path has no CPU fallback")
+    from mmf_b200 import _abi, synthetic
+    from mmf_b200.mmf import MultiModalFlowBridge, time_grid
+    from mmf_b200.param_spec import make_config
+    from mmf_b200.tensorclass import DataCoupling, TensorMultiModal
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    cfg = make_config(args.model, num_timesteps=args.timesteps, temperature=args.temperature)
+    sd = synthetic.make_state_dict(cfg, flavor="wide", seed=0)
+    bridge = MultiModalFlowBridge(cfg)
+    bridge.model.load_state_dict(sd, strict=True)
+    bridge = bridge.to(dev)
+    nm = bridge.model.native()
+    ts, dt = time_grid(cfg)
+
+    # every rank generates its own shard of jets; draws are keyed on the global jet index (world-size invariant)
+    B = args.batch
+    src_host = synthetic.source_state(B, cfg.max_num_particles, cfg.vocab_size, dense=args.dense, seed=1234 + 10 * rank).pin_memory()
+    src_dev = src_host.to(dev)
+    n_per_jet = src_host.mask.squeeze(-1).sum(1)
+    flops_step = algorithmic_flops_per_timestep(args.model, n_per_jet) * args.timesteps
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def one_step(i):
+        opts = _abi.step_options(cfg, seed=7, first_global_jet=(i * world + rank) * B)
+        return nm.generate(src_dev.continuous, src_dev.discrete, src_dev.mask, ts, dt, opts)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = nm.launches
+    evs = []
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                                                            # L2 flush between timed iterations
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        one_step(args.warmup + i)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = nm.launches - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    tmax = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+    total_ms = float(tmax.item())
+    value = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end through the drop-in API with pinned HOST buffers (H2D + D2H inside the timed region) ----
+    def e2e_step():
+        batch = DataCoupling(source=src_host, target=TensorMultiModal())
+        out = bridge.predict_step(batch, 0)
+        return out
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = e2e_step()
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(e2e_t, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / float(e2e_t.item())
+    slots = B * cfg.max_num_particles
+    h2d = slots * (3 * 4 + 8) + 0                      # x0 f32 + k0 i64 (the mask stays on the host: it only feeds the planner)
+    d2h = slots * (3 * 4 + 8)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- gather once at the end, as the sharded sampler does (one NCCL collective, outside the loop) --------
+    if world > 1:
+        xg = [torch.empty_like(out.continuous, device=dev) for _ in range(world)]
+        torch.distributed.all_gather(xg, out.continuous.to(dev))
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+
+    # ---- live per-kernel-class profile of one more step (CUDA events on the launching stream) -------------
+    nm.profile(True)
+    nm.profile_read(reset=True)
+    one_step(10_000)
+    prof = nm.profile_read(reset=True)
+    nm.profile(False)
+    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    shares = {k: round(v["ms"] / tot_ms, 4) for k, v in prof.items() if v["launches"]}
+    tc = {k: v for k, v in prof.items() if k in TC_CLASSES and v["launches"]}
+    dom = max(tc, key=lambda k: tc[k]["ms"])
+    d = tc[dom]
+    ach = d["flops"] / d["launches"] / (d["ms"] / d["launches"] * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + " sustained",
+                "avg_launch_us": 1e3 * d["ms"] / d["launches"], "launches_per_step": d["launches"],
+                "share_of_step": shares[dom], "kernel_time_shares": shares}
+    path_tflops = flops_step / (total_ms / args.steps * 1e-3) / 1e12
+    roofline["whole_path"] = {"algorithmic_tflops": path_tflops, "frac_of_sustained_peak": path_tflops / peaks["bf16_tflops_sustained"]}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "jets/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(args), "jets_per_gpu_per_step": B, "timesteps": args.timesteps,
+                   "real_particles_per_step": int(n_per_jet.sum()), "weights": "synthetic wide init seed 0 (random, no checkpoint offline)",
+                   "l2": "256 MiB buffer written between timed iterations (L2 flush)", "rng": "in-kernel Philox4x32-10",
+                   "wall_s_timed_region": wall},
+        "e2e": {"value": e2e_value, "unit": "jets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "mmf_b200.mmf.MultiModalFlowBridge.predict_step (pinned host batch -> mmf_generate_host)"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+    }
+    if not args.no_step_roofline:
+        line["roofline_step_kernel"] = step_kernel_roofline(peaks, dev)
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        rate, s_per_ts = cpu_port_rate(args, cfg, sd, args.cpu_sample_jets, args.cpu_sample_timesteps)
+        line["cpu_baseline"] = {
+            "value": rate, "unit": "jets/s", "cores": cores, "kind": "port",
+            "sample": f"{args.cpu_sample_jets} jets x {args.cpu_sample_timesteps} timesteps of the same workload "
+                      f"({s_per_ts:.3f} s/timestep), extrapolated to {args.timesteps} timesteps; oracle/mmf_oracle.py torch fp32"}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

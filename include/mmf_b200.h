@@ -120,6 +120,14 @@ int mmf_generate_host(MmfModel* model, const float* x0, const int64_t* k0, const
 /* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
 int64_t mmf_launch_count(const MmfModel* model);
 
+/* Optional per-kernel-class profile: when enabled every launch is bracketed by CUDA events on its stream.
+ * mmf_profile_read synchronises the device and returns, per class, accumulated milliseconds, launch counts and
+ * the algorithmic FLOPs (real particles only) handed to those launches.  Arrays hold mmf_profile_num_classes(). */
+int mmf_profile_enable(MmfModel* model, int32_t on);
+int32_t mmf_profile_num_classes(void);
+const char* mmf_profile_class_name(int32_t cls);
+int mmf_profile_read(MmfModel* model, double* ms, int64_t* launches, double* flops, int32_t reset);
+
 /* ---- diagnostics: the building-block kernels, exposed so that tests can check each against torch ---- */
 /* out = epilogue(A[M,K] * W[N,K]^T + bias); device pointers; A, W bf16; M multiple of 128, K multiple of 64.
  * mode 0: bf16 out (act 0 none / 1 GELU); mode 1: fp32 out (N multiple of 128) */

@@ -137,6 +137,15 @@ struct Plan {
 
 using namespace mmf;
 
+// kernel classes for launch counting and the optional per-class CUDA-event profile (bench.py roofline)
+enum KernelClass { KC_PACK = 0, KC_EMBED_X, KC_GEMM_EMBED, KC_EMBED_FINISH, KC_GEMM_QKV, KC_ATTENTION, KC_GEMM_PROJ,
+                   KC_GEMM_FC, KC_GEMM_MLP_OUT, KC_ADD_LN, KC_GEMM_HEAD, KC_HEAD_OUT_STEP, KC_UNPACK, KC_COUNT };
+static const char* const kKernelClassNames[KC_COUNT] = {
+    "pack", "embed_x", "gemm_embed", "embed_finish", "gemm_qkv", "attention", "gemm_attn_proj_resln", "gemm_mlp_fc_gelu",
+    "gemm_mlp_out_resln", "add_layernorm", "gemm_head_fc_gelu", "head_out_step", "unpack"};
+
+struct ProfRecord { int cls; cudaEvent_t e0, e1; double flops; };
+
 struct MmfModel {
     MmfModelDesc desc{};
     int device = 0;
@@ -152,6 +161,11 @@ struct MmfModel {
     Workspace ws;
     int* d_err = nullptr;
     int64_t launches = 0;
+    bool prof_on = false;
+    std::vector<ProfRecord> prof_records;
+    double prof_ms[KC_COUNT] = {0}, prof_flops[KC_COUNT] = {0};
+    int64_t prof_count[KC_COUNT] = {0};
+    double plan_sum_n2 = 0;          // sum over jets of n^2 (attention FLOP accounting)
     std::vector<float> h_temb, h_temb2;
     ~MmfModel() {
         arena.release();
@@ -168,6 +182,27 @@ namespace {
     do {                         \
         int _rc = (expr);        \
         if (_rc != 0) return _rc; \
+    } while (0)
+
+// Counts a launch and, when profiling is on, brackets it with CUDA events on the launching stream.
+struct LaunchScope {
+    MmfModel* m; int cls; cudaStream_t s; double flops; cudaEvent_t e0 = nullptr;
+    LaunchScope(MmfModel* m_, int cls_, cudaStream_t s_, double flops_ = 0) : m(m_), cls(cls_), s(s_), flops(flops_) {
+        m->launches += 1;
+        if (m->prof_on) { cudaEventCreate(&e0); cudaEventRecord(e0, s); }
+    }
+    ~LaunchScope() {
+        if (e0) {
+            cudaEvent_t e1; cudaEventCreate(&e1); cudaEventRecord(e1, s);
+            m->prof_records.push_back(ProfRecord{cls, e0, e1, flops});
+        }
+    }
+};
+#define MMF_LAUNCH(cls, flops, expr)                    \
+    do {                                                \
+        LaunchScope _scope(m, cls, c.stream, flops);    \
+        int _rc = (expr);                               \
+        if (_rc != 0) return _rc;                       \
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
@@ -405,6 +440,8 @@ int build_plan(const int64_t* mask, int B, int D, Plan* p) {
 
 int upload_plan(MmfModel* m, const Plan& p, cudaStream_t s) {
     Workspace& w = m->ws;
+    m->plan_sum_n2 = 0;
+    for (size_t r = 0; r < p.seg_beg.size(); ++r) m->plan_sum_n2 += p.seg_end[r] - p.seg_beg[r];   // sum_rows n_jet = sum_jets n^2
     const size_t n = static_cast<size_t>(p.rows);
     if (n) {
         MMF_CUDA_OK(cudaMemcpyAsync(w.row_slot, p.row_slot.data(), n * 4, cudaMemcpyHostToDevice, s));
@@ -486,27 +523,27 @@ int run_block(MmfModel* m, const BlockDev& b, const ForwardCtx& c, const float* 
     // fused QKV projection, per-head LayerNorm on q and k, V stored transposed
     a.kblocks = C / kBK; a.a_col_group_stride = C; a.w_rows_per_group = 3 * C; a.bias = b.bqkv;
     a.sect_width = C; a.hs = b.hs; a.q_g = b.qg; a.q_b = b.qb; a.k_g = b.kg; a.k_b = b.kb; a.vt = w.vt; a.vt_ld = w.mcap;
-    MMF_TRY(launch_gemm(EPI_QKV, 128, w.tm_act, b.tm_wqkv, w.tm_q, w.tm_k, a, m_tiles, 3 * C / 128, G, c.stream));
+    const double rows = c.rows;
+    MMF_LAUNCH(KC_GEMM_QKV, 2.0 * rows * C * 3 * C * G, launch_gemm(EPI_QKV, 128, w.tm_act, b.tm_wqkv, w.tm_q, w.tm_k, a, m_tiles, 3 * C / 128, G, c.stream));
     // masked attention
     AttnArgs at{};
     at.items = w.items; at.seg_beg = w.seg_beg; at.seg_end = w.seg_end; at.out = w.attn; at.ld_out = 256; at.hs = b.hs;
     at.scale_log2e = 1.4426950408889634f / std::sqrt(static_cast<float>(b.hs));
-    MMF_TRY(launch_attention(w.tm_q, w.tm_k_ld, w.tm_vt, at, c.n_items, 4, c.stream));
+    MMF_LAUNCH(KC_ATTENTION, 4.0 * m->plan_sum_n2 * 256, launch_attention(w.tm_q, w.tm_k_ld, w.tm_vt, at, c.n_items, 4, c.stream));
     // attention projection + residual, LayerNorm ln2 -> MLP operand
     a = GemmArgs{};
     a.kblocks = C / kBK; a.a_col_group_stride = C; a.w_rows_per_group = C; a.bias = b.bproj;
     a.ln_g = b.ln2g; a.ln_b = b.ln2b;
-    MMF_TRY(launch_gemm(EPI_RESLN, C, w.tm_attn, b.tm_wproj, w.tm_act, w.tm_resid, a, m_tiles, 1, G, c.stream));
+    MMF_LAUNCH(KC_GEMM_PROJ, 2.0 * rows * C * C * G, launch_gemm(EPI_RESLN, C, w.tm_attn, b.tm_wproj, w.tm_act, w.tm_resid, a, m_tiles, 1, G, c.stream));
     // MLP up-projection + exact GELU
     a = GemmArgs{};
     a.kblocks = C / kBK; a.a_col_group_stride = C; a.w_rows_per_group = I; a.bias = b.bfc; a.act = 1; a.out_col_group_stride = I;
-    MMF_TRY(launch_gemm(EPI_STORE_BF16, 128, w.tm_act, b.tm_wfc, w.tm_hidden, w.tm_hidden, a, m_tiles, I / 128, G, c.stream));
+    MMF_LAUNCH(KC_GEMM_FC, 2.0 * rows * C * I * G, launch_gemm(EPI_STORE_BF16, 128, w.tm_act, b.tm_wfc, w.tm_hidden, w.tm_hidden, a, m_tiles, I / 128, G, c.stream));
     // MLP down-projection + residual + time embedding, LayerNorm of the next block -> its QKV operand
     a = GemmArgs{};
     a.kblocks = I / kBK; a.a_col_group_stride = I; a.w_rows_per_group = C; a.bias = b.bp2;
     a.temb = temb; a.temb_ld = 256; a.row_jet = c.row_jet; a.ln_g = next_g; a.ln_b = next_b;
-    MMF_TRY(launch_gemm(EPI_RESLN, C, w.tm_hidden, b.tm_wp2, w.tm_act, w.tm_resid, a, m_tiles, 1, G, c.stream));
-    m->launches += 5;
+    MMF_LAUNCH(KC_GEMM_MLP_OUT, 2.0 * rows * C * I * G, launch_gemm(EPI_RESLN, C, w.tm_hidden, b.tm_wp2, w.tm_act, w.tm_resid, a, m_tiles, 1, G, c.stream));
     return 0;
 }
 
@@ -517,17 +554,17 @@ int run_forward(MmfModel* m, const ForwardCtx& c) {
     const int rows_padded = m_tiles * kTileM;
     const bool pf = d.arch == MMF_ARCH_PARTICLEFORMER;
     // wxe: Linear(3,256) + GELU on CUDA cores, Linear(256,128) on tensor cores (raw output into resid[:, :128])
-    MMF_TRY(launch_embed_x(w.xs, c.rows, m->w0, m->b0, d.n_embd, 1, w.hidden, 1024, c.stream));
+    const double rows = c.rows;
+    MMF_LAUNCH(KC_EMBED_X, 2.0 * rows * 3 * d.n_embd, launch_embed_x(w.xs, c.rows, m->w0, m->b0, d.n_embd, 1, w.hidden, 1024, c.stream));
     GemmArgs a{};
     a.kblocks = d.n_embd / kBK; a.w_rows_per_group = 128; a.bias = m->wxe2_b;
-    MMF_TRY(launch_gemm(EPI_STORE_F32, 128, w.tm_hidden, m->tm_wxe2, w.tm_resid, w.tm_resid, a, m_tiles, 1, 1, c.stream));
+    MMF_LAUNCH(KC_GEMM_EMBED, 2.0 * rows * d.n_embd * 128, launch_gemm(EPI_STORE_F32, 128, w.tm_hidden, m->tm_wxe2, w.tm_resid, w.tm_resid, a, m_tiles, 1, 1, c.stream));
     const std::vector<BlockDev>& first = pf ? m->stream_blocks : m->main_blocks;
     EmbedFinishArgs ef{};
     ef.rows = rows_padded; ef.resid = w.resid; ef.skip = w.skip; ef.act = w.act; ef.ks = w.ks; ef.ytab = m->ytab;
     ef.ln1x_g = m->ln1x_g; ef.ln1x_b = m->ln1x_b; ef.temb = c.temb; ef.temb_ld = 256; ef.row_jet = c.row_jet;
     ef.next_ln_width = first[0].C; ef.next_g = first[0].ln1g; ef.next_b = first[0].ln1b;
-    MMF_TRY(launch_embed_finish(ef, c.stream));
-    m->launches += 3;
+    MMF_LAUNCH(KC_EMBED_FINISH, 0, launch_embed_finish(ef, c.stream));
 
     if (pf) {
         for (size_t i = 0; i < m->stream_blocks.size(); ++i) {
@@ -539,8 +576,7 @@ int run_forward(MmfModel* m, const ForwardCtx& c) {
         j.rows = rows_padded; j.resid = w.resid; j.skip = w.skip; j.act = w.act; j.ln1_width = 128; j.ln1_g = m->lnmid_g;
         j.ln1_b = m->lnmid_b; j.temb = c.temb2; j.temb_ld = 256; j.row_jet = c.row_jet; j.write_resid = 1;
         j.ln2_width = 256; j.ln2_g = m->main_blocks[0].ln1g; j.ln2_b = m->main_blocks[0].ln1b;
-        MMF_TRY(launch_add_ln(j, c.stream));
-        m->launches += 1;
+        MMF_LAUNCH(KC_ADD_LN, 0, launch_add_ln(j, c.stream));
     }
     const float* main_temb = pf ? c.temb2 : c.temb;
     for (size_t i = 0; i < m->main_blocks.size(); ++i) {
@@ -551,17 +587,16 @@ int run_forward(MmfModel* m, const ForwardCtx& c) {
     AddLnArgs f{};                           // ParticleFormer: ln3_x | ln3_y on (z + skip); Fused: ln2 over 256
     f.rows = rows_padded; f.resid = w.resid; f.skip = w.skip; f.act = w.act; f.ln1_width = pf ? 128 : 256;
     f.ln1_g = m->lnfin_g; f.ln1_b = m->lnfin_b;
-    MMF_TRY(launch_add_ln(f, c.stream));
+    MMF_LAUNCH(KC_ADD_LN, 0, launch_add_ln(f, c.stream));
     // heads: Linear(128,512)+GELU for both heads as one 2-group GEMM, then the tiny projections fused with the step
     a = GemmArgs{};
     a.kblocks = 128 / kBK; a.a_col_group_stride = 128; a.w_rows_per_group = d.n_inner; a.bias = m->bhead; a.act = 1;
     a.out_col_group_stride = d.n_inner;
-    MMF_TRY(launch_gemm(EPI_STORE_BF16, 128, w.tm_act, m->tm_whead, w.tm_hidden, w.tm_hidden, a, m_tiles, d.n_inner / 128, 2, c.stream));
+    MMF_LAUNCH(KC_GEMM_HEAD, 2.0 * rows * 128 * d.n_inner * 2, launch_gemm(EPI_STORE_BF16, 128, w.tm_act, m->tm_whead, w.tm_hidden, w.tm_hidden, a, m_tiles, d.n_inner / 128, 2, c.stream));
     HeadOutArgs ho = c.head;
     ho.rows = c.rows; ho.hidden = w.hidden; ho.ld_hidden = 1024; ho.wx = m->wx2; ho.bx = m->bx2; ho.wy = m->wy2; ho.by = m->by2;
     ho.row_slot = w.row_slot; ho.xs = w.xs; ho.ks = w.ks;
-    MMF_TRY(launch_head_out(ho, d.vocab_size, c.stream));
-    m->launches += 3;
+    MMF_LAUNCH(KC_HEAD_OUT_STEP, 2.0 * rows * d.n_inner * (3 + d.vocab_size), launch_head_out(ho, d.vocab_size, c.stream));
     return 0;
 }
 
@@ -597,8 +632,7 @@ int generate_device(MmfModel* m, const float* x0, const int64_t* k0, const int64
     MMF_TRY(upload_plan(m, plan, s));
     MMF_TRY(upload_time_tables(m, t_grid, N, s));
     Workspace& w = m->ws;
-    MMF_TRY(launch_pack(x0, reinterpret_cast<const long long*>(k0), w.row_slot, plan.rows, d.vocab_size, w.xs, w.ks, m->d_err, s));
-    m->launches += 1;
+    { LaunchScope sc(m, KC_PACK, s); MMF_TRY(launch_pack(x0, reinterpret_cast<const long long*>(k0), w.row_slot, plan.rows, d.vocab_size, w.xs, w.ks, m->d_err, s)); }
     const size_t slots = static_cast<size_t>(B) * D;
     for (int i = 0; i < N; ++i) {
         ForwardCtx c{};
@@ -621,8 +655,7 @@ int generate_device(MmfModel* m, const float* x0, const int64_t* k0, const int64
     // the packed state holds everything from here on, so the outputs may alias the inputs
     MMF_CUDA_OK(cudaMemsetAsync(x_out, 0, slots * 3 * 4, s));
     MMF_CUDA_OK(cudaMemsetAsync(k_out, 0, slots * 8, s));
-    MMF_TRY(launch_unpack(w.xs, w.ks, w.row_slot, plan.rows, x_out, reinterpret_cast<long long*>(k_out), s));
-    m->launches += 1;
+    { LaunchScope sc(m, KC_UNPACK, s); MMF_TRY(launch_unpack(w.xs, w.ks, w.row_slot, plan.rows, x_out, reinterpret_cast<long long*>(k_out), s)); }
     return 0;
 }
 
@@ -679,6 +712,33 @@ void mmf_model_destroy(MmfModel* model) {
 
 int64_t mmf_launch_count(const MmfModel* model) { return model ? model->launches : 0; }
 
+int mmf_profile_enable(MmfModel* m, int32_t on) {
+    MMF_REQUIRE(m != nullptr, "null model");
+    m->prof_on = on != 0;
+    return 0;
+}
+int32_t mmf_profile_num_classes(void) { return KC_COUNT; }
+const char* mmf_profile_class_name(int32_t i) { return (i >= 0 && i < KC_COUNT) ? kKernelClassNames[i] : ""; }
+int mmf_profile_read(MmfModel* m, double* ms, int64_t* launches, double* flops, int32_t reset) {
+    MMF_REQUIRE(m != nullptr, "null model");
+    MMF_CUDA_OK(cudaSetDevice(m->device));
+    MMF_CUDA_OK(cudaDeviceSynchronize());
+    for (ProfRecord& r : m->prof_records) {
+        float t = 0.f;
+        MMF_CUDA_OK(cudaEventElapsedTime(&t, r.e0, r.e1));
+        m->prof_ms[r.cls] += t; m->prof_count[r.cls] += 1; m->prof_flops[r.cls] += r.flops;
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    m->prof_records.clear();
+    for (int i = 0; i < KC_COUNT; ++i) {
+        if (ms) ms[i] = m->prof_ms[i];
+        if (launches) launches[i] = m->prof_count[i];
+        if (flops) flops[i] = m->prof_flops[i];
+        if (reset) { m->prof_ms[i] = 0; m->prof_count[i] = 0; m->prof_flops[i] = 0; }
+    }
+    return 0;
+}
+
 int mmf_encoder_forward(MmfModel* m, const float* x, const int64_t* k, const int64_t* mask, const float* t, int32_t B,
                         int32_t D, float* vt_out, float* logits_out, void* stream) {
     MMF_REQUIRE(m && x && mask && t && vt_out, "null argument");
@@ -697,7 +757,7 @@ int mmf_encoder_forward(MmfModel* m, const float* x, const int64_t* k, const int
     MMF_TRY(upload_plan(m, plan, s));
     MMF_TRY(upload_time_tables(m, ht.data(), B, s));
     Workspace& w = m->ws;
-    MMF_TRY(launch_pack(x, reinterpret_cast<const long long*>(k), w.row_slot, plan.rows, m->desc.vocab_size, w.xs, w.ks, m->d_err, s));
+    { LaunchScope sc(m, KC_PACK, s); MMF_TRY(launch_pack(x, reinterpret_cast<const long long*>(k), w.row_slot, plan.rows, m->desc.vocab_size, w.xs, w.ks, m->d_err, s)); }
     const size_t slots = static_cast<size_t>(B) * D;
     MMF_CUDA_OK(cudaMemsetAsync(vt_out, 0, slots * 3 * 4, s));
     MMF_CUDA_OK(cudaMemsetAsync(logits_out, 0, slots * m->desc.vocab_size * 4, s));
@@ -707,7 +767,6 @@ int mmf_encoder_forward(MmfModel* m, const float* x, const int64_t* k, const int
     c.head.vt_out = vt_out; c.head.logits_out = logits_out; c.head.do_step = 0;
     c.head.sl.sp.vocab = m->desc.vocab_size;
     MMF_TRY(run_forward(m, c));
-    m->launches += 1;
     return check_device_flags(m, s);
 }
 

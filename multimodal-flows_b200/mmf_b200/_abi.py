@@ -41,6 +41,7 @@ EXPORTS = [
     "mmf_abi_version", "mmf_last_error", "mmf_model_create", "mmf_model_destroy", "mmf_encoder_forward",
     "mmf_hybrid_step", "mmf_euler_step", "mmf_generate", "mmf_generate_host", "mmf_launch_count",
     "mmf_dbg_gemm", "mmf_dbg_gemm_resln", "mmf_dbg_gemm_qkv", "mmf_dbg_attention",
+    "mmf_profile_enable", "mmf_profile_num_classes", "mmf_profile_class_name", "mmf_profile_read",
 ]
 
 
@@ -77,8 +78,14 @@ def lib() -> ctypes.CDLL:
                                    c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
     L.mmf_dbg_attention.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                     c_void_p, c_int32, c_void_p]
+    L.mmf_profile_enable.argtypes = [c_void_p, c_int32]
+    L.mmf_profile_num_classes.restype = c_int32
+    L.mmf_profile_class_name.argtypes = [c_int32]
+    L.mmf_profile_class_name.restype = c_char_p
+    L.mmf_profile_read.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32]
     for name in EXPORTS:
-        if name not in ("mmf_last_error", "mmf_model_destroy", "mmf_launch_count", "mmf_abi_version"):
+        if name not in ("mmf_last_error", "mmf_model_destroy", "mmf_launch_count", "mmf_abi_version",
+                        "mmf_profile_num_classes", "mmf_profile_class_name"):
             getattr(L, name).restype = c_int32
     if L.mmf_abi_version() != 1:
         raise RuntimeError("libmmf_b200.so ABI version mismatch")
@@ -129,7 +136,9 @@ class NativeModel:
             t = t.detach().to("cpu", torch.float32).contiguous()
             keep.append(t)
             shape = (c_int64 * 4)(*(list(t.shape) + [1] * (4 - t.dim())))
-            refs[i] = MmfWeightRef(name.encode(), t.data_ptr(), t.dim(), shape)
+            bname = name.encode()
+            keep.append(bname)
+            refs[i] = MmfWeightRef(bname, t.data_ptr(), t.dim(), shape)
         handle = c_void_p()
         check(L.mmf_model_create(ctypes.byref(desc), refs, len(state_dict), self.index, ctypes.byref(handle)))
         self.handle = handle
@@ -150,6 +159,20 @@ class NativeModel:
     @property
     def launches(self) -> int:
         return int(lib().mmf_launch_count(self.handle))
+
+    def profile(self, on: bool) -> None:
+        check(lib().mmf_profile_enable(self.handle, int(on)))
+
+    def profile_read(self, reset: bool = True) -> Dict[str, Dict[str, float]]:
+        """Per kernel class: accumulated ms, launches and algorithmic FLOPs since the last reset."""
+        L = lib()
+        n = L.mmf_profile_num_classes()
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_int64 * n)()
+        fl = (ctypes.c_double * n)()
+        check(L.mmf_profile_read(self.handle, ms, cnt, fl, int(reset)))
+        return {L.mmf_profile_class_name(i).decode(): {"ms": ms[i], "launches": int(cnt[i]), "flops": fl[i]}
+                for i in range(n)}
 
     def forward(self, x, k, mask, t):
         """(B,D,3) f32, (B,D[,1]) i64, (B,D[,1]) i64, (B,) f32 -> vt (B,D,3), logits (B,D,V) (None for EPiC)."""
