@@ -87,7 +87,12 @@ class _GenerativeBase(_Base):
         obj.on_load_checkpoint(ckpt)
         return obj
 
-    def _next_jet_offset(self, B: int) -> int:
+    def _next_jet_offset(self, B: int, first_global_jet: Optional[int] = None) -> int:
+        """Global index of the first jet of this call.  Draws are keyed on it (world-size invariant output).
+        Callers that shard explicitly (``mmf_b200.distributed.generate_sharded``) pass it; under Lightning's
+        DistributedSampler-style round robin of equal batches it is derived from (call count, rank)."""
+        if first_global_jet is not None:
+            return int(first_global_jet)
         rank, world = 0, 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
@@ -101,13 +106,14 @@ class MultiModalFlowBridge(_GenerativeBase):
 
     @torch.no_grad()
     def simulate_dynamics(self, batch: DataCoupling, u: Optional[torch.Tensor] = None,
-                          forced_k: Optional[torch.Tensor] = None) -> DataCoupling:
+                          forced_k: Optional[torch.Tensor] = None,
+                          first_global_jet: Optional[int] = None) -> DataCoupling:
         cfg = self.config
         ts, dt = time_grid(cfg)
         src = batch.source
         dev = self.device
         B = len(src)
-        opts = _abi.step_options(cfg, seed=self.seed, first_global_jet=self._next_jet_offset(B))
+        opts = _abi.step_options(cfg, seed=self.seed, first_global_jet=self._next_jet_offset(B, first_global_jet))
         nm = self.model.native()
         x, k, _ = nm.generate(src.continuous.to(dev), src.discrete.to(dev), src.mask.to(dev), ts, dt, opts,
                               u=None if u is None else u.to(dev), forced_k=None if forced_k is None else forced_k.to(dev))

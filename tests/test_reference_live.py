@@ -1,0 +1,61 @@
+"""Oracle vs the LIVE reference (only where /root/reference is mounted: the build container).
+
+Fresh seeds, different from the committed fixtures, so the oracle is checked beyond the golden set.
+Auto-skipped on the GPU box, where the reference does not exist.
+"""
+import pytest
+import torch
+
+import ref_harness
+from mmf_b200 import synthetic
+from mmf_b200.param_spec import make_config
+from oracle import mmf_oracle as orc
+
+pytestmark = pytest.mark.skipif(not ref_harness.available(), reason="reference not mounted")
+
+
+def _state(ns, seed, D=150, V=9):
+    n = torch.tensor(ns)
+    mask = synthetic.prefix_masks(n, D)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(len(ns), D, 3, generator=g) * mask
+    k = torch.randint(1, V, (len(ns), D, 1), generator=g) * mask
+    return torch.rand(len(ns), generator=g), x, k, mask
+
+
+@pytest.mark.parametrize("model", ["ParticleFormer", "FusedParticleFormer", "EPiC"])
+def test_forward_matches_live_reference(model):
+    ref = ref_harness.modules()
+    cfg = make_config(model)
+    sd = synthetic.make_state_dict(cfg, "wide", seed=11)
+    t, x, k, mask = _state([3, 20, 150, 91], seed=21)
+    cls = ref.ConditionalFlowMatching if model == "EPiC" else ref.MultiModalFlowBridge
+    m = cls(cfg).eval()
+    m.model.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        out_ref = m.model(ref.TensorMultiModal(time=t, continuous=x, discrete=k, mask=mask))
+    out = orc.encoder_forward(sd, cfg, t, x, k, mask)
+    real = mask.bool().squeeze(-1)
+    if model == "EPiC":
+        assert torch.allclose(out[real], out_ref[real], rtol=1e-5, atol=1e-6)
+    else:
+        assert torch.allclose(out[0][real], out_ref[0][real], rtol=1e-5, atol=1e-6)
+        assert torch.allclose(out[1][real], out_ref[1][real], rtol=1e-5, atol=1e-6)
+
+
+def test_sampler_matches_live_reference_with_supplied_uniforms():
+    ref = ref_harness.modules()
+    cfg = make_config("FusedParticleFormer", num_timesteps=12, temperature=0.8, top_k=5)
+    sd = synthetic.make_state_dict(cfg, "wide", seed=12)
+    _, x, k, mask = _state([9, 60], seed=22)
+    u = synthetic.uniform_draws(cfg.num_timesteps, 2, 150, cfg.vocab_size, seed=23)
+    m = ref.MultiModalFlowBridge(cfg).eval()
+    m.model.load_state_dict(sd, strict=True)
+    batch = ref.DataCoupling(source=ref.TensorMultiModal(continuous=x.clone(), discrete=k.clone(), mask=mask),
+                             target=ref.TensorMultiModal())
+    with ref_harness.supplied_uniforms(list(u)):
+        tgt = m.simulate_dynamics(batch).target
+    xo, ko, _ = orc.simulate_dynamics(sd, cfg, x, k, mask, u=u)
+    real = mask.bool().squeeze(-1)
+    assert torch.allclose(xo[real], tgt.continuous[real], rtol=1e-4, atol=1e-5)
+    assert (ko[real] == tgt.discrete[real]).float().mean() > 0.995
