@@ -1,0 +1,482 @@
+// EPiC sampler as ONE persistent kernel: a CTA owns a 128-row tile of whole jets for all N timesteps.
+//
+//   local features  loc  [128 x 256] fp32 live in TMEM columns [0,256)   (the residual stream of EPiCLayer)
+//   scratch accum        [128 x 256] fp32        TMEM columns [256,512)
+//   GEMM A operand       [128 x 256] bf16 in shared memory (4 SWIZZLE_128B chunks), rewritten by each epilogue
+//   weights              bf16 16 KB tiles streamed from L2 in consumption order by 1-D bulk copies (4-stage ring)
+//   per-jet global path  masked mean/sum pooling + the two tiny global linears on CUDA cores, overlapped with the
+//                        fc_loc1 tensor-core GEMM of the same layer (it does not depend on them)
+//
+// warps 0..7: epilogue / SIMT (thread = row r, column half hf); warp 8 lane 0: weight producer; warp 9 lane 0:
+// tcgen05.mma issuer.  Reference: networks/EPiC.py:38-62 (forward), :110-124 (projection), :152-173 (layer),
+// :65-72 (pooling); Euler step model/solvers.py:139-143.
+#include "mmf_epic.h"
+#include "mmf_ptx.cuh"
+#include "mmf_tile.cuh"
+
+namespace mmf {
+
+namespace {
+
+constexpr int kEpi = 256;                 // epilogue threads
+constexpr int kThreads = 320;
+constexpr int kStages = 4;
+constexpr int kTile = 128 * 128;          // bytes of one 128 x 64 bf16 tile
+constexpr int kPoolLd = 528;              // pooled vector: mean(256) | 0.01 sum(256) | glob(16)
+
+struct EpicBars {
+    uint64_t full[kStages], empty[kStages], acc_full, a_ready, xchg;
+    uint32_t tmem_base;
+};
+
+// float offsets of the fp32 scratch that follows the operand buffers
+constexpr int oXs = 0, oPool = oXs + 384, oPart = oPool + kEpicMaxJets * kPoolLd, oHid = oPart + 2 * kEpicMaxJets * 256,
+              oJb = oHid + kEpicMaxJets * 256, oGlob = oJb + kEpicMaxJets * 256, oGpre = oGlob + 128, oGskip = oGpre + 128,
+              oHeadp = oGskip + 128, oXchg = oHeadp + 512, oMeta = oXchg + 512, oRowJet = oMeta + 32, oEnd = oRowJet + 32;
+constexpr int kSmemBytes = 1024 /*align*/ + 1024 /*bars*/ + 4 * kTile + kStages * kTile + oEnd * 4;
+
+__device__ __forceinline__ void epi_bar() { named_bar_sync(1, kEpi); }
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// hidden layer of a global MLP for all jets of the tile:
+//   part[kh][j][o] = sum_{k in half kh} Wt[k][o] * pool[j][k]      (Wt bf16 [K][256], transposed on the host)
+// thread: outputs (op, op+1), k-range half kh.  Followed by combine + bias + activation into hid[j][o].
+template <bool GELU>
+__device__ __forceinline__ void global_hidden(const bf16* __restrict__ Wt, int K, const float* s_pool, float* s_part,
+                                              float* s_hid, const float* bias0, int bias_jet_stride,
+                                              const int* jet_tb, int njets, int tid) {
+    const int op = (tid & 127) * 2, kh = tid >> 7;
+    const int kn = K >> 1, k0 = kh * kn;
+    float acc0[kEpicMaxJets], acc1[kEpicMaxJets];
+#pragma unroll
+    for (int j = 0; j < kEpicMaxJets; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(Wt + static_cast<size_t>(k0) * 256 + op);
+#pragma unroll 2
+    for (int k = 0; k < kn; k += 4) {
+        const uint32_t w0 = __ldg(wp + (k + 0) * 128), w1 = __ldg(wp + (k + 1) * 128), w2 = __ldg(wp + (k + 2) * 128),
+                       w3 = __ldg(wp + (k + 3) * 128);
+#pragma unroll
+        for (int j = 0; j < kEpicMaxJets; ++j) {
+            if (j < njets) {
+                const float4 p = *reinterpret_cast<const float4*>(s_pool + j * kPoolLd + k0 + k);
+                acc0[j] = fmaf(bf16_lo(w0), p.x, fmaf(bf16_lo(w1), p.y, fmaf(bf16_lo(w2), p.z, fmaf(bf16_lo(w3), p.w, acc0[j]))));
+                acc1[j] = fmaf(bf16_hi(w0), p.x, fmaf(bf16_hi(w1), p.y, fmaf(bf16_hi(w2), p.z, fmaf(bf16_hi(w3), p.w, acc1[j]))));
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kEpicMaxJets; ++j) {
+        if (j < njets) {
+            *reinterpret_cast<float2*>(s_part + (kh * kEpicMaxJets + j) * 256 + op) = make_float2(acc0[j], acc1[j]);
+        }
+    }
+    epi_bar();
+    for (int j = 0; j < njets; ++j) {
+        const float b = __ldg(bias0 + static_cast<size_t>(bias_jet_stride ? jet_tb[j] : 0) * bias_jet_stride + tid);
+        const float v = s_part[j * 256 + tid] + s_part[(kEpicMaxJets + j) * 256 + tid] + b;
+        s_hid[j * 256 + tid] = GELU ? gelu_erf(v) : leaky_relu(v);
+    }
+    epi_bar();
+}
+
+// 16-wide output of a global MLP: thread (j, q) = (tid / 16, tid % 16); returns W2[q] . hid[j] + b2[q]
+__device__ __forceinline__ float global_out16(const float* __restrict__ W2, const float* __restrict__ b2,
+                                              const float* s_hid, int j, int q) {
+    const float4* w = reinterpret_cast<const float4*>(W2 + q * 256);
+    const float4* h = reinterpret_cast<const float4*>(s_hid + j * 256);
+    float acc = __ldg(b2 + q);
+#pragma unroll 8
+    for (int o = 0; o < 64; ++o) {
+        const float4 a = __ldg(w + o), b = h[o];
+        acc = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    EpicBars* bars = reinterpret_cast<EpicBars*>(smem);
+    uint8_t* Abuf = smem + 1024;
+    uint8_t* ring = Abuf + 4 * kTile;
+    float* fb = reinterpret_cast<float*>(ring + kStages * kTile);
+    float *s_xs = fb + oXs, *s_pool = fb + oPool, *s_part = fb + oPart, *s_hid = fb + oHid, *s_jb = fb + oJb,
+          *s_glob = fb + oGlob, *s_gpre = fb + oGpre, *s_gskip = fb + oGskip, *s_headp = fb + oHeadp, *s_xchg = fb + oXchg;
+    EpicTileMeta* s_meta = reinterpret_cast<EpicTileMeta*>(fb + oMeta);
+    uint8_t* s_rowjet = reinterpret_cast<uint8_t*>(fb + oRowJet);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = a.tile0 + blockIdx.x;
+
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+        mbar_init(&bars->acc_full, 1);
+        mbar_init(&bars->a_ready, kEpi);
+        mbar_init(&bars->xchg, kEpi);
+        fence_mbar_init();
+    }
+    if (warp == 9) {
+        tmem_alloc(&bars->tmem_base, 512);
+        tmem_relinquish();
+    }
+    if (tid < static_cast<int>(sizeof(EpicTileMeta) / 4))
+        reinterpret_cast<int*>(s_meta)[tid] = reinterpret_cast<const int*>(a.meta + tile)[tid];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    cluster_sync_all();                     // the peer's barriers are initialised before any remote arrive
+    const uint32_t tmem_base = bars->tmem_base;
+    const int nrows = s_meta->nrows, njets = s_meta->njets;
+
+    if (warp == 8) {
+        // ------------------------------------------------ weight producer -----------------------------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int step = 0; step < a.nsteps; ++step) {
+                for (int t = 0; t < kEpicTilesPerStep; ++t, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t round = it / kStages;
+                    if (round > 0) mbar_wait(&bars->empty[s], (round - 1) & 1);
+                    mbar_expect_tx(&bars->full[s], kTile);
+                    bulk_load_1d(ring + s * kTile, a.p.wstream + static_cast<size_t>(t) * kTile, kTile, &bars->full[s]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // ------------------------------------------------ MMA issuer ----------------------------------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+            uint32_t it = 0, pa = 0;
+            auto gemm = [&](uint32_t dcol, uint32_t accumulate) {     // D[:, dcol..dcol+256) (+)= A[128x256] W^T
+                mbar_wait(&bars->a_ready, pa);
+                pa ^= 1;
+                tc_fence_after();
+                for (int kb = 0; kb < 4; ++kb) {
+                    for (int nh = 0; nh < 2; ++nh, ++it) {
+                        const int s = it % kStages;
+                        mbar_wait(&bars->full[s], (it / kStages) & 1);
+                        tc_fence_after();
+                        const uint64_t da = umma_desc_sw128(smem_u32(Abuf + kb * kTile));
+                        const uint64_t db = umma_desc_sw128(smem_u32(ring + s * kTile));
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_bf16(tmem_base + dcol + nh * 128, da + 2 * ks, db + 2 * ks, idesc,
+                                      (accumulate | kb | ks) != 0 ? 1u : 0u);
+                        umma_commit(&bars->empty[s]);
+                    }
+                }
+                umma_commit(&bars->acc_full);
+            };
+            for (int step = 0; step < a.nsteps; ++step) {
+                gemm(256, 0);                                   // proj.mlp_local.2
+                for (int l = 0; l < kEpicLayers; ++l) {
+                    gemm(256, 0);                               // fc_loc1 (local part)
+                    gemm(0, 1);                                 // fc_loc2, accumulated onto the residual in TMEM
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------ epilogue / SIMT warps ------------------------------
+        const int r = (warp & 3) * 32 + lane, hf = warp >> 2;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        const uint32_t peer = cluster_ctarank() ^ 1u;
+        uint32_t pf = 0, px = 0;
+        if (tid < 128) {
+            int j = 0;
+            for (int q = 0; q < njets; ++q) j = (tid >= s_meta->jet_begin[q]) ? q : j;
+            s_rowjet[tid] = static_cast<uint8_t>(j);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                s_xs[tid * 3 + c] = tid < nrows ? a.xs0[(static_cast<size_t>(tile) * 128 + tid) * 3 + c] : 0.f;
+        }
+        epi_bar();
+        const int jrow = s_rowjet[r];
+        float* skip_row = a.loc_skip + (static_cast<size_t>(tile) * 128 + r) * 256;
+
+        // masked sum pooling of the bf16 local features in Abuf; thread = column
+        auto pool = [&](bool with_glob) {
+            const int col = tid;
+            const uint8_t* ch = Abuf + (col >> 6) * kTile + (col & 7) * 2;
+            const uint32_t u = (col & 63) >> 3;
+            for (int j = 0; j < njets; ++j) {
+                float s = 0.f;
+                const int r1 = s_meta->jet_begin[j + 1];
+                for (int rr = s_meta->jet_begin[j]; rr < r1; ++rr)
+                    s += __bfloat162float(*reinterpret_cast<const bf16*>(ch + sw128_offset(rr, u)));
+                if (s_meta->pair) {                              // the other half of the jet lives in the peer CTA
+                    dsmem_st_f32(dsmem_addr(s_xchg + px * 256 + col, peer), s);
+                    mbar_arrive_remote(dsmem_addr(&bars->xchg, peer));
+                    mbar_wait_cluster(&bars->xchg, px);
+                    s += s_xchg[px * 256 + col];
+                    px ^= 1;
+                }
+                s_pool[j * kPoolLd + col] = s / static_cast<float>(s_meta->jet_ntot[j]);
+                s_pool[j * kPoolLd + 256 + col] = s * 0.01f;
+            }
+            if (with_glob && tid < njets * 16) s_pool[(tid >> 4) * kPoolLd + 512 + (tid & 15)] = s_glob[tid];
+            epi_bar();
+        };
+
+        for (int step = 0; step < a.nsteps; ++step) {
+            const int tb_row = a.per_jet_time ? s_meta->jet_tb[jrow] : step;
+            const float* tbr = a.tbias + static_cast<size_t>(tb_row) * kEpicTbLd;
+
+            // ---- proj.mlp_local.0 with wxe folded in: h1 = GELU(A3 x + c1(t)), K = 3 on CUDA cores
+            {
+                const float x0 = s_xs[r * 3], x1 = s_xs[r * 3 + 1], x2 = s_xs[r * 3 + 2];
+#pragma unroll 1
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int chunk = hf * 2 + cc;
+                    float v[64];
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) {
+                        const int col = chunk * 64 + i;
+                        const float pre = fmaf(__ldg(a.p.a3 + col * 3 + 2), x2, fmaf(__ldg(a.p.a3 + col * 3 + 1), x1,
+                                          fmaf(__ldg(a.p.a3 + col * 3), x0, __ldg(tbr + col))));
+                        v[i] = gelu_erf(pre);
+                    }
+                    stage_row_bf16(Abuf + chunk * kTile, r, v);
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(&bars->a_ready);
+            }
+            // ---- proj.mlp_local.2: loc = GELU(acc + b); keep fp32 in TMEM, skip copy in global, bf16 operand in Abuf
+            mbar_wait(&bars->acc_full, pf);
+            pf ^= 1;
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int col0 = hf * 128 + c * 32;
+                float v[32];
+                tmem_ld32(taddr + 256 + col0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i] + __ldg(a.p.b_loc2p + col0 + i));
+                tmem_st32(taddr + col0, v);
+                float4* sk = reinterpret_cast<float4*>(skip_row + col0);
+                uint8_t* ch = Abuf + (col0 >> 6) * kTile;
+                const uint32_t u0 = (col0 & 63) >> 3;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sk[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    st_shared_v4(ch + sw128_offset(r, u0 + u), pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                                 pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+            }
+            tmem_st_wait();
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(&bars->a_ready);                     // layer 0's fc_loc1 may start: it only needs loc
+            epi_bar();
+            // ---- proj.mlp_global: pooled(512) ++ temb -> 256 (GELU) -> 16 (GELU)
+            pool(false);
+            global_hidden<true>(a.p.wg0t, 512, s_pool, s_part, s_hid, a.tbias + 256 + (a.per_jet_time ? 0 : static_cast<size_t>(step) * kEpicTbLd),
+                                a.per_jet_time ? kEpicTbLd : 0, s_meta->jet_tb, njets, tid);
+            if (tid < njets * 16) {
+                const float g = gelu_erf(global_out16(a.p.wg2p, a.p.bg2p, s_hid, tid >> 4, tid & 15));
+                s_glob[tid] = g;
+                s_gskip[tid] = g;
+            }
+            epi_bar();
+
+            float hp0 = 0.f, hp1 = 0.f, hp2 = 0.f;
+#pragma unroll 1
+            for (int l = 0; l < kEpicLayers; ++l) {
+                // the fc_loc1 GEMM of this layer is already running on the tensor core; meanwhile the global path:
+                if (l > 0) pool(true);
+                else {
+                    if (tid < njets * 16) s_pool[(tid >> 4) * kPoolLd + 512 + (tid & 15)] = s_glob[tid];
+                    epi_bar();
+                }
+                global_hidden<false>(a.p.wg1t[l], 528, s_pool, s_part, s_hid, a.p.bg1[l], 0, s_meta->jet_tb, njets, tid);
+                if (tid < njets * 16) s_gpre[tid] = s_glob[tid] + global_out16(a.p.wg2[l], a.p.bg2[l], s_hid, tid >> 4, tid & 15);
+                epi_bar();
+                {   // per-jet bias of fc_loc1: time part (table) + global part
+                    const float4* wg = reinterpret_cast<const float4*>(a.p.wl1g[l] + tid * 16);
+                    const float4 w0 = __ldg(wg), w1 = __ldg(wg + 1), w2 = __ldg(wg + 2), w3 = __ldg(wg + 3);
+                    for (int j = 0; j < njets; ++j) {
+                        const int tbj = a.per_jet_time ? s_meta->jet_tb[j] : step;
+                        const float* g = s_gpre + j * 16;
+                        float acc = __ldg(a.tbias + static_cast<size_t>(tbj) * kEpicTbLd + 512 + l * 256 + tid);
+                        acc = fmaf(w0.x, g[0], fmaf(w0.y, g[1], fmaf(w0.z, g[2], fmaf(w0.w, g[3], acc))));
+                        acc = fmaf(w1.x, g[4], fmaf(w1.y, g[5], fmaf(w1.z, g[6], fmaf(w1.w, g[7], acc))));
+                        acc = fmaf(w2.x, g[8], fmaf(w2.y, g[9], fmaf(w2.z, g[10], fmaf(w2.w, g[11], acc))));
+                        acc = fmaf(w3.x, g[12], fmaf(w3.y, g[13], fmaf(w3.z, g[14], fmaf(w3.w, g[15], acc))));
+                        s_jb[j * 256 + tid] = acc;
+                    }
+                }
+                epi_bar();
+                // ---- fc_loc1 epilogue: hidden = leaky_relu(acc + jet bias) -> bf16 operand (overwrites loc in Abuf)
+                mbar_wait(&bars->acc_full, pf);
+                pf ^= 1;
+                tc_fence_after();
+                {
+                    const float* jb = s_jb + jrow * 256;
+#pragma unroll 1
+                    for (int cc = 0; cc < 2; ++cc) {
+                        const int chunk = hf * 2 + cc;
+                        float v[64];
+                        tmem_ld32(taddr + 256 + chunk * 64, v);
+                        tmem_ld32(taddr + 256 + chunk * 64 + 32, v + 32);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 64; i += 4) {
+                            const float4 b = *reinterpret_cast<const float4*>(jb + chunk * 64 + i);
+                            v[i] = leaky_relu(v[i] + b.x); v[i + 1] = leaky_relu(v[i + 1] + b.y);
+                            v[i + 2] = leaky_relu(v[i + 2] + b.z); v[i + 3] = leaky_relu(v[i + 3] + b.w);
+                        }
+                        stage_row_bf16(Abuf + chunk * kTile, r, v);
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(&bars->a_ready);                 // fc_loc2 accumulates onto loc in TMEM
+                // ---- fc_loc2 epilogue: loc = leaky_relu(loc_pre + b) + loc_skip
+                mbar_wait(&bars->acc_full, pf);
+                pf ^= 1;
+                tc_fence_after();
+                const bool last = l + 1 == kEpicLayers;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const int col0 = hf * 128 + c * 32;
+                    float v[32];
+                    tmem_ld32(taddr + col0, v);
+                    const float4* sk = reinterpret_cast<const float4*>(skip_row + col0);
+                    float4 s4[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) s4[u] = sk[u];
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(a.p.bl2[l] + col0) + u);
+                        v[4 * u] = leaky_relu(v[4 * u] + b.x) + s4[u].x;
+                        v[4 * u + 1] = leaky_relu(v[4 * u + 1] + b.y) + s4[u].y;
+                        v[4 * u + 2] = leaky_relu(v[4 * u + 2] + b.z) + s4[u].z;
+                        v[4 * u + 3] = leaky_relu(v[4 * u + 3] + b.w) + s4[u].w;
+                    }
+                    if (!last) {
+                        tmem_st32(taddr + col0, v);
+                        uint8_t* ch = Abuf + (col0 >> 6) * kTile;
+                        const uint32_t u0 = (col0 & 63) >> 3;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            st_shared_v4(ch + sw128_offset(r, u0 + u), pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                                         pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+                    } else {                                  // head: Linear(528,3), local part
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            hp0 = fmaf(__ldg(a.p.wh_loc + col0 + i), v[i], hp0);
+                            hp1 = fmaf(__ldg(a.p.wh_loc + 256 + col0 + i), v[i], hp1);
+                            hp2 = fmaf(__ldg(a.p.wh_loc + 512 + col0 + i), v[i], hp2);
+                        }
+                    }
+                }
+                if (tid < njets * 16) s_glob[tid] = leaky_relu(s_gpre[tid]) + s_gskip[tid];
+                if (!last) {
+                    tmem_st_wait();
+                    fence_proxy_async();
+                    tc_fence_before();
+                    mbar_arrive(&bars->a_ready);             // next layer's fc_loc1
+                }
+                epi_bar();
+            }
+            // ---- head and Euler update
+            if (hf == 1) { s_headp[r * 4] = hp0; s_headp[r * 4 + 1] = hp1; s_headp[r * 4 + 2] = hp2; }
+            epi_bar();
+            if (hf == 0 && r < nrows) {
+                const float* g = s_glob + jrow * 16;
+                float vt[3] = {hp0 + s_headp[r * 4], hp1 + s_headp[r * 4 + 1], hp2 + s_headp[r * 4 + 2]};
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    float acc = vt[d] + __ldg(tbr + 1792 + d);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) acc = fmaf(__ldg(a.p.wh_glob + d * 16 + q), g[q], acc);
+                    vt[d] = acc;
+                }
+                if (a.vt_out) {
+                    const long long slot = a.row_slot[static_cast<size_t>(tile) * 128 + r];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) a.vt_out[slot * 3 + d] = vt[d];
+                } else {
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) s_xs[r * 3 + d] = euler_update(s_xs[r * 3 + d], vt[d], a.dt);
+                }
+            }
+            epi_bar();
+        }
+        if (a.x_out && tid < nrows) {
+            const long long slot = a.row_slot[static_cast<size_t>(tile) * 128 + tid];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) a.x_out[slot * 3 + d] = s_xs[tid * 3 + d];
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                     // a pair CTA must not exit while its peer can still reach its smem
+    if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
+// tbias[tb][m*256 + o] = cst[m][o] + sum_k wt[m][k][o] * temb[tb][k]   (7 folded linears) ; head: 3 outputs
+__global__ void __launch_bounds__(256) epic_time_bias_kernel(const EpicTimeFold f, const float* __restrict__ temb,
+                                                             float* __restrict__ tbias) {
+    __shared__ float s_t[256];
+    const int tb = blockIdx.x, o = threadIdx.x;
+    s_t[o] = temb[static_cast<size_t>(tb) * 256 + o];
+    __syncthreads();
+    float* out = tbias + static_cast<size_t>(tb) * kEpicTbLd;
+    for (int m = 0; m < 7; ++m) {
+        const float* w = f.wt + static_cast<size_t>(m) * 65536 + o;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int k = 0; k < 256; ++k) acc = fmaf(__ldg(w + k * 256), s_t[k], acc);
+        out[m * 256 + o] = acc + f.cst[m * 256 + o];
+    }
+    if (o < 3) {
+        float acc = 0.f;
+        for (int k = 0; k < 256; ++k) acc = fmaf(f.wht[k * 3 + o], s_t[k], acc);
+        out[1792 + o] = acc + f.bh[o];
+    }
+}
+
+}  // namespace
+
+int epic_smem_bytes() { return kSmemBytes; }
+
+int launch_epic_tiles(const EpicLaunch& a, int n_tiles, int cluster, cudaStream_t stream) {
+    if (n_tiles == 0) return 0;
+    static bool configured = false;
+    if (!configured) {
+        MMF_CUDA_OK(cudaFuncSetAttribute(epic_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_tiles);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MMF_REQUIRE(cluster == 1 || (cluster == 2 && n_tiles % 2 == 0), "epic: pair launches need an even tile count");
+    MMF_CUDA_OK(cudaLaunchKernelEx(&cfg, epic_tile_kernel, a));
+    return 0;
+}
+
+int launch_epic_time_bias(const EpicTimeFold& f, const float* temb, int n, float* tbias, cudaStream_t stream) {
+    if (n == 0) return 0;
+    epic_time_bias_kernel<<<n, 256, 0, stream>>>(f, temb, tbias);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace mmf

@@ -110,6 +110,11 @@ __global__ void pack_kernel(const float* __restrict__ x0, const long long* __res
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     const long long s = row_slot[r];
+    if (s < 0) {                       // padding row of a tile-aligned layout
+        xs[r * 3 + 0] = 0.f; xs[r * 3 + 1] = 0.f; xs[r * 3 + 2] = 0.f;
+        if (ks) ks[r] = 0;
+        return;
+    }
     xs[r * 3 + 0] = x0[s * 3 + 0];
     xs[r * 3 + 1] = x0[s * 3 + 1];
     xs[r * 3 + 2] = x0[s * 3 + 2];
@@ -118,7 +123,7 @@ __global__ void pack_kernel(const float* __restrict__ x0, const long long* __res
         const long long kv = k0[s];
         if (kv < 0 || kv >= V) atomicOr(err_flag, 2); else kk = static_cast<int>(kv);
     }
-    ks[r] = kk;
+    if (ks) ks[r] = kk;
 }
 
 __global__ void unpack_kernel(const float* __restrict__ xs, const int* __restrict__ ks,

@@ -1,0 +1,50 @@
+// Device helpers shared by the tensor-core kernels: exact-erf GELU and swizzled shared-memory staging rows.
+#pragma once
+#include "mmf_ptx.cuh"
+
+namespace mmf {
+
+__device__ __forceinline__ float gelu_erf(float x) {
+    // 0.5 x (1 + erf(x / sqrt 2)); erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7), two MUFU ops
+    const float z = fabsf(x) * 0.70710678f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.0f - p * t * exp2f(-1.44269504f * z * z);
+    return 0.5f * x * (1.0f + copysignf(e, x));
+}
+
+__device__ __forceinline__ void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_f4(const void* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+// write 64 fp32 values of row r as bf16 into a [128][128 B] swizzled staging chunk
+__device__ __forceinline__ void stage_row_bf16(uint8_t* chunk, int r, const float* v) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        st_shared_v4(chunk + sw128_offset(r, u), pack_bf16x2(v[u * 8 + 0], v[u * 8 + 1]),
+                     pack_bf16x2(v[u * 8 + 2], v[u * 8 + 3]), pack_bf16x2(v[u * 8 + 4], v[u * 8 + 5]),
+                     pack_bf16x2(v[u * 8 + 6], v[u * 8 + 7]));
+    }
+}
+// write 32 fp32 values of row r into a [128][128 B] swizzled staging chunk
+__device__ __forceinline__ void stage_row_f32(uint8_t* chunk, int r, const float* v) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        st_shared_v4(chunk + sw128_offset(r, u), __float_as_uint(v[u * 4 + 0]), __float_as_uint(v[u * 4 + 1]),
+                     __float_as_uint(v[u * 4 + 2]), __float_as_uint(v[u * 4 + 3]));
+    }
+}
+
+__device__ __forceinline__ float leaky_relu(float x) { return x > 0.f ? x : 0.01f * x; }   // F.leaky_relu default slope
+
+}  // namespace mmf

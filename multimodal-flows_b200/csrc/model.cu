@@ -10,6 +10,8 @@
 #include <vector>
 
 #include "../../include/mmf_b200.h"
+#include "mmf_epic.h"
+#include "mmf_host.h"
 #include "mmf_internal.h"
 #include "mmf_simt.h"
 
@@ -19,81 +21,6 @@ static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 
 namespace {
-
-inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
-
-inline uint16_t f32_to_bf16_bits(float f) {          // round to nearest even, as __float2bfloat16_rn
-    uint32_t x;
-    memcpy(&x, &f, 4);
-    if ((x & 0x7fffffffu) > 0x7f800000u) return static_cast<uint16_t>((x >> 16) | 0x40);
-    const uint32_t lsb = (x >> 16) & 1u;
-    x += 0x7fffu + lsb;
-    return static_cast<uint16_t>(x >> 16);
-}
-
-// ---------------------------------------------------------------------------------------------
-// device memory helpers
-// ---------------------------------------------------------------------------------------------
-struct DeviceArena {            // one allocation, bump sub-allocation, 256-byte aligned
-    uint8_t* base = nullptr;
-    size_t cap = 0, used = 0;
-    std::vector<uint8_t> staging;
-    size_t reserve(size_t bytes) {
-        const size_t off = (staging.size() + 255) / 256 * 256;
-        staging.resize(off + bytes, 0);
-        return off;
-    }
-    size_t put_f32(const std::vector<float>& v) {
-        const size_t off = reserve(v.size() * 4);
-        memcpy(staging.data() + off, v.data(), v.size() * 4);
-        return off;
-    }
-    size_t put_bf16(const std::vector<float>& v) {
-        const size_t off = reserve(v.size() * 2);
-        uint16_t* d = reinterpret_cast<uint16_t*>(staging.data() + off);
-        for (size_t i = 0; i < v.size(); ++i) d[i] = f32_to_bf16_bits(v[i]);
-        return off;
-    }
-    int upload() {
-        cap = staging.size();
-        MMF_CUDA_OK(cudaMalloc(&base, cap ? cap : 256));
-        MMF_CUDA_OK(cudaMemcpy(base, staging.data(), cap, cudaMemcpyHostToDevice));
-        staging.clear();
-        staging.shrink_to_fit();
-        return 0;
-    }
-    template <typename T> T* at(size_t off) const { return reinterpret_cast<T*>(base + off); }
-    void release() { if (base) cudaFree(base); base = nullptr; }
-};
-
-struct WeightMap {
-    std::unordered_map<std::string, const MmfWeightRef*> m;
-    std::string missing;
-    const MmfWeightRef* find(const std::string& name) const {
-        auto it = m.find(name);
-        return it == m.end() ? nullptr : it->second;
-    }
-    // returns a copy; records the first missing / mis-shaped parameter
-    std::vector<float> get(const std::string& name, int64_t d0, int64_t d1 = -1, bool optional = false) {
-        const MmfWeightRef* w = find(name);
-        const int64_t n = d0 * (d1 < 0 ? 1 : d1);
-        if (!w) {
-            if (!optional && missing.empty()) missing = "missing parameter " + name;
-            return std::vector<float>(static_cast<size_t>(n), 0.f);
-        }
-        int64_t have = 1;
-        for (int i = 0; i < w->ndim; ++i) have *= w->shape[i];
-        const bool ok = have == n && w->shape[0] == d0 && (d1 < 0 || w->ndim < 2 || w->shape[1] == d1);
-        if (!ok) {
-            if (missing.empty()) missing = "parameter " + name + " has an unexpected shape";
-            return std::vector<float>(static_cast<size_t>(n), 0.f);
-        }
-        return std::vector<float>(w->data, w->data + n);
-    }
-    bool has(const std::string& name) const { return find(name) != nullptr; }
-};
-
-inline void append(std::vector<float>& dst, const std::vector<float>& src) { dst.insert(dst.end(), src.begin(), src.end()); }
 
 // ---------------------------------------------------------------------------------------------
 // packed parameters
@@ -159,6 +86,7 @@ struct MmfModel {
     CUtensorMap tm_wxe2, tm_whead;
     std::vector<float> time_expand_w, time_expand_b;    // host fp32, ParticleFormer only
     Workspace ws;
+    EpicModel* epic = nullptr;          // EPiC has its own packed checkpoint, workspace and kernel
     int* d_err = nullptr;
     int64_t launches = 0;
     bool prof_on = false;
@@ -172,6 +100,7 @@ struct MmfModel {
         if (ws.base) cudaFree(ws.base);
         if (ws.stage) cudaFree(ws.stage);
         if (d_err) cudaFree(d_err);
+        if (epic) epic_destroy(epic);
     }
 };
 
@@ -466,17 +395,6 @@ int upload_plan(MmfModel* m, const Plan& p, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 // time tables: sin/cos features (reference utils/models.py:62-75) and time_expand (ParticleTransformers.py:109)
 // ---------------------------------------------------------------------------------------------
-void sincos_row(float t, int dim, float* out) {
-    const int half = dim / 2;
-    const float scale = std::log(10000.0f) / static_cast<float>(half - 1);
-    for (int i = 0; i < half; ++i) {
-        const float f = std::exp(static_cast<float>(i) * -scale);
-        const float a = t * f;
-        out[i] = std::sin(a);
-        out[half + i] = std::cos(a);
-    }
-}
-
 int upload_time_tables(MmfModel* m, const float* times, int n, cudaStream_t s) {
     const MmfModelDesc& d = m->desc;
     m->h_temb.assign(static_cast<size_t>(n) * 256, 0.f);
@@ -623,9 +541,9 @@ int generate_device(MmfModel* m, const float* x0, const int64_t* k0, const int64
                     const float* t_grid, int N, float dt, const MmfStepOptions* opts, const float* u,
                     const uint8_t* forced_k, float* x_out, int64_t* k_out, float* rates_out, cudaStream_t s) {
     const MmfModelDesc& d = m->desc;
-    MMF_REQUIRE(d.arch != MMF_ARCH_EPIC, "EPiC generation is not built yet");
+    MMF_REQUIRE(N >= 1 && B >= 1 && D >= 1 && D <= d.max_num_particles, "bad problem shape");
+    if (d.arch == MMF_ARCH_EPIC) return epic_generate(m->epic, x0, mask_host, B, D, t_grid, N, dt, x_out, s);
     MMF_REQUIRE(opts != nullptr && k0 != nullptr && k_out != nullptr, "the transformers need tokens and step options");
-    MMF_REQUIRE(N >= 1 && B >= 1 && D >= 1, "empty problem");
     Plan plan;
     MMF_TRY(build_plan(mask_host, B, D, &plan));
     MMF_TRY(ensure_workspace(m, plan.rows, B * D, N, static_cast<int>(plan.items.size())));
@@ -674,7 +592,8 @@ int mmf_model_create(const MmfModelDesc* desc, const MmfWeightRef* weights, int3
     MMF_REQUIRE(desc && weights && out, "null argument");
     *out = nullptr;
     MMF_REQUIRE(desc->arch >= 0 && desc->arch <= MMF_ARCH_EPIC, "unknown architecture");
-    MMF_REQUIRE(desc->n_embd == 256 && desc->n_inner == 512 && desc->n_head == 4 && desc->dim_continuous == 3,
+    MMF_REQUIRE(desc->n_embd == 256 && desc->dim_continuous == 3 &&
+                    (desc->arch == MMF_ARCH_EPIC || (desc->n_inner == 512 && desc->n_head == 4)),
                 "accelerated path is built for n_embd=256, n_inner=512, n_head=4, dim_continuous=3");
     MMF_REQUIRE(desc->vocab_size >= 2 && desc->vocab_size <= kMaxV, "vocab_size must be in [2,16]");
     MMF_REQUIRE(desc->max_num_particles >= 1 && desc->max_num_particles <= kMaxKeys - 8, "max_num_particles must be <= 152");
@@ -691,11 +610,7 @@ int mmf_model_create(const MmfModelDesc* desc, const MmfWeightRef* weights, int3
     m->device = device;
     WeightMap wm;
     for (int i = 0; i < n_weights; ++i) wm.m[weights[i].name] = &weights[i];
-    if (desc->arch == MMF_ARCH_EPIC) {
-        set_last_error("EPiC is not built yet");
-        return 2;
-    }
-    int rc = build_transformer(m.get(), wm);
+    int rc = desc->arch == MMF_ARCH_EPIC ? epic_create(*desc, wm, &m->epic) : build_transformer(m.get(), wm);
     if (rc) return rc;
     MMF_CUDA_OK(cudaMalloc(&m->d_err, sizeof(int)));
     MMF_CUDA_OK(cudaMemset(m->d_err, 0, sizeof(int)));
@@ -710,7 +625,9 @@ void mmf_model_destroy(MmfModel* model) {
     delete model;
 }
 
-int64_t mmf_launch_count(const MmfModel* model) { return model ? model->launches : 0; }
+int64_t mmf_launch_count(const MmfModel* model) {
+    return model ? model->launches + epic_launches(model->epic) : 0;
+}
 
 int mmf_profile_enable(MmfModel* m, int32_t on) {
     MMF_REQUIRE(m != nullptr, "null model");
@@ -742,8 +659,7 @@ int mmf_profile_read(MmfModel* m, double* ms, int64_t* launches, double* flops, 
 int mmf_encoder_forward(MmfModel* m, const float* x, const int64_t* k, const int64_t* mask, const float* t, int32_t B,
                         int32_t D, float* vt_out, float* logits_out, void* stream) {
     MMF_REQUIRE(m && x && mask && t && vt_out, "null argument");
-    MMF_REQUIRE(m->desc.arch != MMF_ARCH_EPIC, "EPiC forward is not built yet");
-    MMF_REQUIRE(k && logits_out, "the transformers need tokens and a logits buffer");
+    MMF_REQUIRE(B >= 1 && D >= 1 && D <= m->desc.max_num_particles, "bad batch shape");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     MMF_CUDA_OK(cudaSetDevice(m->device));
     std::vector<int64_t> hmask;
@@ -751,6 +667,8 @@ int mmf_encoder_forward(MmfModel* m, const float* x, const int64_t* k, const int
     std::vector<float> ht(B);
     MMF_CUDA_OK(cudaMemcpyAsync(ht.data(), t, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, s));
     MMF_CUDA_OK(cudaStreamSynchronize(s));
+    if (m->desc.arch == MMF_ARCH_EPIC) return epic_forward(m->epic, x, hmask.data(), ht.data(), B, D, vt_out, s);
+    MMF_REQUIRE(k && logits_out, "the transformers need tokens and a logits buffer");
     Plan plan;
     MMF_TRY(build_plan(hmask.data(), B, D, &plan));
     MMF_TRY(ensure_workspace(m, plan.rows, B * D, B, static_cast<int>(plan.items.size())));
