@@ -27,9 +27,13 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 METRIC = "generated jets/sec @100 steps (ParticleFormer, 150 particles)"
-FLOPS_PER_PARTICLE = {"ParticleFormer": 10_630_656, "FusedParticleFormer": 5_649_920}
-FLOPS_PER_JET_CONST = {"ParticleFormer": 65_536, "FusedParticleFormer": 0}
-ATTN_FLOPS_PER_N2 = {"ParticleFormer": 11_264, "FusedParticleFormer": 5_120}
+
+
+def metric_name(args):
+    return METRIC if args.model == "ParticleFormer" else f"generated jets/sec @{args.timesteps} steps ({args.model}, 150 particles)"
+FLOPS_PER_PARTICLE = {"ParticleFormer": 10_630_656, "FusedParticleFormer": 5_649_920, "EPiC": 2_404_960}
+FLOPS_PER_JET_CONST = {"ParticleFormer": 65_536, "FusedParticleFormer": 0, "EPiC": 1_794_048}
+ATTN_FLOPS_PER_N2 = {"ParticleFormer": 11_264, "FusedParticleFormer": 5_120, "EPiC": 0}
 TC_CLASSES = ("gemm_embed", "gemm_qkv", "attention", "gemm_attn_proj_resln", "gemm_mlp_fc_gelu", "gemm_mlp_out_resln",
               "gemm_head_fc_gelu")
 
@@ -40,7 +44,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="ParticleFormer", choices=["ParticleFormer", "FusedParticleFormer"])
+    ap.add_argument("--model", default="ParticleFormer", choices=["ParticleFormer", "FusedParticleFormer", "EPiC"])
     ap.add_argument("--batch", type=int, default=256, help="jets per GPU per step")
     ap.add_argument("--timesteps", type=int, default=100)
     ap.add_argument("--temperature", type=float, default=1.0)
@@ -117,11 +121,17 @@ def cpu_port_rate(args, cfg, sd, sample_jets, sample_timesteps, repeats=1):
     torch.set_num_threads(os.cpu_count() or 1)
     src = synthetic.source_state(sample_jets, cfg.max_num_particles, cfg.vocab_size, dense=args.dense)
     u = synthetic.uniform_draws(sample_timesteps + 1, sample_jets, cfg.max_num_particles, cfg.vocab_size)
-    orc.simulate_dynamics(sd, cfg, src.continuous, src.discrete, src.mask, u=u, max_steps=1)          # warm-up
+
+    def run(uu, steps):
+        if cfg.model == "EPiC":
+            return orc.simulate_dynamics_cfm(sd, cfg, src.continuous, src.mask, max_steps=steps)
+        return orc.simulate_dynamics(sd, cfg, src.continuous, src.discrete, src.mask, u=uu, max_steps=steps)
+
+    run(u, 1)                                                                                         # warm-up
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        orc.simulate_dynamics(sd, cfg, src.continuous, src.discrete, src.mask, u=u[1:], max_steps=sample_timesteps)
+        run(u[1:], sample_timesteps)
         dt = (time.perf_counter() - t0) / sample_timesteps
         best = dt if best is None else min(best, dt)
     return sample_jets / (best * cfg.num_timesteps), best
@@ -145,7 +155,7 @@ def run_reference_arm(args, rank):
     sample = (f"{args.cpu_sample_jets} jets x {args.cpu_sample_timesteps} of {args.timesteps} timesteps per step, oracle port "
               f"(torch fp32, {cores} threads), extrapolated linearly to {args.timesteps} timesteps")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "jets/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args), "value": value, "unit": "jets/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * args.batch / value, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "wall_s": wall},
@@ -202,7 +212,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the accelerated path has no CPU fallback")
     from mmf_b200 import _abi, synthetic
-    from mmf_b200.mmf import MultiModalFlowBridge, time_grid
+    from mmf_b200.mmf import ConditionalFlowMatching, MultiModalFlowBridge, time_grid
     from mmf_b200.param_spec import make_config
     from mmf_b200.tensorclass import DataCoupling, TensorMultiModal
 
@@ -214,7 +224,8 @@ def main():
 
     cfg = make_config(args.model, num_timesteps=args.timesteps, temperature=args.temperature)
     sd = synthetic.make_state_dict(cfg, flavor="wide", seed=0)
-    bridge = MultiModalFlowBridge(cfg)
+    epic = args.model == "EPiC"
+    bridge = (ConditionalFlowMatching if epic else MultiModalFlowBridge)(cfg)
     bridge.model.load_state_dict(sd, strict=True)
     bridge = bridge.to(dev)
     nm = bridge.model.native()
@@ -229,6 +240,8 @@ def main():
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)       # > 126 MB L2
 
     def one_step(i):
+        if epic:
+            return nm.generate(src_dev.continuous, None, src_dev.mask, ts, dt, None)
         opts = _abi.step_options(cfg, seed=7, first_global_jet=(i * world + rank) * B)
         return nm.generate(src_dev.continuous, src_dev.discrete, src_dev.mask, ts, dt, opts)
 
@@ -281,8 +294,8 @@ def main():
         torch.distributed.all_reduce(e2e_t, op=torch.distributed.ReduceOp.MAX)
     e2e_value = world * B * args.steps / float(e2e_t.item())
     slots = B * cfg.max_num_particles
-    h2d = slots * (3 * 4 + 8) + 0                      # x0 f32 + k0 i64 (the mask stays on the host: it only feeds the planner)
-    d2h = slots * (3 * 4 + 8)
+    h2d = slots * (3 * 4 + (0 if epic else 8))         # x0 f32 + k0 i64 (the mask stays on the host: it only feeds the planner)
+    d2h = slots * (3 * 4 + (0 if epic else 8))
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- gather once at the end, as the sharded sampler does (one NCCL collective, outside the loop) --------
@@ -296,26 +309,37 @@ def main():
         return
 
     # ---- live per-kernel-class profile of one more step (CUDA events on the launching stream) -------------
-    nm.profile(True)
-    nm.profile_read(reset=True)
-    one_step(10_000)
-    prof = nm.profile_read(reset=True)
-    nm.profile(False)
-    tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
-    shares = {k: round(v["ms"] / tot_ms, 4) for k, v in prof.items() if v["launches"]}
+    prof = {}
+    if not epic:
+        nm.profile(True)
+        nm.profile_read(reset=True)
+        one_step(10_000)
+        prof = nm.profile_read(reset=True)
+        nm.profile(False)
     tc = {k: v for k, v in prof.items() if k in TC_CLASSES and v["launches"]}
-    dom = max(tc, key=lambda k: tc[k]["ms"])
-    d = tc[dom]
-    ach = d["flops"] / d["launches"] / (d["ms"] / d["launches"] * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + " sustained",
-                "avg_launch_us": 1e3 * d["ms"] / d["launches"], "launches_per_step": d["launches"],
-                "share_of_step": shares[dom], "kernel_time_shares": shares}
+    if not tc:
+        # one persistent kernel runs the whole sampler (all timesteps in one launch): the step time IS that kernel's time
+        ach = flops_step / (total_ms / args.steps * 1e-3) / 1e12
+        name = "epic_tile_kernel" if epic else "tf_tile_kernel"
+        roofline = {"bound": "tensor", "kernel": f"{name} (persistent: one CTA per 128-row tile of whole jets, all timesteps in one launch)",
+                    "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"],
+                    "traffic": None, "peak_source": peaks["source"] + " sustained", "avg_launch_us": 1e3 * total_ms / args.steps,
+                    "launches_per_step": launches / max(args.steps, 1), "share_of_step": 1.0}
+    else:
+        tot_ms = sum(v["ms"] for v in prof.values()) or 1.0
+        shares = {k: round(v["ms"] / tot_ms, 4) for k, v in prof.items() if v["launches"]}
+        dom = max(tc, key=lambda k: tc[k]["ms"])
+        d = tc[dom]
+        ach = d["flops"] / d["launches"] / (d["ms"] / d["launches"] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + " sustained",
+                    "avg_launch_us": 1e3 * d["ms"] / d["launches"], "launches_per_step": d["launches"],
+                    "share_of_step": shares[dom], "kernel_time_shares": shares}
     path_tflops = flops_step / (total_ms / args.steps * 1e-3) / 1e12
     roofline["whole_path"] = {"algorithmic_tflops": path_tflops, "frac_of_sustained_peak": path_tflops / peaks["bf16_tflops_sustained"]}
 
     line = {
-        "metric": METRIC, "value": value, "unit": "jets/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": metric_name(args), "value": value, "unit": "jets/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(args), "jets_per_gpu_per_step": B, "timesteps": args.timesteps,
@@ -323,10 +347,11 @@ def main():
                    "l2": "256 MiB buffer written between timed iterations (L2 flush)", "rng": "in-kernel Philox4x32-10",
                    "wall_s_timed_region": wall},
         "e2e": {"value": e2e_value, "unit": "jets/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "mmf_b200.mmf.MultiModalFlowBridge.predict_step (pinned host batch -> mmf_generate_host)"},
+                "api": ("mmf_b200.mmf.ConditionalFlowMatching.predict_step (pinned host batch -> mmf_generate -> .cpu())" if epic else
+                        "mmf_b200.mmf.MultiModalFlowBridge.predict_step (pinned host batch -> mmf_generate_host)")},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }
-    if not args.no_step_roofline:
+    if not args.no_step_roofline and not epic:
         line["roofline_step_kernel"] = step_kernel_roofline(peaks, dev)
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

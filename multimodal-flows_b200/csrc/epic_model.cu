@@ -3,6 +3,8 @@
 // 2-CTA cluster) and the launches.  Reference: networks/EPiC.py, model/CFM.py:133-154.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 
 #include "mmf_epic.h"
@@ -199,6 +201,13 @@ int run(EpicModel* m, const float* x, const int64_t* mask_host, int B, int D, co
     EpicLaunch a{};
     a.p = m->p; a.meta = m->d_meta; a.xs0 = m->d_xs0; a.row_slot = m->d_row_slot; a.loc_skip = m->d_skip; a.tbias = m->d_tbias;
     a.per_jet_time = per_jet_time ? 1 : 0; a.nsteps = nsteps; a.dt = dt; a.x_out = vt_out ? nullptr : x_out; a.vt_out = vt_out;
+    const char* trace_path = getenv("MMF_TRACE");
+    unsigned long long* d_trace = nullptr;
+    if (trace_path) {
+        MMF_CUDA_OK(cudaMalloc(&d_trace, 128 * 8));
+        MMF_CUDA_OK(cudaMemsetAsync(d_trace, 0, 128 * 8, s));
+        a.trace = d_trace;
+    }
     if (plan.n_plain) {
         a.tile0 = 0;
         MMF_TRY_RC(launch_epic_tiles(a, plan.n_plain, 1, s));
@@ -208,6 +217,19 @@ int run(EpicModel* m, const float* x, const int64_t* mask_host, int B, int D, co
         a.tile0 = plan.n_plain;
         MMF_TRY_RC(launch_epic_tiles(a, plan.n_pair_tiles, 2, s));
         m->launches += 1;
+    }
+    if (d_trace) {                                   // debugging aid: per-phase clock stamps of CTA 0, first two timesteps
+        unsigned long long h[128];
+        MMF_CUDA_OK(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, s));
+        MMF_CUDA_OK(cudaStreamSynchronize(s));
+        cudaFree(d_trace);
+        if (FILE* f = fopen(trace_path, "w")) {
+            for (int st = 0; st < 2; ++st)
+                for (int i = 0; i < 64 && h[st * 64 + i]; ++i)
+                    fprintf(f, "step %d mark %2d  +%llu cycles (total %llu)\n", st, i, i ? h[st * 64 + i] - h[st * 64 + i - 1] : 0ull,
+                            h[st * 64 + i] - h[st * 64]);
+            fclose(f);
+        }
     }
     return 0;
 }

@@ -221,7 +221,14 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
             epi_bar();
         };
 
+        int mark_i = 0;
+        auto mark = [&](int step) {
+            if (a.trace && blockIdx.x == 0 && tid == 0 && step < 2 && mark_i < 64) a.trace[step * 64 + mark_i] = clock64();
+            ++mark_i;
+        };
         for (int step = 0; step < a.nsteps; ++step) {
+            mark_i = 0;
+            mark(step);                                       // 0: step start
             const int tb_row = a.per_jet_time ? s_meta->jet_tb[jrow] : step;
             const float* tbr = a.tbias + static_cast<size_t>(tb_row) * kEpicTbLd;
 
@@ -245,10 +252,12 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
                 tc_fence_before();
                 mbar_arrive(&bars->a_ready);
             }
+            mark(step);                                       // 1: embedding written
             // ---- proj.mlp_local.2: loc = GELU(acc + b); keep fp32 in TMEM, skip copy in global, bf16 operand in Abuf
             mbar_wait(&bars->acc_full, pf);
             pf ^= 1;
             tc_fence_after();
+            mark(step);                                       // 2: proj GEMM done
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 const int col0 = hf * 128 + c * 32;
@@ -273,8 +282,10 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
             tc_fence_before();
             mbar_arrive(&bars->a_ready);                     // layer 0's fc_loc1 may start: it only needs loc
             epi_bar();
+            mark(step);                                       // 3: proj epilogue done
             // ---- proj.mlp_global: pooled(512) ++ temb -> 256 (GELU) -> 16 (GELU)
             pool(false);
+            mark(step);                                       // 4: pooled
             global_hidden<true>(a.p.wg0t, 512, s_pool, s_part, s_hid, a.tbias + 256 + (a.per_jet_time ? 0 : static_cast<size_t>(step) * kEpicTbLd),
                                 a.per_jet_time ? kEpicTbLd : 0, s_meta->jet_tb, njets, tid);
             if (tid < njets * 16) {
@@ -283,6 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
                 s_gskip[tid] = g;
             }
             epi_bar();
+            mark(step);                                       // 5: proj global MLP done
 
             float hp0 = 0.f, hp1 = 0.f, hp2 = 0.f;
 #pragma unroll 1
@@ -293,7 +305,9 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
                     if (tid < njets * 16) s_pool[(tid >> 4) * kPoolLd + 512 + (tid & 15)] = s_glob[tid];
                     epi_bar();
                 }
+                mark(step);                                   // 6+6l: pooled
                 global_hidden<false>(a.p.wg1t[l], 528, s_pool, s_part, s_hid, a.p.bg1[l], 0, s_meta->jet_tb, njets, tid);
+                mark(step);                                   // 7+6l: global hidden done
                 if (tid < njets * 16) s_gpre[tid] = s_glob[tid] + global_out16(a.p.wg2[l], a.p.bg2[l], s_hid, tid >> 4, tid & 15);
                 epi_bar();
                 {   // per-jet bias of fc_loc1: time part (table) + global part
@@ -311,10 +325,12 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
                     }
                 }
                 epi_bar();
+                mark(step);                                   // 8+6l: global path done
                 // ---- fc_loc1 epilogue: hidden = leaky_relu(acc + jet bias) -> bf16 operand (overwrites loc in Abuf)
                 mbar_wait(&bars->acc_full, pf);
                 pf ^= 1;
                 tc_fence_after();
+                mark(step);                                   // 9+6l: fc_loc1 GEMM done (normally long before)
                 {
                     const float* jb = s_jb + jrow * 256;
 #pragma unroll 1
@@ -336,10 +352,12 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
                 fence_proxy_async();
                 tc_fence_before();
                 mbar_arrive(&bars->a_ready);                 // fc_loc2 accumulates onto loc in TMEM
+                mark(step);                                   // 10+6l: fc_loc1 epilogue done
                 // ---- fc_loc2 epilogue: loc = leaky_relu(loc_pre + b) + loc_skip
                 mbar_wait(&bars->acc_full, pf);
                 pf ^= 1;
                 tc_fence_after();
+                mark(step);                                   // 11+6l: fc_loc2 GEMM done
                 const bool last = l + 1 == kEpicLayers;
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
@@ -385,6 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
                 }
                 epi_bar();
             }
+            mark(step);                                       // 36: layers done
             // ---- head and Euler update
             if (hf == 1) { s_headp[r * 4] = hp0; s_headp[r * 4 + 1] = hp1; s_headp[r * 4 + 2] = hp2; }
             epi_bar();

@@ -1,0 +1,800 @@
+// Persistent per-tile ParticleFormer / FusedParticleFormer sampler (see mmf_tftile.h for the data layout).
+//
+// warps 0..7   epilogue / SIMT: thread = (row r, column half hf); runs the hand-written per-timestep program
+// warp  8      lane 0: producer - walks the op table, streams weight tiles and parameter blobs with 1-D bulk copies
+// warp  9      lane 0: tcgen05.mma issuer - walks the op table
+//
+// Synchronisation: `go` (256 arrivals) epilogue -> MMA issuer, consumed in order by the ops flagged `wait`;
+// `done[0/1]` (tcgen05.commit) MMA -> epilogue; full/empty ring barriers producer <-> MMA issuer;
+// pfull/pempty parameter double buffer producer <-> epilogue.
+#include "mmf_ptx.cuh"
+#include "mmf_tftile.h"
+#include "mmf_tile.cuh"
+
+namespace mmf {
+
+namespace {
+
+constexpr int kEpi = 256;
+constexpr int kThreads = 320;
+constexpr int kStages = 3;
+constexpr int kTile = 16384;
+// operand arena (bytes); every region is 1024-byte aligned
+constexpr uint32_t oA = 0;                       // 4 chunks [128 x 64] bf16: LayerNorm output / head input
+constexpr uint32_t oQ = 65536, oK = oQ + kTile;  // Q | K of the current unit; P (probabilities) aliases both
+constexpr uint32_t oVT = oK + kTile;             // V^T [64 d][128 keys]
+constexpr uint32_t oO = oVT + kTile;             // attention output of the current unit [128 x 64]
+constexpr uint32_t oH0 = oQ, oH1 = oVT;          // MLP hidden quarters [128 x 128] (two chunks each), ping-pong
+constexpr uint32_t oRing = oO + kTile;           // weight ring
+constexpr int kArena = oRing + kStages * kTile;
+
+struct TfBars {
+    uint64_t full[kStages], empty[kStages], done[2], go, pfull[2], pempty[2];
+    uint32_t tmem_base;
+};
+
+// fp32 scratch after the two parameter buffers (float offsets)
+constexpr int mXs = 0, mKs = mXs + 384, mSeg = mKs + 128, mRowTb = mSeg + 64, mStat = mRowTb + 128, mRed = mStat + 1024,
+              mSum = mRed + 256, mOut = mSum + 256, mTemb = mOut + 128 * 12, mEnd = mTemb + 512;
+constexpr int kSmemBytes = 1024 + 1024 + kArena + 2 * kTfParamFloats * 4 + mEnd * 4;
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+
+constexpr uint32_t kScr = 256;                   // first scratch column in TMEM
+
+struct Epi {
+    uint8_t* arena;
+    float* pbuf;
+    float* misc;
+    TfBars* bars;
+    const float* P;          // current parameter blob
+    uint32_t taddr;          // TMEM base + this warp's lane quarter
+    int r, hf, tid;
+    uint32_t pd0, pd1, pc;
+    unsigned long long* trace;   // clock stamps of CTA 0 / thread 0 for the first two timesteps (debugging aid) or null
+    int mark_i, step;
+};
+__device__ __forceinline__ void mark(Epi& e) {
+    if (e.trace && e.step < 2 && e.mark_i < 256) e.trace[e.step * 256 + e.mark_i] = clock64();
+    ++e.mark_i;
+}
+
+__device__ __forceinline__ void epi_bar() { named_bar_sync(1, kEpi); }
+__device__ __forceinline__ void wait_done(Epi& e, int b) {
+    if (b == 0) { mbar_wait(&e.bars->done[0], e.pd0); e.pd0 ^= 1; }
+    else { mbar_wait(&e.bars->done[1], e.pd1); e.pd1 ^= 1; }
+    tc_fence_after();
+    mark(e);
+}
+__device__ __forceinline__ void go(Epi& e) {
+    mark(e);
+    fence_proxy_async();
+    tc_fence_before();
+    mbar_arrive(&e.bars->go);
+}
+__device__ __forceinline__ void param_acquire(Epi& e) {
+    const uint32_t p = e.pc & 1;
+    mbar_wait(&e.bars->pfull[p], (e.pc >> 1) & 1);
+    e.P = e.pbuf + p * kTfParamFloats;
+}
+__device__ __forceinline__ void param_release(Epi& e) {
+    mbar_arrive(&e.bars->pempty[e.pc & 1]);
+    ++e.pc;
+}
+
+__device__ __forceinline__ float4 ldf4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// 32 fp32 values -> bf16 into the operand chunk that holds absolute column col0 (multiple of 32) of a 256-wide row
+__device__ __forceinline__ void stage32(uint8_t* abase, int r, int col0, const float* v) {
+    uint8_t* ch = abase + (col0 >> 6) * kTile;
+    const uint32_t u0 = (col0 & 63) >> 3;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        st_shared_v4(ch + sw128_offset(r, u0 + u), pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                     pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+}
+
+// ---- residual-stream passes; every thread owns columns [hf*128, hf*128+128) of its row -----------------------
+// v = resid + add0 (+ add1) (+ skip); stored back; returns the sum over the thread's 128 columns
+__device__ __forceinline__ float resid_update(Epi& e, const float* add0, const float* add1, const float* skipc) {
+    float sum = 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+        const int c0 = cc * 32;
+        float v[32];
+        tmem_ld32(e.taddr + e.hf * 128 + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float4 a = ldf4(add0 + c0 + 4 * u);
+            v[4 * u] += a.x; v[4 * u + 1] += a.y; v[4 * u + 2] += a.z; v[4 * u + 3] += a.w;
+        }
+        if (add1) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float4 a = ldf4(add1 + c0 + 4 * u);
+                v[4 * u] += a.x; v[4 * u + 1] += a.y; v[4 * u + 2] += a.z; v[4 * u + 3] += a.w;
+            }
+        }
+        if (skipc) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += skipc[(c0 + i) * 128];
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sum += v[i];
+        tmem_st32(e.taddr + e.hf * 128 + c0, v);
+    }
+    tmem_st_wait();
+    return sum;
+}
+// LayerNorm statistics of the (stored) residual row: over the thread's 128 columns, or over all 256 (WIDE)
+template <bool WIDE>
+__device__ __forceinline__ void ln_stats(Epi& e, float sum, int slot, float& mean, float& rstd) {
+    mean = sum * (1.0f / 128.0f);
+    float m2 = 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+        float v[32];
+        tmem_ld32(e.taddr + e.hf * 128 + cc * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; m2 = fmaf(d, d, m2); }
+    }
+    if (WIDE) {
+        float* st = e.misc + mStat + slot * 512;
+        st[(e.hf * 128 + e.r) * 2] = mean;
+        st[(e.hf * 128 + e.r) * 2 + 1] = m2;
+        epi_bar();
+        const float om = st[((e.hf ^ 1) * 128 + e.r) * 2], o2 = st[((e.hf ^ 1) * 128 + e.r) * 2 + 1];
+        const float d = mean - om;
+        m2 = m2 + o2 + d * d * 64.0f;
+        mean = 0.5f * (mean + om);
+        rstd = rsqrtf(m2 * (1.0f / 256.0f) + 1e-5f);
+    } else {
+        rstd = rsqrtf(m2 * (1.0f / 128.0f) + 1e-5f);
+    }
+}
+// normalised row -> bf16 GEMM operand (Abuf)
+__device__ __forceinline__ void ln_to_abuf(Epi& e, float mean, float rstd, const float* g, const float* b) {
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+        const int c0 = cc * 32;
+        float v[32];
+        tmem_ld32(e.taddr + e.hf * 128 + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float4 gg = ldf4(g + c0 + 4 * u), bb = ldf4(b + c0 + 4 * u);
+            v[4 * u] = fmaf((v[4 * u] - mean) * rstd, gg.x, bb.x);
+            v[4 * u + 1] = fmaf((v[4 * u + 1] - mean) * rstd, gg.y, bb.y);
+            v[4 * u + 2] = fmaf((v[4 * u + 2] - mean) * rstd, gg.z, bb.z);
+            v[4 * u + 3] = fmaf((v[4 * u + 3] - mean) * rstd, gg.w, bb.w);
+        }
+        stage32(e.arena + oA, e.r, e.hf * 128 + c0, v);
+    }
+}
+// normalised row (+ post) -> back into the residual stream; returns the new row sum (stream junction of ParticleFormer)
+__device__ __forceinline__ float ln_to_resid(Epi& e, float mean, float rstd, const float* g, const float* b, const float* post) {
+    float sum = 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+        const int c0 = cc * 32;
+        float v[32];
+        tmem_ld32(e.taddr + e.hf * 128 + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float4 gg = ldf4(g + c0 + 4 * u), bb = ldf4(b + c0 + 4 * u), pp = ldf4(post + c0 + 4 * u);
+            v[4 * u] = fmaf((v[4 * u] - mean) * rstd, gg.x, bb.x) + pp.x;
+            v[4 * u + 1] = fmaf((v[4 * u + 1] - mean) * rstd, gg.y, bb.y) + pp.y;
+            v[4 * u + 2] = fmaf((v[4 * u + 2] - mean) * rstd, gg.z, bb.z) + pp.z;
+            v[4 * u + 3] = fmaf((v[4 * u + 3] - mean) * rstd, gg.w, bb.w) + pp.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sum += v[i];
+        tmem_st32(e.taddr + e.hf * 128 + c0, v);
+    }
+    tmem_st_wait();
+    return sum;
+}
+
+// LayerNorm over N consecutive register values with affine parameters in shared memory
+template <int N>
+__device__ __forceinline__ void ln_regs(float* v, const float* g, const float* b) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) s += v[i];
+    const float mean = s * (1.0f / N);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(q * (1.0f / N) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+        const float4 gg = ldf4(g + i), bb = ldf4(b + i);
+        v[i] = fmaf((v[i] - mean) * rstd, gg.x, bb.x);
+        v[i + 1] = fmaf((v[i + 1] - mean) * rstd, gg.y, bb.y);
+        v[i + 2] = fmaf((v[i + 2] - mean) * rstd, gg.z, bb.z);
+        v[i + 3] = fmaf((v[i + 3] - mean) * rstd, gg.w, bb.w);
+    }
+}
+
+// ---- attention epilogues -----------------------------------------------------------------------------------------
+// QKV of one 64-column unit sits in scratch: q [0,64) k [64,128) v [128,192).  hf 0: q and v[0,32); hf 1: k and v[32,64).
+// bq/bk/bv point at the unit's 64 bias values; qg.. are the per-head LayerNorm parameters ([HS]).
+template <int HS>
+__device__ __forceinline__ void qkv_epilogue(Epi& e, const float* bq, const float* bk, const float* bv, const float* qg,
+                                             const float* qb, const float* kg, const float* kb) {
+    {
+        float v[64];
+        tmem_ld32(e.taddr + kScr + e.hf * 64, v);
+        tmem_ld32(e.taddr + kScr + e.hf * 64 + 32, v + 32);
+        tmem_ld_wait();
+        const float* bias = e.hf ? bk : bq;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+            const float4 a = ldf4(bias + i);
+            v[i] += a.x; v[i + 1] += a.y; v[i + 2] += a.z; v[i + 3] += a.w;
+        }
+        const float* g = e.hf ? kg : qg;
+        const float* b = e.hf ? kb : qb;
+        if (g) {
+            if (HS == 64) ln_regs<64>(v, g, b);
+            else { ln_regs<32>(v, g, b); ln_regs<32>(v + 32, g, b); }
+        }
+        stage_row_bf16(e.arena + (e.hf ? oK : oQ), e.r, v);
+    }
+    {
+        float w[32];
+        tmem_ld32(e.taddr + kScr + 128 + e.hf * 32, w);
+        tmem_ld_wait();
+        // V^T[d][key = r]: two chunks of 64 keys, 64 rows (d) of 128 bytes each
+        uint8_t* vt = e.arena + oVT + (e.r >> 6) * 8192 + (e.r & 7) * 2;
+        const uint32_t ku = (e.r & 63) >> 3;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const int d = e.hf * 32 + i;
+            const float val = w[i] + bv[e.hf * 32 + i];
+            *reinterpret_cast<bf16*>(vt + sw128_offset(d, ku)) = __float2bfloat16_rn(val);
+        }
+    }
+}
+
+// scores of one head in scratch columns [scol, scol+128); thread handles keys [hf*64, +64) of its row
+__device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, float scale_log2e, int kb, int ke) {
+    float s[64];
+    tmem_ld32(e.taddr + scol + e.hf * 64, s);
+    tmem_ld32(e.taddr + scol + e.hf * 64 + 32, s + 32);
+    tmem_ld_wait();
+    const int k0 = e.hf * 64;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        const int key = k0 + j;
+        if (key >= kb && key < ke) mx = fmaxf(mx, s[j]);
+    }
+    float* red = e.misc + mRed;
+    red[e.hf * 128 + e.r] = mx;
+    epi_bar();
+    mx = fmaxf(mx, red[(e.hf ^ 1) * 128 + e.r]);
+    const float msc = (mx == -INFINITY) ? 0.f : mx * scale_log2e;
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        const int key = k0 + j;
+        const float p = (key >= kb && key < ke) ? exp2f(fmaf(s[j], scale_log2e, -msc)) : 0.f;
+        s[j] = p;
+        sum += p;
+    }
+    stage_row_bf16(e.arena + (e.hf ? oK : oQ), e.r, s);          // P chunk hf (keys hf*64..)
+    e.misc[mSum + e.hf * 128 + e.r] = sum;
+}
+
+// O = P V of one head in scratch columns [ocol, ocol+HS) -> normalised bf16 into Os columns [ucol, ucol+HS) of the unit
+template <int HS>
+__device__ __forceinline__ void o_epilogue(Epi& e, uint32_t ocol, int ucol) {
+    const float tot = e.misc[mSum + e.r] + e.misc[mSum + 128 + e.r];
+    const float inv = 1.0f / (tot > 0.f ? tot : 1.f);
+    constexpr int W = HS / 2;
+    float o[W];
+    if (W == 32) tmem_ld32(e.taddr + ocol + e.hf * W, o);
+    else tmem_ld16(e.taddr + ocol + e.hf * W, o);
+    tmem_ld_wait();
+    const uint32_t u0 = (ucol + e.hf * W) >> 3;
+    uint8_t* os = e.arena + oO;
+#pragma unroll
+    for (int u = 0; u < W / 8; ++u)
+        st_shared_v4(os + sw128_offset(e.r, u0 + u), pack_bf16x2(o[8 * u] * inv, o[8 * u + 1] * inv),
+                     pack_bf16x2(o[8 * u + 2] * inv, o[8 * u + 3] * inv), pack_bf16x2(o[8 * u + 4] * inv, o[8 * u + 5] * inv),
+                     pack_bf16x2(o[8 * u + 6] * inv, o[8 * u + 7] * inv));
+}
+
+// MLP hidden quarter q in scratch half (q&1): GELU(acc + bias) -> bf16 H(q&1); `bias` points at the quarter's 128 values
+__device__ __forceinline__ void fc_epilogue(Epi& e, int q, const float* bias) {
+    float v[64];
+    const uint32_t col = kScr + (q & 1) * 128 + e.hf * 64;
+    tmem_ld32(e.taddr + col, v);
+    tmem_ld32(e.taddr + col + 32, v + 32);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) {
+        const float4 a = ldf4(bias + e.hf * 64 + i);
+        v[i] = gelu_erf(v[i] + a.x); v[i + 1] = gelu_erf(v[i + 1] + a.y);
+        v[i + 2] = gelu_erf(v[i + 2] + a.z); v[i + 3] = gelu_erf(v[i + 3] + a.w);
+    }
+    stage_row_bf16(e.arena + ((q & 1) ? oH1 : oH0) + e.hf * kTile, e.r, v);
+}
+
+// head hidden quarter: GELU(acc + bias) dotted with NO output rows of W2 (row stride ld), accumulated into out[]
+template <int NO>
+__device__ __forceinline__ void head_epilogue(Epi& e, int q, const float* bias, const float* w2, int ld, float* out) {
+    float v[64];
+    const uint32_t col = kScr + (q & 1) * 128 + e.hf * 64;
+    tmem_ld32(e.taddr + col, v);
+    tmem_ld32(e.taddr + col + 32, v + 32);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) {
+        const float4 a = ldf4(bias + e.hf * 64 + i);
+        v[i] = gelu_erf(v[i] + a.x); v[i + 1] = gelu_erf(v[i + 1] + a.y);
+        v[i + 2] = gelu_erf(v[i + 2] + a.z); v[i + 3] = gelu_erf(v[i + 3] + a.w);
+    }
+#pragma unroll
+    for (int o = 0; o < NO; ++o) {
+        const float* w = w2 + o * ld + e.hf * 64;
+        float acc = out[o];
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+            const float4 a = ldf4(w + i);
+            acc = fmaf(a.x, v[i], fmaf(a.y, v[i + 1], fmaf(a.z, v[i + 2], fmaf(a.w, v[i + 3], acc))));
+        }
+        out[o] = acc;
+    }
+}
+
+// one attention unit (64 q-columns = 64/HS heads) of the current block, epilogue side
+template <int HS>
+__device__ __forceinline__ void attention_unit(Epi& e, const float* bq, const float* bk, const float* bv, const float* qg,
+                                               const float* qb, const float* kg, const float* kb, int seg_b, int seg_e) {
+    const float scale = 1.4426950408889634f * rsqrtf(static_cast<float>(HS));
+    wait_done(e, 0);
+    qkv_epilogue<HS>(e, bq, bk, bv, qg, qb, kg, kb);
+    go(e);
+    if (HS == 64) {
+        wait_done(e, 0);
+        softmax_epilogue(e, kScr, scale, seg_b, seg_e);
+        go(e);
+        wait_done(e, 0);
+        o_epilogue<64>(e, kScr + 192, 0);
+        go(e);
+    } else {
+        wait_done(e, 0);                              // both heads' scores: [256,384) and [384,512)
+        softmax_epilogue(e, kScr, scale, seg_b, seg_e);
+        go(e);
+        wait_done(e, 1);                              // O of head 0 in scratch [0,32)
+        o_epilogue<32>(e, kScr, 0);
+        softmax_epilogue(e, kScr + 128, scale, seg_b, seg_e);
+        go(e);
+        wait_done(e, 0);                              // O of head 1 in scratch [32,64)
+        o_epilogue<32>(e, kScr + 32, 32);
+        go(e);
+    }
+}
+
+template <int V>
+__global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    TfBars* bars = reinterpret_cast<TfBars*>(smem);
+    uint8_t* arena = smem + 1024;
+    float* pbuf = reinterpret_cast<float*>(arena + kArena);
+    float* misc = pbuf + 2 * kTfParamFloats;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tile = a.tile0 + blockIdx.x;
+    const TfTileMeta* meta = a.meta + tile;
+
+    if (tid == 0) {
+        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+        mbar_init(&bars->done[0], 1);
+        mbar_init(&bars->done[1], 1);
+        mbar_init(&bars->go, kEpi);
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars->pfull[i], 1); mbar_init(&bars->pempty[i], kEpi); }
+        fence_mbar_init();
+    }
+    if (warp == 9) {
+        tmem_alloc(&bars->tmem_base, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 8) {
+        // ---------------------------------------------------- producer ----------------------------------------------
+        if (lane == 0) {
+            uint32_t it = 0, pcount = 0;
+            const uint4* ops = reinterpret_cast<const uint4*>(a.ops);
+            for (int step = 0; step < a.nsteps; ++step) {
+                size_t woff = 0;
+                uint4 nxt = __ldg(ops);
+                for (int i = 0; i < a.n_ops; ++i) {
+                    const uint4 raw = nxt;
+                    if (i + 1 < a.n_ops) nxt = __ldg(ops + i + 1);
+                    const uint32_t a_off = raw.x, b_off = raw.y, n = raw.z & 0xffffu;
+                    if (b_off == kTfParam) {
+                        const uint32_t p = pcount & 1;
+                        if (pcount >= 2) mbar_wait(&bars->pempty[p], ((pcount >> 1) - 1) & 1);
+                        mbar_expect_tx(&bars->pfull[p], n * 16);
+                        bulk_load_1d(pbuf + p * kTfParamFloats, reinterpret_cast<const uint8_t*>(a.params) + a_off, n * 16, &bars->pfull[p]);
+                        ++pcount;
+                    } else if (b_off == kTfRing) {
+                        const int s = it % kStages;
+                        if (it >= kStages) mbar_wait(&bars->empty[s], ((it / kStages) - 1) & 1);
+                        mbar_expect_tx(&bars->full[s], n * 128);
+                        bulk_load_1d(arena + oRing + s * kTile, a.wstream + woff, n * 128, &bars->full[s]);
+                        woff += static_cast<size_t>(n) * 128;
+                        ++it;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // ---------------------------------------------------- MMA issuer --------------------------------------------
+        if (lane == 0) {
+            uint32_t it = 0, pg = 0;
+            const uint4* ops = reinterpret_cast<const uint4*>(a.ops);
+            const uint32_t arena_u32 = smem_u32(arena);
+            for (int step = 0; step < a.nsteps; ++step) {
+                uint4 nxt = __ldg(ops);
+                for (int i = 0; i < a.n_ops; ++i) {
+                    const uint4 raw = nxt;
+                    if (i + 1 < a.n_ops) nxt = __ldg(ops + i + 1);
+                    const uint32_t a_off = raw.x, b_off = raw.y, n = raw.z & 0xffffu, dcol = raw.z >> 16;
+                    const uint32_t nk16 = raw.w & 0xffu, acc = (raw.w >> 8) & 0xffu, wait = (raw.w >> 16) & 0xffu, sig = raw.w >> 24;
+                    if (b_off == kTfParam) continue;
+                    if (wait) {
+                        mbar_wait(&bars->go, pg);
+                        pg ^= 1;
+                        tc_fence_after();
+                    }
+                    uint64_t db;
+                    int s = 0;
+                    if (b_off == kTfRing) {
+                        s = it % kStages;
+                        mbar_wait(&bars->full[s], (it / kStages) & 1);
+                        tc_fence_after();
+                        db = umma_desc_sw128(arena_u32 + oRing + s * kTile);
+                    } else {
+                        db = umma_desc_sw128(arena_u32 + b_off);
+                    }
+                    const uint64_t da = umma_desc_sw128(arena_u32 + a_off);
+                    const uint32_t idesc = umma_idesc_bf16(128, static_cast<int>(n));
+                    for (uint32_t ks = 0; ks < nk16; ++ks)
+                        umma_bf16(tmem_base + dcol, da + 2 * ks, db + 2 * ks, idesc, (acc | ks) != 0 ? 1u : 0u);
+                    if (b_off == kTfRing) { umma_commit(&bars->empty[s]); ++it; }
+                    if (sig) umma_commit(&bars->done[sig - 1]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------------------------------------------- epilogue warps ----------------------------------------
+        Epi e;
+        e.arena = arena; e.pbuf = pbuf; e.misc = misc; e.bars = bars; e.P = pbuf;
+        e.r = (warp & 3) * 32 + lane; e.hf = warp >> 2; e.tid = tid;
+        e.taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        e.pd0 = 0; e.pd1 = 0; e.pc = 0;
+        const int r = e.r, hf = e.hf;
+        const int nrows = meta->nrows;
+        float* s_xs = misc + mXs;
+        int* s_ks = reinterpret_cast<int*>(misc + mKs);
+        if (tid < 128) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) s_xs[tid * 3 + c] = a.xs0[(static_cast<size_t>(tile) * 128 + tid) * 3 + c];
+            s_ks[tid] = a.ks0[static_cast<size_t>(tile) * 128 + tid];
+        }
+        const int seg_b = meta->seg_beg[r], seg_e = meta->seg_end[r];
+        const int tb_row = a.per_jet_time ? meta->row_tb[r] : 0;
+        const long long slot = a.row_slot[static_cast<size_t>(tile) * 128 + r];
+        float* skipc = a.skip + (static_cast<size_t>(tile) * 256 + hf * 128) * 128 + r;    // + col * 128
+        const bool pf = a.arch == MMF_ARCH_PARTICLEFORMER;
+        epi_bar();
+
+        e.trace = (blockIdx.x == 0 && tid == 0) ? a.trace : nullptr;
+        e.mark_i = 0; e.step = 0;
+
+        for (int step = 0; step < a.nsteps; ++step) {
+            e.mark_i = 0; e.step = step;
+            mark(e);
+            // time embedding of this step: shared row in the sampler, per-jet rows (global) in the forward API
+            const float* tb;
+            if (a.per_jet_time) {
+                tb = a.temb + static_cast<size_t>(tb_row) * 512;
+            } else {
+                float* s_t = misc + mTemb;
+                s_t[tid] = a.temb[static_cast<size_t>(step) * 512 + tid];
+                s_t[256 + tid] = a.temb[static_cast<size_t>(step) * 512 + 256 + tid];
+                epi_bar();
+                tb = s_t;
+            }
+            const float* tb1 = tb + hf * 128;                 // stream-level embedding, this thread's columns
+            const float* tb2 = tb + (pf ? 256 : 0) + hf * 128;  // embedding added inside the main (256-wide) blocks
+
+            // ================= embedding stage =================
+            param_acquire(e);
+            {
+                const float x0 = s_xs[r * 3], x1 = s_xs[r * 3 + 1], x2 = s_xs[r * 3 + 2];
+#pragma unroll 1
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int chunk = hf * 2 + cc;
+                    float v[64];
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) {
+                        const float4 w = ldf4(e.P + tfp::E_W0 + (chunk * 64 + i) * 4);
+                        v[i] = gelu_erf(fmaf(w.z, x2, fmaf(w.y, x1, fmaf(w.x, x0, w.w))));
+                    }
+                    stage_row_bf16(arena + oA + chunk * kTile, r, v);
+                }
+                go(e);
+            }
+            wait_done(e, 0);
+            {
+                // x half: LN_ln1x(wxe.2 output + bias) + temb ; y half: Ytab[k] + temb   -> residual + skip streams
+                float sum = 0.f;
+                if (hf == 0) {
+                    float s1 = 0.f;
+#pragma unroll 1
+                    for (int cc = 0; cc < 4; ++cc) {
+                        float v[32];
+                        tmem_ld32(e.taddr + kScr + cc * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) s1 += v[i] + e.P[tfp::E_BXE2 + cc * 32 + i];
+                    }
+                    const float mean = s1 * (1.0f / 128.0f);
+                    float m2 = 0.f;
+#pragma unroll 1
+                    for (int cc = 0; cc < 4; ++cc) {
+                        float v[32];
+                        tmem_ld32(e.taddr + kScr + cc * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { const float d = v[i] + e.P[tfp::E_BXE2 + cc * 32 + i] - mean; m2 = fmaf(d, d, m2); }
+                    }
+                    const float rstd = rsqrtf(m2 * (1.0f / 128.0f) + 1e-5f);
+#pragma unroll 1
+                    for (int cc = 0; cc < 4; ++cc) {
+                        float v[32];
+                        tmem_ld32(e.taddr + kScr + cc * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int c = cc * 32 + i;
+                            v[i] = fmaf((v[i] + e.P[tfp::E_BXE2 + c] - mean) * rstd, e.P[tfp::E_LN1X_G + c], e.P[tfp::E_LN1X_B + c]) + tb1[c];
+                            sum += v[i];
+                            skipc[c * 128] = v[i];
+                        }
+                        tmem_st32(e.taddr + cc * 32, v);
+                    }
+                } else {
+                    const float* yt = e.P + tfp::E_YTAB + s_ks[r] * 128;
+#pragma unroll 1
+                    for (int cc = 0; cc < 4; ++cc) {
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int c = cc * 32 + i;
+                            v[i] = yt[c] + tb1[c];
+                            sum += v[i];
+                            skipc[c * 128] = v[i];
+                        }
+                        tmem_st32(e.taddr + 128 + cc * 32, v);
+                    }
+                }
+                tmem_st_wait();
+                float mean, rstd;
+                if (pf) ln_stats<false>(e, sum, 0, mean, rstd); else ln_stats<true>(e, sum, 0, mean, rstd);
+                ln_to_abuf(e, mean, rstd, e.P + tfp::E_LNN_G + hf * 128, e.P + tfp::E_LNN_B + hf * 128);
+                go(e);
+            }
+            param_release(e);
+            mark(e);
+
+            // ================= stream blocks (ParticleFormer): two independent 128-wide groups =================
+            for (int blk = 0; blk < a.n_stream; ++blk) {
+                param_acquire(e);
+                const bool last = blk + 1 == a.n_stream;
+                for (int g = 0; g < 2; ++g) {
+                    const float* G = e.P + g * tfp::S_GROUP;
+                    for (int u = 0; u < 2; ++u)
+                        attention_unit<32>(e, G + tfp::S_BQKV + u * 64, G + tfp::S_BQKV + 128 + u * 64, G + tfp::S_BQKV + 256 + u * 64,
+                                           G + tfp::S_QG, G + tfp::S_QB, G + tfp::S_KG, G + tfp::S_KB, seg_b, seg_e);
+                }
+                mark(e);
+                wait_done(e, 0);                              // last projection of group 1 has landed
+                {
+                    const float* G = e.P + hf * tfp::S_GROUP;
+                    const float sum = resid_update(e, G + tfp::S_BPROJ, nullptr, nullptr);
+                    float mean, rstd;
+                    ln_stats<false>(e, sum, 0, mean, rstd);
+                    ln_to_abuf(e, mean, rstd, G + tfp::S_LN2G, G + tfp::S_LN2B);
+                    go(e);
+                }
+                for (int g = 0; g < 2; ++g) {
+                    const float* G = e.P + g * tfp::S_GROUP;
+                    for (int q = 0; q < 4; ++q) {
+                        wait_done(e, q & 1);
+                        fc_epilogue(e, q, G + tfp::S_BFC + q * 128);
+                        go(e);
+                    }
+                }
+                wait_done(e, 0);                              // last down-projection of group 1
+                {
+                    const float* G = e.P + hf * tfp::S_GROUP;
+                    if (!last) {
+                        const float sum = resid_update(e, G + tfp::S_BP2, tb1, nullptr);
+                        float mean, rstd;
+                        ln_stats<false>(e, sum, 0, mean, rstd);
+                        ln_to_abuf(e, mean, rstd, e.P + tfp::S_LNN_G + hf * 128, e.P + tfp::S_LNN_B + hf * 128);
+                    } else {
+                        // stream junction: x = ln2_x(x + x_skip) | y = ln2_y(y + y_skip); z = cat(x, y) + time_expand(temb)
+                        const float sum = resid_update(e, G + tfp::S_BP2, tb1, skipc);
+                        float mean, rstd;
+                        ln_stats<false>(e, sum, 0, mean, rstd);
+                        const float sum2 = ln_to_resid(e, mean, rstd, e.P + tfp::S_LNN_G + hf * 128, e.P + tfp::S_LNN_B + hf * 128, tb2);
+                        ln_stats<true>(e, sum2, 1, mean, rstd);
+                        ln_to_abuf(e, mean, rstd, e.P + tfp::S_LN2ND_G + hf * 128, e.P + tfp::S_LN2ND_B + hf * 128);
+                    }
+                    go(e);
+                }
+                param_release(e);
+                mark(e);
+            }
+
+            // ================= main blocks: one 256-wide stream =================
+            for (int blk = 0; blk < a.n_main; ++blk) {
+                param_acquire(e);
+                const bool last = blk + 1 == a.n_main;
+                for (int u = 0; u < 4; ++u)
+                    attention_unit<64>(e, e.P + tfp::B_BQKV + u * 64, e.P + tfp::B_BQKV + 256 + u * 64, e.P + tfp::B_BQKV + 512 + u * 64,
+                                       e.P + tfp::B_QG, e.P + tfp::B_QB, e.P + tfp::B_KG, e.P + tfp::B_KB, seg_b, seg_e);
+                mark(e);
+                wait_done(e, 0);
+                {
+                    const float sum = resid_update(e, e.P + tfp::B_BPROJ + hf * 128, nullptr, nullptr);
+                    float mean, rstd;
+                    ln_stats<true>(e, sum, 0, mean, rstd);
+                    ln_to_abuf(e, mean, rstd, e.P + tfp::B_LN2G + hf * 128, e.P + tfp::B_LN2B + hf * 128);
+                    go(e);
+                }
+                for (int q = 0; q < 4; ++q) {
+                    wait_done(e, q & 1);
+                    fc_epilogue(e, q, e.P + tfp::B_BFC + q * 128);
+                    go(e);
+                }
+                wait_done(e, 0);
+                {
+                    // not last: z += bias + temb, LayerNorm ln1 of the next block.
+                    // last: ParticleFormer  x = ln3_x(x + x_skip) | y = ln3_y(y + y_skip);  Fused  z = ln2(z + z_skip)
+                    const float sum = resid_update(e, e.P + tfp::B_BP2 + hf * 128, tb2, last ? skipc : nullptr);
+                    float mean, rstd;
+                    if (last && pf) ln_stats<false>(e, sum, 0, mean, rstd); else ln_stats<true>(e, sum, 0, mean, rstd);
+                    ln_to_abuf(e, mean, rstd, e.P + tfp::B_LNN_G + hf * 128, e.P + tfp::B_LNN_B + hf * 128);
+                    go(e);
+                }
+                param_release(e);
+                mark(e);
+            }
+
+            // ================= heads + the hybrid step =================
+            float outx[3] = {0.f, 0.f, 0.f};
+            float outy[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) outy[v] = 0.f;
+            param_acquire(e);                                 // head_x
+            for (int q = 0; q < 4; ++q) {
+                wait_done(e, q & 1);
+                head_epilogue<3>(e, q, e.P + tfp::HX_BIAS + q * 128, e.P + tfp::HX_W2 + q * 128, 512, outx);
+                go(e);
+            }
+            if (hf == 0) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) outx[c] += e.P[tfp::HX_B2 + c];
+            }
+            param_release(e);
+            for (int half = 0; half < 2; ++half) {
+                param_acquire(e);                             // head_y, hidden units [half*256, +256)
+                for (int qq = 0; qq < 2; ++qq) {
+                    const int q = 4 + half * 2 + qq;
+                    wait_done(e, q & 1);
+                    head_epilogue<V>(e, q, e.P + tfp::HY_BIAS + qq * 128, e.P + tfp::HY_W2 + qq * 128, 256, outy);
+                    if (q < 6) go(e);
+                }
+                if (half == 0 && hf == 0) {
+#pragma unroll
+                    for (int v = 0; v < V; ++v) outy[v] += e.P[tfp::HY_B2 + v];
+                }
+                param_release(e);
+            }
+            float* s_out = misc + mOut;
+            if (hf == 1) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) s_out[r * 12 + c] = outx[c];
+#pragma unroll
+                for (int v = 0; v < V; ++v) s_out[r * 12 + 3 + v] = outy[v];
+            }
+            epi_bar();
+            if (hf == 0 && r < nrows) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) outx[c] += s_out[r * 12 + c];
+#pragma unroll
+                for (int v = 0; v < V; ++v) outy[v] += s_out[r * 12 + 3 + v];
+                if (a.vt_out) {                               // forward API: velocity and logits at the padded slots
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) a.vt_out[slot * 3 + c] = outx[c];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) a.logits_out[slot * V + v] = outy[v];
+                } else {
+                    float uu[V], rates[V];
+                    if (a.st.u) {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) uu[v] = __ldg(a.st.u + (static_cast<size_t>(step) * a.st.slots + slot) * V + v);
+                    } else {
+                        philox_uniforms(a.st.seed, a.st.slot0 + static_cast<uint64_t>(slot), static_cast<uint32_t>(step), V, uu);
+                    }
+                    const bool lastst = step + 1 == a.nsteps;
+                    const bool want_rates = lastst && (a.st.rates_out != nullptr || a.st.argmax_last);
+                    const float w = __ldg(a.st.thermo + step * 2), coef = __ldg(a.st.thermo + step * 2 + 1);
+                    int kn = step_particle<V>(outy, s_ks[r], w, coef, a.st.sp, uu, want_rates ? rates : nullptr);
+                    if (a.st.forced) kn = a.st.forced[static_cast<size_t>(step) * a.st.slots + slot];
+                    if (lastst && a.st.rates_out) {
+#pragma unroll
+                        for (int v = 0; v < V; ++v) a.st.rates_out[slot * V + v] = rates[v];
+                    }
+                    if (lastst && a.st.argmax_last) {         // use_final_max_rates (reference model/MMF.py:193-196)
+                        int best = 0;
+#pragma unroll
+                        for (int v = 1; v < V; ++v) best = rates[v] > rates[best] ? v : best;
+                        kn = best;
+                    }
+                    s_ks[r] = kn;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) s_xs[r * 3 + c] = euler_update(s_xs[r * 3 + c], outx[c], a.st.sp.dt);
+                }
+            }
+            epi_bar();
+            mark(e);
+        }
+        if (a.x_out && tid < nrows) {
+            const long long sl = a.row_slot[static_cast<size_t>(tile) * 128 + tid];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) a.x_out[sl * 3 + c] = s_xs[tid * 3 + c];
+            a.k_out[sl] = s_ks[tid];
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+int tf_tile_smem_bytes() { return kSmemBytes; }
+
+int launch_tf_tiles(const TfLaunch& a, int n_tiles, cudaStream_t stream) {
+    if (n_tiles == 0) return 0;
+    MMF_REQUIRE(a.vocab == 9, "the tile kernel is instantiated for vocab_size 9");
+    static bool configured = false;
+    if (!configured) {
+        MMF_CUDA_OK(cudaFuncSetAttribute(tf_tile_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        configured = true;
+    }
+    tf_tile_kernel<9><<<n_tiles, kThreads, kSmemBytes, stream>>>(a);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace mmf

@@ -51,6 +51,7 @@ struct EpicLaunch {
     float dt;
     float* x_out;                       // padded (B,D,3): final state (sampler)
     float* vt_out;                      // padded (B,D,3): velocity of one forward (forward API) or null
+    unsigned long long* trace;          // optional [2 steps][64 marks] clock64 stamps of CTA 0 (MMF_TRACE=file), or null
 };
 
 struct EpicTimeFold {                   // inputs of the time-bias kernel

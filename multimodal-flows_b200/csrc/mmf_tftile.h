@@ -1,0 +1,136 @@
+// ParticleFormer / FusedParticleFormer sampler as ONE persistent kernel: a CTA owns a 128-row tile of whole
+// jets (each <= 128 particles) for all N timesteps; activations never leave the SM.
+//   residual stream [128 x 256] fp32           TMEM columns [0,256)
+//   scratch accumulators                        TMEM columns [256,512)
+//   GEMM operands (bf16, SWIZZLE_128B)          shared memory arena, rewritten by the epilogue warps
+//   weights                                     bf16 tiles streamed from L2 in consumption order (1-D bulk copies)
+//   per-stage fp32 vectors (biases, LN affine)  "parameter blobs" streamed into a double buffer
+// The tensor-core work of one timestep is a flat table of k-tile operations (TfOp) built on the host; the MMA
+// issuer and the weight producer interpret it, the epilogue warps run the matching hand-written program.
+// reference: networks/ParticleTransformers.py:62-122, :177-210; networks/attention.py:23-26, 53-74;
+//            model/solvers.py:22-60 (the step fused after the heads).
+#pragma once
+#include "mmf_host.h"
+#include "mmf_internal.h"
+
+namespace mmf {
+
+constexpr uint32_t kTfRing = 0xFFFFFFFFu;       // TfOp.b_off: B operand is the next tile of the weight stream
+constexpr uint32_t kTfParam = 0xFFFFFFFEu;      // TfOp.b_off: not an MMA - load parameter blob (a_off = byte offset, n = bytes/16)
+constexpr int kTfParamFloats = 4096;            // floats per parameter blob slot
+
+// float offsets inside the parameter blobs (one blob per stage of the per-timestep program)
+namespace tfp {
+// embedding stage
+constexpr int E_W0 = 0;                          // [256][4] = wxe.0 weight (3) and bias
+constexpr int E_BXE2 = 1024;                     // [128] wxe.2 bias
+constexpr int E_LN1X_G = 1152, E_LN1X_B = 1280;  // [128]
+constexpr int E_YTAB = 1408;                     // [V][128], V <= 16: LN_ln1y(wye.2(GELU(wye.0[k])))
+constexpr int E_LNN_G = 3456, E_LNN_B = 3712;    // [256] LayerNorm ln1 of the first block
+// main block (C = 256)
+constexpr int B_BQKV = 0;                        // [768] q | k | v
+constexpr int B_QG = 768, B_QB = 832, B_KG = 896, B_KB = 960;    // [64]
+constexpr int B_BPROJ = 1024;                    // [256]
+constexpr int B_LN2G = 1280, B_LN2B = 1536;      // [256]
+constexpr int B_BFC = 1792;                      // [512]
+constexpr int B_BP2 = 2304;                      // [256]
+constexpr int B_LNN_G = 2560, B_LNN_B = 2816;    // [256] next LayerNorm (ln1 of the next block, or the final one)
+// stream block (two groups of C = 128); group g starts at g * S_GROUP
+constexpr int S_GROUP = 1536;
+constexpr int S_BQKV = 0;                        // [384] q | k | v
+constexpr int S_QG = 384, S_QB = 416, S_KG = 448, S_KB = 480;    // [32]
+constexpr int S_BPROJ = 512;                     // [128]
+constexpr int S_LN2G = 640, S_LN2B = 768;        // [128]
+constexpr int S_BFC = 896;                       // [512]
+constexpr int S_BP2 = 1408;                      // [128]
+constexpr int S_LNN_G = 3072, S_LNN_B = 3328;    // [256] next LayerNorm over both groups (ln1 of next block; last: ln2_x|ln2_y)
+constexpr int S_LN2ND_G = 3584, S_LN2ND_B = 3840;  // [256] last stream block only: ln1 of the first main block
+// head stages
+constexpr int HX_BIAS = 0;                       // [512] head_x.0 bias
+constexpr int HX_W2 = 512;                       // [3][512] head_x.2 weight
+constexpr int HX_B2 = 2048;                      // [3]
+constexpr int HY_BIAS = 0;                       // [256] head_y.0 bias, this half of the hidden units
+constexpr int HY_W2 = 256;                       // [V][256] head_y.2 weight, this half
+constexpr int HY_B2 = 3840;                      // [V] (first half only), V <= 14
+}  // namespace tfp
+
+struct TfOp {               // one tensor-core k-tile: nk16 MMAs of K = 16
+    uint32_t a_off;         // A operand slice, byte offset inside the shared-memory operand arena
+    uint32_t b_off;         // B operand slice in the arena, or kTfRing / kTfParam
+    uint16_t n;             // MMA N = rows of B (multiple of 16)
+    uint16_t dcol;          // TMEM column of D (relative to the allocation base)
+    uint8_t nk16;           // K = 16 steps in this k-tile (4 = one 128-byte swizzled row)
+    uint8_t acc;            // 1: accumulate onto D; 0: the first MMA overwrites
+    uint8_t wait;           // 1: wait for the next "go" of the epilogue warps before issuing
+    uint8_t signal;         // after this k-tile: 0 nothing, 1 commit -> done[0], 2 commit -> done[1]
+};
+static_assert(sizeof(TfOp) == 16, "TfOp is read with one 128-bit load");
+
+struct TfTileMeta {
+    int nrows;              // real rows (<= 128)
+    int pad[3];
+    unsigned char seg_beg[128];   // per row: first row of its jet
+    unsigned char seg_end[128];   // per row: one past the last row of its jet (0,0 for padding rows)
+    int row_tb[128];        // per row: row of the time table when time is per jet (forward API)
+};
+
+struct TfStepCfg {          // the hybrid step (sampler mode)
+    StepParams sp;
+    const float* u;         // (N, B*D, V) supplied uniforms or null -> Philox
+    uint64_t seed, slot0;
+    const unsigned char* forced;   // (N, B*D) teacher-forced tokens or null
+    const float* thermo;    // [N][2] (w, coef) per timestep
+    float* rates_out;       // padded (B*D, V) rates of the last step or null
+    int argmax_last;        // use_final_max_rates
+    int* err_flag;
+    long long slots;        // B*D
+};
+
+struct TfLaunch {
+    int arch;               // MMF_ARCH_PARTICLEFORMER / MMF_ARCH_FUSED_PARTICLEFORMER
+    int n_stream, n_main;   // stream (2 x 128-wide) blocks and main (256-wide) blocks
+    int vocab;
+    const TfOp* ops;        // op table of one timestep
+    int n_ops;
+    const uint8_t* wstream; // weight tiles in op order
+    const float* params;    // parameter blobs, kTfParamFloats apart
+    const TfTileMeta* meta;
+    int tile0;
+    const float* xs0;       // [tiles*128][3] packed state
+    const int* ks0;         // [tiles*128] packed tokens
+    const int* row_slot;    // [tiles*128] packed row -> b*D + d, -1 padding
+    float* skip;            // [tiles][256][128] fp32 skip stream, column-major per tile
+    const float* temb;      // [*][512]: time embedding (256) | time_expand(temb) (256, ParticleFormer)
+    int per_jet_time;
+    int nsteps;
+    TfStepCfg st;
+    float* x_out;           // padded (B,D,3) final state     (sampler)
+    long long* k_out;       // padded (B,D) final tokens      (sampler)
+    float* vt_out;          // padded (B,D,3) velocity        (forward API) or null
+    float* logits_out;      // padded (B,D,V) logits          (forward API)
+    unsigned long long* trace;
+};
+
+int tf_tile_smem_bytes();
+int launch_tf_tiles(const TfLaunch& a, int n_tiles, cudaStream_t stream);
+
+// ---- host object (tftile_model.cu)
+struct TfTileModel;
+int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out);
+void tftile_destroy(TfTileModel* m);
+int64_t tftile_launches(const TfTileModel* m);
+// Jets of the batch that fit a tile (1 <= n <= 128) are handled here; `handled[b]` is set to 1 for them.
+// x0/k0 and the outputs are device pointers in the padded layout; mask_host, times are host arrays.
+struct TfRunArgs {
+    const float* x0; const long long* k0; const int64_t* mask_host; int B, D;
+    const float* times; int n_times; bool per_jet_time; int nsteps; float dt;
+    const MmfStepOptions* opts; const float* u; const unsigned char* forced;
+    float* x_out; long long* k_out; float* rates_out; float* vt_out; float* logits_out;
+    int* err_flag;
+};
+// prepare: plan tiles, upload tables, pack the source state (reads x0/k0).  launch: run the kernel (writes the outputs of
+// the handled jets).  The caller may zero the output buffers in between (they may alias the inputs).
+int tftile_prepare(TfTileModel* m, const TfRunArgs& r, std::vector<unsigned char>* handled, cudaStream_t s);
+int tftile_launch(TfTileModel* m, cudaStream_t s);
+
+}  // namespace mmf

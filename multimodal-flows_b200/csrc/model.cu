@@ -14,6 +14,7 @@
 #include "mmf_host.h"
 #include "mmf_internal.h"
 #include "mmf_simt.h"
+#include "mmf_tftile.h"
 
 namespace mmf {
 
@@ -87,6 +88,7 @@ struct MmfModel {
     std::vector<float> time_expand_w, time_expand_b;    // host fp32, ParticleFormer only
     Workspace ws;
     EpicModel* epic = nullptr;          // EPiC has its own packed checkpoint, workspace and kernel
+    TfTileModel* tile = nullptr;        // persistent per-tile kernel for jets of <= 128 particles (null: outside its envelope)
     int* d_err = nullptr;
     int64_t launches = 0;
     bool prof_on = false;
@@ -101,6 +103,7 @@ struct MmfModel {
         if (ws.stage) cudaFree(ws.stage);
         if (d_err) cudaFree(d_err);
         if (epic) epic_destroy(epic);
+        if (tile) tftile_destroy(tile);
     }
 };
 
@@ -544,14 +547,39 @@ int generate_device(MmfModel* m, const float* x0, const int64_t* k0, const int64
     MMF_REQUIRE(N >= 1 && B >= 1 && D >= 1 && D <= d.max_num_particles, "bad problem shape");
     if (d.arch == MMF_ARCH_EPIC) return epic_generate(m->epic, x0, mask_host, B, D, t_grid, N, dt, x_out, s);
     MMF_REQUIRE(opts != nullptr && k0 != nullptr && k_out != nullptr, "the transformers need tokens and step options");
-    Plan plan;
-    MMF_TRY(build_plan(mask_host, B, D, &plan));
-    MMF_TRY(ensure_workspace(m, plan.rows, B * D, N, static_cast<int>(plan.items.size())));
-    MMF_TRY(upload_plan(m, plan, s));
-    MMF_TRY(upload_time_tables(m, t_grid, N, s));
-    Workspace& w = m->ws;
-    { LaunchScope sc(m, KC_PACK, s); MMF_TRY(launch_pack(x0, reinterpret_cast<const long long*>(k0), w.row_slot, plan.rows, d.vocab_size, w.xs, w.ks, m->d_err, s)); }
     const size_t slots = static_cast<size_t>(B) * D;
+    // jets of <= 128 particles run in the persistent tile kernel; the layered path below takes what is left
+    std::vector<int64_t> rest;
+    const int64_t* lmask = mask_host;
+    if (m->tile) {
+        std::vector<unsigned char> handled;
+        TfRunArgs ta{};
+        ta.x0 = x0; ta.k0 = reinterpret_cast<const long long*>(k0); ta.mask_host = mask_host; ta.B = B; ta.D = D;
+        ta.times = t_grid; ta.n_times = N; ta.per_jet_time = false; ta.nsteps = N; ta.dt = dt; ta.opts = opts; ta.u = u;
+        ta.forced = forced_k; ta.x_out = x_out; ta.k_out = reinterpret_cast<long long*>(k_out); ta.rates_out = rates_out;
+        ta.err_flag = m->d_err;
+        MMF_TRY(tftile_prepare(m->tile, ta, &handled, s));
+        rest.assign(mask_host, mask_host + slots);
+        for (int b = 0; b < B; ++b)
+            if (handled[b]) std::fill(rest.begin() + static_cast<size_t>(b) * D, rest.begin() + static_cast<size_t>(b + 1) * D, 0);
+        lmask = rest.data();
+    }
+    Plan plan;
+    MMF_TRY(build_plan(lmask, B, D, &plan));
+    Workspace& w = m->ws;
+    if (plan.rows > 0) {
+        MMF_TRY(ensure_workspace(m, plan.rows, B * D, N, static_cast<int>(plan.items.size())));
+        MMF_TRY(upload_plan(m, plan, s));
+        MMF_TRY(upload_time_tables(m, t_grid, N, s));
+        LaunchScope sc(m, KC_PACK, s);
+        MMF_TRY(launch_pack(x0, reinterpret_cast<const long long*>(k0), w.row_slot, plan.rows, d.vocab_size, w.xs, w.ks, m->d_err, s));
+    }
+    // both packed states are taken: from here on the outputs may alias the inputs.  Padded slots read as zero.
+    MMF_CUDA_OK(cudaMemsetAsync(x_out, 0, slots * 3 * 4, s));
+    MMF_CUDA_OK(cudaMemsetAsync(k_out, 0, slots * 8, s));
+    if (rates_out) MMF_CUDA_OK(cudaMemsetAsync(rates_out, 0, slots * d.vocab_size * 4, s));
+    if (m->tile) MMF_TRY(tftile_launch(m->tile, s));
+    if (plan.rows == 0) return 0;
     for (int i = 0; i < N; ++i) {
         ForwardCtx c{};
         c.rows = plan.rows; c.n_items = static_cast<int>(plan.items.size());
@@ -570,9 +598,6 @@ int generate_device(MmfModel* m, const float* x0, const int64_t* k0, const int64
         h.argmax_out = (last && opts->use_final_max_rates) ? 1 : 0;
         MMF_TRY(run_forward(m, c));
     }
-    // the packed state holds everything from here on, so the outputs may alias the inputs
-    MMF_CUDA_OK(cudaMemsetAsync(x_out, 0, slots * 3 * 4, s));
-    MMF_CUDA_OK(cudaMemsetAsync(k_out, 0, slots * 8, s));
     { LaunchScope sc(m, KC_UNPACK, s); MMF_TRY(launch_unpack(w.xs, w.ks, w.row_slot, plan.rows, x_out, reinterpret_cast<long long*>(k_out), s)); }
     return 0;
 }
@@ -612,6 +637,10 @@ int mmf_model_create(const MmfModelDesc* desc, const MmfWeightRef* weights, int3
     for (int i = 0; i < n_weights; ++i) wm.m[weights[i].name] = &weights[i];
     int rc = desc->arch == MMF_ARCH_EPIC ? epic_create(*desc, wm, &m->epic) : build_transformer(m.get(), wm);
     if (rc) return rc;
+    if (desc->arch != MMF_ARCH_EPIC && !getenv("MMF_NO_TILE_KERNEL")) {       // env switch: A/B runs of the layered path
+        rc = tftile_create(*desc, wm, &m->tile);
+        if (rc) return rc;
+    }
     MMF_CUDA_OK(cudaMalloc(&m->d_err, sizeof(int)));
     MMF_CUDA_OK(cudaMemset(m->d_err, 0, sizeof(int)));
     *out = m.release();
@@ -626,7 +655,7 @@ void mmf_model_destroy(MmfModel* model) {
 }
 
 int64_t mmf_launch_count(const MmfModel* model) {
-    return model ? model->launches + epic_launches(model->epic) : 0;
+    return model ? model->launches + epic_launches(model->epic) + tftile_launches(model->tile) : 0;
 }
 
 int mmf_profile_enable(MmfModel* m, int32_t on) {
@@ -669,22 +698,35 @@ int mmf_encoder_forward(MmfModel* m, const float* x, const int64_t* k, const int
     MMF_CUDA_OK(cudaStreamSynchronize(s));
     if (m->desc.arch == MMF_ARCH_EPIC) return epic_forward(m->epic, x, hmask.data(), ht.data(), B, D, vt_out, s);
     MMF_REQUIRE(k && logits_out, "the transformers need tokens and a logits buffer");
-    Plan plan;
-    MMF_TRY(build_plan(hmask.data(), B, D, &plan));
-    MMF_TRY(ensure_workspace(m, plan.rows, B * D, B, static_cast<int>(plan.items.size())));
-    MMF_TRY(upload_plan(m, plan, s));
-    MMF_TRY(upload_time_tables(m, ht.data(), B, s));
-    Workspace& w = m->ws;
-    { LaunchScope sc(m, KC_PACK, s); MMF_TRY(launch_pack(x, reinterpret_cast<const long long*>(k), w.row_slot, plan.rows, m->desc.vocab_size, w.xs, w.ks, m->d_err, s)); }
     const size_t slots = static_cast<size_t>(B) * D;
     MMF_CUDA_OK(cudaMemsetAsync(vt_out, 0, slots * 3 * 4, s));
     MMF_CUDA_OK(cudaMemsetAsync(logits_out, 0, slots * m->desc.vocab_size * 4, s));
-    ForwardCtx c{};
-    c.rows = plan.rows; c.n_items = static_cast<int>(plan.items.size());
-    c.temb = w.temb; c.temb2 = w.temb2; c.row_jet = w.row_jet; c.stream = s;
-    c.head.vt_out = vt_out; c.head.logits_out = logits_out; c.head.do_step = 0;
-    c.head.sl.sp.vocab = m->desc.vocab_size;
-    MMF_TRY(run_forward(m, c));
+    if (m->tile) {
+        std::vector<unsigned char> handled;
+        TfRunArgs ta{};
+        ta.x0 = x; ta.k0 = reinterpret_cast<const long long*>(k); ta.mask_host = hmask.data(); ta.B = B; ta.D = D;
+        ta.times = ht.data(); ta.n_times = B; ta.per_jet_time = true; ta.nsteps = 1; ta.vt_out = vt_out; ta.logits_out = logits_out;
+        ta.err_flag = m->d_err;
+        MMF_TRY(tftile_prepare(m->tile, ta, &handled, s));
+        MMF_TRY(tftile_launch(m->tile, s));
+        for (int b = 0; b < B; ++b)
+            if (handled[b]) std::fill(hmask.begin() + static_cast<size_t>(b) * D, hmask.begin() + static_cast<size_t>(b + 1) * D, 0);
+    }
+    Plan plan;
+    MMF_TRY(build_plan(hmask.data(), B, D, &plan));
+    if (plan.rows > 0) {
+        MMF_TRY(ensure_workspace(m, plan.rows, B * D, B, static_cast<int>(plan.items.size())));
+        MMF_TRY(upload_plan(m, plan, s));
+        MMF_TRY(upload_time_tables(m, ht.data(), B, s));
+        Workspace& w = m->ws;
+        { LaunchScope sc(m, KC_PACK, s); MMF_TRY(launch_pack(x, reinterpret_cast<const long long*>(k), w.row_slot, plan.rows, m->desc.vocab_size, w.xs, w.ks, m->d_err, s)); }
+        ForwardCtx c{};
+        c.rows = plan.rows; c.n_items = static_cast<int>(plan.items.size());
+        c.temb = w.temb; c.temb2 = w.temb2; c.row_jet = w.row_jet; c.stream = s;
+        c.head.vt_out = vt_out; c.head.logits_out = logits_out; c.head.do_step = 0;
+        c.head.sl.sp.vocab = m->desc.vocab_size;
+        MMF_TRY(run_forward(m, c));
+    }
     return check_device_flags(m, s);
 }
 

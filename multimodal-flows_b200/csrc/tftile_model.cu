@@ -1,0 +1,471 @@
+// Host side of the persistent transformer tile kernel: builds, once per checkpoint, the per-timestep op table,
+// the weight stream in consumption order and the parameter blobs; plans tiles of whole jets; launches.
+// The op sequence below MUST mirror the epilogue program in kernels_tftile.cu stage by stage.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+
+#include "mmf_simt.h"
+#include "mmf_tftile.h"
+
+namespace mmf {
+
+struct TfTileModel {
+    MmfModelDesc desc{};
+    DeviceArena arena;
+    const TfOp* d_ops = nullptr;
+    int n_ops = 0;
+    const uint8_t* d_wstream = nullptr;
+    const float* d_params = nullptr;
+    std::vector<float> time_expand_w, time_expand_b;     // ParticleFormer, host fp32
+    // workspace
+    int tile_cap = 0, tb_cap = 0;
+    uint8_t* ws = nullptr;
+    TfTileMeta* d_meta = nullptr;
+    float *d_xs0 = nullptr, *d_skip = nullptr, *d_temb = nullptr, *d_thermo = nullptr;
+    int *d_ks0 = nullptr, *d_row_slot = nullptr;
+    int64_t launches = 0;
+    TfLaunch pending{};                                  // prepared by tftile_prepare, consumed by tftile_launch
+    int pending_tiles = 0;
+    ~TfTileModel() {
+        arena.release();
+        if (ws) cudaFree(ws);
+    }
+};
+
+namespace {
+
+// operand arena offsets: keep in sync with kernels_tftile.cu
+constexpr uint32_t kT = 16384, oA = 0, oQ = 65536, oK = oQ + kT, oVT = oK + kT, oO = oVT + kT, oH0 = oQ, oH1 = oVT;
+
+struct Builder {
+    std::vector<TfOp> ops;
+    std::vector<uint16_t> stream;
+    std::vector<float> params;
+    int stage = 0;                                   // blobs emitted so far
+
+    void param_op(int blob) {
+        TfOp o{};
+        o.a_off = static_cast<uint32_t>(blob) * kTfParamFloats * 4;
+        o.b_off = kTfParam;
+        o.n = kTfParamFloats * 4 / 16;
+        ops.push_back(o);
+    }
+    // rows[i] = pointer to the start of a weight row (fp32, K-contiguous); k0 = first input column of this k-tile
+    void ring_op(uint32_t a_off, const std::vector<const float*>& rows, int k0, uint16_t dcol, int acc, int wait, int signal) {
+        const int n = static_cast<int>(rows.size());
+        const size_t base = stream.size();
+        stream.resize(base + static_cast<size_t>(n) * 64);
+        for (int rr = 0; rr < n; ++rr)
+            for (int e = 0; e < 64; ++e)
+                stream[base + static_cast<size_t>(rr) * 64 + (((e >> 3) ^ (rr & 7)) << 3) + (e & 7)] = f32_to_bf16_bits(rows[rr][k0 + e]);
+        TfOp o{};
+        o.a_off = a_off; o.b_off = kTfRing; o.n = static_cast<uint16_t>(n); o.dcol = dcol; o.nk16 = 4;
+        o.acc = static_cast<uint8_t>(acc); o.wait = static_cast<uint8_t>(wait); o.signal = static_cast<uint8_t>(signal);
+        ops.push_back(o);
+    }
+    void smem_op(uint32_t a_off, uint32_t b_off, int n, uint16_t dcol, int nk16, int acc, int wait, int signal) {
+        TfOp o{};
+        o.a_off = a_off; o.b_off = b_off; o.n = static_cast<uint16_t>(n); o.dcol = dcol; o.nk16 = static_cast<uint8_t>(nk16);
+        o.acc = static_cast<uint8_t>(acc); o.wait = static_cast<uint8_t>(wait); o.signal = static_cast<uint8_t>(signal);
+        ops.push_back(o);
+    }
+    float* blob(int idx) {
+        if (params.size() < static_cast<size_t>(idx + 1) * kTfParamFloats) params.resize(static_cast<size_t>(idx + 1) * kTfParamFloats, 0.f);
+        return params.data() + static_cast<size_t>(idx) * kTfParamFloats;
+    }
+};
+
+struct Mat {                                         // fp32 [rows][cols] copy of a checkpoint matrix
+    std::vector<float> w;
+    int rows = 0, cols = 0;
+    const float* row(int r) const { return w.data() + static_cast<size_t>(r) * cols; }
+};
+Mat mat(WeightMap& wm, const std::string& name, int rows, int cols) {
+    Mat m;
+    m.w = wm.get(name, rows, cols);
+    m.rows = rows; m.cols = cols;
+    return m;
+}
+std::vector<const float*> rows_of(const Mat& m, int r0, int n) {
+    std::vector<const float*> v(n);
+    for (int i = 0; i < n; ++i) v[i] = m.row(r0 + i);
+    return v;
+}
+void put(float* dst, const std::vector<float>& src) { std::copy(src.begin(), src.end(), dst); }
+
+float gelu_h(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+struct BlockW { Mat attn, proj, fc, p2; };
+BlockW load_block(WeightMap& wm, const std::string& p, int C, int I) {
+    return BlockW{mat(wm, p + ".attn.c_attn.weight", 3 * C, C), mat(wm, p + ".attn.c_proj.weight", C, C),
+                  mat(wm, p + ".ffw.c_fc.weight", I, C), mat(wm, p + ".ffw.c_proj.weight", C, I)};
+}
+
+// MLP of one group: quarters of the hidden layer ping-pong through the two scratch halves
+void emit_mlp(Builder& b, const BlockW& w, int C, int a_chunk0, uint16_t dcol_out, bool first_wait, bool final_signal) {
+    const int kbC = C / 64, nh = C / 128;
+    auto fc = [&](int q) {
+        for (int kb = 0; kb < kbC; ++kb)
+            b.ring_op(oA + (a_chunk0 + kb) * kT, rows_of(w.fc, q * 128, 128), kb * 64, static_cast<uint16_t>(256 + (q & 1) * 128), kb > 0,
+                      first_wait && q == 0 && kb == 0, kb == kbC - 1 ? 1 + (q & 1) : 0);
+    };
+    auto out = [&](int q) {
+        for (int kb = 0; kb < 2; ++kb)
+            for (int h = 0; h < nh; ++h)
+                b.ring_op(((q & 1) ? oH1 : oH0) + kb * kT, rows_of(w.p2, h * 128, 128), q * 128 + kb * 64,
+                          static_cast<uint16_t>(dcol_out + h * 128), 1, kb == 0 && h == 0,
+                          (final_signal && q == 3 && kb == 1 && h == nh - 1) ? 1 : 0);
+    };
+    fc(0); fc(1); out(0); fc(2); out(1); fc(3); out(2); out(3);
+}
+
+}  // namespace
+
+int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
+    *out = nullptr;
+    const bool pf = d.arch == MMF_ARCH_PARTICLEFORMER;
+    const int E = d.n_embd, h = E / 2, I = d.n_inner, V = d.vocab_size;
+    if (!(E == 256 && I == 512 && d.n_head == 4 && V == 9 && d.qk_layernorm)) return 0;     // outside the tile kernel's envelope
+    const std::string t = "transformer.";
+    std::unique_ptr<TfTileModel> m(new TfTileModel());
+    m->desc = d;
+    Builder b;
+    const int n_stream = pf ? d.n_layer : 0, n_main = pf ? d.n_layer_fused : d.n_layer;
+    int blob_idx = 0;
+
+    // ---------------- embedding stage
+    {
+        float* P = b.blob(blob_idx);
+        const std::vector<float> w0 = wm.get(t + "wxe.0.weight", E, 3), b0 = wm.get(t + "wxe.0.bias", E);
+        for (int c = 0; c < E; ++c) { P[tfp::E_W0 + c * 4] = w0[c * 3]; P[tfp::E_W0 + c * 4 + 1] = w0[c * 3 + 1]; P[tfp::E_W0 + c * 4 + 2] = w0[c * 3 + 2]; P[tfp::E_W0 + c * 4 + 3] = b0[c]; }
+        put(P + tfp::E_BXE2, wm.get(t + "wxe.2.bias", h));
+        put(P + tfp::E_LN1X_G, wm.get(t + "ln1_x.weight", h));
+        put(P + tfp::E_LN1X_B, wm.get(t + "ln1_x.bias", h, -1, true));
+        // discrete embedding branch folded into a V x 128 table (reference ParticleTransformers.py:95-96, 190-191)
+        const std::vector<float> emb = wm.get(t + "wye.0.weight", V, E), w2 = wm.get(t + "wye.2.weight", h, E), b2 = wm.get(t + "wye.2.bias", h),
+                                 g = wm.get(t + "ln1_y.weight", h), bb = wm.get(t + "ln1_y.bias", h, -1, true);
+        for (int k = 0; k < V; ++k) {
+            std::vector<double> row(h);
+            for (int o = 0; o < h; ++o) {
+                double acc = b2[o];
+                for (int i = 0; i < E; ++i) acc += static_cast<double>(gelu_h(emb[static_cast<size_t>(k) * E + i])) * w2[static_cast<size_t>(o) * E + i];
+                row[o] = static_cast<float>(acc);
+            }
+            double s = 0, q = 0;
+            for (int o = 0; o < h; ++o) s += row[o];
+            const double mean = s / h;
+            for (int o = 0; o < h; ++o) q += (row[o] - mean) * (row[o] - mean);
+            const double rstd = 1.0 / std::sqrt(q / h + 1e-5);
+            for (int o = 0; o < h; ++o) P[tfp::E_YTAB + k * 128 + o] = static_cast<float>((row[o] - mean) * rstd) * g[o] + bb[o];
+        }
+        if (pf) {
+            put(P + tfp::E_LNN_G, wm.get(t + "blocks_x.0.ln1.weight", h)); put(P + tfp::E_LNN_G + 128, wm.get(t + "blocks_y.0.ln1.weight", h));
+            put(P + tfp::E_LNN_B, wm.get(t + "blocks_x.0.ln1.bias", h, -1, true)); put(P + tfp::E_LNN_B + 128, wm.get(t + "blocks_y.0.ln1.bias", h, -1, true));
+        } else {
+            put(P + tfp::E_LNN_G, wm.get(t + "blocks.0.ln1.weight", E)); put(P + tfp::E_LNN_B, wm.get(t + "blocks.0.ln1.bias", E, -1, true));
+        }
+        b.param_op(blob_idx++);
+        const Mat wxe2 = mat(wm, t + "wxe.2.weight", h, E);
+        for (int kb = 0; kb < 4; ++kb) b.ring_op(oA + kb * kT, rows_of(wxe2, 0, 128), kb * 64, 256, kb > 0, kb == 0, kb == 3 ? 1 : 0);
+        b.param_op(blob_idx);                            // first block, prefetched
+    }
+
+    // ---------------- stream blocks (ParticleFormer): groups x | y, C = 128, head size 32, units = head pairs
+    for (int i = 0; i < n_stream; ++i) {
+        float* P = b.blob(blob_idx);
+        const std::string px[2] = {t + "blocks_x." + std::to_string(i), t + "blocks_y." + std::to_string(i)};
+        BlockW w[2] = {load_block(wm, px[0], h, I), load_block(wm, px[1], h, I)};
+        for (int g = 0; g < 2; ++g) {
+            float* G = P + g * tfp::S_GROUP;
+            put(G + tfp::S_BQKV, wm.get(px[g] + ".attn.c_attn.bias", 3 * h, -1, true));
+            put(G + tfp::S_QG, wm.get(px[g] + ".attn.q_layernorm.weight", 32)); put(G + tfp::S_QB, wm.get(px[g] + ".attn.q_layernorm.bias", 32, -1, true));
+            put(G + tfp::S_KG, wm.get(px[g] + ".attn.k_layernorm.weight", 32)); put(G + tfp::S_KB, wm.get(px[g] + ".attn.k_layernorm.bias", 32, -1, true));
+            put(G + tfp::S_BPROJ, wm.get(px[g] + ".attn.c_proj.bias", h, -1, true));
+            put(G + tfp::S_LN2G, wm.get(px[g] + ".ln2.weight", h)); put(G + tfp::S_LN2B, wm.get(px[g] + ".ln2.bias", h, -1, true));
+            put(G + tfp::S_BFC, wm.get(px[g] + ".ffw.c_fc.bias", I, -1, true));
+            put(G + tfp::S_BP2, wm.get(px[g] + ".ffw.c_proj.bias", h, -1, true));
+        }
+        const bool last = i + 1 == n_stream;
+        const std::string nx = last ? t + "ln2_x" : t + "blocks_x." + std::to_string(i + 1) + ".ln1";
+        const std::string ny = last ? t + "ln2_y" : t + "blocks_y." + std::to_string(i + 1) + ".ln1";
+        put(P + tfp::S_LNN_G, wm.get(nx + ".weight", h)); put(P + tfp::S_LNN_G + 128, wm.get(ny + ".weight", h));
+        put(P + tfp::S_LNN_B, wm.get(nx + ".bias", h, -1, true)); put(P + tfp::S_LNN_B + 128, wm.get(ny + ".bias", h, -1, true));
+        if (last) {
+            put(P + tfp::S_LN2ND_G, wm.get(t + "blocks_fuse.0.ln1.weight", E)); put(P + tfp::S_LN2ND_B, wm.get(t + "blocks_fuse.0.ln1.bias", E, -1, true));
+        }
+        ++blob_idx;
+        for (int g = 0; g < 2; ++g)
+            for (int u = 0; u < 2; ++u) {
+                // rows of c_attn: q [0,128) k [128,256) v [256,384); unit u = heads 2u, 2u+1 = columns u*64..u*64+63
+                std::vector<const float*> qk = rows_of(w[g].attn, u * 64, 64), kk = rows_of(w[g].attn, 128 + u * 64, 64);
+                qk.insert(qk.end(), kk.begin(), kk.end());
+                for (int kb = 0; kb < 2; ++kb) {
+                    b.ring_op(oA + (2 * g + kb) * kT, qk, kb * 64, 256, kb > 0, g == 0 && u == 0 && kb == 0, 0);
+                    b.ring_op(oA + (2 * g + kb) * kT, rows_of(w[g].attn, 256 + u * 64, 64), kb * 64, 384, kb > 0, 0, kb == 1 ? 1 : 0);
+                }
+                b.smem_op(oQ, oK, 128, 256, 2, 0, 1, 0);                     // S of head 0 of the pair
+                b.smem_op(oQ + 64, oK + 64, 128, 384, 2, 0, 0, 1);           // S of head 1
+                b.smem_op(oQ, oVT, 32, 256, 4, 0, 1, 0);                     // O_h0 = P_h0 V_h0, keys 0..63
+                b.smem_op(oK, oVT + 8192, 32, 256, 4, 1, 0, 2);              //                   keys 64..127
+                b.smem_op(oQ, oVT + 4096, 32, 288, 4, 0, 1, 0);              // O_h1
+                b.smem_op(oK, oVT + 8192 + 4096, 32, 288, 4, 1, 0, 1);
+                b.ring_op(oO, rows_of(w[g].proj, 0, 128), u * 64, static_cast<uint16_t>(g * 128), 1, 1, (g == 1 && u == 1) ? 1 : 0);
+            }
+        b.param_op(blob_idx);                            // next stage, prefetched
+        for (int g = 0; g < 2; ++g) emit_mlp(b, w[g], 128, 2 * g, static_cast<uint16_t>(g * 128), g == 0, g == 1);
+    }
+
+    // ---------------- main blocks: C = 256, head size 64, units = heads
+    for (int j = 0; j < n_main; ++j) {
+        float* P = b.blob(blob_idx);
+        const std::string p = t + (pf ? "blocks_fuse." : "blocks.") + std::to_string(j);
+        const BlockW w = load_block(wm, p, E, I);
+        put(P + tfp::B_BQKV, wm.get(p + ".attn.c_attn.bias", 3 * E, -1, true));
+        put(P + tfp::B_QG, wm.get(p + ".attn.q_layernorm.weight", 64)); put(P + tfp::B_QB, wm.get(p + ".attn.q_layernorm.bias", 64, -1, true));
+        put(P + tfp::B_KG, wm.get(p + ".attn.k_layernorm.weight", 64)); put(P + tfp::B_KB, wm.get(p + ".attn.k_layernorm.bias", 64, -1, true));
+        put(P + tfp::B_BPROJ, wm.get(p + ".attn.c_proj.bias", E, -1, true));
+        put(P + tfp::B_LN2G, wm.get(p + ".ln2.weight", E)); put(P + tfp::B_LN2B, wm.get(p + ".ln2.bias", E, -1, true));
+        put(P + tfp::B_BFC, wm.get(p + ".ffw.c_fc.bias", I, -1, true));
+        put(P + tfp::B_BP2, wm.get(p + ".ffw.c_proj.bias", E, -1, true));
+        const bool last = j + 1 == n_main;
+        if (!last) {
+            const std::string nx = t + (pf ? "blocks_fuse." : "blocks.") + std::to_string(j + 1) + ".ln1";
+            put(P + tfp::B_LNN_G, wm.get(nx + ".weight", E)); put(P + tfp::B_LNN_B, wm.get(nx + ".bias", E, -1, true));
+        } else if (pf) {
+            put(P + tfp::B_LNN_G, wm.get(t + "ln3_x.weight", h)); put(P + tfp::B_LNN_G + 128, wm.get(t + "ln3_y.weight", h));
+            put(P + tfp::B_LNN_B, wm.get(t + "ln3_x.bias", h, -1, true)); put(P + tfp::B_LNN_B + 128, wm.get(t + "ln3_y.bias", h, -1, true));
+        } else {
+            put(P + tfp::B_LNN_G, wm.get(t + "ln2.weight", E)); put(P + tfp::B_LNN_B, wm.get(t + "ln2.bias", E, -1, true));
+        }
+        ++blob_idx;
+        for (int u = 0; u < 4; ++u) {
+            std::vector<const float*> qk = rows_of(w.attn, u * 64, 64), kk = rows_of(w.attn, 256 + u * 64, 64);
+            qk.insert(qk.end(), kk.begin(), kk.end());
+            for (int kb = 0; kb < 4; ++kb) {
+                b.ring_op(oA + kb * kT, qk, kb * 64, 256, kb > 0, u == 0 && kb == 0, 0);
+                b.ring_op(oA + kb * kT, rows_of(w.attn, 512 + u * 64, 64), kb * 64, 384, kb > 0, 0, kb == 3 ? 1 : 0);
+            }
+            b.smem_op(oQ, oK, 128, 256, 4, 0, 1, 1);                         // S = Q K^T
+            b.smem_op(oQ, oVT, 64, 448, 4, 0, 1, 0);                         // O = P V
+            b.smem_op(oK, oVT + 8192, 64, 448, 4, 1, 0, 1);
+            for (int nh = 0; nh < 2; ++nh)
+                b.ring_op(oO, rows_of(w.proj, nh * 128, 128), u * 64, static_cast<uint16_t>(nh * 128), 1, nh == 0, (u == 3 && nh == 1) ? 1 : 0);
+        }
+        b.param_op(blob_idx);
+        emit_mlp(b, w, 256, 0, 0, true, true);
+    }
+
+    // ---------------- heads: Linear(128,512) + GELU on tensor cores, Linear(512, 3 | V) on CUDA cores
+    {
+        const Mat hx = mat(wm, t + "head_x.0.weight", I, h), hy = mat(wm, t + "head_y.0.weight", I, h);
+        const std::vector<float> bx0 = wm.get(t + "head_x.0.bias", I), by0 = wm.get(t + "head_y.0.bias", I),
+                                 wx2 = wm.get(t + "head_x.2.weight", 3, I), bx2 = wm.get(t + "head_x.2.bias", 3),
+                                 wy2 = wm.get(t + "head_y.2.weight", V, I), by2 = wm.get(t + "head_y.2.bias", V);
+        float* P = b.blob(blob_idx);
+        put(P + tfp::HX_BIAS, bx0); put(P + tfp::HX_W2, wx2); put(P + tfp::HX_B2, bx2);
+        for (int half = 0; half < 2; ++half) {
+            float* Q = b.blob(blob_idx + 1 + half);
+            for (int i = 0; i < 256; ++i) Q[tfp::HY_BIAS + i] = by0[half * 256 + i];
+            for (int v = 0; v < V; ++v)
+                for (int i = 0; i < 256; ++i) Q[tfp::HY_W2 + v * 256 + i] = wy2[static_cast<size_t>(v) * I + half * 256 + i];
+            if (half == 0) for (int v = 0; v < V; ++v) Q[tfp::HY_B2 + v] = by2[v];
+        }
+        for (int hq = 0; hq < 8; ++hq) {
+            const Mat& w = hq < 4 ? hx : hy;
+            const int chunk0 = hq < 4 ? 0 : 2;
+            for (int kb = 0; kb < 2; ++kb)
+                b.ring_op(oA + (chunk0 + kb) * kT, rows_of(w, (hq & 3) * 128, 128), kb * 64, static_cast<uint16_t>(256 + (hq & 1) * 128), kb > 0,
+                          kb == 0 && hq != 1, kb == 1 ? 1 + (hq & 1) : 0);
+            if (hq == 0) b.param_op(blob_idx + 1);
+            if (hq == 4) b.param_op(blob_idx + 2);
+        }
+        blob_idx += 3;
+    }
+    if (!wm.missing.empty()) { set_last_error(wm.missing); return 2; }
+    if (pf) {
+        m->time_expand_w = wm.get(t + "time_expand.weight", E, h);
+        m->time_expand_b = wm.get(t + "time_expand.bias", E);
+    }
+    b.params.resize(static_cast<size_t>(blob_idx) * kTfParamFloats, 0.f);
+
+    DeviceArena& ar = m->arena;
+    const size_t o_ops = ar.reserve(b.ops.size() * sizeof(TfOp));
+    memcpy(ar.staging.data() + o_ops, b.ops.data(), b.ops.size() * sizeof(TfOp));
+    const size_t o_stream = ar.reserve(b.stream.size() * 2);
+    memcpy(ar.staging.data() + o_stream, b.stream.data(), b.stream.size() * 2);
+    const size_t o_params = ar.put_f32(b.params);
+    if (ar.upload() != 0) return 1;
+    m->d_ops = ar.at<TfOp>(o_ops);
+    m->n_ops = static_cast<int>(b.ops.size());
+    m->d_wstream = ar.at<uint8_t>(o_stream);
+    m->d_params = ar.at<float>(o_params);
+    *out = m.release();
+    return 0;
+}
+
+void tftile_destroy(TfTileModel* m) { delete m; }
+int64_t tftile_launches(const TfTileModel* m) { return m ? m->launches : 0; }
+
+namespace {
+
+struct TilePlan {
+    std::vector<TfTileMeta> meta;
+    std::vector<int> row_slot;
+};
+
+void plan_tiles(const int64_t* mask, int B, int D, bool per_jet_time, TilePlan* p, std::vector<unsigned char>* handled) {
+    std::vector<int> n(B, 0);
+    for (int b = 0; b < B; ++b)
+        for (int d = 0; d < D; ++d) n[b] += mask[static_cast<size_t>(b) * D + d] != 0;
+    std::vector<int> order(B);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n[a] > n[b]; });
+    struct Bin { int rows = 0; std::vector<int> jets; };
+    std::vector<Bin> bins;
+    // best-fit decreasing with an index of open bins by free space (128 buckets): O(B * 128)
+    std::vector<std::vector<int>> by_free(129);
+    handled->assign(B, 0);
+    for (int b : order) {
+        if (n[b] == 0) { (*handled)[b] = 1; continue; }            // nothing to generate
+        if (n[b] > 128) continue;                                    // handled by the layered path
+        (*handled)[b] = 1;
+        int pick = -1;
+        for (int f = n[b]; f <= 128 && pick < 0; ++f)
+            if (!by_free[f].empty()) { pick = by_free[f].back(); by_free[f].pop_back(); }
+        if (pick < 0) { bins.emplace_back(); pick = static_cast<int>(bins.size()) - 1; }
+        bins[pick].rows += n[b];
+        bins[pick].jets.push_back(b);
+        by_free[128 - bins[pick].rows].push_back(pick);
+    }
+    p->meta.clear();
+    p->row_slot.clear();
+    for (const Bin& bin : bins) {
+        TfTileMeta m{};
+        std::vector<int> slots;
+        for (int b : bin.jets) {
+            const int beg = static_cast<int>(slots.size());
+            for (int d = 0; d < D; ++d)
+                if (mask[static_cast<size_t>(b) * D + d] != 0) slots.push_back(b * D + d);
+            const int end = static_cast<int>(slots.size());
+            for (int r = beg; r < end; ++r) {
+                m.seg_beg[r] = static_cast<unsigned char>(beg);
+                m.seg_end[r] = static_cast<unsigned char>(end);
+                m.row_tb[r] = per_jet_time ? b : 0;
+            }
+        }
+        m.nrows = static_cast<int>(slots.size());
+        slots.resize(128, -1);
+        p->meta.push_back(m);
+        p->row_slot.insert(p->row_slot.end(), slots.begin(), slots.end());
+    }
+}
+
+int ensure_ws(TfTileModel* m, int tiles, int tb) {
+    if (tiles <= m->tile_cap && tb <= m->tb_cap) return 0;
+    const int tc = std::max(m->tile_cap, std::max(tiles, 1)), bc = std::max(m->tb_cap, std::max(tb, 1));
+    if (m->ws) { MMF_CUDA_OK(cudaDeviceSynchronize()); MMF_CUDA_OK(cudaFree(m->ws)); m->ws = nullptr; }
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
+    const size_t rows = static_cast<size_t>(tc) * 128;
+    const size_t o_meta = take(static_cast<size_t>(tc) * sizeof(TfTileMeta)), o_xs = take(rows * 3 * 4), o_ks = take(rows * 4),
+                 o_slot = take(rows * 4), o_skip = take(rows * 256 * 4), o_temb = take(static_cast<size_t>(bc) * 512 * 4),
+                 o_th = take(static_cast<size_t>(bc) * 2 * 4);
+    MMF_CUDA_OK(cudaMalloc(&m->ws, off));
+    m->tile_cap = tc; m->tb_cap = bc;
+    m->d_meta = reinterpret_cast<TfTileMeta*>(m->ws + o_meta);
+    m->d_xs0 = reinterpret_cast<float*>(m->ws + o_xs);
+    m->d_ks0 = reinterpret_cast<int*>(m->ws + o_ks);
+    m->d_row_slot = reinterpret_cast<int*>(m->ws + o_slot);
+    m->d_skip = reinterpret_cast<float*>(m->ws + o_skip);
+    m->d_temb = reinterpret_cast<float*>(m->ws + o_temb);
+    m->d_thermo = reinterpret_cast<float*>(m->ws + o_th);
+    return 0;
+}
+
+}  // namespace
+
+int tftile_prepare(TfTileModel* m, const TfRunArgs& r, std::vector<unsigned char>* handled, cudaStream_t s) {
+    const MmfModelDesc& d = m->desc;
+    const bool pf = d.arch == MMF_ARCH_PARTICLEFORMER;
+    TilePlan plan;
+    plan_tiles(r.mask_host, r.B, r.D, r.per_jet_time, &plan, handled);
+    const int tiles = static_cast<int>(plan.meta.size());
+    m->pending_tiles = tiles;
+    if (tiles == 0) return 0;
+    MMF_TRY_RC(ensure_ws(m, tiles, r.n_times));
+    // time tables: sin/cos features (reference utils/models.py:62-75) and, for ParticleFormer, time_expand(temb)
+    std::vector<float> temb(static_cast<size_t>(r.n_times) * 512, 0.f), thermo(static_cast<size_t>(r.n_times) * 2, 0.f);
+    for (int i = 0; i < r.n_times; ++i) {
+        float* row = &temb[static_cast<size_t>(i) * 512];
+        if (pf) {
+            sincos_row(r.times[i], 128, row);
+            memcpy(row + 128, row, 128 * sizeof(float));
+            for (int o = 0; o < 256; ++o) {
+                float acc = 0.f;
+                const float* wrow = &m->time_expand_w[static_cast<size_t>(o) * 128];
+                for (int j = 0; j < 128; ++j) acc += wrow[j] * row[j];
+                row[256 + o] = acc + m->time_expand_b[o];
+            }
+        } else {
+            sincos_row(r.times[i], 256, row);
+        }
+        if (r.opts) det_thermostat(r.times[i], r.opts->beta, d.vocab_size, &thermo[i * 2], &thermo[i * 2 + 1]);
+    }
+    MMF_CUDA_OK(cudaMemcpyAsync(m->d_temb, temb.data(), temb.size() * 4, cudaMemcpyHostToDevice, s));
+    MMF_CUDA_OK(cudaMemcpyAsync(m->d_thermo, thermo.data(), thermo.size() * 4, cudaMemcpyHostToDevice, s));
+    MMF_CUDA_OK(cudaMemcpyAsync(m->d_meta, plan.meta.data(), plan.meta.size() * sizeof(TfTileMeta), cudaMemcpyHostToDevice, s));
+    MMF_CUDA_OK(cudaMemcpyAsync(m->d_row_slot, plan.row_slot.data(), plan.row_slot.size() * 4, cudaMemcpyHostToDevice, s));
+    MMF_CUDA_OK(cudaStreamSynchronize(s));
+    MMF_TRY_RC(launch_pack(r.x0, r.k0, m->d_row_slot, tiles * 128, d.vocab_size, m->d_xs0, m->d_ks0, r.err_flag, s));
+    m->launches += 1;
+
+    TfLaunch a{};
+    a.arch = d.arch; a.n_stream = pf ? d.n_layer : 0; a.n_main = pf ? d.n_layer_fused : d.n_layer; a.vocab = d.vocab_size;
+    a.ops = m->d_ops; a.n_ops = m->n_ops; a.wstream = m->d_wstream; a.params = m->d_params; a.meta = m->d_meta; a.tile0 = 0;
+    a.xs0 = m->d_xs0; a.ks0 = m->d_ks0; a.row_slot = m->d_row_slot; a.skip = m->d_skip; a.temb = m->d_temb;
+    a.per_jet_time = r.per_jet_time ? 1 : 0; a.nsteps = r.nsteps;
+    if (r.opts) {
+        a.st.sp = StepParams{r.opts->temperature, r.dt, r.opts->beta, r.opts->top_p, r.opts->top_k, d.vocab_size};
+        a.st.seed = r.opts->seed;
+        a.st.slot0 = r.opts->first_global_jet * static_cast<uint64_t>(r.D);
+        a.st.argmax_last = r.opts->use_final_max_rates ? 1 : 0;
+    }
+    a.st.u = r.u; a.st.forced = r.forced; a.st.thermo = m->d_thermo; a.st.rates_out = r.rates_out; a.st.err_flag = r.err_flag;
+    a.st.slots = static_cast<long long>(r.B) * r.D;
+    a.x_out = r.x_out; a.k_out = r.k_out; a.vt_out = r.vt_out; a.logits_out = r.logits_out;
+    m->pending = a;
+    return 0;
+}
+
+int tftile_launch(TfTileModel* m, cudaStream_t s) {
+    const int tiles = m->pending_tiles;
+    if (tiles == 0) return 0;
+    TfLaunch a = m->pending;
+    const char* trace_path = getenv("MMF_TRACE");
+    unsigned long long* d_trace = nullptr;
+    if (trace_path) {
+        MMF_CUDA_OK(cudaMalloc(&d_trace, 512 * 8));
+        MMF_CUDA_OK(cudaMemsetAsync(d_trace, 0, 512 * 8, s));
+        a.trace = d_trace;
+    }
+    MMF_TRY_RC(launch_tf_tiles(a, tiles, s));
+    m->launches += 1;
+    if (d_trace) {
+        std::vector<unsigned long long> hbuf(512);
+        MMF_CUDA_OK(cudaMemcpyAsync(hbuf.data(), d_trace, 512 * 8, cudaMemcpyDeviceToHost, s));
+        MMF_CUDA_OK(cudaStreamSynchronize(s));
+        cudaFree(d_trace);
+        if (FILE* f = fopen(trace_path, "w")) {
+            for (int st = 0; st < 2; ++st)
+                for (int i = 0; i < 256 && hbuf[st * 256 + i]; ++i)
+                    fprintf(f, "step %d mark %2d  +%llu cycles (total %llu)\n", st, i, i ? hbuf[st * 256 + i] - hbuf[st * 256 + i - 1] : 0ull,
+                            hbuf[st * 256 + i] - hbuf[st * 256]);
+            fclose(f);
+        }
+    }
+    return 0;
+}
+
+}  // namespace mmf
