@@ -265,12 +265,13 @@ __device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, float sc
     tmem_ld32(e.taddr + scol + e.hf * 64, s);
     tmem_ld32(e.taddr + scol + e.hf * 64 + 32, s + 32);
     tmem_ld_wait();
-    const int k0 = e.hf * 64;
+    // keys outside the row's jet get -inf: they drop out of the max and ex2(-inf) = 0 removes them from the sum
+    const int lo = kb - e.hf * 64, hi = ke - e.hf * 64;
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 64; ++j) {
-        const int key = k0 + j;
-        if (key >= kb && key < ke) mx = fmaxf(mx, s[j]);
+        s[j] = (j >= lo && j < hi) ? s[j] : -INFINITY;
+        mx = fmaxf(mx, s[j]);
     }
     float* red = e.misc + mRed;
     red[e.hf * 128 + e.r] = mx;
@@ -280,8 +281,7 @@ __device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, float sc
     float sum = 0.f;
 #pragma unroll
     for (int j = 0; j < 64; ++j) {
-        const int key = k0 + j;
-        const float p = (key >= kb && key < ke) ? exp2f(fmaf(s[j], scale_log2e, -msc)) : 0.f;
+        const float p = ex2_approx(fmaf(s[j], scale_log2e, -msc));
         s[j] = p;
         sum += p;
     }
@@ -293,7 +293,7 @@ __device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, float sc
 template <int HS>
 __device__ __forceinline__ void o_epilogue(Epi& e, uint32_t ocol, int ucol) {
     const float tot = e.misc[mSum + e.r] + e.misc[mSum + 128 + e.r];
-    const float inv = 1.0f / (tot > 0.f ? tot : 1.f);
+    const float inv = rcp_approx(tot > 0.f ? tot : 1.f);
     constexpr int W = HS / 2;
     float o[W];
     if (W == 32) tmem_ld32(e.taddr + ocol + e.hf * W, o);
@@ -393,8 +393,12 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) 
     const int tile = a.tile0 + blockIdx.x;
     const TfTileMeta* meta = a.meta + tile;
 
+    // CTAs of a cluster run the same op sequence on different tiles and share every weight tile: each loads 1/cs of it
+    // and multicasts the slice to all of them, so a ring stage is free only when all cs MMA issuers released it.
+    const uint32_t cs = cluster_nctarank(), crank = cluster_ctarank();
+    const uint16_t cmask = static_cast<uint16_t>((1u << cs) - 1u);
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], cs); }
         mbar_init(&bars->done[0], 1);
         mbar_init(&bars->done[1], 1);
         mbar_init(&bars->go, kEpi);
@@ -408,6 +412,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    cluster_sync_all();                      // every CTA's barriers exist before any multicast copy / remote arrive
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 8) {
@@ -432,7 +437,13 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) 
                         const int s = it % kStages;
                         if (it >= kStages) mbar_wait(&bars->empty[s], ((it / kStages) - 1) & 1);
                         mbar_expect_tx(&bars->full[s], n * 128);
-                        bulk_load_1d(arena + oRing + s * kTile, a.wstream + woff, n * 128, &bars->full[s]);
+                        if (cs == 1) {
+                            bulk_load_1d(arena + oRing + s * kTile, a.wstream + woff, n * 128, &bars->full[s]);
+                        } else {
+                            const uint32_t slice = n * 128 / cs;
+                            bulk_load_1d_multicast(arena + oRing + s * kTile + crank * slice, a.wstream + woff + crank * slice, slice,
+                                                   &bars->full[s], cmask);
+                        }
                         woff += static_cast<size_t>(n) * 128;
                         ++it;
                     }
@@ -473,7 +484,10 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) 
                     const uint32_t idesc = umma_idesc_bf16(128, static_cast<int>(n));
                     for (uint32_t ks = 0; ks < nk16; ++ks)
                         umma_bf16(tmem_base + dcol, da + 2 * ks, db + 2 * ks, idesc, (acc | ks) != 0 ? 1u : 0u);
-                    if (b_off == kTfRing) { umma_commit(&bars->empty[s]); ++it; }
+                    if (b_off == kTfRing) {
+                        if (cs == 1) umma_commit(&bars->empty[s]); else umma_commit_multicast(&bars->empty[s], cmask);
+                        ++it;
+                    }
                     if (sig) umma_commit(&bars->done[sig - 1]);
                 }
             }
@@ -777,6 +791,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) 
 
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                      // no CTA leaves while a peer may still multicast into it
     if (warp == 9) tmem_dealloc(tmem_base, 512);
 }
 
@@ -784,16 +799,28 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) 
 
 int tf_tile_smem_bytes() { return kSmemBytes; }
 
-int launch_tf_tiles(const TfLaunch& a, int n_tiles, cudaStream_t stream) {
+int launch_tf_tiles(const TfLaunch& a, int n_tiles, int cluster, cudaStream_t stream) {
     if (n_tiles == 0) return 0;
     MMF_REQUIRE(a.vocab == 9, "the tile kernel is instantiated for vocab_size 9");
+    MMF_REQUIRE((cluster == 1 || cluster == 2 || cluster == 4) && n_tiles % cluster == 0, "tile launch: bad cluster size");
     static bool configured = false;
     if (!configured) {
         MMF_CUDA_OK(cudaFuncSetAttribute(tf_tile_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         configured = true;
     }
-    tf_tile_kernel<9><<<n_tiles, kThreads, kSmemBytes, stream>>>(a);
-    MMF_CUDA_OK(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_tiles);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MMF_CUDA_OK(cudaLaunchKernelEx(&cfg, tf_tile_kernel<9>, a));
     return 0;
 }
 

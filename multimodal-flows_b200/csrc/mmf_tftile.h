@@ -112,7 +112,8 @@ struct TfLaunch {
 };
 
 int tf_tile_smem_bytes();
-int launch_tf_tiles(const TfLaunch& a, int n_tiles, cudaStream_t stream);
+// n_tiles must be a multiple of `cluster` (1, 2 or 4): the CTAs of a cluster share each weight tile through TMA multicast
+int launch_tf_tiles(const TfLaunch& a, int n_tiles, int cluster, cudaStream_t stream);
 
 // ---- host object (tftile_model.cu)
 struct TfTileModel;

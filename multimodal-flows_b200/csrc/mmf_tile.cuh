@@ -4,15 +4,27 @@
 
 namespace mmf {
 
+// MUFU wrappers: one instruction each, no slow-path branch (arguments here are never denormal / special)
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ float gelu_erf(float x) {
-    // 0.5 x (1 + erf(x / sqrt 2)); erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7), two MUFU ops
+    // 0.5 x (1 + erf(x / sqrt 2)); erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7), two MUFU ops, branch-free
     const float z = fabsf(x) * 0.70710678f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
     p = fmaf(p, t, 0.254829592f);
-    const float e = 1.0f - p * t * exp2f(-1.44269504f * z * z);
+    const float e = fmaf(-p * t, ex2_approx(-1.44269504f * z * z), 1.0f);
     return 0.5f * x * (1.0f + copysignf(e, x));
 }
 

@@ -28,6 +28,7 @@ struct TfTileModel {
     int64_t launches = 0;
     TfLaunch pending{};                                  // prepared by tftile_prepare, consumed by tftile_launch
     int pending_tiles = 0;
+    int cluster = 2;                                     // CTAs sharing one weight stream (MMF_TILE_CLUSTER = 1 | 2 | 4)
     ~TfTileModel() {
         arena.release();
         if (ws) cudaFree(ws);
@@ -301,6 +302,10 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
     m->n_ops = static_cast<int>(b.ops.size());
     m->d_wstream = ar.at<uint8_t>(o_stream);
     m->d_params = ar.at<float>(o_params);
+    if (const char* c = getenv("MMF_TILE_CLUSTER")) {
+        const int v = atoi(c);
+        if (v == 1 || v == 2 || v == 4) m->cluster = v;
+    }
     *out = m.release();
     return 0;
 }
@@ -391,6 +396,13 @@ int tftile_prepare(TfTileModel* m, const TfRunArgs& r, std::vector<unsigned char
     const bool pf = d.arch == MMF_ARCH_PARTICLEFORMER;
     TilePlan plan;
     plan_tiles(r.mask_host, r.B, r.D, r.per_jet_time, &plan, handled);
+    if (!plan.meta.empty()) {                            // pad with empty tiles to a whole number of clusters
+        TfTileMeta empty{};
+        while (plan.meta.size() % m->cluster != 0) {
+            plan.meta.push_back(empty);
+            plan.row_slot.insert(plan.row_slot.end(), 128, -1);
+        }
+    }
     const int tiles = static_cast<int>(plan.meta.size());
     m->pending_tiles = tiles;
     if (tiles == 0) return 0;
@@ -450,7 +462,7 @@ int tftile_launch(TfTileModel* m, cudaStream_t s) {
         MMF_CUDA_OK(cudaMemsetAsync(d_trace, 0, 512 * 8, s));
         a.trace = d_trace;
     }
-    MMF_TRY_RC(launch_tf_tiles(a, tiles, s));
+    MMF_TRY_RC(launch_tf_tiles(a, tiles, m->cluster, s));
     m->launches += 1;
     if (d_trace) {
         std::vector<unsigned long long> hbuf(512);
