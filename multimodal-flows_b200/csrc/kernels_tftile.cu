@@ -16,9 +16,14 @@ namespace mmf {
 namespace {
 
 constexpr int kEpi = 256;
-constexpr int kThreads = 320;
-constexpr int kStages = 3;
+constexpr int kThreads = 384;
+constexpr int kProducers = 3;              // warps 8, 10, 11: issuing one bulk copy costs a warp ~700 cycles, so tiles are dealt round robin
+constexpr int kStages = 4;
 constexpr int kTile = 16384;
+#ifndef MMF_COPY_SPLIT
+#define MMF_COPY_SPLIT 1
+#endif
+constexpr int kCopySplit = MMF_COPY_SPLIT;   // bulk copies per weight-tile slice
 // operand arena (bytes); every region is 1024-byte aligned
 constexpr uint32_t oA = 0;                       // 4 chunks [128 x 64] bf16: LayerNorm output / head input
 constexpr uint32_t oQ = 65536, oK = oQ + kTile;  // Q | K of the current unit; P (probabilities) aliases both
@@ -34,8 +39,10 @@ struct TfBars {
 };
 
 // fp32 scratch after the two parameter buffers (float offsets)
-constexpr int mXs = 0, mKs = mXs + 384, mSeg = mKs + 128, mRowTb = mSeg + 64, mStat = mRowTb + 128, mRed = mStat + 1024,
-              mSum = mRed + 256, mOut = mSum + 256, mTemb = mOut + 128 * 12, mEnd = mTemb + 512;
+// (mOut, the per-row head partial sums, is only live at the very end of a timestep and aliases the LayerNorm / softmax exchange)
+constexpr int mXs = 0, mKs = mXs + 384, mStat = mKs + 128, mRed = mStat + 1024, mSum = mRed + 256, mOut = mStat,
+              mTemb = mSum + 256, mEnd = mTemb + 512;
+static_assert(128 * 12 <= 1024 + 256 + 256, "head partial sums alias the exchange buffers");
 constexpr int kSmemBytes = 1024 + 1024 + kArena + 2 * kTfParamFloats * 4 + mEnd * 4;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
@@ -71,10 +78,12 @@ __device__ __forceinline__ void go(Epi& e) {
     tc_fence_before();
     mbar_arrive(&e.bars->go);
 }
-__device__ __forceinline__ void param_acquire(Epi& e) {
-    const uint32_t p = e.pc & 1;
-    mbar_wait(&e.bars->pfull[p], (e.pc >> 1) & 1);
+// blob `ahead` stages past the oldest one still held (0 or 1: two slots)
+__device__ __forceinline__ const float* param_acquire(Epi& e, uint32_t ahead = 0) {
+    const uint32_t c = e.pc + ahead, p = c & 1;
+    mbar_wait(&e.bars->pfull[p], (c >> 1) & 1);
     e.P = e.pbuf + p * kTfParamFloats;
+    return e.P;
 }
 __device__ __forceinline__ void param_release(Epi& e) {
     mbar_arrive(&e.bars->pempty[e.pc & 1]);
@@ -318,8 +327,8 @@ __device__ __forceinline__ void fc_epilogue(Epi& e, int q, const float* bias) {
 #pragma unroll
     for (int i = 0; i < 64; i += 4) {
         const float4 a = ldf4(bias + e.hf * 64 + i);
-        v[i] = gelu_erf(v[i] + a.x); v[i + 1] = gelu_erf(v[i + 1] + a.y);
-        v[i + 2] = gelu_erf(v[i + 2] + a.z); v[i + 3] = gelu_erf(v[i + 3] + a.w);
+        v[i] = gelu_tile(v[i] + a.x); v[i + 1] = gelu_tile(v[i + 1] + a.y);
+        v[i + 2] = gelu_tile(v[i + 2] + a.z); v[i + 3] = gelu_tile(v[i + 3] + a.w);
     }
     stage_row_bf16(e.arena + ((q & 1) ? oH1 : oH0) + e.hf * kTile, e.r, v);
 }
@@ -335,8 +344,8 @@ __device__ __forceinline__ void head_epilogue(Epi& e, int q, const float* bias, 
 #pragma unroll
     for (int i = 0; i < 64; i += 4) {
         const float4 a = ldf4(bias + e.hf * 64 + i);
-        v[i] = gelu_erf(v[i] + a.x); v[i + 1] = gelu_erf(v[i + 1] + a.y);
-        v[i + 2] = gelu_erf(v[i + 2] + a.z); v[i + 3] = gelu_erf(v[i + 3] + a.w);
+        v[i] = gelu_tile(v[i] + a.x); v[i + 1] = gelu_tile(v[i + 1] + a.y);
+        v[i + 2] = gelu_tile(v[i + 2] + a.z); v[i + 3] = gelu_tile(v[i + 3] + a.w);
     }
 #pragma unroll
     for (int o = 0; o < NO; ++o) {
@@ -381,7 +390,8 @@ __device__ __forceinline__ void attention_unit(Epi& e, const float* bq, const fl
 }
 
 template <int V>
-__global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) {
+__global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_constant__ TfLaunch a, const __grid_constant__ TfOpTable optab,
+                                                              const __grid_constant__ TfProdTable prodtab) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     TfBars* bars = reinterpret_cast<TfBars*>(smem);
@@ -415,81 +425,90 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) 
     cluster_sync_all();                      // every CTA's barriers exist before any multicast copy / remote arrive
     const uint32_t tmem_base = bars->tmem_base;
 
-    if (warp == 8) {
-        // ---------------------------------------------------- producer ----------------------------------------------
-        if (lane == 0) {
-            uint32_t it = 0, pcount = 0;
-            const uint4* ops = reinterpret_cast<const uint4*>(a.ops);
-            for (int step = 0; step < a.nsteps; ++step) {
-                size_t woff = 0;
-                uint4 nxt = __ldg(ops);
-                for (int i = 0; i < a.n_ops; ++i) {
-                    const uint4 raw = nxt;
-                    if (i + 1 < a.n_ops) nxt = __ldg(ops + i + 1);
-                    const uint32_t a_off = raw.x, b_off = raw.y, n = raw.z & 0xffffu;
-                    if (b_off == kTfParam) {
-                        const uint32_t p = pcount & 1;
-                        if (pcount >= 2) mbar_wait(&bars->pempty[p], ((pcount >> 1) - 1) & 1);
-                        mbar_expect_tx(&bars->pfull[p], n * 16);
-                        bulk_load_1d(pbuf + p * kTfParamFloats, reinterpret_cast<const uint8_t*>(a.params) + a_off, n * 16, &bars->pfull[p]);
-                        ++pcount;
-                    } else if (b_off == kTfRing) {
-                        const int s = it % kStages;
-                        if (it >= kStages) mbar_wait(&bars->empty[s], ((it / kStages) - 1) & 1);
-                        mbar_expect_tx(&bars->full[s], n * 128);
-                        if (cs == 1) {
-                            bulk_load_1d(arena + oRing + s * kTile, a.wstream + woff, n * 128, &bars->full[s]);
-                        } else {
-                            const uint32_t slice = n * 128 / cs;
-                            bulk_load_1d_multicast(arena + oRing + s * kTile + crank * slice, a.wstream + woff + crank * slice, slice,
-                                                   &bars->full[s], cmask);
-                        }
-                        woff += static_cast<size_t>(n) * 128;
-                        ++it;
+    // The producer and MMA warps run their loops with all 32 lanes converged (loop state and op fields stay in uniform
+    // registers, the tables sit in the constant bank); one elected lane issues the asynchronous instructions.
+    if (warp == 8 || warp >= 10) {
+        // ---------------------------------------------------- producers ---------------------------------------------
+        const uint32_t pw = warp == 8 ? 0u : static_cast<uint32_t>(warp - 9);      // 0, 1, 2
+        uint32_t it = 0, pcount = 0;
+        for (int step = 0; step < a.nsteps; ++step) {
+            size_t woff = 0;
+            for (int i = 0; i < a.n_prod; ++i) {
+                const uint32_t ent = prodtab.e[i];
+                if (ent & 0x8000u) {                          // parameter blob (ent & 0x7fff) -> slot pcount & 1
+                    if (pw != 0) continue;
+                    const uint32_t p = pcount & 1;
+                    if (pcount >= 2) mbar_wait(&bars->pempty[p], ((pcount >> 1) - 1) & 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&bars->pfull[p], kTfParamFloats * 4);
+                        bulk_load_1d(pbuf + p * kTfParamFloats, a.params + static_cast<size_t>(ent & 0x7fffu) * kTfParamFloats,
+                                     kTfParamFloats * 4, &bars->pfull[p]);
                     }
+                    __syncwarp();
+                    ++pcount;
+                } else {                                      // weight tile of `ent` rows x 64 columns
+                    const uint32_t s = it % kStages, bytes = ent * 128u;
+                    if (it % kProducers != pw) { woff += bytes; ++it; continue; }
+                    if (it >= kStages) mbar_wait(&bars->empty[s], ((it / kStages) - 1) & 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(&bars->full[s], bytes);
+                        // several smaller copies per tile: the copy engine overlaps them (one 16 KB copy takes ~2.5k cycles)
+                        const uint32_t slice = bytes / cs, part = slice / kCopySplit;
+                        uint8_t* dst = arena + oRing + s * kTile + crank * slice;
+                        const uint8_t* src = a.wstream + woff + crank * slice;
+#pragma unroll
+                        for (int c = 0; c < kCopySplit; ++c) {
+                            if (cs == 1) bulk_load_1d(dst + c * part, src + c * part, part, &bars->full[s]);
+                            else bulk_load_1d_multicast(dst + c * part, src + c * part, part, &bars->full[s], cmask);
+                        }
+                    }
+                    __syncwarp();
+                    woff += bytes;
+                    ++it;
                 }
             }
         }
-        __syncwarp();
     } else if (warp == 9) {
         // ---------------------------------------------------- MMA issuer --------------------------------------------
-        if (lane == 0) {
-            uint32_t it = 0, pg = 0;
-            const uint4* ops = reinterpret_cast<const uint4*>(a.ops);
-            const uint32_t arena_u32 = smem_u32(arena);
-            for (int step = 0; step < a.nsteps; ++step) {
-                uint4 nxt = __ldg(ops);
-                for (int i = 0; i < a.n_ops; ++i) {
-                    const uint4 raw = nxt;
-                    if (i + 1 < a.n_ops) nxt = __ldg(ops + i + 1);
-                    const uint32_t a_off = raw.x, b_off = raw.y, n = raw.z & 0xffffu, dcol = raw.z >> 16;
-                    const uint32_t nk16 = raw.w & 0xffu, acc = (raw.w >> 8) & 0xffu, wait = (raw.w >> 16) & 0xffu, sig = raw.w >> 24;
-                    if (b_off == kTfParam) continue;
-                    if (wait) {
-                        mbar_wait(&bars->go, pg);
-                        pg ^= 1;
-                        tc_fence_after();
-                    }
-                    uint64_t db;
-                    int s = 0;
-                    if (b_off == kTfRing) {
-                        s = it % kStages;
-                        mbar_wait(&bars->full[s], (it / kStages) & 1);
-                        tc_fence_after();
-                        db = umma_desc_sw128(arena_u32 + oRing + s * kTile);
-                    } else {
-                        db = umma_desc_sw128(arena_u32 + b_off);
-                    }
-                    const uint64_t da = umma_desc_sw128(arena_u32 + a_off);
-                    const uint32_t idesc = umma_idesc_bf16(128, static_cast<int>(n));
-                    for (uint32_t ks = 0; ks < nk16; ++ks)
-                        umma_bf16(tmem_base + dcol, da + 2 * ks, db + 2 * ks, idesc, (acc | ks) != 0 ? 1u : 0u);
-                    if (b_off == kTfRing) {
-                        if (cs == 1) umma_commit(&bars->empty[s]); else umma_commit_multicast(&bars->empty[s], cmask);
-                        ++it;
-                    }
-                    if (sig) umma_commit(&bars->done[sig - 1]);
+        uint32_t it = 0, pg = 0;
+        const uint32_t arena_u32 = smem_u32(arena);
+        for (int step = 0; step < a.nsteps; ++step) {
+            bool pre_ok = false;                              // the ring tile of the current op was already seen complete
+            TfOp nx = optab.ops[0];
+            for (int i = 0; i < a.n_ops; ++i) {
+                const TfOp op = nx;
+                if (i + 1 < a.n_ops) nx = optab.ops[i + 1];   // fetched one op ahead
+                if (op.wait) {
+                    mbar_wait(&bars->go, pg);
+                    pg ^= 1;
                 }
+                const bool ring = op.b_off == kTfRing;
+                const uint32_t s = it % kStages;
+                if (ring && !pre_ok) mbar_wait(&bars->full[s], (it / kStages) & 1);
+                tc_fence_after();
+                // look at the next op's weight tile now: the (non-blocking) barrier read overlaps the MMA issue below
+                pre_ok = false;
+                if (i + 1 < a.n_ops && nx.b_off == kTfRing) {
+                    const uint32_t it2 = it + (ring ? 1u : 0u);
+                    pre_ok = mbar_test_wait(&bars->full[it2 % kStages], (it2 / kStages) & 1);
+                }
+                const uint64_t db = umma_desc_sw128(arena_u32 + (ring ? oRing + s * kTile : op.b_off));
+                const uint64_t da = umma_desc_sw128(arena_u32 + op.a_off);
+                const uint32_t idesc = umma_idesc_bf16(128, op.n);
+                if (elect_one()) {
+                    umma_bf16(tmem_base + op.dcol, da, db, idesc, op.acc);
+                    umma_bf16(tmem_base + op.dcol, da + 2, db + 2, idesc, 1u);
+                    if (op.nk16 == 4) {
+                        umma_bf16(tmem_base + op.dcol, da + 4, db + 4, idesc, 1u);
+                        umma_bf16(tmem_base + op.dcol, da + 6, db + 6, idesc, 1u);
+                    }
+                    if (ring) {
+                        if (cs == 1) umma_commit(&bars->empty[s]); else umma_commit_multicast(&bars->empty[s], cmask);
+                    }
+                    if (op.signal) umma_commit(&bars->done[op.signal - 1]);
+                    if (a.trace && blockIdx.x == 0 && step == 1 && i < 128) a.trace[768 + i] = clock64();
+                }
+                if (ring) ++it;
             }
         }
         __syncwarp();
@@ -537,7 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) 
             const float* tb2 = tb + (pf ? 256 : 0) + hf * 128;  // embedding added inside the main (256-wide) blocks
 
             // ================= embedding stage =================
-            param_acquire(e);
+            const float* PA = param_acquire(e, 0);            // continuous branch
             {
                 const float x0 = s_xs[r * 3], x1 = s_xs[r * 3 + 1], x2 = s_xs[r * 3 + 2];
 #pragma unroll 1
@@ -546,13 +565,14 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) 
                     float v[64];
 #pragma unroll
                     for (int i = 0; i < 64; ++i) {
-                        const float4 w = ldf4(e.P + tfp::E_W0 + (chunk * 64 + i) * 4);
-                        v[i] = gelu_erf(fmaf(w.z, x2, fmaf(w.y, x1, fmaf(w.x, x0, w.w))));
+                        const float4 w = ldf4(PA + tfp::EA_W0 + (chunk * 64 + i) * 4);
+                        v[i] = gelu_tile(fmaf(w.z, x2, fmaf(w.y, x1, fmaf(w.x, x0, w.w))));
                     }
                     stage_row_bf16(arena + oA + chunk * kTile, r, v);
                 }
                 go(e);
             }
+            const float* PB = param_acquire(e, 1);            // discrete branch + first LayerNorm
             wait_done(e, 0);
             {
                 // x half: LN_ln1x(wxe.2 output + bias) + temb ; y half: Ytab[k] + temb   -> residual + skip streams
@@ -565,7 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) 
                         tmem_ld32(e.taddr + kScr + cc * 32, v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) s1 += v[i] + e.P[tfp::E_BXE2 + cc * 32 + i];
+                        for (int i = 0; i < 32; ++i) s1 += v[i] + PA[tfp::EA_BXE2 + cc * 32 + i];
                     }
                     const float mean = s1 * (1.0f / 128.0f);
                     float m2 = 0.f;
@@ -575,7 +595,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) 
                         tmem_ld32(e.taddr + kScr + cc * 32, v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) { const float d = v[i] + e.P[tfp::E_BXE2 + cc * 32 + i] - mean; m2 = fmaf(d, d, m2); }
+                        for (int i = 0; i < 32; ++i) { const float d = v[i] + PA[tfp::EA_BXE2 + cc * 32 + i] - mean; m2 = fmaf(d, d, m2); }
                     }
                     const float rstd = rsqrtf(m2 * (1.0f / 128.0f) + 1e-5f);
 #pragma unroll 1
@@ -586,14 +606,14 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) 
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const int c = cc * 32 + i;
-                            v[i] = fmaf((v[i] + e.P[tfp::E_BXE2 + c] - mean) * rstd, e.P[tfp::E_LN1X_G + c], e.P[tfp::E_LN1X_B + c]) + tb1[c];
+                            v[i] = fmaf((v[i] + PA[tfp::EA_BXE2 + c] - mean) * rstd, PA[tfp::EA_LN1X_G + c], PA[tfp::EA_LN1X_B + c]) + tb1[c];
                             sum += v[i];
                             skipc[c * 128] = v[i];
                         }
                         tmem_st32(e.taddr + cc * 32, v);
                     }
                 } else {
-                    const float* yt = e.P + tfp::E_YTAB + s_ks[r] * 128;
+                    const float* yt = PB + tfp::EB_YTAB + s_ks[r] * 128;
 #pragma unroll 1
                     for (int cc = 0; cc < 4; ++cc) {
                         float v[32];
@@ -610,56 +630,58 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) 
                 tmem_st_wait();
                 float mean, rstd;
                 if (pf) ln_stats<false>(e, sum, 0, mean, rstd); else ln_stats<true>(e, sum, 0, mean, rstd);
-                ln_to_abuf(e, mean, rstd, e.P + tfp::E_LNN_G + hf * 128, e.P + tfp::E_LNN_B + hf * 128);
+                ln_to_abuf(e, mean, rstd, PB + tfp::EB_LNN_G + hf * 128, PB + tfp::EB_LNN_B + hf * 128);
                 go(e);
             }
+            param_release(e);
             param_release(e);
             mark(e);
 
             // ================= stream blocks (ParticleFormer): two independent 128-wide groups =================
             for (int blk = 0; blk < a.n_stream; ++blk) {
-                param_acquire(e);
+                param_acquire(e);                             // attention stage
                 const bool last = blk + 1 == a.n_stream;
                 for (int g = 0; g < 2; ++g) {
-                    const float* G = e.P + g * tfp::S_GROUP;
+                    const float* G = e.P + g * tfp::SA_GROUP;
                     for (int u = 0; u < 2; ++u)
-                        attention_unit<32>(e, G + tfp::S_BQKV + u * 64, G + tfp::S_BQKV + 128 + u * 64, G + tfp::S_BQKV + 256 + u * 64,
-                                           G + tfp::S_QG, G + tfp::S_QB, G + tfp::S_KG, G + tfp::S_KB, seg_b, seg_e);
+                        attention_unit<32>(e, G + tfp::SA_BQKV + u * 64, G + tfp::SA_BQKV + 128 + u * 64, G + tfp::SA_BQKV + 256 + u * 64,
+                                           G + tfp::SA_QG, G + tfp::SA_QB, G + tfp::SA_KG, G + tfp::SA_KB, seg_b, seg_e);
                 }
-                mark(e);
                 wait_done(e, 0);                              // last projection of group 1 has landed
                 {
-                    const float* G = e.P + hf * tfp::S_GROUP;
-                    const float sum = resid_update(e, G + tfp::S_BPROJ, nullptr, nullptr);
+                    const float* G = e.P + hf * tfp::SA_GROUP;
+                    const float sum = resid_update(e, G + tfp::SA_BPROJ, nullptr, nullptr);
                     float mean, rstd;
                     ln_stats<false>(e, sum, 0, mean, rstd);
-                    ln_to_abuf(e, mean, rstd, G + tfp::S_LN2G, G + tfp::S_LN2B);
+                    ln_to_abuf(e, mean, rstd, G + tfp::SA_LN2G, G + tfp::SA_LN2B);
                     go(e);
                 }
+                param_release(e);
+                param_acquire(e);                             // MLP stage
                 for (int g = 0; g < 2; ++g) {
-                    const float* G = e.P + g * tfp::S_GROUP;
+                    const float* G = e.P + g * tfp::SM_GROUP;
                     for (int q = 0; q < 4; ++q) {
                         wait_done(e, q & 1);
-                        fc_epilogue(e, q, G + tfp::S_BFC + q * 128);
+                        fc_epilogue(e, q, G + tfp::SM_BFC + q * 128);
                         go(e);
                     }
                 }
                 wait_done(e, 0);                              // last down-projection of group 1
                 {
-                    const float* G = e.P + hf * tfp::S_GROUP;
+                    const float* G = e.P + hf * tfp::SM_GROUP;
                     if (!last) {
-                        const float sum = resid_update(e, G + tfp::S_BP2, tb1, nullptr);
+                        const float sum = resid_update(e, G + tfp::SM_BP2, tb1, nullptr);
                         float mean, rstd;
                         ln_stats<false>(e, sum, 0, mean, rstd);
-                        ln_to_abuf(e, mean, rstd, e.P + tfp::S_LNN_G + hf * 128, e.P + tfp::S_LNN_B + hf * 128);
+                        ln_to_abuf(e, mean, rstd, e.P + tfp::SM_LNN_G + hf * 128, e.P + tfp::SM_LNN_B + hf * 128);
                     } else {
                         // stream junction: x = ln2_x(x + x_skip) | y = ln2_y(y + y_skip); z = cat(x, y) + time_expand(temb)
-                        const float sum = resid_update(e, G + tfp::S_BP2, tb1, skipc);
+                        const float sum = resid_update(e, G + tfp::SM_BP2, tb1, skipc);
                         float mean, rstd;
                         ln_stats<false>(e, sum, 0, mean, rstd);
-                        const float sum2 = ln_to_resid(e, mean, rstd, e.P + tfp::S_LNN_G + hf * 128, e.P + tfp::S_LNN_B + hf * 128, tb2);
+                        const float sum2 = ln_to_resid(e, mean, rstd, e.P + tfp::SM_LNN_G + hf * 128, e.P + tfp::SM_LNN_B + hf * 128, tb2);
                         ln_stats<true>(e, sum2, 1, mean, rstd);
-                        ln_to_abuf(e, mean, rstd, e.P + tfp::S_LN2ND_G + hf * 128, e.P + tfp::S_LN2ND_B + hf * 128);
+                        ln_to_abuf(e, mean, rstd, e.P + tfp::SM_LN2ND_G + hf * 128, e.P + tfp::SM_LN2ND_B + hf * 128);
                     }
                     go(e);
                 }
@@ -669,33 +691,34 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) 
 
             // ================= main blocks: one 256-wide stream =================
             for (int blk = 0; blk < a.n_main; ++blk) {
-                param_acquire(e);
+                param_acquire(e);                             // attention stage
                 const bool last = blk + 1 == a.n_main;
                 for (int u = 0; u < 4; ++u)
-                    attention_unit<64>(e, e.P + tfp::B_BQKV + u * 64, e.P + tfp::B_BQKV + 256 + u * 64, e.P + tfp::B_BQKV + 512 + u * 64,
-                                       e.P + tfp::B_QG, e.P + tfp::B_QB, e.P + tfp::B_KG, e.P + tfp::B_KB, seg_b, seg_e);
-                mark(e);
+                    attention_unit<64>(e, e.P + tfp::BA_BQKV + u * 64, e.P + tfp::BA_BQKV + 256 + u * 64, e.P + tfp::BA_BQKV + 512 + u * 64,
+                                       e.P + tfp::BA_QG, e.P + tfp::BA_QB, e.P + tfp::BA_KG, e.P + tfp::BA_KB, seg_b, seg_e);
                 wait_done(e, 0);
                 {
-                    const float sum = resid_update(e, e.P + tfp::B_BPROJ + hf * 128, nullptr, nullptr);
+                    const float sum = resid_update(e, e.P + tfp::BA_BPROJ + hf * 128, nullptr, nullptr);
                     float mean, rstd;
                     ln_stats<true>(e, sum, 0, mean, rstd);
-                    ln_to_abuf(e, mean, rstd, e.P + tfp::B_LN2G + hf * 128, e.P + tfp::B_LN2B + hf * 128);
+                    ln_to_abuf(e, mean, rstd, e.P + tfp::BA_LN2G + hf * 128, e.P + tfp::BA_LN2B + hf * 128);
                     go(e);
                 }
+                param_release(e);
+                param_acquire(e);                             // MLP stage
                 for (int q = 0; q < 4; ++q) {
                     wait_done(e, q & 1);
-                    fc_epilogue(e, q, e.P + tfp::B_BFC + q * 128);
+                    fc_epilogue(e, q, e.P + tfp::BM_BFC + q * 128);
                     go(e);
                 }
                 wait_done(e, 0);
                 {
                     // not last: z += bias + temb, LayerNorm ln1 of the next block.
                     // last: ParticleFormer  x = ln3_x(x + x_skip) | y = ln3_y(y + y_skip);  Fused  z = ln2(z + z_skip)
-                    const float sum = resid_update(e, e.P + tfp::B_BP2 + hf * 128, tb2, last ? skipc : nullptr);
+                    const float sum = resid_update(e, e.P + tfp::BM_BP2 + hf * 128, tb2, last ? skipc : nullptr);
                     float mean, rstd;
                     if (last && pf) ln_stats<false>(e, sum, 0, mean, rstd); else ln_stats<true>(e, sum, 0, mean, rstd);
-                    ln_to_abuf(e, mean, rstd, e.P + tfp::B_LNN_G + hf * 128, e.P + tfp::B_LNN_B + hf * 128);
+                    ln_to_abuf(e, mean, rstd, e.P + tfp::BM_LNN_G + hf * 128, e.P + tfp::BM_LNN_B + hf * 128);
                     go(e);
                 }
                 param_release(e);
@@ -718,15 +741,12 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const TfLaunch a) 
                 for (int c = 0; c < 3; ++c) outx[c] += e.P[tfp::HX_B2 + c];
             }
             param_release(e);
-            for (int half = 0; half < 2; ++half) {
-                param_acquire(e);                             // head_y, hidden units [half*256, +256)
-                for (int qq = 0; qq < 2; ++qq) {
-                    const int q = 4 + half * 2 + qq;
-                    wait_done(e, q & 1);
-                    head_epilogue<V>(e, q, e.P + tfp::HY_BIAS + qq * 128, e.P + tfp::HY_W2 + qq * 128, 256, outy);
-                    if (q < 6) go(e);
-                }
-                if (half == 0 && hf == 0) {
+            for (int q = 4; q < 8; ++q) {
+                param_acquire(e);                             // head_y, hidden units [(q-4)*128, +128)
+                wait_done(e, q & 1);
+                head_epilogue<V>(e, q, e.P + tfp::HY_BIAS, e.P + tfp::HY_W2, 128, outy);
+                if (q < 6) go(e);
+                if (q == 4 && hf == 0) {
 #pragma unroll
                     for (int v = 0; v < V; ++v) outy[v] += e.P[tfp::HY_B2 + v];
                 }
@@ -820,7 +840,7 @@ int launch_tf_tiles(const TfLaunch& a, int n_tiles, int cluster, cudaStream_t st
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MMF_CUDA_OK(cudaLaunchKernelEx(&cfg, tf_tile_kernel<9>, a));
+    MMF_CUDA_OK(cudaLaunchKernelEx(&cfg, tf_tile_kernel<9>, a, *a.optab, *a.prodtab));
     return 0;
 }
 

@@ -17,41 +17,45 @@ namespace mmf {
 
 constexpr uint32_t kTfRing = 0xFFFFFFFFu;       // TfOp.b_off: B operand is the next tile of the weight stream
 constexpr uint32_t kTfParam = 0xFFFFFFFEu;      // TfOp.b_off: not an MMA - load parameter blob (a_off = byte offset, n = bytes/16)
-constexpr int kTfParamFloats = 4096;            // floats per parameter blob slot
+constexpr int kTfParamFloats = 2304;            // floats per parameter blob slot
 
-// float offsets inside the parameter blobs (one blob per stage of the per-timestep program)
+// float offsets inside the parameter blobs (one blob per stage of the per-timestep program, <= kTfParamFloats each)
 namespace tfp {
-// embedding stage
-constexpr int E_W0 = 0;                          // [256][4] = wxe.0 weight (3) and bias
-constexpr int E_BXE2 = 1024;                     // [128] wxe.2 bias
-constexpr int E_LN1X_G = 1152, E_LN1X_B = 1280;  // [128]
-constexpr int E_YTAB = 1408;                     // [V][128], V <= 16: LN_ln1y(wye.2(GELU(wye.0[k])))
-constexpr int E_LNN_G = 3456, E_LNN_B = 3712;    // [256] LayerNorm ln1 of the first block
-// main block (C = 256)
-constexpr int B_BQKV = 0;                        // [768] q | k | v
-constexpr int B_QG = 768, B_QB = 832, B_KG = 896, B_KB = 960;    // [64]
-constexpr int B_BPROJ = 1024;                    // [256]
-constexpr int B_LN2G = 1280, B_LN2B = 1536;      // [256]
-constexpr int B_BFC = 1792;                      // [512]
-constexpr int B_BP2 = 2304;                      // [256]
-constexpr int B_LNN_G = 2560, B_LNN_B = 2816;    // [256] next LayerNorm (ln1 of the next block, or the final one)
-// stream block (two groups of C = 128); group g starts at g * S_GROUP
-constexpr int S_GROUP = 1536;
-constexpr int S_BQKV = 0;                        // [384] q | k | v
-constexpr int S_QG = 384, S_QB = 416, S_KG = 448, S_KB = 480;    // [32]
-constexpr int S_BPROJ = 512;                     // [128]
-constexpr int S_LN2G = 640, S_LN2B = 768;        // [128]
-constexpr int S_BFC = 896;                       // [512]
-constexpr int S_BP2 = 1408;                      // [128]
-constexpr int S_LNN_G = 3072, S_LNN_B = 3328;    // [256] next LayerNorm over both groups (ln1 of next block; last: ln2_x|ln2_y)
-constexpr int S_LN2ND_G = 3584, S_LN2ND_B = 3840;  // [256] last stream block only: ln1 of the first main block
+// embedding stage A: continuous branch
+constexpr int EA_W0 = 0;                         // [256][4] = wxe.0 weight (3) and bias
+constexpr int EA_BXE2 = 1024;                    // [128] wxe.2 bias
+constexpr int EA_LN1X_G = 1152, EA_LN1X_B = 1280;  // [128]
+// embedding stage B: discrete branch + first LayerNorm
+constexpr int EB_YTAB = 0;                       // [V][128], V <= 12: LN_ln1y(wye.2(GELU(wye.0[k])))
+constexpr int EB_LNN_G = 1536, EB_LNN_B = 1792;  // [256] LayerNorm ln1 of the first block
+// main block (C = 256), attention stage
+constexpr int BA_BQKV = 0;                       // [768] q | k | v
+constexpr int BA_QG = 768, BA_QB = 832, BA_KG = 896, BA_KB = 960;    // [64]
+constexpr int BA_BPROJ = 1024;                   // [256]
+constexpr int BA_LN2G = 1280, BA_LN2B = 1536;    // [256]
+// main block, MLP stage
+constexpr int BM_BFC = 0;                        // [512]
+constexpr int BM_BP2 = 512;                      // [256]
+constexpr int BM_LNN_G = 768, BM_LNN_B = 1024;   // [256] next LayerNorm (ln1 of the next block, or the final one)
+// stream block (two groups of C = 128), attention stage; group g starts at g * SA_GROUP
+constexpr int SA_GROUP = 896;
+constexpr int SA_BQKV = 0;                       // [384] q | k | v
+constexpr int SA_QG = 384, SA_QB = 416, SA_KG = 448, SA_KB = 480;    // [32]
+constexpr int SA_BPROJ = 512;                    // [128]
+constexpr int SA_LN2G = 640, SA_LN2B = 768;      // [128]
+// stream block, MLP stage; group g starts at g * SM_GROUP
+constexpr int SM_GROUP = 640;
+constexpr int SM_BFC = 0;                        // [512]
+constexpr int SM_BP2 = 512;                      // [128]
+constexpr int SM_LNN_G = 1280, SM_LNN_B = 1536;  // [256] next LayerNorm over both groups (ln1 of next block; last: ln2_x|ln2_y)
+constexpr int SM_LN2ND_G = 1792, SM_LN2ND_B = 2048;  // [256] last stream block only: ln1 of the first main block
 // head stages
 constexpr int HX_BIAS = 0;                       // [512] head_x.0 bias
 constexpr int HX_W2 = 512;                       // [3][512] head_x.2 weight
 constexpr int HX_B2 = 2048;                      // [3]
-constexpr int HY_BIAS = 0;                       // [256] head_y.0 bias, this half of the hidden units
-constexpr int HY_W2 = 256;                       // [V][256] head_y.2 weight, this half
-constexpr int HY_B2 = 3840;                      // [V] (first half only), V <= 14
+constexpr int HY_BIAS = 0;                       // [128] head_y.0 bias, this quarter of the hidden units
+constexpr int HY_W2 = 128;                       // [V][128] head_y.2 weight, this quarter
+constexpr int HY_B2 = 128 + 12 * 128;            // [V] (first quarter only), V <= 12
 }  // namespace tfp
 
 struct TfOp {               // one tensor-core k-tile: nk16 MMAs of K = 16
@@ -65,6 +69,14 @@ struct TfOp {               // one tensor-core k-tile: nk16 MMAs of K = 16
     uint8_t signal;         // after this k-tile: 0 nothing, 1 commit -> done[0], 2 commit -> done[1]
 };
 static_assert(sizeof(TfOp) == 16, "TfOp is read with one 128-bit load");
+
+constexpr int kTfMaxOps = 1024;
+struct TfOpTable {          // MMA ops of one timestep; passed to the kernel BY VALUE (constant bank -> uniform registers)
+    TfOp ops[kTfMaxOps];
+};
+struct TfProdTable {        // producer program of one timestep: rows of the next weight tile, or 0x8000 | parameter blob index
+    uint16_t e[2 * kTfMaxOps];
+};
 
 struct TfTileMeta {
     int nrows;              // real rows (<= 128)
@@ -90,8 +102,9 @@ struct TfLaunch {
     int arch;               // MMF_ARCH_PARTICLEFORMER / MMF_ARCH_FUSED_PARTICLEFORMER
     int n_stream, n_main;   // stream (2 x 128-wide) blocks and main (256-wide) blocks
     int vocab;
-    const TfOp* ops;        // op table of one timestep
-    int n_ops;
+    const TfOpTable* optab; // HOST pointers: the tables of one timestep, copied into the kernel parameters at launch
+    const TfProdTable* prodtab;
+    int n_ops, n_prod;
     const uint8_t* wstream; // weight tiles in op order
     const float* params;    // parameter blobs, kTfParamFloats apart
     const TfTileMeta* meta;

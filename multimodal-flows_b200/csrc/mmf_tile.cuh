@@ -28,6 +28,22 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + copysignf(e, x));
 }
 
+// GELU through its tanh form with one MUFU.TANH: 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))).  It differs from the
+// erf form by at most 4.7e-4 absolute (plus 2^-11 relative from tanh.approx), an order of magnitude below the bf16 rounding
+// of the value it produces; used where the SIMT epilogue is the bottleneck (MMF_TILE_GELU_EXACT restores the erf form).
+__device__ __forceinline__ float gelu_tanh(float x) {
+    const float u = x * fmaf(x * x, 0.0356774081f, 0.7978845608f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
+}
+#ifdef MMF_TILE_GELU_EXACT
+__device__ __forceinline__ float gelu_tile(float x) { return gelu_erf(x); }
+#else
+__device__ __forceinline__ float gelu_tile(float x) { return gelu_tanh(x); }
+#endif
+
 __device__ __forceinline__ void st_shared_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d)
                  : "memory");

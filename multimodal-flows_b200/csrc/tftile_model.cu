@@ -14,8 +14,9 @@ namespace mmf {
 struct TfTileModel {
     MmfModelDesc desc{};
     DeviceArena arena;
-    const TfOp* d_ops = nullptr;
-    int n_ops = 0;
+    std::unique_ptr<TfOpTable> optab;                   // host copies, passed by value at every launch
+    std::unique_ptr<TfProdTable> prodtab;
+    int n_ops = 0, n_prod = 0;
     const uint8_t* d_wstream = nullptr;
     const float* d_params = nullptr;
     std::vector<float> time_expand_w, time_expand_b;     // ParticleFormer, host fp32
@@ -105,7 +106,8 @@ BlockW load_block(WeightMap& wm, const std::string& p, int C, int I) {
 }
 
 // MLP of one group: quarters of the hidden layer ping-pong through the two scratch halves
-void emit_mlp(Builder& b, const BlockW& w, int C, int a_chunk0, uint16_t dcol_out, bool first_wait, bool final_signal) {
+// `prefetch_blob` >= 0: the parameter blob of the NEXT stage is requested after the first up-projection quarter
+void emit_mlp(Builder& b, const BlockW& w, int C, int a_chunk0, uint16_t dcol_out, bool first_wait, bool final_signal, int prefetch_blob) {
     const int kbC = C / 64, nh = C / 128;
     auto fc = [&](int q) {
         for (int kb = 0; kb < kbC; ++kb)
@@ -119,7 +121,9 @@ void emit_mlp(Builder& b, const BlockW& w, int C, int a_chunk0, uint16_t dcol_ou
                           static_cast<uint16_t>(dcol_out + h * 128), 1, kb == 0 && h == 0,
                           (final_signal && q == 3 && kb == 1 && h == nh - 1) ? 1 : 0);
     };
-    fc(0); fc(1); out(0); fc(2); out(1); fc(3); out(2); out(3);
+    fc(0);
+    if (prefetch_blob >= 0) b.param_op(prefetch_blob);
+    fc(1); out(0); fc(2); out(1); fc(3); out(2); out(3);
 }
 
 }  // namespace
@@ -140,10 +144,12 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
     {
         float* P = b.blob(blob_idx);
         const std::vector<float> w0 = wm.get(t + "wxe.0.weight", E, 3), b0 = wm.get(t + "wxe.0.bias", E);
-        for (int c = 0; c < E; ++c) { P[tfp::E_W0 + c * 4] = w0[c * 3]; P[tfp::E_W0 + c * 4 + 1] = w0[c * 3 + 1]; P[tfp::E_W0 + c * 4 + 2] = w0[c * 3 + 2]; P[tfp::E_W0 + c * 4 + 3] = b0[c]; }
-        put(P + tfp::E_BXE2, wm.get(t + "wxe.2.bias", h));
-        put(P + tfp::E_LN1X_G, wm.get(t + "ln1_x.weight", h));
-        put(P + tfp::E_LN1X_B, wm.get(t + "ln1_x.bias", h, -1, true));
+        for (int c = 0; c < E; ++c) { P[tfp::EA_W0 + c * 4] = w0[c * 3]; P[tfp::EA_W0 + c * 4 + 1] = w0[c * 3 + 1]; P[tfp::EA_W0 + c * 4 + 2] = w0[c * 3 + 2]; P[tfp::EA_W0 + c * 4 + 3] = b0[c]; }
+        put(P + tfp::EA_BXE2, wm.get(t + "wxe.2.bias", h));
+        put(P + tfp::EA_LN1X_G, wm.get(t + "ln1_x.weight", h));
+        put(P + tfp::EA_LN1X_B, wm.get(t + "ln1_x.bias", h, -1, true));
+        b.param_op(blob_idx++);
+        P = b.blob(blob_idx);
         // discrete embedding branch folded into a V x 128 table (reference ParticleTransformers.py:95-96, 190-191)
         const std::vector<float> emb = wm.get(t + "wye.0.weight", V, E), w2 = wm.get(t + "wye.2.weight", h, E), b2 = wm.get(t + "wye.2.bias", h),
                                  g = wm.get(t + "ln1_y.weight", h), bb = wm.get(t + "ln1_y.bias", h, -1, true);
@@ -159,44 +165,51 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
             const double mean = s / h;
             for (int o = 0; o < h; ++o) q += (row[o] - mean) * (row[o] - mean);
             const double rstd = 1.0 / std::sqrt(q / h + 1e-5);
-            for (int o = 0; o < h; ++o) P[tfp::E_YTAB + k * 128 + o] = static_cast<float>((row[o] - mean) * rstd) * g[o] + bb[o];
+            for (int o = 0; o < h; ++o) P[tfp::EB_YTAB + k * 128 + o] = static_cast<float>((row[o] - mean) * rstd) * g[o] + bb[o];
         }
         if (pf) {
-            put(P + tfp::E_LNN_G, wm.get(t + "blocks_x.0.ln1.weight", h)); put(P + tfp::E_LNN_G + 128, wm.get(t + "blocks_y.0.ln1.weight", h));
-            put(P + tfp::E_LNN_B, wm.get(t + "blocks_x.0.ln1.bias", h, -1, true)); put(P + tfp::E_LNN_B + 128, wm.get(t + "blocks_y.0.ln1.bias", h, -1, true));
+            put(P + tfp::EB_LNN_G, wm.get(t + "blocks_x.0.ln1.weight", h)); put(P + tfp::EB_LNN_G + 128, wm.get(t + "blocks_y.0.ln1.weight", h));
+            put(P + tfp::EB_LNN_B, wm.get(t + "blocks_x.0.ln1.bias", h, -1, true)); put(P + tfp::EB_LNN_B + 128, wm.get(t + "blocks_y.0.ln1.bias", h, -1, true));
         } else {
-            put(P + tfp::E_LNN_G, wm.get(t + "blocks.0.ln1.weight", E)); put(P + tfp::E_LNN_B, wm.get(t + "blocks.0.ln1.bias", E, -1, true));
+            put(P + tfp::EB_LNN_G, wm.get(t + "blocks.0.ln1.weight", E)); put(P + tfp::EB_LNN_B, wm.get(t + "blocks.0.ln1.bias", E, -1, true));
         }
         b.param_op(blob_idx++);
         const Mat wxe2 = mat(wm, t + "wxe.2.weight", h, E);
         for (int kb = 0; kb < 4; ++kb) b.ring_op(oA + kb * kT, rows_of(wxe2, 0, 128), kb * 64, 256, kb > 0, kb == 0, kb == 3 ? 1 : 0);
-        b.param_op(blob_idx);                            // first block, prefetched
+        // (the first block's attention blob is requested once the embedding epilogue has released a slot: the producer blocks until then)
+        b.param_op(blob_idx);
     }
 
     // ---------------- stream blocks (ParticleFormer): groups x | y, C = 128, head size 32, units = head pairs
     for (int i = 0; i < n_stream; ++i) {
-        float* P = b.blob(blob_idx);
         const std::string px[2] = {t + "blocks_x." + std::to_string(i), t + "blocks_y." + std::to_string(i)};
         BlockW w[2] = {load_block(wm, px[0], h, I), load_block(wm, px[1], h, I)};
-        for (int g = 0; g < 2; ++g) {
-            float* G = P + g * tfp::S_GROUP;
-            put(G + tfp::S_BQKV, wm.get(px[g] + ".attn.c_attn.bias", 3 * h, -1, true));
-            put(G + tfp::S_QG, wm.get(px[g] + ".attn.q_layernorm.weight", 32)); put(G + tfp::S_QB, wm.get(px[g] + ".attn.q_layernorm.bias", 32, -1, true));
-            put(G + tfp::S_KG, wm.get(px[g] + ".attn.k_layernorm.weight", 32)); put(G + tfp::S_KB, wm.get(px[g] + ".attn.k_layernorm.bias", 32, -1, true));
-            put(G + tfp::S_BPROJ, wm.get(px[g] + ".attn.c_proj.bias", h, -1, true));
-            put(G + tfp::S_LN2G, wm.get(px[g] + ".ln2.weight", h)); put(G + tfp::S_LN2B, wm.get(px[g] + ".ln2.bias", h, -1, true));
-            put(G + tfp::S_BFC, wm.get(px[g] + ".ffw.c_fc.bias", I, -1, true));
-            put(G + tfp::S_BP2, wm.get(px[g] + ".ffw.c_proj.bias", h, -1, true));
-        }
         const bool last = i + 1 == n_stream;
-        const std::string nx = last ? t + "ln2_x" : t + "blocks_x." + std::to_string(i + 1) + ".ln1";
-        const std::string ny = last ? t + "ln2_y" : t + "blocks_y." + std::to_string(i + 1) + ".ln1";
-        put(P + tfp::S_LNN_G, wm.get(nx + ".weight", h)); put(P + tfp::S_LNN_G + 128, wm.get(ny + ".weight", h));
-        put(P + tfp::S_LNN_B, wm.get(nx + ".bias", h, -1, true)); put(P + tfp::S_LNN_B + 128, wm.get(ny + ".bias", h, -1, true));
-        if (last) {
-            put(P + tfp::S_LN2ND_G, wm.get(t + "blocks_fuse.0.ln1.weight", E)); put(P + tfp::S_LN2ND_B, wm.get(t + "blocks_fuse.0.ln1.bias", E, -1, true));
+        {
+            float* P = b.blob(blob_idx);                 // attention stage (prefetched by the previous stage)
+            for (int g = 0; g < 2; ++g) {
+                float* G = P + g * tfp::SA_GROUP;
+                put(G + tfp::SA_BQKV, wm.get(px[g] + ".attn.c_attn.bias", 3 * h, -1, true));
+                put(G + tfp::SA_QG, wm.get(px[g] + ".attn.q_layernorm.weight", 32)); put(G + tfp::SA_QB, wm.get(px[g] + ".attn.q_layernorm.bias", 32, -1, true));
+                put(G + tfp::SA_KG, wm.get(px[g] + ".attn.k_layernorm.weight", 32)); put(G + tfp::SA_KB, wm.get(px[g] + ".attn.k_layernorm.bias", 32, -1, true));
+                put(G + tfp::SA_BPROJ, wm.get(px[g] + ".attn.c_proj.bias", h, -1, true));
+                put(G + tfp::SA_LN2G, wm.get(px[g] + ".ln2.weight", h)); put(G + tfp::SA_LN2B, wm.get(px[g] + ".ln2.bias", h, -1, true));
+            }
+            P = b.blob(blob_idx + 1);                    // MLP stage
+            for (int g = 0; g < 2; ++g) {
+                float* G = P + g * tfp::SM_GROUP;
+                put(G + tfp::SM_BFC, wm.get(px[g] + ".ffw.c_fc.bias", I, -1, true));
+                put(G + tfp::SM_BP2, wm.get(px[g] + ".ffw.c_proj.bias", h, -1, true));
+            }
+            const std::string nx = last ? t + "ln2_x" : t + "blocks_x." + std::to_string(i + 1) + ".ln1";
+            const std::string ny = last ? t + "ln2_y" : t + "blocks_y." + std::to_string(i + 1) + ".ln1";
+            put(P + tfp::SM_LNN_G, wm.get(nx + ".weight", h)); put(P + tfp::SM_LNN_G + 128, wm.get(ny + ".weight", h));
+            put(P + tfp::SM_LNN_B, wm.get(nx + ".bias", h, -1, true)); put(P + tfp::SM_LNN_B + 128, wm.get(ny + ".bias", h, -1, true));
+            if (last) {
+                put(P + tfp::SM_LN2ND_G, wm.get(t + "blocks_fuse.0.ln1.weight", E)); put(P + tfp::SM_LN2ND_B, wm.get(t + "blocks_fuse.0.ln1.bias", E, -1, true));
+            }
         }
-        ++blob_idx;
+        ++blob_idx;                                      // -> this block's MLP blob
         for (int g = 0; g < 2; ++g)
             for (int u = 0; u < 2; ++u) {
                 // rows of c_attn: q [0,128) k [128,256) v [256,384); unit u = heads 2u, 2u+1 = columns u*64..u*64+63
@@ -214,33 +227,37 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
                 b.smem_op(oK, oVT + 8192 + 4096, 32, 288, 4, 1, 0, 1);
                 b.ring_op(oO, rows_of(w[g].proj, 0, 128), u * 64, static_cast<uint16_t>(g * 128), 1, 1, (g == 1 && u == 1) ? 1 : 0);
             }
-        b.param_op(blob_idx);                            // next stage, prefetched
-        for (int g = 0; g < 2; ++g) emit_mlp(b, w[g], 128, 2 * g, static_cast<uint16_t>(g * 128), g == 0, g == 1);
+        // parameter prefetch: this block's MLP blob once the attention is under way, the next stage's blob inside the MLP
+        b.param_op(blob_idx++);
+        for (int g = 0; g < 2; ++g) emit_mlp(b, w[g], 128, 2 * g, static_cast<uint16_t>(g * 128), g == 0, g == 1, g == 0 ? blob_idx : -1);
     }
 
     // ---------------- main blocks: C = 256, head size 64, units = heads
     for (int j = 0; j < n_main; ++j) {
-        float* P = b.blob(blob_idx);
         const std::string p = t + (pf ? "blocks_fuse." : "blocks.") + std::to_string(j);
         const BlockW w = load_block(wm, p, E, I);
-        put(P + tfp::B_BQKV, wm.get(p + ".attn.c_attn.bias", 3 * E, -1, true));
-        put(P + tfp::B_QG, wm.get(p + ".attn.q_layernorm.weight", 64)); put(P + tfp::B_QB, wm.get(p + ".attn.q_layernorm.bias", 64, -1, true));
-        put(P + tfp::B_KG, wm.get(p + ".attn.k_layernorm.weight", 64)); put(P + tfp::B_KB, wm.get(p + ".attn.k_layernorm.bias", 64, -1, true));
-        put(P + tfp::B_BPROJ, wm.get(p + ".attn.c_proj.bias", E, -1, true));
-        put(P + tfp::B_LN2G, wm.get(p + ".ln2.weight", E)); put(P + tfp::B_LN2B, wm.get(p + ".ln2.bias", E, -1, true));
-        put(P + tfp::B_BFC, wm.get(p + ".ffw.c_fc.bias", I, -1, true));
-        put(P + tfp::B_BP2, wm.get(p + ".ffw.c_proj.bias", E, -1, true));
         const bool last = j + 1 == n_main;
-        if (!last) {
-            const std::string nx = t + (pf ? "blocks_fuse." : "blocks.") + std::to_string(j + 1) + ".ln1";
-            put(P + tfp::B_LNN_G, wm.get(nx + ".weight", E)); put(P + tfp::B_LNN_B, wm.get(nx + ".bias", E, -1, true));
-        } else if (pf) {
-            put(P + tfp::B_LNN_G, wm.get(t + "ln3_x.weight", h)); put(P + tfp::B_LNN_G + 128, wm.get(t + "ln3_y.weight", h));
-            put(P + tfp::B_LNN_B, wm.get(t + "ln3_x.bias", h, -1, true)); put(P + tfp::B_LNN_B + 128, wm.get(t + "ln3_y.bias", h, -1, true));
-        } else {
-            put(P + tfp::B_LNN_G, wm.get(t + "ln2.weight", E)); put(P + tfp::B_LNN_B, wm.get(t + "ln2.bias", E, -1, true));
+        {
+            float* P = b.blob(blob_idx);                 // attention stage
+            put(P + tfp::BA_BQKV, wm.get(p + ".attn.c_attn.bias", 3 * E, -1, true));
+            put(P + tfp::BA_QG, wm.get(p + ".attn.q_layernorm.weight", 64)); put(P + tfp::BA_QB, wm.get(p + ".attn.q_layernorm.bias", 64, -1, true));
+            put(P + tfp::BA_KG, wm.get(p + ".attn.k_layernorm.weight", 64)); put(P + tfp::BA_KB, wm.get(p + ".attn.k_layernorm.bias", 64, -1, true));
+            put(P + tfp::BA_BPROJ, wm.get(p + ".attn.c_proj.bias", E, -1, true));
+            put(P + tfp::BA_LN2G, wm.get(p + ".ln2.weight", E)); put(P + tfp::BA_LN2B, wm.get(p + ".ln2.bias", E, -1, true));
+            P = b.blob(blob_idx + 1);                    // MLP stage
+            put(P + tfp::BM_BFC, wm.get(p + ".ffw.c_fc.bias", I, -1, true));
+            put(P + tfp::BM_BP2, wm.get(p + ".ffw.c_proj.bias", E, -1, true));
+            if (!last) {
+                const std::string nx = t + (pf ? "blocks_fuse." : "blocks.") + std::to_string(j + 1) + ".ln1";
+                put(P + tfp::BM_LNN_G, wm.get(nx + ".weight", E)); put(P + tfp::BM_LNN_B, wm.get(nx + ".bias", E, -1, true));
+            } else if (pf) {
+                put(P + tfp::BM_LNN_G, wm.get(t + "ln3_x.weight", h)); put(P + tfp::BM_LNN_G + 128, wm.get(t + "ln3_y.weight", h));
+                put(P + tfp::BM_LNN_B, wm.get(t + "ln3_x.bias", h, -1, true)); put(P + tfp::BM_LNN_B + 128, wm.get(t + "ln3_y.bias", h, -1, true));
+            } else {
+                put(P + tfp::BM_LNN_G, wm.get(t + "ln2.weight", E)); put(P + tfp::BM_LNN_B, wm.get(t + "ln2.bias", E, -1, true));
+            }
         }
-        ++blob_idx;
+        ++blob_idx;                                      // -> this block's MLP blob
         for (int u = 0; u < 4; ++u) {
             std::vector<const float*> qk = rows_of(w.attn, u * 64, 64), kk = rows_of(w.attn, 256 + u * 64, 64);
             qk.insert(qk.end(), kk.begin(), kk.end());
@@ -254,8 +271,8 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
             for (int nh = 0; nh < 2; ++nh)
                 b.ring_op(oO, rows_of(w.proj, nh * 128, 128), u * 64, static_cast<uint16_t>(nh * 128), 1, nh == 0, (u == 3 && nh == 1) ? 1 : 0);
         }
-        b.param_op(blob_idx);
-        emit_mlp(b, w, 256, 0, 0, true, true);
+        b.param_op(blob_idx++);
+        emit_mlp(b, w, 256, 0, 0, true, true, blob_idx);
     }
 
     // ---------------- heads: Linear(128,512) + GELU on tensor cores, Linear(512, 3 | V) on CUDA cores
@@ -266,12 +283,12 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
                                  wy2 = wm.get(t + "head_y.2.weight", V, I), by2 = wm.get(t + "head_y.2.bias", V);
         float* P = b.blob(blob_idx);
         put(P + tfp::HX_BIAS, bx0); put(P + tfp::HX_W2, wx2); put(P + tfp::HX_B2, bx2);
-        for (int half = 0; half < 2; ++half) {
-            float* Q = b.blob(blob_idx + 1 + half);
-            for (int i = 0; i < 256; ++i) Q[tfp::HY_BIAS + i] = by0[half * 256 + i];
+        for (int q = 0; q < 4; ++q) {
+            float* Q = b.blob(blob_idx + 1 + q);
+            for (int i = 0; i < 128; ++i) Q[tfp::HY_BIAS + i] = by0[q * 128 + i];
             for (int v = 0; v < V; ++v)
-                for (int i = 0; i < 256; ++i) Q[tfp::HY_W2 + v * 256 + i] = wy2[static_cast<size_t>(v) * I + half * 256 + i];
-            if (half == 0) for (int v = 0; v < V; ++v) Q[tfp::HY_B2 + v] = by2[v];
+                for (int i = 0; i < 128; ++i) Q[tfp::HY_W2 + v * 128 + i] = wy2[static_cast<size_t>(v) * I + q * 128 + i];
+            if (q == 0) for (int v = 0; v < V; ++v) Q[tfp::HY_B2 + v] = by2[v];
         }
         for (int hq = 0; hq < 8; ++hq) {
             const Mat& w = hq < 4 ? hx : hy;
@@ -279,10 +296,11 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
             for (int kb = 0; kb < 2; ++kb)
                 b.ring_op(oA + (chunk0 + kb) * kT, rows_of(w, (hq & 3) * 128, 128), kb * 64, static_cast<uint16_t>(256 + (hq & 1) * 128), kb > 0,
                           kb == 0 && hq != 1, kb == 1 ? 1 + (hq & 1) : 0);
+            // head_y quarter blobs: the first when head_x is under way, then one per consumed quarter
             if (hq == 0) b.param_op(blob_idx + 1);
-            if (hq == 4) b.param_op(blob_idx + 2);
+            if (hq >= 3 && hq < 6) b.param_op(blob_idx + hq - 1);
         }
-        blob_idx += 3;
+        blob_idx += 5;
     }
     if (!wm.missing.empty()) { set_last_error(wm.missing); return 2; }
     if (pf) {
@@ -292,14 +310,28 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
     b.params.resize(static_cast<size_t>(blob_idx) * kTfParamFloats, 0.f);
 
     DeviceArena& ar = m->arena;
-    const size_t o_ops = ar.reserve(b.ops.size() * sizeof(TfOp));
-    memcpy(ar.staging.data() + o_ops, b.ops.data(), b.ops.size() * sizeof(TfOp));
+    // split the builder's sequence into the MMA issuer's table and the producer's table
+    m->optab.reset(new TfOpTable());
+    m->prodtab.reset(new TfProdTable());
+    memset(m->optab.get(), 0, sizeof(TfOpTable));
+    memset(m->prodtab.get(), 0, sizeof(TfProdTable));
+    for (const TfOp& o : b.ops) {
+        if (o.b_off == kTfParam) {
+            MMF_REQUIRE(m->n_prod < 2 * kTfMaxOps, "tile kernel: producer table too long");
+            m->prodtab->e[m->n_prod++] = static_cast<uint16_t>(0x8000u | (o.a_off / (kTfParamFloats * 4)));
+            continue;
+        }
+        if (o.b_off == kTfRing) {
+            MMF_REQUIRE(m->n_prod < 2 * kTfMaxOps, "tile kernel: producer table too long");
+            m->prodtab->e[m->n_prod++] = o.n;
+        }
+        MMF_REQUIRE(m->n_ops < kTfMaxOps && (o.nk16 == 2 || o.nk16 == 4), "tile kernel: op table too long for the kernel parameter space");
+        m->optab->ops[m->n_ops++] = o;
+    }
     const size_t o_stream = ar.reserve(b.stream.size() * 2);
     memcpy(ar.staging.data() + o_stream, b.stream.data(), b.stream.size() * 2);
     const size_t o_params = ar.put_f32(b.params);
     if (ar.upload() != 0) return 1;
-    m->d_ops = ar.at<TfOp>(o_ops);
-    m->n_ops = static_cast<int>(b.ops.size());
     m->d_wstream = ar.at<uint8_t>(o_stream);
     m->d_params = ar.at<float>(o_params);
     if (const char* c = getenv("MMF_TILE_CLUSTER")) {
@@ -435,7 +467,7 @@ int tftile_prepare(TfTileModel* m, const TfRunArgs& r, std::vector<unsigned char
 
     TfLaunch a{};
     a.arch = d.arch; a.n_stream = pf ? d.n_layer : 0; a.n_main = pf ? d.n_layer_fused : d.n_layer; a.vocab = d.vocab_size;
-    a.ops = m->d_ops; a.n_ops = m->n_ops; a.wstream = m->d_wstream; a.params = m->d_params; a.meta = m->d_meta; a.tile0 = 0;
+    a.optab = m->optab.get(); a.prodtab = m->prodtab.get(); a.n_ops = m->n_ops; a.n_prod = m->n_prod; a.wstream = m->d_wstream; a.params = m->d_params; a.meta = m->d_meta; a.tile0 = 0;
     a.xs0 = m->d_xs0; a.ks0 = m->d_ks0; a.row_slot = m->d_row_slot; a.skip = m->d_skip; a.temb = m->d_temb;
     a.per_jet_time = r.per_jet_time ? 1 : 0; a.nsteps = r.nsteps;
     if (r.opts) {
@@ -458,15 +490,15 @@ int tftile_launch(TfTileModel* m, cudaStream_t s) {
     const char* trace_path = getenv("MMF_TRACE");
     unsigned long long* d_trace = nullptr;
     if (trace_path) {
-        MMF_CUDA_OK(cudaMalloc(&d_trace, 512 * 8));
-        MMF_CUDA_OK(cudaMemsetAsync(d_trace, 0, 512 * 8, s));
+        MMF_CUDA_OK(cudaMalloc(&d_trace, 1536 * 8));
+        MMF_CUDA_OK(cudaMemsetAsync(d_trace, 0, 1536 * 8, s));
         a.trace = d_trace;
     }
     MMF_TRY_RC(launch_tf_tiles(a, tiles, m->cluster, s));
     m->launches += 1;
     if (d_trace) {
-        std::vector<unsigned long long> hbuf(512);
-        MMF_CUDA_OK(cudaMemcpyAsync(hbuf.data(), d_trace, 512 * 8, cudaMemcpyDeviceToHost, s));
+        std::vector<unsigned long long> hbuf(1536);
+        MMF_CUDA_OK(cudaMemcpyAsync(hbuf.data(), d_trace, 1536 * 8, cudaMemcpyDeviceToHost, s));
         MMF_CUDA_OK(cudaStreamSynchronize(s));
         cudaFree(d_trace);
         if (FILE* f = fopen(trace_path, "w")) {
@@ -474,6 +506,9 @@ int tftile_launch(TfTileModel* m, cudaStream_t s) {
                 for (int i = 0; i < 256 && hbuf[st * 256 + i]; ++i)
                     fprintf(f, "step %d mark %2d  +%llu cycles (total %llu)\n", st, i, i ? hbuf[st * 256 + i] - hbuf[st * 256 + i - 1] : 0ull,
                             hbuf[st * 256 + i] - hbuf[st * 256]);
+            // when each of the first 128 MMA ops of timestep 1 was issued, relative to the step start
+            for (int i = 0; i < 128; ++i)
+                if (hbuf[768 + i]) fprintf(f, "op %3d issued %lld\n", i, (long long)(hbuf[768 + i] - hbuf[256]));
             fclose(f);
         }
     }
