@@ -1,0 +1,127 @@
+"""The N-step sampler through the drop-in API on the GPU: tile kernel vs layered path, sharding invariance, and
+jet-observable histograms vs the CPU oracle (SURVEY.md 8(c) level L2).
+
+Jets of <= 128 particles run in the persistent tile kernel, larger ones in the layered kernels; both must agree with
+each other (same supplied uniforms) and with the reference within the bf16 tolerance.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _model(name, flavor="wide", seed=0, **over):
+    from mmf_b200 import _abi, synthetic
+    from mmf_b200.param_spec import make_config
+    cfg = make_config(name, **over)
+    sd = synthetic.make_state_dict(cfg, flavor=flavor, seed=seed)
+    return cfg, sd, _abi.NativeModel(cfg, sd, torch.device(DEV))
+
+
+def _rel(a, b, real):
+    a, b = a[real].float(), b[real].float()
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.mark.parametrize("name", ["FusedParticleFormer", "ParticleFormer"])
+def test_tile_kernel_agrees_with_layered_path(name, monkeypatch):
+    """Same weights, inputs and supplied uniforms through both CUDA paths (the layered one is forced by the env switch)."""
+    from mmf_b200 import _abi, synthetic
+    from oracle import mmf_oracle as orc
+    cfg, sd, nm_tile = _model(name, num_timesteps=12)
+    monkeypatch.setenv("MMF_NO_TILE_KERNEL", "1")
+    nm_lay = _abi.NativeModel(cfg, sd, torch.device(DEV))
+    monkeypatch.delenv("MMF_NO_TILE_KERNEL")
+    src = synthetic.source_state(24, seed=101).to(DEV)
+    u = synthetic.uniform_draws(cfg.num_timesteps, 24, seed=102).to(DEV)
+    ts, dt = orc.time_grid(cfg)
+    opts = _abi.step_options(cfg)
+    real = src.mask.bool().squeeze(-1)
+    # teacher-forced tokens so the continuous trajectories are comparable step for step
+    forced = torch.randint(1, 9, (cfg.num_timesteps, 24, 150), device=DEV, dtype=torch.uint8) * src.mask.squeeze(-1).to(torch.uint8)
+    xa, ka, ra = nm_tile.generate(src.continuous, src.discrete, src.mask, ts, float(dt), opts, u=u, forced_k=forced, want_rates=True)
+    xb, kb, rb = nm_lay.generate(src.continuous, src.discrete, src.mask, ts, float(dt), opts, u=u, forced_k=forced, want_rates=True)
+    torch.cuda.synchronize()
+    assert nm_tile.launches <= 4 and nm_lay.launches > 100           # one persistent launch vs one launch per layer
+    assert _rel(xa, xb, real) < 1e-2
+    assert torch.equal(ka, kb)
+    assert _rel(ra, rb, real) < 2e-2
+    assert (xa[~real] == 0).all() and (ka[~real] == 0).all()
+    # forward API (per-jet times) through both
+    t = torch.rand(24, device=DEV)
+    va, la = nm_tile.forward(src.continuous, src.discrete, src.mask, t)
+    vb, lb = nm_lay.forward(src.continuous, src.discrete, src.mask, t)
+    assert _rel(va, vb, real) < 1e-2 and _rel(la, lb, real) < 1e-2
+
+
+def test_philox_draws_are_keyed_on_the_global_jet_index():
+    """Generating a batch in one call or as two shards (first_global_jet offsets) gives identical results."""
+    from mmf_b200 import _abi, synthetic
+    from oracle import mmf_oracle as orc
+    cfg, sd, nm = _model("FusedParticleFormer", num_timesteps=8)
+    src = synthetic.source_state(16, seed=55).to(DEV)
+    ts, dt = orc.time_grid(cfg)
+    x, k, _ = nm.generate(src.continuous, src.discrete, src.mask, ts, float(dt), _abi.step_options(cfg, seed=5, first_global_jet=32))
+    parts = []
+    for lo, hi in ((0, 6), (6, 16)):
+        s = src[lo:hi]
+        parts.append(nm.generate(s.continuous, s.discrete, s.mask, ts, float(dt), _abi.step_options(cfg, seed=5, first_global_jet=32 + lo)))
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat([p[1] for p in parts]), k)
+    assert torch.equal(torch.cat([p[0] for p in parts]), x)
+    # a different seed changes the jumps
+    _, k2, _ = nm.generate(src.continuous, src.discrete, src.mask, ts, float(dt), _abi.step_options(cfg, seed=6, first_global_jet=32))
+    assert not torch.equal(k2, k)
+
+
+def test_free_running_sampler_histograms_match_oracle():
+    """L2: free-running N=100 generation (in-kernel Philox) vs the fp32 CPU oracle with its own draws: jet mass,
+    multiplicity-weighted token fractions and pT sums agree within the spread between two oracle seeds."""
+    from mmf_b200 import _abi, synthetic
+    from oracle import mmf_oracle as orc
+    cfg, sd, nm = _model("FusedParticleFormer", num_timesteps=100)
+    B = 48
+    src = synthetic.source_state(B, seed=900)
+    ts, dt = orc.time_grid(cfg)
+    x, k, _ = nm.generate(src.continuous.to(DEV), src.discrete.to(DEV), src.mask.to(DEV), ts, float(dt), _abi.step_options(cfg, seed=1))
+    torch.cuda.synchronize()
+    g1, g2 = torch.Generator().manual_seed(11), torch.Generator().manual_seed(12)
+    xo1, ko1, _ = orc.simulate_dynamics(sd, cfg, src.continuous, src.discrete, src.mask, generator=g1)
+    xo2, ko2, _ = orc.simulate_dynamics(sd, cfg, src.continuous, src.discrete, src.mask, generator=g2)
+    real = src.mask.bool().squeeze(-1)
+    # the continuous ODE does not depend on the draws beyond the token feedback: trajectories stay close
+    assert _rel(x.cpu(), xo1, real) < 0.15
+    obs = orc.jet_observables(x.cpu(), k.cpu().unsqueeze(-1), src.mask)
+    o1 = orc.jet_observables(xo1, ko1, src.mask)
+    o2 = orc.jet_observables(xo2, ko2, src.mask)
+    frac = lambda o: o["token_counts"].sum(0).double() / o["token_counts"].sum().double()
+    spread = (frac(o1) - frac(o2)).abs().max().item()
+    assert (frac(obs) - frac(o1)).abs().max().item() < max(3 * spread, 0.03)
+    assert torch.equal(obs["multiplicity"], o1["multiplicity"])
+    m_rel = ((obs["mass"] - o1["mass"]).abs() / (o1["mass"].abs() + 1e-3)).median().item()
+    m_ref = ((o2["mass"] - o1["mass"]).abs() / (o1["mass"].abs() + 1e-3)).median().item()
+    assert m_rel < max(3 * m_ref, 0.05), (m_rel, m_ref)
+
+
+def test_dropin_predict_step_host_roundtrip():
+    """predict_step with a HOST batch returns a HOST TensorMultiModal with the reference field layout."""
+    from mmf_b200 import synthetic
+    from mmf_b200.mmf import MultiModalFlowBridge
+    from mmf_b200.param_spec import make_config
+    from mmf_b200.tensorclass import DataCoupling, TensorMultiModal
+    cfg = make_config("ParticleFormer", num_timesteps=5)
+    bridge = MultiModalFlowBridge(cfg)
+    bridge.model.load_state_dict(synthetic.make_state_dict(cfg, "wide", seed=2))
+    bridge = bridge.to(DEV)
+    src = synthetic.source_state(9, seed=7)
+    out = bridge.predict_step(DataCoupling(source=src, target=TensorMultiModal()), 0)
+    assert out.continuous.device.type == "cpu" and out.continuous.shape == (9, 150, 3) and out.continuous.dtype == torch.float32
+    assert out.discrete.shape == (9, 150, 1) and out.discrete.dtype == torch.int64
+    assert out.time.shape == (9,) and abs(float(out.time[0]) - (1 - 1e-5)) < 1e-6
+    real = src.mask.bool().squeeze(-1)
+    assert (out.continuous[~real] == 0).all() and (out.discrete.squeeze(-1)[~real] == 0).all()
+    assert out.discrete.min() >= 0 and out.discrete.max() < 9
