@@ -32,7 +32,9 @@ struct EpicBars {
 // float offsets of the fp32 scratch that follows the operand buffers
 constexpr int oXs = 0, oPool = oXs + 384, oPart = oPool + kEpicMaxJets * kPoolLd, oHid = oPart + 2 * kEpicMaxJets * 256,
               oJb = oHid + kEpicMaxJets * 256, oGlob = oJb + kEpicMaxJets * 256, oGpre = oGlob + 128, oGskip = oGpre + 128,
-              oHeadp = oGskip + 128, oXchg = oHeadp + 512, oMeta = oXchg + 512, oRowJet = oMeta + 32, oEnd = oRowJet + 32;
+              oHeadp = oGskip + 128, oXchg = oHeadp + 512, oMeta = oXchg + 512, oRowJet = oMeta + 32,
+              oConst = oRowJet + 32 /* a3 [256][4] | b_loc2p [256] | bl2 [5][256] */, oTb = oConst + 1024 + 256 + kEpicLayers * 256,
+              oEnd = oTb + kEpicTbLd;
 constexpr int kSmemBytes = 1024 /*align*/ + 1024 /*bars*/ + 4 * kTile + kStages * kTile + oEnd * 4;
 
 __device__ __forceinline__ void epi_bar() { named_bar_sync(1, kEpi); }
@@ -40,64 +42,84 @@ __device__ __forceinline__ void epi_bar() { named_bar_sync(1, kEpi); }
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
-// hidden layer of a global MLP for all jets of the tile:
-//   part[kh][j][o] = sum_{k in half kh} Wt[k][o] * pool[j][k]      (Wt bf16 [K][256], transposed on the host)
-// thread: outputs (op, op+1), k-range half kh.  Followed by combine + bias + activation into hid[j][o].
+// hidden layer of a global MLP for all jets of the tile:  hid[j][o] = act(sum_k Wt[k][o] * pool[j][k] + bias[o])
+// (Wt bf16 [K][256], transposed on the host).  The matrix is streamed from L2 once per call with 16-byte loads, 16 in flight
+// per thread (the loop is bound by bytes in flight, not by FMAs): a warp covers 32 outputs (4 lanes x 8) x 8 k-slices, the
+// k-slices are reduced with shuffles.  Jets are processed four at a time (tiles rarely hold more).
 template <bool GELU>
-__device__ __forceinline__ void global_hidden(const bf16* __restrict__ Wt, int K, const float* s_pool, float* s_part,
-                                              float* s_hid, const float* bias0, int bias_jet_stride,
-                                              const int* jet_tb, int njets, int tid) {
-    const int op = (tid & 127) * 2, kh = tid >> 7;
-    const int kn = K >> 1, k0 = kh * kn;
-    float acc0[kEpicMaxJets], acc1[kEpicMaxJets];
+__device__ __forceinline__ void global_hidden(const bf16* __restrict__ Wt, int K, const float* s_pool, float* s_hid,
+                                              const float* bias0, int bias_jet_stride, const int* jet_tb, int njets, int tid) {
+    const int lane = tid & 31, ks = lane >> 2, o0 = ((tid >> 5) * 4 + (lane & 3)) * 8;
+    const int kn = K >> 3, k0 = ks * kn;                       // 64 or 66 rows of Wt per slice
+    const uint4* wp = reinterpret_cast<const uint4*>(Wt + static_cast<size_t>(k0) * 256 + o0);
+    for (int j0 = 0; j0 < njets; j0 += 4) {
+        float acc[4][8];
 #pragma unroll
-    for (int j = 0; j < kEpicMaxJets; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(Wt + static_cast<size_t>(k0) * 256 + op);
-#pragma unroll 2
-    for (int k = 0; k < kn; k += 4) {
-        const uint32_t w0 = __ldg(wp + (k + 0) * 128), w1 = __ldg(wp + (k + 1) * 128), w2 = __ldg(wp + (k + 2) * 128),
-                       w3 = __ldg(wp + (k + 3) * 128);
+        for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-        for (int j = 0; j < kEpicMaxJets; ++j) {
-            if (j < njets) {
-                const float4 p = *reinterpret_cast<const float4*>(s_pool + j * kPoolLd + k0 + k);
-                acc0[j] = fmaf(bf16_lo(w0), p.x, fmaf(bf16_lo(w1), p.y, fmaf(bf16_lo(w2), p.z, fmaf(bf16_lo(w3), p.w, acc0[j]))));
-                acc1[j] = fmaf(bf16_hi(w0), p.x, fmaf(bf16_hi(w1), p.y, fmaf(bf16_hi(w2), p.z, fmaf(bf16_hi(w3), p.w, acc1[j]))));
+            for (int e = 0; e < 8; ++e) acc[jj][e] = 0.f;
+#pragma unroll 16
+        for (int k = 0; k < kn; ++k) {
+            const uint4 w = __ldg(wp + k * 32);                 // row k0 + k, outputs o0 .. o0+7
+            const float we[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y), bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                if (j0 + jj < njets) {
+                    const float p = s_pool[(j0 + jj) * kPoolLd + k0 + k];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[jj][e] = fmaf(we[e], p, acc[jj][e]);
+                }
+            }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float v = acc[jj][e];
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                acc[jj][e] = v;
+            }
+        if (ks == 0) {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                if (j0 + jj < njets) {
+                    const float* b = bias0 + static_cast<size_t>(bias_jet_stride ? jet_tb[j0 + jj] : 0) * bias_jet_stride + o0;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float v = acc[jj][e] + __ldg(b + e);
+                        s_hid[(j0 + jj) * 256 + o0 + e] = GELU ? gelu_erf(v) : leaky_relu(v);
+                    }
+                }
             }
         }
     }
-#pragma unroll
-    for (int j = 0; j < kEpicMaxJets; ++j) {
-        if (j < njets) {
-            *reinterpret_cast<float2*>(s_part + (kh * kEpicMaxJets + j) * 256 + op) = make_float2(acc0[j], acc1[j]);
-        }
-    }
-    epi_bar();
-    for (int j = 0; j < njets; ++j) {
-        const float b = __ldg(bias0 + static_cast<size_t>(bias_jet_stride ? jet_tb[j] : 0) * bias_jet_stride + tid);
-        const float v = s_part[j * 256 + tid] + s_part[(kEpicMaxJets + j) * 256 + tid] + b;
-        s_hid[j * 256 + tid] = GELU ? gelu_erf(v) : leaky_relu(v);
-    }
     epi_bar();
 }
 
-// 16-wide output of a global MLP: thread (j, q) = (tid / 16, tid % 16); returns W2[q] . hid[j] + b2[q]
-__device__ __forceinline__ float global_out16(const float* __restrict__ W2, const float* __restrict__ b2,
-                                              const float* s_hid, int j, int q) {
-    const float4* w = reinterpret_cast<const float4*>(W2 + q * 256);
-    const float4* h = reinterpret_cast<const float4*>(s_hid + j * 256);
-    float acc = __ldg(b2 + q);
-#pragma unroll 8
-    for (int o = 0; o < 64; ++o) {
-        const float4 a = __ldg(w + o), b = h[o];
+// 16-wide output of a global MLP with all 256 threads: jet j = tid / 32, output q = (tid / 2) % 16, the two lanes of a pair
+// take one half of the 256-long dot product each.  The result W2[q] . hid[j] + b2[q] is valid in the even lane.
+__device__ __forceinline__ float global_out16(const float* W2 /* shared memory */, const float* __restrict__ b2,
+                                              const float* s_hid, int tid) {
+    const int j = tid >> 5, q = (tid >> 1) & 15, half = tid & 1;
+    const float4* w = reinterpret_cast<const float4*>(W2 + q * 256 + half * 128);
+    const float4* h = reinterpret_cast<const float4*>(s_hid + j * 256 + half * 128);
+    float acc = 0.f;
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+        const float4 a = w[o], b = h[o];
         acc = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
     }
-    return acc;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    return acc + __ldg(b2 + q);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // The dynamic shared window starts 1024-byte aligned (no static shared memory in this kernel); it is used directly so
+    // that the compiler keeps the shared address space (LDS/STS instead of generic loads).  SWIZZLE_128B needs the alignment.
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     EpicBars* bars = reinterpret_cast<EpicBars*>(smem);
     uint8_t* Abuf = smem + 1024;
     uint8_t* ring = Abuf + 4 * kTile;
@@ -106,6 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
           *s_glob = fb + oGlob, *s_gpre = fb + oGpre, *s_gskip = fb + oGskip, *s_headp = fb + oHeadp, *s_xchg = fb + oXchg;
     EpicTileMeta* s_meta = reinterpret_cast<EpicTileMeta*>(fb + oMeta);
     uint8_t* s_rowjet = reinterpret_cast<uint8_t*>(fb + oRowJet);
+    float *s_a3 = fb + oConst, *s_b2p = s_a3 + 1024, *s_bl2 = s_b2p + 256, *s_tb = fb + oTb;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = a.tile0 + blockIdx.x;
@@ -130,15 +153,15 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
     const uint32_t tmem_base = bars->tmem_base;
     const int nrows = s_meta->nrows, njets = s_meta->njets;
 
+    // producer and MMA warps run converged (uniform loop state); one elected lane issues the asynchronous instructions
     if (warp == 8) {
         // ------------------------------------------------ weight producer -----------------------------------
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int step = 0; step < a.nsteps; ++step) {
-                for (int t = 0; t < kEpicTilesPerStep; ++t, ++it) {
-                    const int s = it % kStages;
-                    const uint32_t round = it / kStages;
-                    if (round > 0) mbar_wait(&bars->empty[s], (round - 1) & 1);
+        uint32_t it = 0;
+        for (int step = 0; step < a.nsteps; ++step) {
+            for (int t = 0; t < kEpicTilesPerStep; ++t, ++it) {
+                const uint32_t s = it % kStages, round = it / kStages;
+                if (round > 0) mbar_wait(&bars->empty[s], (round - 1) & 1);
+                if (elect_one()) {
                     mbar_expect_tx(&bars->full[s], kTile);
                     bulk_load_1d(ring + s * kTile, a.p.wstream + static_cast<size_t>(t) * kTile, kTile, &bars->full[s]);
                 }
@@ -147,35 +170,35 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
         __syncwarp();
     } else if (warp == 9) {
         // ------------------------------------------------ MMA issuer ----------------------------------------
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
-            uint32_t it = 0, pa = 0;
-            auto gemm = [&](uint32_t dcol, uint32_t accumulate) {     // D[:, dcol..dcol+256) (+)= A[128x256] W^T
-                mbar_wait(&bars->a_ready, pa);
-                pa ^= 1;
-                tc_fence_after();
-                for (int kb = 0; kb < 4; ++kb) {
-                    for (int nh = 0; nh < 2; ++nh, ++it) {
-                        const int s = it % kStages;
-                        mbar_wait(&bars->full[s], (it / kStages) & 1);
-                        tc_fence_after();
-                        const uint64_t da = umma_desc_sw128(smem_u32(Abuf + kb * kTile));
-                        const uint64_t db = umma_desc_sw128(smem_u32(ring + s * kTile));
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks)
-                            umma_bf16(tmem_base + dcol + nh * 128, da + 2 * ks, db + 2 * ks, idesc,
-                                      (accumulate | kb | ks) != 0 ? 1u : 0u);
+        constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+        uint32_t it = 0, pa = 0;
+        const uint32_t a_u32 = smem_u32(Abuf), ring_u32 = smem_u32(ring);
+        auto gemm = [&](uint32_t dcol, uint32_t accumulate) {     // D[:, dcol..dcol+256) (+)= A[128x256] W^T
+            mbar_wait(&bars->a_ready, pa);
+            pa ^= 1;
+            for (int kb = 0; kb < 4; ++kb) {
+                for (int nh = 0; nh < 2; ++nh, ++it) {
+                    const uint32_t s = it % kStages;
+                    mbar_wait(&bars->full[s], (it / kStages) & 1);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(a_u32 + kb * kTile);
+                    const uint64_t db = umma_desc_sw128(ring_u32 + s * kTile);
+                    if (elect_one()) {
+                        umma_bf16(tmem_base + dcol + nh * 128, da, db, idesc, (accumulate | kb) != 0 ? 1u : 0u);
+                        umma_bf16(tmem_base + dcol + nh * 128, da + 2, db + 2, idesc, 1u);
+                        umma_bf16(tmem_base + dcol + nh * 128, da + 4, db + 4, idesc, 1u);
+                        umma_bf16(tmem_base + dcol + nh * 128, da + 6, db + 6, idesc, 1u);
                         umma_commit(&bars->empty[s]);
+                        if (kb == 3 && nh == 1) umma_commit(&bars->acc_full);
                     }
                 }
-                umma_commit(&bars->acc_full);
-            };
-            for (int step = 0; step < a.nsteps; ++step) {
-                gemm(256, 0);                                   // proj.mlp_local.2
-                for (int l = 0; l < kEpicLayers; ++l) {
-                    gemm(256, 0);                               // fc_loc1 (local part)
-                    gemm(0, 1);                                 // fc_loc2, accumulated onto the residual in TMEM
-                }
+            }
+        };
+        for (int step = 0; step < a.nsteps; ++step) {
+            gemm(256, 0);                                   // proj.mlp_local.2
+            for (int l = 0; l < kEpicLayers; ++l) {
+                gemm(256, 0);                               // fc_loc1 (local part)
+                gemm(0, 1);                                 // fc_loc2, accumulated onto the residual in TMEM
             }
         }
         __syncwarp();
@@ -193,9 +216,15 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
             for (int c = 0; c < 3; ++c)
                 s_xs[tid * 3 + c] = tid < nrows ? a.xs0[(static_cast<size_t>(tile) * 128 + tid) * 3 + c] : 0.f;
         }
+        for (int i = tid; i < 256; i += kEpi) {
+            s_a3[i * 4] = a.p.a3[i * 3]; s_a3[i * 4 + 1] = a.p.a3[i * 3 + 1]; s_a3[i * 4 + 2] = a.p.a3[i * 3 + 2]; s_a3[i * 4 + 3] = 0.f;
+            s_b2p[i] = a.p.b_loc2p[i];
+            for (int l = 0; l < kEpicLayers; ++l) s_bl2[l * 256 + i] = a.p.bl2[l][i];
+        }
         epi_bar();
         const int jrow = s_rowjet[r];
-        float* skip_row = a.loc_skip + (static_cast<size_t>(tile) * 128 + r) * 256;
+        // skip stream (bf16), layout per tile [col / 8][row][8]: a warp reads / writes 512 contiguous bytes per instruction
+        uint4* skip8 = reinterpret_cast<uint4*>(a.loc_skip) + static_cast<size_t>(tile) * 32 * 128 + r;   // + (col / 8) * 128
 
         // masked sum pooling of the bf16 local features in Abuf; thread = column
         auto pool = [&](bool with_glob) {
@@ -203,10 +232,17 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
             const uint8_t* ch = Abuf + (col >> 6) * kTile + (col & 7) * 2;
             const uint32_t u = (col & 63) >> 3;
             for (int j = 0; j < njets; ++j) {
-                float s = 0.f;
                 const int r1 = s_meta->jet_begin[j + 1];
-                for (int rr = s_meta->jet_begin[j]; rr < r1; ++rr)
-                    s += __bfloat162float(*reinterpret_cast<const bf16*>(ch + sw128_offset(rr, u)));
+                int rr = s_meta->jet_begin[j];
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;          // independent chains: the loop is LDS-latency bound
+                for (; rr + 4 <= r1; rr += 4) {
+                    s0 += __bfloat162float(*reinterpret_cast<const bf16*>(ch + sw128_offset(rr, u)));
+                    s1 += __bfloat162float(*reinterpret_cast<const bf16*>(ch + sw128_offset(rr + 1, u)));
+                    s2 += __bfloat162float(*reinterpret_cast<const bf16*>(ch + sw128_offset(rr + 2, u)));
+                    s3 += __bfloat162float(*reinterpret_cast<const bf16*>(ch + sw128_offset(rr + 3, u)));
+                }
+                for (; rr < r1; ++rr) s0 += __bfloat162float(*reinterpret_cast<const bf16*>(ch + sw128_offset(rr, u)));
+                float s = (s0 + s1) + (s2 + s3);
                 if (s_meta->pair) {                              // the other half of the jet lives in the peer CTA
                     dsmem_st_f32(dsmem_addr(s_xchg + px * 256 + col, peer), s);
                     mbar_arrive_remote(dsmem_addr(&bars->xchg, peer));
@@ -221,6 +257,14 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
             epi_bar();
         };
 
+        // second linear of a global MLP ([16][256] fp32 = 16 KB): fetched into shared memory while pooling / the hidden layer run
+        auto stage_w2 = [&](const float* W2) {
+            const float4* src = reinterpret_cast<const float4*>(W2);
+            float4* dst = reinterpret_cast<float4*>(s_part);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[tid + i * kEpi] = __ldg(src + tid + i * kEpi);
+        };
+
         int mark_i = 0;
         auto mark = [&](int step) {
             if (a.trace && blockIdx.x == 0 && tid == 0 && step < 2 && mark_i < 64) a.trace[step * 64 + mark_i] = clock64();
@@ -231,6 +275,11 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
             mark(step);                                       // 0: step start
             const int tb_row = a.per_jet_time ? s_meta->jet_tb[jrow] : step;
             const float* tbr = a.tbias + static_cast<size_t>(tb_row) * kEpicTbLd;
+            if (!a.per_jet_time) {                            // one row for the whole tile: stage it in shared memory
+                for (int i = tid; i < kEpicTbLd; i += kEpi) s_tb[i] = tbr[i];
+                epi_bar();
+                tbr = s_tb;
+            }
 
             // ---- proj.mlp_local.0 with wxe folded in: h1 = GELU(A3 x + c1(t)), K = 3 on CUDA cores
             {
@@ -240,11 +289,15 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
                     const int chunk = hf * 2 + cc;
                     float v[64];
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) {
+                    for (int i = 0; i < 64; i += 4) {
                         const int col = chunk * 64 + i;
-                        const float pre = fmaf(__ldg(a.p.a3 + col * 3 + 2), x2, fmaf(__ldg(a.p.a3 + col * 3 + 1), x1,
-                                          fmaf(__ldg(a.p.a3 + col * 3), x0, __ldg(tbr + col))));
-                        v[i] = gelu_erf(pre);
+                        const float4 c1 = *reinterpret_cast<const float4*>(tbr + col);
+                        const float4 wa = *reinterpret_cast<const float4*>(s_a3 + col * 4), wb = *reinterpret_cast<const float4*>(s_a3 + col * 4 + 4),
+                                     wc = *reinterpret_cast<const float4*>(s_a3 + col * 4 + 8), wd = *reinterpret_cast<const float4*>(s_a3 + col * 4 + 12);
+                        v[i] = gelu_tile(fmaf(wa.z, x2, fmaf(wa.y, x1, fmaf(wa.x, x0, c1.x))));
+                        v[i + 1] = gelu_tile(fmaf(wb.z, x2, fmaf(wb.y, x1, fmaf(wb.x, x0, c1.y))));
+                        v[i + 2] = gelu_tile(fmaf(wc.z, x2, fmaf(wc.y, x1, fmaf(wc.x, x0, c1.z))));
+                        v[i + 3] = gelu_tile(fmaf(wd.z, x2, fmaf(wd.y, x1, fmaf(wd.x, x0, c1.w))));
                     }
                     stage_row_bf16(Abuf + chunk * kTile, r, v);
                 }
@@ -265,13 +318,14 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
                 tmem_ld32(taddr + 256 + col0, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i] + __ldg(a.p.b_loc2p + col0 + i));
+                for (int i = 0; i < 32; ++i) v[i] = gelu_tile(v[i] + s_b2p[col0 + i]);
                 tmem_st32(taddr + col0, v);
-                float4* sk = reinterpret_cast<float4*>(skip_row + col0);
                 uint8_t* ch = Abuf + (col0 >> 6) * kTile;
                 const uint32_t u0 = (col0 & 63) >> 3;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) sk[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                for (int u = 0; u < 4; ++u)
+                    skip8[((col0 >> 3) + u) * 128] = make_uint4(pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                                                               pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                     st_shared_v4(ch + sw128_offset(r, u0 + u), pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
@@ -284,14 +338,16 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
             epi_bar();
             mark(step);                                       // 3: proj epilogue done
             // ---- proj.mlp_global: pooled(512) ++ temb -> 256 (GELU) -> 16 (GELU)
+            stage_w2(a.p.wg2p);
             pool(false);
             mark(step);                                       // 4: pooled
-            global_hidden<true>(a.p.wg0t, 512, s_pool, s_part, s_hid, a.tbias + 256 + (a.per_jet_time ? 0 : static_cast<size_t>(step) * kEpicTbLd),
+            global_hidden<true>(a.p.wg0t, 512, s_pool, s_hid, a.tbias + 256 + (a.per_jet_time ? 0 : static_cast<size_t>(step) * kEpicTbLd),
                                 a.per_jet_time ? kEpicTbLd : 0, s_meta->jet_tb, njets, tid);
-            if (tid < njets * 16) {
-                const float g = gelu_erf(global_out16(a.p.wg2p, a.p.bg2p, s_hid, tid >> 4, tid & 15));
-                s_glob[tid] = g;
-                s_gskip[tid] = g;
+            const int gidx = (tid >> 5) * 16 + ((tid >> 1) & 15);      // (jet, output) owned by this thread pair
+            const bool gown = (tid & 1) == 0 && (tid >> 5) < njets;
+            {
+                const float g = gelu_erf(global_out16(s_part, a.p.bg2p, s_hid, tid));
+                if (gown) { s_glob[gidx] = g; s_gskip[gidx] = g; }
             }
             epi_bar();
             mark(step);                                       // 5: proj global MLP done
@@ -300,23 +356,28 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
 #pragma unroll 1
             for (int l = 0; l < kEpicLayers; ++l) {
                 // the fc_loc1 GEMM of this layer is already running on the tensor core; meanwhile the global path:
+                stage_w2(a.p.wg2[l]);                         // (the previous user of s_part finished before the last epi_bar)
+                // fc_loc1's global columns for this thread's output: loaded now, used after the global MLP
+                const float4* wg = reinterpret_cast<const float4*>(a.p.wl1g[l] + tid * 16);
+                const float4 w0 = __ldg(wg), w1 = __ldg(wg + 1), w2 = __ldg(wg + 2), w3 = __ldg(wg + 3);
                 if (l > 0) pool(true);
                 else {
                     if (tid < njets * 16) s_pool[(tid >> 4) * kPoolLd + 512 + (tid & 15)] = s_glob[tid];
                     epi_bar();
                 }
                 mark(step);                                   // 6+6l: pooled
-                global_hidden<false>(a.p.wg1t[l], 528, s_pool, s_part, s_hid, a.p.bg1[l], 0, s_meta->jet_tb, njets, tid);
+                global_hidden<false>(a.p.wg1t[l], 528, s_pool, s_hid, a.p.bg1[l], 0, s_meta->jet_tb, njets, tid);
                 mark(step);                                   // 7+6l: global hidden done
-                if (tid < njets * 16) s_gpre[tid] = s_glob[tid] + global_out16(a.p.wg2[l], a.p.bg2[l], s_hid, tid >> 4, tid & 15);
+                {
+                    const float g2 = global_out16(s_part, a.p.bg2[l], s_hid, tid);
+                    if (gown) s_gpre[gidx] = s_glob[gidx] + g2;
+                }
                 epi_bar();
                 {   // per-jet bias of fc_loc1: time part (table) + global part
-                    const float4* wg = reinterpret_cast<const float4*>(a.p.wl1g[l] + tid * 16);
-                    const float4 w0 = __ldg(wg), w1 = __ldg(wg + 1), w2 = __ldg(wg + 2), w3 = __ldg(wg + 3);
                     for (int j = 0; j < njets; ++j) {
-                        const int tbj = a.per_jet_time ? s_meta->jet_tb[j] : step;
                         const float* g = s_gpre + j * 16;
-                        float acc = __ldg(a.tbias + static_cast<size_t>(tbj) * kEpicTbLd + 512 + l * 256 + tid);
+                        float acc = a.per_jet_time ? __ldg(a.tbias + static_cast<size_t>(s_meta->jet_tb[j]) * kEpicTbLd + 512 + l * 256 + tid)
+                                                   : s_tb[512 + l * 256 + tid];
                         acc = fmaf(w0.x, g[0], fmaf(w0.y, g[1], fmaf(w0.z, g[2], fmaf(w0.w, g[3], acc))));
                         acc = fmaf(w1.x, g[4], fmaf(w1.y, g[5], fmaf(w1.z, g[6], fmaf(w1.w, g[7], acc))));
                         acc = fmaf(w2.x, g[8], fmaf(w2.y, g[9], fmaf(w2.z, g[10], fmaf(w2.w, g[11], acc))));
@@ -353,29 +414,35 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
                 tc_fence_before();
                 mbar_arrive(&bars->a_ready);                 // fc_loc2 accumulates onto loc in TMEM
                 mark(step);                                   // 10+6l: fc_loc1 epilogue done
-                // ---- fc_loc2 epilogue: loc = leaky_relu(loc_pre + b) + loc_skip
+                // ---- fc_loc2 epilogue: loc = leaky_relu(loc_pre + b) + loc_skip.  The skip values of this thread's 128 columns
+                //      are fetched while the GEMM runs.
+                uint4 sk[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) sk[u] = skip8[(hf * 16 + u) * 128];
                 mbar_wait(&bars->acc_full, pf);
                 pf ^= 1;
                 tc_fence_after();
                 mark(step);                                   // 11+6l: fc_loc2 GEMM done
                 const bool last = l + 1 == kEpicLayers;
-#pragma unroll 1
+#pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int col0 = hf * 128 + c * 32;
                     float v[32];
                     tmem_ld32(taddr + col0, v);
-                    const float4* sk = reinterpret_cast<const float4*>(skip_row + col0);
-                    float4 s4[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) s4[u] = sk[u];
                     tmem_ld_wait();
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(a.p.bl2[l] + col0) + u);
-                        v[4 * u] = leaky_relu(v[4 * u] + b.x) + s4[u].x;
-                        v[4 * u + 1] = leaky_relu(v[4 * u + 1] + b.y) + s4[u].y;
-                        v[4 * u + 2] = leaky_relu(v[4 * u + 2] + b.z) + s4[u].z;
-                        v[4 * u + 3] = leaky_relu(v[4 * u + 3] + b.w) + s4[u].w;
+                    for (int u = 0; u < 4; ++u) {
+                        const uint4 s8 = sk[c * 4 + u];
+                        const float4 b0 = *reinterpret_cast<const float4*>(s_bl2 + l * 256 + col0 + 8 * u);
+                        const float4 b1 = *reinterpret_cast<const float4*>(s_bl2 + l * 256 + col0 + 8 * u + 4);
+                        v[8 * u] = leaky_relu(v[8 * u] + b0.x) + bf16_lo(s8.x);
+                        v[8 * u + 1] = leaky_relu(v[8 * u + 1] + b0.y) + bf16_hi(s8.x);
+                        v[8 * u + 2] = leaky_relu(v[8 * u + 2] + b0.z) + bf16_lo(s8.y);
+                        v[8 * u + 3] = leaky_relu(v[8 * u + 3] + b0.w) + bf16_hi(s8.y);
+                        v[8 * u + 4] = leaky_relu(v[8 * u + 4] + b1.x) + bf16_lo(s8.z);
+                        v[8 * u + 5] = leaky_relu(v[8 * u + 5] + b1.y) + bf16_hi(s8.z);
+                        v[8 * u + 6] = leaky_relu(v[8 * u + 6] + b1.z) + bf16_lo(s8.w);
+                        v[8 * u + 7] = leaky_relu(v[8 * u + 7] + b1.w) + bf16_hi(s8.w);
                     }
                     if (!last) {
                         tmem_st32(taddr + col0, v);
@@ -412,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
                 float vt[3] = {hp0 + s_headp[r * 4], hp1 + s_headp[r * 4 + 1], hp2 + s_headp[r * 4 + 2]};
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
-                    float acc = vt[d] + __ldg(tbr + 1792 + d);
+                    float acc = vt[d] + tbr[1792 + d];
 #pragma unroll
                     for (int q = 0; q < 16; ++q) acc = fmaf(__ldg(a.p.wh_glob + d * 16 + q), g[q], acc);
                     vt[d] = acc;

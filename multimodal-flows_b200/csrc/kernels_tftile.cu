@@ -392,8 +392,10 @@ __device__ __forceinline__ void attention_unit(Epi& e, const float* bq, const fl
 template <int V>
 __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_constant__ TfLaunch a, const __grid_constant__ TfOpTable optab,
                                                               const __grid_constant__ TfProdTable prodtab) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // The dynamic shared window starts 1024-byte aligned (no static shared memory in this kernel); it is used directly so
+    // that the compiler keeps the shared address space (LDS/STS instead of generic loads).  SWIZZLE_128B needs the alignment.
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     TfBars* bars = reinterpret_cast<TfBars*>(smem);
     uint8_t* arena = smem + 1024;
     float* pbuf = reinterpret_cast<float*>(arena + kArena);
