@@ -105,12 +105,13 @@ __device__ __forceinline__ float global_out16(const float* W2 /* shared memory *
     const int j = tid >> 5, q = (tid >> 1) & 15, half = tid & 1;
     const float4* w = reinterpret_cast<const float4*>(W2 + q * 256 + half * 128);
     const float4* h = reinterpret_cast<const float4*>(s_hid + j * 256 + half * 128);
-    float acc = 0.f;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;             // four independent chains
 #pragma unroll
     for (int o = 0; o < 32; ++o) {
         const float4 a = w[o], b = h[o];
-        acc = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, acc))));
+        a0 = fmaf(a.x, b.x, a0); a1 = fmaf(a.y, b.y, a1); a2 = fmaf(a.z, b.z, a2); a3 = fmaf(a.w, b.w, a3);
     }
+    float acc = (a0 + a1) + (a2 + a3);
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     return acc + __ldg(b2 + q);
 }
