@@ -1,8 +1,9 @@
 // Persistent per-tile ParticleFormer / FusedParticleFormer sampler (see mmf_tftile.h for the data layout).
 //
 // warps 0..7   epilogue / SIMT: thread = (row r, column half hf); runs the hand-written per-timestep program
-// warp  8      lane 0: producer - walks the op table, streams weight tiles and parameter blobs with 1-D bulk copies
-// warp  9      lane 0: tcgen05.mma issuer - walks the op table
+// warp  8      parameter producer: streams the per-stage parameter blobs into the double buffer
+// warp  9      tcgen05.mma issuer - walks the op table (one elected lane issues)
+// warps 10,11  weight producers: stream the weight tiles into the ring with 1-D bulk copies, alternating tiles
 //
 // Synchronisation: `go` (256 arrivals) epilogue -> MMA issuer, consumed in order by the ops flagged `wait`;
 // `done[0/1]` (tcgen05.commit) MMA -> epilogue; full/empty ring barriers producer <-> MMA issuer;
@@ -17,7 +18,7 @@ namespace {
 
 constexpr int kEpi = 256;
 constexpr int kThreads = 384;
-constexpr int kProducers = 3;              // warps 8, 10, 11: issuing one bulk copy costs a warp ~700 cycles, so tiles are dealt round robin
+constexpr int kProducers = 2;              // warps 10, 11: weight tiles are dealt round robin
 constexpr int kStages = 4;
 constexpr int kTile = 16384;
 #ifndef MMF_COPY_SPLIT
@@ -228,15 +229,17 @@ __device__ __forceinline__ void ln_regs(float* v, const float* g, const float* b
 }
 
 // ---- attention epilogues -----------------------------------------------------------------------------------------
-// QKV of one 64-column unit sits in scratch: q [0,64) k [64,128) v [128,192).  hf 0: q and v[0,32); hf 1: k and v[32,64).
+// QKV of one 64-column unit sits in scratch (q | k | v, 64 columns each).  hf 0: q and v[0,32); hf 1: k and v[32,64).
 // bq/bk/bv point at the unit's 64 bias values; qg.. are the per-head LayerNorm parameters ([HS]).
 template <int HS>
 __device__ __forceinline__ void qkv_epilogue(Epi& e, const float* bq, const float* bk, const float* bv, const float* qg,
                                              const float* qb, const float* kg, const float* kb) {
+    // scratch columns of q|k and v (see the op emission in tftile_model.cu)
+    constexpr uint32_t cQK = HS == 64 ? kScr : kScr + 128, cV = HS == 64 ? kScr + 128 : kScr + 64;
     {
         float v[64];
-        tmem_ld32(e.taddr + kScr + e.hf * 64, v);
-        tmem_ld32(e.taddr + kScr + e.hf * 64 + 32, v + 32);
+        tmem_ld32(e.taddr + cQK + e.hf * 64, v);
+        tmem_ld32(e.taddr + cQK + e.hf * 64 + 32, v + 32);
         tmem_ld_wait();
         const float* bias = e.hf ? bk : bq;
 #pragma unroll
@@ -254,7 +257,7 @@ __device__ __forceinline__ void qkv_epilogue(Epi& e, const float* bq, const floa
     }
     {
         float w[32];
-        tmem_ld32(e.taddr + kScr + 128 + e.hf * 32, w);
+        tmem_ld32(e.taddr + cV + e.hf * 32, w);
         tmem_ld_wait();
         // V^T[d][key = r]: two chunks of 64 keys, 64 rows (d) of 128 bytes each
         uint8_t* vt = e.arena + oVT + (e.r >> 6) * 8192 + (e.r & 7) * 2;
@@ -365,7 +368,7 @@ template <int HS>
 __device__ __forceinline__ void attention_unit(Epi& e, const float* bq, const float* bk, const float* bv, const float* qg,
                                                const float* qb, const float* kg, const float* kb, int seg_b, int seg_e) {
     const float scale = 1.4426950408889634f * rsqrtf(static_cast<float>(HS));
-    wait_done(e, 0);
+    wait_done(e, 1);                                  // QKV of this unit (issued under the previous unit's epilogue)
     qkv_epilogue<HS>(e, bq, bk, bv, qg, qb, kg, kb);
     go(e);
     if (HS == 64) {
@@ -429,88 +432,98 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
 
     // The producer and MMA warps run their loops with all 32 lanes converged (loop state and op fields stay in uniform
     // registers, the tables sit in the constant bank); one elected lane issues the asynchronous instructions.
-    if (warp == 8 || warp >= 10) {
-        // ---------------------------------------------------- producers ---------------------------------------------
-        const uint32_t pw = warp == 8 ? 0u : static_cast<uint32_t>(warp - 9);      // 0, 1, 2
-        uint32_t it = 0, pcount = 0;
+    if (warp == 8) {
+        // ---------------------------------------------------- parameter producer ------------------------------------
+        // Blobs are consumed in index order; blob c goes to slot c & 1 as soon as the epilogue warps released blob c - 2.
+        uint32_t pcount = 0;
         for (int step = 0; step < a.nsteps; ++step) {
-            size_t woff = 0;
-            for (int i = 0; i < a.n_prod; ++i) {
-                const uint32_t ent = prodtab.e[i];
-                if (ent & 0x8000u) {                          // parameter blob (ent & 0x7fff) -> slot pcount & 1
-                    if (pw != 0) continue;
-                    const uint32_t p = pcount & 1;
-                    if (pcount >= 2) mbar_wait(&bars->pempty[p], ((pcount >> 1) - 1) & 1);
-                    if (elect_one()) {
-                        mbar_expect_tx(&bars->pfull[p], kTfParamFloats * 4);
-                        bulk_load_1d(pbuf + p * kTfParamFloats, a.params + static_cast<size_t>(ent & 0x7fffu) * kTfParamFloats,
-                                     kTfParamFloats * 4, &bars->pfull[p]);
-                    }
-                    __syncwarp();
-                    ++pcount;
-                } else {                                      // weight tile of `ent` rows x 64 columns
-                    const uint32_t s = it % kStages, bytes = ent * 128u;
-                    if (it % kProducers != pw) { woff += bytes; ++it; continue; }
-                    if (it >= kStages) mbar_wait(&bars->empty[s], ((it / kStages) - 1) & 1);
-                    if (elect_one()) {
-                        mbar_expect_tx(&bars->full[s], bytes);
-                        // several smaller copies per tile: the copy engine overlaps them (one 16 KB copy takes ~2.5k cycles)
-                        const uint32_t slice = bytes / cs, part = slice / kCopySplit;
-                        uint8_t* dst = arena + oRing + s * kTile + crank * slice;
-                        const uint8_t* src = a.wstream + woff + crank * slice;
-#pragma unroll
-                        for (int c = 0; c < kCopySplit; ++c) {
-                            if (cs == 1) bulk_load_1d(dst + c * part, src + c * part, part, &bars->full[s]);
-                            else bulk_load_1d_multicast(dst + c * part, src + c * part, part, &bars->full[s], cmask);
-                        }
-                    }
-                    __syncwarp();
-                    woff += bytes;
-                    ++it;
+            for (int i = 0; i < a.n_blobs; ++i) {
+                const uint32_t p = pcount & 1;
+                if (pcount >= 2) mbar_wait(&bars->pempty[p], ((pcount >> 1) - 1) & 1);
+                if (elect_one()) {
+                    mbar_expect_tx(&bars->pfull[p], kTfParamFloats * 4);
+                    bulk_load_1d(pbuf + p * kTfParamFloats, a.params + static_cast<size_t>(i) * kTfParamFloats, kTfParamFloats * 4, &bars->pfull[p]);
                 }
+                __syncwarp();
+                ++pcount;
+            }
+        }
+    } else if (warp >= 10) {
+        // ---------------------------------------------------- weight producers --------------------------------------
+        const uint32_t pw = static_cast<uint32_t>(warp - 10);
+        uint32_t it = pw;                                     // ring tile counter over the whole launch
+        for (int step = 0; step < a.nsteps; ++step) {
+            for (int i = pw; i < a.n_prod; i += kProducers, it += kProducers) {
+                const uint32_t ent = prodtab.e[i];
+                const uint32_t s = it % kStages, bytes = (ent & 0xffu) * 1024u;
+                if (it >= kStages) mbar_wait(&bars->empty[s], ((it / kStages) - 1) & 1);
+                if (elect_one()) {
+                    mbar_expect_tx(&bars->full[s], bytes);
+                    const uint32_t slice = bytes / cs, part = slice / kCopySplit;
+                    uint8_t* dst = arena + oRing + s * kTile + crank * slice;
+                    const uint8_t* src = a.wstream + static_cast<size_t>(ent >> 8) * 128u + crank * slice;
+#pragma unroll
+                    for (int c = 0; c < kCopySplit; ++c) {
+                        if (cs == 1) bulk_load_1d(dst + c * part, src + c * part, part, &bars->full[s]);
+                        else bulk_load_1d_multicast(dst + c * part, src + c * part, part, &bars->full[s], cmask);
+                    }
+                }
+                __syncwarp();
             }
         }
     } else if (warp == 9) {
         // ---------------------------------------------------- MMA issuer --------------------------------------------
+        // All 32 lanes run the loop converged (op fields stay in uniform registers, the table sits in the constant bank);
+        // one elected lane issues the asynchronous instructions.  Descriptors come precomputed from the host.
         uint32_t it = 0, pg = 0;
-        const uint32_t arena_u32 = smem_u32(arena);
+        const uint32_t base16 = smem_u32(arena) >> 4;
+        const uint32_t ring16 = base16 + (oRing >> 4) + (1u << 16);
+        constexpr uint64_t kDescHi = static_cast<uint64_t>(0x40004040u) << 32;   // SBO 1024 B | version 1 | SWIZZLE_128B
         for (int step = 0; step < a.nsteps; ++step) {
-            bool pre_ok = false;                              // the ring tile of the current op was already seen complete
             TfOp nx = optab.ops[0];
             for (int i = 0; i < a.n_ops; ++i) {
                 const TfOp op = nx;
                 if (i + 1 < a.n_ops) nx = optab.ops[i + 1];   // fetched one op ahead
-                if (op.wait) {
+                const uint32_t fl = op.flags;
+                if (fl & kTfOpWait) {
                     mbar_wait(&bars->go, pg);
                     pg ^= 1;
                 }
-                const bool ring = op.b_off == kTfRing;
-                const uint32_t s = it % kStages;
-                if (ring && !pre_ok) mbar_wait(&bars->full[s], (it / kStages) & 1);
-                tc_fence_after();
-                // look at the next op's weight tile now: the (non-blocking) barrier read overlaps the MMA issue below
-                pre_ok = false;
-                if (i + 1 < a.n_ops && nx.b_off == kTfRing) {
-                    const uint32_t it2 = it + (ring ? 1u : 0u);
-                    pre_ok = mbar_test_wait(&bars->full[it2 % kStages], (it2 / kStages) & 1);
-                }
-                const uint64_t db = umma_desc_sw128(arena_u32 + (ring ? oRing + s * kTile : op.b_off));
-                const uint64_t da = umma_desc_sw128(arena_u32 + op.a_off);
-                const uint32_t idesc = umma_idesc_bf16(128, op.n);
-                if (elect_one()) {
-                    umma_bf16(tmem_base + op.dcol, da, db, idesc, op.acc);
-                    umma_bf16(tmem_base + op.dcol, da + 2, db + 2, idesc, 1u);
-                    if (op.nk16 == 4) {
-                        umma_bf16(tmem_base + op.dcol, da + 4, db + 4, idesc, 1u);
-                        umma_bf16(tmem_base + op.dcol, da + 6, db + 6, idesc, 1u);
-                    }
+                const bool ring = (fl & kTfOpRing) != 0;
+                uint32_t a_lo = op.a_lo + base16, b_lo = op.b_lo + base16, acc = fl & kTfOpAcc;
+                const uint32_t d = tmem_base + op.dcol;
+                for (uint32_t kt = 0; kt < op.nkt; ++kt) {
+                    const uint32_t s = it % kStages;
                     if (ring) {
-                        if (cs == 1) umma_commit(&bars->empty[s]); else umma_commit_multicast(&bars->empty[s], cmask);
+                        mbar_wait(&bars->full[s], (it / kStages) & 1);
+                        b_lo = ring16 + s * (kTile >> 4);
+                        ++it;
                     }
-                    if (op.signal) umma_commit(&bars->done[op.signal - 1]);
-                    if (a.trace && blockIdx.x == 0 && step == 1 && i < 128) a.trace[768 + i] = clock64();
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t da = kDescHi | a_lo, db = kDescHi | b_lo;
+                        umma_bf16(d, da, db, op.idesc, acc);
+                        umma_bf16(d, da + 2, db + 2, op.idesc, 1u);
+                        if (!(fl & kTfOpHalfK)) {
+                            umma_bf16(d, da + 4, db + 4, op.idesc, 1u);
+                            umma_bf16(d, da + 6, db + 6, op.idesc, 1u);
+                        }
+                        if (ring) {
+                            if (cs == 1) umma_commit(&bars->empty[s]); else umma_commit_multicast(&bars->empty[s], cmask);
+                        }
+                    }
+                    __syncwarp();
+                    a_lo += kTile >> 4;
+                    b_lo += 8192 >> 4;
+                    acc = 1u;
                 }
-                if (ring) ++it;
+                if (fl & 0x30u) {
+                    if (elect_one()) {
+                        umma_commit(&bars->done[(fl >> 5) & 1u]);
+                        if (a.trace && blockIdx.x == 0 && step == 1 && i < 128) a.trace[768 + i] = clock64();
+                    }
+                    __syncwarp();
+                }
             }
         }
         __syncwarp();

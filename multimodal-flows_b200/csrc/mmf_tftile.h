@@ -15,8 +15,6 @@
 
 namespace mmf {
 
-constexpr uint32_t kTfRing = 0xFFFFFFFFu;       // TfOp.b_off: B operand is the next tile of the weight stream
-constexpr uint32_t kTfParam = 0xFFFFFFFEu;      // TfOp.b_off: not an MMA - load parameter blob (a_off = byte offset, n = bytes/16)
 constexpr int kTfParamFloats = 2304;            // floats per parameter blob slot
 
 // float offsets inside the parameter blobs (one blob per stage of the per-timestep program, <= kTfParamFloats each)
@@ -58,15 +56,21 @@ constexpr int HY_W2 = 128;                       // [V][128] head_y.2 weight, th
 constexpr int HY_B2 = 128 + 12 * 128;            // [V] (first quarter only), V <= 12
 }  // namespace tfp
 
-struct TfOp {               // one tensor-core k-tile: nk16 MMAs of K = 16
-    uint32_t a_off;         // A operand slice, byte offset inside the shared-memory operand arena
-    uint32_t b_off;         // B operand slice in the arena, or kTfRing / kTfParam
-    uint16_t n;             // MMA N = rows of B (multiple of 16)
+// One tensor-core operation = `nkt` k-tiles (K = 64 each, or one K = 32 k-tile) accumulated into the same D columns.
+// Everything the issuing warp needs is precomputed on the host: the low words of the shared-memory matrix
+// descriptors (relative to the operand arena) and the instruction descriptor.
+//   A advances by one 16 KB chunk per k-tile; B is the next `nkt` tiles of the weight ring, or an arena slice
+//   advancing by 8 KB per k-tile (V^T halves of the P V product).
+constexpr uint32_t kTfOpAcc = 1u, kTfOpWait = 2u, kTfOpRing = 4u, kTfOpHalfK = 8u;   // TfOp.flags
+struct TfOp {
+    uint32_t a_lo;          // (arena offset of A >> 4) | LBO field of the descriptor low word
+    uint32_t b_lo;          // same for B when it lives in the arena (ignored for ring operands)
+    uint32_t idesc;         // kind::f16 instruction descriptor (M = 128, N)
     uint16_t dcol;          // TMEM column of D (relative to the allocation base)
-    uint8_t nk16;           // K = 16 steps in this k-tile (4 = one 128-byte swizzled row)
-    uint8_t acc;            // 1: accumulate onto D; 0: the first MMA overwrites
-    uint8_t wait;           // 1: wait for the next "go" of the epilogue warps before issuing
-    uint8_t signal;         // after this k-tile: 0 nothing, 1 commit -> done[0], 2 commit -> done[1]
+    uint8_t nkt;            // k-tiles
+    uint8_t flags;          // kTfOpAcc: the first MMA accumulates onto D; kTfOpWait: wait for the next "go" of the epilogue
+                            // warps first; kTfOpRing: B from the weight ring; kTfOpHalfK: K = 32 (2 MMAs) instead of 64 (4);
+                            // bits 4-5: after the last k-tile 0 nothing, 1 commit -> done[0], 2 commit -> done[1]
 };
 static_assert(sizeof(TfOp) == 16, "TfOp is read with one 128-bit load");
 
@@ -74,8 +78,8 @@ constexpr int kTfMaxOps = 1024;
 struct TfOpTable {          // MMA ops of one timestep; passed to the kernel BY VALUE (constant bank -> uniform registers)
     TfOp ops[kTfMaxOps];
 };
-struct TfProdTable {        // producer program of one timestep: rows of the next weight tile, or 0x8000 | parameter blob index
-    uint16_t e[2 * kTfMaxOps];
+struct TfProdTable {        // weight tiles of one timestep in consumption order: (offset in the stream / 128) << 8 | rows / 8
+    uint32_t e[kTfMaxOps];
 };
 
 struct TfTileMeta {
@@ -104,7 +108,8 @@ struct TfLaunch {
     int vocab;
     const TfOpTable* optab; // HOST pointers: the tables of one timestep, copied into the kernel parameters at launch
     const TfProdTable* prodtab;
-    int n_ops, n_prod;
+    int n_ops, n_prod;      // ops of the MMA issuer; weight tiles of the producers
+    int n_blobs;            // parameter blobs per timestep (consumed in index order)
     const uint8_t* wstream; // weight tiles in op order
     const float* params;    // parameter blobs, kTfParamFloats apart
     const TfTileMeta* meta;

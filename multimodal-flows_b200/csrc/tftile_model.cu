@@ -16,7 +16,7 @@ struct TfTileModel {
     DeviceArena arena;
     std::unique_ptr<TfOpTable> optab;                   // host copies, passed by value at every launch
     std::unique_ptr<TfProdTable> prodtab;
-    int n_ops = 0, n_prod = 0;
+    int n_ops = 0, n_prod = 0, n_blobs = 0;
     const uint8_t* d_wstream = nullptr;
     const float* d_params = nullptr;
     std::vector<float> time_expand_w, time_expand_b;     // ParticleFormer, host fp32
@@ -41,36 +41,37 @@ namespace {
 // operand arena offsets: keep in sync with kernels_tftile.cu
 constexpr uint32_t kT = 16384, oA = 0, oQ = 65536, oK = oQ + kT, oVT = oK + kT, oO = oVT + kT, oH0 = oQ, oH1 = oVT;
 
+uint32_t desc_lo(uint32_t arena_off) { return (arena_off >> 4) | (1u << 16); }
+uint32_t idesc_bf16(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24); }
+
 struct Builder {
     std::vector<TfOp> ops;
+    std::vector<uint32_t> tiles;                     // producer table
     std::vector<uint16_t> stream;
     std::vector<float> params;
-    int stage = 0;                                   // blobs emitted so far
 
-    void param_op(int blob) {
-        TfOp o{};
-        o.a_off = static_cast<uint32_t>(blob) * kTfParamFloats * 4;
-        o.b_off = kTfParam;
-        o.n = kTfParamFloats * 4 / 16;
-        ops.push_back(o);
-    }
-    // rows[i] = pointer to the start of a weight row (fp32, K-contiguous); k0 = first input column of this k-tile
-    void ring_op(uint32_t a_off, const std::vector<const float*>& rows, int k0, uint16_t dcol, int acc, int wait, int signal) {
+    // rows[i] = pointer to the start of a weight row (fp32, K-contiguous); the op covers input columns [k0, k0 + 64 nkt)
+    // and A chunks a_off, a_off + 16 KB, ...
+    void ring_op(uint32_t a_off, const std::vector<const float*>& rows, int k0, int nkt, uint16_t dcol, int acc, int wait, int signal) {
         const int n = static_cast<int>(rows.size());
-        const size_t base = stream.size();
-        stream.resize(base + static_cast<size_t>(n) * 64);
-        for (int rr = 0; rr < n; ++rr)
-            for (int e = 0; e < 64; ++e)
-                stream[base + static_cast<size_t>(rr) * 64 + (((e >> 3) ^ (rr & 7)) << 3) + (e & 7)] = f32_to_bf16_bits(rows[rr][k0 + e]);
+        for (int kt = 0; kt < nkt; ++kt) {
+            const size_t base = stream.size();
+            tiles.push_back(static_cast<uint32_t>(base / 64) << 8 | static_cast<uint32_t>(n / 8));
+            stream.resize(base + static_cast<size_t>(n) * 64);
+            for (int rr = 0; rr < n; ++rr)
+                for (int e = 0; e < 64; ++e)
+                    stream[base + static_cast<size_t>(rr) * 64 + (((e >> 3) ^ (rr & 7)) << 3) + (e & 7)] = f32_to_bf16_bits(rows[rr][k0 + kt * 64 + e]);
+        }
         TfOp o{};
-        o.a_off = a_off; o.b_off = kTfRing; o.n = static_cast<uint16_t>(n); o.dcol = dcol; o.nk16 = 4;
-        o.acc = static_cast<uint8_t>(acc); o.wait = static_cast<uint8_t>(wait); o.signal = static_cast<uint8_t>(signal);
+        o.a_lo = desc_lo(a_off); o.b_lo = 0; o.idesc = idesc_bf16(n); o.dcol = dcol; o.nkt = static_cast<uint8_t>(nkt);
+        o.flags = static_cast<uint8_t>((acc ? kTfOpAcc : 0u) | (wait ? kTfOpWait : 0u) | kTfOpRing | (static_cast<uint32_t>(signal) << 4));
         ops.push_back(o);
     }
-    void smem_op(uint32_t a_off, uint32_t b_off, int n, uint16_t dcol, int nk16, int acc, int wait, int signal) {
+    // both operands in the arena; B advances by 8 KB per k-tile
+    void smem_op(uint32_t a_off, uint32_t b_off, int n, uint16_t dcol, int nkt, bool half_k, int acc, int wait, int signal) {
         TfOp o{};
-        o.a_off = a_off; o.b_off = b_off; o.n = static_cast<uint16_t>(n); o.dcol = dcol; o.nk16 = static_cast<uint8_t>(nk16);
-        o.acc = static_cast<uint8_t>(acc); o.wait = static_cast<uint8_t>(wait); o.signal = static_cast<uint8_t>(signal);
+        o.a_lo = desc_lo(a_off); o.b_lo = desc_lo(b_off); o.idesc = idesc_bf16(n); o.dcol = dcol; o.nkt = static_cast<uint8_t>(nkt);
+        o.flags = static_cast<uint8_t>((acc ? kTfOpAcc : 0u) | (wait ? kTfOpWait : 0u) | (half_k ? kTfOpHalfK : 0u) | (static_cast<uint32_t>(signal) << 4));
         ops.push_back(o);
     }
     float* blob(int idx) {
@@ -106,24 +107,18 @@ BlockW load_block(WeightMap& wm, const std::string& p, int C, int I) {
 }
 
 // MLP of one group: quarters of the hidden layer ping-pong through the two scratch halves
-// `prefetch_blob` >= 0: the parameter blob of the NEXT stage is requested after the first up-projection quarter
-void emit_mlp(Builder& b, const BlockW& w, int C, int a_chunk0, uint16_t dcol_out, bool first_wait, bool final_signal, int prefetch_blob) {
+void emit_mlp(Builder& b, const BlockW& w, int C, int a_chunk0, uint16_t dcol_out, bool first_wait, bool final_signal) {
     const int kbC = C / 64, nh = C / 128;
     auto fc = [&](int q) {
-        for (int kb = 0; kb < kbC; ++kb)
-            b.ring_op(oA + (a_chunk0 + kb) * kT, rows_of(w.fc, q * 128, 128), kb * 64, static_cast<uint16_t>(256 + (q & 1) * 128), kb > 0,
-                      first_wait && q == 0 && kb == 0, kb == kbC - 1 ? 1 + (q & 1) : 0);
+        b.ring_op(oA + a_chunk0 * kT, rows_of(w.fc, q * 128, 128), 0, kbC, static_cast<uint16_t>(256 + (q & 1) * 128), 0,
+                  first_wait && q == 0, 1 + (q & 1));
     };
     auto out = [&](int q) {
-        for (int kb = 0; kb < 2; ++kb)
-            for (int h = 0; h < nh; ++h)
-                b.ring_op(((q & 1) ? oH1 : oH0) + kb * kT, rows_of(w.p2, h * 128, 128), q * 128 + kb * 64,
-                          static_cast<uint16_t>(dcol_out + h * 128), 1, kb == 0 && h == 0,
-                          (final_signal && q == 3 && kb == 1 && h == nh - 1) ? 1 : 0);
+        for (int h = 0; h < nh; ++h)
+            b.ring_op((q & 1) ? oH1 : oH0, rows_of(w.p2, h * 128, 128), q * 128, 2, static_cast<uint16_t>(dcol_out + h * 128), 1, h == 0,
+                      (final_signal && q == 3 && h == nh - 1) ? 1 : 0);
     };
-    fc(0);
-    if (prefetch_blob >= 0) b.param_op(prefetch_blob);
-    fc(1); out(0); fc(2); out(1); fc(3); out(2); out(3);
+    fc(0); fc(1); out(0); fc(2); out(1); fc(3); out(2); out(3);
 }
 
 }  // namespace
@@ -148,7 +143,7 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
         put(P + tfp::EA_BXE2, wm.get(t + "wxe.2.bias", h));
         put(P + tfp::EA_LN1X_G, wm.get(t + "ln1_x.weight", h));
         put(P + tfp::EA_LN1X_B, wm.get(t + "ln1_x.bias", h, -1, true));
-        b.param_op(blob_idx++);
+        ++blob_idx;
         P = b.blob(blob_idx);
         // discrete embedding branch folded into a V x 128 table (reference ParticleTransformers.py:95-96, 190-191)
         const std::vector<float> emb = wm.get(t + "wye.0.weight", V, E), w2 = wm.get(t + "wye.2.weight", h, E), b2 = wm.get(t + "wye.2.bias", h),
@@ -173,11 +168,9 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
         } else {
             put(P + tfp::EB_LNN_G, wm.get(t + "blocks.0.ln1.weight", E)); put(P + tfp::EB_LNN_B, wm.get(t + "blocks.0.ln1.bias", E, -1, true));
         }
-        b.param_op(blob_idx++);
+        ++blob_idx;
         const Mat wxe2 = mat(wm, t + "wxe.2.weight", h, E);
-        for (int kb = 0; kb < 4; ++kb) b.ring_op(oA + kb * kT, rows_of(wxe2, 0, 128), kb * 64, 256, kb > 0, kb == 0, kb == 3 ? 1 : 0);
-        // (the first block's attention blob is requested once the embedding epilogue has released a slot: the producer blocks until then)
-        b.param_op(blob_idx);
+        b.ring_op(oA, rows_of(wxe2, 0, 128), 0, 4, 256, 0, 1, 1);
     }
 
     // ---------------- stream blocks (ParticleFormer): groups x | y, C = 128, head size 32, units = head pairs
@@ -210,26 +203,28 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
             }
         }
         ++blob_idx;                                      // -> this block's MLP blob
+        // Scratch columns of a unit: S_h0 [256,384) S_h1 [384,512); O_h0 [256,288) O_h1 [288,320) (over the consumed S_h0);
+        // Q|K [384,512), V [320,384).  The QKV product of the NEXT unit is issued right after the last P V of this one: by
+        // then both score tiles are consumed and the O columns are not touched, so it runs under the epilogue of this unit.
+        auto qkv = [&](int g, int u, int wait) {
+            // rows of c_attn: q [0,128) k [128,256) v [256,384); unit u = heads 2u, 2u+1 = columns u*64..u*64+63
+            std::vector<const float*> qk = rows_of(w[g].attn, u * 64, 64), kk = rows_of(w[g].attn, 128 + u * 64, 64);
+            qk.insert(qk.end(), kk.begin(), kk.end());
+            b.ring_op(oA + 2 * g * kT, qk, 0, 2, 384, 0, wait, 0);
+            b.ring_op(oA + 2 * g * kT, rows_of(w[g].attn, 256 + u * 64, 64), 0, 2, 320, 0, 0, 2);
+        };
+        qkv(0, 0, 1);
         for (int g = 0; g < 2; ++g)
             for (int u = 0; u < 2; ++u) {
-                // rows of c_attn: q [0,128) k [128,256) v [256,384); unit u = heads 2u, 2u+1 = columns u*64..u*64+63
-                std::vector<const float*> qk = rows_of(w[g].attn, u * 64, 64), kk = rows_of(w[g].attn, 128 + u * 64, 64);
-                qk.insert(qk.end(), kk.begin(), kk.end());
-                for (int kb = 0; kb < 2; ++kb) {
-                    b.ring_op(oA + (2 * g + kb) * kT, qk, kb * 64, 256, kb > 0, g == 0 && u == 0 && kb == 0, 0);
-                    b.ring_op(oA + (2 * g + kb) * kT, rows_of(w[g].attn, 256 + u * 64, 64), kb * 64, 384, kb > 0, 0, kb == 1 ? 1 : 0);
-                }
-                b.smem_op(oQ, oK, 128, 256, 2, 0, 1, 0);                     // S of head 0 of the pair
-                b.smem_op(oQ + 64, oK + 64, 128, 384, 2, 0, 0, 1);           // S of head 1
-                b.smem_op(oQ, oVT, 32, 256, 4, 0, 1, 0);                     // O_h0 = P_h0 V_h0, keys 0..63
-                b.smem_op(oK, oVT + 8192, 32, 256, 4, 1, 0, 2);              //                   keys 64..127
-                b.smem_op(oQ, oVT + 4096, 32, 288, 4, 0, 1, 0);              // O_h1
-                b.smem_op(oK, oVT + 8192 + 4096, 32, 288, 4, 1, 0, 1);
-                b.ring_op(oO, rows_of(w[g].proj, 0, 128), u * 64, static_cast<uint16_t>(g * 128), 1, 1, (g == 1 && u == 1) ? 1 : 0);
+                b.smem_op(oQ, oK, 128, 256, 1, true, 0, 1, 0);               // S of head 0 of the pair
+                b.smem_op(oQ + 64, oK + 64, 128, 384, 1, true, 0, 0, 1);     // S of head 1
+                b.smem_op(oQ, oVT, 32, 256, 2, false, 0, 1, 2);              // O_h0 = P_h0 V_h0 (keys 0..63, 64..127)
+                b.smem_op(oQ, oVT + 4096, 32, 288, 2, false, 0, 1, 1);       // O_h1
+                if (!(g == 1 && u == 1)) qkv(u == 1 ? 1 : g, u == 1 ? 0 : 1, 0);
+                b.ring_op(oO, rows_of(w[g].proj, 0, 128), u * 64, 1, static_cast<uint16_t>(g * 128), 1, 1, (g == 1 && u == 1) ? 1 : 0);
             }
-        // parameter prefetch: this block's MLP blob once the attention is under way, the next stage's blob inside the MLP
-        b.param_op(blob_idx++);
-        for (int g = 0; g < 2; ++g) emit_mlp(b, w[g], 128, 2 * g, static_cast<uint16_t>(g * 128), g == 0, g == 1, g == 0 ? blob_idx : -1);
+        ++blob_idx;
+        for (int g = 0; g < 2; ++g) emit_mlp(b, w[g], 128, 2 * g, static_cast<uint16_t>(g * 128), g == 0, g == 1);
     }
 
     // ---------------- main blocks: C = 256, head size 64, units = heads
@@ -258,21 +253,24 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
             }
         }
         ++blob_idx;                                      // -> this block's MLP blob
-        for (int u = 0; u < 4; ++u) {
+        // Scratch columns of a unit: Q|K [256,384), V [384,448); S [256,384); O [448,512).  QKV of the next unit is issued
+        // right after P V (S is consumed, O is elsewhere) and runs under the O / projection epilogue of this unit.
+        auto qkv = [&](int u, int wait) {
             std::vector<const float*> qk = rows_of(w.attn, u * 64, 64), kk = rows_of(w.attn, 256 + u * 64, 64);
             qk.insert(qk.end(), kk.begin(), kk.end());
-            for (int kb = 0; kb < 4; ++kb) {
-                b.ring_op(oA + kb * kT, qk, kb * 64, 256, kb > 0, u == 0 && kb == 0, 0);
-                b.ring_op(oA + kb * kT, rows_of(w.attn, 512 + u * 64, 64), kb * 64, 384, kb > 0, 0, kb == 3 ? 1 : 0);
-            }
-            b.smem_op(oQ, oK, 128, 256, 4, 0, 1, 1);                         // S = Q K^T
-            b.smem_op(oQ, oVT, 64, 448, 4, 0, 1, 0);                         // O = P V
-            b.smem_op(oK, oVT + 8192, 64, 448, 4, 1, 0, 1);
+            b.ring_op(oA, qk, 0, 4, 256, 0, wait, 0);
+            b.ring_op(oA, rows_of(w.attn, 512 + u * 64, 64), 0, 4, 384, 0, 0, 2);
+        };
+        qkv(0, 1);
+        for (int u = 0; u < 4; ++u) {
+            b.smem_op(oQ, oK, 128, 256, 1, false, 0, 1, 1);                  // S = Q K^T
+            b.smem_op(oQ, oVT, 64, 448, 2, false, 0, 1, 1);                  // O = P V
+            if (u < 3) qkv(u + 1, 0);
             for (int nh = 0; nh < 2; ++nh)
-                b.ring_op(oO, rows_of(w.proj, nh * 128, 128), u * 64, static_cast<uint16_t>(nh * 128), 1, nh == 0, (u == 3 && nh == 1) ? 1 : 0);
+                b.ring_op(oO, rows_of(w.proj, nh * 128, 128), u * 64, 1, static_cast<uint16_t>(nh * 128), 1, nh == 0, (u == 3 && nh == 1) ? 1 : 0);
         }
-        b.param_op(blob_idx++);
-        emit_mlp(b, w, 256, 0, 0, true, true, blob_idx);
+        ++blob_idx;
+        emit_mlp(b, w, 256, 0, 0, true, true);
     }
 
     // ---------------- heads: Linear(128,512) + GELU on tensor cores, Linear(512, 3 | V) on CUDA cores
@@ -293,12 +291,7 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
         for (int hq = 0; hq < 8; ++hq) {
             const Mat& w = hq < 4 ? hx : hy;
             const int chunk0 = hq < 4 ? 0 : 2;
-            for (int kb = 0; kb < 2; ++kb)
-                b.ring_op(oA + (chunk0 + kb) * kT, rows_of(w, (hq & 3) * 128, 128), kb * 64, static_cast<uint16_t>(256 + (hq & 1) * 128), kb > 0,
-                          kb == 0 && hq != 1, kb == 1 ? 1 + (hq & 1) : 0);
-            // head_y quarter blobs: the first when head_x is under way, then one per consumed quarter
-            if (hq == 0) b.param_op(blob_idx + 1);
-            if (hq >= 3 && hq < 6) b.param_op(blob_idx + hq - 1);
+            b.ring_op(oA + chunk0 * kT, rows_of(w, (hq & 3) * 128, 128), 0, 2, static_cast<uint16_t>(256 + (hq & 1) * 128), 0, hq != 1, 1 + (hq & 1));
         }
         blob_idx += 5;
     }
@@ -310,24 +303,17 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
     b.params.resize(static_cast<size_t>(blob_idx) * kTfParamFloats, 0.f);
 
     DeviceArena& ar = m->arena;
-    // split the builder's sequence into the MMA issuer's table and the producer's table
+    MMF_REQUIRE(b.ops.size() <= static_cast<size_t>(kTfMaxOps) && b.tiles.size() <= static_cast<size_t>(kTfMaxOps),
+                "tile kernel: op table too long for the kernel parameter space");
     m->optab.reset(new TfOpTable());
     m->prodtab.reset(new TfProdTable());
     memset(m->optab.get(), 0, sizeof(TfOpTable));
     memset(m->prodtab.get(), 0, sizeof(TfProdTable));
-    for (const TfOp& o : b.ops) {
-        if (o.b_off == kTfParam) {
-            MMF_REQUIRE(m->n_prod < 2 * kTfMaxOps, "tile kernel: producer table too long");
-            m->prodtab->e[m->n_prod++] = static_cast<uint16_t>(0x8000u | (o.a_off / (kTfParamFloats * 4)));
-            continue;
-        }
-        if (o.b_off == kTfRing) {
-            MMF_REQUIRE(m->n_prod < 2 * kTfMaxOps, "tile kernel: producer table too long");
-            m->prodtab->e[m->n_prod++] = o.n;
-        }
-        MMF_REQUIRE(m->n_ops < kTfMaxOps && (o.nk16 == 2 || o.nk16 == 4), "tile kernel: op table too long for the kernel parameter space");
-        m->optab->ops[m->n_ops++] = o;
-    }
+    std::copy(b.ops.begin(), b.ops.end(), m->optab->ops);
+    std::copy(b.tiles.begin(), b.tiles.end(), m->prodtab->e);
+    m->n_ops = static_cast<int>(b.ops.size());
+    m->n_prod = static_cast<int>(b.tiles.size());
+    m->n_blobs = blob_idx;
     const size_t o_stream = ar.reserve(b.stream.size() * 2);
     memcpy(ar.staging.data() + o_stream, b.stream.data(), b.stream.size() * 2);
     const size_t o_params = ar.put_f32(b.params);
@@ -467,7 +453,7 @@ int tftile_prepare(TfTileModel* m, const TfRunArgs& r, std::vector<unsigned char
 
     TfLaunch a{};
     a.arch = d.arch; a.n_stream = pf ? d.n_layer : 0; a.n_main = pf ? d.n_layer_fused : d.n_layer; a.vocab = d.vocab_size;
-    a.optab = m->optab.get(); a.prodtab = m->prodtab.get(); a.n_ops = m->n_ops; a.n_prod = m->n_prod; a.wstream = m->d_wstream; a.params = m->d_params; a.meta = m->d_meta; a.tile0 = 0;
+    a.optab = m->optab.get(); a.prodtab = m->prodtab.get(); a.n_ops = m->n_ops; a.n_prod = m->n_prod; a.n_blobs = m->n_blobs; a.wstream = m->d_wstream; a.params = m->d_params; a.meta = m->d_meta; a.tile0 = 0;
     a.xs0 = m->d_xs0; a.ks0 = m->d_ks0; a.row_slot = m->d_row_slot; a.skip = m->d_skip; a.temb = m->d_temb;
     a.per_jet_time = r.per_jet_time ? 1 : 0; a.nsteps = r.nsteps;
     if (r.opts) {
