@@ -19,8 +19,8 @@ namespace {
 constexpr int kEpi = 256;
 constexpr int kThreads = 384;
 constexpr int kProducers = 2;              // warps 10, 11: weight tiles are dealt round robin
-constexpr int kStages = 4;
-constexpr int kTile = 16384;
+constexpr int kTile = 16384;                // operand chunk: [128 rows][64] bf16
+constexpr int kBars = kTfRingBars;          // weight-ring barrier pairs, used round robin by tile index
 #ifndef MMF_COPY_SPLIT
 #define MMF_COPY_SPLIT 1
 #endif
@@ -32,10 +32,10 @@ constexpr uint32_t oVT = oK + kTile;             // V^T [64 d][128 keys]
 constexpr uint32_t oO = oVT + kTile;             // attention output of the current unit [128 x 64]
 constexpr uint32_t oH0 = oQ, oH1 = oVT;          // MLP hidden quarters [128 x 128] (two chunks each), ping-pong
 constexpr uint32_t oRing = oO + kTile;           // weight ring
-constexpr int kArena = oRing + kStages * kTile;
+constexpr int kArena = oRing + kTfRingBytes;
 
 struct TfBars {
-    uint64_t full[kStages], empty[kStages], done[2], go, pfull[2], pempty[2];
+    uint64_t full[kBars], empty[kBars], done[2], go, pfull[2], pempty[2];
     uint32_t tmem_base;
 };
 
@@ -93,6 +93,33 @@ __device__ __forceinline__ void param_release(Epi& e) {
 
 __device__ __forceinline__ float4 ldf4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+// Reductions over register arrays with four independent chains: the epilogue runs two warps per scheduler, so a
+// 32-deep dependent chain would leave the issue slots empty.
+template <int N>
+__device__ __forceinline__ float sum_regs(const float* v) {
+    float s0 = v[0], s1 = v[1], s2 = v[2], s3 = v[3];
+#pragma unroll
+    for (int i = 4; i < N; i += 4) { s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3]; }
+    return (s0 + s1) + (s2 + s3);
+}
+template <int N>
+__device__ __forceinline__ float sqdev_regs(const float* v, float mean) {
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+        const float d0 = v[i] - mean, d1 = v[i + 1] - mean, d2 = v[i + 2] - mean, d3 = v[i + 3] - mean;
+        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+    }
+    return (q0 + q1) + (q2 + q3);
+}
+template <int N>
+__device__ __forceinline__ float max_regs(const float* v) {
+    float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
+#pragma unroll
+    for (int i = 4; i < N; i += 4) { m0 = fmaxf(m0, v[i]); m1 = fmaxf(m1, v[i + 1]); m2 = fmaxf(m2, v[i + 2]); m3 = fmaxf(m3, v[i + 3]); }
+    return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+
 // 32 fp32 values -> bf16 into the operand chunk that holds absolute column col0 (multiple of 32) of a 256-wide row
 __device__ __forceinline__ void stage32(uint8_t* abase, int r, int col0, const float* v) {
     uint8_t* ch = abase + (col0 >> 6) * kTile;
@@ -129,8 +156,7 @@ __device__ __forceinline__ float resid_update(Epi& e, const float* add0, const f
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += skipc[(c0 + i) * 128];
         }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sum += v[i];
+        sum += sum_regs<32>(v);
         tmem_st32(e.taddr + e.hf * 128 + c0, v);
     }
     tmem_st_wait();
@@ -146,8 +172,7 @@ __device__ __forceinline__ void ln_stats(Epi& e, float sum, int slot, float& mea
         float v[32];
         tmem_ld32(e.taddr + e.hf * 128 + cc * 32, v);
         tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; m2 = fmaf(d, d, m2); }
+        m2 += sqdev_regs<32>(v, mean);
     }
     if (WIDE) {
         float* st = e.misc + mStat + slot * 512;
@@ -199,8 +224,7 @@ __device__ __forceinline__ float ln_to_resid(Epi& e, float mean, float rstd, con
             v[4 * u + 2] = fmaf((v[4 * u + 2] - mean) * rstd, gg.z, bb.z) + pp.z;
             v[4 * u + 3] = fmaf((v[4 * u + 3] - mean) * rstd, gg.w, bb.w) + pp.w;
         }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sum += v[i];
+        sum += sum_regs<32>(v);
         tmem_st32(e.taddr + e.hf * 128 + c0, v);
     }
     tmem_st_wait();
@@ -210,13 +234,8 @@ __device__ __forceinline__ float ln_to_resid(Epi& e, float mean, float rstd, con
 // LayerNorm over N consecutive register values with affine parameters in shared memory
 template <int N>
 __device__ __forceinline__ void ln_regs(float* v, const float* g, const float* b) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < N; ++i) s += v[i];
-    const float mean = s * (1.0f / N);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < N; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float mean = sum_regs<N>(v) * (1.0f / N);
+    const float q = sqdev_regs<N>(v, mean);
     const float rstd = rsqrtf(q * (1.0f / N) + 1e-5f);
 #pragma unroll
     for (int i = 0; i < N; i += 4) {
@@ -232,42 +251,44 @@ __device__ __forceinline__ void ln_regs(float* v, const float* g, const float* b
 // QKV of one 64-column unit sits in scratch (q | k | v, 64 columns each).  hf 0: q and v[0,32); hf 1: k and v[32,64).
 // bq/bk/bv point at the unit's 64 bias values; qg.. are the per-head LayerNorm parameters ([HS]).
 template <int HS>
-__device__ __forceinline__ void qkv_epilogue(Epi& e, const float* bq, const float* bk, const float* bv, const float* qg,
-                                             const float* qb, const float* kg, const float* kb) {
-    // scratch columns of q|k and v (see the op emission in tftile_model.cu)
-    constexpr uint32_t cQK = HS == 64 ? kScr : kScr + 128, cV = HS == 64 ? kScr + 128 : kScr + 64;
-    {
-        float v[64];
-        tmem_ld32(e.taddr + cQK + e.hf * 64, v);
-        tmem_ld32(e.taddr + cQK + e.hf * 64 + 32, v + 32);
-        tmem_ld_wait();
-        const float* bias = e.hf ? bk : bq;
+struct QkvCols {     // scratch columns of q|k and v (see the op emission in tftile_model.cu)
+    static constexpr uint32_t cQK = HS == 64 ? kScr : kScr + 128, cV = HS == 64 ? kScr + 128 : kScr + 64;
+};
+// q and k: bias, per-head LayerNorm, bf16 -> the Q / K operand chunks.  The score product only needs these.
+template <int HS>
+__device__ __forceinline__ void qk_epilogue(Epi& e, const float* bq, const float* bk, const float* qg, const float* qb,
+                                            const float* kg, const float* kb) {
+    float v[64];
+    tmem_ld32(e.taddr + QkvCols<HS>::cQK + e.hf * 64, v);
+    tmem_ld32(e.taddr + QkvCols<HS>::cQK + e.hf * 64 + 32, v + 32);
+    tmem_ld_wait();
+    const float* bias = e.hf ? bk : bq;
 #pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-            const float4 a = ldf4(bias + i);
-            v[i] += a.x; v[i + 1] += a.y; v[i + 2] += a.z; v[i + 3] += a.w;
-        }
-        const float* g = e.hf ? kg : qg;
-        const float* b = e.hf ? kb : qb;
-        if (g) {
-            if (HS == 64) ln_regs<64>(v, g, b);
-            else { ln_regs<32>(v, g, b); ln_regs<32>(v + 32, g, b); }
-        }
-        stage_row_bf16(e.arena + (e.hf ? oK : oQ), e.r, v);
+    for (int i = 0; i < 64; i += 4) {
+        const float4 a = ldf4(bias + i);
+        v[i] += a.x; v[i + 1] += a.y; v[i + 2] += a.z; v[i + 3] += a.w;
     }
-    {
-        float w[32];
-        tmem_ld32(e.taddr + cV + e.hf * 32, w);
-        tmem_ld_wait();
-        // V^T[d][key = r]: two chunks of 64 keys, 64 rows (d) of 128 bytes each
-        uint8_t* vt = e.arena + oVT + (e.r >> 6) * 8192 + (e.r & 7) * 2;
-        const uint32_t ku = (e.r & 63) >> 3;
+    const float* g = e.hf ? kg : qg;
+    const float* b = e.hf ? kb : qb;
+    if (g) {
+        if (HS == 64) ln_regs<64>(v, g, b);
+        else { ln_regs<32>(v, g, b); ln_regs<32>(v + 32, g, b); }
+    }
+    stage_row_bf16(e.arena + (e.hf ? oK : oQ), e.r, v);
+}
+// v: bias, bf16, transposed into V^T[d][key = r] (two chunks of 64 keys, 64 rows d of 128 bytes); runs under the score MMA
+template <int HS>
+__device__ __forceinline__ void v_epilogue(Epi& e, const float* bv) {
+    float w[32];
+    tmem_ld32(e.taddr + QkvCols<HS>::cV + e.hf * 32, w);
+    tmem_ld_wait();
+    uint8_t* vt = e.arena + oVT + (e.r >> 6) * 8192 + (e.r & 7) * 2;
+    const uint32_t ku = (e.r & 63) >> 3;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const int d = e.hf * 32 + i;
-            const float val = w[i] + bv[e.hf * 32 + i];
-            *reinterpret_cast<bf16*>(vt + sw128_offset(d, ku)) = __float2bfloat16_rn(val);
-        }
+    for (int i = 0; i < 32; ++i) {
+        const int d = e.hf * 32 + i;
+        const float val = w[i] + bv[e.hf * 32 + i];
+        *reinterpret_cast<bf16*>(vt + sw128_offset(d, ku)) = __float2bfloat16_rn(val);
     }
 }
 
@@ -279,24 +300,17 @@ __device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, float sc
     tmem_ld_wait();
     // keys outside the row's jet get -inf: they drop out of the max and ex2(-inf) = 0 removes them from the sum
     const int lo = kb - e.hf * 64, hi = ke - e.hf * 64;
-    float mx = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) {
-        s[j] = (j >= lo && j < hi) ? s[j] : -INFINITY;
-        mx = fmaxf(mx, s[j]);
-    }
+    for (int j = 0; j < 64; ++j) s[j] = (j >= lo && j < hi) ? s[j] : -INFINITY;
+    float mx = max_regs<64>(s);
     float* red = e.misc + mRed;
     red[e.hf * 128 + e.r] = mx;
     epi_bar();
     mx = fmaxf(mx, red[(e.hf ^ 1) * 128 + e.r]);
     const float msc = (mx == -INFINITY) ? 0.f : mx * scale_log2e;
-    float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) {
-        const float p = ex2_approx(fmaf(s[j], scale_log2e, -msc));
-        s[j] = p;
-        sum += p;
-    }
+    for (int j = 0; j < 64; ++j) s[j] = ex2_approx(fmaf(s[j], scale_log2e, -msc));
+    const float sum = sum_regs<64>(s);
     stage_row_bf16(e.arena + (e.hf ? oK : oQ), e.r, s);          // P chunk hf (keys hf*64..)
     e.misc[mSum + e.hf * 128 + e.r] = sum;
 }
@@ -369,8 +383,9 @@ __device__ __forceinline__ void attention_unit(Epi& e, const float* bq, const fl
                                                const float* qb, const float* kg, const float* kb, int seg_b, int seg_e) {
     const float scale = 1.4426950408889634f * rsqrtf(static_cast<float>(HS));
     wait_done(e, 1);                                  // QKV of this unit (issued under the previous unit's epilogue)
-    qkv_epilogue<HS>(e, bq, bk, bv, qg, qb, kg, kb);
+    qk_epilogue<HS>(e, bq, bk, qg, qb, kg, kb);
     go(e);
+    v_epilogue<HS>(e, bv);                            // under the score MMA; P V is only issued after the next go
     if (HS == 64) {
         wait_done(e, 0);
         softmax_epilogue(e, kScr, scale, seg_b, seg_e);
@@ -413,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
     const uint32_t cs = cluster_nctarank(), crank = cluster_ctarank();
     const uint16_t cmask = static_cast<uint16_t>((1u << cs) - 1u);
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], cs); }
+        for (int i = 0; i < kBars; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], cs); }
         mbar_init(&bars->done[0], 1);
         mbar_init(&bars->done[1], 1);
         mbar_init(&bars->go, kEpi);
@@ -450,22 +465,29 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
         }
     } else if (warp >= 10) {
         // ---------------------------------------------------- weight producers --------------------------------------
+        // Tile g of the launch may be written once every tile up to g - dep has been consumed (host plan); `known` counts
+        // the tiles this warp has seen consumed, waiting on their barriers strictly in order.
         const uint32_t pw = static_cast<uint32_t>(warp - 10);
-        uint32_t it = pw;                                     // ring tile counter over the whole launch
-        for (int step = 0; step < a.nsteps; ++step) {
-            for (int i = pw; i < a.n_prod; i += kProducers, it += kProducers) {
-                const uint32_t ent = prodtab.e[i];
-                const uint32_t s = it % kStages, bytes = (ent & 0xffu) * 1024u;
-                if (it >= kStages) mbar_wait(&bars->empty[s], ((it / kStages) - 1) & 1);
+        uint32_t known = 0, gbase = 0;
+        for (int step = 0; step < a.nsteps; ++step, gbase += a.n_prod) {
+            for (int i = pw; i < a.n_prod; i += kProducers) {
+                const uint2 ent = prodtab.e[i];
+                const uint32_t g = gbase + i, bytes = (ent.x >> 24) * 1024u;
+                const int need = static_cast<int>(g) - static_cast<int>((ent.y >> 8) & 0xffu) + 1;
+                while (static_cast<int>(known) < need) {
+                    mbar_wait(&bars->empty[known % kBars], (known / kBars) & 1);
+                    ++known;
+                }
                 if (elect_one()) {
-                    mbar_expect_tx(&bars->full[s], bytes);
-                    const uint32_t slice = bytes / cs, part = slice / kCopySplit;
-                    uint8_t* dst = arena + oRing + s * kTile + crank * slice;
-                    const uint8_t* src = a.wstream + static_cast<size_t>(ent >> 8) * 128u + crank * slice;
+                    uint64_t* full = &bars->full[g % kBars];
+                    mbar_expect_tx(full, bytes);
+                    const uint32_t slice = cs == 1 ? bytes : (cs == 2 ? bytes >> 1 : bytes >> 2), part = slice / kCopySplit;
+                    uint8_t* dst = arena + oRing + (ent.y & 0xffu) * 1024u + crank * slice;
+                    const uint8_t* src = a.wstream + static_cast<size_t>(ent.x & 0xffffffu) * 128u + crank * slice;
 #pragma unroll
                     for (int c = 0; c < kCopySplit; ++c) {
-                        if (cs == 1) bulk_load_1d(dst + c * part, src + c * part, part, &bars->full[s]);
-                        else bulk_load_1d_multicast(dst + c * part, src + c * part, part, &bars->full[s], cmask);
+                        if (cs == 1) bulk_load_1d(dst + c * part, src + c * part, part, full);
+                        else bulk_load_1d_multicast(dst + c * part, src + c * part, part, full, cmask);
                     }
                 }
                 __syncwarp();
@@ -475,12 +497,13 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
         // ---------------------------------------------------- MMA issuer --------------------------------------------
         // All 32 lanes run the loop converged (op fields stay in uniform registers, the table sits in the constant bank);
         // one elected lane issues the asynchronous instructions.  Descriptors come precomputed from the host.
-        uint32_t it = 0, pg = 0;
+        uint32_t pg = 0, gbase = 0;
         const uint32_t base16 = smem_u32(arena) >> 4;
         const uint32_t ring16 = base16 + (oRing >> 4) + (1u << 16);
         constexpr uint64_t kDescHi = static_cast<uint64_t>(0x40004040u) << 32;   // SBO 1024 B | version 1 | SWIZZLE_128B
-        for (int step = 0; step < a.nsteps; ++step) {
+        for (int step = 0; step < a.nsteps; ++step, gbase += a.n_prod) {
             TfOp nx = optab.ops[0];
+            uint32_t ti = 0, nt = prodtab.e[0].y;             // next weight tile of this timestep and its ring placement
             for (int i = 0; i < a.n_ops; ++i) {
                 const TfOp op = nx;
                 if (i + 1 < a.n_ops) nx = optab.ops[i + 1];   // fetched one op ahead
@@ -493,11 +516,12 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 uint32_t a_lo = op.a_lo + base16, b_lo = op.b_lo + base16, acc = fl & kTfOpAcc;
                 const uint32_t d = tmem_base + op.dcol;
                 for (uint32_t kt = 0; kt < op.nkt; ++kt) {
-                    const uint32_t s = it % kStages;
+                    const uint32_t g = gbase + ti;
                     if (ring) {
-                        mbar_wait(&bars->full[s], (it / kStages) & 1);
-                        b_lo = ring16 + s * (kTile >> 4);
-                        ++it;
+                        b_lo = ring16 + (nt & 0xffu) * (1024u >> 4);
+                        ++ti;
+                        nt = prodtab.e[ti < static_cast<uint32_t>(a.n_prod) ? ti : 0].y;
+                        mbar_wait(&bars->full[g % kBars], (g / kBars) & 1);
                     }
                     tc_fence_after();
                     if (elect_one()) {
@@ -509,7 +533,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                             umma_bf16(d, da + 6, db + 6, op.idesc, 1u);
                         }
                         if (ring) {
-                            if (cs == 1) umma_commit(&bars->empty[s]); else umma_commit_multicast(&bars->empty[s], cmask);
+                            if (cs == 1) umma_commit(&bars->empty[g % kBars]); else umma_commit_multicast(&bars->empty[g % kBars], cmask);
                         }
                     }
                     __syncwarp();
@@ -600,7 +624,8 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                         tmem_ld32(e.taddr + kScr + cc * 32, v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) s1 += v[i] + PA[tfp::EA_BXE2 + cc * 32 + i];
+                        for (int i = 0; i < 32; ++i) v[i] += PA[tfp::EA_BXE2 + cc * 32 + i];
+                        s1 += sum_regs<32>(v);
                     }
                     const float mean = s1 * (1.0f / 128.0f);
                     float m2 = 0.f;
@@ -610,7 +635,8 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                         tmem_ld32(e.taddr + kScr + cc * 32, v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) { const float d = v[i] + PA[tfp::EA_BXE2 + cc * 32 + i] - mean; m2 = fmaf(d, d, m2); }
+                        for (int i = 0; i < 32; ++i) v[i] += PA[tfp::EA_BXE2 + cc * 32 + i];
+                        m2 += sqdev_regs<32>(v, mean);
                     }
                     const float rstd = rsqrtf(m2 * (1.0f / 128.0f) + 1e-5f);
 #pragma unroll 1

@@ -78,8 +78,15 @@ constexpr int kTfMaxOps = 1024;
 struct TfOpTable {          // MMA ops of one timestep; passed to the kernel BY VALUE (constant bank -> uniform registers)
     TfOp ops[kTfMaxOps];
 };
-struct TfProdTable {        // weight tiles of one timestep in consumption order: (offset in the stream / 128) << 8 | rows / 8
-    uint32_t e[kTfMaxOps];
+// Weight tiles of one timestep in consumption order.  The ring is a 64 KB byte range; a tile of `kb` KB ([n rows][64] bf16,
+// n = 8 kb) is copied to offset `dst` KB.  Placement is planned on the host (tiles never wrap; the plan is the same every
+// timestep): before tile g (global index over the launch) is written, all tiles up to g - dep must have been consumed.
+// Tile g uses the barrier pair g % kTfRingBars.
+//   x = offset in the weight stream / 128 | kb << 24        y = dst | dep << 8
+constexpr int kTfRingBytes = 65536;
+constexpr int kTfRingBars = 16;
+struct TfProdTable {
+    uint2 e[kTfMaxOps];
 };
 
 struct TfTileMeta {

@@ -46,7 +46,7 @@ uint32_t idesc_bf16(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | (static
 
 struct Builder {
     std::vector<TfOp> ops;
-    std::vector<uint32_t> tiles;                     // producer table
+    std::vector<uint2> tiles;                        // producer table (ring placement filled in by plan_ring)
     std::vector<uint16_t> stream;
     std::vector<float> params;
 
@@ -56,7 +56,7 @@ struct Builder {
         const int n = static_cast<int>(rows.size());
         for (int kt = 0; kt < nkt; ++kt) {
             const size_t base = stream.size();
-            tiles.push_back(static_cast<uint32_t>(base / 64) << 8 | static_cast<uint32_t>(n / 8));
+            tiles.push_back(make_uint2(static_cast<uint32_t>(base / 64) | static_cast<uint32_t>(n / 8) << 24, 0u));
             stream.resize(base + static_cast<size_t>(n) * 64);
             for (int rr = 0; rr < n; ++rr)
                 for (int e = 0; e < 64; ++e)
@@ -73,6 +73,38 @@ struct Builder {
         o.a_lo = desc_lo(a_off); o.b_lo = desc_lo(b_off); o.idesc = idesc_bf16(n); o.dcol = dcol; o.nkt = static_cast<uint8_t>(nkt);
         o.flags = static_cast<uint8_t>((acc ? kTfOpAcc : 0u) | (wait ? kTfOpWait : 0u) | (half_k ? kTfOpHalfK : 0u) | (static_cast<uint32_t>(signal) << 4));
         ops.push_back(o);
+    }
+    // Ring placement: tiles go to increasing offsets and restart at 0 when the next one would not fit (and at every
+    // timestep start, so that the plan repeats).  Two timesteps are simulated; the second gives the steady-state
+    // dependency of every tile on the consumption of the tiles it overwrites.
+    bool plan_ring() {
+        struct Res { long idx; int beg, end; };
+        std::vector<Res> res;
+        const long n = static_cast<long>(tiles.size());
+        long required = -1;                           // newest tile that must have been consumed so far
+        for (int pass = 0; pass < 2; ++pass) {
+            int pos = 0;
+            for (long j = 0; j < n; ++j) {
+                const int bytes = static_cast<int>(tiles[j].x >> 24) * 1024;
+                if (bytes <= 0 || bytes > kTfRingBytes) return false;
+                if (pos + bytes > kTfRingBytes) pos = 0;
+                size_t newest = res.size();
+                for (size_t i = 0; i < res.size(); ++i)
+                    if (res[i].beg < pos + bytes && pos < res[i].end) newest = i;
+                if (newest != res.size()) {
+                    required = std::max(required, res[newest].idx);
+                    res.erase(res.begin(), res.begin() + newest + 1);
+                }
+                const long g = pass * n + j;
+                res.push_back(Res{g, pos, pos + bytes});
+                if (static_cast<int>(res.size()) >= kTfRingBars) return false;
+                const long dep = required < 0 ? 255 : g - required;
+                if (dep < 1 || (dep > 255)) return false;
+                if (pass == 1) tiles[j].y = static_cast<uint32_t>(pos / 1024) | static_cast<uint32_t>(dep) << 8;
+                pos += bytes;
+            }
+        }
+        return true;
     }
     float* blob(int idx) {
         if (params.size() < static_cast<size_t>(idx + 1) * kTfParamFloats) params.resize(static_cast<size_t>(idx + 1) * kTfParamFloats, 0.f);
@@ -108,15 +140,13 @@ BlockW load_block(WeightMap& wm, const std::string& p, int C, int I) {
 
 // MLP of one group: quarters of the hidden layer ping-pong through the two scratch halves
 void emit_mlp(Builder& b, const BlockW& w, int C, int a_chunk0, uint16_t dcol_out, bool first_wait, bool final_signal) {
-    const int kbC = C / 64, nh = C / 128;
+    const int kbC = C / 64;
     auto fc = [&](int q) {
         b.ring_op(oA + a_chunk0 * kT, rows_of(w.fc, q * 128, 128), 0, kbC, static_cast<uint16_t>(256 + (q & 1) * 128), 0,
                   first_wait && q == 0, 1 + (q & 1));
     };
-    auto out = [&](int q) {
-        for (int h = 0; h < nh; ++h)
-            b.ring_op((q & 1) ? oH1 : oH0, rows_of(w.p2, h * 128, 128), q * 128, 2, static_cast<uint16_t>(dcol_out + h * 128), 1, h == 0,
-                      (final_signal && q == 3 && h == nh - 1) ? 1 : 0);
+    auto out = [&](int q) {                            // all C output columns in one MMA (N = 128 or 256)
+        b.ring_op((q & 1) ? oH1 : oH0, rows_of(w.p2, 0, C), q * 128, 2, dcol_out, 1, 1, (final_signal && q == 3) ? 1 : 0);
     };
     fc(0); fc(1); out(0); fc(2); out(1); fc(3); out(2); out(3);
 }
@@ -208,10 +238,11 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
         // then both score tiles are consumed and the O columns are not touched, so it runs under the epilogue of this unit.
         auto qkv = [&](int g, int u, int wait) {
             // rows of c_attn: q [0,128) k [128,256) v [256,384); unit u = heads 2u, 2u+1 = columns u*64..u*64+63
-            std::vector<const float*> qk = rows_of(w[g].attn, u * 64, 64), kk = rows_of(w[g].attn, 128 + u * 64, 64);
-            qk.insert(qk.end(), kk.begin(), kk.end());
-            b.ring_op(oA + 2 * g * kT, qk, 0, 2, 384, 0, wait, 0);
-            b.ring_op(oA + 2 * g * kT, rows_of(w[g].attn, 256 + u * 64, 64), 0, 2, 320, 0, 0, 2);
+            // one N = 192 MMA per k-tile: rows v | q | k -> columns [320,384) [384,448) [448,512)
+            std::vector<const float*> r = rows_of(w[g].attn, 256 + u * 64, 64), qq = rows_of(w[g].attn, u * 64, 64), kk = rows_of(w[g].attn, 128 + u * 64, 64);
+            r.insert(r.end(), qq.begin(), qq.end());
+            r.insert(r.end(), kk.begin(), kk.end());
+            b.ring_op(oA + 2 * g * kT, r, 0, 2, 320, 0, wait, 2);
         };
         qkv(0, 0, 1);
         for (int g = 0; g < 2; ++g)
@@ -256,18 +287,18 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
         // Scratch columns of a unit: Q|K [256,384), V [384,448); S [256,384); O [448,512).  QKV of the next unit is issued
         // right after P V (S is consumed, O is elsewhere) and runs under the O / projection epilogue of this unit.
         auto qkv = [&](int u, int wait) {
-            std::vector<const float*> qk = rows_of(w.attn, u * 64, 64), kk = rows_of(w.attn, 256 + u * 64, 64);
-            qk.insert(qk.end(), kk.begin(), kk.end());
-            b.ring_op(oA, qk, 0, 4, 256, 0, wait, 0);
-            b.ring_op(oA, rows_of(w.attn, 512 + u * 64, 64), 0, 4, 384, 0, 0, 2);
+            // one N = 192 MMA per k-tile: rows q | k | v -> columns [256,320) [320,384) [384,448)
+            std::vector<const float*> r = rows_of(w.attn, u * 64, 64), kk = rows_of(w.attn, 256 + u * 64, 64), vv = rows_of(w.attn, 512 + u * 64, 64);
+            r.insert(r.end(), kk.begin(), kk.end());
+            r.insert(r.end(), vv.begin(), vv.end());
+            b.ring_op(oA, r, 0, 4, 256, 0, wait, 2);
         };
         qkv(0, 1);
         for (int u = 0; u < 4; ++u) {
             b.smem_op(oQ, oK, 128, 256, 1, false, 0, 1, 1);                  // S = Q K^T
             b.smem_op(oQ, oVT, 64, 448, 2, false, 0, 1, 1);                  // O = P V
             if (u < 3) qkv(u + 1, 0);
-            for (int nh = 0; nh < 2; ++nh)
-                b.ring_op(oO, rows_of(w.proj, nh * 128, 128), u * 64, 1, static_cast<uint16_t>(nh * 128), 1, nh == 0, (u == 3 && nh == 1) ? 1 : 0);
+            b.ring_op(oO, rows_of(w.proj, 0, 256), u * 64, 1, 0, 1, 1, u == 3 ? 1 : 0);      // N = 256
         }
         ++blob_idx;
         emit_mlp(b, w, 256, 0, 0, true, true);
@@ -309,6 +340,7 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
     m->prodtab.reset(new TfProdTable());
     memset(m->optab.get(), 0, sizeof(TfOpTable));
     memset(m->prodtab.get(), 0, sizeof(TfProdTable));
+    MMF_REQUIRE(b.plan_ring(), "tile kernel: weight ring plan failed");
     std::copy(b.ops.begin(), b.ops.end(), m->optab->ops);
     std::copy(b.tiles.begin(), b.tiles.end(), m->prodtab->e);
     m->n_ops = static_cast<int>(b.ops.size());
