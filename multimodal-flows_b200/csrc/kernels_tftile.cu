@@ -28,7 +28,7 @@ constexpr int kCopySplit = MMF_COPY_SPLIT;   // bulk copies per weight-tile slic
 // operand arena (bytes); every region is 1024-byte aligned
 constexpr uint32_t oA = 0;                       // 4 chunks [128 x 64] bf16: LayerNorm output / head input
 constexpr uint32_t oQ = 65536, oK = oQ + kTile;  // Q | K of the current unit; P (probabilities) aliases both
-constexpr uint32_t oVT = oK + kTile;             // V^T [64 d][128 keys]
+constexpr uint32_t oVT = oK + kTile;             // V [128 keys][64 d] (the MN-major B operand of P V)
 constexpr uint32_t oO = oVT + kTile;             // attention output of the current unit [128 x 64]
 constexpr uint32_t oH0 = oQ, oH1 = oVT;          // MLP hidden quarters [128 x 128] (two chunks each), ping-pong
 constexpr uint32_t oRing = oO + kTile;           // weight ring
@@ -58,6 +58,7 @@ struct Epi {
     uint32_t taddr;          // TMEM base + this warp's lane quarter
     int r, hf, tid;
     uint32_t pd0, pd1, pc;
+    uint32_t kmask;          // 16-key groups of this thread's key half that any row of the warp attends to
     unsigned long long* trace;   // clock stamps of CTA 0 / thread 0 for the first two timesteps (debugging aid) or null
     int mark_i, step;
 };
@@ -276,41 +277,62 @@ __device__ __forceinline__ void qk_epilogue(Epi& e, const float* bq, const float
     }
     stage_row_bf16(e.arena + (e.hf ? oK : oQ), e.r, v);
 }
-// v: bias, bf16, transposed into V^T[d][key = r] (two chunks of 64 keys, 64 rows d of 128 bytes); runs under the score MMA
+// v: bias, bf16 -> V[key = r][d] (row r of a [128][128 B] swizzled chunk: the MN-major B operand of P V, so no transpose);
+// runs under the score MMA
 template <int HS>
 __device__ __forceinline__ void v_epilogue(Epi& e, const float* bv) {
     float w[32];
     tmem_ld32(e.taddr + QkvCols<HS>::cV + e.hf * 32, w);
     tmem_ld_wait();
-    uint8_t* vt = e.arena + oVT + (e.r >> 6) * 8192 + (e.r & 7) * 2;
-    const uint32_t ku = (e.r & 63) >> 3;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        const int d = e.hf * 32 + i;
-        const float val = w[i] + bv[e.hf * 32 + i];
-        *reinterpret_cast<bf16*>(vt + sw128_offset(d, ku)) = __float2bfloat16_rn(val);
+    for (int i = 0; i < 32; i += 4) {
+        const float4 b = ldf4(bv + e.hf * 32 + i);
+        w[i] += b.x; w[i + 1] += b.y; w[i + 2] += b.z; w[i + 3] += b.w;
     }
+    uint8_t* vb = e.arena + oVT;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        st_shared_v4(vb + sw128_offset(e.r, e.hf * 4 + u), pack_bf16x2(w[8 * u], w[8 * u + 1]), pack_bf16x2(w[8 * u + 2], w[8 * u + 3]),
+                     pack_bf16x2(w[8 * u + 4], w[8 * u + 5]), pack_bf16x2(w[8 * u + 6], w[8 * u + 7]));
 }
 
-// scores of one head in scratch columns [scol, scol+128); thread handles keys [hf*64, +64) of its row
+// scores of one head in scratch columns [scol, scol+128); thread handles keys [hf*64, +64) of its row.
+// e.kmask: which of the thread's four 16-key groups hold a key of ANY row of this warp (warp-uniform, fixed for the
+// launch): the other groups are outside every jet of these 32 rows, so their probabilities are exact zeros.
 __device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, float scale_log2e, int kb, int ke) {
     float s[64];
+    const uint32_t km = e.kmask;
     tmem_ld32(e.taddr + scol + e.hf * 64, s);
     tmem_ld32(e.taddr + scol + e.hf * 64 + 32, s + 32);
     tmem_ld_wait();
     // keys outside the row's jet get -inf: they drop out of the max and ex2(-inf) = 0 removes them from the sum
     const int lo = kb - e.hf * 64, hi = ke - e.hf * 64;
+    float mx = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) s[j] = (j >= lo && j < hi) ? s[j] : -INFINITY;
-    float mx = max_regs<64>(s);
+    for (int g = 0; g < 4; ++g) {
+        if (km & (1u << g)) {
+#pragma unroll
+            for (int j = 16 * g; j < 16 * g + 16; ++j) s[j] = (j >= lo && j < hi) ? s[j] : -INFINITY;
+            mx = fmaxf(mx, max_regs<16>(s + 16 * g));
+        }
+    }
     float* red = e.misc + mRed;
     red[e.hf * 128 + e.r] = mx;
     epi_bar();
     mx = fmaxf(mx, red[(e.hf ^ 1) * 128 + e.r]);
     const float msc = (mx == -INFINITY) ? 0.f : mx * scale_log2e;
+    float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < 64; ++j) s[j] = ex2_approx(fmaf(s[j], scale_log2e, -msc));
-    const float sum = sum_regs<64>(s);
+    for (int g = 0; g < 4; ++g) {
+        if (km & (1u << g)) {
+#pragma unroll
+            for (int j = 16 * g; j < 16 * g + 16; ++j) s[j] = ex2_approx(fmaf(s[j], scale_log2e, -msc));
+            sum += sum_regs<16>(s + 16 * g);
+        } else {
+#pragma unroll
+            for (int j = 16 * g; j < 16 * g + 16; ++j) s[j] = 0.f;
+        }
+    }
     stage_row_bf16(e.arena + (e.hf ? oK : oQ), e.r, s);          // P chunk hf (keys hf*64..)
     e.misc[mSum + e.hf * 128 + e.r] = sum;
 }
@@ -526,11 +548,12 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                     tc_fence_after();
                     if (elect_one()) {
                         const uint64_t da = kDescHi | a_lo, db = kDescHi | b_lo;
+                        const uint32_t bs = (fl & kTfOpBMn) ? (2048u >> 4) : 2u;   // B per K = 16: 16 rows (MN-major) or 32 bytes
                         umma_bf16(d, da, db, op.idesc, acc);
-                        umma_bf16(d, da + 2, db + 2, op.idesc, 1u);
+                        umma_bf16(d, da + 2, db + bs, op.idesc, 1u);
                         if (!(fl & kTfOpHalfK)) {
-                            umma_bf16(d, da + 4, db + 4, op.idesc, 1u);
-                            umma_bf16(d, da + 6, db + 6, op.idesc, 1u);
+                            umma_bf16(d, da + 4, db + 2 * bs, op.idesc, 1u);
+                            umma_bf16(d, da + 6, db + 3 * bs, op.idesc, 1u);
                         }
                         if (ring) {
                             if (cs == 1) umma_commit(&bars->empty[g % kBars]); else umma_commit_multicast(&bars->empty[g % kBars], cmask);
@@ -568,6 +591,12 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
             s_ks[tid] = a.ks0[static_cast<size_t>(tile) * 128 + tid];
         }
         const int seg_b = meta->seg_beg[r], seg_e = meta->seg_end[r];
+        e.kmask = 0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int k0 = hf * 64 + 16 * g;
+            if (__ballot_sync(0xffffffffu, seg_b < k0 + 16 && seg_e > k0) != 0u) e.kmask |= 1u << g;
+        }
         const int tb_row = a.per_jet_time ? meta->row_tb[r] : 0;
         const long long slot = a.row_slot[static_cast<size_t>(tile) * 128 + r];
         float* skipc = a.skip + (static_cast<size_t>(tile) * 256 + hf * 128) * 128 + r;    // + col * 128

@@ -68,10 +68,12 @@ struct Builder {
         ops.push_back(o);
     }
     // both operands in the arena; B advances by 8 KB per k-tile
-    void smem_op(uint32_t a_off, uint32_t b_off, int n, uint16_t dcol, int nkt, bool half_k, int acc, int wait, int signal) {
+    // b_mn: B is MN-major (rows = K, N contiguous inside the 128-byte row) - bit 16 of the instruction descriptor
+    void smem_op(uint32_t a_off, uint32_t b_off, int n, uint16_t dcol, int nkt, bool half_k, int acc, int wait, int signal, bool b_mn = false) {
         TfOp o{};
-        o.a_lo = desc_lo(a_off); o.b_lo = desc_lo(b_off); o.idesc = idesc_bf16(n); o.dcol = dcol; o.nkt = static_cast<uint8_t>(nkt);
-        o.flags = static_cast<uint8_t>((acc ? kTfOpAcc : 0u) | (wait ? kTfOpWait : 0u) | (half_k ? kTfOpHalfK : 0u) | (static_cast<uint32_t>(signal) << 4));
+        o.a_lo = desc_lo(a_off); o.b_lo = desc_lo(b_off); o.idesc = idesc_bf16(n) | (b_mn ? 1u << 16 : 0u); o.dcol = dcol; o.nkt = static_cast<uint8_t>(nkt);
+        o.flags = static_cast<uint8_t>((acc ? kTfOpAcc : 0u) | (wait ? kTfOpWait : 0u) | (half_k ? kTfOpHalfK : 0u) | (b_mn ? kTfOpBMn : 0u) |
+                                       (static_cast<uint32_t>(signal) << 4));
         ops.push_back(o);
     }
     // Ring placement: tiles go to increasing offsets and restart at 0 when the next one would not fit (and at every
@@ -249,8 +251,8 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
             for (int u = 0; u < 2; ++u) {
                 b.smem_op(oQ, oK, 128, 256, 1, true, 0, 1, 0);               // S of head 0 of the pair
                 b.smem_op(oQ + 64, oK + 64, 128, 384, 1, true, 0, 0, 1);     // S of head 1
-                b.smem_op(oQ, oVT, 32, 256, 2, false, 0, 1, 2);              // O_h0 = P_h0 V_h0 (keys 0..63, 64..127)
-                b.smem_op(oQ, oVT + 4096, 32, 288, 2, false, 0, 1, 1);       // O_h1
+                b.smem_op(oQ, oVT, 32, 256, 2, false, 0, 1, 2, true);        // O_h0 = P_h0 V_h0 (keys 0..63, 64..127); V is [key][d]
+                b.smem_op(oQ, oVT + 64, 32, 288, 2, false, 0, 1, 1, true);   // O_h1: d columns 32..63 of the V rows
                 if (!(g == 1 && u == 1)) qkv(u == 1 ? 1 : g, u == 1 ? 0 : 1, 0);
                 b.ring_op(oO, rows_of(w[g].proj, 0, 128), u * 64, 1, static_cast<uint16_t>(g * 128), 1, 1, (g == 1 && u == 1) ? 1 : 0);
             }
@@ -296,7 +298,7 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
         qkv(0, 1);
         for (int u = 0; u < 4; ++u) {
             b.smem_op(oQ, oK, 128, 256, 1, false, 0, 1, 1);                  // S = Q K^T
-            b.smem_op(oQ, oVT, 64, 448, 2, false, 0, 1, 1);                  // O = P V
+            b.smem_op(oQ, oVT, 64, 448, 2, false, 0, 1, 1, true);            // O = P V; V is [key][d] (MN-major B)
             if (u < 3) qkv(u + 1, 0);
             b.ring_op(oO, rows_of(w.proj, 0, 256), u * 64, 1, 0, 1, 1, u == 3 ? 1 : 0);      // N = 256
         }
