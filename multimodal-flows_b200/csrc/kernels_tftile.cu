@@ -58,7 +58,8 @@ struct Epi {
     uint32_t taddr;          // TMEM base + this warp's lane quarter
     int r, hf, tid;
     uint32_t pd0, pd1, pc;
-    uint32_t kmask;          // 16-key groups of this thread's key half that any row of the warp attends to
+    uint32_t kmask, kfull, kpart;   // 16-key groups of this thread's key half: attended by any row of the warp / in full by
+                                    // every row / cut by a jet boundary of some row
     unsigned long long* trace;   // clock stamps of CTA 0 / thread 0 for the first two timesteps (debugging aid) or null
     int mark_i, step;
 };
@@ -113,6 +114,21 @@ __device__ __forceinline__ float sqdev_regs(const float* v, float mean) {
     }
     return (q0 + q1) + (q2 + q3);
 }
+// LayerNorm statistics gathered in the same pass that produces the row: sums of (v - c) and (v - c)^2 around a pivot c
+// taken from the row itself (its first value), so the variance does not suffer the cancellation of E[x^2] - mean^2.
+struct RowStat { float c, s1, s2; };
+template <int N>
+__device__ __forceinline__ void stat_regs(const float* v, RowStat& st) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+        const float d0 = v[i] - st.c, d1 = v[i + 1] - st.c, d2 = v[i + 2] - st.c, d3 = v[i + 3] - st.c;
+        a0 += d0; a1 += d1; a2 += d2; a3 += d3;
+        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+    }
+    st.s1 += (a0 + a1) + (a2 + a3);
+    st.s2 += (q0 + q1) + (q2 + q3);
+}
 template <int N>
 __device__ __forceinline__ float max_regs(const float* v) {
     float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
@@ -132,9 +148,9 @@ __device__ __forceinline__ void stage32(uint8_t* abase, int r, int col0, const f
 }
 
 // ---- residual-stream passes; every thread owns columns [hf*128, hf*128+128) of its row -----------------------
-// v = resid + add0 (+ add1) (+ skip); stored back; returns the sum over the thread's 128 columns
-__device__ __forceinline__ float resid_update(Epi& e, const float* add0, const float* add1, const float* skipc) {
-    float sum = 0.f;
+// v = resid + add0 (+ add1) (+ skip); stored back; returns the statistics of the thread's 128 columns
+__device__ __forceinline__ RowStat resid_update(Epi& e, const float* add0, const float* add1, const float* skipc) {
+    RowStat st{0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
         const int c0 = cc * 32;
@@ -157,30 +173,26 @@ __device__ __forceinline__ float resid_update(Epi& e, const float* add0, const f
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += skipc[(c0 + i) * 128];
         }
-        sum += sum_regs<32>(v);
+        if (cc == 0) st.c = v[0];
+        stat_regs<32>(v, st);
         tmem_st32(e.taddr + e.hf * 128 + c0, v);
     }
     tmem_st_wait();
-    return sum;
+    return st;
 }
-// LayerNorm statistics of the (stored) residual row: over the thread's 128 columns, or over all 256 (WIDE)
+// LayerNorm mean / rstd from the row statistics: over the thread's 128 columns, or over all 256 (WIDE: the two threads of
+// a row exchange (mean, M2) through shared memory and merge them)
 template <bool WIDE>
-__device__ __forceinline__ void ln_stats(Epi& e, float sum, int slot, float& mean, float& rstd) {
-    mean = sum * (1.0f / 128.0f);
-    float m2 = 0.f;
-#pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
-        float v[32];
-        tmem_ld32(e.taddr + e.hf * 128 + cc * 32, v);
-        tmem_ld_wait();
-        m2 += sqdev_regs<32>(v, mean);
-    }
+__device__ __forceinline__ void ln_stats(Epi& e, const RowStat& st, int slot, float& mean, float& rstd) {
+    const float dm = st.s1 * (1.0f / 128.0f);
+    mean = st.c + dm;
+    float m2 = fmaxf(fmaf(-st.s1, dm, st.s2), 0.f);
     if (WIDE) {
-        float* st = e.misc + mStat + slot * 512;
-        st[(e.hf * 128 + e.r) * 2] = mean;
-        st[(e.hf * 128 + e.r) * 2 + 1] = m2;
+        float* ex = e.misc + mStat + slot * 512;
+        ex[(e.hf * 128 + e.r) * 2] = mean;
+        ex[(e.hf * 128 + e.r) * 2 + 1] = m2;
         epi_bar();
-        const float om = st[((e.hf ^ 1) * 128 + e.r) * 2], o2 = st[((e.hf ^ 1) * 128 + e.r) * 2 + 1];
+        const float om = ex[((e.hf ^ 1) * 128 + e.r) * 2], o2 = ex[((e.hf ^ 1) * 128 + e.r) * 2 + 1];
         const float d = mean - om;
         m2 = m2 + o2 + d * d * 64.0f;
         mean = 0.5f * (mean + om);
@@ -208,9 +220,9 @@ __device__ __forceinline__ void ln_to_abuf(Epi& e, float mean, float rstd, const
         stage32(e.arena + oA, e.r, e.hf * 128 + c0, v);
     }
 }
-// normalised row (+ post) -> back into the residual stream; returns the new row sum (stream junction of ParticleFormer)
-__device__ __forceinline__ float ln_to_resid(Epi& e, float mean, float rstd, const float* g, const float* b, const float* post) {
-    float sum = 0.f;
+// normalised row (+ post) -> back into the residual stream; returns the new row statistics (stream junction of ParticleFormer)
+__device__ __forceinline__ RowStat ln_to_resid(Epi& e, float mean, float rstd, const float* g, const float* b, const float* post) {
+    RowStat st{0.f, 0.f, 0.f};
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
         const int c0 = cc * 32;
@@ -225,11 +237,12 @@ __device__ __forceinline__ float ln_to_resid(Epi& e, float mean, float rstd, con
             v[4 * u + 2] = fmaf((v[4 * u + 2] - mean) * rstd, gg.z, bb.z) + pp.z;
             v[4 * u + 3] = fmaf((v[4 * u + 3] - mean) * rstd, gg.w, bb.w) + pp.w;
         }
-        sum += sum_regs<32>(v);
+        if (cc == 0) st.c = v[0];
+        stat_regs<32>(v, st);
         tmem_st32(e.taddr + e.hf * 128 + c0, v);
     }
     tmem_st_wait();
-    return sum;
+    return st;
 }
 
 // LayerNorm over N consecutive register values with affine parameters in shared memory
@@ -305,14 +318,28 @@ __device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, float sc
     tmem_ld32(e.taddr + scol + e.hf * 64, s);
     tmem_ld32(e.taddr + scol + e.hf * 64 + 32, s + 32);
     tmem_ld_wait();
-    // keys outside the row's jet get -inf: they drop out of the max and ex2(-inf) = 0 removes them from the sum
-    const int lo = kb - e.hf * 64, hi = ke - e.hf * 64;
+    // keys outside the row's jet get -inf: they drop out of the max and ex2(-inf) = 0 removes them from the sum.
+    // Key j of this thread is valid iff (unsigned)(j - lo) < span.  lo / span are made opaque here: otherwise the compiler
+    // hoists the 64 comparisons out of the timestep loop into a bit mask and then serialises on predicate registers.
+    // Per 16-key group (all warp-uniform, fixed for the launch): e.kfull - inside the jet of every row of the warp, no
+    // masking; e.kpart - a jet boundary of some row falls inside the group, per-key masks; otherwise every row is either
+    // all-in or all-out and one per-lane predicate covers the 16 keys.
+    int lo = kb - e.hf * 64;
+    uint32_t span = static_cast<uint32_t>(ke - kb);
+    asm volatile("" : "+r"(lo), "+r"(span));
+    const int hi = lo + static_cast<int>(span);
     float mx = -INFINITY;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         if (km & (1u << g)) {
+            if (e.kpart & (1u << g)) {
 #pragma unroll
-            for (int j = 16 * g; j < 16 * g + 16; ++j) s[j] = (j >= lo && j < hi) ? s[j] : -INFINITY;
+                for (int j = 16 * g; j < 16 * g + 16; ++j) s[j] = static_cast<uint32_t>(j - lo) < span ? s[j] : -INFINITY;
+            } else if (!(e.kfull & (1u << g))) {
+                const bool in = lo <= 16 * g && hi >= 16 * g + 16;
+#pragma unroll
+                for (int j = 16 * g; j < 16 * g + 16; ++j) s[j] = in ? s[j] : -INFINITY;
+            }
             mx = fmaxf(mx, max_regs<16>(s + 16 * g));
         }
     }
@@ -591,11 +618,14 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
             s_ks[tid] = a.ks0[static_cast<size_t>(tile) * 128 + tid];
         }
         const int seg_b = meta->seg_beg[r], seg_e = meta->seg_end[r];
-        e.kmask = 0;
+        e.kmask = 0; e.kfull = 0; e.kpart = 0;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int k0 = hf * 64 + 16 * g;
             if (__ballot_sync(0xffffffffu, seg_b < k0 + 16 && seg_e > k0) != 0u) e.kmask |= 1u << g;
+            if (__all_sync(0xffffffffu, seg_b <= k0 && seg_e >= k0 + 16)) e.kfull |= 1u << g;
+            const bool in = seg_b <= k0 && seg_e >= k0 + 16, out = seg_e <= k0 || seg_b >= k0 + 16;
+            if (!__all_sync(0xffffffffu, in || out)) e.kpart |= 1u << g;
         }
         const int tb_row = a.per_jet_time ? meta->row_tb[r] : 0;
         const long long slot = a.row_slot[static_cast<size_t>(tile) * 128 + r];
@@ -644,42 +674,42 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
             wait_done(e, 0);
             {
                 // x half: LN_ln1x(wxe.2 output + bias) + temb ; y half: Ytab[k] + temb   -> residual + skip streams
-                float sum = 0.f;
+                RowStat sum{0.f, 0.f, 0.f};
                 if (hf == 0) {
-                    float s1 = 0.f;
+                    RowStat st1{0.f, 0.f, 0.f};
 #pragma unroll 1
                     for (int cc = 0; cc < 4; ++cc) {
                         float v[32];
                         tmem_ld32(e.taddr + kScr + cc * 32, v);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] += PA[tfp::EA_BXE2 + cc * 32 + i];
-                        s1 += sum_regs<32>(v);
-                    }
-                    const float mean = s1 * (1.0f / 128.0f);
-                    float m2 = 0.f;
-#pragma unroll 1
-                    for (int cc = 0; cc < 4; ++cc) {
-                        float v[32];
-                        tmem_ld32(e.taddr + kScr + cc * 32, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] += PA[tfp::EA_BXE2 + cc * 32 + i];
-                        m2 += sqdev_regs<32>(v, mean);
-                    }
-                    const float rstd = rsqrtf(m2 * (1.0f / 128.0f) + 1e-5f);
-#pragma unroll 1
-                    for (int cc = 0; cc < 4; ++cc) {
-                        float v[32];
-                        tmem_ld32(e.taddr + kScr + cc * 32, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int c = cc * 32 + i;
-                            v[i] = fmaf((v[i] + PA[tfp::EA_BXE2 + c] - mean) * rstd, PA[tfp::EA_LN1X_G + c], PA[tfp::EA_LN1X_B + c]) + tb1[c];
-                            sum += v[i];
-                            skipc[c * 128] = v[i];
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 bx = ldf4(PA + tfp::EA_BXE2 + cc * 32 + i);
+                            v[i] += bx.x; v[i + 1] += bx.y; v[i + 2] += bx.z; v[i + 3] += bx.w;
                         }
+                        if (cc == 0) st1.c = v[0];
+                        stat_regs<32>(v, st1);
+                    }
+                    const float dm = st1.s1 * (1.0f / 128.0f), mean = st1.c + dm;
+                    const float rstd = rsqrtf(fmaxf(fmaf(-st1.s1, dm, st1.s2), 0.f) * (1.0f / 128.0f) + 1e-5f);
+#pragma unroll 1
+                    for (int cc = 0; cc < 4; ++cc) {
+                        float v[32];
+                        tmem_ld32(e.taddr + kScr + cc * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const int c = cc * 32 + i;
+                            const float4 bx = ldf4(PA + tfp::EA_BXE2 + c), gg = ldf4(PA + tfp::EA_LN1X_G + c), bb = ldf4(PA + tfp::EA_LN1X_B + c), tt = ldf4(tb1 + c);
+                            v[i] = fmaf((v[i] + bx.x - mean) * rstd, gg.x, bb.x) + tt.x;
+                            v[i + 1] = fmaf((v[i + 1] + bx.y - mean) * rstd, gg.y, bb.y) + tt.y;
+                            v[i + 2] = fmaf((v[i + 2] + bx.z - mean) * rstd, gg.z, bb.z) + tt.z;
+                            v[i + 3] = fmaf((v[i + 3] + bx.w - mean) * rstd, gg.w, bb.w) + tt.w;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) skipc[(cc * 32 + i) * 128] = v[i];
+                        if (cc == 0) sum.c = v[0];
+                        stat_regs<32>(v, sum);
                         tmem_st32(e.taddr + cc * 32, v);
                     }
                 } else {
@@ -688,12 +718,14 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                     for (int cc = 0; cc < 4; ++cc) {
                         float v[32];
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int c = cc * 32 + i;
-                            v[i] = yt[c] + tb1[c];
-                            sum += v[i];
-                            skipc[c * 128] = v[i];
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 yy = ldf4(yt + cc * 32 + i), tt = ldf4(tb1 + cc * 32 + i);
+                            v[i] = yy.x + tt.x; v[i + 1] = yy.y + tt.y; v[i + 2] = yy.z + tt.z; v[i + 3] = yy.w + tt.w;
                         }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) skipc[(cc * 32 + i) * 128] = v[i];
+                        if (cc == 0) sum.c = v[0];
+                        stat_regs<32>(v, sum);
                         tmem_st32(e.taddr + 128 + cc * 32, v);
                     }
                 }
@@ -720,7 +752,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 wait_done(e, 0);                              // last projection of group 1 has landed
                 {
                     const float* G = e.P + hf * tfp::SA_GROUP;
-                    const float sum = resid_update(e, G + tfp::SA_BPROJ, nullptr, nullptr);
+                    const RowStat sum = resid_update(e, G + tfp::SA_BPROJ, nullptr, nullptr);
                     float mean, rstd;
                     ln_stats<false>(e, sum, 0, mean, rstd);
                     ln_to_abuf(e, mean, rstd, G + tfp::SA_LN2G, G + tfp::SA_LN2B);
@@ -740,16 +772,16 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 {
                     const float* G = e.P + hf * tfp::SM_GROUP;
                     if (!last) {
-                        const float sum = resid_update(e, G + tfp::SM_BP2, tb1, nullptr);
+                        const RowStat sum = resid_update(e, G + tfp::SM_BP2, tb1, nullptr);
                         float mean, rstd;
                         ln_stats<false>(e, sum, 0, mean, rstd);
                         ln_to_abuf(e, mean, rstd, e.P + tfp::SM_LNN_G + hf * 128, e.P + tfp::SM_LNN_B + hf * 128);
                     } else {
                         // stream junction: x = ln2_x(x + x_skip) | y = ln2_y(y + y_skip); z = cat(x, y) + time_expand(temb)
-                        const float sum = resid_update(e, G + tfp::SM_BP2, tb1, skipc);
+                        const RowStat sum = resid_update(e, G + tfp::SM_BP2, tb1, skipc);
                         float mean, rstd;
                         ln_stats<false>(e, sum, 0, mean, rstd);
-                        const float sum2 = ln_to_resid(e, mean, rstd, e.P + tfp::SM_LNN_G + hf * 128, e.P + tfp::SM_LNN_B + hf * 128, tb2);
+                        const RowStat sum2 = ln_to_resid(e, mean, rstd, e.P + tfp::SM_LNN_G + hf * 128, e.P + tfp::SM_LNN_B + hf * 128, tb2);
                         ln_stats<true>(e, sum2, 1, mean, rstd);
                         ln_to_abuf(e, mean, rstd, e.P + tfp::SM_LN2ND_G + hf * 128, e.P + tfp::SM_LN2ND_B + hf * 128);
                     }
@@ -768,7 +800,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                                        e.P + tfp::BA_QG, e.P + tfp::BA_QB, e.P + tfp::BA_KG, e.P + tfp::BA_KB, seg_b, seg_e);
                 wait_done(e, 0);
                 {
-                    const float sum = resid_update(e, e.P + tfp::BA_BPROJ + hf * 128, nullptr, nullptr);
+                    const RowStat sum = resid_update(e, e.P + tfp::BA_BPROJ + hf * 128, nullptr, nullptr);
                     float mean, rstd;
                     ln_stats<true>(e, sum, 0, mean, rstd);
                     ln_to_abuf(e, mean, rstd, e.P + tfp::BA_LN2G + hf * 128, e.P + tfp::BA_LN2B + hf * 128);
@@ -785,7 +817,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 {
                     // not last: z += bias + temb, LayerNorm ln1 of the next block.
                     // last: ParticleFormer  x = ln3_x(x + x_skip) | y = ln3_y(y + y_skip);  Fused  z = ln2(z + z_skip)
-                    const float sum = resid_update(e, e.P + tfp::BM_BP2 + hf * 128, tb2, last ? skipc : nullptr);
+                    const RowStat sum = resid_update(e, e.P + tfp::BM_BP2 + hf * 128, tb2, last ? skipc : nullptr);
                     float mean, rstd;
                     if (last && pf) ln_stats<false>(e, sum, 0, mean, rstd); else ln_stats<true>(e, sum, 0, mean, rstd);
                     ln_to_abuf(e, mean, rstd, e.P + tfp::BM_LNN_G + hf * 128, e.P + tfp::BM_LNN_B + hf * 128);
