@@ -763,7 +763,10 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 for (int g = 0; g < 2; ++g) {
                     const float* G = e.P + g * tfp::SM_GROUP;
                     for (int q = 0; q < 4; ++q) {
-                        wait_done(e, q & 1);
+                        // up-projection halves land on done[0]; before H1 is rewritten (q = 3) the down-projection of
+                        // quarter 1 must have read it (done[1]) - see emit_mlp
+                        if (q == 0 || q == 2) wait_done(e, 0);
+                        if (q == 3) wait_done(e, 1);
                         fc_epilogue(e, q, G + tfp::SM_BFC + q * 128);
                         go(e);
                     }
@@ -809,7 +812,8 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 param_release(e);
                 param_acquire(e);                             // MLP stage
                 for (int q = 0; q < 4; ++q) {
-                    wait_done(e, q & 1);
+                    if (q == 0 || q == 2) wait_done(e, 0);
+                    if (q == 3) wait_done(e, 1);
                     fc_epilogue(e, q, e.P + tfp::BM_BFC + q * 128);
                     go(e);
                 }

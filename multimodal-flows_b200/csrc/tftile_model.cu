@@ -140,17 +140,21 @@ BlockW load_block(WeightMap& wm, const std::string& p, int C, int I) {
                   mat(wm, p + ".ffw.c_fc.weight", I, C), mat(wm, p + ".ffw.c_proj.weight", C, I)};
 }
 
-// MLP of one group: quarters of the hidden layer ping-pong through the two scratch halves
+// MLP of one group.  The up-projection runs as two N = 256 halves over the whole scratch (one MMA instruction per K = 16
+// step costs ~90 cycles to issue whatever N is, so wide instructions halve the issue time); the epilogue turns each half
+// into two 128-column quarters H0 | H1, and the down-projection of a quarter accumulates onto the residual (N = C).
+//   MMA order   fc(h0) | out(q0) | fc(h1) out(q1) | out(q2) | out(q3)      ("|" = waits for the next go of the epilogue)
+//   signals     fc(h) -> done[0]; out(q1) -> done[1] (H1 may be rewritten); the last out(q3) -> done[0] when final_signal
 void emit_mlp(Builder& b, const BlockW& w, int C, int a_chunk0, uint16_t dcol_out, bool first_wait, bool final_signal) {
     const int kbC = C / 64;
-    auto fc = [&](int q) {
-        b.ring_op(oA + a_chunk0 * kT, rows_of(w.fc, q * 128, 128), 0, kbC, static_cast<uint16_t>(256 + (q & 1) * 128), 0,
-                  first_wait && q == 0, 1 + (q & 1));
-    };
-    auto out = [&](int q) {                            // all C output columns in one MMA (N = 128 or 256)
-        b.ring_op((q & 1) ? oH1 : oH0, rows_of(w.p2, 0, C), q * 128, 2, dcol_out, 1, 1, (final_signal && q == 3) ? 1 : 0);
-    };
-    fc(0); fc(1); out(0); fc(2); out(1); fc(3); out(2); out(3);
+    auto fc = [&](int h, int wait) { b.ring_op(oA + a_chunk0 * kT, rows_of(w.fc, h * 256, 256), 0, kbC, 256, 0, wait, 1); };
+    auto out = [&](int q, int wait, int signal) { b.ring_op((q & 1) ? oH1 : oH0, rows_of(w.p2, 0, C), q * 128, 2, dcol_out, 1, wait, signal); };
+    fc(0, first_wait);
+    out(0, 1, 0);
+    fc(1, 1);
+    out(1, 0, 2);
+    out(2, 1, 0);
+    out(3, 1, final_signal ? 1 : 0);
 }
 
 }  // namespace
