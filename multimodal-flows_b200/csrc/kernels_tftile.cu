@@ -523,9 +523,12 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 const uint2 ent = prodtab.e[i];
                 const uint32_t g = gbase + i, bytes = (ent.x >> 24) * 1024u;
                 const int need = static_cast<int>(g) - static_cast<int>((ent.y >> 8) & 0xffu) + 1;
-                while (static_cast<int>(known) < need) {
-                    mbar_wait(&bars->empty[known % kBars], (known / kBars) & 1);
-                    ++known;
+                if (static_cast<int>(known) < need) {
+                    // consumption is in order, so waiting for tile need - 1 covers all earlier ones; its barrier cannot be a
+                    // phase behind, because need advances by far fewer than kBars tiles between two waits of this warp
+                    const uint32_t t = static_cast<uint32_t>(need - 1);
+                    mbar_wait(&bars->empty[t % kBars], (t / kBars) & 1);
+                    known = static_cast<uint32_t>(need);
                 }
                 if (elect_one()) {
                     uint64_t* full = &bars->full[g % kBars];

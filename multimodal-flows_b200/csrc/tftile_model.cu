@@ -76,20 +76,33 @@ struct Builder {
                                        (static_cast<uint32_t>(signal) << 4));
         ops.push_back(o);
     }
-    // Ring placement: tiles go to increasing offsets and restart at 0 when the next one would not fit (and at every
-    // timestep start, so that the plan repeats).  Two timesteps are simulated; the second gives the steady-state
-    // dependency of every tile on the consumption of the tiles it overwrites.
+    // Ring placement.  Tiles are consumed in order, so writing a tile over older ones only has to wait for the NEWEST tile
+    // it overlaps (all older ones were consumed before it).  Every tile takes the size-aligned position whose newest
+    // overlapped tile is oldest: with uniform sizes this is a plain ring; with mixed 16 / 24 / 32 KB tiles it keeps two big
+    // tiles in flight instead of serialising them on a misaligned offset.  Two timesteps are simulated (the plan repeats
+    // every timestep); the second gives the steady-state dependency of every tile.
     bool plan_ring() {
         struct Res { long idx; int beg, end; };
         std::vector<Res> res;
         const long n = static_cast<long>(tiles.size());
         long required = -1;                           // newest tile that must have been consumed so far
+        std::vector<int> place(static_cast<size_t>(n), -1);
         for (int pass = 0; pass < 2; ++pass) {
-            int pos = 0;
             for (long j = 0; j < n; ++j) {
                 const int bytes = static_cast<int>(tiles[j].x >> 24) * 1024;
                 if (bytes <= 0 || bytes > kTfRingBytes) return false;
-                if (pos + bytes > kTfRingBytes) pos = 0;
+                int pos = place[j];
+                if (pos < 0) {                        // first pass decides; the second pass must repeat the same offsets
+                    const int align = bytes >= 32768 ? 32768 : (bytes >= 16384 && bytes % 16384 == 0 ? 16384 : 8192);
+                    long best = 0;
+                    for (int cand = 0; cand + bytes <= kTfRingBytes; cand += align) {
+                        long newest = -1;
+                        for (const Res& r : res)
+                            if (r.beg < cand + bytes && cand < r.end) newest = std::max(newest, r.idx);
+                        if (pos < 0 || newest < best) { pos = cand; best = newest; }
+                    }
+                    place[j] = pos;
+                }
                 size_t newest = res.size();
                 for (size_t i = 0; i < res.size(); ++i)
                     if (res[i].beg < pos + bytes && pos < res[i].end) newest = i;
@@ -102,8 +115,10 @@ struct Builder {
                 if (static_cast<int>(res.size()) >= kTfRingBars) return false;
                 const long dep = required < 0 ? 255 : g - required;
                 if (dep < 1 || (dep > 255)) return false;
-                if (pass == 1) tiles[j].y = static_cast<uint32_t>(pos / 1024) | static_cast<uint32_t>(dep) << 8;
-                pos += bytes;
+                if (pass == 1) {
+                    if (dep > kTfRingBars - 4) return false;      // the producers rely on dep staying well below the barrier count
+                    tiles[j].y = static_cast<uint32_t>(pos / 1024) | static_cast<uint32_t>(dep) << 8;
+                }
             }
         }
         return true;
