@@ -41,9 +41,10 @@ struct TfBars {
 
 // fp32 scratch after the two parameter buffers (float offsets)
 // (mOut, the per-row head partial sums, is only live at the very end of a timestep and aliases the LayerNorm / softmax exchange)
-constexpr int mXs = 0, mKs = mXs + 384, mStat = mKs + 128, mRed = mStat + 1024, mSum = mRed + 256, mOut = mStat,
-              mTemb = mSum + 256, mEnd = mTemb + 512;
-static_assert(128 * 12 <= 1024 + 256 + 256, "head partial sums alias the exchange buffers");
+// (mRed / mSum have two slots: the two heads of a 64-column unit are in flight together)
+constexpr int mXs = 0, mKs = mXs + 384, mStat = mKs + 128, mRed = mStat + 1024, mSum = mRed + 512, mOut = mStat,
+              mTemb = mSum + 512, mEnd = mTemb + 512;
+static_assert(128 * 12 <= 1024 + 512 + 512, "head partial sums alias the exchange buffers");
 constexpr int kSmemBytes = 1024 + 1024 + kArena + 2 * kTfParamFloats * 4 + mEnd * 4;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
@@ -312,8 +313,10 @@ __device__ __forceinline__ void v_epilogue(Epi& e, const float* bv) {
 // scores of one head in scratch columns [scol, scol+128); thread handles keys [hf*64, +64) of its row.
 // e.kmask: which of the thread's four 16-key groups hold a key of ANY row of this warp (warp-uniform, fixed for the
 // launch): the other groups are outside every jet of these 32 rows, so their probabilities are exact zeros.
-__device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, float scale_log2e, int kb, int ke) {
-    float s[64];
+// softmax_probs leaves the unnormalised probabilities in s[] and returns their sum; softmax_store writes them as the bf16
+// P operand (chunk hf of the Q|K staging area, which the previous P V product must have finished reading).
+// `slot` selects the exchange buffers.
+__device__ __forceinline__ float softmax_probs(Epi& e, uint32_t scol, float scale_log2e, int kb, int ke, int slot, float* s) {
     const uint32_t km = e.kmask;
     tmem_ld32(e.taddr + scol + e.hf * 64, s);
     tmem_ld32(e.taddr + scol + e.hf * 64 + 32, s + 32);
@@ -343,7 +346,7 @@ __device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, float sc
             mx = fmaxf(mx, max_regs<16>(s + 16 * g));
         }
     }
-    float* red = e.misc + mRed;
+    float* red = e.misc + mRed + slot * 256;
     red[e.hf * 128 + e.r] = mx;
     epi_bar();
     mx = fmaxf(mx, red[(e.hf ^ 1) * 128 + e.r]);
@@ -360,14 +363,22 @@ __device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, float sc
             for (int j = 16 * g; j < 16 * g + 16; ++j) s[j] = 0.f;
         }
     }
+    return sum;
+}
+__device__ __forceinline__ void softmax_store(Epi& e, int slot, const float* s, float sum) {
     stage_row_bf16(e.arena + (e.hf ? oK : oQ), e.r, s);          // P chunk hf (keys hf*64..)
-    e.misc[mSum + e.hf * 128 + e.r] = sum;
+    e.misc[mSum + slot * 256 + e.hf * 128 + e.r] = sum;
+}
+__device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, float scale_log2e, int kb, int ke, int slot) {
+    float s[64];
+    const float sum = softmax_probs(e, scol, scale_log2e, kb, ke, slot, s);
+    softmax_store(e, slot, s, sum);
 }
 
 // O = P V of one head in scratch columns [ocol, ocol+HS) -> normalised bf16 into Os columns [ucol, ucol+HS) of the unit
 template <int HS>
-__device__ __forceinline__ void o_epilogue(Epi& e, uint32_t ocol, int ucol) {
-    const float tot = e.misc[mSum + e.r] + e.misc[mSum + 128 + e.r];
+__device__ __forceinline__ void o_epilogue(Epi& e, uint32_t ocol, int ucol, int slot) {
+    const float tot = e.misc[mSum + slot * 256 + e.r] + e.misc[mSum + slot * 256 + 128 + e.r];
     const float inv = rcp_approx(tot > 0.f ? tot : 1.f);
     constexpr int W = HS / 2;
     float o[W];
@@ -437,21 +448,23 @@ __device__ __forceinline__ void attention_unit(Epi& e, const float* bq, const fl
     v_epilogue<HS>(e, bv);                            // under the score MMA; P V is only issued after the next go
     if (HS == 64) {
         wait_done(e, 0);
-        softmax_epilogue(e, kScr, scale, seg_b, seg_e);
+        softmax_epilogue(e, kScr, scale, seg_b, seg_e, 0);
         go(e);
         wait_done(e, 0);
-        o_epilogue<64>(e, kScr + 192, 0);
+        o_epilogue<64>(e, kScr + 192, 0, 0);
         go(e);
     } else {
         wait_done(e, 0);                              // both heads' scores: [256,384) and [384,512)
-        softmax_epilogue(e, kScr, scale, seg_b, seg_e);
-        go(e);
-        wait_done(e, 1);                              // O of head 0 in scratch [0,32)
-        o_epilogue<32>(e, kScr, 0);
-        softmax_epilogue(e, kScr + 128, scale, seg_b, seg_e);
-        go(e);
+        softmax_epilogue(e, kScr, scale, seg_b, seg_e, 0);
+        go(e);                                        // -> P V of head 0
+        float s[64];                                  // head 1's probabilities are computed under that product ...
+        const float sum = softmax_probs(e, kScr + 128, scale, seg_b, seg_e, 1, s);
+        wait_done(e, 1);                              // ... and stored once it has finished reading head 0's
+        softmax_store(e, 1, s, sum);
+        go(e);                                        // -> P V of head 1
+        o_epilogue<32>(e, kScr, 0, 0);                // O of head 0 in scratch [0,32), under P V of head 1
         wait_done(e, 0);                              // O of head 1 in scratch [32,64)
-        o_epilogue<32>(e, kScr + 32, 32);
+        o_epilogue<32>(e, kScr + 32, 32, 1);
         go(e);
     }
 }
