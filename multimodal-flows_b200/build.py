@@ -9,7 +9,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "mmf_b200", "libmmf_b200.so")
-SOURCES = ["kernels_tc.cu", "kernels_simt.cu", "kernels_epic.cu", "epic_model.cu", "kernels_tftile.cu", "tftile_model.cu", "model.cu"]
+SOURCES = ["kernels_tc.cu", "kernels_simt.cu", "kernels_epic.cu", "epic_model.cu", "kernels_tftile.cu", "kernels_tftile.cu@trace",
+           "tftile_model.cu", "model.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "--expt-relaxed-constexpr"]
@@ -30,8 +31,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        extra = []
+        if src.endswith("@trace"):                    # second build of the tile kernel with clock stamps (debugging aid)
+            src = src[: -len("@trace")]
+            obj = os.path.join(objdir, src.replace(".cu", "_trace.o"))
+            extra = ["-DMMF_TILE_TRACE=1"]
+        else:
+            obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [NVCC, *FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         res = subprocess.run(cmd, capture_output=True, text=True)

@@ -100,15 +100,18 @@ __device__ __forceinline__ void global_hidden(const bf16* __restrict__ Wt, int K
 
 // 16-wide output of a global MLP with all 256 threads: jet j = tid / 32, output q = (tid / 2) % 16, the two lanes of a pair
 // take one half of the 256-long dot product each.  The result W2[q] . hid[j] + b2[q] is valid in the even lane.
-__device__ __forceinline__ float global_out16(const float* W2 /* shared memory */, const float* __restrict__ b2,
+// W2 sits in shared memory as [16][64] float4 with the float4 index of row q XOR-ed by (2q + (c >> 5)) & 7 (stage_w2): the 8
+// lanes of a quarter warp (4 rows x 2 halves) then read 8 different 16-byte bank groups instead of one.
+__device__ __forceinline__ int w2_slot(int q, int c) { return q * 64 + (c ^ ((2 * q + (c >> 5)) & 7)); }
+__device__ __forceinline__ float global_out16(const float* W2 /* shared memory, swizzled */, const float* __restrict__ b2,
                                               const float* s_hid, int tid) {
     const int j = tid >> 5, q = (tid >> 1) & 15, half = tid & 1;
-    const float4* w = reinterpret_cast<const float4*>(W2 + q * 256 + half * 128);
+    const float4* w = reinterpret_cast<const float4*>(W2);
     const float4* h = reinterpret_cast<const float4*>(s_hid + j * 256 + half * 128);
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;             // four independent chains
 #pragma unroll
     for (int o = 0; o < 32; ++o) {
-        const float4 a = w[o], b = h[o];
+        const float4 a = w[w2_slot(q, half * 32 + o)], b = h[o];
         a0 = fmaf(a.x, b.x, a0); a1 = fmaf(a.y, b.y, a1); a2 = fmaf(a.z, b.z, a2); a3 = fmaf(a.w, b.w, a3);
     }
     float acc = (a0 + a1) + (a2 + a3);
@@ -227,32 +230,49 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
         // skip stream (bf16), layout per tile [col / 8][row][8]: a warp reads / writes 512 contiguous bytes per instruction
         uint4* skip8 = reinterpret_cast<uint4*>(a.loc_skip) + static_cast<size_t>(tile) * 32 * 128 + r;   // + (col / 8) * 128
 
-        // masked sum pooling of the bf16 local features in Abuf; thread = column
+        // masked sum pooling of the bf16 local features in Abuf.  A warp covers 32 columns (4 lanes x 8 columns, one 16-byte
+        // unit per load) x 8 row slices; the slices are reduced with shuffles, so the order is fixed and the result deterministic.
         auto pool = [&](bool with_glob) {
-            const int col = tid;
-            const uint8_t* ch = Abuf + (col >> 6) * kTile + (col & 7) * 2;
-            const uint32_t u = (col & 63) >> 3;
+            const int g = lane >> 2, cu = warp * 4 + (lane & 3);              // row slice, 8-column unit (0..31)
+            const uint8_t* ch = Abuf + (cu >> 3) * kTile;
+            const uint32_t u = cu & 7;
             for (int j = 0; j < njets; ++j) {
                 const int r1 = s_meta->jet_begin[j + 1];
-                int rr = s_meta->jet_begin[j];
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;          // independent chains: the loop is LDS-latency bound
-                for (; rr + 4 <= r1; rr += 4) {
-                    s0 += __bfloat162float(*reinterpret_cast<const bf16*>(ch + sw128_offset(rr, u)));
-                    s1 += __bfloat162float(*reinterpret_cast<const bf16*>(ch + sw128_offset(rr + 1, u)));
-                    s2 += __bfloat162float(*reinterpret_cast<const bf16*>(ch + sw128_offset(rr + 2, u)));
-                    s3 += __bfloat162float(*reinterpret_cast<const bf16*>(ch + sw128_offset(rr + 3, u)));
+                float acc[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+                for (int rr = s_meta->jet_begin[j] + g; rr < r1; rr += 8) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(ch + sw128_offset(rr, u));
+                    acc[0] += bf16_lo(w.x); acc[1] += bf16_hi(w.x); acc[2] += bf16_lo(w.y); acc[3] += bf16_hi(w.y);
+                    acc[4] += bf16_lo(w.z); acc[5] += bf16_hi(w.z); acc[6] += bf16_lo(w.w); acc[7] += bf16_hi(w.w);
                 }
-                for (; rr < r1; ++rr) s0 += __bfloat162float(*reinterpret_cast<const bf16*>(ch + sw128_offset(rr, u)));
-                float s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float v = acc[e];
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 8);
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                    acc[e] = v;
+                }
                 if (s_meta->pair) {                              // the other half of the jet lives in the peer CTA
-                    dsmem_st_f32(dsmem_addr(s_xchg + px * 256 + col, peer), s);
+                    if (g == 0) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) dsmem_st_f32(dsmem_addr(s_xchg + px * 256 + cu * 8 + e, peer), acc[e]);
+                    }
                     mbar_arrive_remote(dsmem_addr(&bars->xchg, peer));
                     mbar_wait_cluster(&bars->xchg, px);
-                    s += s_xchg[px * 256 + col];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[e] += s_xchg[px * 256 + cu * 8 + e];
                     px ^= 1;
                 }
-                s_pool[j * kPoolLd + col] = s / static_cast<float>(s_meta->jet_ntot[j]);
-                s_pool[j * kPoolLd + 256 + col] = s * 0.01f;
+                if (g == 0) {
+                    const float ntot = static_cast<float>(s_meta->jet_ntot[j]);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        s_pool[j * kPoolLd + cu * 8 + e] = acc[e] / ntot;
+                        s_pool[j * kPoolLd + 256 + cu * 8 + e] = acc[e] * 0.01f;
+                    }
+                }
             }
             if (with_glob && tid < njets * 16) s_pool[(tid >> 4) * kPoolLd + 512 + (tid & 15)] = s_glob[tid];
             epi_bar();
@@ -263,7 +283,10 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
             const float4* src = reinterpret_cast<const float4*>(W2);
             float4* dst = reinterpret_cast<float4*>(s_part);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dst[tid + i * kEpi] = __ldg(src + tid + i * kEpi);
+            for (int i = 0; i < 4; ++i) {
+                const int idx = tid + i * kEpi;
+                dst[w2_slot(idx >> 6, idx & 63)] = __ldg(src + idx);
+            }
         };
 
         int mark_i = 0;

@@ -64,9 +64,16 @@ struct Epi {
     unsigned long long* trace;   // clock stamps of CTA 0 / thread 0 for the first two timesteps (debugging aid) or null
     int mark_i, step;
 };
+// This file is compiled twice (build.py): the production object has no clock stamps at all; the object built with
+// -DMMF_TILE_TRACE=1 exports launch_tf_tiles_trace, which tftile_launch uses when MMF_TRACE is set.
+#ifndef MMF_TILE_TRACE
+#define MMF_TILE_TRACE 0
+#endif
 __device__ __forceinline__ void mark(Epi& e) {
+#if MMF_TILE_TRACE
     if (e.trace && e.step < 2 && e.mark_i < 256) e.trace[e.step * 256 + e.mark_i] = clock64();
     ++e.mark_i;
+#endif
 }
 
 __device__ __forceinline__ void epi_bar() { named_bar_sync(1, kEpi); }
@@ -610,7 +617,9 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 if (fl & 0x30u) {
                     if (elect_one()) {
                         umma_commit(&bars->done[(fl >> 5) & 1u]);
+#if MMF_TILE_TRACE
                         if (a.trace && blockIdx.x == 0 && step == 1 && i < 128) a.trace[768 + i] = clock64();
+#endif
                     }
                     __syncwarp();
                 }
@@ -939,9 +948,13 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
 
 }  // namespace
 
+#if MMF_TILE_TRACE
+int launch_tf_tiles_trace(const TfLaunch& a, int n_tiles, int cluster, cudaStream_t stream) {
+#else
 int tf_tile_smem_bytes() { return kSmemBytes; }
 
 int launch_tf_tiles(const TfLaunch& a, int n_tiles, int cluster, cudaStream_t stream) {
+#endif
     if (n_tiles == 0) return 0;
     MMF_REQUIRE(a.vocab == 9, "the tile kernel is instantiated for vocab_size 9");
     MMF_REQUIRE((cluster == 1 || cluster == 2 || cluster == 4) && n_tiles % cluster == 0, "tile launch: bad cluster size");

@@ -533,7 +533,7 @@ int tftile_launch(TfTileModel* m, cudaStream_t s) {
         MMF_CUDA_OK(cudaMemsetAsync(d_trace, 0, 1536 * 8, s));
         a.trace = d_trace;
     }
-    MMF_TRY_RC(launch_tf_tiles(a, tiles, m->cluster, s));
+    MMF_TRY_RC(d_trace ? launch_tf_tiles_trace(a, tiles, m->cluster, s) : launch_tf_tiles(a, tiles, m->cluster, s));
     m->launches += 1;
     if (d_trace) {
         std::vector<unsigned long long> hbuf(1536);

@@ -6,3 +6,6 @@ for M in ParticleFormer FusedParticleFormer; do
   MMF_TRACE=gpurun_out/iter_trace_$M.txt timeout 120 python tools/tf_trace.py $M > /dev/null 2>&1
 done
 timeout 300 python bench.py --model ParticleFormer --batch 1024 --steps 3 --warmup 3 --no-cpu-baseline --no-step-roofline 2>/dev/null | cut -c1-330
+timeout 300 python bench.py --model EPiC --steps 5 --warmup 3 --no-cpu-baseline --no-step-roofline 2>/dev/null | cut -c1-330
+timeout 300 python bench.py --model EPiC --batch 4096 --steps 3 --warmup 3 --no-cpu-baseline --no-step-roofline 2>/dev/null | cut -c1-330
+MMF_TRACE=gpurun_out/iter_trace_EPiC.txt timeout 120 python tools/epic_trace.py > /dev/null 2>&1
