@@ -46,60 +46,65 @@ __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w 
 // (Wt bf16 [K][256], transposed on the host).  The matrix is streamed from L2 once per call with 16-byte loads, 16 in flight
 // per thread (the loop is bound by bytes in flight, not by FMAs): a warp covers 32 outputs (4 lanes x 8) x 8 k-slices, the
 // k-slices are reduced with shuffles.  Jets are processed four at a time (tiles rarely hold more).
+// NJ jets (1..4) at a time; NJ is a template parameter so that no predicated-off FMAs are issued for missing jets
+template <bool GELU, int NJ>
+__device__ __forceinline__ void global_hidden_jets(const uint4* __restrict__ wp, int kn, const float* s_pool_k0, float* s_hid,
+                                                   const float* bias0, int bias_jet_stride, const int* jet_tb, int j0, int o0, int ks) {
+    float acc[NJ][8];
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[jj][e] = 0.f;
+#pragma unroll 16
+    for (int k = 0; k < kn; ++k) {
+        const uint4 w = __ldg(wp + k * 256);                // row 8 k + ks, outputs o0 .. o0+7
+        const float we[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y), bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+            const float p = s_pool_k0[(j0 + jj) * kPoolLd + k * 8];   // the 8 slices of a warp read 8 consecutive words
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[jj][e] = fmaf(we[e], p, acc[jj][e]);
+        }
+    }
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float v = acc[jj][e];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            acc[jj][e] = v;
+        }
+    if (ks == 0) {
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+            const float* b = bias0 + static_cast<size_t>(bias_jet_stride ? jet_tb[j0 + jj] : 0) * bias_jet_stride + o0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float v = acc[jj][e] + __ldg(b + e);
+                s_hid[(j0 + jj) * 256 + o0 + e] = GELU ? gelu_erf(v) : leaky_relu(v);
+            }
+        }
+    }
+}
+
 template <bool GELU>
 __device__ __forceinline__ void global_hidden(const bf16* __restrict__ Wt, int K, const float* s_pool, float* s_hid,
                                               const float* bias0, int bias_jet_stride, const int* jet_tb, int njets, int tid) {
     const int lane = tid & 31, ks = lane >> 2, o0 = ((tid >> 5) * 4 + (lane & 3)) * 8;
-    const int kn = K >> 3, k0 = ks * kn;                       // 64 or 66 rows of Wt per slice
+    const int kn = K >> 3, k0 = ks;                            // slice ks takes rows ks, ks + 8, ... (64 or 66 of them)
     const uint4* wp = reinterpret_cast<const uint4*>(Wt + static_cast<size_t>(k0) * 256 + o0);
     for (int j0 = 0; j0 < njets; j0 += 4) {
-        float acc[4][8];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[jj][e] = 0.f;
-#pragma unroll 16
-        for (int k = 0; k < kn; ++k) {
-            const uint4 w = __ldg(wp + k * 32);                 // row k0 + k, outputs o0 .. o0+7
-            const float we[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y), bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                if (j0 + jj < njets) {
-                    const float p = s_pool[(j0 + jj) * kPoolLd + k0 + k];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[jj][e] = fmaf(we[e], p, acc[jj][e]);
-                }
-            }
-        }
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                float v = acc[jj][e];
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 8);
-                v += __shfl_xor_sync(0xffffffffu, v, 16);
-                acc[jj][e] = v;
-            }
-        if (ks == 0) {
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                if (j0 + jj < njets) {
-                    const float* b = bias0 + static_cast<size_t>(bias_jet_stride ? jet_tb[j0 + jj] : 0) * bias_jet_stride + o0;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float v = acc[jj][e] + __ldg(b + e);
-                        s_hid[(j0 + jj) * 256 + o0 + e] = GELU ? gelu_erf(v) : leaky_relu(v);
-                    }
-                }
-            }
-        }
+        const int nj = njets - j0;                             // warp-uniform
+        if (nj >= 4) global_hidden_jets<GELU, 4>(wp, kn, s_pool + k0, s_hid, bias0, bias_jet_stride, jet_tb, j0, o0, ks);
+        else if (nj == 3) global_hidden_jets<GELU, 3>(wp, kn, s_pool + k0, s_hid, bias0, bias_jet_stride, jet_tb, j0, o0, ks);
+        else if (nj == 2) global_hidden_jets<GELU, 2>(wp, kn, s_pool + k0, s_hid, bias0, bias_jet_stride, jet_tb, j0, o0, ks);
+        else global_hidden_jets<GELU, 1>(wp, kn, s_pool + k0, s_hid, bias0, bias_jet_stride, jet_tb, j0, o0, ks);
     }
     epi_bar();
 }
 
-// 16-wide output of a global MLP with all 256 threads: jet j = tid / 32, output q = (tid / 2) % 16, the two lanes of a pair
-// take one half of the 256-long dot product each.  The result W2[q] . hid[j] + b2[q] is valid in the even lane.
 // W2 sits in shared memory as [16][64] float4 with the float4 index of row q XOR-ed by (2q + (c >> 5)) & 7 (stage_w2): the 8
 // lanes of a quarter warp (4 rows x 2 halves) then read 8 different 16-byte bank groups instead of one.
 __device__ __forceinline__ int w2_slot(int q, int c) { return q * 64 + (c ^ ((2 * q + (c >> 5)) & 7)); }
@@ -380,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
 #pragma unroll 1
             for (int l = 0; l < kEpicLayers; ++l) {
                 // the fc_loc1 GEMM of this layer is already running on the tensor core; meanwhile the global path:
-                stage_w2(a.p.wg2[l]);                         // (the previous user of s_part finished before the last epi_bar)
+                if (l == 0) stage_w2(a.p.wg2[0]);             // (later layers: staged under the previous layer's fc_loc2 GEMM)
                 // fc_loc1's global columns for this thread's output: loaded now, used after the global MLP
                 const float4* wg = reinterpret_cast<const float4*>(a.p.wl1g[l] + tid * 16);
                 const float4 w0 = __ldg(wg), w1 = __ldg(wg + 1), w2 = __ldg(wg + 2), w3 = __ldg(wg + 3);
@@ -443,6 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
                 uint4 sk[16];
 #pragma unroll
                 for (int u = 0; u < 16; ++u) sk[u] = skip8[(hf * 16 + u) * 128];
+                if (l + 1 < kEpicLayers) stage_w2(a.p.wg2[l + 1]);   // this layer's global output (the last reader of s_part) is done
                 mbar_wait(&bars->acc_full, pf);
                 pf ^= 1;
                 tc_fence_after();
