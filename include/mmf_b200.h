@@ -146,6 +146,11 @@ int mmf_dbg_gemm_qkv(const void* A_bf16, const void* W_bf16, const float* bias, 
 int mmf_dbg_attention(const void* q, const void* k, const void* vT, const int32_t* jet_n, int32_t n_jets, int32_t M,
                       int32_t C, int32_t hs, void* out, int32_t device, void* stream);
 
+/* host only: placement of n weight tiles (sizes in KB, consumption order, repeated every timestep) in the 64 KB
+ * shared-memory ring of the persistent tile kernel.  dst_kb[i] = offset in KB; dep[i]: tile g of the launch may be written
+ * once all tiles up to g - dep[i] have been consumed.  Fails when a tile cannot be placed. */
+int mmf_dbg_ring_plan(const int32_t* tile_kb, int32_t n, int32_t* dst_kb, int32_t* dep);
+
 #ifdef __cplusplus
 }
 #endif

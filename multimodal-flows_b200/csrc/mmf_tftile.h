@@ -138,6 +138,9 @@ struct TfLaunch {
     unsigned long long* trace;
 };
 
+// host-side placement of the weight tiles in the 64 KB ring (tftile_model.cu); exported for tests as mmf_dbg_ring_plan
+bool plan_weight_ring(const std::vector<int>& kb, std::vector<int>* dst_kb, std::vector<int>* dep);
+
 int tf_tile_smem_bytes();
 // n_tiles must be a multiple of `cluster` (1, 2 or 4): the CTAs of a cluster share each weight tile through TMA multicast
 int launch_tf_tiles(const TfLaunch& a, int n_tiles, int cluster, cudaStream_t stream);

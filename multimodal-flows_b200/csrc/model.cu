@@ -791,6 +791,14 @@ int mmf_generate_host(MmfModel* m, const float* x0, const int64_t* k0, const int
 }
 
 // ------------------------------------------------------------------------------- diagnostics
+int mmf_dbg_ring_plan(const int32_t* tile_kb, int32_t n, int32_t* dst_kb, int32_t* dep) {
+    MMF_REQUIRE(tile_kb && dst_kb && dep && n > 0, "dbg_ring_plan: null argument");
+    std::vector<int> kb(tile_kb, tile_kb + n), d, q;
+    MMF_REQUIRE(plan_weight_ring(kb, &d, &q), "dbg_ring_plan: no valid plan for these tile sizes");
+    for (int i = 0; i < n; ++i) { dst_kb[i] = d[i]; dep[i] = q[i]; }
+    return 0;
+}
+
 int mmf_dbg_gemm(const void* A, const void* W, const float* bias, int32_t M, int32_t N, int32_t K, int32_t mode,
                  int32_t act, void* out, int32_t device, void* stream) {
     MMF_REQUIRE(M % 128 == 0 && N % 128 == 0 && K % 64 == 0, "dbg_gemm: M,N multiples of 128, K multiple of 64");

@@ -36,6 +36,59 @@ struct TfTileModel {
     }
 };
 
+// Ring placement.  Tiles are consumed in order, so writing a tile over older ones only has to wait for the NEWEST tile
+// it overlaps (all older ones were consumed before it).  Every tile takes the size-aligned position whose newest
+// overlapped tile is oldest: with uniform sizes this is a plain ring; with mixed 16 / 24 / 32 KB tiles it keeps two big
+// tiles in flight instead of serialising them on a misaligned offset.  Two timesteps are simulated (the plan repeats
+// every timestep); the second gives the steady-state dependency of every tile.
+//   kb[i]   size of tile i in KB            dst_kb[i]  offset in the ring in KB
+//   dep[i]  tile g (global index over the launch) may be written once all tiles up to g - dep[i] were consumed
+bool plan_weight_ring(const std::vector<int>& kb, std::vector<int>* dst_kb, std::vector<int>* dep_out) {
+    struct Res { long idx; int beg, end; };
+    std::vector<Res> res;
+    const long n = static_cast<long>(kb.size());
+    long required = -1;                           // newest tile that must have been consumed so far
+    std::vector<int> place(static_cast<size_t>(n), -1);
+    dst_kb->assign(static_cast<size_t>(n), 0);
+    dep_out->assign(static_cast<size_t>(n), 0);
+    for (int pass = 0; pass < 2; ++pass) {
+        for (long j = 0; j < n; ++j) {
+            const int bytes = kb[j] * 1024;
+            if (bytes <= 0 || bytes > kTfRingBytes) return false;
+            int pos = place[j];
+            if (pos < 0) {                        // first pass decides; the second pass must repeat the same offsets
+                const int align = bytes > 16384 ? 32768 : (bytes > 8192 ? 16384 : 8192);   // 24 KB tiles take a 32 KB half like the 32 KB ones
+                long best = 0;
+                for (int cand = 0; cand + bytes <= kTfRingBytes; cand += align) {
+                    long newest = -1;
+                    for (const Res& r : res)
+                        if (r.beg < cand + bytes && cand < r.end) newest = std::max(newest, r.idx);
+                    if (pos < 0 || newest < best) { pos = cand; best = newest; }
+                }
+                place[j] = pos;
+            }
+            size_t newest = res.size();
+            for (size_t i = 0; i < res.size(); ++i)
+                if (res[i].beg < pos + bytes && pos < res[i].end) newest = i;
+            if (newest != res.size()) {
+                required = std::max(required, res[newest].idx);
+                res.erase(res.begin(), res.begin() + newest + 1);
+            }
+            const long g = pass * n + j;
+            res.push_back(Res{g, pos, pos + bytes});
+            if (static_cast<int>(res.size()) >= kTfRingBars) return false;
+            const long dep = required < 0 ? 255 : g - required;
+            if (dep < 1 || dep > 255) return false;
+            if (pass == 1) {
+                if (dep > kTfRingBars - 4) return false;      // the producers rely on dep staying well below the barrier count
+                (*dst_kb)[j] = pos / 1024;
+                (*dep_out)[j] = static_cast<int>(dep);
+            }
+        }
+    }
+    return true;
+}
+
 namespace {
 
 // operand arena offsets: keep in sync with kernels_tftile.cu
@@ -76,51 +129,12 @@ struct Builder {
                                        (static_cast<uint32_t>(signal) << 4));
         ops.push_back(o);
     }
-    // Ring placement.  Tiles are consumed in order, so writing a tile over older ones only has to wait for the NEWEST tile
-    // it overlaps (all older ones were consumed before it).  Every tile takes the size-aligned position whose newest
-    // overlapped tile is oldest: with uniform sizes this is a plain ring; with mixed 16 / 24 / 32 KB tiles it keeps two big
-    // tiles in flight instead of serialising them on a misaligned offset.  Two timesteps are simulated (the plan repeats
-    // every timestep); the second gives the steady-state dependency of every tile.
     bool plan_ring() {
-        struct Res { long idx; int beg, end; };
-        std::vector<Res> res;
-        const long n = static_cast<long>(tiles.size());
-        long required = -1;                           // newest tile that must have been consumed so far
-        std::vector<int> place(static_cast<size_t>(n), -1);
-        for (int pass = 0; pass < 2; ++pass) {
-            for (long j = 0; j < n; ++j) {
-                const int bytes = static_cast<int>(tiles[j].x >> 24) * 1024;
-                if (bytes <= 0 || bytes > kTfRingBytes) return false;
-                int pos = place[j];
-                if (pos < 0) {                        // first pass decides; the second pass must repeat the same offsets
-                    const int align = bytes >= 32768 ? 32768 : (bytes >= 16384 && bytes % 16384 == 0 ? 16384 : 8192);
-                    long best = 0;
-                    for (int cand = 0; cand + bytes <= kTfRingBytes; cand += align) {
-                        long newest = -1;
-                        for (const Res& r : res)
-                            if (r.beg < cand + bytes && cand < r.end) newest = std::max(newest, r.idx);
-                        if (pos < 0 || newest < best) { pos = cand; best = newest; }
-                    }
-                    place[j] = pos;
-                }
-                size_t newest = res.size();
-                for (size_t i = 0; i < res.size(); ++i)
-                    if (res[i].beg < pos + bytes && pos < res[i].end) newest = i;
-                if (newest != res.size()) {
-                    required = std::max(required, res[newest].idx);
-                    res.erase(res.begin(), res.begin() + newest + 1);
-                }
-                const long g = pass * n + j;
-                res.push_back(Res{g, pos, pos + bytes});
-                if (static_cast<int>(res.size()) >= kTfRingBars) return false;
-                const long dep = required < 0 ? 255 : g - required;
-                if (dep < 1 || (dep > 255)) return false;
-                if (pass == 1) {
-                    if (dep > kTfRingBars - 4) return false;      // the producers rely on dep staying well below the barrier count
-                    tiles[j].y = static_cast<uint32_t>(pos / 1024) | static_cast<uint32_t>(dep) << 8;
-                }
-            }
-        }
+        std::vector<int> kb(tiles.size());
+        for (size_t i = 0; i < tiles.size(); ++i) kb[i] = static_cast<int>(tiles[i].x >> 24);
+        std::vector<int> dst, dep;
+        if (!plan_weight_ring(kb, &dst, &dep)) return false;
+        for (size_t i = 0; i < tiles.size(); ++i) tiles[i].y = static_cast<uint32_t>(dst[i]) | static_cast<uint32_t>(dep[i]) << 8;
         return true;
     }
     float* blob(int idx) {

@@ -40,7 +40,7 @@ _lib: Optional[ctypes.CDLL] = None
 EXPORTS = [
     "mmf_abi_version", "mmf_last_error", "mmf_model_create", "mmf_model_destroy", "mmf_encoder_forward",
     "mmf_hybrid_step", "mmf_euler_step", "mmf_generate", "mmf_generate_host", "mmf_launch_count",
-    "mmf_dbg_gemm", "mmf_dbg_gemm_resln", "mmf_dbg_gemm_qkv", "mmf_dbg_attention",
+    "mmf_dbg_gemm", "mmf_dbg_gemm_resln", "mmf_dbg_gemm_qkv", "mmf_dbg_attention", "mmf_dbg_ring_plan",
     "mmf_profile_enable", "mmf_profile_num_classes", "mmf_profile_class_name", "mmf_profile_read",
 ]
 

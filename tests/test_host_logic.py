@@ -116,3 +116,57 @@ def test_shard_bounds_cover_everything_once():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _check_ring_plan(sizes_kb):
+    """Replays a plan the way the device does and checks that no tile is written over one that may still be unread."""
+    import ctypes
+    import numpy as np
+    from mmf_b200 import _abi
+    L = _abi.lib()
+    n = len(sizes_kb)
+    kb = np.asarray(sizes_kb, dtype=np.int32)
+    dst = np.zeros(n, dtype=np.int32)
+    dep = np.zeros(n, dtype=np.int32)
+    as_p = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    _abi.check(L.mmf_dbg_ring_plan(as_p(kb), n, as_p(dst), as_p(dep)))
+    assert ((dst >= 0) & (dst + kb <= 64)).all() and (dep >= 1).all() and (dep <= 12).all()
+    # three timesteps: tile g may overwrite tile h (h < g) only if h <= g - dep[g % n], i.e. h is known to be consumed
+    live = []                                         # (global index, begin, end) of the tiles written so far
+    in_flight = []
+    for g in range(3 * n):
+        i = g % n
+        beg, end = int(dst[i]), int(dst[i] + kb[i])
+        consumed_upto = g - int(dep[i])               # the producer waits for this tile before writing
+        for (h, b, e) in live:
+            if b < end and beg < e:
+                assert h <= consumed_upto, (g, h, dep[i])
+        live = [(h, b, e) for (h, b, e) in live if not (b < end and beg < e)] + [(g, beg, end)]
+        if g >= n:
+            in_flight.append(g - max(consumed_upto, -1))
+    return dst, dep, in_flight
+
+
+def test_weight_ring_plan_uniform_tiles_is_a_plain_ring():
+    dst, dep, _ = _check_ring_plan([16] * 12)
+    assert sorted(set(dst.tolist())) == [0, 16, 32, 48] and (dep == 4).all()
+
+
+def test_weight_ring_plan_mixed_tiles_keeps_two_big_tiles_in_flight():
+    # one main block of the transformer: 4 x (QKV 4 x 24 KB, proj 32 KB), MLP 4 x 32 | 2 x 32 | 4 x 32 | 6 x 32 KB
+    block = ([24] * 4 + [32]) * 4 + [32] * 16
+    dst, dep, in_flight = _check_ring_plan(block * 2)
+    big = [d for d, k in zip(dst.tolist(), block * 2) if k == 32]
+    assert set(big) <= {0, 32}                        # 32 KB tiles never straddle the middle of the ring
+    assert min(in_flight) >= 2                        # at least two tiles may always be in flight
+
+
+def test_weight_ring_plan_rejects_oversized_tiles():
+    import ctypes
+    import numpy as np
+    from mmf_b200 import _abi
+    L = _abi.lib()
+    kb = np.asarray([16, 80, 16], dtype=np.int32)
+    out = np.zeros(3, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    assert L.mmf_dbg_ring_plan(p(kb), 3, p(out), p(out.copy())) != 0
