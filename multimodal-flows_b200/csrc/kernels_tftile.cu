@@ -8,6 +8,12 @@
 // Synchronisation: `go` (256 arrivals) epilogue -> MMA issuer, consumed in order by the ops flagged `wait`;
 // `done[0/1]` (tcgen05.commit) MMA -> epilogue; full/empty ring barriers producer <-> MMA issuer;
 // pfull/pempty parameter double buffer producer <-> epilogue.
+#include <cstdio>
+#include <cstring>
+#ifndef MMF_TILE_TRACE
+#define MMF_TILE_TRACE 0
+#endif
+#define MMF_WAIT_DIAG MMF_TILE_TRACE
 #include "mmf_ptx.cuh"
 #include "mmf_tftile.h"
 #include "mmf_tile.cuh"
@@ -78,8 +84,8 @@ __device__ __forceinline__ void mark(Epi& e) {
 
 __device__ __forceinline__ void epi_bar() { named_bar_sync(1, kEpi); }
 __device__ __forceinline__ void wait_done(Epi& e, int b) {
-    if (b == 0) { mbar_wait(&e.bars->done[0], e.pd0); e.pd0 ^= 1; }
-    else { mbar_wait(&e.bars->done[1], e.pd1); e.pd1 ^= 1; }
+    if (b == 0) { mbar_wait(&e.bars->done[0], e.pd0, e.mark_i); e.pd0 ^= 1; }     // (tag for the time-out diagnostics)
+    else { mbar_wait(&e.bars->done[1], e.pd1, e.mark_i); e.pd1 ^= 1; }
     tc_fence_after();
     mark(e);
 }
@@ -581,7 +587,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 if (i + 1 < a.n_ops) nx = optab.ops[i + 1];   // fetched one op ahead
                 const uint32_t fl = op.flags;
                 if (fl & kTfOpWait) {
-                    mbar_wait(&bars->go, pg);
+                    mbar_wait(&bars->go, pg, static_cast<uint32_t>(i));
                     pg ^= 1;
                 }
                 const bool ring = (fl & kTfOpRing) != 0;
@@ -593,7 +599,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                         b_lo = ring16 + (nt & 0xffu) * (1024u >> 4);
                         ++ti;
                         nt = prodtab.e[ti < static_cast<uint32_t>(a.n_prod) ? ti : 0].y;
-                        mbar_wait(&bars->full[g % kBars], (g / kBars) & 1);
+                        mbar_wait(&bars->full[g % kBars], (g / kBars) & 1, 0x8000u | static_cast<uint32_t>(i));
                     }
                     tc_fence_after();
                     if (elect_one()) {
@@ -949,7 +955,24 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
 }  // namespace
 
 #if MMF_TILE_TRACE
+static unsigned long long* g_dbg_host = nullptr;
+void tf_tiles_dump_timeouts() {     // after a failed launch: which barrier waits of CTA 0 timed out (see mbar_wait)
+    if (!g_dbg_host) return;
+    const unsigned n = static_cast<unsigned>(g_dbg_host[0]);
+    fprintf(stderr, "tile kernel: %u timed-out barrier waits in CTA 0 (tag: epilogue = stamps passed, issuer = op index, 0x8000 | op = weight tile)\n", n);
+    for (unsigned i = 0; i < n && i < 62; ++i) {
+        const unsigned long long v = g_dbg_host[1 + i];
+        fprintf(stderr, "  barrier smem+0x%llx parity %llu warp %llu tag %llu\n", (v >> 32) & 0xffff, (v >> 28) & 1, (v & 0xfff) >> 5, v >> 48);
+    }
+}
 int launch_tf_tiles_trace(const TfLaunch& a, int n_tiles, int cluster, cudaStream_t stream) {
+    if (!g_dbg_host) {
+        unsigned long long* dptr = nullptr;
+        MMF_CUDA_OK(cudaHostAlloc(&g_dbg_host, 64 * 8, cudaHostAllocMapped));
+        memset(g_dbg_host, 0, 64 * 8);
+        MMF_CUDA_OK(cudaHostGetDevicePointer(&dptr, g_dbg_host, 0));
+        MMF_CUDA_OK(cudaMemcpyToSymbol(mmf_dbg_sink, &dptr, sizeof(dptr)));
+    }
 #else
 int tf_tile_smem_bytes() { return kSmemBytes; }
 

@@ -64,14 +64,46 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: 2^26 retries (seconds), then trap (the launch fails loudly; the box never hangs).  The retry loop is kept
-// to four instructions so that waiting warps do not take issue slots from working ones.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded wait: 2^22 retries (a few seconds of wall clock at most), then trap (the launch fails loudly; the box never
+// hangs).  The retry loop is kept to four instructions so that waiting warps do not take issue slots from working ones.
+//
+// NOTE on phases: a wait tells the phases of an mbarrier apart by PARITY only.  A waiter that falls two completed phases
+// behind sees the parity it is waiting for "in progress" again and blocks for ever.  Every barrier protocol in this
+// library therefore keeps the arriving side at most ONE phase ahead: between two arrivals on the same barrier the
+// arriving threads wait for a result that the waiter can only have produced after passing the first arrival.
+//
+// Debugging aid (translation units compiled with -DMMF_WAIT_DIAG=1, i.e. the trace build of the tile kernel): a wait of
+// CTA 0 that times out first leaves {tag, barrier shared address, parity, thread} in mapped host memory (mmf_dbg_sink),
+// keeps waiting half as long again so that the other stuck warps get recorded too, and only then traps.
+#ifndef MMF_WAIT_DIAG
+#define MMF_WAIT_DIAG 0
+#endif
+#if MMF_WAIT_DIAG
+static __device__ unsigned long long* mmf_dbg_sink = nullptr;
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins == (1u << 26)) __trap();
+        ++spins;
+        if (spins == (1u << 22) && mmf_dbg_sink && (threadIdx.x & 31) == 0 && blockIdx.x == 0) {
+            const unsigned int slot = atomicAdd(reinterpret_cast<unsigned int*>(mmf_dbg_sink), 1u);
+            if (slot < 62) {
+                mmf_dbg_sink[1 + slot] = (static_cast<unsigned long long>(tag) << 48) | (static_cast<unsigned long long>(smem_u32(bar) & 0xffffu) << 32) |
+                                         (static_cast<unsigned long long>(parity) << 28) | (static_cast<unsigned long long>(blockIdx.x) << 12) | threadIdx.x;
+                __threadfence_system();
+            }
+        }
+        if (spins == (3u << 21)) __trap();
     }
 }
+#else
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
+    (void)tag;
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins == (1u << 22)) __trap();
+    }
+}
+#endif
 
 // --------------------------------------- TMA -------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

@@ -145,6 +145,7 @@ int tf_tile_smem_bytes();
 // n_tiles must be a multiple of `cluster` (1, 2 or 4): the CTAs of a cluster share each weight tile through TMA multicast
 int launch_tf_tiles(const TfLaunch& a, int n_tiles, int cluster, cudaStream_t stream);
 int launch_tf_tiles_trace(const TfLaunch& a, int n_tiles, int cluster, cudaStream_t stream);   // the same kernel with clock stamps
+void tf_tiles_dump_timeouts();   // trace build: prints the barrier waits that timed out in a failed launch
 
 // ---- host object (tftile_model.cu)
 struct TfTileModel;

@@ -551,7 +551,10 @@ int tftile_launch(TfTileModel* m, cudaStream_t s) {
     m->launches += 1;
     if (d_trace) {
         std::vector<unsigned long long> hbuf(1536);
-        MMF_CUDA_OK(cudaMemcpyAsync(hbuf.data(), d_trace, 1536 * 8, cudaMemcpyDeviceToHost, s));
+        if (cudaMemcpyAsync(hbuf.data(), d_trace, 1536 * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+            tf_tiles_dump_timeouts();
+            MMF_REQUIRE(false, "tile kernel: traced launch failed (stderr lists the barrier waits that timed out)");
+        }
         MMF_CUDA_OK(cudaStreamSynchronize(s));
         cudaFree(d_trace);
         if (FILE* f = fopen(trace_path, "w")) {
