@@ -335,6 +335,15 @@ def main():
                     "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + " sustained",
                     "avg_launch_us": 1e3 * d["ms"] / d["launches"], "launches_per_step": d["launches"],
                     "share_of_step": shares[dom], "kernel_time_shares": shares}
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (bytes per launch; null when absent)
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tr = json.load(f).get(roofline["kernel"].split(" ")[0])
+        if tr:
+            roofline["traffic"] = tr["dram_bytes_per_launch"]
+            roofline["traffic_note"] = tr["note"]
+    except (OSError, ValueError, KeyError):
+        pass
     path_tflops = flops_step / (total_ms / args.steps * 1e-3) / 1e12
     roofline["whole_path"] = {"algorithmic_tflops": path_tflops, "frac_of_sustained_peak": path_tflops / peaks["bf16_tflops_sustained"]}
 
