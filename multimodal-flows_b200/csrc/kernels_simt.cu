@@ -1,6 +1,7 @@
 // CUDA-core kernels of the hot path: the fused hybrid step, packing, the K=3 input embedding, row
 // LayerNorms that sit between streams, and the tiny output projections fused with the step.
 // All are memory-bound: one coalesced, vectorised pass over the data.
+#include <cstdlib>
 #include "mmf_internal.h"
 #include "mmf_simt.h"
 
@@ -47,7 +48,9 @@ __device__ __forceinline__ void block_store(float* g, const float* s, int count,
     }
 }
 
-template <int V>
+// FAST: production mode (in-kernel Philox draws, no rates returned) - MUFU exp / division and the two-uniform form of the
+// jump law (StepMath / step_particle_2u in step_math.cuh); the parity modes keep the reproducible per-channel arithmetic
+template <int V, bool FAST>
 __global__ void __launch_bounds__(kStepThreads)
 hybrid_step_kernel(const float* __restrict__ vt, const float* __restrict__ logits, float* __restrict__ x,
                    long long* __restrict__ k, const float* __restrict__ t, long long n_particles, int D,
@@ -72,17 +75,25 @@ hybrid_step_kernel(const float* __restrict__ vt, const float* __restrict__ logit
         float lg[V], u[V], rates[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) lg[v] = s_lg[tid * V + v];
-        if (sl.u) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) u[v] = s_u[tid * V + v];
-        } else {
-            philox_uniforms(sl.seed, sl.slot0 + static_cast<uint64_t>(i), sl.step, V, u);
-        }
         long long kc = k[i];
         if (kc < 0 || kc >= V) { atomicOr(sl.err_flag, 2); kc = 0; }
         float w, coef;
         det_thermostat(__ldg(t + i / D), sl.sp.beta, V, &w, &coef);
-        const int kn = step_particle<V>(lg, static_cast<int>(kc), w, coef, sl.sp, u, rates_out ? rates : nullptr);
+        int kn;
+        if (FAST) {                                   // production mode: one Philox block, two uniforms (step_particle_2u)
+            const uint64_t slot = sl.slot0 + static_cast<uint64_t>(i);
+            const Philox4 r = philox4x32_10(Philox4{static_cast<uint32_t>(slot), static_cast<uint32_t>(slot >> 32), sl.step, 0x32u},
+                                            static_cast<uint32_t>(sl.seed), static_cast<uint32_t>(sl.seed >> 32));
+            kn = step_particle_2u<V>(lg, static_cast<int>(kc), w, coef, sl.sp, u01_from_bits(r.x), u01_from_bits(r.y));
+        } else {
+            if (sl.u) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) u[v] = s_u[tid * V + v];
+            } else {
+                philox_uniforms(sl.seed, sl.slot0 + static_cast<uint64_t>(i), sl.step, V, u);
+            }
+            kn = step_particle<V, false>(lg, static_cast<int>(kc), w, coef, sl.sp, u, rates_out ? rates : nullptr);
+        }
         k[i] = kn;
 #pragma unroll
         for (int c = 0; c < 3; ++c) s_x[tid * 3 + c] = euler_update(s_x[tid * 3 + c], s_v[tid * 3 + c], sl.sp.dt);
@@ -388,7 +399,14 @@ int launch_hybrid_step(const float* vt, const float* logits, float* x, long long
     const long long n = static_cast<long long>(B) * D;
     if (n == 0) return 0;
     const unsigned blocks = static_cast<unsigned>((n + kStepThreads - 1) / kStepThreads);
-    MMF_DISPATCH_V(sl.sp.vocab, (hybrid_step_kernel<VV><<<blocks, kStepThreads, 0, stream>>>(vt, logits, x, k, t, n, D, sl, rates_out)));
+    // production mode (Philox draws, no rates) runs the MUFU arithmetic; MMF_STEP_EXACT=1 forces the reproducible one
+    const char* fe = getenv("MMF_STEP_EXACT");
+    const bool force_exact = fe != nullptr && atoi(fe) != 0;
+    if (sl.u == nullptr && rates_out == nullptr && !force_exact) {
+        MMF_DISPATCH_V(sl.sp.vocab, (hybrid_step_kernel<VV, true><<<blocks, kStepThreads, 0, stream>>>(vt, logits, x, k, t, n, D, sl, rates_out)));
+    } else {
+        MMF_DISPATCH_V(sl.sp.vocab, (hybrid_step_kernel<VV, false><<<blocks, kStepThreads, 0, stream>>>(vt, logits, x, k, t, n, D, sl, rates_out)));
+    }
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }

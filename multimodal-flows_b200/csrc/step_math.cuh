@@ -16,22 +16,46 @@ struct StepParams {
     int vocab;
 };
 
-template <int V>
+// Arithmetic policy.  EXACT (default): individually rounded IEEE ops and the polynomial det_expf, reproduced bit for bit by
+// oracle/step_oracle.c - used whenever uniforms are supplied, rates are returned or tokens are forced (the parity modes).
+// FAST: MUFU ex2 / rcp (relative error ~2^-22) for the production mode with in-kernel Philox draws, where no draw-level
+// comparison exists and the step has to stay memory-bound; a decision differs from EXACT only when a uniform falls within
+// ~1e-6 of a threshold (tests/test_gpu_step.py::test_fast_step_arithmetic_agrees_with_exact).
+template <bool FAST> struct StepMath;
+template <> struct StepMath<false> {
+    static __device__ __forceinline__ float exp(float x) { return det_expf(x); }
+    static __device__ __forceinline__ float div(float a, float b) { return det_div(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return det_mul(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return det_add(a, b); }
+};
+template <> struct StepMath<true> {
+    static __device__ __forceinline__ float exp(float x) {
+        float y;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.44269504f));
+        return y;
+    }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+};
+
+template <int V, bool FAST = false>
 __device__ __forceinline__ void step_softmax(const float* l, float T, float* p) {
+    using M = StepMath<FAST>;
     float z[V];
 #pragma unroll
-    for (int v = 0; v < V; ++v) z[v] = (T != 1.0f) ? det_div(l[v], T) : l[v];
+    for (int v = 0; v < V; ++v) z[v] = (T != 1.0f) ? M::div(l[v], T) : l[v];
     float m = z[0];
 #pragma unroll
     for (int v = 1; v < V; ++v) m = z[v] > m ? z[v] : m;
     float s = 0.0f;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        p[v] = det_expf(det_add(z[v], -m));
-        s = (v == 0) ? p[0] : det_add(s, p[v]);
+        p[v] = M::exp(M::add(z[v], -m));
+        s = (v == 0) ? p[0] : M::add(s, p[v]);
     }
 #pragma unroll
-    for (int v = 0; v < V; ++v) p[v] = det_div(p[v], s);
+    for (int v = 0; v < V; ++v) p[v] = M::div(p[v], s);
 }
 
 template <int V>
@@ -45,28 +69,30 @@ __device__ __forceinline__ void step_ranks(const float* p, int* rank) {
     }
 }
 
-template <int V>
+template <int V, bool FAST = false>
 __device__ __forceinline__ void step_renorm(float* p, const bool* keep) {
+    using M = StepMath<FAST>;
     float s = 0.0f;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         p[v] = keep[v] ? p[v] : 0.0f;
-        s = (v == 0) ? p[0] : det_add(s, p[v]);
+        s = (v == 0) ? p[0] : M::add(s, p[v]);
     }
-    const float d = det_add(s, 1e-8f);
+    const float d = M::add(s, 1e-8f);
 #pragma unroll
-    for (int v = 0; v < V; ++v) p[v] = det_div(p[v], d);
+    for (int v = 0; v < V; ++v) p[v] = M::div(p[v], d);
 }
 
-template <int V>
+template <int V, bool FAST = false>
 __device__ __forceinline__ void step_filters(float* p, int top_k, float top_p) {
+    using M = StepMath<FAST>;
     if (top_k > 0 && top_k != V) {
         int rank[V];
         bool keep[V];
         step_ranks<V>(p, rank);
 #pragma unroll
         for (int v = 0; v < V; ++v) keep[v] = rank[v] < top_k;
-        step_renorm<V>(p, keep);
+        step_renorm<V, FAST>(p, keep);
     }
     if (top_p > 0.0f) {
         int rank[V];
@@ -79,7 +105,7 @@ __device__ __forceinline__ void step_filters(float* p, int top_k, float top_p) {
             float pj = 0.0f;
 #pragma unroll
             for (int v = 0; v < V; ++v) pj = (rank[v] == j) ? p[v] : pj;
-            cum = (j == 0) ? pj : det_add(cum, pj);
+            cum = (j == 0) ? pj : M::add(cum, pj);
             keep_sorted[j] = (j == 0) || (cum <= top_p);
         }
 #pragma unroll
@@ -89,33 +115,63 @@ __device__ __forceinline__ void step_filters(float* p, int top_k, float top_p) {
             for (int j = 0; j < V; ++j) kv = (rank[v] == j) ? keep_sorted[j] : kv;
             keep[v] = kv;
         }
-        step_renorm<V>(p, keep);
+        step_renorm<V, FAST>(p, keep);
     }
 }
 
 // returns the new token; `rates` (V floats) is written when non-null.  `k` must be in [0,V).
-template <int V>
+template <int V, bool FAST = false>
 __device__ __forceinline__ int step_particle(const float* logits, int k, float w, float coef, const StepParams& sp,
                                              const float* u, float* rates) {
+    using M = StepMath<FAST>;
     float p[V];
-    step_softmax<V>(logits, sp.temperature, p);
-    step_filters<V>(p, sp.top_k, sp.top_p);
+    step_softmax<V, FAST>(logits, sp.temperature, p);
+    step_filters<V, FAST>(p, sp.top_k, sp.top_p);
     float qk = p[0];
 #pragma unroll
     for (int v = 1; v < V; ++v) qk = (k == v) ? p[v] : qk;
-    const float wq = det_mul(w, qk);
+    const float wq = M::mul(w, qk);
     int total = 0, single = k;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        const float rate = det_add(det_add(1.0f, det_mul(coef, p[v])), wq);
+        const float rate = M::add(M::add(1.0f, M::mul(coef, p[v])), wq);
         if (rates) rates[v] = rate;
-        const float lam = det_mul(rate, sp.dt);
-        const float e = det_expf(-lam);
-        const int c = (u[v] >= e) + (u[v] >= det_mul(e, det_add(1.0f, lam)));
+        const float lam = M::mul(rate, sp.dt);
+        const float e = M::exp(-lam);
+        const int c = (u[v] >= e) + (u[v] >= M::mul(e, M::add(1.0f, lam)));
         total += c;
         single = (c == 1) ? v : single;
     }
     return (total == 1) ? single : k;
+}
+
+// The same transition law from TWO uniforms: the V channel counts are independent Poisson(lam_v), so their
+// total is Poisson(L), L = sum lam_v; the token changes iff the total is exactly one - probability L e^-L - and then to
+// channel j with probability lam_j / L.  Distributionally identical to the per-channel form, not draw-identical: used only
+// by the production mode of the standalone step kernel (in-kernel draws), where it cuts the RNG work by three.
+template <int V>
+__device__ __forceinline__ int step_particle_2u(const float* logits, int k, float w, float coef, const StepParams& sp, float u1, float u2) {
+    using M = StepMath<true>;
+    float p[V];
+    step_softmax<V, true>(logits, sp.temperature, p);
+    step_filters<V, true>(p, sp.top_k, sp.top_p);
+    float qk = p[0];
+#pragma unroll
+    for (int v = 1; v < V; ++v) qk = (k == v) ? p[v] : qk;
+    const float base = fmaf(w, qk, 1.0f);
+    float cum[V];
+    float L = 0.0f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        L += fmaf(coef, p[v], base) * sp.dt;
+        cum[v] = L;
+    }
+    if (!(u1 < L * M::exp(-L))) return k;            // zero or >= 2 events: the token stays (reference model/solvers.py:49-54)
+    const float target = u2 * L;
+    int j = V - 1;
+#pragma unroll
+    for (int v = V - 2; v >= 0; --v) j = (target < cum[v]) ? v : j;
+    return j;
 }
 
 __device__ __forceinline__ float euler_update(float x, float vt, float dt) { return det_add(x, det_mul(vt, dt)); }

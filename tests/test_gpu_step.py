@@ -91,6 +91,40 @@ def test_step_philox_statistics_and_invariance():
     assert (ha - hc).abs().max().item() < 0.01
 
 
+def test_production_step_matches_reproducible_step_in_distribution(monkeypatch):
+    """Production mode (Philox draws, no rates) uses MUFU arithmetic and the two-uniform form of the jump law (total count
+    Poisson(L): change iff exactly one event, target ~ lam_j / L).  It must agree in distribution with the
+    reproducible per-channel arithmetic (MMF_STEP_EXACT=1): jump fraction, destination histogram and the joint (from, to)
+    table, also with temperature and top-k / top-p filters; the Euler part is identical."""
+    from mmf_b200 import _abi
+    dev = torch.device("cuda:0")
+    B, D, V = 4096, 150, 9
+    g = torch.Generator().manual_seed(21)
+    vt = torch.randn(B, D, 3, generator=g).to(dev)
+    logits = (torch.randn(1, 1, V, generator=g) * 1.5 + torch.randn(B, D, V, generator=g) * 0.5).to(dev)
+    x0 = torch.randn(B, D, 3, generator=g).to(dev)
+    k0 = torch.randint(0, V, (B, D), generator=g).to(dev)
+    for tval, opts in ((0.3, _abi.MmfStepOptions(1.0, 0.075, 0, 0.0, 0, 77, 0)), (0.9, _abi.MmfStepOptions(0.8, 0.075, 5, 0.9, 0, 78, 0))):
+        t = torch.full((B,), tval).to(dev)
+        out = {}
+        for exact in ("1", "0"):
+            monkeypatch.setenv("MMF_STEP_EXACT", exact)
+            k = k0.clone(); x = x0.clone()
+            _abi.hybrid_step(vt, logits, x, k, t, 0.0101, opts, u=None, step_index=5, want_rates=False)
+            torch.cuda.synchronize()
+            out[exact] = (k, x)
+        ke, kf = out["1"][0], out["0"][0]
+        n = float(k0.numel())
+        fe, ff = (ke != k0).float().mean().item(), (kf != k0).float().mean().item()
+        assert fe > 0.01 and abs(fe - ff) < 4 * (fe / n) ** 0.5 + 1e-4, (fe, ff)
+        je = torch.bincount((k0 * V + ke).flatten(), minlength=V * V).float() / n
+        jf = torch.bincount((k0 * V + kf).flatten(), minlength=V * V).float() / n
+        # two independent samples of n particles: sd of a difference of frequencies p is sqrt(2 p / n); 6 sd over 81 cells
+        tol = 6 * (2 * torch.maximum(je, jf).clamp_min(1.0 / n) / n).sqrt() + 3e-5
+        assert ((je - jf).abs() < tol).all(), ((je - jf).abs() / tol).max().item()
+        assert torch.equal(out["1"][1], out["0"][1])
+
+
 def test_step_rejects_out_of_range_tokens_only_in_flag():
     """Tokens outside [0,V) are clamped and flagged (the reference asserts, MJB.py:177-182); no crash."""
     from mmf_b200 import _abi
