@@ -77,8 +77,16 @@ hybrid_step_kernel(const float* __restrict__ vt, const float* __restrict__ logit
         for (int v = 0; v < V; ++v) lg[v] = s_lg[tid * V + v];
         long long kc = k[i];
         if (kc < 0 || kc >= V) { atomicOr(sl.err_flag, 2); kc = 0; }
+        // jet of this particle: 32-bit division whenever the slot index fits (a 64-bit one costs ~100 instructions)
+        const long long jet = n_particles < 0x7fffffffLL ? static_cast<long long>(static_cast<unsigned>(i) / static_cast<unsigned>(D)) : i / D;
         float w, coef;
-        det_thermostat(__ldg(t + i / D), sl.sp.beta, V, &w, &coef);
+        if (FAST) {
+            const float a = static_cast<float>(-static_cast<double>(V) * static_cast<double>(sl.sp.beta));
+            w = StepMath<true>::exp(a * (1.0f - __ldg(t + jet)));
+            coef = __fdividef(w * static_cast<float>(V), 1.0f - w);
+        } else {
+            det_thermostat(__ldg(t + jet), sl.sp.beta, V, &w, &coef);
+        }
         int kn;
         if (FAST) {                                   // production mode: one Philox block, two uniforms (step_particle_2u)
             const uint64_t slot = sl.slot0 + static_cast<uint64_t>(i);
