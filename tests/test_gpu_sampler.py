@@ -58,6 +58,48 @@ def test_tile_kernel_agrees_with_layered_path(name, monkeypatch):
     assert _rel(va, vb, real) < 1e-2 and _rel(la, lb, real) < 1e-2
 
 
+@pytest.mark.parametrize("name", ["FusedParticleFormer", "ParticleFormer"])
+def test_ragged_edge_cases_vs_oracle(name):
+    """Multiplicity edge cases against the fp32 CPU oracle (forward API, per-jet times): tiles packed with dozens of 1..3
+    particle jets (every 16-key softmax group cut by jet boundaries), jets of exactly 128 particles (one full tile), 127 + 1,
+    empty jets (nothing to generate, outputs stay zero), and 129..150-particle jets (layered path) in the same batch; then a
+    short teacher-forced sampler run over the same batch.  Tolerances: SURVEY 8(c) level L1 (rel-L2 2e-2, max-abs 3e-2 max|ref|)."""
+    from mmf_b200 import _abi, synthetic
+    from oracle import mmf_oracle as orc
+    cfg, sd, nm = _model(name, num_timesteps=4)
+    g = torch.Generator().manual_seed(77)
+    n = torch.cat([torch.randint(1, 4, (70,), generator=g), torch.tensor([128, 128, 127, 1, 0, 0, 64, 64, 129, 150, 140, 2, 126]),
+                   torch.randint(30, 100, (10,), generator=g)])
+    n = n[torch.randperm(len(n), generator=g)]
+    B = len(n)
+    mask = synthetic.prefix_masks(n, 150)
+    x0 = torch.randn(B, 150, 3, generator=g) * mask
+    k0 = torch.randint(1, 9, (B, 150, 1), generator=g) * mask
+    t = torch.rand(B, generator=g)
+    real = mask.bool().squeeze(-1)
+    va, la = nm.forward(x0.to(DEV), k0.to(DEV), mask.to(DEV), t.to(DEV))
+    vr, lr = orc.encoder_forward(sd, cfg, t, x0, k0, mask)
+    for got, ref in ((va.cpu(), vr), (la.cpu(), lr)):
+        d = (got[real] - ref[real]).float()
+        assert float(d.norm() / ref[real].norm()) < 2e-2
+        assert float(d.abs().max()) < 3e-2 * float(ref[real].abs().max())
+        assert torch.isfinite(got).all()
+    # per-jet check as well: a tiny jet must not be polluted by its tile neighbours
+    for b in range(B):
+        if 0 < int(n[b]) <= 3:
+            d = (va.cpu()[b, :int(n[b])] - vr[b, :int(n[b])]).abs().max()
+            assert float(d) < 5e-2 * float(vr[real].abs().max()), (b, int(n[b]), float(d))
+    # free-running sampler over the same batch with the same supplied uniforms (4 timesteps: jumps rarely diverge)
+    u = synthetic.uniform_draws(cfg.num_timesteps, B, seed=5)
+    xo, ko, _ = orc.simulate_dynamics(sd, cfg, x0, k0, mask, u=u)
+    ts, dt = orc.time_grid(cfg)
+    xg, kg, _ = nm.generate(x0.to(DEV), k0.to(DEV), mask.to(DEV), ts, float(dt), _abi.step_options(cfg), u=u.to(DEV))
+    torch.cuda.synchronize()
+    assert torch.isfinite(xg).all() and (xg.cpu()[~real] == 0).all() and (kg.cpu()[~real] == 0).all()
+    assert _rel(xg.cpu(), xo, real) < 2e-2
+    assert (kg.cpu()[real].flatten() == ko[real].flatten()).float().mean() > 0.97
+
+
 def test_philox_draws_are_keyed_on_the_global_jet_index():
     """Generating a batch in one call or as two shards (first_global_jet offsets) gives the same sample.
 
