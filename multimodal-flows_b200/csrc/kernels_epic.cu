@@ -235,49 +235,65 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
         // skip stream (bf16), layout per tile [col / 8][row][8]: a warp reads / writes 512 contiguous bytes per instruction
         uint4* skip8 = reinterpret_cast<uint4*>(a.loc_skip) + static_cast<size_t>(tile) * 32 * 128 + r;   // + (col / 8) * 128
 
-        // masked sum pooling of the bf16 local features in Abuf.  A warp covers 32 columns (4 lanes x 8 columns, one 16-byte
-        // unit per load) x 8 row slices; the slices are reduced with shuffles, so the order is fixed and the result deterministic.
+        int mark_i = 0;
+        auto mark = [&](int step) {
+            if (a.trace && blockIdx.x == 0 && tid == 0 && step < 2 && mark_i < 64) a.trace[step * 64 + mark_i] = clock64();
+            ++mark_i;
+        };
+        // masked sum pooling of the bf16 local features in Abuf, one pass over the rows whatever the number of jets: warp =
+        // (64-column chunk, row half), lane = a column pair; a thread walks its 64 rows in order and flushes its partial sums
+        // at every jet boundary (rows of a jet are contiguous, the boundary test is warp-uniform) into s_acc[half][jet][col]
+        // (the hidden-layer buffers, free at this point); a second pass, thread = column, adds the two halves.  Fixed order,
+        // so the result is deterministic.
+        // The fc_loc1 GEMM of the layer is released (a_ready) only AFTER the rows have been read: an N = 128 tcgen05.mma with both
+        // operands in shared memory takes the whole 128 B/clk of the shared-memory pipe, and pooling under it ran 5x slower.
+        // The GEMM is not needed before the global path (~12 k cycles) is through, so nothing is lost by starting it here.
         auto pool = [&](bool with_glob) {
-            const int g = lane >> 2, cu = warp * 4 + (lane & 3);              // row slice, 8-column unit (0..31)
-            const uint8_t* ch = Abuf + (cu >> 3) * kTile;
-            const uint32_t u = cu & 7;
-            for (int j = 0; j < njets; ++j) {
-                const int r1 = s_meta->jet_begin[j + 1];
-                float acc[8];
+            const int chunk = warp & 3, half = warp >> 2;
+            const uint8_t* ch = Abuf + chunk * kTile + (lane & 3) * 4;
+            const uint32_t u = lane >> 2;
+            float* s_acc = s_hid;                                            // [2][kEpicMaxJets][256] floats = s_hid | s_jb
+            const int r0 = half * 64, r1 = nrows < r0 + 64 ? nrows : r0 + 64;
+            float* mine = s_acc + half * kEpicMaxJets * 256 + chunk * 64 + 2 * lane;
+            for (int j = 0; j < njets; ++j)                                  // jets without a row in this half contribute zero
+                if (s_meta->jet_begin[j + 1] <= r0 || s_meta->jet_begin[j] >= r1) { mine[j * 256] = 0.f; mine[j * 256 + 1] = 0.f; }
+            if (r0 < r1) {
+                int j = s_rowjet[r0], rr = r0;
+                float a0 = 0.f, a1 = 0.f;
+                while (true) {
+                    const int jend = s_meta->jet_begin[j + 1], lim = jend < r1 ? jend : r1;       // rows [rr, lim) belong to jet j
+                    for (; rr + 8 <= lim; rr += 8) {                     // eight loads in flight, tree sums
+                        uint32_t w[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-                for (int rr = s_meta->jet_begin[j] + g; rr < r1; rr += 8) {
-                    const uint4 w = *reinterpret_cast<const uint4*>(ch + sw128_offset(rr, u));
-                    acc[0] += bf16_lo(w.x); acc[1] += bf16_hi(w.x); acc[2] += bf16_lo(w.y); acc[3] += bf16_hi(w.y);
-                    acc[4] += bf16_lo(w.z); acc[5] += bf16_hi(w.z); acc[6] += bf16_lo(w.w); acc[7] += bf16_hi(w.w);
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    float v = acc[e];
-                    v += __shfl_xor_sync(0xffffffffu, v, 4);
-                    v += __shfl_xor_sync(0xffffffffu, v, 8);
-                    v += __shfl_xor_sync(0xffffffffu, v, 16);
-                    acc[e] = v;
-                }
-                if (s_meta->pair) {                              // the other half of the jet lives in the peer CTA
-                    if (g == 0) {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) dsmem_st_f32(dsmem_addr(s_xchg + px * 256 + cu * 8 + e, peer), acc[e]);
+                        for (int i = 0; i < 8; ++i) w[i] = *reinterpret_cast<const uint32_t*>(ch + sw128_offset(rr + i, u));
+                        a0 += ((bf16_lo(w[0]) + bf16_lo(w[1])) + (bf16_lo(w[2]) + bf16_lo(w[3]))) + ((bf16_lo(w[4]) + bf16_lo(w[5])) + (bf16_lo(w[6]) + bf16_lo(w[7])));
+                        a1 += ((bf16_hi(w[0]) + bf16_hi(w[1])) + (bf16_hi(w[2]) + bf16_hi(w[3]))) + ((bf16_hi(w[4]) + bf16_hi(w[5])) + (bf16_hi(w[6]) + bf16_hi(w[7])));
                     }
+                    for (; rr < lim; ++rr) {
+                        const uint32_t w = *reinterpret_cast<const uint32_t*>(ch + sw128_offset(rr, u));
+                        a0 += bf16_lo(w);
+                        a1 += bf16_hi(w);
+                    }
+                    mine[j * 256] = a0; mine[j * 256 + 1] = a1;
+                    if (rr >= r1) break;
+                    a0 = 0.f; a1 = 0.f;
+                    ++j;
+                }
+            }
+            mbar_arrive(&bars->a_ready);                         // fc_loc1 of this layer may start (operand fenced by its writers)
+            epi_bar();
+            const int col = tid;
+            for (int j = 0; j < njets; ++j) {
+                float s = s_acc[j * 256 + col] + s_acc[(kEpicMaxJets + j) * 256 + col];
+                if (s_meta->pair) {                              // the other half of the jet lives in the peer CTA
+                    dsmem_st_f32(dsmem_addr(s_xchg + px * 256 + col, peer), s);
                     mbar_arrive_remote(dsmem_addr(&bars->xchg, peer));
                     mbar_wait_cluster(&bars->xchg, px);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[e] += s_xchg[px * 256 + cu * 8 + e];
+                    s += s_xchg[px * 256 + col];
                     px ^= 1;
                 }
-                if (g == 0) {
-                    const float ntot = static_cast<float>(s_meta->jet_ntot[j]);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        s_pool[j * kPoolLd + cu * 8 + e] = acc[e] / ntot;
-                        s_pool[j * kPoolLd + 256 + cu * 8 + e] = acc[e] * 0.01f;
-                    }
-                }
+                s_pool[j * kPoolLd + col] = s / static_cast<float>(s_meta->jet_ntot[j]);
+                s_pool[j * kPoolLd + 256 + col] = s * 0.01f;
             }
             if (with_glob && tid < njets * 16) s_pool[(tid >> 4) * kPoolLd + 512 + (tid & 15)] = s_glob[tid];
             epi_bar();
@@ -294,11 +310,6 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
             }
         };
 
-        int mark_i = 0;
-        auto mark = [&](int step) {
-            if (a.trace && blockIdx.x == 0 && tid == 0 && step < 2 && mark_i < 64) a.trace[step * 64 + mark_i] = clock64();
-            ++mark_i;
-        };
         for (int step = 0; step < a.nsteps; ++step) {
             mark_i = 0;
             mark(step);                                       // 0: step start
@@ -363,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
             tmem_st_wait();
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(&bars->a_ready);                     // layer 0's fc_loc1 may start: it only needs loc
+            // (layer 0's fc_loc1, which only needs loc, is released inside pool() below)
             epi_bar();
             mark(step);                                       // 3: proj epilogue done
             // ---- proj.mlp_global: pooled(512) ++ temb -> 256 (GELU) -> 16 (GELU)
@@ -496,7 +507,7 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
                     tmem_st_wait();
                     fence_proxy_async();
                     tc_fence_before();
-                    mbar_arrive(&bars->a_ready);             // next layer's fc_loc1
+                    // (the next layer's fc_loc1 is released inside its pool())
                 }
                 epi_bar();
             }
