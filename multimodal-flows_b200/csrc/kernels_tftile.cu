@@ -2,8 +2,10 @@
 //
 // warps 0..7   epilogue / SIMT: thread = (row r, column half hf); runs the hand-written per-timestep program
 // warp  8      parameter producer: streams the per-stage parameter blobs into the double buffer
-// warp  9      tcgen05.mma issuer - walks the op table (one elected lane issues)
-// warps 10,11  weight producers: stream the weight tiles into the ring with 1-D bulk copies, alternating tiles
+// warp  9      tcgen05.mma issuer of the weight GEMMs (every op that reads the ring) - walks the op table, one elected lane issues
+// warp  10     weight producer: streams the weight tiles into the ring with 1-D bulk copies
+// warp  11     tcgen05.mma issuer of the attention products S = Q K^T and O = P V (both operands in the arena): they are
+//              short and latency-critical, and no longer queue behind the streaming GEMM of the next unit
 //
 // Synchronisation: `go` (256 arrivals) epilogue -> MMA issuer, consumed in order by the ops flagged `wait`;
 // `done[0/1]` (tcgen05.commit) MMA -> epilogue; full/empty ring barriers producer <-> MMA issuer;
@@ -24,7 +26,7 @@ namespace {
 
 constexpr int kEpi = 256;
 constexpr int kThreads = 384;
-constexpr int kProducers = 2;              // warps 10, 11: weight tiles are dealt round robin
+constexpr int kProducers = 1;              // warp 10 (one warp keeps up: the ring is latency-bound, ~500 cycles per copy suffice)
 constexpr int kTile = 16384;                // operand chunk: [128 rows][64] bf16
 constexpr int kBars = kTfRingBars;          // weight-ring barrier pairs, used round robin by tile index
 #ifndef MMF_COPY_SPLIT
@@ -40,8 +42,12 @@ constexpr uint32_t oH0 = oQ, oH1 = oVT;          // MLP hidden quarters [128 x 1
 constexpr uint32_t oRing = oO + kTile;           // weight ring
 constexpr int kArena = oRing + kTfRingBytes;
 
+// Hand-offs epilogue -> weight-GEMM issuer rotate over kGoBars barriers: a waiter tells phases apart by parity only, and
+// with two issuer warps the GEMM issuer can be a hand-off behind (an unsignalled projection waiting for its weight tile
+// while the attention issuer keeps the epilogue going), so one barrier could complete two phases unobserved.
+constexpr int kGoBars = 4;
 struct TfBars {
-    uint64_t full[kBars], empty[kBars], done[2], go, pfull[2], pempty[2];
+    uint64_t full[kBars], empty[kBars], done[3], go[kGoBars], go_attn, pfull[2], pempty[2];
     uint32_t tmem_base;
 };
 
@@ -64,7 +70,8 @@ struct Epi {
     const float* P;          // current parameter blob
     uint32_t taddr;          // TMEM base + this warp's lane quarter
     int r, hf, tid;
-    uint32_t pd0, pd1, pc;
+    uint32_t pd0, pd1, pd2, pc;
+    uint32_t gc;             // hand-offs to the weight-GEMM issuer so far (barrier gc % kGoBars, parity (gc / kGoBars) & 1)
     uint32_t kmask, kfull, kpart;   // 16-key groups of this thread's key half: attended by any row of the warp / in full by
                                     // every row / cut by a jet boundary of some row
     unsigned long long* trace;   // clock stamps of CTA 0 / thread 0 for the first two timesteps (debugging aid) or null
@@ -85,15 +92,25 @@ __device__ __forceinline__ void mark(Epi& e) {
 __device__ __forceinline__ void epi_bar() { named_bar_sync(1, kEpi); }
 __device__ __forceinline__ void wait_done(Epi& e, int b) {
     if (b == 0) { mbar_wait(&e.bars->done[0], e.pd0, e.mark_i); e.pd0 ^= 1; }     // (tag for the time-out diagnostics)
-    else { mbar_wait(&e.bars->done[1], e.pd1, e.mark_i); e.pd1 ^= 1; }
+    else if (b == 1) { mbar_wait(&e.bars->done[1], e.pd1, e.mark_i); e.pd1 ^= 1; }
+    else { mbar_wait(&e.bars->done[2], e.pd2, e.mark_i); e.pd2 ^= 1; }
     tc_fence_after();
     mark(e);
 }
+// hand-offs epilogue -> issuers: `go` releases the next waiting op of the weight-GEMM issuer, `go_attn` of the attention issuer
 __device__ __forceinline__ void go(Epi& e) {
     mark(e);
     fence_proxy_async();
     tc_fence_before();
-    mbar_arrive(&e.bars->go);
+    mbar_arrive(&e.bars->go[e.gc % kGoBars]);
+    ++e.gc;
+}
+__device__ __forceinline__ void go_attn(Epi& e, bool also_gemm = false) {
+    mark(e);
+    fence_proxy_async();
+    tc_fence_before();
+    mbar_arrive(&e.bars->go_attn);
+    if (also_gemm) { mbar_arrive(&e.bars->go[e.gc % kGoBars]); ++e.gc; }
 }
 // blob `ahead` stages past the oldest one still held (0 or 1: two slots)
 __device__ __forceinline__ const float* param_acquire(Epi& e, uint32_t ahead = 0) {
@@ -452,29 +469,31 @@ __device__ __forceinline__ void head_epilogue(Epi& e, int q, const float* bias, 
 
 // one attention unit (64 q-columns = 64/HS heads) of the current block, epilogue side
 template <int HS>
-__device__ __forceinline__ void attention_unit(Epi& e, const float* bq, const float* bk, const float* bv, const float* qg,
+__device__ __forceinline__ void attention_unit(Epi& e, bool first, bool more, const float* bq, const float* bk, const float* bv, const float* qg,
                                                const float* qb, const float* kg, const float* kb, int seg_b, int seg_e) {
     const float scale = 1.4426950408889634f * rsqrtf(static_cast<float>(HS));
     wait_done(e, 1);                                  // QKV of this unit (issued under the previous unit's epilogue)
     qk_epilogue<HS>(e, bq, bk, qg, qb, kg, kb);
-    go(e);
-    v_epilogue<HS>(e, bv);                            // under the score MMA; P V is only issued after the next go
+    go_attn(e);                                       // -> S
+    v_epilogue<HS>(e, bv);                            // under the score MMA; P V is only issued after the next hand-off
     if (HS == 64) {
         wait_done(e, 0);
         softmax_epilogue(e, kScr, scale, seg_b, seg_e, 0);
-        go(e);
+        go_attn(e, more);                             // -> P V, and (S is consumed) the QKV GEMM of the next unit
         wait_done(e, 0);
+        if (!first) wait_done(e, 2);                      // the previous unit's projection (other issuer warp) has read oO
         o_epilogue<64>(e, kScr + 192, 0, 0);
-        go(e);
+        go(e);                                        // -> projection
     } else {
         wait_done(e, 0);                              // both heads' scores: [256,384) and [384,512)
         softmax_epilogue(e, kScr, scale, seg_b, seg_e, 0);
-        go(e);                                        // -> P V of head 0
+        go_attn(e);                                   // -> P V of head 0
         float s[64];                                  // head 1's probabilities are computed under that product ...
         const float sum = softmax_probs(e, kScr + 128, scale, seg_b, seg_e, 1, s);
         wait_done(e, 1);                              // ... and stored once it has finished reading head 0's
         softmax_store(e, 1, s, sum);
-        go(e);                                        // -> P V of head 1
+        go_attn(e, more);                             // -> P V of head 1, and the QKV GEMM of the next unit
+        if (!first) wait_done(e, 2);                      // the previous unit's projection (other issuer warp) has read oO
         o_epilogue<32>(e, kScr, 0, 0);                // O of head 0 in scratch [0,32), under P V of head 1
         wait_done(e, 0);                              // O of head 1 in scratch [32,64)
         o_epilogue<32>(e, kScr + 32, 32, 1);
@@ -506,7 +525,9 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
         for (int i = 0; i < kBars; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], cs); }
         mbar_init(&bars->done[0], 1);
         mbar_init(&bars->done[1], 1);
-        mbar_init(&bars->go, kEpi);
+        mbar_init(&bars->done[2], 1);
+        for (int i = 0; i < kGoBars; ++i) mbar_init(&bars->go[i], kEpi);
+        mbar_init(&bars->go_attn, kEpi);
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->pfull[i], 1); mbar_init(&bars->pempty[i], kEpi); }
         fence_mbar_init();
     }
@@ -538,7 +559,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 ++pcount;
             }
         }
-    } else if (warp >= 10) {
+    } else if (warp == 10) {
         // ---------------------------------------------------- weight producers --------------------------------------
         // Tile g of the launch may be written once every tile up to g - dep has been consumed (host plan); `known` counts
         // the tiles this warp has seen consumed, waiting on their barriers strictly in order.
@@ -571,11 +592,13 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 __syncwarp();
             }
         }
-    } else if (warp == 9) {
-        // ---------------------------------------------------- MMA issuer --------------------------------------------
+    } else if (warp == 9 || warp == 11) {
+        // ---------------------------------------------------- MMA issuers -------------------------------------------
+        // Both warps walk the whole table; warp 11 issues the ops flagged kTfOpAttn, warp 9 all the others.
+        const bool attn_issuer = warp == 11;
         // All 32 lanes run the loop converged (op fields stay in uniform registers, the table sits in the constant bank);
         // one elected lane issues the asynchronous instructions.  Descriptors come precomputed from the host.
-        uint32_t pg = 0, gbase = 0;
+        uint32_t pg = 0, gbase = 0;                           // hand-offs consumed so far
         const uint32_t base16 = smem_u32(arena) >> 4;
         const uint32_t ring16 = base16 + (oRing >> 4) + (1u << 16);
         constexpr uint64_t kDescHi = static_cast<uint64_t>(0x40004040u) << 32;   // SBO 1024 B | version 1 | SWIZZLE_128B
@@ -586,9 +609,11 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 const TfOp op = nx;
                 if (i + 1 < a.n_ops) nx = optab.ops[i + 1];   // fetched one op ahead
                 const uint32_t fl = op.flags;
+                if (((fl & kTfOpAttn) != 0) != attn_issuer) continue;       // the other issuer's op (attention ops never touch the ring)
                 if (fl & kTfOpWait) {
-                    mbar_wait(&bars->go, pg, static_cast<uint32_t>(i));
-                    pg ^= 1;
+                    if (attn_issuer) mbar_wait(&bars->go_attn, pg & 1, static_cast<uint32_t>(i));
+                    else mbar_wait(&bars->go[pg % kGoBars], (pg / kGoBars) & 1, static_cast<uint32_t>(i));
+                    ++pg;
                 }
                 const bool ring = (fl & kTfOpRing) != 0;
                 uint32_t a_lo = op.a_lo + base16, b_lo = op.b_lo + base16, acc = fl & kTfOpAcc;
@@ -622,7 +647,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 }
                 if (fl & 0x30u) {
                     if (elect_one()) {
-                        umma_commit(&bars->done[(fl >> 5) & 1u]);
+                        umma_commit(&bars->done[((fl >> 4) & 3u) - 1u]);
 #if MMF_TILE_TRACE
                         if (a.trace && blockIdx.x == 0 && step == 1 && i < 128) a.trace[768 + i] = clock64();
 #endif
@@ -638,7 +663,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
         e.arena = arena; e.pbuf = pbuf; e.misc = misc; e.bars = bars; e.P = pbuf;
         e.r = (warp & 3) * 32 + lane; e.hf = warp >> 2; e.tid = tid;
         e.taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-        e.pd0 = 0; e.pd1 = 0; e.pc = 0;
+        e.pd0 = 0; e.pd1 = 0; e.pd2 = 0; e.pc = 0; e.gc = 0;
         const int r = e.r, hf = e.hf;
         const int nrows = meta->nrows;
         float* s_xs = misc + mXs;
@@ -777,7 +802,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 for (int g = 0; g < 2; ++g) {
                     const float* G = e.P + g * tfp::SA_GROUP;
                     for (int u = 0; u < 2; ++u)
-                        attention_unit<32>(e, G + tfp::SA_BQKV + u * 64, G + tfp::SA_BQKV + 128 + u * 64, G + tfp::SA_BQKV + 256 + u * 64,
+                        attention_unit<32>(e, g == 0 && u == 0, !(g == 1 && u == 1), G + tfp::SA_BQKV + u * 64, G + tfp::SA_BQKV + 128 + u * 64, G + tfp::SA_BQKV + 256 + u * 64,
                                            G + tfp::SA_QG, G + tfp::SA_QB, G + tfp::SA_KG, G + tfp::SA_KB, seg_b, seg_e);
                 }
                 wait_done(e, 0);                              // last projection of group 1 has landed
@@ -830,7 +855,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 param_acquire(e);                             // attention stage
                 const bool last = blk + 1 == a.n_main;
                 for (int u = 0; u < 4; ++u)
-                    attention_unit<64>(e, e.P + tfp::BA_BQKV + u * 64, e.P + tfp::BA_BQKV + 256 + u * 64, e.P + tfp::BA_BQKV + 512 + u * 64,
+                    attention_unit<64>(e, u == 0, u < 3, e.P + tfp::BA_BQKV + u * 64, e.P + tfp::BA_BQKV + 256 + u * 64, e.P + tfp::BA_BQKV + 512 + u * 64,
                                        e.P + tfp::BA_QG, e.P + tfp::BA_QB, e.P + tfp::BA_KG, e.P + tfp::BA_KB, seg_b, seg_e);
                 wait_done(e, 0);
                 {
@@ -959,10 +984,10 @@ static unsigned long long* g_dbg_host = nullptr;
 void tf_tiles_dump_timeouts() {     // after a failed launch: which barrier waits of CTA 0 timed out (see mbar_wait)
     if (!g_dbg_host) return;
     const unsigned n = static_cast<unsigned>(g_dbg_host[0]);
-    fprintf(stderr, "tile kernel: %u timed-out barrier waits in CTA 0 (tag: epilogue = stamps passed, issuer = op index, 0x8000 | op = weight tile)\n", n);
+    fprintf(stderr, "tile kernel: %u timed-out barrier waits (first 62; tag: epilogue = stamps passed, issuer = op index, 0x8000 | op = weight tile)\n", n);
     for (unsigned i = 0; i < n && i < 62; ++i) {
         const unsigned long long v = g_dbg_host[1 + i];
-        fprintf(stderr, "  barrier smem+0x%llx parity %llu warp %llu tag %llu\n", (v >> 32) & 0xffff, (v >> 28) & 1, (v & 0xfff) >> 5, v >> 48);
+        fprintf(stderr, "  cta %llu barrier smem+0x%llx parity %llu warp %llu tag %llu\n", (v >> 12) & 0xffff, (v >> 32) & 0xffff, (v >> 28) & 1, (v & 0xfff) >> 5, v >> 48);
     }
 }
 int launch_tf_tiles_trace(const TfLaunch& a, int n_tiles, int cluster, cudaStream_t stream) {

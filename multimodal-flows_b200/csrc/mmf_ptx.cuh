@@ -84,7 +84,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         ++spins;
-        if (spins == (1u << 22) && mmf_dbg_sink && (threadIdx.x & 31) == 0 && blockIdx.x == 0) {
+        if (spins == (1u << 22) && mmf_dbg_sink && (threadIdx.x & 31) == 0) {
             const unsigned int slot = atomicAdd(reinterpret_cast<unsigned int*>(mmf_dbg_sink), 1u);
             if (slot < 62) {
                 mmf_dbg_sink[1 + slot] = (static_cast<unsigned long long>(tag) << 48) | (static_cast<unsigned long long>(smem_u32(bar) & 0xffffu) << 32) |

@@ -61,7 +61,7 @@ constexpr int HY_B2 = 128 + 12 * 128;            // [V] (first quarter only), V 
 // descriptors (relative to the operand arena) and the instruction descriptor.
 //   A advances by one 16 KB chunk per k-tile; B is the next `nkt` tiles of the weight ring, or an arena slice
 //   advancing by 8 KB per k-tile (V^T halves of the P V product).
-constexpr uint32_t kTfOpAcc = 1u, kTfOpWait = 2u, kTfOpRing = 4u, kTfOpHalfK = 8u, kTfOpBMn = 64u;   // TfOp.flags
+constexpr uint32_t kTfOpAcc = 1u, kTfOpWait = 2u, kTfOpRing = 4u, kTfOpHalfK = 8u, kTfOpBMn = 64u, kTfOpAttn = 128u;   // TfOp.flags
 struct TfOp {
     uint32_t a_lo;          // (arena offset of A >> 4) | LBO field of the descriptor low word
     uint32_t b_lo;          // same for B when it lives in the arena (ignored for ring operands)
@@ -70,7 +70,9 @@ struct TfOp {
     uint8_t nkt;            // k-tiles
     uint8_t flags;          // kTfOpAcc: the first MMA accumulates onto D; kTfOpWait: wait for the next "go" of the epilogue
                             // warps first; kTfOpRing: B from the weight ring; kTfOpHalfK: K = 32 (2 MMAs) instead of 64 (4);
-                            // bits 4-5: after the last k-tile 0 nothing, 1 commit -> done[0], 2 commit -> done[1];
+                            // bits 4-5: after the last k-tile 0 nothing, 1 commit -> done[0], 2 commit -> done[1], 3 commit -> done[2];
+                            // kTfOpAttn: issued by the attention issuer warp (S and P V: both operands in the arena) and handed
+                            // off on its own barrier; every other op belongs to the weight-GEMM issuer, which alone reads the ring;
                             // kTfOpBMn: B is MN-major ([K rows][N] with N contiguous: the V operand of P V as the epilogue
                             // writes it, no transpose) - each K = 16 step advances B by 16 rows of 128 bytes
 };

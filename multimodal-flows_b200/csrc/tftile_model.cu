@@ -126,7 +126,7 @@ struct Builder {
         TfOp o{};
         o.a_lo = desc_lo(a_off); o.b_lo = desc_lo(b_off); o.idesc = idesc_bf16(n) | (b_mn ? 1u << 16 : 0u); o.dcol = dcol; o.nkt = static_cast<uint8_t>(nkt);
         o.flags = static_cast<uint8_t>((acc ? kTfOpAcc : 0u) | (wait ? kTfOpWait : 0u) | (half_k ? kTfOpHalfK : 0u) | (b_mn ? kTfOpBMn : 0u) |
-                                       (static_cast<uint32_t>(signal) << 4));
+                                       kTfOpAttn | (static_cast<uint32_t>(signal) << 4));
         ops.push_back(o);
     }
     bool plan_ring() {
@@ -286,8 +286,8 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
                 b.smem_op(oQ + 64, oK + 64, 128, 384, 1, true, 0, 0, 1);     // S of head 1
                 b.smem_op(oQ, oVT, 32, 256, 2, false, 0, 1, 2, true);        // O_h0 = P_h0 V_h0 (keys 0..63, 64..127); V is [key][d]
                 b.smem_op(oQ, oVT + 64, 32, 288, 2, false, 0, 1, 1, true);   // O_h1: d columns 32..63 of the V rows
-                if (!(g == 1 && u == 1)) qkv(u == 1 ? 1 : g, u == 1 ? 0 : 1, 0);
-                b.ring_op(oO, rows_of(w[g].proj, 0, 128), u * 64, 1, static_cast<uint16_t>(g * 128), 1, 1, (g == 1 && u == 1) ? 1 : 0);
+                if (!(g == 1 && u == 1)) qkv(u == 1 ? 1 : g, u == 1 ? 0 : 1, 1);    // released together with P V of head 1
+                b.ring_op(oO, rows_of(w[g].proj, 0, 128), u * 64, 1, static_cast<uint16_t>(g * 128), 1, 1, (g == 1 && u == 1) ? 1 : 3);   // 3: done[2] = oO may be rewritten
             }
         ++blob_idx;
         for (int g = 0; g < 2; ++g) emit_mlp(b, w[g], 128, 2 * g, static_cast<uint16_t>(g * 128), g == 0, g == 1);
@@ -332,8 +332,8 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
         for (int u = 0; u < 4; ++u) {
             b.smem_op(oQ, oK, 128, 256, 1, false, 0, 1, 1);                  // S = Q K^T
             b.smem_op(oQ, oVT, 64, 448, 2, false, 0, 1, 1, true);            // O = P V; V is [key][d] (MN-major B)
-            if (u < 3) qkv(u + 1, 0);
-            b.ring_op(oO, rows_of(w.proj, 0, 256), u * 64, 1, 0, 1, 1, u == 3 ? 1 : 0);      // N = 256
+            if (u < 3) qkv(u + 1, 1);                                      // released together with P V
+            b.ring_op(oO, rows_of(w.proj, 0, 256), u * 64, 1, 0, 1, 1, u == 3 ? 1 : 3);      // N = 256; 3: done[2] = oO may be rewritten
         }
         ++blob_idx;
         emit_mlp(b, w, 256, 0, 0, true, true);
