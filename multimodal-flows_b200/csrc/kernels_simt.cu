@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include "mmf_internal.h"
 #include "mmf_simt.h"
+#include "mmf_ptx.cuh"
 
 namespace mmf {
 
@@ -113,6 +114,211 @@ hybrid_step_kernel(const float* __restrict__ vt, const float* __restrict__ logit
     __syncthreads();
     block_store(x + base * 3, s_x, kStepThreads * 3, nval * 3);
     if (rates_out) block_store(rates_out + base * V, s_lg, kStepThreads * V, nval * V);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1b. production mode of the step (in-kernel Philox draws, no rates returned): the HBM-bound form.
+//     Persistent CTAs walk 512-particle chunks; a chunk's logits / x / vt / k arrive in shared memory by four 1-D bulk
+//     copies (cp.async.bulk + mbarrier) issued one chunk ahead into the other of two stages, and x / k leave by two bulk
+//     stores - the SM issues no global load or store instruction on this path, so the ~170 instructions per particle
+//     that remain (softmax, thermostat, jump law, Philox) fit under the HBM time of 88 bytes per particle.
+//     A thread owns the two ADJACENT particles (2 tid, 2 tid + 1) of the chunk: their 18 logits are nine conflict-free
+//     8-byte shared loads (V odd), and one Philox4x32-10 block - keyed on (seed, global slot >> 1, step) - yields the two
+//     uniforms of both (x, y for the even slot, z, w for the odd one), independent of launch geometry and sharding.
+//     Arithmetic: StepMath<true> (MUFU ex2 / rcp) and the two-uniform jump law of step_particle_2u.
+// ---------------------------------------------------------------------------------------------
+constexpr int kProdThreads = 256, kProdChunk = 2 * kProdThreads, kProdStages = 2;
+template <int V> constexpr int prod_stage_bytes() { return kProdChunk * (8 + 4 * V + 12 + 12); }
+template <int V> constexpr int prod_smem_bytes() { return kProdStages * prod_stage_bytes<V>() + 64; }
+
+__device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(reinterpret_cast<uint64_t>(gdst)), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct ProdConst {
+    float sc;            // log2(e) / temperature: p_v = 2^(sc (l_v - max l))
+    float a2;            // -V beta log2(e): w = 2^(a2 (1 - t))
+    int filters;         // top-k or top-p active
+    unsigned long long div_magic;   // floor(2^64 / D) + 1: jet = umul64hi(slot, magic), exact below 2^64 / D
+};
+
+// one particle: logits in registers (lg, also at s_lg for the indexed read of l_k) -> new token
+template <int V>
+__device__ __forceinline__ int prod_particle(const float* lg, const float* s_lg, int k, float t, const StepParams& sp, const ProdConst& pc,
+                                             float u1, float u2) {
+    float m = lg[0];
+#pragma unroll
+    for (int v = 1; v < V; ++v) m = fmaxf(m, lg[v]);
+    const float nm = -m * pc.sc;
+    float p[V];
+    float s = 0.0f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        p[v] = ex2_approx(fmaf(lg[v], pc.sc, nm));
+        s += p[v];
+    }
+    const float inv = rcp_approx(s);
+    float qk;
+    if (pc.filters) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) p[v] *= inv;
+        step_filters<V, true>(p, sp.top_k, sp.top_p);
+        qk = p[0];
+#pragma unroll
+        for (int v = 1; v < V; ++v) qk = (k == v) ? p[v] : qk;
+    } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) p[v] *= inv;
+        qk = ex2_approx(fmaf(s_lg[k], pc.sc, nm)) * inv;
+    }
+    const float w = ex2_approx(pc.a2 * (1.0f - t));
+    const float coef = w * static_cast<float>(V) * rcp_approx(1.0f - w);
+    // lam_v = dt (1 + coef p_v + w q_k); sum_v p_v = 1, so L = V dt (1 + w q_k) + dt coef
+    const float bdt = fmaf(w, qk, 1.0f) * sp.dt, cdt = coef * sp.dt;
+    const float L = fmaf(static_cast<float>(V), bdt, cdt);
+    if (!(u1 < L * ex2_approx(-1.44269504f * L))) return k;     // zero or >= 2 events: the token stays (model/solvers.py:49-54)
+    const float target = u2 * L;
+    float c = 0.0f;
+    int j = 0;
+#pragma unroll
+    for (int v = 0; v < V - 1; ++v) {
+        c += fmaf(cdt, p[v], bdt);
+        j += (target >= c) ? 1 : 0;
+    }
+    return j;
+}
+
+template <int V>
+__global__ void __launch_bounds__(kProdThreads)
+hybrid_step_prod_kernel(const float* __restrict__ vt, const float* __restrict__ logits, float* __restrict__ x, long long* __restrict__ k,
+                        const float* __restrict__ t, long long n_particles, int D, const StepLaunch sl, const ProdConst pc, int bulk_ok) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    constexpr int kStage = prod_stage_bytes<V>();
+    constexpr uint32_t kBytesK = kProdChunk * 8, kBytesL = kProdChunk * 4 * V, kBytesX = kProdChunk * 12;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kProdStages * kStage);
+    const int tid = threadIdx.x;
+    const long long n_chunks = (n_particles + kProdChunk - 1) / kProdChunk;
+    if (tid == 0) {
+        for (int i = 0; i < kProdStages; ++i) mbar_init(&full[i], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto stage_k = [&](int st) { return reinterpret_cast<long long*>(smem_raw + st * kStage); };
+    auto stage_lg = [&](int st) { return reinterpret_cast<float*>(smem_raw + st * kStage + kBytesK); };
+    auto stage_x = [&](int st) { return reinterpret_cast<float*>(smem_raw + st * kStage + kBytesK + kBytesL); };
+    auto stage_v = [&](int st) { return reinterpret_cast<float*>(smem_raw + st * kStage + kBytesK + kBytesL + kBytesX); };
+    // a chunk travels by bulk copies when it is complete and every array is 16-byte aligned (else plain loads / stores)
+    auto is_bulk = [&](long long c) { return bulk_ok && c < n_chunks && (c + 1) * kProdChunk <= n_particles; };
+    auto issue_load = [&](long long c, int st) {          // one thread
+        const long long b = c * kProdChunk;
+        mbar_expect_tx(&full[st], kBytesK + kBytesL + 2 * kBytesX);
+        bulk_load_1d(stage_k(st), k + b, kBytesK, &full[st]);
+        bulk_load_1d(stage_lg(st), logits + b * V, kBytesL, &full[st]);
+        bulk_load_1d(stage_x(st), x + b * 3, kBytesX, &full[st]);
+        bulk_load_1d(stage_v(st), vt + b * 3, kBytesX, &full[st]);
+    };
+
+    uint32_t phase0 = 0, phase1 = 0;
+    long long chunk = blockIdx.x;
+    if (tid == 0 && is_bulk(chunk)) issue_load(chunk, 0);
+    for (int it = 0; chunk < n_chunks; ++it, chunk += gridDim.x) {
+        const int st = it & 1;
+        const long long next = chunk + gridDim.x;
+        if (tid == 0) {
+            tma_store_wait_read<0>();                     // the stores of the previous chunk have read the other stage
+            if (is_bulk(next)) issue_load(next, st ^ 1);
+        }
+        const long long base = chunk * kProdChunk;
+        const long long remain = n_particles - base;
+        const int nval = remain < kProdChunk ? static_cast<int>(remain) : kProdChunk;
+        long long* s_k = stage_k(st);
+        float* s_lg = stage_lg(st);
+        float* s_x = stage_x(st);
+        float* s_v = stage_v(st);
+        const bool bulk = is_bulk(chunk);
+        if (bulk) {
+            mbar_wait(&full[st], st ? phase1 : phase0);
+            if (st) phase1 ^= 1; else phase0 ^= 1;
+        } else {
+            for (int i = tid; i < nval; i += kProdThreads) s_k[i] = k[base + i];
+            for (int i = tid; i < nval * V; i += kProdThreads) s_lg[i] = logits[base * V + i];
+            for (int i = tid; i < nval * 3; i += kProdThreads) { s_x[i] = x[base * 3 + i]; s_v[i] = vt[base * 3 + i]; }
+            __syncthreads();
+        }
+
+        const int p0 = 2 * tid;
+        if (p0 < nval) {
+            float lg[2 * V], xs[6], vs[6];
+            const float2* lg2 = reinterpret_cast<const float2*>(s_lg + 2 * V * tid);
+#pragma unroll
+            for (int v = 0; v < V; ++v) { const float2 q = lg2[v]; lg[2 * v] = q.x; lg[2 * v + 1] = q.y; }
+            const longlong2 kk = *reinterpret_cast<const longlong2*>(s_k + p0);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float2 q = reinterpret_cast<const float2*>(s_x + 6 * tid)[c], r = reinterpret_cast<const float2*>(s_v + 6 * tid)[c];
+                xs[2 * c] = q.x; xs[2 * c + 1] = q.y; vs[2 * c] = r.x; vs[2 * c + 1] = r.y;
+            }
+            long long ka = kk.x, kb = kk.y;
+            const bool has_b = p0 + 1 < nval;
+            if (ka < 0 || ka >= V) { atomicOr(sl.err_flag, 2); ka = 0; }
+            if (has_b && (kb < 0 || kb >= V)) { atomicOr(sl.err_flag, 2); kb = 0; }
+            if (!has_b) kb = 0;
+            // jets (for the per-jet time) and global slots (for the draws) of the pair
+            const unsigned long long ia = static_cast<unsigned long long>(base + p0);
+            const unsigned long long ja = D == 1 ? ia : __umul64hi(ia, pc.div_magic);
+            const unsigned long long jb = ja + ((ia - ja * static_cast<unsigned long long>(D) + 1ull == static_cast<unsigned long long>(D)) ? 1ull : 0ull);
+            const float ta = __ldg(t + ja);
+            const float tb = (has_b && jb != ja) ? __ldg(t + jb) : ta;
+            const uint64_t ga = sl.slot0 + ia;
+            const uint32_t k0 = static_cast<uint32_t>(sl.seed), k1 = static_cast<uint32_t>(sl.seed >> 32);
+            float ua1, ua2, ub1, ub2;
+            {
+                const uint64_t pa = ga >> 1;
+                const Philox4 r = philox4x32_10(Philox4{static_cast<uint32_t>(pa), static_cast<uint32_t>(pa >> 32), sl.step, 0x32u}, k0, k1);
+                if ((ga & 1ull) == 0) {
+                    ua1 = u01_from_bits(r.x); ua2 = u01_from_bits(r.y); ub1 = u01_from_bits(r.z); ub2 = u01_from_bits(r.w);
+                } else {                                  // odd first slot of the launch: the pair straddles two blocks
+                    ua1 = u01_from_bits(r.z); ua2 = u01_from_bits(r.w);
+                    const uint64_t pb = pa + 1;
+                    const Philox4 q = philox4x32_10(Philox4{static_cast<uint32_t>(pb), static_cast<uint32_t>(pb >> 32), sl.step, 0x32u}, k0, k1);
+                    ub1 = u01_from_bits(q.x); ub2 = u01_from_bits(q.y);
+                }
+            }
+            const int na = prod_particle<V>(lg, s_lg + 2 * V * tid, static_cast<int>(ka), ta, sl.sp, pc, ua1, ua2);
+            const int nb = prod_particle<V>(lg + V, s_lg + 2 * V * tid + V, static_cast<int>(kb), tb, sl.sp, pc, ub1, ub2);
+            *reinterpret_cast<longlong2*>(s_k + p0) = make_longlong2(na, has_b ? nb : kk.y);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                reinterpret_cast<float2*>(s_x + 6 * tid)[c] = make_float2(euler_update(xs[2 * c], vs[2 * c], sl.sp.dt), euler_update(xs[2 * c + 1], vs[2 * c + 1], sl.sp.dt));
+        }
+        if (bulk) {
+            fence_proxy_async();                          // the generic-proxy writes above, before the async-proxy reads below
+            __syncthreads();
+            if (tid == 0) {
+                bulk_store_1d(k + base, s_k, kBytesK);
+                bulk_store_1d(x + base * 3, s_x, kBytesX);
+                tma_store_commit();
+            }
+        } else {
+            __syncthreads();
+            for (int i = tid; i < nval; i += kProdThreads) k[base + i] = s_k[i];
+            for (int i = tid; i < nval * 3; i += kProdThreads) x[base * 3 + i] = s_x[i];
+            __syncthreads();                              // (a later chunk of this CTA may reuse the stage)
+        }
+    }
+    if (tid == 0) tma_store_wait_all();
 }
 
 __global__ void euler_kernel(const float* __restrict__ vt, float* __restrict__ x, float dt, long long n) {
@@ -382,6 +588,36 @@ int launch_head_out_t(const HeadOutArgs& a, cudaStream_t stream) {
     return 0;
 }
 
+template <int V>
+int launch_step_prod(const float* vt, const float* logits, float* x, long long* k, const float* t, long long n, int D,
+                     const StepLaunch& sl, cudaStream_t stream) {
+    static int resident[64] = {0};                        // CTAs the device holds at once, per device ordinal
+    int dev = 0;
+    MMF_CUDA_OK(cudaGetDevice(&dev));
+    constexpr int smem = prod_smem_bytes<V>();
+    if (dev < 0 || dev >= 64 || resident[dev] == 0) {
+        MMF_CUDA_OK(cudaFuncSetAttribute(hybrid_step_prod_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int sms = 0, per_sm = 0;
+        MMF_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        MMF_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hybrid_step_prod_kernel<V>, kProdThreads, smem));
+        MMF_REQUIRE(per_sm > 0, "step kernel does not fit on this device");
+        if (dev >= 0 && dev < 64) resident[dev] = sms * per_sm;
+        else return 2;
+    }
+    ProdConst pc;
+    pc.sc = 1.44269504f / sl.sp.temperature;
+    pc.a2 = static_cast<float>(-static_cast<double>(V) * static_cast<double>(sl.sp.beta) * 1.4426950408889634);
+    pc.filters = (sl.sp.top_k > 0 && sl.sp.top_k != V) || sl.sp.top_p > 0.0f;
+    pc.div_magic = D > 1 ? ~0ull / static_cast<unsigned long long>(D) + 1ull : 0ull;
+    const auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    const int bulk_ok = aligned(vt) && aligned(logits) && aligned(x) && aligned(k);
+    const long long chunks = (n + kProdChunk - 1) / kProdChunk;
+    const unsigned grid = static_cast<unsigned>(chunks < resident[dev] ? chunks : resident[dev]);
+    hybrid_step_prod_kernel<V><<<grid, kProdThreads, smem, stream>>>(vt, logits, x, k, t, n, D, sl, pc, bulk_ok);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 #define MMF_DISPATCH_V(V_, CALL)                                        \
@@ -411,7 +647,7 @@ int launch_hybrid_step(const float* vt, const float* logits, float* x, long long
     const char* fe = getenv("MMF_STEP_EXACT");
     const bool force_exact = fe != nullptr && atoi(fe) != 0;
     if (sl.u == nullptr && rates_out == nullptr && !force_exact) {
-        MMF_DISPATCH_V(sl.sp.vocab, (hybrid_step_kernel<VV, true><<<blocks, kStepThreads, 0, stream>>>(vt, logits, x, k, t, n, D, sl, rates_out)));
+        MMF_DISPATCH_V(sl.sp.vocab, return launch_step_prod<VV>(vt, logits, x, k, t, n, D, sl, stream));
     } else {
         MMF_DISPATCH_V(sl.sp.vocab, (hybrid_step_kernel<VV, false><<<blocks, kStepThreads, 0, stream>>>(vt, logits, x, k, t, n, D, sl, rates_out)));
     }

@@ -125,6 +125,43 @@ def test_production_step_matches_reproducible_step_in_distribution(monkeypatch):
         assert torch.equal(out["1"][1], out["0"][1])
 
 
+@pytest.mark.parametrize("D", [7, 150])
+def test_production_step_sharding_tail_and_alignment(D):
+    """Production kernel (bulk-copy chunks of 512 particles, one Philox block per pair of adjacent global slots): the result
+    for a particle depends on (seed, global slot, step) only - not on where the launch starts (odd first slot: pairs straddle
+    Philox blocks), on the ragged last chunk, or on 16-byte alignment (unaligned views take the plain-load path)."""
+    from mmf_b200 import _abi
+    dev = torch.device("cuda:0")
+    B, V = 1543, 9
+    g = torch.Generator().manual_seed(31)
+    vt = torch.randn(B, D, 3, generator=g).to(dev)
+    logits = (torch.randn(B, D, V, generator=g) * 2).to(dev)
+    x0 = torch.randn(B, D, 3, generator=g).to(dev)
+    k0 = torch.randint(0, V, (B, D), generator=g).to(dev)
+    t = torch.rand(B, generator=g).mul(0.9).to(dev)            # per-jet times
+    def run(lo, hi, misalign):
+        def view(a):
+            a = a[lo:hi].contiguous()
+            if not misalign:
+                return a.clone()
+            buf = torch.empty(a.numel() + 1, dtype=a.dtype, device=dev)
+            v = buf[1:].view(a.shape)                          # 4 / 8 bytes past an aligned allocation
+            v.copy_(a)
+            return v
+        x, k = view(x0), view(k0)
+        opts = _abi.MmfStepOptions(1.0, 0.075, 0, 0.0, 0, 99, lo)
+        _abi.hybrid_step(view(vt), view(logits), x, k, t[lo:hi].contiguous(), 0.0101, opts, u=None, step_index=7, want_rates=False)
+        torch.cuda.synchronize()
+        return x, k
+    xa, ka = run(0, B, False)
+    assert (ka != k0).float().mean().item() > 0.01
+    assert torch.equal(xa, (x0 + vt * 0.0101)) or torch.allclose(xa, x0 + vt * 0.0101, rtol=0, atol=1e-6)
+    for lo, hi, mis in ((1, B, False), (0, B - 3, False), (777, 1290, False), (0, B, True), (5, 1031, True)):
+        xb, kb = run(lo, hi, mis)
+        assert torch.equal(kb, ka[lo:hi]), (D, lo, hi, mis)
+        assert torch.equal(xb, xa[lo:hi]), (D, lo, hi, mis)
+
+
 def test_step_rejects_out_of_range_tokens_only_in_flag():
     """Tokens outside [0,V) are clamped and flagged (the reference asserts, MJB.py:177-182); no crash."""
     from mmf_b200 import _abi
