@@ -15,6 +15,9 @@
  *   mmf_euler_step               ContinuousSolver.euler_step  model/solvers.py:139-143 (after the model call)
  *   mmf_generate[_host]          MultiModalFlowBridge.simulate_dynamics  model/MMF.py:172-200
  *                                ConditionalFlowMatching.simulate_dynamics  model/CFM.py:133-154
+ *   mmf_jet_observables          ParticleClouds / JetFeatures kinematics    utils/aoj.py:333-368, 452-471, 514-521
+ *                                flavor_mutliplicities                      utils/metrics.py:10-33
+ *                                de-standardisation of the sample           utils/callbacks.py:52-56
  *
  * Conventions
  *   - all functions return 0 on success, non-zero on failure; mmf_last_error() gives a thread-local message.
@@ -100,6 +103,21 @@ int mmf_hybrid_step(const float* vt, const float* logits, float* x, int64_t* k, 
 
 /* x += vt * dt on n floats (EPiC / ContinuousSolver carrier). */
 int mmf_euler_step(const float* vt, float* x, float dt, int64_t n, int32_t device, void* stream);
+
+/* Jet-level observables of a sample in one fused pass over device tensors (the parity / quality report of a run):
+ *   utils/callbacks.py:52-56   de-standardisation continuous * std + mean (mean, std: HOST float[3], NULL = identity)
+ *   utils/aoj.py:333-346       ParticleClouds: px, py, pz, E of every unmasked particle from (pT, eta_rel, phi_rel)
+ *   utils/aoj.py:358-368       particle charge from the token (+1: 4, 6, 8; -1: 3, 5, 7)
+ *   utils/aoj.py:452-463       JetFeatures: summed four-momentum, pt, m, eta, phi
+ *   utils/aoj.py:514-521       jet charge for kappa = 0 and kappa = 1
+ *   utils/metrics.py:10-33     flavor multiplicities: counts of each token per jet (the derived sums are host arithmetic)
+ * x (B,D,3) f32 standardised, k (B,D) i64 or NULL, mask (B,D) i64 (a slot counts when mask > 0).
+ * kin_out (B, MMF_OBS_NKIN) f32 = px py pz E pt m eta phi charge jet_charge multiplicity m2 (m = sqrt(m2); sums in fp64);
+ * counts_out (B,V) i32 or NULL.  Empty jets give the reference's values (0 sums, NaN eta / jet_charge). */
+#define MMF_OBS_NKIN 12
+int mmf_jet_observables(const float* x, const int64_t* k, const int64_t* mask, const float* mean, const float* std_,
+                        int32_t B, int32_t D, int32_t V, float* kin_out, int32_t* counts_out, int32_t device,
+                        void* stream);
 
 /* The whole N-step sampler on device tensors.
  *   t_grid      host array of the N time points (the caller builds torch.linspace(eps, 1-eps, N) so that it is

@@ -248,6 +248,16 @@ hybrid_step_prod_kernel(const float* __restrict__ vt, const float* __restrict__ 
         float* s_x = stage_x(st);
         float* s_v = stage_v(st);
         const bool bulk = is_bulk(chunk);
+        // jets of this thread's pair and their times: fetched before the wait, so the L2 latency hides under the bulk copies
+        const int p0 = 2 * tid;
+        const unsigned long long ia = static_cast<unsigned long long>(base + p0);
+        float ta = 0.0f, tb = 0.0f;
+        if (p0 < nval) {
+            const unsigned long long ja = D == 1 ? ia : __umul64hi(ia, pc.div_magic);
+            const unsigned long long jb = ja + ((ia - ja * static_cast<unsigned long long>(D) + 1ull == static_cast<unsigned long long>(D)) ? 1ull : 0ull);
+            ta = __ldg(t + ja);
+            tb = (p0 + 1 < nval && jb != ja) ? __ldg(t + jb) : ta;
+        }
         if (bulk) {
             mbar_wait(&full[st], st ? phase1 : phase0);
             if (st) phase1 ^= 1; else phase0 ^= 1;
@@ -258,7 +268,6 @@ hybrid_step_prod_kernel(const float* __restrict__ vt, const float* __restrict__ 
             __syncthreads();
         }
 
-        const int p0 = 2 * tid;
         if (p0 < nval) {
             float lg[2 * V], xs[6], vs[6];
             const float2* lg2 = reinterpret_cast<const float2*>(s_lg + 2 * V * tid);
@@ -275,12 +284,6 @@ hybrid_step_prod_kernel(const float* __restrict__ vt, const float* __restrict__ 
             if (ka < 0 || ka >= V) { atomicOr(sl.err_flag, 2); ka = 0; }
             if (has_b && (kb < 0 || kb >= V)) { atomicOr(sl.err_flag, 2); kb = 0; }
             if (!has_b) kb = 0;
-            // jets (for the per-jet time) and global slots (for the draws) of the pair
-            const unsigned long long ia = static_cast<unsigned long long>(base + p0);
-            const unsigned long long ja = D == 1 ? ia : __umul64hi(ia, pc.div_magic);
-            const unsigned long long jb = ja + ((ia - ja * static_cast<unsigned long long>(D) + 1ull == static_cast<unsigned long long>(D)) ? 1ull : 0ull);
-            const float ta = __ldg(t + ja);
-            const float tb = (has_b && jb != ja) ? __ldg(t + jb) : ta;
             const uint64_t ga = sl.slot0 + ia;
             const uint32_t k0 = static_cast<uint32_t>(sl.seed), k1 = static_cast<uint32_t>(sl.seed >> 32);
             float ua1, ua2, ub1, ub2;
@@ -319,6 +322,106 @@ hybrid_step_prod_kernel(const float* __restrict__ vt, const float* __restrict__ 
         }
     }
     if (tid == 0) tma_store_wait_all();
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1c. jet observables of a sample, one fused pass: de-standardise (utils/callbacks.py:52-56), particle
+//     four-momenta and charges (utils/aoj.py:333-368), per-jet sums -> pt, m, eta, phi, charge, jet charge (aoj.py:452-471,
+//     514-521), token counts (utils/metrics.py:10-33).  One warp per jet, lanes stride over the D slots; padded slots cost
+//     their 8 mask bytes only.  Sums are carried in fp64 (the mass is a difference of squares of the sums).
+//     HBM-bound: 8 B per slot + 20 B per real particle in, 48 + 4 V bytes per jet out.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256)
+jet_observables_kernel(const float* __restrict__ x, const long long* __restrict__ k, const long long* __restrict__ mask, const ObsArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long jet = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (jet >= a.B) return;                                   // whole warps leave together
+    const long long base = jet * a.D;
+    double px = 0.0, py = 0.0, pz = 0.0, E = 0.0, qpt = 0.0;
+    int n = 0, q = 0;
+    unsigned long long c_lo = 0ull, c_hi = 0ull;              // 8-bit counters of tokens 0..7 / 8..15 (a lane sees <= 255 slots)
+    // kObsUnroll slots per lane and pass: all mask loads of a pass are issued together, then the x / k loads of the unmasked
+    // slots, then the arithmetic - a jet costs two memory round trips per 160 slots instead of two per 32
+    constexpr int kObsUnroll = 5;
+    for (int d0 = lane; d0 < a.D; d0 += 32 * kObsUnroll) {
+        long long mk[kObsUnroll], tk[kObsUnroll];
+        float xv[kObsUnroll][3];
+#pragma unroll
+        for (int u = 0; u < kObsUnroll; ++u) {
+            const int d = d0 + 32 * u;
+            mk[u] = d < a.D ? __ldcs(mask + base + d) : 0;    // mask_bool = mask > 0 (aoj.py:336)
+        }
+#pragma unroll
+        for (int u = 0; u < kObsUnroll; ++u) {
+            const long long s = base + d0 + 32 * u;
+            xv[u][0] = xv[u][1] = xv[u][2] = 0.0f;
+            tk[u] = -1;
+            if (mk[u] > 0) {
+                xv[u][0] = __ldcs(x + s * 3); xv[u][1] = __ldcs(x + s * 3 + 1); xv[u][2] = __ldcs(x + s * 3 + 2);
+                if (k) tk[u] = __ldcs(k + s);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kObsUnroll; ++u) {
+            if (mk[u] <= 0) continue;
+            const float pt = det_add(det_mul(xv[u][0], a.std[0]), a.mean[0]);          // (x * sig) + mu, rounded like the reference
+            const float eta = det_add(det_mul(xv[u][1], a.std[1]), a.mean[1]);
+            const float phi = det_add(det_mul(xv[u][2], a.std[2]), a.mean[2]);
+            float sn, cs;
+            sincosf(phi, &sn, &cs);
+            // sinh / cosh from one exponential: absolute error ~1e-7 cosh(eta), i.e. ~1e-7 of this particle's energy
+            const float ex = expf(eta), exi = __frcp_rn(ex);
+            px += static_cast<double>(pt * cs);
+            py += static_cast<double>(pt * sn);
+            pz += static_cast<double>(pt * (0.5f * (ex - exi)));
+            E += static_cast<double>(pt * (0.5f * (ex + exi)));
+            ++n;
+            const long long tok = tk[u];
+            if (tok >= 0 && tok < 16) {
+                const unsigned sh = 8u * (static_cast<unsigned>(tok) & 7u);
+                if (tok < 8) c_lo += 1ull << sh; else c_hi += 1ull << sh;
+                // charge (aoj.py:358-368): two bits per token, code 0 -> -1 (tokens 3, 5, 7), 1 -> 0, 2 -> +1 (tokens 4, 6, 8)
+                const int ch = static_cast<int>((0x55562215u >> (2u * static_cast<unsigned>(tok))) & 3u) - 1;
+                q += ch;
+                qpt += static_cast<double>(static_cast<float>(ch) * pt);
+            }
+        }
+    }
+    px = warp_sum(px); py = warp_sum(py); pz = warp_sum(pz); E = warp_sum(E); qpt = warp_sum(qpt);
+    n = __reduce_add_sync(0xffffffffu, n);
+    q = __reduce_add_sync(0xffffffffu, q);
+    if (a.counts) {
+        int mine_tot = 0;
+        for (int v = 0; v < a.V; ++v) {
+            const int mine = static_cast<int>(((v < 8 ? c_lo : c_hi) >> (8 * (v & 7))) & 0xffull);
+            const int tot = __reduce_add_sync(0xffffffffu, mine);
+            mine_tot = (lane == v) ? tot : mine_tot;
+        }
+        if (lane < a.V) a.counts[jet * a.V + lane] = mine_tot;    // one coalesced store per jet
+    }
+    if (lane == 0) {
+        // sums and the mass-squared difference in fp64; the transcendental tail in fp32 (the reference's own precision)
+        const double pt2 = px * px + py * py;
+        const double m2 = E * E - pt2 - pz * pz;
+        const float ptf = sqrtf(static_cast<float>(pt2));
+        const double ptj = static_cast<double>(ptf);
+        float* o = a.kin + jet * kObsKin;
+        o[0] = static_cast<float>(px); o[1] = static_cast<float>(py); o[2] = static_cast<float>(pz); o[3] = static_cast<float>(E);
+        o[4] = ptf;
+        o[5] = sqrtf(static_cast<float>(m2));
+        o[6] = 0.5f * logf(static_cast<float>(ptj + pz) / static_cast<float>(ptj - pz));
+        o[7] = atan2f(static_cast<float>(py), static_cast<float>(px));
+        o[8] = static_cast<float>(q);
+        o[9] = static_cast<float>(qpt) / ptf;
+        o[10] = static_cast<float>(n);
+        o[11] = static_cast<float>(m2);
+    }
 }
 
 __global__ void euler_kernel(const float* __restrict__ vt, float* __restrict__ x, float dt, long long n) {
@@ -658,6 +761,14 @@ int launch_hybrid_step(const float* vt, const float* logits, float* x, long long
 int launch_euler(const float* vt, float* x, float dt, long long n, cudaStream_t stream) {
     if (n == 0) return 0;
     euler_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(vt, x, dt, n);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_jet_observables(const float* x, const long long* k, const long long* mask, const ObsArgs& a, cudaStream_t stream) {
+    if (a.B == 0) return 0;
+    const long long threads = static_cast<long long>(a.B) * 32;
+    jet_observables_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(x, k, mask, a);
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -81,4 +81,15 @@ int launch_hybrid_step(const float* vt, const float* logits, float* x, long long
 // continuous-only Euler update x += vt dt (EPiC carrier)
 int launch_euler(const float* vt, float* x, float dt, long long n, cudaStream_t stream);
 
+// jet observables (kernels_simt.cu 1c): kin (B, kObsKin) = px py pz E pt m eta phi charge jet_charge multiplicity m2
+constexpr int kObsKin = 12;
+struct ObsArgs {
+    long long B;
+    int D, V;
+    float mean[3], std[3];   // de-standardisation x * std + mean
+    float* kin;              // (B, kObsKin)
+    int* counts;             // (B, V) tokens among unmasked particles, or null
+};
+int launch_jet_observables(const float* x, const long long* k, const long long* mask, const ObsArgs& a, cudaStream_t stream);
+
 }  // namespace mmf

@@ -755,6 +755,21 @@ int mmf_euler_step(const float* vt, float* x, float dt, int64_t n, int32_t devic
     return launch_euler(vt, x, dt, n, static_cast<cudaStream_t>(stream));
 }
 
+int mmf_jet_observables(const float* x, const int64_t* k, const int64_t* mask, const float* mean, const float* std_, int32_t B,
+                        int32_t D, int32_t V, float* kin_out, int32_t* counts_out, int32_t device, void* stream) {
+    MMF_REQUIRE(x && mask && kin_out, "null argument");
+    MMF_REQUIRE(B >= 0 && D >= 1 && D <= 8160, "D must be in [1, 8160] (8-bit per-lane token counters)");
+    MMF_REQUIRE(counts_out == nullptr || (k != nullptr && V >= 1 && V <= 16), "token counts need k and 1 <= V <= 16");
+    MMF_CUDA_OK(cudaSetDevice(device));
+    ObsArgs a{};
+    a.B = B; a.D = D; a.V = V;
+    for (int c = 0; c < 3; ++c) { a.mean[c] = mean ? mean[c] : 0.0f; a.std[c] = std_ ? std_[c] : 1.0f; }
+    a.kin = kin_out;
+    a.counts = counts_out;
+    return launch_jet_observables(x, reinterpret_cast<const long long*>(k), reinterpret_cast<const long long*>(mask), a,
+                                  static_cast<cudaStream_t>(stream));
+}
+
 int mmf_generate(MmfModel* m, const float* x0, const int64_t* k0, const int64_t* mask, int32_t B, int32_t D,
                  const float* t_grid, int32_t N, float dt, const MmfStepOptions* opts, const float* u,
                  const uint8_t* forced_k, float* x_out, int64_t* k_out, float* rates_out, void* stream) {

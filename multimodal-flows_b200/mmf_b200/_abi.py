@@ -39,7 +39,7 @@ _lib: Optional[ctypes.CDLL] = None
 
 EXPORTS = [
     "mmf_abi_version", "mmf_last_error", "mmf_model_create", "mmf_model_destroy", "mmf_encoder_forward",
-    "mmf_hybrid_step", "mmf_euler_step", "mmf_generate", "mmf_generate_host", "mmf_launch_count",
+    "mmf_hybrid_step", "mmf_euler_step", "mmf_generate", "mmf_generate_host", "mmf_launch_count", "mmf_jet_observables",
     "mmf_dbg_gemm", "mmf_dbg_gemm_resln", "mmf_dbg_gemm_qkv", "mmf_dbg_attention", "mmf_dbg_ring_plan",
     "mmf_profile_enable", "mmf_profile_num_classes", "mmf_profile_class_name", "mmf_profile_read",
 ]
@@ -66,6 +66,8 @@ def lib() -> ctypes.CDLL:
     L.mmf_hybrid_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, POINTER(MmfStepOptions),
                                   c_void_p, c_uint32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]
     L.mmf_euler_step.argtypes = [c_void_p, c_void_p, c_float, c_int64, c_int32, c_void_p]
+    L.mmf_jet_observables.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
+                                      c_void_p, c_int32, c_void_p]
     L.mmf_generate.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_float,
                                POINTER(MmfStepOptions), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.mmf_generate_host.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32,
@@ -248,6 +250,28 @@ def hybrid_step(vt, logits, x, k, t, dt, opts: MmfStepOptions, u=None, step_inde
     check(lib().mmf_hybrid_step(ptr(vt), ptr(logits), ptr(x), ptr(k), ptr(t), float(dt), ctypes.byref(opts), ptr(u),
                                 int(step_index), B, D, V, ptr(rates), idx, stream_handle(x.device)))
     return rates
+
+
+OBS_COLUMNS = ("px", "py", "pz", "E", "pt", "m", "eta", "phi", "charge", "jet_charge", "multiplicity", "m2")
+
+
+def jet_observables(x, k, mask, mean=None, std=None, vocab_size=9):
+    """Fused jet observables of a sample on the device: returns (kin (B,12) f32 in OBS_COLUMNS order, counts (B,V) i32 or None).
+    x (B,D,3) f32 standardised, k (B,D[,1]) i64 or None, mask (B,D[,1]) i64; mean / std: 3 floats each (None = identity)."""
+    assert x.is_cuda and x.dtype == torch.float32
+    B, D = x.shape[:2]
+    x = x.contiguous()
+    mask = mask.reshape(B, D).to(torch.int64).contiguous()
+    if k is not None:
+        k = k.reshape(B, D).to(torch.int64).contiguous()
+    kin = torch.empty(B, len(OBS_COLUMNS), device=x.device, dtype=torch.float32)
+    counts = torch.empty(B, vocab_size, device=x.device, dtype=torch.int32) if k is not None else None
+    mean_c = (ctypes.c_float * 3)(*[float(v) for v in mean]) if mean is not None else None
+    std_c = (ctypes.c_float * 3)(*[float(v) for v in std]) if std is not None else None
+    idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    check(lib().mmf_jet_observables(ptr(x), ptr(k), ptr(mask), mean_c, std_c, B, D, int(vocab_size), ptr(kin), ptr(counts), idx,
+                                    stream_handle(x.device)))
+    return kin, counts
 
 
 def euler_step(vt, x, dt):
