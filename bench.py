@@ -194,10 +194,48 @@ def step_kernel_roofline(peaks, dev):
         ms = e0.elapsed_time(e1) / reps
         bytes_per_particle = 12 + 36 + 12 + 8 + 12 + 8 + (36 if u is not None else 0)
         gbs = B * D * bytes_per_particle / (ms * 1e-3) / 1e9
-        out[mode] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+        out[mode] = {"bound": "hbm", "kernel": "hybrid_step_prod_kernel" if u is None else "hybrid_step_kernel",
+                     "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
                      "traffic": None, "bytes_per_particle": bytes_per_particle, "ms_per_launch": ms, "particles": B * D}
+        try:                                  # DRAM bytes per launch of the same shape from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tr = json.load(f).get(out[mode]["kernel"])
+            if tr:
+                out[mode]["traffic"] = tr["dram_bytes_per_launch"]
+                out[mode]["traffic_note"] = tr["note"]
+        except (OSError, ValueError, KeyError):
+            pass
         del u
+    del vt, logits, x, k
+    out["jet_observables"] = observables_roofline(peaks, dev)
     return out
+
+
+def observables_roofline(peaks, dev):
+    """mmf_jet_observables on 2^19 AOJ-shaped jets (2.2 GB of input, far larger than L2).
+    Algorithmic bytes: 8 (mask) per slot + 20 (x 12 + k 8) per real particle in, 48 + 4 V per jet out."""
+    from mmf_b200 import _abi
+    B, D, V = 1 << 19, 150, 9
+    g = torch.Generator(device=dev).manual_seed(2)
+    n = torch.clamp(torch.round(55 + 18 * torch.randn(B, device=dev, generator=g)), 1, D).long()
+    mask = (torch.arange(D, device=dev)[None, :] < n[:, None]).long()
+    x = torch.randn(B, D, 3, device=dev, generator=g)
+    k = torch.randint(1, V, (B, D), device=dev, generator=g)
+    for _ in range(3):
+        _abi.jet_observables(x, k, mask, [1.9, 0.0, 0.0], [0.8, 0.11, 0.1])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        _abi.jet_observables(x, k, mask, [1.9, 0.0, 0.0], [0.8, 0.11, 0.1])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nbytes = 8 * B * D + 20 * int(n.sum()) + (48 + 4 * V) * B
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "jet_observables_kernel", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": gbs / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes": nbytes, "ms_per_launch": ms, "jets": B,
+            "jets_per_s": B / (ms * 1e-3)}
 
 
 def main():
