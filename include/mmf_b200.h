@@ -15,6 +15,8 @@
  *   mmf_euler_step               ContinuousSolver.euler_step  model/solvers.py:139-143 (after the model call)
  *   mmf_generate[_host]          MultiModalFlowBridge.simulate_dynamics  model/MMF.py:172-200
  *                                ConditionalFlowMatching.simulate_dynamics  model/CFM.py:133-154
+ *   mmf_make_source              _make_source_dataloader (noise, masks)     scripts/sample_mmf.py:70-92
+ *                                sample_from_empirical_masks                utils/aoj.py:875-890
  *   mmf_jet_observables          ParticleClouds / JetFeatures kinematics    utils/aoj.py:333-368, 452-471, 514-521
  *                                flavor_mutliplicities                      utils/metrics.py:10-33
  *                                de-standardisation of the sample           utils/callbacks.py:52-56
@@ -118,6 +120,18 @@ int mmf_euler_step(const float* vt, float* x, float dt, int64_t n, int32_t devic
 int mmf_jet_observables(const float* x, const int64_t* k, const int64_t* mask, const float* mean, const float* std_,
                         int32_t B, int32_t D, int32_t V, float* kin_out, int32_t* counts_out, int32_t device,
                         void* stream);
+
+/* The source state of the sampler, built on the device (no host RNG, no H2D copy of the batch):
+ *   scripts/sample_mmf.py:82-84   noise_continuous = randn * pad_mask, noise_discrete = randint(1, vocab_size) * pad_mask
+ *   utils/aoj.py:875-890          sample_from_empirical_masks: multiplicity ~ Categorical(histogram), prefix masks
+ * mult_probs: HOST float[D+1], weight of multiplicity 0..D (the density histogram of aoj.py:877; need not be normalised).
+ * Every draw is a function of (seed, first_global_jet + b, slot) only - Philox4x32-10, Box-Muller - so the sample is
+ * independent of batch size and of the sharding over GPUs.  The reference draws from torch's generators, so parity is in
+ * distribution; masks, multiplicities and tokens are bit-exact against oracle/source_oracle.py (same counters).
+ * Device outputs: x0 (B,D,3) f32, k0 (B,D) i64 or NULL (EPiC), mask (B,D) i64, n_out (B) i32 (the multiplicities).
+ * D <= 255. */
+int mmf_make_source(const float* mult_probs, int32_t B, int32_t D, int32_t V, uint64_t seed, uint64_t first_global_jet,
+                    float* x0, int64_t* k0, int64_t* mask, int32_t* n_out, int32_t device, void* stream);
 
 /* The whole N-step sampler on device tensors.
  *   t_grid      host array of the N time points (the caller builds torch.linspace(eps, 1-eps, N) so that it is

@@ -424,6 +424,74 @@ jet_observables_kernel(const float* __restrict__ x, const long long* __restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 1d. source state of the sampler, built on the device: multiplicity ~ Categorical(empirical histogram)
+//     with prefix masks (utils/aoj.py:875-890), x0 = N(0,1) * mask, k0 = U{1..V-1} * mask (scripts/sample_mmf.py:82-84).
+//     Counter-based: every draw is a function of (seed, GLOBAL jet, slot) only, so the sample does not depend on batch size
+//     or on how jets are sharded over GPUs, and oracle/source_oracle.py reproduces masks and tokens bit for bit.
+//       jet J:   Philox4x32-10(ctr = (J lo, J hi, 0, 'MULT'), key = seed) -> u = (x >> 8) 2^-24 -> n = #{m : cdf[m] <= u}
+//       slot S = J D + d:  Philox(ctr = (S lo, S hi, 0, 'SRCE')) -> u_i = ((w_i >> 9) + 0.5) 2^-23;
+//                z0, z1 = sqrt(-2 ln u_x) (cos, sin)(2 pi u_y), z2 = sqrt(-2 ln u_z) cos(2 pi u_w);
+//                token = 1 + mulhi(low bytes of the four words, V - 1)
+//     Write-bound: 28 B per slot (x 12, k 8, mask 8).
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kSrcTagMult = 0x4d554c54u, kSrcTagSlot = 0x53524345u;
+
+__global__ void source_mult_kernel(const SourceArgs a, int* __restrict__ n_out) {
+    const long long b = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const uint64_t J = a.first_jet + static_cast<uint64_t>(b);
+    const Philox4 r = philox4x32_10(Philox4{static_cast<uint32_t>(J), static_cast<uint32_t>(J >> 32), 0u, kSrcTagMult},
+                                    static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32));
+    const float u = u01_from_bits(r.x);
+    int n = 0;
+    for (int m = 0; m < a.D; ++m) n += (a.cdf[m] <= u) ? 1 : 0;      // cdf[m] = P(multiplicity <= m); cdf[D] = 1 > u
+    n_out[b] = n;
+}
+
+__global__ void __launch_bounds__(256)
+source_fill_kernel(const SourceArgs a, const int* __restrict__ n_in, float* __restrict__ x0, long long* __restrict__ k0,
+                   long long* __restrict__ mask) {
+    __shared__ __align__(16) float s_x[256 * 3];
+    const long long total = a.B * a.D;
+    const long long i0 = static_cast<long long>(blockIdx.x) * 256, i = i0 + threadIdx.x;
+    const bool valid = i < total;
+    float z0 = 0.0f, z1 = 0.0f, z2 = 0.0f;
+    long long tok = 0;
+    bool real = false;
+    if (valid) {
+        const unsigned long long b = a.D == 1 ? static_cast<unsigned long long>(i) : __umul64hi(static_cast<unsigned long long>(i), a.div_magic);
+        const int d = static_cast<int>(i - static_cast<long long>(b) * a.D);
+        real = d < __ldg(n_in + b);
+        if (real) {
+            const uint64_t S = (a.first_jet + b) * static_cast<uint64_t>(a.D) + static_cast<uint64_t>(d);
+            const Philox4 r = philox4x32_10(Philox4{static_cast<uint32_t>(S), static_cast<uint32_t>(S >> 32), 0u, kSrcTagSlot},
+                                            static_cast<uint32_t>(a.seed), static_cast<uint32_t>(a.seed >> 32));
+            // 23-bit uniforms strictly inside (0,1): (w >> 9) + 0.5 is exact in binary32
+            const float ux = (static_cast<float>(r.x >> 9) + 0.5f) * 1.1920929e-07f, uy = (static_cast<float>(r.y >> 9) + 0.5f) * 1.1920929e-07f;
+            const float uz = (static_cast<float>(r.z >> 9) + 0.5f) * 1.1920929e-07f, uw = (static_cast<float>(r.w >> 9) + 0.5f) * 1.1920929e-07f;
+            const float ra = sqrtf(-2.0f * logf(ux)), rb = sqrtf(-2.0f * logf(uz));
+            float sn, cs, sn2, cs2;
+            sincospif(2.0f * uy, &sn, &cs);
+            sincospif(2.0f * uw, &sn2, &cs2);
+            z0 = ra * cs; z1 = ra * sn; z2 = rb * cs2;
+            const uint32_t bits = (r.x & 0xffu) | ((r.y & 0xffu) << 8) | ((r.z & 0xffu) << 16) | ((r.w & 0xffu) << 24);
+            tok = 1 + static_cast<long long>(__umulhi(bits, static_cast<uint32_t>(a.V - 1)));
+        }
+        if (k0) __stcs(k0 + i, tok);
+        __stcs(mask + i, real ? 1ll : 0ll);
+    }
+    // x0: the block's 768 floats leave as 192 16-byte stores (full blocks of an aligned array), else element-wise
+    const bool vec = i0 + 256 <= total && (reinterpret_cast<uintptr_t>(x0) & 15u) == 0;
+    if (vec) {
+        s_x[threadIdx.x * 3] = z0; s_x[threadIdx.x * 3 + 1] = z1; s_x[threadIdx.x * 3 + 2] = z2;
+        __syncthreads();
+        if (threadIdx.x < 192) __stcs(reinterpret_cast<float4*>(x0 + i0 * 3) + threadIdx.x, reinterpret_cast<const float4*>(s_x)[threadIdx.x]);
+    } else if (valid) {
+        __stcs(x0 + i * 3, z0); __stcs(x0 + i * 3 + 1, z1); __stcs(x0 + i * 3 + 2, z2);
+    }
+}
+
 __global__ void euler_kernel(const float* __restrict__ vt, float* __restrict__ x, float dt, long long n) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) x[i] = euler_update(x[i], vt[i], dt);
@@ -769,6 +837,16 @@ int launch_jet_observables(const float* x, const long long* k, const long long* 
     if (a.B == 0) return 0;
     const long long threads = static_cast<long long>(a.B) * 32;
     jet_observables_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(x, k, mask, a);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_make_source(const SourceArgs& a, float* x0, long long* k0, long long* mask, int* n_out, cudaStream_t stream) {
+    if (a.B == 0) return 0;
+    source_mult_kernel<<<static_cast<unsigned>((a.B + 255) / 256), 256, 0, stream>>>(a, n_out);
+    MMF_CUDA_OK(cudaGetLastError());
+    const long long slots = a.B * a.D;
+    source_fill_kernel<<<static_cast<unsigned>((slots + 255) / 256), 256, 0, stream>>>(a, n_out, x0, k0, mask);
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -92,4 +92,14 @@ struct ObsArgs {
 };
 int launch_jet_observables(const float* x, const long long* k, const long long* mask, const ObsArgs& a, cudaStream_t stream);
 
+// source state on the device (kernels_simt.cu 1d)
+constexpr int kSrcMaxD = 255;
+struct SourceArgs {
+    long long B;
+    int D, V;
+    unsigned long long seed, first_jet, div_magic;   // div_magic = floor(2^64 / D) + 1
+    float cdf[kSrcMaxD + 1];                         // cdf[m] = P(multiplicity <= m), m = 0..D
+};
+int launch_make_source(const SourceArgs& a, float* x0, long long* k0, long long* mask, int* n_out, cudaStream_t stream);
+
 }  // namespace mmf

@@ -770,6 +770,30 @@ int mmf_jet_observables(const float* x, const int64_t* k, const int64_t* mask, c
                                   static_cast<cudaStream_t>(stream));
 }
 
+int mmf_make_source(const float* mult_probs, int32_t B, int32_t D, int32_t V, uint64_t seed, uint64_t first_global_jet, float* x0,
+                    int64_t* k0, int64_t* mask, int32_t* n_out, int32_t device, void* stream) {
+    MMF_REQUIRE(mult_probs && x0 && mask && n_out, "null argument");
+    MMF_REQUIRE(B >= 0 && D >= 1 && D <= kSrcMaxD, "max_num_particles must be in [1, 255]");
+    MMF_REQUIRE(k0 == nullptr || V >= 2, "vocab_size must be at least 2 when tokens are requested");
+    double tot = 0.0;
+    for (int m = 0; m <= D; ++m) {
+        MMF_REQUIRE(mult_probs[m] >= 0.0f, "multiplicity probabilities must be non-negative");
+        tot += static_cast<double>(mult_probs[m]);
+    }
+    MMF_REQUIRE(tot > 0.0, "multiplicity probabilities sum to zero");
+    MMF_CUDA_OK(cudaSetDevice(device));
+    SourceArgs a{};
+    a.B = B; a.D = D; a.V = V; a.seed = seed; a.first_jet = first_global_jet;
+    a.div_magic = D > 1 ? ~0ull / static_cast<unsigned long long>(D) + 1ull : 0ull;
+    double run = 0.0;
+    for (int m = 0; m <= D; ++m) {                       // cdf in double, rounded once; the last entry is exactly 1
+        run += static_cast<double>(mult_probs[m]);
+        a.cdf[m] = m == D ? 1.0f : static_cast<float>(run / tot);
+    }
+    return launch_make_source(a, x0, reinterpret_cast<long long*>(k0), reinterpret_cast<long long*>(mask), n_out,
+                              static_cast<cudaStream_t>(stream));
+}
+
 int mmf_generate(MmfModel* m, const float* x0, const int64_t* k0, const int64_t* mask, int32_t B, int32_t D,
                  const float* t_grid, int32_t N, float dt, const MmfStepOptions* opts, const float* u,
                  const uint8_t* forced_k, float* x_out, int64_t* k_out, float* rates_out, void* stream) {

@@ -39,7 +39,7 @@ _lib: Optional[ctypes.CDLL] = None
 
 EXPORTS = [
     "mmf_abi_version", "mmf_last_error", "mmf_model_create", "mmf_model_destroy", "mmf_encoder_forward",
-    "mmf_hybrid_step", "mmf_euler_step", "mmf_generate", "mmf_generate_host", "mmf_launch_count", "mmf_jet_observables",
+    "mmf_hybrid_step", "mmf_euler_step", "mmf_generate", "mmf_generate_host", "mmf_launch_count", "mmf_jet_observables", "mmf_make_source",
     "mmf_dbg_gemm", "mmf_dbg_gemm_resln", "mmf_dbg_gemm_qkv", "mmf_dbg_attention", "mmf_dbg_ring_plan",
     "mmf_profile_enable", "mmf_profile_num_classes", "mmf_profile_class_name", "mmf_profile_read",
 ]
@@ -68,6 +68,8 @@ def lib() -> ctypes.CDLL:
     L.mmf_euler_step.argtypes = [c_void_p, c_void_p, c_float, c_int64, c_int32, c_void_p]
     L.mmf_jet_observables.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p,
                                       c_void_p, c_int32, c_void_p]
+    L.mmf_make_source.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int32, c_void_p]
     L.mmf_generate.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_float,
                                POINTER(MmfStepOptions), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.mmf_generate_host.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32,
@@ -250,6 +252,25 @@ def hybrid_step(vt, logits, x, k, t, dt, opts: MmfStepOptions, u=None, step_inde
     check(lib().mmf_hybrid_step(ptr(vt), ptr(logits), ptr(x), ptr(k), ptr(t), float(dt), ctypes.byref(opts), ptr(u),
                                 int(step_index), B, D, V, ptr(rates), idx, stream_handle(x.device)))
     return rates
+
+
+def make_source(mult_probs, num_jets, max_num_particles, vocab_size, seed, first_global_jet, device, discrete=True):
+    """Source state on the device: returns (x0 (B,D,3) f32, k0 (B,D) i64 or None, mask (B,D) i64, n (B,) i32).
+    mult_probs: D+1 non-negative weights of multiplicity 0..D (host)."""
+    device = torch.device(device)
+    assert device.type == "cuda", "the source is built on the GPU (no CPU fallback)"
+    B, D = int(num_jets), int(max_num_particles)
+    probs = [float(v) for v in mult_probs]
+    assert len(probs) == D + 1, "mult_probs needs one weight per multiplicity 0..D"
+    probs_c = (ctypes.c_float * (D + 1))(*probs)
+    x0 = torch.empty(B, D, 3, device=device, dtype=torch.float32)
+    k0 = torch.empty(B, D, device=device, dtype=torch.int64) if discrete else None
+    mask = torch.empty(B, D, device=device, dtype=torch.int64)
+    n = torch.empty(B, device=device, dtype=torch.int32)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    check(lib().mmf_make_source(probs_c, B, D, int(vocab_size), int(seed), int(first_global_jet), ptr(x0), ptr(k0), ptr(mask), ptr(n),
+                                idx, stream_handle(device)))
+    return x0, k0, mask, n
 
 
 OBS_COLUMNS = ("px", "py", "pz", "E", "pt", "m", "eta", "phi", "charge", "jet_charge", "multiplicity", "m2")
