@@ -17,7 +17,7 @@ n = np.clip(np.round(55 + 18 * np.random.default_rng(0).standard_normal(200000))
 probs = (np.bincount(n, minlength=D + 1) / len(n)).astype(np.float32)
 epic = model == "EPiC"
 def sync(): torch.cuda.synchronize(); return time.perf_counter()
-for it in range(6):
+for it in range(int(sys.argv[3]) if len(sys.argv) > 3 else 6):
     t0 = sync()
     x0, k0, mask, nn = _abi.make_source(probs, batch, D, V, 1, it * batch, dev, discrete=not epic)
     t1 = sync()
