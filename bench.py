@@ -49,8 +49,13 @@ def parse_args():
     ap.add_argument("--timesteps", type=int, default=100)
     ap.add_argument("--temperature", type=float, default=1.0)
     ap.add_argument("--dense", action="store_true", help="every jet has 150 particles (worst case)")
-    ap.add_argument("--cpu-sample-jets", type=int, default=32)
-    ap.add_argument("--cpu-sample-timesteps", type=int, default=2)
+    ap.add_argument("--cpu-sample-jets", type=int, default=32,
+                    help="jets of the CPU sample (0 = the whole batch).  32 jets is the CPU's best case: its fp32 attention tensors still "
+                         "fit in cache, the whole batch of 256 runs ~20x slower per jet (see cpu_baseline.whole_batch_probe)")
+    ap.add_argument("--cpu-sample-timesteps", type=int, default=100,
+                    help="timesteps of the cpu_baseline sample (32 jets x all 100 timesteps: 5-15 s of CPU work, no extrapolation)")
+    ap.add_argument("--ref-sample-timesteps", type=int, default=25,
+                    help="timesteps of ONE step of --impl reference (each step is a bounded sample: K + W of them must fit in minutes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-step-roofline", action="store_true")
     return ap.parse_args()
@@ -149,10 +154,10 @@ def run_reference_arm(args, rank):
     for _ in range(max(args.warmup, 0)):
         cpu_port_rate(args, cfg, sd, args.cpu_sample_jets, 1)
     t0 = time.perf_counter()
-    rates = [cpu_port_rate(args, cfg, sd, args.cpu_sample_jets, args.cpu_sample_timesteps)[0] for _ in range(max(args.steps, 1))]
+    rates = [cpu_port_rate(args, cfg, sd, args.cpu_sample_jets, args.ref_sample_timesteps)[0] for _ in range(max(args.steps, 1))]
     wall = time.perf_counter() - t0
     value = sum(rates) / len(rates)
-    sample = (f"{args.cpu_sample_jets} jets x {args.cpu_sample_timesteps} of {args.timesteps} timesteps per step, oracle port "
+    sample = (f"{args.cpu_sample_jets} jets x {args.ref_sample_timesteps} of {args.timesteps} timesteps per step, oracle port "
               f"(torch fp32, {cores} threads), extrapolated linearly to {args.timesteps} timesteps")
     print(json.dumps({
         "impl": "reference", "metric": metric_name(args), "value": value, "unit": "jets/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -240,6 +245,10 @@ def observables_roofline(peaks, dev):
 
 def main():
     args = parse_args()
+    if args.cpu_sample_jets <= 0:
+        args.cpu_sample_jets = args.batch
+    args.cpu_sample_timesteps = max(1, min(args.cpu_sample_timesteps, args.timesteps))
+    args.ref_sample_timesteps = max(1, min(args.ref_sample_timesteps, args.timesteps))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -407,6 +416,10 @@ def main():
             "value": rate, "unit": "jets/s", "cores": cores, "kind": "port",
             "sample": f"{args.cpu_sample_jets} jets x {args.cpu_sample_timesteps} timesteps of the same workload "
                       f"({s_per_ts:.3f} s/timestep), extrapolated to {args.timesteps} timesteps; oracle/mmf_oracle.py torch fp32"}
+        if args.cpu_sample_jets < args.batch:
+            # the same port on the WHOLE batch, one timestep: what the reference's own batch size costs on these cores
+            wb_rate, wb_s = cpu_port_rate(args, cfg, sd, args.batch, 1)
+            line["cpu_baseline"]["whole_batch_probe"] = {"value": wb_rate, "unit": "jets/s", "sample": f"{args.batch} jets x 1 timestep ({wb_s:.2f} s), extrapolated"}
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()
