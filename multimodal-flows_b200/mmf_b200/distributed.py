@@ -80,3 +80,29 @@ def generate_sharded(run_batch: RunBatch, source: TensorMultiModal, batch_size: 
         return local
     counts = [shard_bounds(n, r, ws)[1] - shard_bounds(n, r, ws)[0] for r in range(ws)]
     return gather_sample(local, counts)
+
+
+def generate_from_device_source(run_batch: RunBatch, mult_probs, num_jets: int, batch_size: int, max_num_particles: int = 150,
+                                vocab_size: int = 9, time_eps: float = 1e-5, seed: int = 0, device="cuda", discrete: bool = True,
+                                gather: bool = True) -> TensorMultiModal:
+    """``generate_sharded`` without a host-side source: every batch of this rank's shard is BUILT ON THE DEVICE
+    (``mmf_b200.source.make_source``: multiplicities from ``mult_probs``, prefix masks, noise and tokens keyed on
+    (seed, GLOBAL jet index, slot)), so nothing but the multiplicities ever crosses PCIe and the sample is the same for every
+    batch size and world size.  Replaces the replicated ``_make_source_dataloader`` of ``scripts/sample_mmf.py:70-92``."""
+    from .source import make_source
+    rank, ws = world()
+    lo, hi = shard_bounds(num_jets, rank, ws)
+    outs = []
+    for b0 in range(lo, hi, batch_size):
+        b1 = min(b0 + batch_size, hi)
+        src = make_source(mult_probs, b1 - b0, max_num_particles, vocab_size, time_eps, seed=seed, first_global_jet=b0, device=device,
+                          discrete=discrete)
+        outs.append(run_batch(src, b0))
+    if outs:
+        local = TensorMultiModal.cat(outs, dim=0)
+    else:
+        local = make_source(mult_probs, 0, max_num_particles, vocab_size, time_eps, seed=seed, device=device, discrete=discrete)
+    if not gather:
+        return local
+    counts = [shard_bounds(num_jets, r, ws)[1] - shard_bounds(num_jets, r, ws)[0] for r in range(ws)]
+    return gather_sample(local, counts)

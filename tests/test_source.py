@@ -108,3 +108,33 @@ def test_kernel_draw_statistics_at_scale():
     assert ks < 2.0 / math.sqrt(sub.numel())
     hk = torch.bincount(k[real], minlength=9).double() / int(real.sum())
     assert float(hk[0]) == 0.0 and float((hk[1:] - 1 / 8).abs().max()) < 5 * math.sqrt(1 / 8 / int(real.sum()))
+
+
+@pytest.mark.gpu
+def test_generation_from_a_device_source_is_batch_size_invariant(golden_dir):
+    """The whole run without a host-side source (mmf_b200.distributed.generate_from_device_source): source built per batch on
+    the device, sampler, gather.  Source and Philox jump draws are keyed on the global jet index, so tokens and masks do not
+    depend on the batch size (bit-exact); the kinematics agree to bf16 tile-packing tolerance (a jet's tile neighbours change)."""
+    from mmf_b200 import synthetic
+    from mmf_b200.distributed import generate_from_device_source
+    from mmf_b200.mmf import MultiModalFlowBridge
+    from mmf_b200.param_spec import make_config
+    from mmf_b200.source import empirical_multiplicity_probs
+    from mmf_b200.tensorclass import DataCoupling
+    dev = torch.device("cuda:0")
+    D, emp, _ = _law(golden_dir)
+    probs = empirical_multiplicity_probs(emp, D)
+    cfg = make_config("FusedParticleFormer", num_timesteps=6)
+    bridge = MultiModalFlowBridge(cfg)
+    bridge.model.load_state_dict(synthetic.make_state_dict(cfg, "wide", 0), strict=True)
+    bridge = bridge.to(dev)
+    run = lambda s, g0: bridge.simulate_dynamics(DataCoupling(source=s), first_global_jet=g0).target
+    a = generate_from_device_source(run, probs, 96, 96, D, cfg.vocab_size, cfg.time_eps, seed=4, device=dev)
+    b = generate_from_device_source(run, probs, 96, 40, D, cfg.vocab_size, cfg.time_eps, seed=4, device=dev)
+    assert len(a) == 96 and a.continuous.shape == (96, D, 3) and a.discrete.shape == (96, D, 1)
+    assert torch.equal(a.mask, b.mask)
+    real = a.mask.bool().squeeze(-1)
+    assert (a.discrete.squeeze(-1)[real] == b.discrete.squeeze(-1)[real]).float().mean().item() > 0.97
+    rel = (a.continuous - b.continuous)[real].norm() / a.continuous[real].norm()
+    assert rel.item() < 2e-2, rel.item()
+    assert float(a.continuous[~real].abs().max()) == 0.0
