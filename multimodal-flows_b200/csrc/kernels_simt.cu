@@ -327,39 +327,45 @@ hybrid_step_prod_kernel(const float* __restrict__ vt, const float* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // 1c. jet observables of a sample, one fused pass: de-standardise (utils/callbacks.py:52-56), particle
 //     four-momenta and charges (utils/aoj.py:333-368), per-jet sums -> pt, m, eta, phi, charge, jet charge (aoj.py:452-471,
-//     514-521), token counts (utils/metrics.py:10-33).  One warp per jet, lanes stride over the D slots; padded slots cost
+//     514-521), token counts (utils/metrics.py:10-33).  Half a warp per jet, lanes stride over the D slots; padded slots cost
 //     their 8 mask bytes only.  Sums are carried in fp64 (the mass is a difference of squares of the sums).
 //     HBM-bound: 8 B per slot + 20 B per real particle in, 48 + 4 V bytes per jet out.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double warp_sum(double v) {
+constexpr int kObsLanes = 16;                                 // lanes per jet: a warp works on two jets at once
+__device__ __forceinline__ double group_sum(double v) {      // sum over the kObsLanes lanes of this thread's jet
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = kObsLanes / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 jet_observables_kernel(const float* __restrict__ x, const long long* __restrict__ k, const long long* __restrict__ mask, const ObsArgs a) {
-    const int lane = threadIdx.x & 31;
-    const long long jet = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    if (jet >= a.B) return;                                   // whole warps leave together
-    const long long base = jet * a.D;
+    // half a warp per jet: the per-jet tail (reductions, token counts, the transcendental finish) is half of the instruction
+    // stream at the typical 55 particles per jet, and two jets share every one of those instructions
+    const int lane = threadIdx.x & (kObsLanes - 1);
+    const unsigned gmask = 0xffffu << (threadIdx.x & 16);     // the lanes of this jet
+    const long long jet = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / kObsLanes;
+    const bool live = jet < a.B;                               // (an odd last jet leaves half a warp idle, but in step)
+    const long long base = (live ? jet : 0) * a.D;
     double px = 0.0, py = 0.0, pz = 0.0, E = 0.0, qpt = 0.0;
     int n = 0, q = 0;
     unsigned long long c_lo = 0ull, c_hi = 0ull;              // 8-bit counters of tokens 0..7 / 8..15 (a lane sees <= 255 slots)
-    // kObsUnroll slots per lane and pass: all mask loads of a pass are issued together, then the x / k loads of the unmasked
-    // slots, then the arithmetic - a jet costs two memory round trips per 160 slots instead of two per 32
+    // kObsUnroll slots per lane and pass (80 slots of the jet): all mask loads of a pass are issued together, then the x / k
+    // loads of the unmasked slots, then the arithmetic - two memory round trips per pass.  (Measured alternatives: ten per
+    // pass - one pass at D = 150 - spills at 64 registers, 2x slower; masks folded into a bit word and 32-bit tokens, 20 % slower.)
     constexpr int kObsUnroll = 5;
-    for (int d0 = lane; d0 < a.D; d0 += 32 * kObsUnroll) {
+    const int D = live ? a.D : 0;
+    for (int d0 = lane; d0 < D; d0 += kObsLanes * kObsUnroll) {
         long long mk[kObsUnroll], tk[kObsUnroll];
         float xv[kObsUnroll][3];
 #pragma unroll
         for (int u = 0; u < kObsUnroll; ++u) {
-            const int d = d0 + 32 * u;
-            mk[u] = d < a.D ? __ldcs(mask + base + d) : 0;    // mask_bool = mask > 0 (aoj.py:336)
+            const int d = d0 + kObsLanes * u;
+            mk[u] = d < D ? __ldcs(mask + base + d) : 0;      // mask_bool = mask > 0 (aoj.py:336)
         }
 #pragma unroll
         for (int u = 0; u < kObsUnroll; ++u) {
-            const long long s = base + d0 + 32 * u;
+            const long long s = base + d0 + kObsLanes * u;
             xv[u][0] = xv[u][1] = xv[u][2] = 0.0f;
             tk[u] = -1;
             if (mk[u] > 0) {
@@ -393,19 +399,19 @@ jet_observables_kernel(const float* __restrict__ x, const long long* __restrict_
             }
         }
     }
-    px = warp_sum(px); py = warp_sum(py); pz = warp_sum(pz); E = warp_sum(E); qpt = warp_sum(qpt);
-    n = __reduce_add_sync(0xffffffffu, n);
-    q = __reduce_add_sync(0xffffffffu, q);
+    px = group_sum(px); py = group_sum(py); pz = group_sum(pz); E = group_sum(E); qpt = group_sum(qpt);
+    n = __reduce_add_sync(gmask, n);
+    q = __reduce_add_sync(gmask, q);
     if (a.counts) {
         int mine_tot = 0;
         for (int v = 0; v < a.V; ++v) {
             const int mine = static_cast<int>(((v < 8 ? c_lo : c_hi) >> (8 * (v & 7))) & 0xffull);
-            const int tot = __reduce_add_sync(0xffffffffu, mine);
+            const int tot = __reduce_add_sync(gmask, mine);
             mine_tot = (lane == v) ? tot : mine_tot;
         }
-        if (lane < a.V) a.counts[jet * a.V + lane] = mine_tot;    // one coalesced store per jet
+        if (live && lane < a.V) a.counts[jet * a.V + lane] = mine_tot;    // one coalesced store per jet (V <= 16 = kObsLanes)
     }
-    if (lane == 0) {
+    if (live && lane == 0) {
         // sums and the mass-squared difference in fp64; the transcendental tail in fp32 (the reference's own precision)
         const double pt2 = px * px + py * py;
         const double m2 = E * E - pt2 - pz * pz;
@@ -835,7 +841,7 @@ int launch_euler(const float* vt, float* x, float dt, long long n, cudaStream_t 
 
 int launch_jet_observables(const float* x, const long long* k, const long long* mask, const ObsArgs& a, cudaStream_t stream) {
     if (a.B == 0) return 0;
-    const long long threads = static_cast<long long>(a.B) * 32;
+    const long long threads = static_cast<long long>(a.B) * kObsLanes;
     jet_observables_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(x, k, mask, a);
     MMF_CUDA_OK(cudaGetLastError());
     return 0;

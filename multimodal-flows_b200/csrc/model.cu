@@ -788,7 +788,7 @@ int mmf_euler_step(const float* vt, float* x, float dt, int64_t n, int32_t devic
 int mmf_jet_observables(const float* x, const int64_t* k, const int64_t* mask, const float* mean, const float* std_, int32_t B,
                         int32_t D, int32_t V, float* kin_out, int32_t* counts_out, int32_t device, void* stream) {
     MMF_REQUIRE(x && mask && kin_out, "null argument");
-    MMF_REQUIRE(B >= 0 && D >= 1 && D <= 8160, "D must be in [1, 8160] (8-bit per-lane token counters)");
+    MMF_REQUIRE(B >= 0 && D >= 1 && D <= 4080, "D must be in [1, 4080] (8-bit per-lane token counters, 16 lanes per jet)");
     MMF_REQUIRE(counts_out == nullptr || (k != nullptr && V >= 1 && V <= 16), "token counts need k and 1 <= V <= 16");
     MMF_CUDA_OK(cudaSetDevice(device));
     ObsArgs a{};
