@@ -47,7 +47,7 @@ constexpr int kArena = oRing + kTfRingBytes;
 // while the attention issuer keeps the epilogue going), so one barrier could complete two phases unobserved.
 constexpr int kGoBars = 4;
 struct TfBars {
-    uint64_t full[kBars], empty[kBars], done[3], go[kGoBars], go_attn, pfull[2], pempty[2];
+    uint64_t full[kBars], empty[kBars], done[4], go[kGoBars], go_attn, pfull[2], pempty[2];
     uint32_t tmem_base;
 };
 
@@ -70,7 +70,7 @@ struct Epi {
     const float* P;          // current parameter blob
     uint32_t taddr;          // TMEM base + this warp's lane quarter
     int r, hf, tid;
-    uint32_t pd0, pd1, pd2, pc;
+    uint32_t pd0, pd1, pd2, pd3, pc;
     uint32_t gc;             // hand-offs to the weight-GEMM issuer so far (barrier gc % kGoBars, parity (gc / kGoBars) & 1)
     uint32_t kmask, kfull, kpart;   // 16-key groups of this thread's key half: attended by any row of the warp / in full by
                                     // every row / cut by a jet boundary of some row
@@ -93,7 +93,8 @@ __device__ __forceinline__ void epi_bar() { named_bar_sync(1, kEpi); }
 __device__ __forceinline__ void wait_done(Epi& e, int b) {
     if (b == 0) { mbar_wait(&e.bars->done[0], e.pd0, e.mark_i); e.pd0 ^= 1; }     // (tag for the time-out diagnostics)
     else if (b == 1) { mbar_wait(&e.bars->done[1], e.pd1, e.mark_i); e.pd1 ^= 1; }
-    else { mbar_wait(&e.bars->done[2], e.pd2, e.mark_i); e.pd2 ^= 1; }
+    else if (b == 2) { mbar_wait(&e.bars->done[2], e.pd2, e.mark_i); e.pd2 ^= 1; }
+    else { mbar_wait(&e.bars->done[3], e.pd3, e.mark_i); e.pd3 ^= 1; }
     tc_fence_after();
     mark(e);
 }
@@ -346,11 +347,20 @@ __device__ __forceinline__ void v_epilogue(Epi& e, const float* bv) {
 // softmax_probs leaves the unnormalised probabilities in s[] and returns their sum; softmax_store writes them as the bf16
 // P operand (chunk hf of the Q|K staging area, which the previous P V product must have finished reading).
 // `slot` selects the exchange buffers.
-__device__ __forceinline__ float softmax_probs(Epi& e, uint32_t scol, float scale_log2e, int kb, int ke, int slot, float* s) {
+// `release_gemm`: the scores read here are the last live scratch columns the next unit's QKV product overwrites, so the
+// weight-GEMM issuer is handed that product as soon as they sit in registers (a whole softmax earlier than the P V hand-off;
+// it reads only Abuf and the ring, no shared memory written by this epilogue, hence no proxy fence).
+__device__ __forceinline__ float softmax_probs(Epi& e, uint32_t scol, float scale_log2e, int kb, int ke, int slot, float* s,
+                                               bool release_gemm = false) {
     const uint32_t km = e.kmask;
     tmem_ld32(e.taddr + scol + e.hf * 64, s);
     tmem_ld32(e.taddr + scol + e.hf * 64 + 32, s + 32);
     tmem_ld_wait();
+    if (release_gemm) {
+        tc_fence_before();
+        mbar_arrive(&e.bars->go[e.gc % kGoBars]);
+        ++e.gc;
+    }
     // keys outside the row's jet get -inf: they drop out of the max and ex2(-inf) = 0 removes them from the sum.
     // Key j of this thread is valid iff (unsigned)(j - lo) < span.  lo / span are made opaque here: otherwise the compiler
     // hoists the 64 comparisons out of the timestep loop into a bit mask and then serialises on predicate registers.
@@ -399,9 +409,9 @@ __device__ __forceinline__ void softmax_store(Epi& e, int slot, const float* s, 
     stage_row_bf16(e.arena + (e.hf ? oK : oQ), e.r, s);          // P chunk hf (keys hf*64..)
     e.misc[mSum + slot * 256 + e.hf * 128 + e.r] = sum;
 }
-__device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, float scale_log2e, int kb, int ke, int slot) {
+__device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, float scale_log2e, int kb, int ke, int slot, bool release_gemm = false) {
     float s[64];
-    const float sum = softmax_probs(e, scol, scale_log2e, kb, ke, slot, s);
+    const float sum = softmax_probs(e, scol, scale_log2e, kb, ke, slot, s, release_gemm);
     softmax_store(e, slot, s, sum);
 }
 
@@ -478,24 +488,24 @@ __device__ __forceinline__ void attention_unit(Epi& e, bool first, bool more, co
     v_epilogue<HS>(e, bv);                            // under the score MMA; P V is only issued after the next hand-off
     if (HS == 64) {
         wait_done(e, 0);
-        softmax_epilogue(e, kScr, scale, seg_b, seg_e, 0);
-        go_attn(e, more);                             // -> P V, and (S is consumed) the QKV GEMM of the next unit
+        softmax_epilogue(e, kScr, scale, seg_b, seg_e, 0, more);   // (S in registers -> the QKV GEMM of the next unit)
+        go_attn(e);                                       // -> P V
         wait_done(e, 0);
         if (!first) wait_done(e, 2);                      // the previous unit's projection (other issuer warp) has read oO
         o_epilogue<64>(e, kScr + 192, 0, 0);
-        go(e);                                        // -> projection
+        go(e);                                            // -> projection
     } else {
-        wait_done(e, 0);                              // both heads' scores: [256,384) and [384,512)
+        wait_done(e, 0);                                  // both heads' scores: [256,384) and [384,512)
         softmax_epilogue(e, kScr, scale, seg_b, seg_e, 0);
-        go_attn(e);                                   // -> P V of head 0
-        float s[64];                                  // head 1's probabilities are computed under that product ...
-        const float sum = softmax_probs(e, kScr + 128, scale, seg_b, seg_e, 1, s);
-        wait_done(e, 1);                              // ... and stored once it has finished reading head 0's
+        go_attn(e);                                       // -> P V of head 0
+        float s[64];                                      // head 1's probabilities are computed under that product ...
+        const float sum = softmax_probs(e, kScr + 128, scale, seg_b, seg_e, 1, s, more);   // (both S in registers -> next QKV GEMM)
+        wait_done(e, 3);                                  // ... and stored once it has finished reading head 0's
         softmax_store(e, 1, s, sum);
-        go_attn(e, more);                             // -> P V of head 1, and the QKV GEMM of the next unit
+        go_attn(e);                                       // -> P V of head 1
         if (!first) wait_done(e, 2);                      // the previous unit's projection (other issuer warp) has read oO
-        o_epilogue<32>(e, kScr, 0, 0);                // O of head 0 in scratch [0,32), under P V of head 1
-        wait_done(e, 0);                              // O of head 1 in scratch [32,64)
+        o_epilogue<32>(e, kScr, 0, 0);                    // O of head 0 in scratch [0,32), under P V of head 1
+        wait_done(e, 0);                                  // O of head 1 in scratch [32,64)
         o_epilogue<32>(e, kScr + 32, 32, 1);
         go(e);
     }
@@ -526,6 +536,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
         mbar_init(&bars->done[0], 1);
         mbar_init(&bars->done[1], 1);
         mbar_init(&bars->done[2], 1);
+        mbar_init(&bars->done[3], 1);
         for (int i = 0; i < kGoBars; ++i) mbar_init(&bars->go[i], kEpi);
         mbar_init(&bars->go_attn, kEpi);
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->pfull[i], 1); mbar_init(&bars->pempty[i], kEpi); }
@@ -618,7 +629,8 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 const bool ring = (fl & kTfOpRing) != 0;
                 uint32_t a_lo = op.a_lo + base16, b_lo = op.b_lo + base16, acc = fl & kTfOpAcc;
                 const uint32_t d = tmem_base + op.dcol;
-                for (uint32_t kt = 0; kt < op.nkt; ++kt) {
+                const uint32_t nkt = op.nkt & 0x7fu, sig = ((fl >> 4) & 3u) | ((op.nkt & 0x80u) >> 5);
+                for (uint32_t kt = 0; kt < nkt; ++kt) {
                     const uint32_t g = gbase + ti;
                     if (ring) {
                         b_lo = ring16 + (nt & 0xffu) * (1024u >> 4);
@@ -645,9 +657,9 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                     b_lo += 8192 >> 4;
                     acc = 1u;
                 }
-                if (fl & 0x30u) {
+                if (sig) {
                     if (elect_one()) {
-                        umma_commit(&bars->done[((fl >> 4) & 3u) - 1u]);
+                        umma_commit(&bars->done[sig - 1u]);
 #if MMF_TILE_TRACE
                         if (a.trace && blockIdx.x == 0 && step == 1 && i < 128) a.trace[768 + i] = clock64();
 #endif
@@ -663,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
         e.arena = arena; e.pbuf = pbuf; e.misc = misc; e.bars = bars; e.P = pbuf;
         e.r = (warp & 3) * 32 + lane; e.hf = warp >> 2; e.tid = tid;
         e.taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-        e.pd0 = 0; e.pd1 = 0; e.pd2 = 0; e.pc = 0; e.gc = 0;
+        e.pd0 = 0; e.pd1 = 0; e.pd2 = 0; e.pd3 = 0; e.pc = 0; e.gc = 0;
         const int r = e.r, hf = e.hf;
         const int nrows = meta->nrows;
         float* s_xs = misc + mXs;

@@ -67,10 +67,10 @@ struct TfOp {
     uint32_t b_lo;          // same for B when it lives in the arena (ignored for ring operands)
     uint32_t idesc;         // kind::f16 instruction descriptor (M = 128, N)
     uint16_t dcol;          // TMEM column of D (relative to the allocation base)
-    uint8_t nkt;            // k-tiles
+    uint8_t nkt;            // bits 0-6: k-tiles; bit 7: third bit of the completion signal (signal 4 = commit -> done[3])
     uint8_t flags;          // kTfOpAcc: the first MMA accumulates onto D; kTfOpWait: wait for the next "go" of the epilogue
                             // warps first; kTfOpRing: B from the weight ring; kTfOpHalfK: K = 32 (2 MMAs) instead of 64 (4);
-                            // bits 4-5: after the last k-tile 0 nothing, 1 commit -> done[0], 2 commit -> done[1], 3 commit -> done[2];
+                            // bits 4-5 (+ nkt bit 7): after the last k-tile 0 nothing, s = 1..4 commit -> done[s - 1];
                             // kTfOpAttn: issued by the attention issuer warp (S and P V: both operands in the arena) and handed
                             // off on its own barrier; every other op belongs to the weight-GEMM issuer, which alone reads the ring;
                             // kTfOpBMn: B is MN-major ([K rows][N] with N contiguous: the V operand of P V as the epilogue

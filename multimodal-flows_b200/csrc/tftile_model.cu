@@ -116,17 +116,17 @@ struct Builder {
                     stream[base + static_cast<size_t>(rr) * 64 + (((e >> 3) ^ (rr & 7)) << 3) + (e & 7)] = f32_to_bf16_bits(rows[rr][k0 + kt * 64 + e]);
         }
         TfOp o{};
-        o.a_lo = desc_lo(a_off); o.b_lo = 0; o.idesc = idesc_bf16(n); o.dcol = dcol; o.nkt = static_cast<uint8_t>(nkt);
-        o.flags = static_cast<uint8_t>((acc ? kTfOpAcc : 0u) | (wait ? kTfOpWait : 0u) | kTfOpRing | (static_cast<uint32_t>(signal) << 4));
+        o.a_lo = desc_lo(a_off); o.b_lo = 0; o.idesc = idesc_bf16(n); o.dcol = dcol; o.nkt = static_cast<uint8_t>(nkt | ((signal >> 2) << 7));
+        o.flags = static_cast<uint8_t>((acc ? kTfOpAcc : 0u) | (wait ? kTfOpWait : 0u) | kTfOpRing | (static_cast<uint32_t>(signal & 3) << 4));
         ops.push_back(o);
     }
     // both operands in the arena; B advances by 8 KB per k-tile
     // b_mn: B is MN-major (rows = K, N contiguous inside the 128-byte row) - bit 16 of the instruction descriptor
     void smem_op(uint32_t a_off, uint32_t b_off, int n, uint16_t dcol, int nkt, bool half_k, int acc, int wait, int signal, bool b_mn = false) {
         TfOp o{};
-        o.a_lo = desc_lo(a_off); o.b_lo = desc_lo(b_off); o.idesc = idesc_bf16(n) | (b_mn ? 1u << 16 : 0u); o.dcol = dcol; o.nkt = static_cast<uint8_t>(nkt);
+        o.a_lo = desc_lo(a_off); o.b_lo = desc_lo(b_off); o.idesc = idesc_bf16(n) | (b_mn ? 1u << 16 : 0u); o.dcol = dcol; o.nkt = static_cast<uint8_t>(nkt | ((signal >> 2) << 7));
         o.flags = static_cast<uint8_t>((acc ? kTfOpAcc : 0u) | (wait ? kTfOpWait : 0u) | (half_k ? kTfOpHalfK : 0u) | (b_mn ? kTfOpBMn : 0u) |
-                                       kTfOpAttn | (static_cast<uint32_t>(signal) << 4));
+                                       kTfOpAttn | (static_cast<uint32_t>(signal & 3) << 4));
         ops.push_back(o);
     }
     bool plan_ring() {
@@ -284,9 +284,9 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
             for (int u = 0; u < 2; ++u) {
                 b.smem_op(oQ, oK, 128, 256, 1, true, 0, 1, 0);               // S of head 0 of the pair
                 b.smem_op(oQ + 64, oK + 64, 128, 384, 1, true, 0, 0, 1);     // S of head 1
-                b.smem_op(oQ, oVT, 32, 256, 2, false, 0, 1, 2, true);        // O_h0 = P_h0 V_h0 (keys 0..63, 64..127); V is [key][d]
+                b.smem_op(oQ, oVT, 32, 256, 2, false, 0, 1, 4, true);        // O_h0 = P_h0 V_h0 (keys 0..63, 64..127); V is [key][d]; -> done[3]
                 b.smem_op(oQ, oVT + 64, 32, 288, 2, false, 0, 1, 1, true);   // O_h1: d columns 32..63 of the V rows
-                if (!(g == 1 && u == 1)) qkv(u == 1 ? 1 : g, u == 1 ? 0 : 1, 1);    // released together with P V of head 1
+                if (!(g == 1 && u == 1)) qkv(u == 1 ? 1 : g, u == 1 ? 0 : 1, 1);    // released as soon as both score tiles are in registers
                 b.ring_op(oO, rows_of(w[g].proj, 0, 128), u * 64, 1, static_cast<uint16_t>(g * 128), 1, 1, (g == 1 && u == 1) ? 1 : 3);   // 3: done[2] = oO may be rewritten
             }
         ++blob_idx;
@@ -332,7 +332,7 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
         for (int u = 0; u < 4; ++u) {
             b.smem_op(oQ, oK, 128, 256, 1, false, 0, 1, 1);                  // S = Q K^T
             b.smem_op(oQ, oVT, 64, 448, 2, false, 0, 1, 1, true);            // O = P V; V is [key][d] (MN-major B)
-            if (u < 3) qkv(u + 1, 1);                                      // released together with P V
+            if (u < 3) qkv(u + 1, 1);                                      // released as soon as the score tile is in registers
             b.ring_op(oO, rows_of(w.proj, 0, 256), u * 64, 1, 0, 1, 1, u == 3 ? 1 : 3);      // N = 256; 3: done[2] = oO may be rewritten
         }
         ++blob_idx;
