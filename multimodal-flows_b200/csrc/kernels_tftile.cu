@@ -82,21 +82,25 @@ struct Epi {
 #ifndef MMF_TILE_TRACE
 #define MMF_TILE_TRACE 0
 #endif
-__device__ __forceinline__ void mark(Epi& e) {
+// stamp = clock (low 56 bits) | tag << 56.  tag 0: a point of the epilogue program; 1: about to wait; 2 + b: done[b] arrived
+// (so the stamp after a tag-1 stamp measures a pure wait, everything else is epilogue work) - tools/tf_trace.py sums them up
+__device__ __forceinline__ void mark(Epi& e, unsigned tag = 0) {
 #if MMF_TILE_TRACE
-    if (e.trace && e.step < 2 && e.mark_i < 256) e.trace[e.step * 256 + e.mark_i] = clock64();
+    if (e.trace && e.step < 2 && e.mark_i < 512)
+        e.trace[e.step * 512 + e.mark_i] = (static_cast<unsigned long long>(clock64()) & 0x00ffffffffffffffull) | (static_cast<unsigned long long>(tag) << 56);
     ++e.mark_i;
 #endif
 }
 
 __device__ __forceinline__ void epi_bar() { named_bar_sync(1, kEpi); }
 __device__ __forceinline__ void wait_done(Epi& e, int b) {
+    mark(e, 1);
     if (b == 0) { mbar_wait(&e.bars->done[0], e.pd0, e.mark_i); e.pd0 ^= 1; }     // (tag for the time-out diagnostics)
     else if (b == 1) { mbar_wait(&e.bars->done[1], e.pd1, e.mark_i); e.pd1 ^= 1; }
     else if (b == 2) { mbar_wait(&e.bars->done[2], e.pd2, e.mark_i); e.pd2 ^= 1; }
     else { mbar_wait(&e.bars->done[3], e.pd3, e.mark_i); e.pd3 ^= 1; }
     tc_fence_after();
-    mark(e);
+    mark(e, 2 + b);
 }
 // hand-offs epilogue -> issuers: `go` releases the next waiting op of the weight-GEMM issuer, `go_attn` of the attention issuer
 __device__ __forceinline__ void go(Epi& e) {
@@ -661,7 +665,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                     if (elect_one()) {
                         umma_commit(&bars->done[sig - 1u]);
 #if MMF_TILE_TRACE
-                        if (a.trace && blockIdx.x == 0 && step == 1 && i < 128) a.trace[768 + i] = clock64();
+                        if (a.trace && blockIdx.x == 0 && step == 1 && i < 128) a.trace[1024 + i] = clock64();
 #endif
                     }
                     __syncwarp();

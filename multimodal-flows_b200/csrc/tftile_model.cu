@@ -545,28 +545,32 @@ int tftile_launch(TfTileModel* m, cudaStream_t s) {
     const char* trace_path = getenv("MMF_TRACE");
     unsigned long long* d_trace = nullptr;
     if (trace_path) {
-        MMF_CUDA_OK(cudaMalloc(&d_trace, 1536 * 8));
-        MMF_CUDA_OK(cudaMemsetAsync(d_trace, 0, 1536 * 8, s));
+        MMF_CUDA_OK(cudaMalloc(&d_trace, 2048 * 8));
+        MMF_CUDA_OK(cudaMemsetAsync(d_trace, 0, 2048 * 8, s));
         a.trace = d_trace;
     }
     MMF_TRY_RC(d_trace ? launch_tf_tiles_trace(a, tiles, m->cluster, s) : launch_tf_tiles(a, tiles, m->cluster, s));
     m->launches += 1;
     if (d_trace) {
-        std::vector<unsigned long long> hbuf(1536);
-        if (cudaMemcpyAsync(hbuf.data(), d_trace, 1536 * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+        std::vector<unsigned long long> hbuf(2048);
+        if (cudaMemcpyAsync(hbuf.data(), d_trace, 2048 * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
             tf_tiles_dump_timeouts();
             MMF_REQUIRE(false, "tile kernel: traced launch failed (stderr lists the barrier waits that timed out)");
         }
         MMF_CUDA_OK(cudaStreamSynchronize(s));
         cudaFree(d_trace);
         if (FILE* f = fopen(trace_path, "w")) {
+            const unsigned long long kClk = 0x00ffffffffffffffull;
+            static const char* kTag[] = {"", " [before a wait]", " [done0 arrived]", " [done1 arrived]", " [done2 arrived]", " [done3 arrived]"};
             for (int st = 0; st < 2; ++st)
-                for (int i = 0; i < 256 && hbuf[st * 256 + i]; ++i)
-                    fprintf(f, "step %d mark %2d  +%llu cycles (total %llu)\n", st, i, i ? hbuf[st * 256 + i] - hbuf[st * 256 + i - 1] : 0ull,
-                            hbuf[st * 256 + i] - hbuf[st * 256]);
+                for (int i = 0; i < 512 && hbuf[st * 512 + i]; ++i) {
+                    const unsigned long long c = hbuf[st * 512 + i] & kClk, c0 = hbuf[st * 512] & kClk, cp = i ? hbuf[st * 512 + i - 1] & kClk : c;
+                    const unsigned tag = static_cast<unsigned>(hbuf[st * 512 + i] >> 56);
+                    fprintf(f, "step %d mark %3d  +%llu cycles (total %llu)%s\n", st, i, c - cp, c - c0, tag < 6 ? kTag[tag] : "");
+                }
             // when each of the first 128 MMA ops of timestep 1 was issued, relative to the step start
             for (int i = 0; i < 128; ++i)
-                if (hbuf[768 + i]) fprintf(f, "op %3d issued %lld\n", i, (long long)(hbuf[768 + i] - hbuf[256]));
+                if (hbuf[1024 + i]) fprintf(f, "op %3d issued %lld\n", i, (long long)(hbuf[1024 + i] - (hbuf[512] & kClk)));
             fclose(f);
         }
     }

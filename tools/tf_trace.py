@@ -15,4 +15,24 @@ ts, dt = time_grid(cfg)
 for _ in range(2):
     nm.generate(src.continuous, src.discrete, src.mask, ts, dt, _abi.step_options(cfg))
 torch.cuda.synchronize()
-print(open(os.environ["MMF_TRACE"]).read())
+text = open(os.environ["MMF_TRACE"]).read()
+print(text)
+# summary of timestep 1: cycles the epilogue warps spent waiting on each completion barrier (a stamp tagged "doneN arrived"
+# follows a stamp tagged "before a wait", so its delta is a pure wait) against everything else (epilogue work)
+import re
+waits, work, nwait = {}, 0, {}
+for line in text.splitlines():
+    m = re.match(r"step 1 mark\s+\d+\s+\+(\d+) cycles \(total (\d+)\)(?: \[(.*)\])?", line)
+    if not m:
+        continue
+    d, tag = int(m.group(1)), m.group(3)
+    if tag and tag.endswith("arrived"):
+        waits[tag] = waits.get(tag, 0) + d
+        nwait[tag] = nwait.get(tag, 0) + 1
+    else:
+        work += d
+total = work + sum(waits.values())
+if total:
+    print(f"summary of timestep 1 ({model}): {total} cycles; epilogue work {work} ({100 * work / total:.1f} %)")
+    for tag in sorted(waits):
+        print(f"  waiting, {tag}: {waits[tag]} cycles in {nwait[tag]} waits ({100 * waits[tag] / total:.1f} %)")
