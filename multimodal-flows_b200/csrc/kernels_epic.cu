@@ -50,22 +50,31 @@ __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w 
 template <bool GELU, int NJ>
 __device__ __forceinline__ void global_hidden_jets(const uint4* __restrict__ wp, int kn, const float* s_pool_k0, float* s_hid,
                                                    const float* bias0, int bias_jet_stride, const int* jet_tb, int j0, int o0, int ks) {
+    // accumulators as float2 pairs: the 3-register FFMA issues every other cycle per scheduler on this part, the packed
+    // fma.rn.f32x2 (FFMA2) does two of them per instruction - the loop is FMA-pipe-bound (528 x 256 x NJ FMAs per tile)
+    float2 acc2[NJ][4];
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc2[jj][e] = make_float2(0.f, 0.f);
+#pragma unroll 16
+    for (int k = 0; k < kn; ++k) {
+        const uint4 w = __ldg(wp + k * 256);                // row 8 k + ks, outputs o0 .. o0+7
+        const float2 we[4] = {make_float2(bf16_lo(w.x), bf16_hi(w.x)), make_float2(bf16_lo(w.y), bf16_hi(w.y)),
+                              make_float2(bf16_lo(w.z), bf16_hi(w.z)), make_float2(bf16_lo(w.w), bf16_hi(w.w))};
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+            const float p = s_pool_k0[(j0 + jj) * kPoolLd + k * 8];   // the 8 slices of a warp read 8 consecutive words
+            const float2 pp = make_float2(p, p);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc2[jj][e] = __ffma2_rn(we[e], pp, acc2[jj][e]);
+        }
+    }
     float acc[NJ][8];
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[jj][e] = 0.f;
-#pragma unroll 16
-    for (int k = 0; k < kn; ++k) {
-        const uint4 w = __ldg(wp + k * 256);                // row 8 k + ks, outputs o0 .. o0+7
-        const float we[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y), bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
-#pragma unroll
-        for (int jj = 0; jj < NJ; ++jj) {
-            const float p = s_pool_k0[(j0 + jj) * kPoolLd + k * 8];   // the 8 slices of a warp read 8 consecutive words
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[jj][e] = fmaf(we[e], p, acc[jj][e]);
-        }
-    }
+        for (int e = 0; e < 4; ++e) { acc[jj][2 * e] = acc2[jj][e].x; acc[jj][2 * e + 1] = acc2[jj][e].y; }
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj)
 #pragma unroll
