@@ -135,35 +135,37 @@ __device__ __forceinline__ float4 ldf4(const float* p) { return *reinterpret_cas
 // 32-deep dependent chain would leave the issue slots empty.
 template <int N>
 __device__ __forceinline__ float sum_regs(const float* v) {
-    float s0 = v[0], s1 = v[1], s2 = v[2], s3 = v[3];
+    float2 s01 = MMF_V2(v, 0), s23 = MMF_V2(v, 2);
 #pragma unroll
-    for (int i = 4; i < N; i += 4) { s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3]; }
-    return (s0 + s1) + (s2 + s3);
+    for (int i = 4; i < N; i += 4) { s01 = f2add(s01, MMF_V2(v, i)); s23 = f2add(s23, MMF_V2(v, i + 2)); }
+    return (s01.x + s01.y) + (s23.x + s23.y);
 }
 template <int N>
 __device__ __forceinline__ float sqdev_regs(const float* v, float mean) {
-    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+    float2 q01 = f2dup(0.f), q23 = f2dup(0.f);
+    const float2 nm = f2dup(-mean);
 #pragma unroll
     for (int i = 0; i < N; i += 4) {
-        const float d0 = v[i] - mean, d1 = v[i + 1] - mean, d2 = v[i + 2] - mean, d3 = v[i + 3] - mean;
-        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+        const float2 d01 = f2add(MMF_V2(v, i), nm), d23 = f2add(MMF_V2(v, i + 2), nm);
+        q01 = f2fma(d01, d01, q01); q23 = f2fma(d23, d23, q23);
     }
-    return (q0 + q1) + (q2 + q3);
+    return (q01.x + q01.y) + (q23.x + q23.y);
 }
 // LayerNorm statistics gathered in the same pass that produces the row: sums of (v - c) and (v - c)^2 around a pivot c
 // taken from the row itself (its first value), so the variance does not suffer the cancellation of E[x^2] - mean^2.
 struct RowStat { float c, s1, s2; };
 template <int N>
 __device__ __forceinline__ void stat_regs(const float* v, RowStat& st) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+    float2 a01 = f2dup(0.f), a23 = f2dup(0.f), q01 = f2dup(0.f), q23 = f2dup(0.f);
+    const float2 nc = f2dup(-st.c);
 #pragma unroll
     for (int i = 0; i < N; i += 4) {
-        const float d0 = v[i] - st.c, d1 = v[i + 1] - st.c, d2 = v[i + 2] - st.c, d3 = v[i + 3] - st.c;
-        a0 += d0; a1 += d1; a2 += d2; a3 += d3;
-        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+        const float2 d01 = f2add(MMF_V2(v, i), nc), d23 = f2add(MMF_V2(v, i + 2), nc);
+        a01 = f2add(a01, d01); a23 = f2add(a23, d23);
+        q01 = f2fma(d01, d01, q01); q23 = f2fma(d23, d23, q23);
     }
-    st.s1 += (a0 + a1) + (a2 + a3);
-    st.s2 += (q0 + q1) + (q2 + q3);
+    st.s1 += (a01.x + a01.y) + (a23.x + a23.y);
+    st.s2 += (q01.x + q01.y) + (q23.x + q23.y);
 }
 template <int N>
 __device__ __forceinline__ float max_regs(const float* v) {
@@ -196,13 +198,15 @@ __device__ __forceinline__ RowStat resid_update(Epi& e, const float* add0, const
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const float4 a = ldf4(add0 + c0 + 4 * u);
-            v[4 * u] += a.x; v[4 * u + 1] += a.y; v[4 * u + 2] += a.z; v[4 * u + 3] += a.w;
+            MMF_SET2(v, 4 * u, f2add(MMF_V2(v, 4 * u), make_float2(a.x, a.y)));
+            MMF_SET2(v, 4 * u + 2, f2add(MMF_V2(v, 4 * u + 2), make_float2(a.z, a.w)));
         }
         if (add1) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const float4 a = ldf4(add1 + c0 + 4 * u);
-                v[4 * u] += a.x; v[4 * u + 1] += a.y; v[4 * u + 2] += a.z; v[4 * u + 3] += a.w;
+                MMF_SET2(v, 4 * u, f2add(MMF_V2(v, 4 * u), make_float2(a.x, a.y)));
+                MMF_SET2(v, 4 * u + 2, f2add(MMF_V2(v, 4 * u + 2), make_float2(a.z, a.w)));
             }
         }
         if (skipc) {
@@ -246,12 +250,12 @@ __device__ __forceinline__ void ln_to_abuf(Epi& e, float mean, float rstd, const
         tmem_ld32(e.taddr + e.hf * 128 + c0, v);
         tmem_ld_wait();
 #pragma unroll
+        const float2 nm = f2dup(-mean), rs = f2dup(rstd);
+#pragma unroll
         for (int u = 0; u < 8; ++u) {
             const float4 gg = ldf4(g + c0 + 4 * u), bb = ldf4(b + c0 + 4 * u);
-            v[4 * u] = fmaf((v[4 * u] - mean) * rstd, gg.x, bb.x);
-            v[4 * u + 1] = fmaf((v[4 * u + 1] - mean) * rstd, gg.y, bb.y);
-            v[4 * u + 2] = fmaf((v[4 * u + 2] - mean) * rstd, gg.z, bb.z);
-            v[4 * u + 3] = fmaf((v[4 * u + 3] - mean) * rstd, gg.w, bb.w);
+            MMF_SET2(v, 4 * u, f2fma(f2mul(f2add(MMF_V2(v, 4 * u), nm), rs), make_float2(gg.x, gg.y), make_float2(bb.x, bb.y)));
+            MMF_SET2(v, 4 * u + 2, f2fma(f2mul(f2add(MMF_V2(v, 4 * u + 2), nm), rs), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w)));
         }
         stage32(e.arena + oA, e.r, e.hf * 128 + c0, v);
     }
@@ -288,12 +292,12 @@ __device__ __forceinline__ void ln_regs(float* v, const float* g, const float* b
     const float q = sqdev_regs<N>(v, mean);
     const float rstd = rsqrtf(q * (1.0f / N) + 1e-5f);
 #pragma unroll
+    const float2 nm = f2dup(-mean), rs = f2dup(rstd);
+#pragma unroll
     for (int i = 0; i < N; i += 4) {
         const float4 gg = ldf4(g + i), bb = ldf4(b + i);
-        v[i] = fmaf((v[i] - mean) * rstd, gg.x, bb.x);
-        v[i + 1] = fmaf((v[i + 1] - mean) * rstd, gg.y, bb.y);
-        v[i + 2] = fmaf((v[i + 2] - mean) * rstd, gg.z, bb.z);
-        v[i + 3] = fmaf((v[i + 3] - mean) * rstd, gg.w, bb.w);
+        MMF_SET2(v, i, f2fma(f2mul(f2add(MMF_V2(v, i), nm), rs), make_float2(gg.x, gg.y), make_float2(bb.x, bb.y)));
+        MMF_SET2(v, i + 2, f2fma(f2mul(f2add(MMF_V2(v, i + 2), nm), rs), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w)));
     }
 }
 
@@ -316,7 +320,8 @@ __device__ __forceinline__ void qk_epilogue(Epi& e, const float* bq, const float
 #pragma unroll
     for (int i = 0; i < 64; i += 4) {
         const float4 a = ldf4(bias + i);
-        v[i] += a.x; v[i + 1] += a.y; v[i + 2] += a.z; v[i + 3] += a.w;
+        MMF_SET2(v, i, f2add(MMF_V2(v, i), make_float2(a.x, a.y)));
+        MMF_SET2(v, i + 2, f2add(MMF_V2(v, i + 2), make_float2(a.z, a.w)));
     }
     const float* g = e.hf ? kg : qg;
     const float* b = e.hf ? kb : qb;
@@ -400,7 +405,10 @@ __device__ __forceinline__ float softmax_probs(Epi& e, uint32_t scol, float scal
     for (int g = 0; g < 4; ++g) {
         if (km & (1u << g)) {
 #pragma unroll
-            for (int j = 16 * g; j < 16 * g + 16; ++j) s[j] = ex2_approx(fmaf(s[j], scale_log2e, -msc));
+            for (int j = 16 * g; j < 16 * g + 16; j += 2) {
+                const float2 a = f2fma(MMF_V2(s, j), f2dup(scale_log2e), f2dup(-msc));
+                s[j] = ex2_approx(a.x); s[j + 1] = ex2_approx(a.y);
+            }
             sum += sum_regs<16>(s + 16 * g);
         } else {
 #pragma unroll
@@ -448,8 +456,8 @@ __device__ __forceinline__ void fc_epilogue(Epi& e, int q, const float* bias) {
 #pragma unroll
     for (int i = 0; i < 64; i += 4) {
         const float4 a = ldf4(bias + e.hf * 64 + i);
-        v[i] = gelu_tile(v[i] + a.x); v[i + 1] = gelu_tile(v[i + 1] + a.y);
-        v[i + 2] = gelu_tile(v[i + 2] + a.z); v[i + 3] = gelu_tile(v[i + 3] + a.w);
+        MMF_SET2(v, i, gelu_tile2(f2add(MMF_V2(v, i), make_float2(a.x, a.y))));
+        MMF_SET2(v, i + 2, gelu_tile2(f2add(MMF_V2(v, i + 2), make_float2(a.z, a.w))));
     }
     stage_row_bf16(e.arena + ((q & 1) ? oH1 : oH0) + e.hf * kTile, e.r, v);
 }

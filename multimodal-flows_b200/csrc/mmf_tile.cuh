@@ -38,6 +38,29 @@ __device__ __forceinline__ float gelu_tanh(float x) {
     const float hx = 0.5f * x;
     return fmaf(hx, t, hx);
 }
+// Packed fp32 arithmetic (sm_100 add / mul / fma.rn.f32x2 on an aligned register pair): one instruction for two elements,
+// each lane rounded exactly like the scalar instruction.  The row-per-thread epilogues are bound by instruction issue and
+// dependent-issue latency (two warps per scheduler), so halving the instruction count of their element-wise passes pays.
+__device__ __forceinline__ float2 f2dup(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#define MMF_V2(v, i) make_float2((v)[(i)], (v)[(i) + 1])
+#define MMF_SET2(v, i, expr) do { const float2 _r2 = (expr); (v)[(i)] = _r2.x; (v)[(i) + 1] = _r2.y; } while (0)
+
+__device__ __forceinline__ float2 gelu_tanh2(float2 x) {     // gelu_tanh on a pair: five packed instructions + two MUFU.TANH
+    const float2 u = f2mul(x, f2fma(f2mul(x, x), f2dup(0.0356774081f), f2dup(0.7978845608f)));
+    float2 t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+    const float2 hx = f2mul(x, f2dup(0.5f));
+    return f2fma(hx, t, hx);
+}
+#ifdef MMF_TILE_GELU_EXACT
+__device__ __forceinline__ float2 gelu_tile2(float2 x) { return make_float2(gelu_erf(x.x), gelu_erf(x.y)); }
+#else
+__device__ __forceinline__ float2 gelu_tile2(float2 x) { return gelu_tanh2(x); }
+#endif
 #ifdef MMF_TILE_GELU_EXACT
 __device__ __forceinline__ float gelu_tile(float x) { return gelu_erf(x); }
 #else
