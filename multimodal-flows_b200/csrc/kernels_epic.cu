@@ -122,13 +122,14 @@ __device__ __forceinline__ float global_out16(const float* W2 /* shared memory, 
     const int j = tid >> 5, q = (tid >> 1) & 15, half = tid & 1;
     const float4* w = reinterpret_cast<const float4*>(W2);
     const float4* h = reinterpret_cast<const float4*>(s_hid + j * 256 + half * 128);
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;             // four independent chains
+    float2 a01 = f2dup(0.f), a23 = f2dup(0.f);                // four independent chains in two packed accumulators
 #pragma unroll
     for (int o = 0; o < 32; ++o) {
         const float4 a = w[w2_slot(q, half * 32 + o)], b = h[o];
-        a0 = fmaf(a.x, b.x, a0); a1 = fmaf(a.y, b.y, a1); a2 = fmaf(a.z, b.z, a2); a3 = fmaf(a.w, b.w, a3);
+        a01 = f2fma(make_float2(a.x, a.y), make_float2(b.x, b.y), a01);
+        a23 = f2fma(make_float2(a.z, a.w), make_float2(b.z, b.w), a23);
     }
-    float acc = (a0 + a1) + (a2 + a3);
+    float acc = (a01.x + a01.y) + (a23.x + a23.y);
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     return acc + __ldg(b2 + q);
 }
@@ -275,8 +276,12 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
                         uint32_t w[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) w[i] = *reinterpret_cast<const uint32_t*>(ch + sw128_offset(rr + i, u));
-                        a0 += ((bf16_lo(w[0]) + bf16_lo(w[1])) + (bf16_lo(w[2]) + bf16_lo(w[3]))) + ((bf16_lo(w[4]) + bf16_lo(w[5])) + (bf16_lo(w[6]) + bf16_lo(w[7])));
-                        a1 += ((bf16_hi(w[0]) + bf16_hi(w[1])) + (bf16_hi(w[2]) + bf16_hi(w[3]))) + ((bf16_hi(w[4]) + bf16_hi(w[5])) + (bf16_hi(w[6]) + bf16_hi(w[7])));
+                        float2 t[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) t[i] = make_float2(bf16_lo(w[i]), bf16_hi(w[i]));
+                        const float2 s = f2add(f2add(f2add(t[0], t[1]), f2add(t[2], t[3])), f2add(f2add(t[4], t[5]), f2add(t[6], t[7])));   // same tree
+                        a0 += s.x;
+                        a1 += s.y;
                     }
                     for (; rr < lim; ++rr) {
                         const uint32_t w = *reinterpret_cast<const uint32_t*>(ch + sw128_offset(rr, u));
@@ -453,8 +458,8 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
 #pragma unroll
                         for (int i = 0; i < 64; i += 4) {
                             const float4 b = *reinterpret_cast<const float4*>(jb + chunk * 64 + i);
-                            v[i] = leaky_relu(v[i] + b.x); v[i + 1] = leaky_relu(v[i + 1] + b.y);
-                            v[i + 2] = leaky_relu(v[i + 2] + b.z); v[i + 3] = leaky_relu(v[i + 3] + b.w);
+                            MMF_SET2(v, i, leaky_relu2(f2add(MMF_V2(v, i), make_float2(b.x, b.y))));
+                            MMF_SET2(v, i + 2, leaky_relu2(f2add(MMF_V2(v, i + 2), make_float2(b.z, b.w))));
                         }
                         stage_row_bf16(Abuf + chunk * kTile, r, v);
                     }
@@ -485,14 +490,10 @@ __global__ void __launch_bounds__(kThreads, 1) epic_tile_kernel(const EpicLaunch
                         const uint4 s8 = sk[c * 4 + u];
                         const float4 b0 = *reinterpret_cast<const float4*>(s_bl2 + l * 256 + col0 + 8 * u);
                         const float4 b1 = *reinterpret_cast<const float4*>(s_bl2 + l * 256 + col0 + 8 * u + 4);
-                        v[8 * u] = leaky_relu(v[8 * u] + b0.x) + bf16_lo(s8.x);
-                        v[8 * u + 1] = leaky_relu(v[8 * u + 1] + b0.y) + bf16_hi(s8.x);
-                        v[8 * u + 2] = leaky_relu(v[8 * u + 2] + b0.z) + bf16_lo(s8.y);
-                        v[8 * u + 3] = leaky_relu(v[8 * u + 3] + b0.w) + bf16_hi(s8.y);
-                        v[8 * u + 4] = leaky_relu(v[8 * u + 4] + b1.x) + bf16_lo(s8.z);
-                        v[8 * u + 5] = leaky_relu(v[8 * u + 5] + b1.y) + bf16_hi(s8.z);
-                        v[8 * u + 6] = leaky_relu(v[8 * u + 6] + b1.z) + bf16_lo(s8.w);
-                        v[8 * u + 7] = leaky_relu(v[8 * u + 7] + b1.w) + bf16_hi(s8.w);
+                        MMF_SET2(v, 8 * u, f2add(leaky_relu2(f2add(MMF_V2(v, 8 * u), make_float2(b0.x, b0.y))), make_float2(bf16_lo(s8.x), bf16_hi(s8.x))));
+                        MMF_SET2(v, 8 * u + 2, f2add(leaky_relu2(f2add(MMF_V2(v, 8 * u + 2), make_float2(b0.z, b0.w))), make_float2(bf16_lo(s8.y), bf16_hi(s8.y))));
+                        MMF_SET2(v, 8 * u + 4, f2add(leaky_relu2(f2add(MMF_V2(v, 8 * u + 4), make_float2(b1.x, b1.y))), make_float2(bf16_lo(s8.z), bf16_hi(s8.z))));
+                        MMF_SET2(v, 8 * u + 6, f2add(leaky_relu2(f2add(MMF_V2(v, 8 * u + 6), make_float2(b1.z, b1.w))), make_float2(bf16_lo(s8.w), bf16_hi(s8.w))));
                     }
                     if (!last) {
                         tmem_st32(taddr + col0, v);

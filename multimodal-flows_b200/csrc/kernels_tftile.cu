@@ -341,7 +341,8 @@ __device__ __forceinline__ void v_epilogue(Epi& e, const float* bv) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
         const float4 b = ldf4(bv + e.hf * 32 + i);
-        w[i] += b.x; w[i + 1] += b.y; w[i + 2] += b.z; w[i + 3] += b.w;
+        MMF_SET2(w, i, f2add(MMF_V2(w, i), make_float2(b.x, b.y)));
+        MMF_SET2(w, i + 2, f2add(MMF_V2(w, i + 2), make_float2(b.z, b.w)));
     }
     uint8_t* vb = e.arena + oVT;
 #pragma unroll
@@ -439,11 +440,13 @@ __device__ __forceinline__ void o_epilogue(Epi& e, uint32_t ocol, int ucol, int 
     tmem_ld_wait();
     const uint32_t u0 = (ucol + e.hf * W) >> 3;
     uint8_t* os = e.arena + oO;
+    // (the products below are written o[i] * inv: the compiler does not pair them, so scale the row with packed multiplies first)
+#pragma unroll
+    for (int i = 0; i < W; i += 2) MMF_SET2(o, i, f2mul(MMF_V2(o, i), f2dup(inv)));
 #pragma unroll
     for (int u = 0; u < W / 8; ++u)
-        st_shared_v4(os + sw128_offset(e.r, u0 + u), pack_bf16x2(o[8 * u] * inv, o[8 * u + 1] * inv),
-                     pack_bf16x2(o[8 * u + 2] * inv, o[8 * u + 3] * inv), pack_bf16x2(o[8 * u + 4] * inv, o[8 * u + 5] * inv),
-                     pack_bf16x2(o[8 * u + 6] * inv, o[8 * u + 7] * inv));
+        st_shared_v4(os + sw128_offset(e.r, u0 + u), pack_bf16x2(o[8 * u], o[8 * u + 1]), pack_bf16x2(o[8 * u + 2], o[8 * u + 3]),
+                     pack_bf16x2(o[8 * u + 4], o[8 * u + 5]), pack_bf16x2(o[8 * u + 6], o[8 * u + 7]));
 }
 
 // MLP hidden quarter q in scratch half (q&1): GELU(acc + bias) -> bf16 H(q&1); `bias` points at the quarter's 128 values
@@ -473,19 +476,20 @@ __device__ __forceinline__ void head_epilogue(Epi& e, int q, const float* bias, 
 #pragma unroll
     for (int i = 0; i < 64; i += 4) {
         const float4 a = ldf4(bias + e.hf * 64 + i);
-        v[i] = gelu_tile(v[i] + a.x); v[i + 1] = gelu_tile(v[i + 1] + a.y);
-        v[i + 2] = gelu_tile(v[i + 2] + a.z); v[i + 3] = gelu_tile(v[i + 3] + a.w);
+        MMF_SET2(v, i, gelu_tile2(f2add(MMF_V2(v, i), make_float2(a.x, a.y))));
+        MMF_SET2(v, i + 2, gelu_tile2(f2add(MMF_V2(v, i + 2), make_float2(a.z, a.w))));
     }
 #pragma unroll
     for (int o = 0; o < NO; ++o) {
         const float* w = w2 + o * ld + e.hf * 64;
-        float acc = out[o];
+        float2 acc = f2dup(0.f);                              // even / odd hidden units, packed
 #pragma unroll
         for (int i = 0; i < 64; i += 4) {
             const float4 a = ldf4(w + i);
-            acc = fmaf(a.x, v[i], fmaf(a.y, v[i + 1], fmaf(a.z, v[i + 2], fmaf(a.w, v[i + 3], acc))));
+            acc = f2fma(make_float2(a.x, a.y), MMF_V2(v, i), acc);
+            acc = f2fma(make_float2(a.z, a.w), MMF_V2(v, i + 2), acc);
         }
-        out[o] = acc;
+        out[o] += acc.x + acc.y;
     }
 }
 

@@ -97,5 +97,10 @@ __device__ __forceinline__ void stage_row_f32(uint8_t* chunk, int r, const float
 }
 
 __device__ __forceinline__ float leaky_relu(float x) { return x > 0.f ? x : 0.01f * x; }   // F.leaky_relu default slope
+// the same on a pair: max(x, 0.01 x) equals the select for every finite x (one packed multiply + two FMNMX)
+__device__ __forceinline__ float2 leaky_relu2(float2 x) {
+    const float2 y = f2mul(x, f2dup(0.01f));
+    return make_float2(fmaxf(x.x, y.x), fmaxf(x.y, y.y));
+}
 
 }  // namespace mmf
