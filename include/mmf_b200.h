@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define MMF_ABI_VERSION 1
+#define MMF_ABI_VERSION 2
 
 typedef struct MmfModel MmfModel;
 
@@ -77,6 +77,7 @@ typedef struct MmfStepOptions {
     int32_t top_k;              /* <= 0: off */
     float top_p;                /* <= 0: off */
     int32_t use_final_max_rates;
+    int32_t method;             /* mmf_hybrid_step only: 0 tau-leap (model/solvers.py:22-60), 1 categorical Euler (:62-91) */
     uint64_t seed;              /* Philox key when no uniforms are supplied */
     uint64_t first_global_jet;  /* global index of jet 0 of this call: draws depend on (seed, global slot, step) only */
 } MmfStepOptions;
@@ -92,16 +93,24 @@ int mmf_model_create(const MmfModelDesc* desc, const MmfWeightRef* weights, int3
 void mmf_model_destroy(MmfModel* model);
 
 /* One encoder forward.  Device pointers.  t is per jet.  logits_out may be NULL for EPiC (k is ignored then).
- * Synchronises once internally (multiplicities are read back to plan the packed layout). */
+ * Synchronises internally (mask and times are read back to plan the packed layout; the token flag at the end). */
 int mmf_encoder_forward(MmfModel* model, const float* x, const int64_t* k, const int64_t* mask, const float* t,
                         int32_t B, int32_t D, float* vt_out, float* logits_out, void* stream);
 
-/* The fused hybrid step on device tensors, in place on x and k: Euler update of x, telegraph tau-leap of k.
+/* The fused hybrid step on device tensors, in place on x and k: Euler update of x, telegraph tau-leap of k
+ * (opts->method 0) or the categorical Euler jump of HybridSolver.euler_step (opts->method 1, model/solvers.py:62-91:
+ * k' ~ Categorical(dp), dp_v = min(rate_v dt, 1) off the diagonal, dp_k = max(1 - sum, 0), filters on dp; it consumes
+ * u[..., 0] only, by inverse CDF in channel order).
  * u: (B,D,V) uniforms in [0,1) or NULL (Philox from opts->seed, opts->first_global_jet, step_index).
  * rates_out: (B,D,V) or NULL.  No model handle needed; `device` selects the GPU. */
 int mmf_hybrid_step(const float* vt, const float* logits, float* x, int64_t* k, const float* t, float dt,
                     const MmfStepOptions* opts, const float* u, uint32_t step_index, int32_t B, int32_t D,
                     int32_t V, float* rates_out, int32_t device, void* stream);
+
+/* The reference asserts 0 <= k < V before every rate evaluation (model/MJB.py:177-182, two host synchronisations per
+ * step).  mmf_hybrid_step instead clamps an out-of-range token to 0 and raises a per-device flag; this call waits for
+ * `stream`, returns 3 (message in mmf_last_error) when the flag was raised since the last query, and clears it. */
+int mmf_hybrid_step_status(int32_t device, void* stream);
 
 /* x += vt * dt on n floats (EPiC / ContinuousSolver carrier). */
 int mmf_euler_step(const float* vt, float* x, float dt, int64_t n, int32_t device, void* stream);
@@ -121,6 +130,21 @@ int mmf_jet_observables(const float* x, const int64_t* k, const int64_t* mask, c
                         int32_t B, int32_t D, int32_t V, float* kin_out, int32_t* counts_out, int32_t device,
                         void* stream);
 
+/* The generated sample as one narrow record per jet - the device-side half of FlowGeneratorCallback:
+ *   utils/callbacks.py:52-56   sample.continuous = sample.continuous * std + mean     (mean, std: HOST float[3], NULL = identity)
+ *   utils/callbacks.py:57      sample.apply_mask()                                    (padded slots zeroed)
+ * fused with the narrowing of the int64 token / mask tensors to one byte per slot.  Record of jet b, R =
+ * mmf_sample_record_bytes(D) = round_up(13 D, 16) bytes:  [D][3] f32 kinematics | [D] u8 (token | mask << 7) | zero padding.
+ * The records of a rank's shard are what the single end-of-run collective moves (utils/callbacks.py:27-58 writes one temp
+ * file per rank and re-reads them on rank 0) and what mmf_b200.writer lays out as generated_sample.h5.
+ * x (B,D,3) f32, k (B,D) i64 or NULL (EPiC), mask (B,D) i64; records: B * R bytes (device).  mmf_unpack_sample is the inverse
+ * (k / mask may be NULL), producing the reference's dtypes again. */
+int64_t mmf_sample_record_bytes(int32_t D);
+int mmf_pack_sample(const float* x, const int64_t* k, const int64_t* mask, const float* mean, const float* std_, int64_t B,
+                    int32_t D, uint8_t* records, int32_t device, void* stream);
+int mmf_unpack_sample(const uint8_t* records, int64_t B, int32_t D, float* x, int64_t* k, int64_t* mask, int32_t device,
+                      void* stream);
+
 /* The source state of the sampler, built on the device (no host RNG, no H2D copy of the batch):
  *   scripts/sample_mmf.py:82-84   noise_continuous = randn * pad_mask, noise_discrete = randint(1, vocab_size) * pad_mask
  *   utils/aoj.py:875-890          sample_from_empirical_masks: multiplicity ~ Categorical(histogram), prefix masks
@@ -139,15 +163,30 @@ int mmf_make_source(const float* mult_probs, int32_t B, int32_t D, int32_t V, ui
  *   u           device (N,B,D,V) supplied uniforms or NULL
  *   forced_k    device (N,B,D) uint8 teacher-forced tokens applied after each step, or NULL
  *   rates_out   device (B,D,V) rates of the last step, or NULL
- * k0 / k_out / opts may be NULL for EPiC.  x_out may alias x0, k_out may alias k0. */
+ * k0 / k_out / opts may be NULL for EPiC.  x_out may alias x0, k_out may alias k0.
+ * Synchronises twice: the mask is copied to the host to plan the tiles (use mmf_generate_n to avoid it), and the
+ * out-of-range-token flag is read back at the end (status 3, the reference's assert of model/MJB.py:177-182). */
 int mmf_generate(MmfModel* model, const float* x0, const int64_t* k0, const int64_t* mask, int32_t B, int32_t D,
                  const float* t_grid, int32_t N, float dt, const MmfStepOptions* opts, const float* u,
                  const uint8_t* forced_k, float* x_out, int64_t* k_out, float* rates_out, void* stream);
 
-/* Same with HOST buffers: stages inputs to the device, runs, copies results back and waits. */
+/* Fully asynchronous form of mmf_generate for the reference's prefix masks (utils/aoj.py:882-883: mask[i, :n_i] = 1):
+ * n_per_jet is a HOST array of the B multiplicities, so nothing is copied back and the host never waits - the per-call
+ * tables travel through pinned memory and the call returns as soon as the kernel is queued on `stream`.  Out-of-range
+ * tokens are reported by mmf_model_status, not by this call. */
+int mmf_generate_n(MmfModel* model, const float* x0, const int64_t* k0, const int32_t* n_per_jet, int32_t B, int32_t D,
+                   const float* t_grid, int32_t N, float dt, const MmfStepOptions* opts, const float* u,
+                   const uint8_t* forced_k, float* x_out, int64_t* k_out, float* rates_out, void* stream);
+
+/* Waits for `stream` and returns 3 (message in mmf_last_error) if a kernel of this handle met a token outside
+ * [0, vocab_size) since the last query (reference model/MJB.py:177-182); clears the flag. */
+int mmf_model_status(MmfModel* model, void* stream);
+
+/* mmf_generate with HOST buffers (pinned or pageable): stages inputs to the device on `stream`, runs, copies the results
+ * back and waits for `stream` (the results are on the host when it returns). */
 int mmf_generate_host(MmfModel* model, const float* x0, const int64_t* k0, const int64_t* mask, int32_t B, int32_t D,
                       const float* t_grid, int32_t N, float dt, const MmfStepOptions* opts, float* x_out,
-                      int64_t* k_out);
+                      int64_t* k_out, void* stream);
 
 /* Number of kernels this handle has launched so far (bench.py reports it as gpu_launches). */
 int64_t mmf_launch_count(const MmfModel* model);

@@ -23,7 +23,9 @@ struct EpicModel {
     float *d_xs0 = nullptr, *d_skip = nullptr, *d_tbias = nullptr, *d_temb = nullptr;
     int* d_row_slot = nullptr;
     int64_t launches = 0;
+    PinnedStage stage;                                   // per-call tables on their way to the device
     ~EpicModel() {
+        stage.release();
         arena.release();
         if (ws) cudaFree(ws);
     }
@@ -191,10 +193,11 @@ int run(EpicModel* m, const float* x, const int64_t* mask_host, int B, int D, co
     }
     std::vector<float> temb(static_cast<size_t>(n_times) * 256);
     for (int i = 0; i < n_times; ++i) sincos_row(times[i], 256, &temb[static_cast<size_t>(i) * 256]);
-    MMF_CUDA_OK(cudaMemcpyAsync(m->d_temb, temb.data(), temb.size() * 4, cudaMemcpyHostToDevice, s));
-    MMF_CUDA_OK(cudaMemcpyAsync(m->d_meta, plan.meta.data(), plan.meta.size() * sizeof(EpicTileMeta), cudaMemcpyHostToDevice, s));
-    MMF_CUDA_OK(cudaMemcpyAsync(m->d_row_slot, plan.row_slot.data(), plan.row_slot.size() * 4, cudaMemcpyHostToDevice, s));
-    MMF_CUDA_OK(cudaStreamSynchronize(s));           // the host vectors above go out of scope
+    MMF_TRY_RC(m->stage.begin(temb.size() * 4 + plan.meta.size() * sizeof(EpicTileMeta) + plan.row_slot.size() * 4 + 64));
+    MMF_TRY_RC(m->stage.push(m->d_temb, temb.data(), temb.size() * 4, s));
+    MMF_TRY_RC(m->stage.push(m->d_meta, plan.meta.data(), plan.meta.size() * sizeof(EpicTileMeta), s));
+    MMF_TRY_RC(m->stage.push(m->d_row_slot, plan.row_slot.data(), plan.row_slot.size() * 4, s));
+    MMF_TRY_RC(m->stage.end(s));                     // pinned staging: no host synchronisation
     MMF_TRY_RC(launch_epic_time_bias(m->fold, m->d_temb, n_times, m->d_tbias, s));
     MMF_TRY_RC(launch_pack(x, nullptr, m->d_row_slot, tiles * 128, 0, m->d_xs0, nullptr, nullptr, s));
     MMF_CUDA_OK(cudaMemsetAsync(out, 0, static_cast<size_t>(B) * D * 3 * 4, s));     // after the pack: x_out may alias x0

@@ -587,10 +587,12 @@ int epic_smem_bytes() { return kSmemBytes; }
 
 int launch_epic_tiles(const EpicLaunch& a, int n_tiles, int cluster, cudaStream_t stream) {
     if (n_tiles == 0) return 0;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};                 // the attribute is per device
+    int dev = 0;
+    MMF_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         MMF_CUDA_OK(cudaFuncSetAttribute(epic_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_tiles);

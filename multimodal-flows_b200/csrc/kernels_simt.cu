@@ -101,7 +101,8 @@ hybrid_step_kernel(const float* __restrict__ vt, const float* __restrict__ logit
             } else {
                 philox_uniforms(sl.seed, sl.slot0 + static_cast<uint64_t>(i), sl.step, V, u);
             }
-            kn = step_particle<V, false>(lg, static_cast<int>(kc), w, coef, sl.sp, u, rates_out ? rates : nullptr);
+            kn = sl.sp.method == 1 ? step_particle_euler<V>(lg, static_cast<int>(kc), w, coef, sl.sp, u[0], rates_out ? rates : nullptr)
+                                   : step_particle<V, false>(lg, static_cast<int>(kc), w, coef, sl.sp, u, rates_out ? rates : nullptr);
         }
         k[i] = kn;
 #pragma unroll
@@ -540,6 +541,49 @@ __global__ void unpack_kernel(const float* __restrict__ xs, const int* __restric
     if (k_out) k_out[s] = ks[r];
 }
 
+// ---------------------------------------------------------------------------------------------
+// 2b. the generated sample as ONE narrow record per jet: what FlowGeneratorCallback does on the host after the run
+//     (reference utils/callbacks.py:52-57: continuous * std + mean, then apply_mask) fused with the narrowing of the int64
+//     token / mask tensors to one byte per slot.  Record of jet b (R = round_up(13 D, 16) bytes):
+//         [D][3] fp32 de-standardised kinematics, zero at padded slots | [D] uint8 token | mask << 7 | zero padding
+//     The records of a shard are what the single end-of-run collective moves (13 B instead of 28 B per slot) and what the
+//     writer lays out as generated_sample.h5.  HBM: 28 B read + 13 B written per slot.
+// ---------------------------------------------------------------------------------------------
+struct SampleNorm { float mean[3], std[3]; };
+
+__global__ void sample_pack_kernel(const float* __restrict__ x, const long long* __restrict__ k, const long long* __restrict__ mask,
+                                   SampleNorm nm, long long slots, int D, int rec_bytes, unsigned char* __restrict__ rec) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= slots) return;
+    const long long b = i / D;
+    const int d = static_cast<int>(i - b * D);
+    const bool real = mask[i] != 0;
+    unsigned char* r = rec + b * rec_bytes;
+    float* xo = reinterpret_cast<float*>(r) + d * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) xo[c] = real ? det_add(det_mul(x[i * 3 + c], nm.std[c]), nm.mean[c]) : 0.0f;
+    const int tok = (k != nullptr && real) ? static_cast<int>(k[i]) & 0x7f : 0;
+    r[D * 12 + d] = static_cast<unsigned char>(tok | (real ? 0x80 : 0));
+    if (d == 0) {                                         // the record's tail padding
+        for (int j = D * 13; j < rec_bytes; ++j) r[j] = 0;
+    }
+}
+
+__global__ void sample_unpack_kernel(const unsigned char* __restrict__ rec, long long slots, int D, int rec_bytes,
+                                     float* __restrict__ x, long long* __restrict__ k, long long* __restrict__ mask) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= slots) return;
+    const long long b = i / D;
+    const int d = static_cast<int>(i - b * D);
+    const unsigned char* r = rec + b * rec_bytes;
+    const float* xi = reinterpret_cast<const float*>(r) + d * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) x[i * 3 + c] = xi[c];
+    const unsigned char kb = r[D * 12 + d];
+    if (k) k[i] = kb & 0x7f;
+    if (mask) mask[i] = kb >> 7;
+}
+
 __global__ void force_tokens_kernel(const unsigned char* __restrict__ forced, const int* __restrict__ row_slot,
                                     int rows, int* __restrict__ ks) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -730,7 +774,7 @@ head_out_kernel(HeadOutArgs a) {
                 } else {
                     philox_uniforms(a.sl.seed, a.sl.slot0 + static_cast<uint64_t>(slot), a.sl.step, V, u);
                 }
-                const int kn = step_particle<V>(acc + 3, a.ks[row], a.w, a.coef, a.sl.sp, u, a.rates_out ? rates : nullptr);
+                const int kn = step_particle<V>(acc + 3, a.ks[row], a.w, a.coef, a.sl.sp, u, (a.rates_out || a.argmax_out) ? rates : nullptr);
                 a.ks[row] = a.forced ? static_cast<int>(a.forced[slot]) : kn;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) a.xs[row * 3 + c] = euler_update(a.xs[row * 3 + c], acc[c], a.sl.sp.dt);
@@ -752,10 +796,12 @@ head_out_kernel(HeadOutArgs a) {
 template <int V>
 int launch_head_out_t(const HeadOutArgs& a, cudaStream_t stream) {
     const int smem = ((3 + V) * 512 + (3 + V)) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};                 // the attribute is per device
+    int dev = 0;
+    MMF_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         MMF_CUDA_OK(cudaFuncSetAttribute(head_out_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     int blocks = (a.rows + 7) / 8;
     if (blocks > 148 * 4) blocks = 148 * 4;
@@ -823,7 +869,7 @@ int launch_hybrid_step(const float* vt, const float* logits, float* x, long long
     // production mode (Philox draws, no rates) runs the MUFU arithmetic; MMF_STEP_EXACT=1 forces the reproducible one
     const char* fe = getenv("MMF_STEP_EXACT");
     const bool force_exact = fe != nullptr && atoi(fe) != 0;
-    if (sl.u == nullptr && rates_out == nullptr && !force_exact) {
+    if (sl.u == nullptr && rates_out == nullptr && !force_exact && sl.sp.method == 0) {
         MMF_DISPATCH_V(sl.sp.vocab, return launch_step_prod<VV>(vt, logits, x, k, t, n, D, sl, stream));
     } else {
         MMF_DISPATCH_V(sl.sp.vocab, (hybrid_step_kernel<VV, false><<<blocks, kStepThreads, 0, stream>>>(vt, logits, x, k, t, n, D, sl, rates_out)));
@@ -869,6 +915,27 @@ int launch_unpack(const float* xs, const int* ks, const int* row_slot, int rows,
                   cudaStream_t stream) {
     if (rows == 0) return 0;
     unpack_kernel<<<(rows + 255) / 256, 256, 0, stream>>>(xs, ks, row_slot, rows, x_out, k_out);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int sample_record_bytes(int D) { return (D * 13 + 15) / 16 * 16; }
+
+int launch_sample_pack(const float* x, const long long* k, const long long* mask, const float* mean, const float* std_, long long B,
+                       int D, unsigned char* rec, cudaStream_t stream) {
+    const long long slots = B * D;
+    if (slots == 0) return 0;
+    SampleNorm nm;
+    for (int c = 0; c < 3; ++c) { nm.mean[c] = mean ? mean[c] : 0.0f; nm.std[c] = std_ ? std_[c] : 1.0f; }
+    sample_pack_kernel<<<static_cast<unsigned>((slots + 255) / 256), 256, 0, stream>>>(x, k, mask, nm, slots, D, sample_record_bytes(D), rec);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_sample_unpack(const unsigned char* rec, long long B, int D, float* x, long long* k, long long* mask, cudaStream_t stream) {
+    const long long slots = B * D;
+    if (slots == 0) return 0;
+    sample_unpack_kernel<<<static_cast<unsigned>((slots + 255) / 256), 256, 0, stream>>>(rec, slots, D, sample_record_bytes(D), x, k, mask);
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -311,10 +311,12 @@ int launch_gemm_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
                   const GemmArgs& args, int m_tiles, int n_tiles, int groups, cudaStream_t stream) {
     const int stages = args.kblocks < (BN == 128 ? 3 : 2) ? args.kblocks : (BN == 128 ? 3 : 2);
     const int smem = gemm_smem_bytes(EPI, BN, args.kblocks);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};                 // the attribute is per device
+    int dev = 0;
+    MMF_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         MMF_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     gemm_kernel<BN, EPI><<<dim3(m_tiles, n_tiles, groups), 192, smem, stream>>>(tmA, tmB, tmOut0, tmOut1, args, stages);
     MMF_CUDA_OK(cudaGetLastError());
@@ -515,10 +517,12 @@ int launch_gemm(int epilogue, int BN, const CUtensorMap& tmA, const CUtensorMap&
 int launch_attention(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmVT, const AttnArgs& args,
                      int n_items, int n_slabs, cudaStream_t stream) {
     MMF_REQUIRE(args.hs == 32 || args.hs == 64, "attention: head size must be 32 or 64");
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};                 // the attribute is per device
+    int dev = 0;
+    MMF_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         MMF_CUDA_OK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     if (n_items == 0) return 0;
     attn_kernel<<<dim3(n_items, n_slabs), 128, kAttnSmem, stream>>>(tmQ, tmK, tmVT, args);

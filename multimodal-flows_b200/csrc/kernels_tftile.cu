@@ -1034,10 +1034,12 @@ int launch_tf_tiles(const TfLaunch& a, int n_tiles, int cluster, cudaStream_t st
     if (n_tiles == 0) return 0;
     MMF_REQUIRE(a.vocab == 9, "the tile kernel is instantiated for vocab_size 9");
     MMF_REQUIRE((cluster == 1 || cluster == 2 || cluster == 4) && n_tiles % cluster == 0, "tile launch: bad cluster size");
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};                 // the attribute is per device
+    int dev = 0;
+    MMF_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
         MMF_CUDA_OK(cudaFuncSetAttribute(tf_tile_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_tiles);

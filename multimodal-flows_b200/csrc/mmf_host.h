@@ -64,6 +64,49 @@ struct DeviceArena {            // one allocation, bump sub-allocation, 256-byte
     void release() { if (base) cudaFree(base); base = nullptr; }
 };
 
+// Pinned staging for the small per-call tables (tile plans, time tables): the H2D copies are truly asynchronous and the
+// host vectors they came from may go out of scope at once.  One buffer per owner; a call first waits (host side) until the
+// copies of the previous call have left the buffer - they are queued ahead of that call's kernel, so in steady state the
+// wait returns immediately and the entry points never synchronise with running kernels.
+struct PinnedStage {
+    uint8_t* base = nullptr;
+    size_t cap = 0, used = 0;
+    cudaEvent_t ev = nullptr;
+    bool pending = false;
+    int begin(size_t bytes) {
+        if (pending) { MMF_CUDA_OK(cudaEventSynchronize(ev)); pending = false; }
+        if (!ev) MMF_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        if (bytes > cap) {
+            if (base) MMF_CUDA_OK(cudaFreeHost(base));
+            base = nullptr;
+            cap = bytes + bytes / 4 + 4096;
+            MMF_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&base), cap, cudaHostAllocDefault));
+        }
+        used = 0;
+        return 0;
+    }
+    // copies `bytes` from src into the stage and queues the H2D copy to dst on `s`
+    int push(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+        if (bytes == 0) return 0;
+        const size_t off = (used + 15) / 16 * 16;
+        if (off + bytes > cap) { set_last_error("pinned stage overflow"); return 2; }
+        memcpy(base + off, src, bytes);
+        used = off + bytes;
+        MMF_CUDA_OK(cudaMemcpyAsync(dst, base + off, bytes, cudaMemcpyHostToDevice, s));
+        return 0;
+    }
+    int end(cudaStream_t s) {
+        MMF_CUDA_OK(cudaEventRecord(ev, s));
+        pending = true;
+        return 0;
+    }
+    void release() {
+        if (ev) { cudaEventSynchronize(ev); cudaEventDestroy(ev); ev = nullptr; }
+        if (base) cudaFreeHost(base);
+        base = nullptr;
+    }
+};
+
 struct WeightMap {
     std::unordered_map<std::string, const MmfWeightRef*> m;
     std::string missing;

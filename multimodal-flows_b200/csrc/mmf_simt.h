@@ -57,6 +57,10 @@ int launch_pack(const float* x0, const long long* k0, const int* row_slot, int r
                 int* err_flag, cudaStream_t stream);
 int launch_unpack(const float* xs, const int* ks, const int* row_slot, int rows, float* x_out, long long* k_out,
                   cudaStream_t stream);
+int sample_record_bytes(int D);
+int launch_sample_pack(const float* x, const long long* k, const long long* mask, const float* mean, const float* std_, long long B,
+                       int D, unsigned char* rec, cudaStream_t stream);
+int launch_sample_unpack(const unsigned char* rec, long long B, int D, float* x, long long* k, long long* mask, cudaStream_t stream);
 int launch_force_tokens(const unsigned char* forced, const int* row_slot, int rows, int* ks, cudaStream_t stream);
 int launch_embed_x(const float* xs, int rows, const float* w0, const float* b0, int E, int apply_gelu, bf16* out,
                    int ld_out, cudaStream_t stream);

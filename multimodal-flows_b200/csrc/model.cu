@@ -555,6 +555,7 @@ int generate_device(MmfModel* m, const float* x0, const int64_t* k0, const int64
     MMF_REQUIRE(N >= 1 && B >= 1 && D >= 1 && D <= d.max_num_particles, "bad problem shape");
     if (d.arch == MMF_ARCH_EPIC) return epic_generate(m->epic, x0, mask_host, B, D, t_grid, N, dt, x_out, s);
     MMF_REQUIRE(opts != nullptr && k0 != nullptr && k_out != nullptr, "the transformers need tokens and step options");
+    MMF_REQUIRE(opts->method == 0, "the sampler loop uses the tau-leap step (hard-coded in the reference, model/solvers.py:9)");
     const size_t slots = static_cast<size_t>(B) * D;
     // jets of <= 128 particles run in the persistent tile kernel; the layered path below takes what is left
     std::vector<int64_t> rest;
@@ -760,22 +761,49 @@ int mmf_encoder_forward(MmfModel* m, const float* x, const int64_t* k, const int
     return check_device_flags(m, s);
 }
 
+// out-of-range-token flag of the standalone step, one per device (the step has no model handle to hang it on)
+static int* g_step_flag[64] = {nullptr};
+static int step_flag(int device, int** out) {
+    MMF_REQUIRE(device >= 0 && device < 64, "device index out of range");
+    if (!g_step_flag[device]) {
+        MMF_CUDA_OK(cudaMalloc(&g_step_flag[device], sizeof(int)));
+        MMF_CUDA_OK(cudaMemset(g_step_flag[device], 0, sizeof(int)));
+    }
+    *out = g_step_flag[device];
+    return 0;
+}
+
+int mmf_hybrid_step_status(int32_t device, void* stream) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    MMF_CUDA_OK(cudaSetDevice(device));
+    int* d = nullptr;
+    MMF_TRY(step_flag(device, &d));
+    int flag = 0;
+    MMF_CUDA_OK(cudaMemcpyAsync(&flag, d, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MMF_CUDA_OK(cudaStreamSynchronize(s));
+    if (flag) {
+        MMF_CUDA_OK(cudaMemsetAsync(d, 0, sizeof(int), s));
+        set_last_error("Values in `k` outside of bound [0, vocab_size)");      // reference model/MJB.py:177-182
+        return 3;
+    }
+    return 0;
+}
+
 int mmf_hybrid_step(const float* vt, const float* logits, float* x, int64_t* k, const float* t, float dt,
                     const MmfStepOptions* opts, const float* u, uint32_t step_index, int32_t B, int32_t D, int32_t V,
                     float* rates_out, int32_t device, void* stream) {
     MMF_REQUIRE(vt && logits && x && k && t && opts, "null argument");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     MMF_CUDA_OK(cudaSetDevice(device));
-    static thread_local int* d_flag[16] = {nullptr};
-    MMF_REQUIRE(device >= 0 && device < 16, "device index out of range");
-    if (!d_flag[device]) {
-        MMF_CUDA_OK(cudaMalloc(&d_flag[device], sizeof(int)));
-        MMF_CUDA_OK(cudaMemset(d_flag[device], 0, sizeof(int)));
-    }
+    int* d_flag_dev = nullptr;
+    MMF_TRY(step_flag(device, &d_flag_dev));
+    MMF_REQUIRE(opts->method == 0 || opts->method == 1, "MmfStepOptions.method must be 0 (tau-leap) or 1 (categorical Euler)");
+    MMF_REQUIRE(opts->method == 0 || opts->temperature == 1.0f,
+                "the categorical Euler step is defined for temperature 1 only (reference solvers.py:95-99 rescales per class for a fixed batch shape)");
     StepLaunch sl{};
-    sl.sp = StepParams{opts->temperature, dt, opts->beta, opts->top_p, opts->top_k, V};
+    sl.sp = StepParams{opts->temperature, dt, opts->beta, opts->top_p, opts->top_k, V, opts->method};
     sl.u = u; sl.seed = opts->seed; sl.slot0 = opts->first_global_jet * static_cast<uint64_t>(D); sl.step = step_index;
-    sl.err_flag = d_flag[device];
+    sl.err_flag = d_flag_dev;
     return launch_hybrid_step(vt, logits, x, reinterpret_cast<long long*>(k), t, B, D, sl, rates_out, s);
 }
 
@@ -802,8 +830,9 @@ int mmf_jet_observables(const float* x, const int64_t* k, const int64_t* mask, c
 
 int mmf_make_source(const float* mult_probs, int32_t B, int32_t D, int32_t V, uint64_t seed, uint64_t first_global_jet, float* x0,
                     int64_t* k0, int64_t* mask, int32_t* n_out, int32_t device, void* stream) {
-    MMF_REQUIRE(mult_probs && x0 && mask && n_out, "null argument");
     MMF_REQUIRE(B >= 0 && D >= 1 && D <= kSrcMaxD, "max_num_particles must be in [1, 255]");
+    if (B == 0) return 0;                                 // an empty shard (more ranks than jets): nothing to draw
+    MMF_REQUIRE(mult_probs && x0 && mask && n_out, "null argument");
     MMF_REQUIRE(k0 == nullptr || V >= 2, "vocab_size must be at least 2 when tokens are requested");
     double tot = 0.0;
     for (int m = 0; m <= D; ++m) {
@@ -824,6 +853,27 @@ int mmf_make_source(const float* mult_probs, int32_t B, int32_t D, int32_t V, ui
                               static_cast<cudaStream_t>(stream));
 }
 
+int64_t mmf_sample_record_bytes(int32_t D) { return D >= 1 ? sample_record_bytes(D) : 0; }
+
+int mmf_pack_sample(const float* x, const int64_t* k, const int64_t* mask, const float* mean, const float* std_, int64_t B,
+                    int32_t D, uint8_t* records, int32_t device, void* stream) {
+    MMF_REQUIRE(B >= 0 && D >= 1, "bad sample shape");
+    if (B == 0) return 0;
+    MMF_REQUIRE(x && mask && records, "null argument");
+    MMF_CUDA_OK(cudaSetDevice(device));
+    return launch_sample_pack(x, reinterpret_cast<const long long*>(k), reinterpret_cast<const long long*>(mask), mean, std_, B, D,
+                              records, static_cast<cudaStream_t>(stream));
+}
+
+int mmf_unpack_sample(const uint8_t* records, int64_t B, int32_t D, float* x, int64_t* k, int64_t* mask, int32_t device, void* stream) {
+    MMF_REQUIRE(B >= 0 && D >= 1, "bad sample shape");
+    if (B == 0) return 0;
+    MMF_REQUIRE(records && x, "null argument");
+    MMF_CUDA_OK(cudaSetDevice(device));
+    return launch_sample_unpack(records, B, D, x, reinterpret_cast<long long*>(k), reinterpret_cast<long long*>(mask),
+                                static_cast<cudaStream_t>(stream));
+}
+
 int mmf_generate(MmfModel* m, const float* x0, const int64_t* k0, const int64_t* mask, int32_t B, int32_t D,
                  const float* t_grid, int32_t N, float dt, const MmfStepOptions* opts, const float* u,
                  const uint8_t* forced_k, float* x_out, int64_t* k_out, float* rates_out, void* stream) {
@@ -836,11 +886,38 @@ int mmf_generate(MmfModel* m, const float* x0, const int64_t* k0, const int64_t*
     return check_device_flags(m, s);
 }
 
+static int prefix_mask_from_counts(const int32_t* n_per_jet, int B, int D, std::vector<int64_t>* hmask) {
+    hmask->assign(static_cast<size_t>(B) * D, 0);
+    for (int b = 0; b < B; ++b) {
+        MMF_REQUIRE(n_per_jet[b] >= 0 && n_per_jet[b] <= D, "n_per_jet out of [0, D]");
+        std::fill(hmask->begin() + static_cast<size_t>(b) * D, hmask->begin() + static_cast<size_t>(b) * D + n_per_jet[b], 1);
+    }
+    return 0;
+}
+
+int mmf_generate_n(MmfModel* m, const float* x0, const int64_t* k0, const int32_t* n_per_jet, int32_t B, int32_t D,
+                   const float* t_grid, int32_t N, float dt, const MmfStepOptions* opts, const float* u,
+                   const uint8_t* forced_k, float* x_out, int64_t* k_out, float* rates_out, void* stream) {
+    MMF_REQUIRE(m && x0 && n_per_jet && t_grid && x_out, "null argument");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    MMF_CUDA_OK(cudaSetDevice(m->device));
+    std::vector<int64_t> hmask;
+    MMF_TRY(prefix_mask_from_counts(n_per_jet, B, D, &hmask));
+    return generate_device(m, x0, k0, hmask.data(), B, D, t_grid, N, dt, opts, u, forced_k, x_out, k_out, rates_out, s);
+}
+
+int mmf_model_status(MmfModel* m, void* stream) {
+    MMF_REQUIRE(m != nullptr, "null model");
+    MMF_CUDA_OK(cudaSetDevice(m->device));
+    return check_device_flags(m, static_cast<cudaStream_t>(stream));
+}
+
 int mmf_generate_host(MmfModel* m, const float* x0, const int64_t* k0, const int64_t* mask, int32_t B, int32_t D,
-                      const float* t_grid, int32_t N, float dt, const MmfStepOptions* opts, float* x_out, int64_t* k_out) {
+                      const float* t_grid, int32_t N, float dt, const MmfStepOptions* opts, float* x_out, int64_t* k_out,
+                      void* stream) {
     MMF_REQUIRE(m && x0 && mask && t_grid && x_out, "null argument");
     MMF_CUDA_OK(cudaSetDevice(m->device));
-    cudaStream_t s = nullptr;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t slots = static_cast<size_t>(B) * D;
     const size_t need = slots * (3 * 4 + 8);
     Workspace& w = m->ws;

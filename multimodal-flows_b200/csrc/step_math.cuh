@@ -14,6 +14,7 @@ struct StepParams {
     float top_p;         // <= 0: off
     int top_k;           // <= 0: off
     int vocab;
+    int method;          // 0: tau-leap (reference solvers.py:22-60, the one the sampler uses); 1: categorical Euler (:62-91)
 };
 
 // Arithmetic policy.  EXACT (default): individually rounded IEEE ops and the polynomial det_expf, reproduced bit for bit by
@@ -143,6 +144,48 @@ __device__ __forceinline__ int step_particle(const float* logits, int k, float w
         single = (c == 1) ? v : single;
     }
     return (total == 1) ? single : k;
+}
+
+// HybridSolver.euler_step (reference model/solvers.py:62-91, T = 1): the categorical jump.  Off-diagonal transition
+// probabilities dp_v = min(rate_v dt, 1), diagonal dp_k = max(1 - sum_{v != k} dp_v, 0); top-k / top-p act on dp (not on the
+// softmax); k' ~ Categorical(dp), which normalises dp.  One uniform: k' = min{v : u sum(dp) < cum_v} (sequential sums,
+// falling back to the last channel with dp > 0).  `rates` (unfiltered softmax, as in the reference) is written when non-null.
+template <int V>
+__device__ __forceinline__ int step_particle_euler(const float* logits, int k, float w, float coef, const StepParams& sp,
+                                                   float u0, float* rates) {
+    using M = StepMath<false>;
+    float p[V], dp[V];
+    step_softmax<V, false>(logits, 1.0f, p);
+    float qk = p[0];
+#pragma unroll
+    for (int v = 1; v < V; ++v) qk = (k == v) ? p[v] : qk;
+    const float wq = M::mul(w, qk);
+    float s = 0.0f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const float rate = M::add(M::add(1.0f, M::mul(coef, p[v])), wq);
+        if (rates) rates[v] = rate;
+        const float d = fminf(M::mul(rate, sp.dt), 1.0f);
+        dp[v] = (v == k) ? 0.0f : d;
+        s = (v == 0) ? dp[0] : M::add(s, dp[v]);
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v) dp[v] = (v == k) ? fmaxf(M::add(1.0f, -s), 0.0f) : dp[v];
+    step_filters<V, false>(dp, sp.top_k, sp.top_p);
+    float cum[V];
+    float tot = 0.0f;
+    int last = 0;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        tot = (v == 0) ? dp[0] : M::add(tot, dp[v]);
+        cum[v] = tot;
+        last = dp[v] > 0.0f ? v : last;
+    }
+    const float target = M::mul(u0, tot);
+    int j = last;
+#pragma unroll
+    for (int v = V - 1; v >= 0; --v) j = (target < cum[v] && dp[v] > 0.0f) ? v : j;
+    return j;
 }
 
 // The same transition law from TWO uniforms: the V channel counts are independent Poisson(lam_v), so their

@@ -30,7 +30,9 @@ struct TfTileModel {
     TfLaunch pending{};                                  // prepared by tftile_prepare, consumed by tftile_launch
     int pending_tiles = 0;
     int cluster = 2;                                     // CTAs sharing one weight stream (MMF_TILE_CLUSTER = 1 | 2 | 4)
+    PinnedStage stage;                                   // per-call tables on their way to the device
     ~TfTileModel() {
+        stage.release();
         arena.release();
         if (ws) cudaFree(ws);
     }
@@ -512,11 +514,12 @@ int tftile_prepare(TfTileModel* m, const TfRunArgs& r, std::vector<unsigned char
         }
         if (r.opts) det_thermostat(r.times[i], r.opts->beta, d.vocab_size, &thermo[i * 2], &thermo[i * 2 + 1]);
     }
-    MMF_CUDA_OK(cudaMemcpyAsync(m->d_temb, temb.data(), temb.size() * 4, cudaMemcpyHostToDevice, s));
-    MMF_CUDA_OK(cudaMemcpyAsync(m->d_thermo, thermo.data(), thermo.size() * 4, cudaMemcpyHostToDevice, s));
-    MMF_CUDA_OK(cudaMemcpyAsync(m->d_meta, plan.meta.data(), plan.meta.size() * sizeof(TfTileMeta), cudaMemcpyHostToDevice, s));
-    MMF_CUDA_OK(cudaMemcpyAsync(m->d_row_slot, plan.row_slot.data(), plan.row_slot.size() * 4, cudaMemcpyHostToDevice, s));
-    MMF_CUDA_OK(cudaStreamSynchronize(s));
+    MMF_TRY_RC(m->stage.begin(temb.size() * 4 + thermo.size() * 4 + plan.meta.size() * sizeof(TfTileMeta) + plan.row_slot.size() * 4 + 64));
+    MMF_TRY_RC(m->stage.push(m->d_temb, temb.data(), temb.size() * 4, s));
+    MMF_TRY_RC(m->stage.push(m->d_thermo, thermo.data(), thermo.size() * 4, s));
+    MMF_TRY_RC(m->stage.push(m->d_meta, plan.meta.data(), plan.meta.size() * sizeof(TfTileMeta), s));
+    MMF_TRY_RC(m->stage.push(m->d_row_slot, plan.row_slot.data(), plan.row_slot.size() * 4, s));
+    MMF_TRY_RC(m->stage.end(s));                         // no host synchronisation: the tables travel through pinned memory
     MMF_TRY_RC(launch_pack(r.x0, r.k0, m->d_row_slot, tiles * 128, d.vocab_size, m->d_xs0, m->d_ks0, r.err_flag, s));
     m->launches += 1;
 

@@ -32,14 +32,16 @@ class MmfWeightRef(ctypes.Structure):
 
 class MmfStepOptions(ctypes.Structure):
     _fields_ = [("temperature", c_float), ("beta", c_float), ("top_k", c_int32), ("top_p", c_float),
-                ("use_final_max_rates", c_int32), ("seed", c_uint64), ("first_global_jet", c_uint64)]
+                ("use_final_max_rates", c_int32), ("method", c_int32), ("seed", c_uint64), ("first_global_jet", c_uint64)]
 
 
 _lib: Optional[ctypes.CDLL] = None
 
 EXPORTS = [
     "mmf_abi_version", "mmf_last_error", "mmf_model_create", "mmf_model_destroy", "mmf_encoder_forward",
-    "mmf_hybrid_step", "mmf_euler_step", "mmf_generate", "mmf_generate_host", "mmf_launch_count", "mmf_jet_observables", "mmf_make_source",
+    "mmf_hybrid_step", "mmf_hybrid_step_status", "mmf_euler_step", "mmf_generate", "mmf_generate_n", "mmf_model_status",
+    "mmf_generate_host", "mmf_launch_count", "mmf_jet_observables", "mmf_make_source",
+    "mmf_sample_record_bytes", "mmf_pack_sample", "mmf_unpack_sample",
     "mmf_dbg_gemm", "mmf_dbg_gemm_resln", "mmf_dbg_gemm_qkv", "mmf_dbg_attention", "mmf_dbg_ring_plan",
     "mmf_profile_enable", "mmf_profile_num_classes", "mmf_profile_class_name", "mmf_profile_read",
 ]
@@ -72,8 +74,15 @@ def lib() -> ctypes.CDLL:
                                   c_int32, c_void_p]
     L.mmf_generate.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_float,
                                POINTER(MmfStepOptions), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.mmf_sample_record_bytes.argtypes = [c_int32]
+    L.mmf_sample_record_bytes.restype = c_int64
+    L.mmf_pack_sample.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p]
+    L.mmf_unpack_sample.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
+    L.mmf_generate_n.argtypes = L.mmf_generate.argtypes
+    L.mmf_model_status.argtypes = [c_void_p, c_void_p]
+    L.mmf_hybrid_step_status.argtypes = [c_int32, c_void_p]
     L.mmf_generate_host.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32,
-                                    c_float, POINTER(MmfStepOptions), c_void_p, c_void_p]
+                                    c_float, POINTER(MmfStepOptions), c_void_p, c_void_p, c_void_p]
     L.mmf_dbg_gemm.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                c_int32, c_void_p]
     L.mmf_dbg_gemm_resln.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
@@ -88,10 +97,10 @@ def lib() -> ctypes.CDLL:
     L.mmf_profile_class_name.restype = c_char_p
     L.mmf_profile_read.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32]
     for name in EXPORTS:
-        if name not in ("mmf_last_error", "mmf_model_destroy", "mmf_launch_count", "mmf_abi_version",
+        if name not in ("mmf_last_error", "mmf_model_destroy", "mmf_launch_count", "mmf_abi_version", "mmf_sample_record_bytes",
                         "mmf_profile_num_classes", "mmf_profile_class_name"):
             getattr(L, name).restype = c_int32
-    if L.mmf_abi_version() != 1:
+    if L.mmf_abi_version() != 2:
         raise RuntimeError("libmmf_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -111,12 +120,12 @@ def stream_handle(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def step_options(cfg, seed: int = 0, first_global_jet: int = 0) -> MmfStepOptions:
+def step_options(cfg, seed: int = 0, first_global_jet: int = 0, method: int = 0) -> MmfStepOptions:
     return MmfStepOptions(
         temperature=float(cfg.temperature if cfg.temperature is not None else 1.0), beta=float(cfg.beta),
         top_k=int(cfg.top_k or 0), top_p=float(cfg.top_p or 0.0),
         use_final_max_rates=int(bool(getattr(cfg, "use_final_max_rates", False))),
-        seed=int(seed), first_global_jet=int(first_global_jet))
+        method=int(method), seed=int(seed), first_global_jet=int(first_global_jet))
 
 
 class NativeModel:
@@ -148,6 +157,7 @@ class NativeModel:
         self.handle = handle
         self.vocab_size = cfg.vocab_size
         self.is_epic = cfg.model == "EPiC"
+        self._pinned = {}                                 # cached pinned result buffers of generate_host, by shape
 
     def close(self) -> None:
         if getattr(self, "handle", None):
@@ -193,12 +203,24 @@ class NativeModel:
                                         B, D, ptr(vt), ptr(logits), stream_handle(self.device)))
         return vt, logits
 
+    def status(self) -> None:
+        """Waits for the current stream and raises if a kernel of this handle met a token outside [0, V)
+        (the reference's assert, model/MJB.py:177-182)."""
+        check(lib().mmf_model_status(self.handle, stream_handle(self.device)))
+
     def generate(self, x0, k0, mask, t_grid, dt, opts: Optional[MmfStepOptions], u=None, forced_k=None,
-                 want_rates=False):
+                 want_rates=False, n_per_jet=None):
+        """The N-step sampler on device tensors.  With ``n_per_jet`` (HOST int32 multiplicities of prefix masks,
+        reference utils/aoj.py:882-883) the call is fully asynchronous (``mmf_generate_n``; errors via ``status()``);
+        otherwise the device mask is read back to plan the tiles (``mmf_generate``, two host synchronisations)."""
         B, D = x0.shape[:2]
         N = int(t_grid.numel())
         x0 = x0.contiguous().float()
-        mask = mask.reshape(B, D).contiguous().long()
+        if n_per_jet is not None:
+            n_per_jet = torch.as_tensor(n_per_jet).to("cpu", torch.int32).contiguous()
+            assert n_per_jet.numel() == B
+        else:
+            mask = mask.reshape(B, D).contiguous().long()
         tg = t_grid.detach().to("cpu", torch.float32).contiguous()
         x_out = torch.empty_like(x0)
         k_out = rates = None
@@ -212,10 +234,11 @@ class NativeModel:
             assert u.shape == (N, B, D, self.vocab_size)
         if forced_k is not None:
             forced_k = forced_k.reshape(N, B, D).contiguous().to(torch.uint8)
-        check(lib().mmf_generate(self.handle, ptr(x0), ptr(k0) if not self.is_epic else None, ptr(mask), B, D,
-                                 tg.data_ptr(), N, float(dt), ctypes.byref(opts) if opts is not None else None,
-                                 ptr(u), ptr(forced_k), ptr(x_out), ptr(k_out), ptr(rates),
-                                 stream_handle(self.device)))
+        fn = lib().mmf_generate if n_per_jet is None else lib().mmf_generate_n
+        check(fn(self.handle, ptr(x0), ptr(k0) if not self.is_epic else None,
+                 ptr(mask) if n_per_jet is None else n_per_jet.data_ptr(), B, D,
+                 tg.data_ptr(), N, float(dt), ctypes.byref(opts) if opts is not None else None,
+                 ptr(u), ptr(forced_k), ptr(x_out), ptr(k_out), ptr(rates), stream_handle(self.device)))
         return x_out, k_out, rates
 
     def generate_host(self, x0, k0, mask, t_grid, dt, opts: Optional[MmfStepOptions]):
@@ -226,15 +249,18 @@ class NativeModel:
         x0 = x0.contiguous().float()
         mask = mask.reshape(B, D).contiguous().long()
         tg = t_grid.detach().to("cpu", torch.float32).contiguous()
-        x_out = torch.empty_like(x0).pin_memory()
-        k_out = None
+        # pinned result buffers are cached per batch shape (pinning costs more than the copy); the caller gets clones
+        key = (B, D)
+        if key not in self._pinned:
+            self._pinned[key] = (torch.empty(B, D, 3, dtype=torch.float32).pin_memory(),
+                                 None if self.is_epic else torch.empty(B, D, dtype=torch.int64).pin_memory())
+        px, pk = self._pinned[key]
         if not self.is_epic:
             k0 = k0.reshape(B, D).contiguous().long()
-            k_out = torch.empty_like(k0).pin_memory()
         check(lib().mmf_generate_host(self.handle, ptr(x0), ptr(k0) if not self.is_epic else None, ptr(mask), B, D,
                                       tg.data_ptr(), N, float(dt), ctypes.byref(opts) if opts is not None else None,
-                                      ptr(x_out), ptr(k_out)))
-        return x_out, k_out
+                                      ptr(px), ptr(pk), stream_handle(self.device)))
+        return px.clone(), None if pk is None else pk.clone()
 
 
 def hybrid_step(vt, logits, x, k, t, dt, opts: MmfStepOptions, u=None, step_index=0, want_rates=True):
@@ -254,11 +280,19 @@ def hybrid_step(vt, logits, x, k, t, dt, opts: MmfStepOptions, u=None, step_inde
     return rates
 
 
+def hybrid_step_status(device) -> None:
+    """Raises when ``hybrid_step`` met a token outside [0, V) on ``device`` since the last query (model/MJB.py:177-182)."""
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    check(lib().mmf_hybrid_step_status(idx, stream_handle(device)))
+
+
 def make_source(mult_probs, num_jets, max_num_particles, vocab_size, seed, first_global_jet, device, discrete=True):
     """Source state on the device: returns (x0 (B,D,3) f32, k0 (B,D) i64 or None, mask (B,D) i64, n (B,) i32).
     mult_probs: D+1 non-negative weights of multiplicity 0..D (host)."""
     device = torch.device(device)
-    assert device.type == "cuda", "the source is built on the GPU (no CPU fallback)"
+    if device.type != "cuda":
+        raise RuntimeError("the source is built on the GPU (no CPU fallback)")
     B, D = int(num_jets), int(max_num_particles)
     probs = [float(v) for v in mult_probs]
     assert len(probs) == D + 1, "mult_probs needs one weight per multiplicity 0..D"
@@ -293,6 +327,39 @@ def jet_observables(x, k, mask, mean=None, std=None, vocab_size=9):
     check(lib().mmf_jet_observables(ptr(x), ptr(k), ptr(mask), mean_c, std_c, B, D, int(vocab_size), ptr(kin), ptr(counts), idx,
                                     stream_handle(x.device)))
     return kin, counts
+
+
+def sample_record_bytes(D: int) -> int:
+    return int(lib().mmf_sample_record_bytes(int(D)))
+
+
+def pack_sample(x, k, mask, mean=None, std=None) -> torch.Tensor:
+    """De-standardise + mask + narrow the generated sample into one record per jet: (B, R) uint8 on the device
+    (reference utils/callbacks.py:52-57 fused with the int64 -> uint8 narrowing; layout in include/mmf_b200.h)."""
+    assert x.is_cuda and x.dtype == torch.float32
+    B, D = x.shape[:2]
+    x = x.contiguous()
+    mask = mask.reshape(B, D).to(torch.int64).contiguous()
+    if k is not None:
+        k = k.reshape(B, D).to(torch.int64).contiguous()
+    rec = torch.empty(B, sample_record_bytes(D), device=x.device, dtype=torch.uint8)
+    mean_c = (ctypes.c_float * 3)(*[float(v) for v in mean]) if mean is not None else None
+    std_c = (ctypes.c_float * 3)(*[float(v) for v in std]) if std is not None else None
+    idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    check(lib().mmf_pack_sample(ptr(x), ptr(k), ptr(mask), mean_c, std_c, B, D, ptr(rec), idx, stream_handle(x.device)))
+    return rec
+
+
+def unpack_sample(rec, D: int, discrete: bool = True):
+    """Inverse of ``pack_sample`` on the device: (x (B,D,3) f32, k (B,D) i64 or None, mask (B,D) i64)."""
+    assert rec.is_cuda and rec.dtype == torch.uint8 and rec.is_contiguous() and rec.shape[1] == sample_record_bytes(D)
+    B = rec.shape[0]
+    x = torch.empty(B, D, 3, device=rec.device, dtype=torch.float32)
+    k = torch.empty(B, D, device=rec.device, dtype=torch.int64) if discrete else None
+    mask = torch.empty(B, D, device=rec.device, dtype=torch.int64)
+    idx = rec.device.index if rec.device.index is not None else torch.cuda.current_device()
+    check(lib().mmf_unpack_sample(ptr(rec), B, D, ptr(x), ptr(k), ptr(mask), idx, stream_handle(rec.device)))
+    return x, k, mask
 
 
 def euler_step(vt, x, dt):

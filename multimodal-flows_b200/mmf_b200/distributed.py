@@ -55,6 +55,42 @@ def gather_sample(local: TensorMultiModal, counts: List[int]) -> TensorMultiModa
                             discrete=_gather_rows(local.discrete, counts), mask=_gather_rows(local.mask, counts))
 
 
+def gather_records(rec: torch.Tensor, counts: List[int]) -> torch.Tensor:
+    """THE end-of-run collective: one ``all_gather_into_tensor`` of the per-jet records of this rank's shard
+    ((n_rank, R) uint8, ``_abi.pack_sample``; shards are padded to the largest).  Returns the records of the whole
+    sample in global jet order on every rank.  13 bytes per slot instead of the 28 of the fp32 / int64 / int64 tensors."""
+    rank, ws = world()
+    if ws == 1:
+        return rec
+    cap, R = max(counts), rec.shape[1]
+    pad = rec
+    if rec.shape[0] != cap:
+        pad = torch.zeros(cap, R, dtype=rec.dtype, device=rec.device)
+        pad[: rec.shape[0]] = rec
+    out = torch.empty(ws * cap, R, dtype=rec.dtype, device=rec.device)
+    dist.all_gather_into_tensor(out, pad.contiguous())
+    if all(c == cap for c in counts):
+        return out
+    return torch.cat([out[r * cap: r * cap + c] for r, c in enumerate(counts)], dim=0)
+
+
+def gather_packed_sample(local: TensorMultiModal, counts: List[int], mean=None, std=None, unpack: bool = True):
+    """De-standardise + mask + narrow on the device (``mmf_pack_sample``), ONE collective, and (optionally) the reference's
+    tensors again.  Replaces FlowGeneratorCallback's temp-file merge and its host-side post-processing
+    (reference ``utils/callbacks.py:27-58``).  Returns a ``TensorMultiModal`` (``unpack=True``) or the (N, R) records."""
+    from . import _abi
+    D = local.continuous.shape[1]
+    rec = _abi.pack_sample(local.continuous, None if local.discrete is None else local.discrete, local.mask, mean, std)
+    rec = gather_records(rec, counts)
+    if not unpack:
+        return rec
+    x, k, mask = _abi.unpack_sample(rec, D, discrete=local.discrete is not None)
+    t = local.time
+    if t is not None:
+        t = torch.full((x.shape[0],), float(t[0]) if t.numel() else 0.0, device=x.device, dtype=t.dtype)
+    return TensorMultiModal(time=t, continuous=x, discrete=None if k is None else k.unsqueeze(-1), mask=mask.unsqueeze(-1))
+
+
 def generate_sharded(run_batch: RunBatch, source: TensorMultiModal, batch_size: int,
                      gather: bool = True) -> TensorMultiModal:
     """Generate ``len(source)`` jets with the global source state replicated on every rank.
@@ -100,8 +136,11 @@ def generate_from_device_source(run_batch: RunBatch, mult_probs, num_jets: int, 
         outs.append(run_batch(src, b0))
     if outs:
         local = TensorMultiModal.cat(outs, dim=0)
-    else:
-        local = make_source(mult_probs, 0, max_num_particles, vocab_size, time_eps, seed=seed, device=device, discrete=discrete)
+    else:                                   # more ranks than jets: an empty shard (no library call for zero jets)
+        dev, D = torch.device(device), max_num_particles
+        local = TensorMultiModal(time=torch.zeros(0, device=dev), continuous=torch.zeros(0, D, 3, device=dev),
+                                 discrete=torch.zeros(0, D, 1, dtype=torch.int64, device=dev) if discrete else None,
+                                 mask=torch.zeros(0, D, 1, dtype=torch.int64, device=dev))
     if not gather:
         return local
     counts = [shard_bounds(num_jets, r, ws)[1] - shard_bounds(num_jets, r, ws)[0] for r in range(ws)]

@@ -87,17 +87,26 @@ class _GenerativeBase(_Base):
         obj.on_load_checkpoint(ckpt)
         return obj
 
-    def _next_jet_offset(self, B: int, first_global_jet: Optional[int] = None) -> int:
-        """Global index of the first jet of this call.  Draws are keyed on it (world-size invariant output).
-        Callers that shard explicitly (``mmf_b200.distributed.generate_sharded``) pass it; under Lightning's
-        DistributedSampler-style round robin of equal batches it is derived from (call count, rank)."""
+    def _next_jet_offset(self, B: int, first_global_jet: Optional[int] = None, batch_idx: Optional[int] = None) -> int:
+        """Global index of the first jet of this call.  Draws are keyed on it, so two calls must never share a range.
+        Callers that shard explicitly (``mmf_b200.distributed.generate_sharded``) pass ``first_global_jet``.  Under
+        Lightning's predict loop (``predict_step(batch, batch_idx)``) the range is ``(batch_idx * world + rank) * S`` with
+        the configured ``config.batch_size`` as the stride S - independent of how many calls each rank has made, of a
+        short last batch and of skipped batches.  Without either, a single-process run counts the jets it has handed out;
+        a multi-process run cannot know what the other ranks drew and raises instead of silently re-using draws."""
         if first_global_jet is not None:
             return int(first_global_jet)
         rank, world = 0, 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
-        off = self._jet_cursor + rank * B
-        self._jet_cursor += world * B
+        stride = int(getattr(self.config, "batch_size", 0) or 0)
+        if batch_idx is not None and stride >= B:
+            return (int(batch_idx) * world + rank) * stride
+        if world > 1:
+            raise RuntimeError("cannot derive the global jet index of this batch on a multi-process run: pass "
+                               "first_global_jet, or set config.batch_size (>= the batch length) and call predict_step with batch_idx")
+        off = self._jet_cursor
+        self._jet_cursor += B
         return off
 
 
@@ -122,18 +131,18 @@ class MultiModalFlowBridge(_GenerativeBase):
         return batch
 
     @torch.no_grad()
-    def predict_step(self, batch: DataCoupling, batch_idx: int = 0, dataloader_idx: int = 0) -> TensorMultiModal:
+    def predict_step(self, batch: DataCoupling, batch_idx: Optional[int] = None, dataloader_idx: int = 0) -> TensorMultiModal:
         """Returns the generated sample on the HOST (reference model/MMF.py:70-75)."""
         src = batch.source
         if src.continuous.device.type == "cpu":
             cfg = self.config
             ts, dt = time_grid(cfg)
             B = len(src)
-            opts = _abi.step_options(cfg, seed=self.seed, first_global_jet=self._next_jet_offset(B))
+            opts = _abi.step_options(cfg, seed=self.seed, first_global_jet=self._next_jet_offset(B, batch_idx=batch_idx))
             x, k = self.model.native().generate_host(src.continuous, src.discrete, src.mask, ts, dt, opts)
             return TensorMultiModal(time=torch.full((B,), float(ts[-1])), continuous=x, discrete=k.unsqueeze(-1),
                                     mask=src.mask)
-        return self.simulate_dynamics(batch).target.detach().cpu()
+        return self.simulate_dynamics(batch, first_global_jet=self._next_jet_offset(len(src), batch_idx=batch_idx)).target.detach().cpu()
 
 
 class ConditionalFlowMatching(_GenerativeBase):
@@ -151,5 +160,5 @@ class ConditionalFlowMatching(_GenerativeBase):
         return batch
 
     @torch.no_grad()
-    def predict_step(self, batch: DataCoupling, batch_idx: int = 0, dataloader_idx: int = 0) -> TensorMultiModal:
+    def predict_step(self, batch: DataCoupling, batch_idx: Optional[int] = None, dataloader_idx: int = 0) -> TensorMultiModal:
         return self.simulate_dynamics(batch).target.detach().cpu()

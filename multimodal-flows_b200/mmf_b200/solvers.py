@@ -25,7 +25,15 @@ class HybridSolver:
         self.first_global_jet = 0
 
     def fwd_step(self, state: TensorMultiModal, delta_t, u=None):
-        return self.tauleap_step(state, delta_t, u=u)
+        if self.method == "tauleap":
+            return self.tauleap_step(state, delta_t, u=u)
+        elif self.method == "euler":
+            return self.euler_step(state, delta_t, u=u)
+
+    def check(self, device) -> None:
+        """The reference asserts 0 <= k < V inside every step (model/MJB.py:177-182, two host syncs per step); here
+        the kernels raise a device flag instead and this call (one sync) turns it into the same error."""
+        _abi.hybrid_step_status(device)
 
     @torch.no_grad()
     def tauleap_step(self, state: TensorMultiModal, delta_t, u=None):
@@ -38,6 +46,31 @@ class HybridSolver:
         if k.data_ptr() == state.discrete.data_ptr():
             k = k.clone()
         opts = _abi.step_options(self.config, seed=self.seed, first_global_jet=self.first_global_jet)
+        rates = _abi.hybrid_step(vt, logits, x, k, state.time.reshape(-1), float(delta_t), opts, u=u,
+                                 step_index=self.step_index, want_rates=True)
+        self.step_index += 1
+        state.continuous = x
+        state.discrete = k.unsqueeze(-1)
+        return state, rates
+
+
+    @torch.no_grad()
+    def euler_step(self, state: TensorMultiModal, delta_t, u=None):
+        """The categorical jump of reference model/solvers.py:62-91 (temperature 1; the reference's per-class
+        ``_temperature_scaling`` only broadcasts for one batch shape).  ``u``: optional (B,D) supplied uniforms."""
+        vt, logits = self.model(state)
+        B, D = state.continuous.shape[:2]
+        x = state.continuous.contiguous().float()
+        k = state.discrete.reshape(B, D).contiguous().long()
+        if x.data_ptr() == state.continuous.data_ptr():
+            x = x.clone()
+        if k.data_ptr() == state.discrete.data_ptr():
+            k = k.clone()
+        opts = _abi.step_options(self.config, seed=self.seed, first_global_jet=self.first_global_jet, method=1)
+        if u is not None:                        # the kernel reads channel 0 of a (B,D,V) block
+            uu = torch.zeros(B, D, self.vocab_size, device=x.device, dtype=torch.float32)
+            uu[..., 0] = u.to(x.device)
+            u = uu
         rates = _abi.hybrid_step(vt, logits, x, k, state.time.reshape(-1), float(delta_t), opts, u=u,
                                  step_index=self.step_index, want_rates=True)
         self.step_index += 1

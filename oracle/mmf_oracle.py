@@ -251,7 +251,7 @@ def top_p_filter(probs: torch.Tensor, top_p: float) -> torch.Tensor:
     srt, idx = torch.sort(probs, dim=-1, descending=True)
     keep = srt.cumsum(dim=-1) <= top_p
     keep[..., 0] = True
-    keep = torch.zeros_like(probs).scatter(-1, idx, keep.float())
+    keep = torch.zeros_like(probs).scatter(-1, idx, keep.to(probs.dtype))
     probs = probs * keep
     return probs / (probs.sum(dim=-1, keepdim=True) + 1e-8)
 
@@ -282,6 +282,53 @@ def hybrid_step(vt, logits, x, k, t, dt, u, *, temperature=1.0, beta=0.075, voca
     k_new = ((ks + net * allow) % vocab_size).unsqueeze(-1)
     x_new = x + vt * dt
     return x_new, k_new, rates
+
+
+def categorical_from_uniform(probs: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+    """``Categorical(probs).sample()`` by inverse CDF of one supplied uniform per row (channel order):
+    the index of the first channel whose cumulative normalised probability exceeds u."""
+    p = probs / probs.sum(dim=-1, keepdim=True)
+    cum = p.cumsum(dim=-1)
+    idx = (u.unsqueeze(-1) >= cum).sum(dim=-1)
+    last = (probs > 0).float().cumsum(-1).argmax(-1)            # last channel with positive mass
+    return torch.minimum(idx, last)
+
+
+def hybrid_euler_step(vt, logits, x, k, t, dt, u, *, beta=0.075, vocab_size=9, top_k=None, top_p=None):
+    """``HybridSolver.euler_step`` for temperature 1 (reference ``model/solvers.py:62-91``): categorical jump with
+    off-diagonal probabilities ``clamp(rate dt, max=1)`` and diagonal ``clamp(1 - sum, min=0)``; the filters act on
+    these transition probabilities.  ``u`` is (B,D).  Returns (x', k' (B,D,1), rates)."""
+    probs = F.softmax(logits, dim=-1)
+    rates = telegraph_rate(t, k, probs, beta, vocab_size)
+    delta_p = (rates * dt).clamp(max=1.0)
+    delta_p = delta_p.scatter(-1, k, 0.0)
+    delta_p = delta_p.scatter(-1, k, (1.0 - delta_p.sum(dim=-1, keepdim=True)).clamp(min=0.0))
+    if top_k is not None:
+        delta_p = top_k_filter(delta_p, top_k, vocab_size)
+    if top_p is not None:
+        delta_p = top_p_filter(delta_p, top_p)
+    k_new = categorical_from_uniform(delta_p, u).unsqueeze(-1)
+    return x + vt * dt, k_new, rates
+
+
+def step_uniforms(seed: int, first_global_jet: int, num_steps: int, B: int, D: int, V: int) -> torch.Tensor:
+    """The in-kernel draws of the sampler, restated: u[step, b, d, v] of the library's counter-based generator
+    (``philox_uniforms`` in csrc/mmf_common.cuh) - Philox4x32-10, key = seed, counter = (global slot lo, hi, step, v // 4),
+    word v % 4, u = (word >> 8) 2^-24 with global slot = (first_global_jet + b) D + d.  Feeding these to
+    ``simulate_dynamics(u=...)`` reproduces a production-mode (no supplied uniforms) run of ``mmf_generate`` draw for draw."""
+    import numpy as np
+    from .source_oracle import philox4x32_10
+    slot = (np.arange(B * D, dtype=np.uint64) + np.uint64(first_global_jet) * np.uint64(D)).reshape(1, B * D)
+    lo, hi = slot & np.uint64(0xFFFFFFFF), slot >> np.uint64(32)
+    step = np.arange(num_steps, dtype=np.uint64).reshape(num_steps, 1)
+    out = np.empty((num_steps, B * D, V), np.float32)
+    for blk in range((V + 3) // 4):
+        words = philox4x32_10(np.broadcast_to(lo, (num_steps, B * D)), np.broadcast_to(hi, (num_steps, B * D)),
+                              np.broadcast_to(step, (num_steps, B * D)), blk, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+        for j in range(4):
+            if blk * 4 + j < V:
+                out[:, :, blk * 4 + j] = (words[j] >> np.uint32(8)).astype(np.float32) * np.float32(5.96046448e-08)
+    return torch.from_numpy(out.reshape(num_steps, B, D, V))
 
 
 def time_grid(cfg, device="cpu"):

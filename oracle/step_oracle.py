@@ -32,6 +32,9 @@ def lib() -> ctypes.CDLL:
         _lib.mmf_oracle_hybrid_step.restype = ctypes.c_int
         _lib.mmf_oracle_hybrid_step.argtypes = [p, p, p, p, p, f, f, f, ctypes.c_int, ctypes.c_int, f, p,
                                                 ctypes.c_int, ctypes.c_int, p, p, p]
+        _lib.mmf_oracle_euler_step.restype = ctypes.c_int
+        _lib.mmf_oracle_euler_step.argtypes = [p, p, p, p, p, f, f, ctypes.c_int, ctypes.c_int, f, p,
+                                               ctypes.c_int, ctypes.c_int, p, p, p]
     return _lib
 
 
@@ -66,3 +69,23 @@ def hybrid_step(vt, logits, x, k, t, dt, u, *, temperature=1.0, beta=0.075, voca
         raise AssertionError(f"{bad} tokens outside [0,{V})")
     return (torch.from_numpy(xo), torch.from_numpy(ko).unsqueeze(-1),
             torch.from_numpy(ro) if want_rates else None)
+
+
+def euler_categorical_step(vt, logits, x, k, t, dt, u, *, beta=0.075, vocab_size=9, top_k=None, top_p=None,
+                           want_rates=True):
+    """``HybridSolver.euler_step`` (reference model/solvers.py:62-91, T = 1) with the deterministic arithmetic of
+    step_oracle.c; ``u`` is (B,D) - one uniform per particle.  Returns (x', k' (B,D,1), rates)."""
+    B, D = x.shape[:2]
+    V = vocab_size
+    c = lambda a, dt_: np.ascontiguousarray(a.detach().cpu().numpy().astype(dt_))
+    vt_, lg_, x_, u_, t_ = c(vt, np.float32), c(logits, np.float32), c(x, np.float32), c(u, np.float32), c(t, np.float32)
+    k_ = c(k.reshape(B, D), np.int64)
+    xo = np.empty_like(x_)
+    ko = np.empty_like(k_)
+    ro = np.empty((B, D, V), np.float32) if want_rates else None
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+    bad = lib().mmf_oracle_euler_step(ptr(vt_), ptr(lg_), ptr(x_), ptr(k_), ptr(t_), float(dt), float(beta), V,
+                                      int(top_k or 0), float(top_p or 0.0), ptr(u_), B, D, ptr(xo), ptr(ko), ptr(ro))
+    if bad:
+        raise AssertionError(f"{bad} tokens outside [0,{V})")
+    return (torch.from_numpy(xo), torch.from_numpy(ko).unsqueeze(-1), torch.from_numpy(ro) if want_rates else None)

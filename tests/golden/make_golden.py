@@ -15,6 +15,7 @@ Fixtures written next to this file:
 
   encoder_<Model>_<flavor>.npz   one forward, per-jet times, ragged multiplicities
   step_cases.npz                 HybridSolver.tauleap_step on supplied (vt, logits, u), tie-free
+  euler_step_cases.npz           HybridSolver.euler_step (categorical jump) on supplied (vt, logits, u), tie-free
   traj_<Model>.npz               full N-step simulate_dynamics with supplied uniforms
 """
 from __future__ import annotations
@@ -82,6 +83,20 @@ def gen_encoders(ref):
                     vt, logits = m(st)
                     ovt, ologits = orc.encoder_forward(sd, cfg, t, x, k, mask)
             real = mask.bool().squeeze(-1)
+            # SURVEY 8(c) L1 calibration: the reference's own bf16-autocast error against its fp32 self on this fixture
+            with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+                if model == "EPiC":
+                    avt = m(ref.TensorMultiModal(time=t, continuous=x.clone(), mask=mask)).float()
+                    alogits = logits
+                else:
+                    avt, alogits = m(ref.TensorMultiModal(time=t, continuous=x.clone(), discrete=k.clone(), mask=mask))
+                    avt, alogits = avt.float(), alogits.float()
+            ac = {"autocast_vt_rel": relerr(avt[real], vt[real]),
+                  "autocast_vt_maxabs": float((avt[real] - vt[real]).abs().max() / vt[real].abs().max())}
+            if model != "EPiC":
+                ac["autocast_logits_rel"] = relerr(alogits[real], logits[real])
+                ac["autocast_logits_maxabs"] = float((alogits[real] - logits[real]).abs().max() / logits[real].abs().max())
+            print("   bf16-autocast of the reference vs its fp32 self:", {k_: f"{v_:.2e}" for k_, v_ in ac.items()})
             print(f"encoder {model:20s} {flavor:7s} |vt|max={vt[real].abs().max():.3f} "
                   f"oracle-vs-ref vt {relerr(ovt[real], vt[real]):.2e}"
                   + ("" if model == "EPiC" else f" logits {relerr(ologits[real], logits[real]):.2e} "
@@ -90,7 +105,7 @@ def gen_encoders(ref):
                 os.path.join(HERE, f"encoder_{model}_{flavor}.npz"),
                 time=t.numpy(), continuous=x.numpy(), discrete=k.numpy().astype(np.int64),
                 mask=mask.numpy().astype(np.int64), vt=vt.numpy(), logits=logits.numpy(),
-                weight_seed=11, weight_checksum=synthetic.state_dict_checksum(sd))
+                weight_seed=11, weight_checksum=synthetic.state_dict_checksum(sd), **ac)
 
 
 def tie_free_uniforms(lam64, g, margin=2e-5):
@@ -172,6 +187,83 @@ def gen_steps(ref):
     np.savez_compressed(os.path.join(HERE, "step_cases.npz"), **out)
 
 
+def gen_euler_steps(ref):
+    """HybridSolver.euler_step (reference model/solvers.py:62-91) on supplied (vt, logits) with one supplied uniform per
+    particle routed through Categorical.sample; uniforms kept away from the cumulative thresholds."""
+    from model.MJB import RandomTelegraphBridge           # type: ignore
+    from utils.thermostats import ConstantThermostat      # type: ignore
+    B, D, V = 8, 128, 9
+    cases = [dict(top_k=None, top_p=None), dict(top_k=5, top_p=None), dict(top_k=None, top_p=0.9)]
+    out = {}
+    for ci, case in enumerate(cases):
+        g = torch.Generator().manual_seed(300 + ci)
+        cfg = make_config("ParticleFormer", temperature=1.0, top_k=case["top_k"], top_p=case["top_p"])
+        vt = torch.randn(B, D, 3, generator=g) * 2.0
+        logits = torch.randn(B, D, V, generator=g) * 2.5
+        x = torch.randn(B, D, 3, generator=g)
+        k = torch.randint(0, V, (B, D, 1), generator=g)
+        t = torch.tensor([1e-5, 0.1, 0.35, 0.6, 0.85, 0.97, 0.99, 1.0 - 1e-5], dtype=torch.float32)
+        if case["top_k"] is not None or case["top_p"] is not None:
+            # the filters sort the transition probabilities; in the tail of the grid they all clamp to 1 and the order of
+            # ties is implementation-defined (SURVEY 8 a-7), so the filtered cases stay where the values are distinct
+            t = torch.tensor([1e-5, 0.05, 0.1, 0.2, 0.35, 0.5, 0.6, 0.7], dtype=torch.float32)
+        dt = torch.tensor(0.010100808, dtype=torch.float32)
+
+        class Stub:
+            bridge_discrete = RandomTelegraphBridge(cfg.beta, V, ConstantThermostat(cfg.beta, V))
+
+            def eval(self):
+                return self
+
+            def __call__(self, state):
+                return vt.clone(), logits.clone()
+
+        # thresholds in double from the oracle's restatement, to place the uniforms
+        _, _, rates64 = orc.hybrid_euler_step(vt.double(), logits.double(), x.double(), k, t.double(), dt.double(),
+                                              torch.zeros(B, D, dtype=torch.float64), beta=cfg.beta, vocab_size=V)
+        dp = (rates64 * dt.double()).clamp(max=1.0).scatter(-1, k, 0.0)
+        dp = dp.scatter(-1, k, (1.0 - dp.sum(-1, keepdim=True)).clamp(min=0.0))
+        if case["top_k"] is not None or case["top_p"] is not None:
+            # the kept set must not depend on how ties are ordered: filter the channel-reversed row as well
+            def filt(q):
+                if case["top_k"] is not None:
+                    q = orc.top_k_filter(q, case["top_k"], V)
+                if case["top_p"] is not None:
+                    q = orc.top_p_filter(q, case["top_p"])
+                return q
+            assert torch.equal(filt(dp) > 0, filt(dp.flip(-1)).flip(-1) > 0), "regenerate: outcome depends on tie order"
+        if case["top_k"] is not None:
+            dp = orc.top_k_filter(dp, case["top_k"], V)
+        if case["top_p"] is not None:
+            srt = torch.sort(dp, -1, descending=True)[0].cumsum(-1)
+            assert ((srt - case["top_p"]).abs() > 1e-6).all(), "regenerate: top-p tie"
+            dp = orc.top_p_filter(dp, case["top_p"])
+        cum = (dp / dp.sum(-1, keepdim=True)).cumsum(-1)
+        u = torch.rand(B, D, generator=g)
+        for _ in range(50):
+            bad = ((u.double().unsqueeze(-1) - cum).abs() < 2e-5).any(-1)
+            if not bad.any():
+                break
+            u = torch.where(bad, torch.rand(B, D, generator=g), u)
+        assert not bad.any()
+        solver = ref.HybridSolver(model=Stub(), config=cfg)
+        st = ref.TensorMultiModal(time=t, continuous=x.clone(), discrete=k.clone(), mask=torch.ones(B, D, 1, dtype=torch.int64))
+        with ref_harness.supplied_categorical([u]):
+            st2, rates = solver.euler_step(st, dt)
+        ox, ok, orates = orc.hybrid_euler_step(vt, logits, x, k, t, dt, u, beta=cfg.beta, vocab_size=V, top_k=case["top_k"], top_p=case["top_p"])
+        changed = float((st2.discrete != k).float().mean())
+        print(f"euler case {ci} {case}: oracle k equal={torch.equal(ok, st2.discrete)} x equal={torch.equal(ox, st2.continuous)} "
+              f"rates rel={relerr(orates, rates):.1e} changed={changed:.3f}")
+        pre = f"c{ci}_"
+        out.update({pre + "vt": vt.numpy(), pre + "logits": logits.numpy(), pre + "x": x.numpy(), pre + "k": k.numpy().astype(np.uint8),
+                    pre + "t": t.numpy(), pre + "dt": dt.numpy(), pre + "u": u.numpy(), pre + "top_k": np.int32(case["top_k"] or 0),
+                    pre + "top_p": np.float32(case["top_p"] or 0.0), pre + "x_out": st2.continuous.numpy(),
+                    pre + "k_out": st2.discrete.numpy().astype(np.uint8), pre + "rates": rates.numpy()})
+    out["num_cases"] = np.int32(len(cases))
+    out["beta"] = np.float32(0.075)
+    np.savez_compressed(os.path.join(HERE, "euler_step_cases.npz"), **out)
+
+
 def gen_trajectories(ref):
     for model, N in (("FusedParticleFormer", 100), ("ParticleFormer", 100), ("EPiC", 100)):
         cfg = make_config(model, num_timesteps=N, temperature=1.0)
@@ -225,10 +317,12 @@ def gen_trajectories(ref):
 if __name__ == "__main__":
     torch.manual_seed(0)
     ref = ref_harness.modules()
-    which = sys.argv[1:] or ["encoders", "steps", "traj"]
+    which = sys.argv[1:] or ["encoders", "steps", "euler", "traj"]
     if "encoders" in which:
         gen_encoders(ref)
     if "steps" in which:
         gen_steps(ref)
+    if "euler" in which:
+        gen_euler_steps(ref)
     if "traj" in which:
         gen_trajectories(ref)

@@ -113,3 +113,28 @@ def supplied_uniforms(u_per_step):
         yield
     finally:
         torch.poisson = real
+
+
+@contextlib.contextmanager
+def supplied_categorical(u_per_call):
+    """Route ``Categorical(probs).sample()`` inside the reference's solvers through pre-drawn uniforms (one (B,D) tensor
+    per call, in order): inverse CDF in channel order on the normalised probabilities torch itself stores."""
+    install()
+    import model.solvers as ref_solvers                   # type: ignore
+    it = iter(u_per_call)
+    real = ref_solvers.Categorical
+
+    class FakeCategorical(real):
+        def sample(self, sample_shape=torch.Size()):
+            u = next(it).to(self.probs.device)
+            assert u.shape == self.probs.shape[:-1], (u.shape, self.probs.shape)
+            cum = self.probs.cumsum(-1)
+            idx = (u.unsqueeze(-1) >= cum).sum(-1)
+            last = (self.probs > 0).float().cumsum(-1).argmax(-1)
+            return torch.minimum(idx, last)
+
+    ref_solvers.Categorical = FakeCategorical
+    try:
+        yield
+    finally:
+        ref_solvers.Categorical = real

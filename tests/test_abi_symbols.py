@@ -41,7 +41,7 @@ def test_library_exports_every_declared_symbol(built_lib):
 
 def test_abi_version_and_struct_layout(built_lib):
     L = built_lib.lib()
-    assert L.mmf_abi_version() == 1
+    assert L.mmf_abi_version() == 2
     # struct sizes must equal the C layout (11 x int32; float,float,int32,float,int32,pad,uint64,uint64)
     assert ctypes.sizeof(built_lib.MmfModelDesc) == 44
     assert ctypes.sizeof(built_lib.MmfStepOptions) == 40

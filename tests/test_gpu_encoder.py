@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
 
 REL_L2 = 2e-2
 MAX_ABS = 3e-2
+AUTOCAST_FACTOR = 1.5
 
 
 def _setup(model, flavor, seed):
@@ -46,6 +47,14 @@ def test_encoder_forward_matches_reference_golden(model, flavor, golden_dir):
     assert (vt[~real] == 0).all() and (logits[~real] == 0).all()
     assert e_vt[0] < REL_L2 and e_vt[1] < MAX_ABS, ("vt", e_vt)
     assert e_lg[0] < REL_L2 and e_lg[1] < MAX_ABS, ("logits", e_lg)
+    # SURVEY 8(c) L1, second clause: no worse than 1.5x the error of the reference's OWN bf16 autocast against its fp32 self
+    # on this very fixture (stored by tests/golden/make_golden.py)
+    ac = {n: float(g[n]) for n in ("autocast_vt_rel", "autocast_vt_maxabs", "autocast_logits_rel", "autocast_logits_maxabs")}
+    print(f"{model} {flavor}: vt rel {e_vt[0]:.2e} (autocast {ac['autocast_vt_rel']:.2e}) max {e_vt[1]:.2e} ({ac['autocast_vt_maxabs']:.2e}); "
+          f"logits rel {e_lg[0]:.2e} ({ac['autocast_logits_rel']:.2e}) max {e_lg[1]:.2e} ({ac['autocast_logits_maxabs']:.2e})")
+    assert e_vt[0] <= AUTOCAST_FACTOR * ac["autocast_vt_rel"], ("vt vs autocast", e_vt[0], ac["autocast_vt_rel"])
+    assert e_lg[0] <= AUTOCAST_FACTOR * ac["autocast_logits_rel"], ("logits vs autocast", e_lg[0], ac["autocast_logits_rel"])
+    assert e_vt[1] <= AUTOCAST_FACTOR * ac["autocast_vt_maxabs"] and e_lg[1] <= AUTOCAST_FACTOR * ac["autocast_logits_maxabs"], (e_vt, e_lg, ac)
 
 
 @pytest.mark.parametrize("model", ["FusedParticleFormer", "ParticleFormer"])
@@ -70,8 +79,17 @@ def test_generate_teacher_forced_matches_reference_trajectory(model, golden_dir)
     xr = torch.from_numpy(g["x_out"]).to(dev)
     rel, mx = _errs(x, xr, real)
     assert rel < REL_L2, (rel, mx)
-    assert torch.equal(k[real], torch.from_numpy(g["k_out"]).long().to(dev).reshape(B, D)[real])
-    # free-running (no forcing): jump decisions stay close to the reference trajectory early on
+    # (no token assertion here: with forcing the final tokens equal the forced trajectory by construction)
+    # UN-forced: the first steps of the same 100-point grid against the reference's own token trajectory.  Decisions are
+    # bit-exact given identical logits (test_gpu_step.py); through the encoder a uniform within ~1e-3 of a threshold flips.
+    traj = torch.from_numpy(g["traj_k"]).long().reshape(-1, B, D)
+    for nsteps, need in ((1, 0.995), (5, 0.98), (20, 0.93)):
+        xs, ks, _ = nm.generate(x0, k0, mask, ts[:nsteps], float(dt), opts, u=u[:nsteps].to(dev))
+        torch.cuda.synchronize()
+        agree = (ks[real].cpu() == traj[nsteps - 1][real.cpu()]).float().mean().item()
+        print(f"{model}: un-forced agreement with the reference trajectory after {nsteps} steps: {agree:.4f}")
+        assert agree >= need, (nsteps, agree)
+    # free-running over the whole grid: jump decisions stay close to the reference trajectory
     x2, k2, _ = nm.generate(x0, k0, mask, ts, float(dt), opts, u=u.to(dev))
     torch.cuda.synchronize()
     agree = (k2[real] == torch.from_numpy(g["k_out"]).long().to(dev).reshape(B, D)[real]).float().mean().item()

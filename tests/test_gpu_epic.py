@@ -47,6 +47,9 @@ def test_epic_forward_matches_reference_golden(flavor, golden_dir):
         rb = _errs(vt[b:b + 1], T("vt")[b:b + 1], real[b:b + 1])
         assert rb[0] < REL_L2 and rb[1] < MAX_ABS, (b, rb)
     assert rel < REL_L2 and mx < MAX_ABS, (rel, mx)
+    # SURVEY 8(c) L1, second clause: within 1.5x the reference's own bf16-autocast error on this fixture
+    print(f"EPiC {flavor}: vt rel {rel:.2e} (autocast {float(g['autocast_vt_rel']):.2e}) max {mx:.2e} ({float(g['autocast_vt_maxabs']):.2e})")
+    assert rel <= 1.5 * float(g["autocast_vt_rel"]) and mx <= 1.5 * float(g["autocast_vt_maxabs"]), (rel, mx)
 
 
 def test_epic_sampler_matches_reference_trajectory(golden_dir):

@@ -1,0 +1,319 @@
+"""Parity of the sampler's options and front-ends through the C ABI (round-2 additions).
+
+  * ``mmf_generate`` (the step fused into the tile kernel) with temperature, top-k, top-p and use_final_max_rates
+    against ``oracle.mmf_oracle.simulate_dynamics`` on the same supplied uniforms;
+  * the HOST path (``predict_step`` -> ``mmf_generate_host``, in-kernel Philox draws) against the oracle fed with the
+    oracle's restatement of those draws (``mmf_oracle.step_uniforms``) - values, not shapes;
+  * ``HybridSolver.fwd_step`` (tau-leap and the categorical Euler jump), ``ContinuousSolver.fwd_step`` and
+    ``mmf_euler_step`` against the reference's golden vectors;
+  * BASELINE config #2 itself (256 AOJ-shaped jets, seed 1234, 2-CTA clusters) for two timesteps against the oracle.
+
+Why free-running token comparisons are agreement thresholds and not equalities: the jump decisions are bit-exact given
+identical logits (tests/test_gpu_step.py), but through the encoder the logits carry the bf16 operand error (rel-L2 <= 2e-2),
+which moves every threshold exp(-lambda) by ~1e-3 relative; a supplied uniform that falls inside that sliver flips one
+decision and the jet's later trajectory follows.  Measured: 0.5 % of real particles per 4 timesteps.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _model(name, flavor="wide", seed=0, **over):
+    from mmf_b200 import _abi, synthetic
+    from mmf_b200.param_spec import make_config
+    cfg = make_config(name, **over)
+    sd = synthetic.make_state_dict(cfg, flavor=flavor, seed=seed)
+    return cfg, sd, _abi.NativeModel(cfg, sd, torch.device(DEV))
+
+
+def _rel(a, b, real):
+    a, b = a[real].float(), b[real].float()
+    return float((a - b).norm() / b.norm())
+
+
+OPTION_CASES = [
+    dict(temperature=0.8), dict(temperature=1.2), dict(top_k=5), dict(top_p=0.9), dict(temperature=0.8, top_k=4, top_p=0.8),
+    dict(use_final_max_rates=True), dict(temperature=1.2, use_final_max_rates=True),
+]
+
+
+@pytest.mark.parametrize("name", ["FusedParticleFormer", "ParticleFormer"])
+@pytest.mark.parametrize("case", OPTION_CASES, ids=lambda c: ",".join(f"{k}={v}" for k, v in c.items()))
+def test_generate_options_match_oracle(name, case):
+    """reference model/solvers.py:22-60, 101-119 and model/MMF.py:193-196 through mmf_generate (tile kernel, fused step).
+    N = 6 grid points: the last two sit in the blown-up tail of the thermostat."""
+    from mmf_b200 import _abi, synthetic
+    from oracle import mmf_oracle as orc
+    cfg, sd, nm = _model(name, num_timesteps=6, **case)
+    g = torch.Generator().manual_seed(31)
+    n = torch.tensor([3, 17, 40, 64, 90, 128, 1, 55, 128, 77, 20, 100])
+    B = len(n)
+    mask = synthetic.prefix_masks(n, 150)
+    x0 = torch.randn(B, 150, 3, generator=g) * mask
+    k0 = torch.randint(1, 9, (B, 150, 1), generator=g) * mask
+    u = synthetic.uniform_draws(cfg.num_timesteps, B, seed=32)
+    xo, ko, ro = orc.simulate_dynamics(sd, cfg, x0, k0, mask, u=u)
+    ts, dt = orc.time_grid(cfg)
+    opts = _abi.step_options(cfg)
+    assert opts.use_final_max_rates == int(bool(case.get("use_final_max_rates", False)))
+    xg, kg, rg = nm.generate(x0.to(DEV), k0.to(DEV), mask.to(DEV), ts, float(dt), opts, u=u.to(DEV), want_rates=True)
+    torch.cuda.synchronize()
+    real = mask.bool().squeeze(-1)
+    assert nm.launches <= 4                                   # all on the persistent tile path
+    assert _rel(xg.cpu(), xo, real) < 2e-2
+    agree = (kg.cpu()[real] == ko.squeeze(-1)[real]).float().mean().item()
+    assert agree > 0.97, agree
+    # rates of the last step: 1 + coef q + w q_k with coef = 1.3e6 at t = 1 - eps, i.e. the softmax itself
+    assert _rel(rg.cpu(), ro, real) < 5e-2
+    if case.get("use_final_max_rates"):
+        # the ADVICE case: no rates requested, tokens must still be the argmax of the last rates
+        xg2, kg2, _ = nm.generate(x0.to(DEV), k0.to(DEV), mask.to(DEV), ts, float(dt), opts, u=u.to(DEV), want_rates=False)
+        torch.cuda.synchronize()
+        assert torch.equal(kg2, kg) and torch.equal(xg2, xg)
+        assert torch.equal(kg.cpu()[real], rg.cpu()[real].argmax(-1))
+
+
+def test_final_max_rates_without_rates_on_the_layered_path(monkeypatch):
+    """ADVICE r1 (kernels_simt.cu head_out_kernel): use_final_max_rates with no rates buffer read uninitialised registers."""
+    from mmf_b200 import _abi, synthetic
+    from oracle import mmf_oracle as orc
+    from mmf_b200.param_spec import make_config
+    monkeypatch.setenv("MMF_NO_TILE_KERNEL", "1")
+    cfg = make_config("FusedParticleFormer", num_timesteps=4, use_final_max_rates=True)
+    sd = synthetic.make_state_dict(cfg, flavor="wide", seed=0)
+    nm = _abi.NativeModel(cfg, sd, torch.device(DEV))
+    monkeypatch.delenv("MMF_NO_TILE_KERNEL")
+    src = synthetic.source_state(6, seed=41)
+    u = synthetic.uniform_draws(4, 6, seed=42)
+    xo, ko, ro = orc.simulate_dynamics(sd, cfg, src.continuous, src.discrete, src.mask, u=u)
+    ts, dt = orc.time_grid(cfg)
+    x, k, _ = nm.generate(src.continuous.to(DEV), src.discrete.to(DEV), src.mask.to(DEV), ts, float(dt), _abi.step_options(cfg), u=u.to(DEV))
+    x2, k2, r2 = nm.generate(src.continuous.to(DEV), src.discrete.to(DEV), src.mask.to(DEV), ts, float(dt), _abi.step_options(cfg), u=u.to(DEV), want_rates=True)
+    torch.cuda.synchronize()
+    real = src.mask.bool().squeeze(-1)
+    assert nm.launches > 100
+    assert torch.equal(k, k2)
+    assert torch.equal(k.cpu()[real], r2.cpu()[real].argmax(-1))
+    assert (k.cpu()[real] == ko.squeeze(-1)[real]).float().mean() > 0.97
+
+
+@pytest.mark.parametrize("name", ["FusedParticleFormer", "ParticleFormer"])
+def test_predict_step_host_path_values_match_oracle(name):
+    """predict_step with a HOST batch (mmf_generate_host, Philox draws keyed on (seed, global slot, step)) against the fp32
+    oracle driven by the oracle's own restatement of those draws - the e2e leg of the bench, checked by value."""
+    from mmf_b200 import synthetic
+    from mmf_b200.mmf import MultiModalFlowBridge
+    from mmf_b200.param_spec import make_config
+    from mmf_b200.tensorclass import DataCoupling, TensorMultiModal
+    from oracle import mmf_oracle as orc
+    cfg = make_config(name, num_timesteps=4, temperature=0.9, batch_size=16, seed=77)
+    sd = synthetic.make_state_dict(cfg, "wide", seed=2)
+    bridge = MultiModalFlowBridge(cfg)
+    bridge.model.load_state_dict(sd)
+    bridge = bridge.to(DEV)
+    B = 11
+    src = synthetic.source_state(B, seed=7)
+    batch_idx = 3                                             # global jets [3 * 16, 3 * 16 + 11)
+    out = bridge.predict_step(DataCoupling(source=src, target=TensorMultiModal()), batch_idx)
+    assert out.continuous.device.type == "cpu" and out.discrete.dtype == torch.int64 and out.discrete.shape == (B, 150, 1)
+    u = orc.step_uniforms(seed=77, first_global_jet=batch_idx * 16, num_steps=4, B=B, D=150, V=9)
+    xo, ko, _ = orc.simulate_dynamics(sd, cfg, src.continuous, src.discrete, src.mask, u=u)
+    real = src.mask.bool().squeeze(-1)
+    assert _rel(out.continuous, xo, real) < 2e-2
+    agree = (out.discrete.squeeze(-1)[real] == ko.squeeze(-1)[real]).float().mean().item()
+    assert agree > 0.97, agree
+    assert (out.continuous[~real] == 0).all() and (out.discrete.squeeze(-1)[~real] == 0).all()
+    assert abs(float(out.time[0]) - (1 - 1e-5)) < 1e-6
+    # the same batch on the device path with the same global offset is the same sample, bit for bit
+    dev_out = bridge.simulate_dynamics(DataCoupling(source=src.to(DEV), target=TensorMultiModal()), first_global_jet=batch_idx * 16).target
+    assert torch.equal(dev_out.continuous.cpu(), out.continuous) and torch.equal(dev_out.discrete.cpu(), out.discrete)
+    # wrong draws (another offset) do NOT reproduce the oracle's tokens: the comparison above is not vacuous
+    u_bad = orc.step_uniforms(seed=77, first_global_jet=0, num_steps=4, B=B, D=150, V=9)
+    _, kb, _ = orc.simulate_dynamics(sd, cfg, src.continuous, src.discrete, src.mask, u=u_bad)
+    assert (out.discrete.squeeze(-1)[real] == kb.squeeze(-1)[real]).float().mean().item() < agree - 0.02
+
+
+def test_epic_predict_step_values_match_oracle():
+    from mmf_b200 import synthetic
+    from mmf_b200.mmf import ConditionalFlowMatching
+    from mmf_b200.param_spec import make_config
+    from mmf_b200.tensorclass import DataCoupling, TensorMultiModal
+    from oracle import mmf_oracle as orc
+    cfg = make_config("EPiC", num_timesteps=6)
+    sd = synthetic.make_state_dict(cfg, "wide", seed=4)
+    cfm = ConditionalFlowMatching(cfg)
+    cfm.model.load_state_dict(sd)
+    cfm = cfm.to(DEV)
+    src = synthetic.source_state(10, seed=8)
+    src.discrete = None
+    out = cfm.predict_step(DataCoupling(source=src.to(DEV), target=TensorMultiModal()), 0)
+    xo = orc.simulate_dynamics_cfm(sd, cfg, src.continuous, src.mask)
+    real = src.mask.bool().squeeze(-1)
+    assert out.continuous.device.type == "cpu"
+    assert _rel(out.continuous, xo, real) < 2e-2
+
+
+class _StubModel:
+    """model(state) -> (vt, logits) on the device, as the reference's encoders return them."""
+
+    def __init__(self, vt, logits=None):
+        self.vt, self.logits = vt, logits
+
+    def __call__(self, state):
+        return (self.vt.clone(), self.logits.clone()) if self.logits is not None else self.vt.clone()
+
+
+def test_hybrid_solver_fwd_step_matches_reference_goldens(golden_dir):
+    """HybridSolver(model, config).fwd_step(state, dt) -> (state, rates): reference model/solvers.py:8-60."""
+    from mmf_b200.param_spec import make_config
+    from mmf_b200.solvers import HybridSolver
+    from mmf_b200.tensorclass import TensorMultiModal
+    g = np.load(os.path.join(golden_dir, "step_cases.npz"))
+    for ci in range(int(g["num_cases"])):
+        p = f"c{ci}_"
+        T = lambda n: torch.from_numpy(g[p + n]).to(DEV)
+        cfg = make_config("ParticleFormer", temperature=float(g[p + "T"]), top_k=int(g[p + "top_k"]) or None,
+                          top_p=float(g[p + "top_p"]) or None)
+        solver = HybridSolver(_StubModel(T("vt"), T("logits")), cfg)
+        assert solver.method == "tauleap"
+        x_in, k_in = T("x"), T("k").long()
+        state = TensorMultiModal(time=T("t"), continuous=x_in, discrete=k_in, mask=torch.ones_like(k_in))
+        state, rates = solver.fwd_step(state, torch.tensor(float(g[p + "dt"])), u=T("u"))
+        solver.check(DEV)
+        assert state.discrete.shape == k_in.shape and state.discrete.dtype == torch.int64
+        assert torch.equal(state.discrete.cpu(), torch.from_numpy(g[p + "k_out"]).long()), f"case {ci}"
+        assert torch.equal(state.continuous.cpu(), torch.from_numpy(g[p + "x_out"])), f"case {ci}"
+        assert ((rates.cpu() - torch.from_numpy(g[p + "rates"])).abs() / torch.from_numpy(g[p + "rates"]).abs()).max() < 1e-6
+        assert state.continuous.data_ptr() != x_in.data_ptr()      # the input tensors are not written in place
+
+
+def test_hybrid_solver_euler_step_matches_reference_goldens(golden_dir):
+    """The categorical jump, reference model/solvers.py:62-91: golden = the reference's own euler_step with
+    Categorical.sample routed through supplied uniforms (tests/golden/make_golden.py: gen_euler_steps);
+    also bit-exact against the C oracle on a fresh input."""
+    from mmf_b200.param_spec import make_config
+    from mmf_b200.solvers import HybridSolver
+    from mmf_b200.tensorclass import TensorMultiModal
+    from oracle import step_oracle
+    g = np.load(os.path.join(golden_dir, "euler_step_cases.npz"))
+    for ci in range(int(g["num_cases"])):
+        p = f"c{ci}_"
+        T = lambda n: torch.from_numpy(g[p + n]).to(DEV)
+        cfg = make_config("ParticleFormer", temperature=1.0, top_k=int(g[p + "top_k"]) or None, top_p=float(g[p + "top_p"]) or None)
+        solver = HybridSolver(_StubModel(T("vt"), T("logits")), cfg)
+        solver.method = "euler"
+        k_in = T("k").long()
+        state = TensorMultiModal(time=T("t"), continuous=T("x"), discrete=k_in, mask=torch.ones_like(k_in))
+        state, rates = solver.fwd_step(state, torch.tensor(float(g[p + "dt"])), u=T("u"))
+        mism = int((state.discrete.cpu() != torch.from_numpy(g[p + "k_out"]).long()).sum())
+        assert mism == 0, f"case {ci}: {mism} token mismatches"
+        assert torch.equal(state.continuous.cpu(), torch.from_numpy(g[p + "x_out"]))
+        assert ((rates.cpu() - torch.from_numpy(g[p + "rates"])).abs() / torch.from_numpy(g[p + "rates"]).abs()).max() < 1e-6
+    # random (not tie-free) input: CUDA vs the C restatement, bit for bit
+    gen = torch.Generator().manual_seed(5)
+    B, D, V = 6, 150, 9
+    vt, lg, x = torch.randn(B, D, 3, generator=gen), torch.randn(B, D, V, generator=gen) * 2, torch.randn(B, D, 3, generator=gen)
+    k = torch.randint(0, V, (B, D, 1), generator=gen)
+    t = torch.tensor([1e-5, 0.2, 0.5, 0.9, 0.99, 1 - 1e-5])
+    u = torch.rand(B, D, generator=gen)
+    for top_k, top_p in ((None, None), (3, None), (None, 0.7)):
+        cfg = make_config("ParticleFormer", temperature=1.0, top_k=top_k, top_p=top_p)
+        xr, kr, rr = step_oracle.euler_categorical_step(vt, lg, x, k, t, 0.0101, u, top_k=top_k, top_p=top_p)
+        solver = HybridSolver(_StubModel(vt.to(DEV), lg.to(DEV)), cfg)
+        solver.method = "euler"
+        st = TensorMultiModal(time=t.to(DEV), continuous=x.to(DEV), discrete=k.to(DEV), mask=torch.ones_like(k).to(DEV))
+        st, rates = solver.fwd_step(st, 0.0101, u=u.to(DEV))
+        assert torch.equal(st.discrete.cpu(), kr) and torch.equal(st.continuous.cpu(), xr) and torch.equal(rates.cpu(), rr)
+
+
+def test_hybrid_step_reports_out_of_range_tokens():
+    """reference model/MJB.py:177-182 asserts inside rate(); here: device flag -> status 3 at the query."""
+    from mmf_b200 import _abi
+    from mmf_b200.param_spec import make_config
+    cfg = make_config("ParticleFormer")
+    B, D, V = 2, 150, 9
+    x = torch.zeros(B, D, 3, device=DEV)
+    k = torch.ones(B, D, dtype=torch.int64, device=DEV)
+    _abi.hybrid_step(torch.zeros(B, D, 3, device=DEV), torch.zeros(B, D, V, device=DEV), x, k, torch.full((B,), 0.5, device=DEV), 0.01,
+                     _abi.step_options(cfg), u=torch.rand(B, D, V, device=DEV))
+    _abi.hybrid_step_status(DEV)                              # clean
+    k[1, 7] = 11
+    _abi.hybrid_step(torch.zeros(B, D, 3, device=DEV), torch.zeros(B, D, V, device=DEV), x, k, torch.full((B,), 0.5, device=DEV), 0.01,
+                     _abi.step_options(cfg), u=torch.rand(B, D, V, device=DEV))
+    with pytest.raises(RuntimeError, match="outside of bound"):
+        _abi.hybrid_step_status(DEV)
+    _abi.hybrid_step_status(DEV)                              # cleared by the query
+
+
+def test_continuous_solver_and_euler_step(golden_dir):
+    """ContinuousSolver.fwd_step (reference model/solvers.py:123-143) and the raw mmf_euler_step: x + vt dt with
+    individually rounded multiply and add, i.e. exactly what torch computes."""
+    from mmf_b200 import _abi
+    from mmf_b200.solvers import ContinuousSolver
+    from mmf_b200.tensorclass import TensorMultiModal
+    g = np.load(os.path.join(golden_dir, "step_cases.npz"))
+    vt, x, dt = torch.from_numpy(g["c0_vt"]), torch.from_numpy(g["c0_x"]), float(g["c0_dt"])
+    solver = ContinuousSolver(_StubModel(vt.to(DEV)), None)
+    assert solver.method == "euler"
+    st = TensorMultiModal(time=torch.zeros(x.shape[0], device=DEV), continuous=x.to(DEV), mask=torch.ones(x.shape[0], x.shape[1], 1, dtype=torch.int64, device=DEV))
+    st = solver.fwd_step(st, dt)
+    assert torch.equal(st.continuous.cpu(), torch.from_numpy(g["c0_x_out"]))      # the reference's own x + vt * dt
+    assert torch.equal(st.continuous.cpu(), x + vt * torch.tensor(dt))
+    xd = x.to(DEV).clone()
+    _abi.euler_step(vt.to(DEV), xd, dt)
+    assert torch.equal(xd.cpu(), torch.from_numpy(g["c0_x_out"]))
+    empty = TensorMultiModal(time=torch.zeros(2, device=DEV))
+    assert solver.fwd_step(empty, dt) is empty                                      # no continuous mode: returned untouched
+
+
+def test_baseline_config2_batch_matches_oracle():
+    """BASELINE config #2 itself: ParticleFormer, 256 AOJ-shaped jets (multiplicities seed 1234 as in bench.py), which plans
+    110 tiles in 2-CTA clusters; two grid points with supplied uniforms against the fp32 oracle on the whole batch."""
+    from mmf_b200 import _abi, synthetic
+    from oracle import mmf_oracle as orc
+    cfg, sd, nm = _model("ParticleFormer", flavor="wide", seed=0, num_timesteps=2)
+    src = synthetic.source_state(256, seed=1234)
+    n = src.mask.squeeze(-1).sum(1)
+    assert int(n.sum()) == 13819 and int(n.max()) <= 128      # the bench batch
+    u = synthetic.uniform_draws(2, 256, seed=1237)
+    xo, ko, ro = orc.simulate_dynamics(sd, cfg, src.continuous, src.discrete, src.mask, u=u)
+    ts, dt = orc.time_grid(cfg)
+    n_host = n.to(torch.int32)
+    xg, kg, rg = nm.generate(src.continuous.to(DEV), src.discrete.to(DEV), None, ts, float(dt), _abi.step_options(cfg), u=u.to(DEV),
+                             want_rates=True, n_per_jet=n_host)                    # the asynchronous entry point (mmf_generate_n)
+    nm.status()
+    real = src.mask.bool().squeeze(-1)
+    assert nm.launches <= 3
+    assert _rel(xg.cpu(), xo, real) < 2e-2
+    assert (kg.cpu()[real] == ko.squeeze(-1)[real]).float().mean() > 0.98
+    assert _rel(rg.cpu(), ro, real) < 5e-2
+    assert (xg.cpu()[~real] == 0).all() and (kg.cpu()[~real] == 0).all()
+    # and through the mask-reading entry point: identical
+    xm, km, _ = nm.generate(src.continuous.to(DEV), src.discrete.to(DEV), src.mask.to(DEV), ts, float(dt), _abi.step_options(cfg), u=u.to(DEV))
+    assert torch.equal(xm, xg) and torch.equal(km, kg)
+
+
+def test_two_devices_in_one_process_if_present():
+    """the shared-memory opt-in is per device; a second GPU in the same process must launch too."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU")
+    from mmf_b200 import _abi, synthetic
+    from mmf_b200.param_spec import make_config
+    from oracle import mmf_oracle as orc
+    cfg = make_config("FusedParticleFormer", num_timesteps=2)
+    sd = synthetic.make_state_dict(cfg, "wide", seed=0)
+    src = synthetic.source_state(4, seed=3)
+    ts, dt = orc.time_grid(cfg)
+    outs = []
+    for d in ("cuda:0", "cuda:1"):
+        nm = _abi.NativeModel(cfg, sd, torch.device(d))
+        with torch.cuda.device(d):
+            x, k, _ = nm.generate(src.continuous.to(d), src.discrete.to(d), src.mask.to(d), ts, float(dt), _abi.step_options(cfg, seed=3))
+            torch.cuda.synchronize()
+        outs.append((x.cpu(), k.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])

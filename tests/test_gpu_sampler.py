@@ -48,8 +48,13 @@ def test_tile_kernel_agrees_with_layered_path(name, monkeypatch):
     torch.cuda.synchronize()
     assert nm_tile.launches <= 4 and nm_lay.launches > 100           # one persistent launch vs one launch per layer
     assert _rel(xa, xb, real) < 1e-2
-    assert torch.equal(ka, kb)
-    assert _rel(ra, rb, real) < 2e-2
+    assert _rel(ra, rb, real) < 2e-2                                   # (tokens are forced: comparing them would be vacuous)
+    # un-forced: the two paths take the same decisions except where a draw sits on a threshold
+    ts4 = ts[:4]
+    _, kfa, _ = nm_tile.generate(src.continuous, src.discrete, src.mask, ts4, float(dt), opts, u=u[:4])
+    _, kfb, _ = nm_lay.generate(src.continuous, src.discrete, src.mask, ts4, float(dt), opts, u=u[:4])
+    torch.cuda.synchronize()
+    assert (kfa[real] == kfb[real]).float().mean() > 0.985
     assert (xa[~real] == 0).all() and (ka[~real] == 0).all()
     # forward API (per-jet times) through both
     t = torch.rand(24, device=DEV)
