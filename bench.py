@@ -7,8 +7,14 @@ Contract (see the task description): `python bench.py --gpus N --steps K --warmu
   value     = whole-job jets/s with inputs resident in HBM when the timed region starts (CUDA events, max over ranks)
   e2e       = same metric through the drop-in API with HOST buffers (H2D and D2H copies inside the timed region)
   roofline  = the dominant kernel class, timed live with CUDA events, against MEASURED_PEAKS.json
-  cpu_baseline = the oracle port (torch fp32, reference algorithm) timed on this box's host cores, bounded sample
-`--impl reference` times that CPU port as the reference arm (rank 0 only).
+  roofline_dense = the same kernel on the dense worst case (every jet 150 particles: CTA-pair tiles)
+  cpu_baseline = the UNMODIFIED reference's own sampler (oracle/_ref, copied by oracle/make_ref.py; the oracle port when that
+              copy is absent) on this box's host cores: the WHOLE batch for a bounded number of timesteps
+  gpu_eager_baseline = the fp32 oracle port (plain torch, TF32 off) on the same GPU, whole batch, bounded timesteps
+  extra_models = FusedParticleFormer / EPiC on one GPU; whole_run = source -> sampler -> records -> ONE collective, timed
+              end to end on every rank (BASELINE configs #3 and #4)
+`--impl reference` times the reference's own CPU sampler as the reference arm (rank 0 only): every step is the whole batch
+for `--ref-sample-timesteps` timesteps, nothing is extrapolated over jets.
 """
 from __future__ import annotations
 
@@ -54,8 +60,12 @@ def parse_args():
                          "fit in cache, the whole batch of 256 runs ~20x slower per jet (see cpu_baseline.whole_batch_probe)")
     ap.add_argument("--cpu-sample-timesteps", type=int, default=100,
                     help="timesteps of the cpu_baseline sample (32 jets x all 100 timesteps: 5-15 s of CPU work, no extrapolation)")
-    ap.add_argument("--ref-sample-timesteps", type=int, default=25,
-                    help="timesteps of ONE step of --impl reference (each step is a bounded sample: K + W of them must fit in minutes)")
+    ap.add_argument("--ref-sample-timesteps", type=int, default=2,
+                    help="timesteps of ONE step of --impl reference / cpu_baseline: the WHOLE batch is stepped through this many grid "
+                         "points (about a second each on 16 cores), so K + W steps fit in minutes")
+    ap.add_argument("--eager-timesteps", type=int, default=3, help="timesteps of the gpu_eager_baseline sample (whole batch)")
+    ap.add_argument("--whole-run-jets", type=int, default=4096, help="jets per rank of the whole_run legs (x4 for EPiC)")
+    ap.add_argument("--no-extras", action="store_true", help="skip roofline_dense, extra_models, whole_run, gpu_eager_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-step-roofline", action="store_true")
     return ap.parse_args()
@@ -119,27 +129,101 @@ def algorithmic_flops_per_timestep(model: str, n: torch.Tensor) -> float:
     return float((FLOPS_PER_PARTICLE[model] * nf + FLOPS_PER_JET_CONST[model] + ATTN_FLOPS_PER_N2[model] * nf * nf).sum())
 
 
-def cpu_port_rate(args, cfg, sd, sample_jets, sample_timesteps, repeats=1):
-    """jets/s at `timesteps` steps of the CPU oracle port, extrapolated from `sample_timesteps` timesteps."""
+def cpu_port_rate(args, cfg, sd, sample_jets, sample_timesteps, repeats=1, device="cpu"):
+    """jets/s at `timesteps` steps of the oracle port (torch fp32), from `sample_timesteps` timesteps of `sample_jets` jets."""
     from mmf_b200 import synthetic
     from oracle import mmf_oracle as orc
-    torch.set_num_threads(os.cpu_count() or 1)
-    src = synthetic.source_state(sample_jets, cfg.max_num_particles, cfg.vocab_size, dense=args.dense)
-    u = synthetic.uniform_draws(sample_timesteps + 1, sample_jets, cfg.max_num_particles, cfg.vocab_size)
+    if device == "cpu":
+        torch.set_num_threads(os.cpu_count() or 1)
+    src = synthetic.source_state(sample_jets, cfg.max_num_particles, cfg.vocab_size, dense=args.dense).to(device)
+    u = synthetic.uniform_draws(sample_timesteps + 1, sample_jets, cfg.max_num_particles, cfg.vocab_size).to(device)
+    sdd = {k: v.to(device) for k, v in sd.items()}
 
     def run(uu, steps):
         if cfg.model == "EPiC":
-            return orc.simulate_dynamics_cfm(sd, cfg, src.continuous, src.mask, max_steps=steps)
-        return orc.simulate_dynamics(sd, cfg, src.continuous, src.discrete, src.mask, u=uu, max_steps=steps)
+            return orc.simulate_dynamics_cfm(sdd, cfg, src.continuous, src.mask, max_steps=steps)
+        return orc.simulate_dynamics(sdd, cfg, src.continuous, src.discrete, src.mask, u=uu, max_steps=steps)
+
+    def sync():
+        if device != "cpu":
+            torch.cuda.synchronize()
 
     run(u, 1)                                                                                         # warm-up
+    sync()
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
         run(u[1:], sample_timesteps)
+        sync()
         dt = (time.perf_counter() - t0) / sample_timesteps
         best = dt if best is None else min(best, dt)
     return sample_jets / (best * cfg.num_timesteps), best
+
+
+class ReferenceSampler:
+    """The UNMODIFIED reference (oracle/_ref or /root/reference behind the stub modules of oracle/ref_loader.py): its own
+    MultiModalFlowBridge / ConditionalFlowMatching.simulate_dynamics on the whole batch, fp32, all host threads."""
+
+    def __init__(self, args, cfg, sd):
+        from oracle import ref_loader
+        self.ok = ref_loader.available()
+        self.where = ref_loader.REF_ROOT
+        if not self.ok:
+            return
+        from mmf_b200 import synthetic
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.ref = ref_loader.modules()
+        self.args, self.cfg = args, cfg
+        self.epic = cfg.model == "EPiC"
+        self.sd = sd
+        self.src = synthetic.source_state(args.batch, cfg.max_num_particles, cfg.vocab_size, dense=args.dense)
+        self._models = {}
+
+    def _model(self, timesteps):
+        if timesteps not in self._models:
+            import copy
+            c = copy.copy(self.cfg)
+            c.num_timesteps = timesteps
+            m = (self.ref.ConditionalFlowMatching if self.epic else self.ref.MultiModalFlowBridge)(c).eval()
+            m.model.load_state_dict(self.sd, strict=True)
+            self._models[timesteps] = m
+        return self._models[timesteps]
+
+    def step(self, timesteps):
+        """One bounded sample: the reference's simulate_dynamics over `timesteps` grid points of the whole batch. Seconds."""
+        m = self._model(timesteps)
+        ref = self.ref
+        src = ref.TensorMultiModal(continuous=self.src.continuous.clone(), discrete=None if self.epic else self.src.discrete.clone(),
+                                   mask=self.src.mask.clone())
+        batch = ref.DataCoupling(source=src, target=ref.TensorMultiModal())
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            m.simulate_dynamics(batch)
+        return time.perf_counter() - t0
+
+
+def cpu_reference_measure(args, cfg, sd, steps, warmup):
+    """(value jets/s @ cfg.num_timesteps, seconds per bench step, kind, sample text).  Every step = whole batch x S timesteps."""
+    S = max(2, min(args.ref_sample_timesteps, cfg.num_timesteps))      # (S = 1 divides by zero in the reference's own dt, MMF.py:183-185)
+    cores = os.cpu_count() or 1
+    rs = ReferenceSampler(args, cfg, sd)
+    if rs.ok:
+        for _ in range(warmup):
+            rs.step(S)
+        secs = [rs.step(S) for _ in range(max(steps, 1))]
+        kind = "reference"
+        what = f"the unmodified reference ({'oracle/_ref' if rs.where.endswith('_ref') else rs.where}) simulate_dynamics"
+    else:
+        for _ in range(warmup):
+            cpu_port_rate(args, cfg, sd, args.batch, 1)
+        secs = [cpu_port_rate(args, cfg, sd, args.batch, S)[1] * S for _ in range(max(steps, 1))]
+        kind = "port"
+        what = "oracle/mmf_oracle.py (port; oracle/_ref absent)"
+    per_step = sum(secs) / len(secs)
+    value = args.batch / (per_step / S * cfg.num_timesteps)
+    sample = (f"{what}, torch fp32, {cores} threads: the WHOLE batch of {args.batch} jets x {S} timesteps per step "
+              f"({per_step:.2f} s measured), scaled by {cfg.num_timesteps}/{S} timesteps to the metric's {cfg.num_timesteps} steps; no extrapolation over jets")
+    return value, per_step, kind, sample
 
 
 def run_reference_arm(args, rank):
@@ -150,23 +234,122 @@ def run_reference_arm(args, rank):
     cfg = make_config(args.model, num_timesteps=args.timesteps, temperature=args.temperature)
     sd = synthetic.make_state_dict(cfg, flavor="wide", seed=0)
     cores = os.cpu_count() or 1
-    # one "step" = a bounded sample (sample_jets x sample_timesteps) of the same workload, extrapolated to the full step
-    for _ in range(max(args.warmup, 0)):
-        cpu_port_rate(args, cfg, sd, args.cpu_sample_jets, 1)
     t0 = time.perf_counter()
-    rates = [cpu_port_rate(args, cfg, sd, args.cpu_sample_jets, args.ref_sample_timesteps)[0] for _ in range(max(args.steps, 1))]
+    value, per_step, kind, sample = cpu_reference_measure(args, cfg, sd, args.steps, max(args.warmup, 0))
     wall = time.perf_counter() - t0
-    value = sum(rates) / len(rates)
-    sample = (f"{args.cpu_sample_jets} jets x {args.ref_sample_timesteps} of {args.timesteps} timesteps per step, oracle port "
-              f"(torch fp32, {cores} threads), extrapolated linearly to {args.timesteps} timesteps")
     print(json.dumps({
         "impl": "reference", "metric": metric_name(args), "value": value, "unit": "jets/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * args.batch / value, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "wall_s": wall},
-        "cpu_baseline": {"value": value, "unit": "jets/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(args), "wall_s": wall,
+                   "step": f"one step = the whole batch for {max(2, min(args.ref_sample_timesteps, args.timesteps))} of the {args.timesteps} timesteps (bounded sample)"},
+        "cpu_baseline": {"value": value, "unit": "jets/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "jets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def timed_generate(nm, src_dev, ts, dt, cfg, steps, warmup, flush, epic):
+    """ms per call of the device-resident sampler (CUDA events on the launching stream, L2 flushed between calls)."""
+    from mmf_b200 import _abi
+
+    def call(i):
+        if epic:
+            return nm.generate(src_dev.continuous, None, src_dev.mask, ts, dt, None)
+        return nm.generate(src_dev.continuous, src_dev.discrete, src_dev.mask, ts, dt, _abi.step_options(cfg, seed=7, first_global_jet=i * len(src_dev)))
+    for i in range(warmup):
+        call(i)
+    torch.cuda.synchronize()
+    ms = 0.0
+    for i in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call(warmup + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms += e0.elapsed_time(e1)
+    return ms / steps
+
+
+def side_model(name, args, dev):
+    from mmf_b200 import synthetic
+    from mmf_b200.mmf import ConditionalFlowMatching, MultiModalFlowBridge, time_grid
+    from mmf_b200.param_spec import make_config
+    cfg = make_config(name, num_timesteps=args.timesteps, temperature=args.temperature)
+    bridge = (ConditionalFlowMatching if name == "EPiC" else MultiModalFlowBridge)(cfg)
+    bridge.model.load_state_dict(synthetic.make_state_dict(cfg, flavor="wide", seed=0), strict=True)
+    bridge = bridge.to(dev)
+    ts, dt = time_grid(cfg)
+    return cfg, bridge, bridge.model.native(), ts, dt
+
+
+def extra_model_lines(args, peaks, dev, flush, rank):
+    """FusedParticleFormer and EPiC on one GPU, same batch shape and timing rules as the headline (a few steps each)."""
+    from mmf_b200 import synthetic
+    out = {}
+    for name in ("FusedParticleFormer", "EPiC"):
+        cfg, bridge, nm, ts, dt = side_model(name, args, dev)
+        src = synthetic.source_state(args.batch, cfg.max_num_particles, cfg.vocab_size, seed=1234 + 10 * rank)
+        n = src.mask.squeeze(-1).sum(1)
+        ms = timed_generate(nm, src.to(dev), ts, dt, cfg, 3, 3, flush, name == "EPiC")
+        tf = algorithmic_flops_per_timestep(name, n) * args.timesteps / (ms * 1e-3) / 1e12
+        out[name] = {"value": args.batch / (ms * 1e-3), "unit": "jets/s", "ms_per_step": ms, "steps": 3, "warmup": 3,
+                     "roofline": {"bound": "tensor", "kernel": "epic_tile_kernel" if name == "EPiC" else "tf_tile_kernel", "achieved": tf,
+                                  "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops_sustained"]}}
+        del bridge, nm
+    return out
+
+
+def whole_run_lines(args, dev, rank, world):
+    """BASELINE configs #3 / #4 as a whole run on every rank, everything inside the clock: source built on the device
+    (mmf_make_source) -> sampler (mmf_generate_n, asynchronous) -> de-standardise + mask + narrow (mmf_pack_sample) ->
+    ONE all_gather_into_tensor of the per-jet records (13 B/slot).  jets/s = all jets of all ranks / max-over-ranks time."""
+    from mmf_b200 import _abi, distributed as mdist
+    out = {}
+    for name, jets, batch in (("FusedParticleFormer", args.whole_run_jets, 1024), ("EPiC", 4 * args.whole_run_jets, 4096)):
+        cfg, bridge, nm, ts, dt = side_model(name, args, dev)
+        epic = name == "EPiC"
+        D, V = cfg.max_num_particles, cfg.vocab_size
+        probs = torch.exp(-0.5 * ((torch.arange(D + 1, dtype=torch.float64) - 55.0) / 18.0) ** 2)
+        probs[0] = 0.0
+        probs = probs.float().tolist()
+        total = jets * world
+
+        def run():
+            lo, hi = mdist.shard_bounds(total, rank, world)
+            recs = []
+            for b0 in range(lo, hi, batch):
+                b1 = min(b0 + batch, hi)
+                x0, k0, mask, n = _abi.make_source(probs, b1 - b0, D, V, 11, b0, dev, discrete=not epic)
+                x, k, _ = nm.generate(x0, k0, None, ts, dt, None if epic else _abi.step_options(cfg, seed=11, first_global_jet=b0),
+                                      n_per_jet=n.cpu())
+                recs.append(_abi.pack_sample(x, k, mask, [1.9, 0.0, 0.0], [0.8, 0.11, 0.1]))
+            rec = torch.cat(recs, 0)
+            counts = [mdist.shard_bounds(total, r, world)[1] - mdist.shard_bounds(total, r, world)[0] for r in range(world)]
+            return mdist.gather_records(rec, counts)
+
+        run()                                                  # warm-up (workspaces, NCCL communicator)
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        rec = run()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        tmax = torch.tensor([e0.elapsed_time(e1) * 1e-3, wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+        nm.status()
+        assert rec.shape[0] == total
+        out[name] = {"jets": total, "jets_per_rank": jets, "batch": batch, "timesteps": args.timesteps, "temperature": args.temperature,
+                     "seconds_device": float(tmax[0]), "seconds_wall": float(tmax[1]), "value": total / float(tmax[0]), "unit": "jets/s",
+                     "collective": "one all_gather_into_tensor of (jets, %d) uint8 records inside the timed region" % rec.shape[1],
+                     "gathered_bytes": int(rec.numel())}
+        del bridge, nm, rec
+    return out
 
 
 def workload_name(args):
@@ -345,10 +528,8 @@ def main():
     d2h = slots * (3 * 4 + (0 if epic else 8))
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- gather once at the end, as the sharded sampler does (one NCCL collective, outside the loop) --------
-    if world > 1:
-        xg = [torch.empty_like(out.continuous, device=dev) for _ in range(world)]
-        torch.distributed.all_gather(xg, out.continuous.to(dev))
+    # ---- whole runs with the single end-of-run collective INSIDE the clock (all ranks) -----------------------
+    whole_run = None if args.no_extras else whole_run_lines(args, dev, rank, world)
 
     if rank != 0:
         if world > 1:
@@ -407,19 +588,34 @@ def main():
                         "mmf_b200.mmf.MultiModalFlowBridge.predict_step (pinned host batch -> mmf_generate_host)")},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }
+    if whole_run is not None:
+        line["whole_run"] = whole_run
+    if not args.no_extras:
+        if not epic and not args.dense:
+            # the dense worst case (every jet 150 particles -> CTA-pair tiles) on the same kernel, same timing rules
+            dsrc = synthetic.source_state(B, cfg.max_num_particles, cfg.vocab_size, dense=True, seed=1234)
+            dms = timed_generate(nm, dsrc.to(dev), ts, dt, cfg, 2, 2, flush, False)
+            dn = dsrc.mask.squeeze(-1).sum(1)
+            dtf = algorithmic_flops_per_timestep(args.model, dn) * args.timesteps / (dms * 1e-3) / 1e12
+            line["roofline_dense"] = {"bound": "tensor", "kernel": "tf_tile_kernel (pair tiles: one 150-particle jet per 2-CTA cluster)",
+                                      "workload": f"{args.model}, {B} jets of 150 particles x {args.timesteps} timesteps", "value": B / (dms * 1e-3),
+                                      "unit_value": "jets/s", "ms_per_step": dms, "achieved": dtf, "peak": peaks["bf16_tflops_sustained"],
+                                      "unit": "TFLOP/s", "frac": dtf / peaks["bf16_tflops_sustained"], "steps": 2, "warmup": 2}
+        line["extra_models"] = extra_model_lines(args, peaks, dev, flush, rank)
     if not args.no_step_roofline and not epic:
         line["roofline_step_kernel"] = step_kernel_roofline(peaks, dev)
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        rate, s_per_ts = cpu_port_rate(args, cfg, sd, args.cpu_sample_jets, args.cpu_sample_timesteps)
-        line["cpu_baseline"] = {
-            "value": rate, "unit": "jets/s", "cores": cores, "kind": "port",
-            "sample": f"{args.cpu_sample_jets} jets x {args.cpu_sample_timesteps} timesteps of the same workload "
-                      f"({s_per_ts:.3f} s/timestep), extrapolated to {args.timesteps} timesteps; oracle/mmf_oracle.py torch fp32"}
-        if args.cpu_sample_jets < args.batch:
-            # the same port on the WHOLE batch, one timestep: what the reference's own batch size costs on these cores
-            wb_rate, wb_s = cpu_port_rate(args, cfg, sd, args.batch, 1)
-            line["cpu_baseline"]["whole_batch_probe"] = {"value": wb_rate, "unit": "jets/s", "sample": f"{args.batch} jets x 1 timestep ({wb_s:.2f} s), extrapolated"}
+        value_cpu, per_step, kind, sample = cpu_reference_measure(args, cfg, sd, 1, 1)
+        line["cpu_baseline"] = {"value": value_cpu, "unit": "jets/s", "cores": cores, "kind": kind, "sample": sample}
+        if not args.no_extras:
+            # the same fp32 algorithm as plain eager torch on THIS GPU (TF32 off, the torch default)
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            S = max(1, min(args.eager_timesteps, args.timesteps))
+            rate, s_per_ts = cpu_port_rate(args, cfg, sd, args.batch, S, device=str(dev))
+            line["gpu_eager_baseline"] = {"value": rate, "unit": "jets/s", "kind": "port on cuda (oracle/mmf_oracle.py, eager torch fp32, TF32 off)",
+                                          "sample": f"the whole batch of {args.batch} jets x {S} timesteps ({s_per_ts * 1e3:.1f} ms/timestep), scaled to {args.timesteps} timesteps"}
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()

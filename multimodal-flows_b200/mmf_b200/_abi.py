@@ -34,6 +34,12 @@ class MmfStepOptions(ctypes.Structure):
     _fields_ = [("temperature", c_float), ("beta", c_float), ("top_k", c_int32), ("top_p", c_float),
                 ("use_final_max_rates", c_int32), ("method", c_int32), ("seed", c_uint64), ("first_global_jet", c_uint64)]
 
+    def __init__(self, temperature=1.0, beta=0.075, top_k=0, top_p=0.0, use_final_max_rates=0, seed=0, first_global_jet=0,
+                 method=0):
+        # (`method` sits in what used to be padding of the C struct; positional construction keeps its historical order)
+        super().__init__(temperature=temperature, beta=beta, top_k=top_k, top_p=top_p, use_final_max_rates=use_final_max_rates,
+                         method=method, seed=seed, first_global_jet=first_global_jet)
+
 
 _lib: Optional[ctypes.CDLL] = None
 
