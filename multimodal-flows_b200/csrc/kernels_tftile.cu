@@ -27,20 +27,13 @@ namespace {
 constexpr int kEpi = 256;
 constexpr int kThreads = 384;
 constexpr int kProducers = 1;              // warp 10 (one warp keeps up: the ring is latency-bound, ~500 cycles per copy suffice)
-constexpr int kTile = 16384;                // operand chunk: [128 rows][64] bf16
+constexpr int kTile = 16384;                // k-tile of a B operand in the arena: 64 keys x 128 bytes (V rows of a P V k-tile)
 constexpr int kBars = kTfRingBars;          // weight-ring barrier pairs, used round robin by tile index
 #ifndef MMF_COPY_SPLIT
 #define MMF_COPY_SPLIT 1
 #endif
 constexpr int kCopySplit = MMF_COPY_SPLIT;   // bulk copies per weight-tile slice
-// operand arena (bytes); every region is 1024-byte aligned
-constexpr uint32_t oA = 0;                       // 4 chunks [128 x 64] bf16: LayerNorm output / head input
-constexpr uint32_t oQ = 65536, oK = oQ + kTile;  // Q | K of the current unit; P (probabilities) aliases both
-constexpr uint32_t oVT = oK + kTile;             // V [128 keys][64 d] (the MN-major B operand of P V)
-constexpr uint32_t oO = oVT + kTile;             // attention output of the current unit [128 x 64]
-constexpr uint32_t oH0 = oQ, oH1 = oVT;          // MLP hidden quarters [128 x 128] (two chunks each), ping-pong
-constexpr uint32_t oRing = oO + kTile;           // weight ring
-constexpr int kArena = oRing + kTfRingBytes;
+// operand arena: TfLay<PAIR> in mmf_tftile.h (plain tiles / pair tiles)
 
 // Hand-offs epilogue -> weight-GEMM issuer rotate over kGoBars barriers: a waiter tells phases apart by parity only, and
 // with two issuer warps the GEMM issuer can be a hand-off behind (an unsignalled projection waiting for its weight tile
@@ -48,6 +41,9 @@ constexpr int kArena = oRing + kTfRingBytes;
 constexpr int kGoBars = 4;
 struct TfBars {
     uint64_t full[kBars], empty[kBars], done[4], go[kGoBars], go_attn, pfull[2], pempty[2];
+    // pair tiles: kvfull - the partner's epilogue has written its K / V rows of the current unit into this CTA (256 remote
+    // arrivals); kvfree - the partner's MMAs have finished reading ITS K / V buffers, this CTA may write the next unit's rows
+    uint64_t kvfull, kvfree;
     uint32_t tmem_base;
 };
 
@@ -57,8 +53,8 @@ struct TfBars {
 constexpr int mXs = 0, mKs = mXs + 384, mStat = mKs + 128, mRed = mStat + 1024, mSum = mRed + 512, mOut = mStat,
               mTemb = mSum + 512, mEnd = mTemb + 512;
 static_assert(128 * 12 <= 1024 + 512 + 512, "head partial sums alias the exchange buffers");
-constexpr int kSmemBytes = 1024 + 1024 + kArena + 2 * kTfParamFloats * 4 + mEnd * 4;
-static_assert(kSmemBytes <= 232448, "shared memory budget");
+template <bool PAIR> constexpr int smem_bytes() { return 1024 + 1024 + static_cast<int>(TfLay<PAIR>::kArena) + 2 * kTfParamFloats * 4 + mEnd * 4; }
+static_assert(smem_bytes<false>() <= 232448 && smem_bytes<true>() <= 232448, "shared memory budget");
 
 constexpr uint32_t kScr = 256;                   // first scratch column in TMEM
 
@@ -74,6 +70,8 @@ struct Epi {
     uint32_t gc;             // hand-offs to the weight-GEMM issuer so far (barrier gc % kGoBars, parity (gc / kGoBars) & 1)
     uint32_t kmask, kfull, kpart;   // 16-key groups of this thread's key half: attended by any row of the warp / in full by
                                     // every row / cut by a jet boundary of some row
+    // pair tiles: shared::cluster address of the partner CTA's arena and barriers, hand-off counter of attention units
+    uint32_t peer_arena, peer_kvfull, peer_kvfree, uc;
     unsigned long long* trace;   // clock stamps of CTA 0 / thread 0 for the first two timesteps (debugging aid) or null
     int mark_i, step;
 };
@@ -131,6 +129,16 @@ __device__ __forceinline__ void param_release(Epi& e) {
 
 __device__ __forceinline__ float4 ldf4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 
+// Pair tiles: operand rows 80...127 do not exist in shared memory (TfLay<true>), so the threads of those rows run the
+// whole program (tcgen05.ld / barriers are collective) but never store an operand row.
+template <bool PAIR>
+__device__ __forceinline__ bool row_ok(int r) { return !PAIR || r < static_cast<int>(TfLay<true>::kRows); }
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// generic-proxy writes (also those to the partner's shared memory) -> visible to tcgen05.mma operand reads
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // Reductions over register arrays with four independent chains: the epilogue runs two warps per scheduler, so a
 // 32-deep dependent chain would leave the issue slots empty.
 template <int N>
@@ -176,8 +184,10 @@ __device__ __forceinline__ float max_regs(const float* v) {
 }
 
 // 32 fp32 values -> bf16 into the operand chunk that holds absolute column col0 (multiple of 32) of a 256-wide row
+template <bool PAIR>
 __device__ __forceinline__ void stage32(uint8_t* abase, int r, int col0, const float* v) {
-    uint8_t* ch = abase + (col0 >> 6) * kTile;
+    if (!row_ok<PAIR>(r)) return;
+    uint8_t* ch = abase + (col0 >> 6) * TfLay<PAIR>::kChunk;
     const uint32_t u0 = (col0 & 63) >> 3;
 #pragma unroll
     for (int u = 0; u < 4; ++u)
@@ -242,6 +252,7 @@ __device__ __forceinline__ void ln_stats(Epi& e, const RowStat& st, int slot, fl
     }
 }
 // normalised row -> bf16 GEMM operand (Abuf)
+template <bool PAIR>
 __device__ __forceinline__ void ln_to_abuf(Epi& e, float mean, float rstd, const float* g, const float* b) {
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
@@ -257,7 +268,7 @@ __device__ __forceinline__ void ln_to_abuf(Epi& e, float mean, float rstd, const
             MMF_SET2(v, 4 * u, f2fma(f2mul(f2add(MMF_V2(v, 4 * u), nm), rs), make_float2(gg.x, gg.y), make_float2(bb.x, bb.y)));
             MMF_SET2(v, 4 * u + 2, f2fma(f2mul(f2add(MMF_V2(v, 4 * u + 2), nm), rs), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w)));
         }
-        stage32(e.arena + oA, e.r, e.hf * 128 + c0, v);
+        stage32<PAIR>(e.arena + TfLay<PAIR>::oA, e.r, e.hf * 128 + c0, v);
     }
 }
 // normalised row (+ post) -> back into the residual stream; returns the new row statistics (stream junction of ParticleFormer)
@@ -304,17 +315,27 @@ __device__ __forceinline__ void ln_regs(float* v, const float* g, const float* b
 // ---- attention epilogues -----------------------------------------------------------------------------------------
 // QKV of one 64-column unit sits in scratch (q | k | v, 64 columns each).  hf 0: q and v[0,32); hf 1: k and v[32,64).
 // bq/bk/bv point at the unit's 64 bias values; qg.. are the per-head LayerNorm parameters ([HS]).
-template <int HS>
+template <int HS, bool PAIR>
 struct QkvCols {     // scratch columns of q|k and v (see the op emission in tftile_model.cu)
-    static constexpr uint32_t cQK = HS == 64 ? kScr : kScr + 128, cV = HS == 64 ? kScr + 128 : kScr + 64;
+    static constexpr uint32_t cQK = HS == 64 ? TfLay<PAIR>::cQkv64 : kScr + 128, cV = HS == 64 ? TfLay<PAIR>::cQkv64 + 128 : kScr + 64;
 };
+// row `row` of a [keys][128 B] swizzled chunk in the PARTNER's arena (pair tiles): units u0 .. u0 + NU - 1 from packed words
+template <int NU>
+__device__ __forceinline__ void stage_units_remote(uint32_t peer_chunk, int row, int u0, const float* v) {
+#pragma unroll
+    for (int u = 0; u < NU; ++u)
+        st_cluster_v4(peer_chunk + sw128_offset(row, u0 + u), pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                      pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+}
 // q and k: bias, per-head LayerNorm, bf16 -> the Q / K operand chunks.  The score product only needs these.
-template <int HS>
+// Pair tiles: k of row r is key r here and key 80 + r in the partner CTA.
+template <int HS, bool PAIR>
 __device__ __forceinline__ void qk_epilogue(Epi& e, const float* bq, const float* bk, const float* qg, const float* qb,
                                             const float* kg, const float* kb) {
+    using L = TfLay<PAIR>;
     float v[64];
-    tmem_ld32(e.taddr + QkvCols<HS>::cQK + e.hf * 64, v);
-    tmem_ld32(e.taddr + QkvCols<HS>::cQK + e.hf * 64 + 32, v + 32);
+    tmem_ld32(e.taddr + QkvCols<HS, PAIR>::cQK + e.hf * 64, v);
+    tmem_ld32(e.taddr + QkvCols<HS, PAIR>::cQK + e.hf * 64 + 32, v + 32);
     tmem_ld_wait();
     const float* bias = e.hf ? bk : bq;
 #pragma unroll
@@ -329,14 +350,18 @@ __device__ __forceinline__ void qk_epilogue(Epi& e, const float* bq, const float
         if (HS == 64) ln_regs<64>(v, g, b);
         else { ln_regs<32>(v, g, b); ln_regs<32>(v + 32, g, b); }
     }
-    stage_row_bf16(e.arena + (e.hf ? oK : oQ), e.r, v);
+    if (row_ok<PAIR>(e.r)) {
+        stage_row_bf16(e.arena + (e.hf ? L::oK : L::oQ), e.r, v);
+        if (PAIR && e.hf) stage_units_remote<8>(e.peer_arena + L::oK, static_cast<int>(L::kRows) + e.r, 0, v);
+    }
 }
-// v: bias, bf16 -> V[key = r][d] (row r of a [128][128 B] swizzled chunk: the MN-major B operand of P V, so no transpose);
-// runs under the score MMA
-template <int HS>
+// v: bias, bf16 -> V[key = r][d] (row r of a [keys][128 B] swizzled chunk: the MN-major B operand of P V, so no transpose);
+// runs under the score MMA (plain tiles) / before it (pair tiles: the 160 score columns cover the v accumulator)
+template <int HS, bool PAIR>
 __device__ __forceinline__ void v_epilogue(Epi& e, const float* bv) {
+    using L = TfLay<PAIR>;
     float w[32];
-    tmem_ld32(e.taddr + QkvCols<HS>::cV + e.hf * 32, w);
+    tmem_ld32(e.taddr + QkvCols<HS, PAIR>::cV + e.hf * 32, w);
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
@@ -344,27 +369,34 @@ __device__ __forceinline__ void v_epilogue(Epi& e, const float* bv) {
         MMF_SET2(w, i, f2add(MMF_V2(w, i), make_float2(b.x, b.y)));
         MMF_SET2(w, i + 2, f2add(MMF_V2(w, i + 2), make_float2(b.z, b.w)));
     }
-    uint8_t* vb = e.arena + oVT;
+    if (!row_ok<PAIR>(e.r)) return;
+    uint8_t* vb = e.arena + L::oVT;
 #pragma unroll
     for (int u = 0; u < 4; ++u)
         st_shared_v4(vb + sw128_offset(e.r, e.hf * 4 + u), pack_bf16x2(w[8 * u], w[8 * u + 1]), pack_bf16x2(w[8 * u + 2], w[8 * u + 3]),
                      pack_bf16x2(w[8 * u + 4], w[8 * u + 5]), pack_bf16x2(w[8 * u + 6], w[8 * u + 7]));
+    if (PAIR) stage_units_remote<4>(e.peer_arena + L::oVT, static_cast<int>(L::kRows) + e.r, e.hf * 4, w);
 }
 
-// scores of one head in scratch columns [scol, scol+128); thread handles keys [hf*64, +64) of its row.
-// e.kmask: which of the thread's four 16-key groups hold a key of ANY row of this warp (warp-uniform, fixed for the
+// scores of one head in scratch columns [scol, scol + 2 NK); thread handles keys [hf*NK, +NK) of its row (NK = 64: plain
+// tiles; NK = 80: pair tiles, hf 0 = the CTA's own rows, hf 1 = the partner's).
+// e.kmask: which of the thread's 16-key groups hold a key of ANY row of this warp (warp-uniform, fixed for the
 // launch): the other groups are outside every jet of these 32 rows, so their probabilities are exact zeros.
 // softmax_probs leaves the unnormalised probabilities in s[] and returns their sum; softmax_store writes them as the bf16
-// P operand (chunk hf of the Q|K staging area, which the previous P V product must have finished reading).
-// `slot` selects the exchange buffers.
+// P operand (plain: chunk hf of the Q|K staging area, which the previous P V product must have finished reading; pair: its
+// own region).  `slot` selects the exchange buffers.
 // `release_gemm`: the scores read here are the last live scratch columns the next unit's QKV product overwrites, so the
 // weight-GEMM issuer is handed that product as soon as they sit in registers (a whole softmax earlier than the P V hand-off;
 // it reads only Abuf and the ring, no shared memory written by this epilogue, hence no proxy fence).
-__device__ __forceinline__ float softmax_probs(Epi& e, uint32_t scol, float scale_log2e, int kb, int ke, int slot, float* s,
+// Key j of this thread is valid iff (unsigned)(j - lo) < span (plain: the row's jet; pair: the real rows of that CTA).
+template <int NK>
+__device__ __forceinline__ float softmax_probs(Epi& e, uint32_t scol, float scale_log2e, int lo, uint32_t span, int slot, float* s,
                                                bool release_gemm = false) {
+    constexpr int NG = NK / 16;
     const uint32_t km = e.kmask;
-    tmem_ld32(e.taddr + scol + e.hf * 64, s);
-    tmem_ld32(e.taddr + scol + e.hf * 64 + 32, s + 32);
+    tmem_ld32(e.taddr + scol + e.hf * NK, s);
+    tmem_ld32(e.taddr + scol + e.hf * NK + 32, s + 32);
+    if (NK == 80) tmem_ld16(e.taddr + scol + e.hf * NK + 64, s + 64);
     tmem_ld_wait();
     if (release_gemm) {
         tc_fence_before();
@@ -372,18 +404,16 @@ __device__ __forceinline__ float softmax_probs(Epi& e, uint32_t scol, float scal
         ++e.gc;
     }
     // keys outside the row's jet get -inf: they drop out of the max and ex2(-inf) = 0 removes them from the sum.
-    // Key j of this thread is valid iff (unsigned)(j - lo) < span.  lo / span are made opaque here: otherwise the compiler
-    // hoists the 64 comparisons out of the timestep loop into a bit mask and then serialises on predicate registers.
+    // lo / span are made opaque here: otherwise the compiler hoists the comparisons out of the timestep loop into a bit
+    // mask and then serialises on predicate registers.
     // Per 16-key group (all warp-uniform, fixed for the launch): e.kfull - inside the jet of every row of the warp, no
     // masking; e.kpart - a jet boundary of some row falls inside the group, per-key masks; otherwise every row is either
     // all-in or all-out and one per-lane predicate covers the 16 keys.
-    int lo = kb - e.hf * 64;
-    uint32_t span = static_cast<uint32_t>(ke - kb);
     asm volatile("" : "+r"(lo), "+r"(span));
     const int hi = lo + static_cast<int>(span);
     float mx = -INFINITY;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < NG; ++g) {
         if (km & (1u << g)) {
             if (e.kpart & (1u << g)) {
 #pragma unroll
@@ -403,7 +433,7 @@ __device__ __forceinline__ float softmax_probs(Epi& e, uint32_t scol, float scal
     const float msc = (mx == -INFINITY) ? 0.f : mx * scale_log2e;
     float sum = 0.f;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < NG; ++g) {
         if (km & (1u << g)) {
 #pragma unroll
             for (int j = 16 * g; j < 16 * g + 16; j += 2) {
@@ -418,18 +448,31 @@ __device__ __forceinline__ float softmax_probs(Epi& e, uint32_t scol, float scal
     }
     return sum;
 }
+template <bool PAIR>
 __device__ __forceinline__ void softmax_store(Epi& e, int slot, const float* s, float sum) {
-    stage_row_bf16(e.arena + (e.hf ? oK : oQ), e.r, s);          // P chunk hf (keys hf*64..)
+    using L = TfLay<PAIR>;
+    if (!PAIR) {
+        stage_row_bf16(e.arena + (e.hf ? L::oK : L::oQ), e.r, s);          // P chunk hf (keys hf*64..)
+    } else if (row_ok<PAIR>(e.r)) {
+        // keys [hf*80, +80) = 16-byte units hf*10 .. hf*10 + 9 of the row; 8 units per 64-key chunk, chunks kChunk apart
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            const int U = e.hf * 10 + i;
+            st_shared_v4(e.arena + L::oP + (U >> 3) * L::kChunk + sw128_offset(e.r, U & 7), pack_bf16x2(s[8 * i], s[8 * i + 1]),
+                         pack_bf16x2(s[8 * i + 2], s[8 * i + 3]), pack_bf16x2(s[8 * i + 4], s[8 * i + 5]), pack_bf16x2(s[8 * i + 6], s[8 * i + 7]));
+        }
+    }
     e.misc[mSum + slot * 256 + e.hf * 128 + e.r] = sum;
 }
-__device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, float scale_log2e, int kb, int ke, int slot, bool release_gemm = false) {
-    float s[64];
-    const float sum = softmax_probs(e, scol, scale_log2e, kb, ke, slot, s, release_gemm);
-    softmax_store(e, slot, s, sum);
+template <bool PAIR>
+__device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, float scale_log2e, int lo, uint32_t span, int slot, bool release_gemm = false) {
+    float s[PAIR ? 80 : 64];
+    const float sum = softmax_probs<PAIR ? 80 : 64>(e, scol, scale_log2e, lo, span, slot, s, release_gemm);
+    softmax_store<PAIR>(e, slot, s, sum);
 }
 
 // O = P V of one head in scratch columns [ocol, ocol+HS) -> normalised bf16 into Os columns [ucol, ucol+HS) of the unit
-template <int HS>
+template <int HS, bool PAIR>
 __device__ __forceinline__ void o_epilogue(Epi& e, uint32_t ocol, int ucol, int slot) {
     const float tot = e.misc[mSum + slot * 256 + e.r] + e.misc[mSum + slot * 256 + 128 + e.r];
     const float inv = rcp_approx(tot > 0.f ? tot : 1.f);
@@ -438,8 +481,9 @@ __device__ __forceinline__ void o_epilogue(Epi& e, uint32_t ocol, int ucol, int 
     if (W == 32) tmem_ld32(e.taddr + ocol + e.hf * W, o);
     else tmem_ld16(e.taddr + ocol + e.hf * W, o);
     tmem_ld_wait();
+    if (!row_ok<PAIR>(e.r)) return;
     const uint32_t u0 = (ucol + e.hf * W) >> 3;
-    uint8_t* os = e.arena + oO;
+    uint8_t* os = e.arena + TfLay<PAIR>::oO;
     // (the products below are written o[i] * inv: the compiler does not pair them, so scale the row with packed multiplies first)
 #pragma unroll
     for (int i = 0; i < W; i += 2) MMF_SET2(o, i, f2mul(MMF_V2(o, i), f2dup(inv)));
@@ -450,19 +494,22 @@ __device__ __forceinline__ void o_epilogue(Epi& e, uint32_t ocol, int ucol, int 
 }
 
 // MLP hidden quarter q in scratch half (q&1): GELU(acc + bias) -> bf16 H(q&1); `bias` points at the quarter's 128 values
+template <bool PAIR>
 __device__ __forceinline__ void fc_epilogue(Epi& e, int q, const float* bias) {
+    using L = TfLay<PAIR>;
     float v[64];
     const uint32_t col = kScr + (q & 1) * 128 + e.hf * 64;
     tmem_ld32(e.taddr + col, v);
     tmem_ld32(e.taddr + col + 32, v + 32);
     tmem_ld_wait();
+    if (!row_ok<PAIR>(e.r)) return;
 #pragma unroll
     for (int i = 0; i < 64; i += 4) {
         const float4 a = ldf4(bias + e.hf * 64 + i);
         MMF_SET2(v, i, gelu_tile2(f2add(MMF_V2(v, i), make_float2(a.x, a.y))));
         MMF_SET2(v, i + 2, gelu_tile2(f2add(MMF_V2(v, i + 2), make_float2(a.z, a.w))));
     }
-    stage_row_bf16(e.arena + ((q & 1) ? oH1 : oH0) + e.hf * kTile, e.r, v);
+    stage_row_bf16(e.arena + ((q & 1) ? L::oH1 : L::oH0) + e.hf * L::kChunk, e.r, v);
 }
 
 // head hidden quarter: GELU(acc + bias) dotted with NO output rows of W2 (row stride ld), accumulated into out[]
@@ -494,49 +541,94 @@ __device__ __forceinline__ void head_epilogue(Epi& e, int q, const float* bias, 
 }
 
 // one attention unit (64 q-columns = 64/HS heads) of the current block, epilogue side
-template <int HS>
+template <int HS, bool PAIR>
 __device__ __forceinline__ void attention_unit(Epi& e, bool first, bool more, const float* bq, const float* bk, const float* bv, const float* qg,
-                                               const float* qb, const float* kg, const float* kb, int seg_b, int seg_e) {
+                                               const float* qb, const float* kg, const float* kb, int lo, uint32_t span) {
+    using L = TfLay<PAIR>;
     const float scale = 1.4426950408889634f * rsqrtf(static_cast<float>(HS));
     wait_done(e, 1);                                  // QKV of this unit (issued under the previous unit's epilogue)
-    qk_epilogue<HS>(e, bq, bk, qg, qb, kg, kb);
-    go_attn(e);                                       // -> S
-    v_epilogue<HS>(e, bv);                            // under the score MMA; P V is only issued after the next hand-off
-    if (HS == 64) {
-        wait_done(e, 0);
-        softmax_epilogue(e, kScr, scale, seg_b, seg_e, 0, more);   // (S in registers -> the QKV GEMM of the next unit)
-        go_attn(e);                                       // -> P V
-        wait_done(e, 0);
-        if (!first) wait_done(e, 2);                      // the previous unit's projection (other issuer warp) has read oO
-        o_epilogue<64>(e, kScr + 192, 0, 0);
-        go(e);                                            // -> projection
+    if (!PAIR) {
+        qk_epilogue<HS, false>(e, bq, bk, qg, qb, kg, kb);
+        go_attn(e);                                       // -> S
+        v_epilogue<HS, false>(e, bv);                     // under the score MMA; P V is only issued after the next hand-off
+        if (HS == 64) {
+            wait_done(e, 0);
+            softmax_epilogue<false>(e, kScr, scale, lo, span, 0, more);   // (S in registers -> the QKV GEMM of the next unit)
+            go_attn(e);                                       // -> P V
+            wait_done(e, 0);
+            if (!first) wait_done(e, 2);                      // the previous unit's projection (other issuer warp) has read oO
+            o_epilogue<64, false>(e, kScr + 192, 0, 0);
+            go(e);                                            // -> projection
+        } else {
+            wait_done(e, 0);                                  // both heads' scores: [256,384) and [384,512)
+            softmax_epilogue<false>(e, kScr, scale, lo, span, 0);
+            go_attn(e);                                       // -> P V of head 0
+            float s[64];                                      // head 1's probabilities are computed under that product ...
+            const float sum = softmax_probs<64>(e, kScr + 128, scale, lo, span, 1, s, more);   // (both S in registers -> next QKV GEMM)
+            wait_done(e, 3);                                  // ... and stored once it has finished reading head 0's
+            softmax_store<false>(e, 1, s, sum);
+            go_attn(e);                                       // -> P V of head 1
+            if (!first) wait_done(e, 2);                      // the previous unit's projection (other issuer warp) has read oO
+            o_epilogue<32, false>(e, kScr, 0, 0);             // O of head 0 in scratch [0,32), under P V of head 1
+            wait_done(e, 0);                                  // O of head 1 in scratch [32,64)
+            o_epilogue<32, false>(e, kScr + 32, 32, 1);
+            go(e);
+        }
     } else {
-        wait_done(e, 0);                                  // both heads' scores: [256,384) and [384,512)
-        softmax_epilogue(e, kScr, scale, seg_b, seg_e, 0);
-        go_attn(e);                                       // -> P V of head 0
-        float s[64];                                      // head 1's probabilities are computed under that product ...
-        const float sum = softmax_probs(e, kScr + 128, scale, seg_b, seg_e, 1, s, more);   // (both S in registers -> next QKV GEMM)
-        wait_done(e, 3);                                  // ... and stored once it has finished reading head 0's
-        softmax_store(e, 1, s, sum);
-        go_attn(e);                                       // -> P V of head 1
-        if (!first) wait_done(e, 2);                      // the previous unit's projection (other issuer warp) has read oO
-        o_epilogue<32>(e, kScr, 0, 0);                    // O of head 0 in scratch [0,32), under P V of head 1
-        wait_done(e, 0);                                  // O of head 1 in scratch [32,64)
-        o_epilogue<32>(e, kScr + 32, 32, 1);
-        go(e);
+        // ---- pair tile: this CTA holds one half of a 129...160-particle jet; keys = own 80 rows | partner's 80 rows ----
+        // The partner's MMAs of the previous unit must have finished reading ITS K / V buffers before this CTA writes
+        // the rows of this unit into them (kvfree, one phase per unit).
+        if (e.uc > 0) mbar_wait_cluster(&e.bars->kvfree, (e.uc - 1) & 1);
+        qk_epilogue<HS, true>(e, bq, bk, qg, qb, kg, kb);
+        v_epilogue<HS, true>(e, bv);                      // (before S: its 160 columns cover the v accumulator)
+        fence_proxy_async_all();
+        mbar_arrive_remote(e.peer_kvfull);                // my K / V rows are in the partner's arena
+        go_attn(e);                                       // -> S (the issuer also waits for the partner's rows: kvfull)
+        constexpr uint32_t cS = L::cS;
+        if (HS == 64) {
+            wait_done(e, 0);
+            softmax_epilogue<true>(e, cS, scale, lo, span, 0, more);
+            go_attn(e);                                       // -> P V (O in scratch [0,64))
+            wait_done(e, 0);
+            mbar_arrive_remote(e.peer_kvfree);                // this CTA has finished reading its K / V buffers
+            if (!first) wait_done(e, 2);
+            o_epilogue<64, true>(e, L::cO64, 0, 0);
+            go(e);                                            // -> projection
+        } else {
+            // the two heads take turns on the score columns: S0, softmax 0, then S1 under the P store of head 0
+            wait_done(e, 0);                                  // S of head 0
+            float s[80];
+            float sum = softmax_probs<80>(e, cS, scale, lo, span, 0, s);
+            go_attn(e);                                       // S0 in registers -> S of head 1 may overwrite its columns
+            softmax_store<true>(e, 0, s, sum);                // (P is free: the previous unit's P V products were waited for)
+            go_attn(e);                                       // -> P V of head 0 (done[3])
+            wait_done(e, 0);                                  // S of head 1
+            sum = softmax_probs<80>(e, cS, scale, lo, span, 1, s, more);   // (all scores in registers -> next QKV GEMM)
+            wait_done(e, 3);                                  // P V of head 0 has read P
+            softmax_store<true>(e, 1, s, sum);
+            go_attn(e);                                       // -> P V of head 1
+            if (!first) wait_done(e, 2);
+            o_epilogue<32, true>(e, kScr, 0, 0);              // O of head 0 in scratch [0,32), under P V of head 1
+            wait_done(e, 0);                                  // O of head 1 in scratch [32,64)
+            mbar_arrive_remote(e.peer_kvfree);
+            o_epilogue<32, true>(e, kScr + 32, 32, 1);
+            go(e);
+        }
+        ++e.uc;
     }
 }
 
-template <int V>
+template <int V, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_constant__ TfLaunch a, const __grid_constant__ TfOpTable optab,
                                                               const __grid_constant__ TfProdTable prodtab) {
+    using L = TfLay<PAIR>;
     // The dynamic shared window starts 1024-byte aligned (no static shared memory in this kernel); it is used directly so
     // that the compiler keeps the shared address space (LDS/STS instead of generic loads).  SWIZZLE_128B needs the alignment.
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     TfBars* bars = reinterpret_cast<TfBars*>(smem);
     uint8_t* arena = smem + 1024;
-    float* pbuf = reinterpret_cast<float*>(arena + kArena);
+    float* pbuf = reinterpret_cast<float*>(arena + L::kArena);
     float* misc = pbuf + 2 * kTfParamFloats;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -556,6 +648,8 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
         for (int i = 0; i < kGoBars; ++i) mbar_init(&bars->go[i], kEpi);
         mbar_init(&bars->go_attn, kEpi);
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->pfull[i], 1); mbar_init(&bars->pempty[i], kEpi); }
+        mbar_init(&bars->kvfull, kEpi);                   // pair tiles: arrivals of the partner CTA's epilogue threads
+        mbar_init(&bars->kvfree, kEpi);
         fence_mbar_init();
     }
     if (warp == 9) {
@@ -608,7 +702,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                     uint64_t* full = &bars->full[g % kBars];
                     mbar_expect_tx(full, bytes);
                     const uint32_t slice = cs == 1 ? bytes : (cs == 2 ? bytes >> 1 : bytes >> 2), part = slice / kCopySplit;
-                    uint8_t* dst = arena + oRing + (ent.y & 0xffu) * 1024u + crank * slice;
+                    uint8_t* dst = arena + L::oRing + (ent.y & 0xffu) * 1024u + crank * slice;
                     const uint8_t* src = a.wstream + static_cast<size_t>(ent.x & 0xffffffu) * 128u + crank * slice;
 #pragma unroll
                     for (int c = 0; c < kCopySplit; ++c) {
@@ -625,9 +719,9 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
         const bool attn_issuer = warp == 11;
         // All 32 lanes run the loop converged (op fields stay in uniform registers, the table sits in the constant bank);
         // one elected lane issues the asynchronous instructions.  Descriptors come precomputed from the host.
-        uint32_t pg = 0, gbase = 0;                           // hand-offs consumed so far
+        uint32_t pg = 0, gbase = 0, pk = 0;                   // hand-offs consumed so far; pair tiles: kvfull phases consumed
         const uint32_t base16 = smem_u32(arena) >> 4;
-        const uint32_t ring16 = base16 + (oRing >> 4) + (1u << 16);
+        const uint32_t ring16 = base16 + (L::oRing >> 4) + (1u << 16);
         constexpr uint64_t kDescHi = static_cast<uint64_t>(0x40004040u) << 32;   // SBO 1024 B | version 1 | SWIZZLE_128B
         for (int step = 0; step < a.nsteps; ++step, gbase += a.n_prod) {
             TfOp nx = optab.ops[0];
@@ -642,10 +736,15 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                     else mbar_wait(&bars->go[pg % kGoBars], (pg / kGoBars) & 1, static_cast<uint32_t>(i));
                     ++pg;
                 }
+                if (PAIR && (op.nkt & kTfNktPairWait)) {      // the partner's K / V rows of this unit (written through DSMEM)
+                    mbar_wait_cluster(&bars->kvfull, pk & 1);
+                    ++pk;
+                    fence_proxy_async_all();
+                }
                 const bool ring = (fl & kTfOpRing) != 0;
                 uint32_t a_lo = op.a_lo + base16, b_lo = op.b_lo + base16, acc = fl & kTfOpAcc;
                 const uint32_t d = tmem_base + op.dcol;
-                const uint32_t nkt = op.nkt & 0x7fu, sig = ((fl >> 4) & 3u) | ((op.nkt & 0x80u) >> 5);
+                const uint32_t nkt = op.nkt & 0x3fu, sig = ((fl >> 4) & 3u) | ((op.nkt & 0x80u) >> 5);
                 for (uint32_t kt = 0; kt < nkt; ++kt) {
                     const uint32_t g = gbase + ti;
                     if (ring) {
@@ -669,7 +768,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                         }
                     }
                     __syncwarp();
-                    a_lo += kTile >> 4;
+                    a_lo += L::kChunk >> 4;
                     b_lo += 8192 >> 4;
                     acc = 1u;
                 }
@@ -701,15 +800,28 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
             for (int c = 0; c < 3; ++c) s_xs[tid * 3 + c] = a.xs0[(static_cast<size_t>(tile) * 128 + tid) * 3 + c];
             s_ks[tid] = a.ks0[static_cast<size_t>(tile) * 128 + tid];
         }
-        const int seg_b = meta->seg_beg[r], seg_e = meta->seg_end[r];
+        // keys this thread's row attends, in the coordinates of the thread's own key range [hf*NK, hf*NK + NK):
+        // plain tile: the rows of its jet; pair tile: the real rows of this CTA (hf 0) / of the partner (hf 1)
+        constexpr int NK = PAIR ? 80 : 64;
+        const int seg_b = PAIR ? hf * NK : meta->seg_beg[r];
+        const int seg_e = PAIR ? hf * NK + (hf ? meta->pad[0] : meta->nrows) : meta->seg_end[r];
+        const int att_lo = seg_b - hf * NK;
+        const uint32_t att_span = static_cast<uint32_t>(seg_e - seg_b);
         e.kmask = 0; e.kfull = 0; e.kpart = 0;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            const int k0 = hf * 64 + 16 * g;
+        for (int g = 0; g < NK / 16; ++g) {
+            const int k0 = hf * NK + 16 * g;
             if (__ballot_sync(0xffffffffu, seg_b < k0 + 16 && seg_e > k0) != 0u) e.kmask |= 1u << g;
             if (__all_sync(0xffffffffu, seg_b <= k0 && seg_e >= k0 + 16)) e.kfull |= 1u << g;
             const bool in = seg_b <= k0 && seg_e >= k0 + 16, out = seg_e <= k0 || seg_b >= k0 + 16;
             if (!__all_sync(0xffffffffu, in || out)) e.kpart |= 1u << g;
+        }
+        e.uc = 0;
+        e.peer_arena = 0; e.peer_kvfull = 0; e.peer_kvfree = 0;
+        if (PAIR) {
+            e.peer_arena = dsmem_addr(arena, crank ^ 1u);
+            e.peer_kvfull = dsmem_addr(&bars->kvfull, crank ^ 1u);
+            e.peer_kvfree = dsmem_addr(&bars->kvfree, crank ^ 1u);
         }
         const int tb_row = a.per_jet_time ? meta->row_tb[r] : 0;
         const long long slot = a.row_slot[static_cast<size_t>(tile) * 128 + r];
@@ -750,7 +862,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                         const float4 w = ldf4(PA + tfp::EA_W0 + (chunk * 64 + i) * 4);
                         v[i] = gelu_tile(fmaf(w.z, x2, fmaf(w.y, x1, fmaf(w.x, x0, w.w))));
                     }
-                    stage_row_bf16(arena + oA + chunk * kTile, r, v);
+                    if (row_ok<PAIR>(r)) stage_row_bf16(arena + L::oA + chunk * L::kChunk, r, v);
                 }
                 go(e);
             }
@@ -816,7 +928,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 tmem_st_wait();
                 float mean, rstd;
                 if (pf) ln_stats<false>(e, sum, 0, mean, rstd); else ln_stats<true>(e, sum, 0, mean, rstd);
-                ln_to_abuf(e, mean, rstd, PB + tfp::EB_LNN_G + hf * 128, PB + tfp::EB_LNN_B + hf * 128);
+                ln_to_abuf<PAIR>(e, mean, rstd, PB + tfp::EB_LNN_G + hf * 128, PB + tfp::EB_LNN_B + hf * 128);
                 go(e);
             }
             param_release(e);
@@ -830,8 +942,8 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 for (int g = 0; g < 2; ++g) {
                     const float* G = e.P + g * tfp::SA_GROUP;
                     for (int u = 0; u < 2; ++u)
-                        attention_unit<32>(e, g == 0 && u == 0, !(g == 1 && u == 1), G + tfp::SA_BQKV + u * 64, G + tfp::SA_BQKV + 128 + u * 64, G + tfp::SA_BQKV + 256 + u * 64,
-                                           G + tfp::SA_QG, G + tfp::SA_QB, G + tfp::SA_KG, G + tfp::SA_KB, seg_b, seg_e);
+                        attention_unit<32, PAIR>(e, g == 0 && u == 0, !(g == 1 && u == 1), G + tfp::SA_BQKV + u * 64, G + tfp::SA_BQKV + 128 + u * 64, G + tfp::SA_BQKV + 256 + u * 64,
+                                           G + tfp::SA_QG, G + tfp::SA_QB, G + tfp::SA_KG, G + tfp::SA_KB, att_lo, att_span);
                 }
                 wait_done(e, 0);                              // last projection of group 1 has landed
                 {
@@ -839,7 +951,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                     const RowStat sum = resid_update(e, G + tfp::SA_BPROJ, nullptr, nullptr);
                     float mean, rstd;
                     ln_stats<false>(e, sum, 0, mean, rstd);
-                    ln_to_abuf(e, mean, rstd, G + tfp::SA_LN2G, G + tfp::SA_LN2B);
+                    ln_to_abuf<PAIR>(e, mean, rstd, G + tfp::SA_LN2G, G + tfp::SA_LN2B);
                     go(e);
                 }
                 param_release(e);
@@ -851,7 +963,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                         // quarter 1 must have read it (done[1]) - see emit_mlp
                         if (q == 0 || q == 2) wait_done(e, 0);
                         if (q == 3) wait_done(e, 1);
-                        fc_epilogue(e, q, G + tfp::SM_BFC + q * 128);
+                        fc_epilogue<PAIR>(e, q, G + tfp::SM_BFC + q * 128);
                         go(e);
                     }
                 }
@@ -862,7 +974,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                         const RowStat sum = resid_update(e, G + tfp::SM_BP2, tb1, nullptr);
                         float mean, rstd;
                         ln_stats<false>(e, sum, 0, mean, rstd);
-                        ln_to_abuf(e, mean, rstd, e.P + tfp::SM_LNN_G + hf * 128, e.P + tfp::SM_LNN_B + hf * 128);
+                        ln_to_abuf<PAIR>(e, mean, rstd, e.P + tfp::SM_LNN_G + hf * 128, e.P + tfp::SM_LNN_B + hf * 128);
                     } else {
                         // stream junction: x = ln2_x(x + x_skip) | y = ln2_y(y + y_skip); z = cat(x, y) + time_expand(temb)
                         const RowStat sum = resid_update(e, G + tfp::SM_BP2, tb1, skipc);
@@ -870,7 +982,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                         ln_stats<false>(e, sum, 0, mean, rstd);
                         const RowStat sum2 = ln_to_resid(e, mean, rstd, e.P + tfp::SM_LNN_G + hf * 128, e.P + tfp::SM_LNN_B + hf * 128, tb2);
                         ln_stats<true>(e, sum2, 1, mean, rstd);
-                        ln_to_abuf(e, mean, rstd, e.P + tfp::SM_LN2ND_G + hf * 128, e.P + tfp::SM_LN2ND_B + hf * 128);
+                        ln_to_abuf<PAIR>(e, mean, rstd, e.P + tfp::SM_LN2ND_G + hf * 128, e.P + tfp::SM_LN2ND_B + hf * 128);
                     }
                     go(e);
                 }
@@ -883,14 +995,14 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 param_acquire(e);                             // attention stage
                 const bool last = blk + 1 == a.n_main;
                 for (int u = 0; u < 4; ++u)
-                    attention_unit<64>(e, u == 0, u < 3, e.P + tfp::BA_BQKV + u * 64, e.P + tfp::BA_BQKV + 256 + u * 64, e.P + tfp::BA_BQKV + 512 + u * 64,
-                                       e.P + tfp::BA_QG, e.P + tfp::BA_QB, e.P + tfp::BA_KG, e.P + tfp::BA_KB, seg_b, seg_e);
+                    attention_unit<64, PAIR>(e, u == 0, u < 3, e.P + tfp::BA_BQKV + u * 64, e.P + tfp::BA_BQKV + 256 + u * 64, e.P + tfp::BA_BQKV + 512 + u * 64,
+                                       e.P + tfp::BA_QG, e.P + tfp::BA_QB, e.P + tfp::BA_KG, e.P + tfp::BA_KB, att_lo, att_span);
                 wait_done(e, 0);
                 {
                     const RowStat sum = resid_update(e, e.P + tfp::BA_BPROJ + hf * 128, nullptr, nullptr);
                     float mean, rstd;
                     ln_stats<true>(e, sum, 0, mean, rstd);
-                    ln_to_abuf(e, mean, rstd, e.P + tfp::BA_LN2G + hf * 128, e.P + tfp::BA_LN2B + hf * 128);
+                    ln_to_abuf<PAIR>(e, mean, rstd, e.P + tfp::BA_LN2G + hf * 128, e.P + tfp::BA_LN2B + hf * 128);
                     go(e);
                 }
                 param_release(e);
@@ -898,7 +1010,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 for (int q = 0; q < 4; ++q) {
                     if (q == 0 || q == 2) wait_done(e, 0);
                     if (q == 3) wait_done(e, 1);
-                    fc_epilogue(e, q, e.P + tfp::BM_BFC + q * 128);
+                    fc_epilogue<PAIR>(e, q, e.P + tfp::BM_BFC + q * 128);
                     go(e);
                 }
                 wait_done(e, 0);
@@ -908,7 +1020,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                     const RowStat sum = resid_update(e, e.P + tfp::BM_BP2 + hf * 128, tb2, last ? skipc : nullptr);
                     float mean, rstd;
                     if (last && pf) ln_stats<false>(e, sum, 0, mean, rstd); else ln_stats<true>(e, sum, 0, mean, rstd);
-                    ln_to_abuf(e, mean, rstd, e.P + tfp::BM_LNN_G + hf * 128, e.P + tfp::BM_LNN_B + hf * 128);
+                    ln_to_abuf<PAIR>(e, mean, rstd, e.P + tfp::BM_LNN_G + hf * 128, e.P + tfp::BM_LNN_B + hf * 128);
                     go(e);
                 }
                 param_release(e);
@@ -1018,7 +1130,7 @@ void tf_tiles_dump_timeouts() {     // after a failed launch: which barrier wait
         fprintf(stderr, "  cta %llu barrier smem+0x%llx parity %llu warp %llu tag %llu\n", (v >> 12) & 0xffff, (v >> 32) & 0xffff, (v >> 28) & 1, (v & 0xfff) >> 5, v >> 48);
     }
 }
-int launch_tf_tiles_trace(const TfLaunch& a, int n_tiles, int cluster, cudaStream_t stream) {
+int launch_tf_tiles_trace(const TfLaunch& a, int n_tiles, int cluster, bool pair, cudaStream_t stream) {
     if (!g_dbg_host) {
         unsigned long long* dptr = nullptr;
         MMF_CUDA_OK(cudaHostAlloc(&g_dbg_host, 64 * 8, cudaHostAllocMapped));
@@ -1027,24 +1139,26 @@ int launch_tf_tiles_trace(const TfLaunch& a, int n_tiles, int cluster, cudaStrea
         MMF_CUDA_OK(cudaMemcpyToSymbol(mmf_dbg_sink, &dptr, sizeof(dptr)));
     }
 #else
-int tf_tile_smem_bytes() { return kSmemBytes; }
+int tf_tile_smem_bytes() { return smem_bytes<false>(); }
 
-int launch_tf_tiles(const TfLaunch& a, int n_tiles, int cluster, cudaStream_t stream) {
+int launch_tf_tiles(const TfLaunch& a, int n_tiles, int cluster, bool pair, cudaStream_t stream) {
 #endif
     if (n_tiles == 0) return 0;
     MMF_REQUIRE(a.vocab == 9, "the tile kernel is instantiated for vocab_size 9");
     MMF_REQUIRE((cluster == 1 || cluster == 2 || cluster == 4) && n_tiles % cluster == 0, "tile launch: bad cluster size");
+    MMF_REQUIRE(!pair || cluster == 2, "pair tiles run as 2-CTA clusters");
     static bool configured[64] = {false};                 // the attribute is per device
     int dev = 0;
     MMF_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        MMF_CUDA_OK(cudaFuncSetAttribute(tf_tile_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        MMF_CUDA_OK(cudaFuncSetAttribute(tf_tile_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<false>()));
+        MMF_CUDA_OK(cudaFuncSetAttribute(tf_tile_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<true>()));
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_tiles);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.dynamicSmemBytes = pair ? smem_bytes<true>() : smem_bytes<false>();
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1053,7 +1167,8 @@ int launch_tf_tiles(const TfLaunch& a, int n_tiles, int cluster, cudaStream_t st
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MMF_CUDA_OK(cudaLaunchKernelEx(&cfg, tf_tile_kernel<9>, a, *a.optab, *a.prodtab));
+    if (pair) MMF_CUDA_OK(cudaLaunchKernelEx(&cfg, tf_tile_kernel<9, true>, a, *a.optab, *a.prodtab));
+    else MMF_CUDA_OK(cudaLaunchKernelEx(&cfg, tf_tile_kernel<9, false>, a, *a.optab, *a.prodtab));
     return 0;
 }
 

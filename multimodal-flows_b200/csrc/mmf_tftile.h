@@ -78,6 +78,8 @@ struct TfOp {
 };
 static_assert(sizeof(TfOp) == 16, "TfOp is read with one 128-bit load");
 
+constexpr uint8_t kTfNktPairWait = 0x40;      // TfOp.nkt bit 6 (pair tiles): wait for the partner CTA's K / V rows first
+
 constexpr int kTfMaxOps = 1024;
 struct TfOpTable {          // MMA ops of one timestep; passed to the kernel BY VALUE (constant bank -> uniform registers)
     TfOp ops[kTfMaxOps];
@@ -94,8 +96,8 @@ struct TfProdTable {
 };
 
 struct TfTileMeta {
-    int nrows;              // real rows (<= 128)
-    int pad[3];
+    int nrows;              // real rows (<= 128; <= 80 in a pair tile)
+    int pad[3];             // pad[0]: pair tiles - real rows of the partner CTA (the other half of the jet)
     unsigned char seg_beg[128];   // per row: first row of its jet
     unsigned char seg_end[128];   // per row: one past the last row of its jet (0,0 for padding rows)
     int row_tb[128];        // per row: row of the time table when time is per jet (forward API)
@@ -140,13 +142,46 @@ struct TfLaunch {
     unsigned long long* trace;
 };
 
+// Operand arena of a CTA (byte offsets; every region is 1024-byte aligned).  Two layouts:
+//   plain tile  128 rows of whole jets, each <= 128 particles; keys = the tile's own 128 rows
+//   PAIR tile   one jet of 129...160 particles split over the two CTAs of a cluster, <= 80 rows each.  The 160 keys of a CTA
+//               are its own 80 rows followed by the partner's 80, whose K / V rows the partner's epilogue writes straight
+//               into this CTA's shared memory (DSMEM).  Rows 80...127 of every A operand are don't-care, so A chunks
+//               ([rows][64] bf16, SWIZZLE_128B) are laid 10 KB apart instead of 16 KB: the MMA reads M = 128 rows and
+//               what it finds behind row 79 only reaches accumulator rows nobody looks at.  That makes room for K and V
+//               of 160 keys and for a probability operand P that does not alias Q | K (the two heads of a 32-wide unit
+//               take turns on the score columns, so head 1's Q and K must survive head 0's softmax).
+template <bool PAIR>
+struct TfLay {
+    static constexpr uint32_t kChunk = PAIR ? 10240u : 16384u;      // stride of an A-operand chunk
+    static constexpr uint32_t kRows = PAIR ? 80u : 128u;            // rows (and own keys) that exist in shared memory
+    static constexpr uint32_t kKeys = PAIR ? 160u : 128u;           // keys a query row sees
+    static constexpr uint32_t kKV = kKeys * 128u;                   // K / V: [keys][64] bf16
+    static constexpr uint32_t oA = 0;                               // 4 chunks: LayerNorm output / head input
+    static constexpr uint32_t oQ = 4 * kChunk;                      // Q of the current unit
+    static constexpr uint32_t oK = oQ + kChunk;                     // K [keys][64]
+    static constexpr uint32_t oVT = oK + kKV;                       // V [keys][64 d] (MN-major B operand of P V)
+    static constexpr uint32_t oP = PAIR ? oVT + kKV : oQ;           // probabilities [rows][keys]; plain: aliases Q | K
+    static constexpr uint32_t oO = PAIR ? oP + 3 * kChunk : oVT + kKV;   // attention output of the current unit
+    static constexpr uint32_t oH0 = oQ, oH1 = oQ + 2 * kChunk;      // MLP hidden quarters [rows][128] (two chunks each)
+    static constexpr uint32_t oRing = oO + kChunk;                  // weight ring
+    static constexpr uint32_t kArena = oRing + 65536u;
+    // scratch columns of TMEM (relative to the allocation base; the residual stream owns [0,256))
+    static constexpr uint32_t cQkv64 = PAIR ? 320u : 256u;          // 64-wide units: q | k | v
+    static constexpr uint32_t cS = PAIR ? 320u : 256u;              // scores (pair: one head at a time, 160 columns)
+    static constexpr uint32_t cO64 = PAIR ? 256u : 448u;            // O of a 64-wide head
+};
+static_assert(TfLay<false>::oO == 114688u && TfLay<false>::kArena == 196608u, "plain arena layout");
+static_assert(TfLay<true>::kArena == 198656u, "pair arena layout");
+
 // host-side placement of the weight tiles in the 64 KB ring (tftile_model.cu); exported for tests as mmf_dbg_ring_plan
 bool plan_weight_ring(const std::vector<int>& kb, std::vector<int>* dst_kb, std::vector<int>* dep);
 
 int tf_tile_smem_bytes();
 // n_tiles must be a multiple of `cluster` (1, 2 or 4): the CTAs of a cluster share each weight tile through TMA multicast
-int launch_tf_tiles(const TfLaunch& a, int n_tiles, int cluster, cudaStream_t stream);
-int launch_tf_tiles_trace(const TfLaunch& a, int n_tiles, int cluster, cudaStream_t stream);   // the same kernel with clock stamps
+// pair = true: pair tiles (cluster must be 2; a.optab is the pair op table)
+int launch_tf_tiles(const TfLaunch& a, int n_tiles, int cluster, bool pair, cudaStream_t stream);
+int launch_tf_tiles_trace(const TfLaunch& a, int n_tiles, int cluster, bool pair, cudaStream_t stream);   // the same kernel with clock stamps
 void tf_tiles_dump_timeouts();   // trace build: prints the barrier waits that timed out in a failed launch
 
 // ---- host object (tftile_model.cu)

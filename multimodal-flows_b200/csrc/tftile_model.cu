@@ -14,9 +14,9 @@ namespace mmf {
 struct TfTileModel {
     MmfModelDesc desc{};
     DeviceArena arena;
-    std::unique_ptr<TfOpTable> optab;                   // host copies, passed by value at every launch
+    std::unique_ptr<TfOpTable> optab, optab_pair;       // host copies, passed by value at every launch (plain / pair tiles)
     std::unique_ptr<TfProdTable> prodtab;
-    int n_ops = 0, n_prod = 0, n_blobs = 0;
+    int n_ops = 0, n_ops_pair = 0, n_prod = 0, n_blobs = 0;
     const uint8_t* d_wstream = nullptr;
     const float* d_params = nullptr;
     std::vector<float> time_expand_w, time_expand_b;     // ParticleFormer, host fp32
@@ -28,13 +28,18 @@ struct TfTileModel {
     int *d_ks0 = nullptr, *d_row_slot = nullptr;
     int64_t launches = 0;
     TfLaunch pending{};                                  // prepared by tftile_prepare, consumed by tftile_launch
-    int pending_tiles = 0;
+    int pending_tiles = 0, pending_pair_tiles = 0;      // plain tiles [0, pending_tiles), pair tiles behind them
+    cudaStream_t side = nullptr;                         // pair tiles run beside the plain ones (fork / join with events)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int cluster = 2;                                     // CTAs sharing one weight stream (MMF_TILE_CLUSTER = 1 | 2 | 4)
     PinnedStage stage;                                   // per-call tables on their way to the device
     ~TfTileModel() {
         stage.release();
         arena.release();
         if (ws) cudaFree(ws);
+        if (side) cudaStreamDestroy(side);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
     }
 };
 
@@ -93,8 +98,19 @@ bool plan_weight_ring(const std::vector<int>& kb, std::vector<int>* dst_kb, std:
 
 namespace {
 
-// operand arena offsets: keep in sync with kernels_tftile.cu
-constexpr uint32_t kT = 16384, oA = 0, oQ = 65536, oK = oQ + kT, oVT = oK + kT, oO = oVT + kT, oH0 = oQ, oH1 = oVT;
+// operand arena and scratch columns of the two tile kinds (TfLay<PAIR> in mmf_tftile.h), as run-time values for the emitter
+struct LayH {
+    bool pair;
+    uint32_t chunk, oA, oQ, oK, oVT, oP, oO, oH0, oH1;
+    uint16_t cQkv64, cS, cO64;
+    int keys;
+};
+template <bool PAIR>
+LayH make_lay() {
+    using L = TfLay<PAIR>;
+    return LayH{PAIR, L::kChunk, L::oA, L::oQ, L::oK, L::oVT, L::oP, L::oO, L::oH0, L::oH1,
+                static_cast<uint16_t>(L::cQkv64), static_cast<uint16_t>(L::cS), static_cast<uint16_t>(L::cO64), static_cast<int>(L::kKeys)};
+}
 
 uint32_t desc_lo(uint32_t arena_off) { return (arena_off >> 4) | (1u << 16); }
 uint32_t idesc_bf16(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24); }
@@ -124,9 +140,11 @@ struct Builder {
     }
     // both operands in the arena; B advances by 8 KB per k-tile
     // b_mn: B is MN-major (rows = K, N contiguous inside the 128-byte row) - bit 16 of the instruction descriptor
-    void smem_op(uint32_t a_off, uint32_t b_off, int n, uint16_t dcol, int nkt, bool half_k, int acc, int wait, int signal, bool b_mn = false) {
+    void smem_op(uint32_t a_off, uint32_t b_off, int n, uint16_t dcol, int nkt, bool half_k, int acc, int wait, int signal, bool b_mn = false,
+                 bool pair_wait = false) {
         TfOp o{};
-        o.a_lo = desc_lo(a_off); o.b_lo = desc_lo(b_off); o.idesc = idesc_bf16(n) | (b_mn ? 1u << 16 : 0u); o.dcol = dcol; o.nkt = static_cast<uint8_t>(nkt | ((signal >> 2) << 7));
+        o.a_lo = desc_lo(a_off); o.b_lo = desc_lo(b_off); o.idesc = idesc_bf16(n) | (b_mn ? 1u << 16 : 0u); o.dcol = dcol;
+        o.nkt = static_cast<uint8_t>(nkt | ((signal >> 2) << 7) | (pair_wait ? kTfNktPairWait : 0));
         o.flags = static_cast<uint8_t>((acc ? kTfOpAcc : 0u) | (wait ? kTfOpWait : 0u) | (half_k ? kTfOpHalfK : 0u) | (b_mn ? kTfOpBMn : 0u) |
                                        kTfOpAttn | (static_cast<uint32_t>(signal & 3) << 4));
         ops.push_back(o);
@@ -176,10 +194,10 @@ BlockW load_block(WeightMap& wm, const std::string& p, int C, int I) {
 // into two 128-column quarters H0 | H1, and the down-projection of a quarter accumulates onto the residual (N = C).
 //   MMA order   fc(h0) | out(q0) | fc(h1) out(q1) | out(q2) | out(q3)      ("|" = waits for the next go of the epilogue)
 //   signals     fc(h) -> done[0]; out(q1) -> done[1] (H1 may be rewritten); the last out(q3) -> done[0] when final_signal
-void emit_mlp(Builder& b, const BlockW& w, int C, int a_chunk0, uint16_t dcol_out, bool first_wait, bool final_signal) {
+void emit_mlp(Builder& b, const LayH& L, const BlockW& w, int C, int a_chunk0, uint16_t dcol_out, bool first_wait, bool final_signal) {
     const int kbC = C / 64;
-    auto fc = [&](int h, int wait) { b.ring_op(oA + a_chunk0 * kT, rows_of(w.fc, h * 256, 256), 0, kbC, 256, 0, wait, 1); };
-    auto out = [&](int q, int wait, int signal) { b.ring_op((q & 1) ? oH1 : oH0, rows_of(w.p2, 0, C), q * 128, 2, dcol_out, 1, wait, signal); };
+    auto fc = [&](int h, int wait) { b.ring_op(L.oA + a_chunk0 * L.chunk, rows_of(w.fc, h * 256, 256), 0, kbC, 256, 0, wait, 1); };
+    auto out = [&](int q, int wait, int signal) { b.ring_op((q & 1) ? L.oH1 : L.oH0, rows_of(w.p2, 0, C), q * 128, 2, dcol_out, 1, wait, signal); };
     fc(0, first_wait);
     out(0, 1, 0);
     fc(1, 1);
@@ -190,16 +208,15 @@ void emit_mlp(Builder& b, const BlockW& w, int C, int a_chunk0, uint16_t dcol_ou
 
 }  // namespace
 
-int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
-    *out = nullptr;
+// The per-timestep program of one tile kind: MMA ops, weight stream (consumption order) and parameter blobs.  Both kinds
+// consume the SAME weight tiles in the SAME order (the pair program differs only in operand addresses, scratch columns and
+// the attention products), so the stream, ring plan and blobs of the plain program serve both.
+static int emit_program(const MmfModelDesc& d, WeightMap& wm, const LayH& L, Builder& b, int* n_blobs) {
     const bool pf = d.arch == MMF_ARCH_PARTICLEFORMER;
     const int E = d.n_embd, h = E / 2, I = d.n_inner, V = d.vocab_size;
-    if (!(E == 256 && I == 512 && d.n_head == 4 && V == 9 && d.qk_layernorm)) return 0;     // outside the tile kernel's envelope
     const std::string t = "transformer.";
-    std::unique_ptr<TfTileModel> m(new TfTileModel());
-    m->desc = d;
-    Builder b;
     const int n_stream = pf ? d.n_layer : 0, n_main = pf ? d.n_layer_fused : d.n_layer;
+    const uint32_t oA = L.oA, oQ = L.oQ, oK = L.oK, oVT = L.oVT, oO = L.oO, oP = L.oP, kT = L.chunk;
     int blob_idx = 0;
 
     // ---------------- embedding stage
@@ -284,15 +301,26 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
         qkv(0, 0, 1);
         for (int g = 0; g < 2; ++g)
             for (int u = 0; u < 2; ++u) {
-                b.smem_op(oQ, oK, 128, 256, 1, true, 0, 1, 0);               // S of head 0 of the pair
-                b.smem_op(oQ + 64, oK + 64, 128, 384, 1, true, 0, 0, 1);     // S of head 1
-                b.smem_op(oQ, oVT, 32, 256, 2, false, 0, 1, 4, true);        // O_h0 = P_h0 V_h0 (keys 0..63, 64..127); V is [key][d]; -> done[3]
-                b.smem_op(oQ, oVT + 64, 32, 288, 2, false, 0, 1, 1, true);   // O_h1: d columns 32..63 of the V rows
+                if (!L.pair) {
+                    b.smem_op(oQ, oK, 128, 256, 1, true, 0, 1, 0);               // S of head 0 of the pair
+                    b.smem_op(oQ + 64, oK + 64, 128, 384, 1, true, 0, 0, 1);     // S of head 1
+                    b.smem_op(oQ, oVT, 32, 256, 2, false, 0, 1, 4, true);        // O_h0 = P_h0 V_h0 (keys 0..63, 64..127); V is [key][d]; -> done[3]
+                    b.smem_op(oQ, oVT + 64, 32, 288, 2, false, 0, 1, 1, true);   // O_h1: d columns 32..63 of the V rows
+                } else {
+                    // pair tile: 160 keys, one head at a time on the score columns [320,480); O_h0 [256,288), O_h1 [288,320);
+                    // P [rows][160 keys] = two 64-key k-tiles + one 32-key tail, V rows 128 bytes apart
+                    b.smem_op(oQ, oK, 160, L.cS, 1, true, 0, 1, 1, false, true);          // S of head 0 (after the partner's K / V rows)
+                    b.smem_op(oQ + 64, oK + 64, 160, L.cS, 1, true, 0, 1, 1);             // S of head 1 (head 0's scores are in registers)
+                    b.smem_op(oP, oVT, 32, 256, 2, false, 0, 1, 0, true);                 // O_h0: keys 0..127
+                    b.smem_op(oP + 2 * kT, oVT + 128 * 128, 32, 256, 1, true, 1, 0, 4, true);   //       keys 128..159 -> done[3]
+                    b.smem_op(oP, oVT + 64, 32, 288, 2, false, 0, 1, 0, true);            // O_h1
+                    b.smem_op(oP + 2 * kT, oVT + 128 * 128 + 64, 32, 288, 1, true, 1, 0, 1, true);
+                }
                 if (!(g == 1 && u == 1)) qkv(u == 1 ? 1 : g, u == 1 ? 0 : 1, 1);    // released as soon as both score tiles are in registers
                 b.ring_op(oO, rows_of(w[g].proj, 0, 128), u * 64, 1, static_cast<uint16_t>(g * 128), 1, 1, (g == 1 && u == 1) ? 1 : 3);   // 3: done[2] = oO may be rewritten
             }
         ++blob_idx;
-        for (int g = 0; g < 2; ++g) emit_mlp(b, w[g], 128, 2 * g, static_cast<uint16_t>(g * 128), g == 0, g == 1);
+        for (int g = 0; g < 2; ++g) emit_mlp(b, L, w[g], 128, 2 * g, static_cast<uint16_t>(g * 128), g == 0, g == 1);
     }
 
     // ---------------- main blocks: C = 256, head size 64, units = heads
@@ -328,17 +356,23 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
             std::vector<const float*> r = rows_of(w.attn, u * 64, 64), kk = rows_of(w.attn, 256 + u * 64, 64), vv = rows_of(w.attn, 512 + u * 64, 64);
             r.insert(r.end(), kk.begin(), kk.end());
             r.insert(r.end(), vv.begin(), vv.end());
-            b.ring_op(oA, r, 0, 4, 256, 0, wait, 2);
+            b.ring_op(oA, r, 0, 4, L.cQkv64, 0, wait, 2);      // (pair tiles: columns [320,512), O of the unit lives in [256,320))
         };
         qkv(0, 1);
         for (int u = 0; u < 4; ++u) {
-            b.smem_op(oQ, oK, 128, 256, 1, false, 0, 1, 1);                  // S = Q K^T
-            b.smem_op(oQ, oVT, 64, 448, 2, false, 0, 1, 1, true);            // O = P V; V is [key][d] (MN-major B)
+            if (!L.pair) {
+                b.smem_op(oQ, oK, 128, 256, 1, false, 0, 1, 1);                  // S = Q K^T
+                b.smem_op(oQ, oVT, 64, 448, 2, false, 0, 1, 1, true);            // O = P V; V is [key][d] (MN-major B)
+            } else {
+                b.smem_op(oQ, oK, 160, L.cS, 1, false, 0, 1, 1, false, true);            // S over 160 keys (after the partner's rows)
+                b.smem_op(oP, oVT, 64, L.cO64, 2, false, 0, 1, 0, true);                 // O: keys 0..127
+                b.smem_op(oP + 2 * kT, oVT + 128 * 128, 64, L.cO64, 1, true, 1, 0, 1, true);   //    keys 128..159
+            }
             if (u < 3) qkv(u + 1, 1);                                      // released as soon as the score tile is in registers
             b.ring_op(oO, rows_of(w.proj, 0, 256), u * 64, 1, 0, 1, 1, u == 3 ? 1 : 3);      // N = 256; 3: done[2] = oO may be rewritten
         }
         ++blob_idx;
-        emit_mlp(b, w, 256, 0, 0, true, true);
+        emit_mlp(b, L, w, 256, 0, 0, true, true);
     }
 
     // ---------------- heads: Linear(128,512) + GELU on tensor cores, Linear(512, 3 | V) on CUDA cores
@@ -364,23 +398,46 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
         blob_idx += 5;
     }
     if (!wm.missing.empty()) { set_last_error(wm.missing); return 2; }
+    b.params.resize(static_cast<size_t>(blob_idx) * kTfParamFloats, 0.f);
+    *n_blobs = blob_idx;
+    return 0;
+}
+
+int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
+    *out = nullptr;
+    const bool pf = d.arch == MMF_ARCH_PARTICLEFORMER;
+    const int E = d.n_embd, h = E / 2, I = d.n_inner, V = d.vocab_size;
+    if (!(E == 256 && I == 512 && d.n_head == 4 && V == 9 && d.qk_layernorm)) return 0;     // outside the tile kernel's envelope
+    const std::string t = "transformer.";
+    std::unique_ptr<TfTileModel> m(new TfTileModel());
+    m->desc = d;
+    Builder b, bp;
+    int blob_idx = 0, blob_idx_pair = 0;
+    MMF_TRY_RC(emit_program(d, wm, make_lay<false>(), b, &blob_idx));
+    MMF_TRY_RC(emit_program(d, wm, make_lay<true>(), bp, &blob_idx_pair));
+    MMF_REQUIRE(bp.tiles.size() == b.tiles.size() && bp.stream == b.stream && blob_idx_pair == blob_idx,
+                "tile kernel: the pair program must consume the weight stream of the plain program");
     if (pf) {
         m->time_expand_w = wm.get(t + "time_expand.weight", E, h);
         m->time_expand_b = wm.get(t + "time_expand.bias", E);
     }
-    b.params.resize(static_cast<size_t>(blob_idx) * kTfParamFloats, 0.f);
 
     DeviceArena& ar = m->arena;
-    MMF_REQUIRE(b.ops.size() <= static_cast<size_t>(kTfMaxOps) && b.tiles.size() <= static_cast<size_t>(kTfMaxOps),
+    MMF_REQUIRE(b.ops.size() <= static_cast<size_t>(kTfMaxOps) && bp.ops.size() <= static_cast<size_t>(kTfMaxOps) &&
+                    b.tiles.size() <= static_cast<size_t>(kTfMaxOps),
                 "tile kernel: op table too long for the kernel parameter space");
     m->optab.reset(new TfOpTable());
+    m->optab_pair.reset(new TfOpTable());
     m->prodtab.reset(new TfProdTable());
     memset(m->optab.get(), 0, sizeof(TfOpTable));
+    memset(m->optab_pair.get(), 0, sizeof(TfOpTable));
     memset(m->prodtab.get(), 0, sizeof(TfProdTable));
     MMF_REQUIRE(b.plan_ring(), "tile kernel: weight ring plan failed");
     std::copy(b.ops.begin(), b.ops.end(), m->optab->ops);
+    std::copy(bp.ops.begin(), bp.ops.end(), m->optab_pair->ops);
     std::copy(b.tiles.begin(), b.tiles.end(), m->prodtab->e);
     m->n_ops = static_cast<int>(b.ops.size());
+    m->n_ops_pair = static_cast<int>(bp.ops.size());
     m->n_prod = static_cast<int>(b.tiles.size());
     m->n_blobs = blob_idx;
     const size_t o_stream = ar.reserve(b.stream.size() * 2);
@@ -403,11 +460,14 @@ int64_t tftile_launches(const TfTileModel* m) { return m ? m->launches : 0; }
 namespace {
 
 struct TilePlan {
-    std::vector<TfTileMeta> meta;
+    std::vector<TfTileMeta> meta;        // plain tiles first (padded to a whole number of clusters), then pair tiles
     std::vector<int> row_slot;
+    int n_plain = 0, n_pair = 0;
 };
 
-void plan_tiles(const int64_t* mask, int B, int D, bool per_jet_time, TilePlan* p, std::vector<unsigned char>* handled) {
+constexpr int kPairRows = static_cast<int>(TfLay<true>::kRows);       // rows a CTA of a pair holds at most
+
+void plan_tiles(const int64_t* mask, int B, int D, bool per_jet_time, int cluster, TilePlan* p, std::vector<unsigned char>* handled) {
     std::vector<int> n(B, 0);
     for (int b = 0; b < B; ++b)
         for (int d = 0; d < D; ++d) n[b] += mask[static_cast<size_t>(b) * D + d] != 0;
@@ -416,13 +476,15 @@ void plan_tiles(const int64_t* mask, int B, int D, bool per_jet_time, TilePlan* 
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n[a] > n[b]; });
     struct Bin { int rows = 0; std::vector<int> jets; };
     std::vector<Bin> bins;
+    std::vector<int> big;                                             // jets of 129 ... 160 particles: one CTA pair each
     // best-fit decreasing with an index of open bins by free space (128 buckets): O(B * 128)
     std::vector<std::vector<int>> by_free(129);
     handled->assign(B, 0);
     for (int b : order) {
         if (n[b] == 0) { (*handled)[b] = 1; continue; }            // nothing to generate
-        if (n[b] > 128) continue;                                    // handled by the layered path
+        if (n[b] > 2 * kPairRows) continue;                          // (not reachable with max_num_particles <= 152)
         (*handled)[b] = 1;
+        if (n[b] > 128) { big.push_back(b); continue; }
         int pick = -1;
         for (int f = n[b]; f <= 128 && pick < 0; ++f)
             if (!by_free[f].empty()) { pick = by_free[f].back(); by_free[f].pop_back(); }
@@ -452,6 +514,36 @@ void plan_tiles(const int64_t* mask, int B, int D, bool per_jet_time, TilePlan* 
         p->meta.push_back(m);
         p->row_slot.insert(p->row_slot.end(), slots.begin(), slots.end());
     }
+    if (!p->meta.empty()) {                              // pad with empty tiles to a whole number of clusters
+        TfTileMeta empty{};
+        while (p->meta.size() % cluster != 0) {
+            p->meta.push_back(empty);
+            p->row_slot.insert(p->row_slot.end(), 128, -1);
+        }
+    }
+    p->n_plain = static_cast<int>(p->meta.size());
+    // pair tiles: CTA 0 of the cluster takes the first ceil(n / 2) particles of the jet, CTA 1 the rest
+    for (int b : big) {
+        std::vector<int> s;
+        for (int d = 0; d < D; ++d)
+            if (mask[static_cast<size_t>(b) * D + d] != 0) s.push_back(b * D + d);
+        const int h0 = (n[b] + 1) / 2, h1 = n[b] - h0;
+        for (int half = 0; half < 2; ++half) {
+            TfTileMeta m{};
+            std::vector<int> slots(half == 0 ? s.begin() : s.begin() + h0, half == 0 ? s.begin() + h0 : s.end());
+            m.nrows = half == 0 ? h0 : h1;
+            m.pad[0] = half == 0 ? h1 : h0;
+            for (int r = 0; r < m.nrows; ++r) {
+                m.seg_beg[r] = 0;
+                m.seg_end[r] = static_cast<unsigned char>(m.nrows);
+                m.row_tb[r] = per_jet_time ? b : 0;
+            }
+            slots.resize(128, -1);
+            p->meta.push_back(m);
+            p->row_slot.insert(p->row_slot.end(), slots.begin(), slots.end());
+        }
+    }
+    p->n_pair = 2 * static_cast<int>(big.size());
 }
 
 int ensure_ws(TfTileModel* m, int tiles, int tb) {
@@ -484,16 +576,10 @@ int tftile_prepare(TfTileModel* m, const TfRunArgs& r, std::vector<unsigned char
     const MmfModelDesc& d = m->desc;
     const bool pf = d.arch == MMF_ARCH_PARTICLEFORMER;
     TilePlan plan;
-    plan_tiles(r.mask_host, r.B, r.D, r.per_jet_time, &plan, handled);
-    if (!plan.meta.empty()) {                            // pad with empty tiles to a whole number of clusters
-        TfTileMeta empty{};
-        while (plan.meta.size() % m->cluster != 0) {
-            plan.meta.push_back(empty);
-            plan.row_slot.insert(plan.row_slot.end(), 128, -1);
-        }
-    }
+    plan_tiles(r.mask_host, r.B, r.D, r.per_jet_time, m->cluster, &plan, handled);
     const int tiles = static_cast<int>(plan.meta.size());
-    m->pending_tiles = tiles;
+    m->pending_tiles = plan.n_plain;
+    m->pending_pair_tiles = plan.n_pair;
     if (tiles == 0) return 0;
     MMF_TRY_RC(ensure_ws(m, tiles, r.n_times));
     // time tables: sin/cos features (reference utils/models.py:62-75) and, for ParticleFormer, time_expand(temb)
@@ -542,8 +628,8 @@ int tftile_prepare(TfTileModel* m, const TfRunArgs& r, std::vector<unsigned char
 }
 
 int tftile_launch(TfTileModel* m, cudaStream_t s) {
-    const int tiles = m->pending_tiles;
-    if (tiles == 0) return 0;
+    const int tiles = m->pending_tiles, pair_tiles = m->pending_pair_tiles;
+    if (tiles + pair_tiles == 0) return 0;
     TfLaunch a = m->pending;
     const char* trace_path = getenv("MMF_TRACE");
     unsigned long long* d_trace = nullptr;
@@ -552,8 +638,33 @@ int tftile_launch(TfTileModel* m, cudaStream_t s) {
         MMF_CUDA_OK(cudaMemsetAsync(d_trace, 0, 2048 * 8, s));
         a.trace = d_trace;
     }
-    MMF_TRY_RC(d_trace ? launch_tf_tiles_trace(a, tiles, m->cluster, s) : launch_tf_tiles(a, tiles, m->cluster, s));
-    m->launches += 1;
+    // Plain tiles and pair tiles are two launches of the same program (different operand layout).  With both kinds in a
+    // batch the pair tiles go to a side stream, so a few large jets fill SMs the plain tiles leave free instead of
+    // waiting behind them (fork / join with events; `s` never runs ahead of either launch).
+    const bool fork = tiles > 0 && pair_tiles > 0 && !d_trace && getenv("MMF_NO_OVERLAP") == nullptr;
+    cudaStream_t sp = s;
+    if (fork) {
+        if (!m->side) {
+            MMF_CUDA_OK(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+            MMF_CUDA_OK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+            MMF_CUDA_OK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+        }
+        MMF_CUDA_OK(cudaEventRecord(m->ev_fork, s));
+        MMF_CUDA_OK(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+        sp = m->side;
+    }
+    if (pair_tiles > 0) {
+        TfLaunch ap = a;
+        ap.optab = m->optab_pair.get(); ap.n_ops = m->n_ops_pair; ap.tile0 = tiles;
+        MMF_TRY_RC(d_trace && tiles == 0 ? launch_tf_tiles_trace(ap, pair_tiles, 2, true, sp) : launch_tf_tiles(ap, pair_tiles, 2, true, sp));
+        m->launches += 1;
+        if (fork) MMF_CUDA_OK(cudaEventRecord(m->ev_join, sp));
+    }
+    if (tiles > 0) {
+        MMF_TRY_RC(d_trace ? launch_tf_tiles_trace(a, tiles, m->cluster, false, s) : launch_tf_tiles(a, tiles, m->cluster, false, s));
+        m->launches += 1;
+    }
+    if (fork) MMF_CUDA_OK(cudaStreamWaitEvent(s, m->ev_join, 0));
     if (d_trace) {
         std::vector<unsigned long long> hbuf(2048);
         if (cudaMemcpyAsync(hbuf.data(), d_trace, 2048 * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {

@@ -180,3 +180,62 @@ def test_dropin_predict_step_host_roundtrip():
     real = src.mask.bool().squeeze(-1)
     assert (out.continuous[~real] == 0).all() and (out.discrete.squeeze(-1)[~real] == 0).all()
     assert out.discrete.min() >= 0 and out.discrete.max() < 9
+
+
+@pytest.mark.parametrize("name", ["FusedParticleFormer", "ParticleFormer"])
+def test_jets_above_128_particles_run_on_the_tile_path(name):
+    """Jets of 129...150 particles are split over a 2-CTA cluster (pair tiles: K / V rows exchanged through DSMEM); they no
+    longer fall back to the layered kernels.  Forward (per-jet times) and a 4-step sampler against the fp32 oracle, per jet;
+    mixed with small jets (both launches in flight) and alone (only the pair launch)."""
+    from mmf_b200 import _abi, synthetic
+    from oracle import mmf_oracle as orc
+    cfg, sd, nm = _model(name, num_timesteps=4)
+    g = torch.Generator().manual_seed(91)
+    for ns in ([129, 150, 140, 133, 149, 130, 17, 64, 128, 1, 150], [150, 129], [145]):
+        n = torch.tensor(ns)
+        B = len(n)
+        mask = synthetic.prefix_masks(n, 150)
+        x0 = torch.randn(B, 150, 3, generator=g) * mask
+        k0 = torch.randint(1, 9, (B, 150, 1), generator=g) * mask
+        t = torch.rand(B, generator=g)
+        real = mask.bool().squeeze(-1)
+        l0 = nm.launches
+        va, la = nm.forward(x0.to(DEV), k0.to(DEV), mask.to(DEV), t.to(DEV))
+        torch.cuda.synchronize()
+        assert nm.launches - l0 <= 3, "pack + at most two tile launches: no layered kernels"
+        vr, lr = orc.encoder_forward(sd, cfg, t, x0, k0, mask)
+        for b in range(B):
+            rb = real[b:b + 1]
+            for got, ref in ((va.cpu()[b:b + 1], vr[b:b + 1]), (la.cpu()[b:b + 1], lr[b:b + 1])):
+                d = (got[rb] - ref[rb]).float()
+                assert float(d.norm() / ref[rb].norm()) < 2e-2, (ns, b, int(n[b]))
+                assert float(d.abs().max()) < 3e-2 * float(ref[real].abs().max()), (ns, b, int(n[b]))
+        assert torch.isfinite(va).all() and (va.cpu()[~real] == 0).all() and (la.cpu()[~real] == 0).all()
+        u = synthetic.uniform_draws(cfg.num_timesteps, B, seed=92)
+        xo, ko, ro = orc.simulate_dynamics(sd, cfg, x0, k0, mask, u=u)
+        ts, dt = orc.time_grid(cfg)
+        l0 = nm.launches
+        xg, kg, rg = nm.generate(x0.to(DEV), k0.to(DEV), mask.to(DEV), ts, float(dt), _abi.step_options(cfg), u=u.to(DEV), want_rates=True)
+        torch.cuda.synchronize()
+        assert nm.launches - l0 <= 3
+        assert _rel(xg.cpu(), xo, real) < 2e-2
+        assert (kg.cpu()[real] == ko.squeeze(-1)[real]).float().mean() > 0.96
+        assert _rel(rg.cpu(), ro, real) < 5e-2
+        assert (xg.cpu()[~real] == 0).all() and (kg.cpu()[~real] == 0).all()
+
+
+def test_dense_batch_of_150_particle_jets_matches_oracle():
+    """The dense worst case (every jet 150 particles, `bench.py --dense`): 24 jets = 24 CTA pairs, 3 timesteps."""
+    from mmf_b200 import _abi, synthetic
+    from oracle import mmf_oracle as orc
+    cfg, sd, nm = _model("ParticleFormer", num_timesteps=3)
+    src = synthetic.source_state(24, dense=True, seed=93)
+    u = synthetic.uniform_draws(3, 24, seed=94)
+    xo, ko, _ = orc.simulate_dynamics(sd, cfg, src.continuous, src.discrete, src.mask, u=u)
+    ts, dt = orc.time_grid(cfg)
+    xg, kg, _ = nm.generate(src.continuous.to(DEV), src.discrete.to(DEV), src.mask.to(DEV), ts, float(dt), _abi.step_options(cfg), u=u.to(DEV))
+    torch.cuda.synchronize()
+    real = src.mask.bool().squeeze(-1)
+    assert nm.launches <= 2
+    assert _rel(xg.cpu(), xo, real) < 2e-2
+    assert (kg.cpu()[real] == ko.squeeze(-1)[real]).float().mean() > 0.96
