@@ -41,9 +41,11 @@ constexpr int kCopySplit = MMF_COPY_SPLIT;   // bulk copies per weight-tile slic
 constexpr int kGoBars = 4;
 struct TfBars {
     uint64_t full[kBars], empty[kBars], done[4], go[kGoBars], go_attn, pfull[2], pempty[2];
-    // pair tiles: kvfull - the partner's epilogue has written its K / V rows of the current unit into this CTA (256 remote
-    // arrivals); kvfree - the partner's MMAs have finished reading ITS K / V buffers, this CTA may write the next unit's rows
-    uint64_t kvfull, kvfree;
+    // pair tiles: kfull / vfull - the partner's K / V rows of the current unit have landed in this CTA (one expect_tx arrival
+    // + the bytes of one bulk copy each, issued by the partner's attention issuer; S waits for K only, the V rows travel
+    // under the softmax); kvfree - the partner's MMAs of the current unit have finished reading ITS K / V buffers
+    // (tcgen05.commit multicast to this CTA): the next unit's rows may go there
+    uint64_t kfull, vfull, kvfree;
     uint32_t tmem_base;
 };
 
@@ -70,8 +72,7 @@ struct Epi {
     uint32_t gc;             // hand-offs to the weight-GEMM issuer so far (barrier gc % kGoBars, parity (gc / kGoBars) & 1)
     uint32_t kmask, kfull, kpart;   // 16-key groups of this thread's key half: attended by any row of the warp / in full by
                                     // every row / cut by a jet boundary of some row
-    // pair tiles: shared::cluster address of the partner CTA's arena and barriers, hand-off counter of attention units
-    uint32_t peer_arena, peer_kvfull, peer_kvfree, uc;
+    uint32_t uc;                    // pair tiles: attention units done so far
     unsigned long long* trace;   // clock stamps of CTA 0 / thread 0 for the first two timesteps (debugging aid) or null
     int mark_i, step;
 };
@@ -133,11 +134,16 @@ __device__ __forceinline__ float4 ldf4(const float* p) { return *reinterpret_cas
 // whole program (tcgen05.ld / barriers are collective) but never store an operand row.
 template <bool PAIR>
 __device__ __forceinline__ bool row_ok(int r) { return !PAIR || r < static_cast<int>(TfLay<true>::kRows); }
-__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+// Pair tiles, issued by one thread of the attention issuer warp: the rows [0, 80) of this CTA's K and V operands are
+// byte-for-byte the rows [80, 160) of the partner's (80 is a multiple of the 8-row swizzle atom), so each goes there as ONE
+// 10 KB bulk copy shared::cta -> shared::cluster whose bytes complete on the partner's kvfull barrier.
+__device__ __forceinline__ void mbar_expect_tx_remote(uint32_t cluster_bar_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar_addr), "r"(bytes) : "memory");
 }
-// generic-proxy writes (also those to the partner's shared memory) -> visible to tcgen05.mma operand reads
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t cluster_dst, const void* local_src, uint32_t bytes, uint32_t cluster_bar_addr) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(cluster_dst), "r"(smem_u32(local_src)), "r"(bytes), "r"(cluster_bar_addr) : "memory");
+}
 
 // Reductions over register arrays with four independent chains: the epilogue runs two warps per scheduler, so a
 // 32-deep dependent chain would leave the issue slots empty.
@@ -319,16 +325,8 @@ template <int HS, bool PAIR>
 struct QkvCols {     // scratch columns of q|k and v (see the op emission in tftile_model.cu)
     static constexpr uint32_t cQK = HS == 64 ? TfLay<PAIR>::cQkv64 : kScr + 128, cV = HS == 64 ? TfLay<PAIR>::cQkv64 + 128 : kScr + 64;
 };
-// row `row` of a [keys][128 B] swizzled chunk in the PARTNER's arena (pair tiles): units u0 .. u0 + NU - 1 from packed words
-template <int NU>
-__device__ __forceinline__ void stage_units_remote(uint32_t peer_chunk, int row, int u0, const float* v) {
-#pragma unroll
-    for (int u = 0; u < NU; ++u)
-        st_cluster_v4(peer_chunk + sw128_offset(row, u0 + u), pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
-                      pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
-}
 // q and k: bias, per-head LayerNorm, bf16 -> the Q / K operand chunks.  The score product only needs these.
-// Pair tiles: k of row r is key r here and key 80 + r in the partner CTA.
+// Pair tiles: k of row r is key r here and key 80 + r in the partner CTA (copied there by the attention issuer).
 template <int HS, bool PAIR>
 __device__ __forceinline__ void qk_epilogue(Epi& e, const float* bq, const float* bk, const float* qg, const float* qb,
                                             const float* kg, const float* kb) {
@@ -352,7 +350,6 @@ __device__ __forceinline__ void qk_epilogue(Epi& e, const float* bq, const float
     }
     if (row_ok<PAIR>(e.r)) {
         stage_row_bf16(e.arena + (e.hf ? L::oK : L::oQ), e.r, v);
-        if (PAIR && e.hf) stage_units_remote<8>(e.peer_arena + L::oK, static_cast<int>(L::kRows) + e.r, 0, v);
     }
 }
 // v: bias, bf16 -> V[key = r][d] (row r of a [keys][128 B] swizzled chunk: the MN-major B operand of P V, so no transpose);
@@ -375,7 +372,6 @@ __device__ __forceinline__ void v_epilogue(Epi& e, const float* bv) {
     for (int u = 0; u < 4; ++u)
         st_shared_v4(vb + sw128_offset(e.r, e.hf * 4 + u), pack_bf16x2(w[8 * u], w[8 * u + 1]), pack_bf16x2(w[8 * u + 2], w[8 * u + 3]),
                      pack_bf16x2(w[8 * u + 4], w[8 * u + 5]), pack_bf16x2(w[8 * u + 6], w[8 * u + 7]));
-    if (PAIR) stage_units_remote<4>(e.peer_arena + L::oVT, static_cast<int>(L::kRows) + e.r, e.hf * 4, w);
 }
 
 // scores of one head in scratch columns [scol, scol + 2 NK); thread handles keys [hf*NK, +NK) of its row (NK = 64: plain
@@ -576,21 +572,21 @@ __device__ __forceinline__ void attention_unit(Epi& e, bool first, bool more, co
         }
     } else {
         // ---- pair tile: this CTA holds one half of a 129...160-particle jet; keys = own 80 rows | partner's 80 rows ----
-        // The partner's MMAs of the previous unit must have finished reading ITS K / V buffers before this CTA writes
-        // the rows of this unit into them (kvfree, one phase per unit).
-        if (e.uc > 0) mbar_wait_cluster(&e.bars->kvfree, (e.uc - 1) & 1);
+        // The epilogue only fills this CTA's own rows; the attention issuer ships them to the partner and waits for the
+        // partner's before it issues S (kvfull / kvfree, see the issuer loop).
+        // kvfree of the previous unit = the partner's MMAs ran, hence the outgoing copy of this CTA's previous rows was
+        // complete long ago: the rows may be overwritten (normally an immediate pass).
+        if (e.uc > 0) { mark(e, 1); mbar_wait_cluster(&e.bars->kvfree, (e.uc - 1) & 1); mark(e, 6); }
+        ++e.uc;
         qk_epilogue<HS, true>(e, bq, bk, qg, qb, kg, kb);
         v_epilogue<HS, true>(e, bv);                      // (before S: its 160 columns cover the v accumulator)
-        fence_proxy_async_all();
-        mbar_arrive_remote(e.peer_kvfull);                // my K / V rows are in the partner's arena
-        go_attn(e);                                       // -> S (the issuer also waits for the partner's rows: kvfull)
+        go_attn(e);                                       // -> exchange of K / V rows, then S
         constexpr uint32_t cS = L::cS;
         if (HS == 64) {
             wait_done(e, 0);
             softmax_epilogue<true>(e, cS, scale, lo, span, 0, more);
             go_attn(e);                                       // -> P V (O in scratch [0,64))
             wait_done(e, 0);
-            mbar_arrive_remote(e.peer_kvfree);                // this CTA has finished reading its K / V buffers
             if (!first) wait_done(e, 2);
             o_epilogue<64, true>(e, L::cO64, 0, 0);
             go(e);                                            // -> projection
@@ -610,11 +606,9 @@ __device__ __forceinline__ void attention_unit(Epi& e, bool first, bool more, co
             if (!first) wait_done(e, 2);
             o_epilogue<32, true>(e, kScr, 0, 0);              // O of head 0 in scratch [0,32), under P V of head 1
             wait_done(e, 0);                                  // O of head 1 in scratch [32,64)
-            mbar_arrive_remote(e.peer_kvfree);
             o_epilogue<32, true>(e, kScr + 32, 32, 1);
             go(e);
         }
-        ++e.uc;
     }
 }
 
@@ -648,8 +642,9 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
         for (int i = 0; i < kGoBars; ++i) mbar_init(&bars->go[i], kEpi);
         mbar_init(&bars->go_attn, kEpi);
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->pfull[i], 1); mbar_init(&bars->pempty[i], kEpi); }
-        mbar_init(&bars->kvfull, kEpi);                   // pair tiles: arrivals of the partner CTA's epilogue threads
-        mbar_init(&bars->kvfree, kEpi);
+        mbar_init(&bars->kfull, 1);                       // pair tiles (see TfBars)
+        mbar_init(&bars->vfull, 1);
+        mbar_init(&bars->kvfree, 1);
         fence_mbar_init();
     }
     if (warp == 9) {
@@ -736,15 +731,30 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                     else mbar_wait(&bars->go[pg % kGoBars], (pg / kGoBars) & 1, static_cast<uint32_t>(i));
                     ++pg;
                 }
-                if (PAIR && (op.nkt & kTfNktPairWait)) {      // the partner's K / V rows of this unit (written through DSMEM)
-                    mbar_wait_cluster(&bars->kvfull, pk & 1);
+                if (PAIR && (op.nkt & kTfNktPairWait)) {
+                    // Exchange of the unit's K / V rows (this CTA's epilogue has just stored rows [0, 80) of both operands):
+                    // once the partner's MMAs of the previous unit are done with ITS buffers (kvfree), copy my rows into its
+                    // rows [80, 160) - K first: S only waits for the partner's K rows (kfull); the V rows (DSMEM moves
+                    // ~17 B/clk, 10 KB take ~1000 cycles) arrive under the softmax and are waited for before P V (vfull).
+                    if (pk > 0) mbar_wait_cluster(&bars->kvfree, (pk - 1) & 1);
+                    if (elect_one()) {
+                        const uint32_t peer = crank ^ 1u;
+                        const uint32_t kbar = dsmem_addr(&bars->kfull, peer), vbar = dsmem_addr(&bars->vfull, peer);
+                        constexpr uint32_t kHalf = L::kRows * 128u;
+                        mbar_expect_tx_remote(kbar, kHalf);
+                        bulk_copy_to_peer(dsmem_addr(arena + L::oK + kHalf, peer), arena + L::oK, kHalf, kbar);
+                        mbar_expect_tx_remote(vbar, kHalf);
+                        bulk_copy_to_peer(dsmem_addr(arena + L::oVT + kHalf, peer), arena + L::oVT, kHalf, vbar);
+                    }
+                    __syncwarp();
+                    mbar_wait_cluster(&bars->kfull, pk & 1);
                     ++pk;
-                    fence_proxy_async_all();
                 }
+                if (PAIR && (op.nkt & kTfNktPairWaitV)) mbar_wait_cluster(&bars->vfull, (pk - 1) & 1);   // first P V of the unit
                 const bool ring = (fl & kTfOpRing) != 0;
                 uint32_t a_lo = op.a_lo + base16, b_lo = op.b_lo + base16, acc = fl & kTfOpAcc;
                 const uint32_t d = tmem_base + op.dcol;
-                const uint32_t nkt = op.nkt & 0x3fu, sig = ((fl >> 4) & 3u) | ((op.nkt & 0x80u) >> 5);
+                const uint32_t nkt = op.nkt & 0x07u, sig = ((fl >> 4) & 3u) | ((op.nkt & 0x80u) >> 5);
                 for (uint32_t kt = 0; kt < nkt; ++kt) {
                     const uint32_t g = gbase + ti;
                     if (ring) {
@@ -772,6 +782,10 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                     b_lo += 8192 >> 4;
                     acc = 1u;
                 }
+                if (PAIR && (op.nkt & kTfNktPairFree)) {      // last product of the unit that reads K / V: tell the partner
+                    if (elect_one()) umma_commit_multicast(&bars->kvfree, static_cast<uint16_t>(1u << (crank ^ 1u)));
+                    __syncwarp();
+                }
                 if (sig) {
                     if (elect_one()) {
                         umma_commit(&bars->done[sig - 1u]);
@@ -783,6 +797,8 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 }
             }
         }
+        // the partner's last kvfree commit lands in THIS CTA's shared memory: wait for it before anybody may leave
+        if (PAIR && attn_issuer && pk > 0) mbar_wait_cluster(&bars->kvfree, (pk - 1) & 1);
         __syncwarp();
     } else {
         // ---------------------------------------------------- epilogue warps ----------------------------------------
@@ -816,13 +832,8 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
             const bool in = seg_b <= k0 && seg_e >= k0 + 16, out = seg_e <= k0 || seg_b >= k0 + 16;
             if (!__all_sync(0xffffffffu, in || out)) e.kpart |= 1u << g;
         }
+
         e.uc = 0;
-        e.peer_arena = 0; e.peer_kvfull = 0; e.peer_kvfree = 0;
-        if (PAIR) {
-            e.peer_arena = dsmem_addr(arena, crank ^ 1u);
-            e.peer_kvfull = dsmem_addr(&bars->kvfull, crank ^ 1u);
-            e.peer_kvfree = dsmem_addr(&bars->kvfree, crank ^ 1u);
-        }
         const int tb_row = a.per_jet_time ? meta->row_tb[r] : 0;
         const long long slot = a.row_slot[static_cast<size_t>(tile) * 128 + r];
         float* skipc = a.skip + (static_cast<size_t>(tile) * 256 + hf * 128) * 128 + r;    // + col * 128

@@ -67,7 +67,7 @@ struct TfOp {
     uint32_t b_lo;          // same for B when it lives in the arena (ignored for ring operands)
     uint32_t idesc;         // kind::f16 instruction descriptor (M = 128, N)
     uint16_t dcol;          // TMEM column of D (relative to the allocation base)
-    uint8_t nkt;            // bits 0-6: k-tiles; bit 7: third bit of the completion signal (signal 4 = commit -> done[3])
+    uint8_t nkt;            // bits 0-2: k-tiles; bits 4-6: pair-tile hand-offs (kTfNktPair*); bit 7: third bit of the completion signal (signal 4 = commit -> done[3])
     uint8_t flags;          // kTfOpAcc: the first MMA accumulates onto D; kTfOpWait: wait for the next "go" of the epilogue
                             // warps first; kTfOpRing: B from the weight ring; kTfOpHalfK: K = 32 (2 MMAs) instead of 64 (4);
                             // bits 4-5 (+ nkt bit 7): after the last k-tile 0 nothing, s = 1..4 commit -> done[s - 1];
@@ -78,7 +78,9 @@ struct TfOp {
 };
 static_assert(sizeof(TfOp) == 16, "TfOp is read with one 128-bit load");
 
-constexpr uint8_t kTfNktPairWait = 0x40;      // TfOp.nkt bit 6 (pair tiles): wait for the partner CTA's K / V rows first
+constexpr uint8_t kTfNktPairWait = 0x40;      // TfOp.nkt bit 6 (pair tiles): exchange the unit's K / V rows with the partner CTA first
+constexpr uint8_t kTfNktPairWaitV = 0x10;     // TfOp.nkt bit 4 (pair tiles): first P V of the unit - wait for the partner's V rows
+constexpr uint8_t kTfNktPairFree = 0x20;      // TfOp.nkt bit 5 (pair tiles): last product of the unit that reads K / V
 
 constexpr int kTfMaxOps = 1024;
 struct TfOpTable {          // MMA ops of one timestep; passed to the kernel BY VALUE (constant bank -> uniform registers)

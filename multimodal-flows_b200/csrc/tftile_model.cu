@@ -141,10 +141,11 @@ struct Builder {
     // both operands in the arena; B advances by 8 KB per k-tile
     // b_mn: B is MN-major (rows = K, N contiguous inside the 128-byte row) - bit 16 of the instruction descriptor
     void smem_op(uint32_t a_off, uint32_t b_off, int n, uint16_t dcol, int nkt, bool half_k, int acc, int wait, int signal, bool b_mn = false,
-                 bool pair_wait = false) {
+                 bool pair_wait = false, bool pair_free = false, bool pair_wait_v = false) {
         TfOp o{};
         o.a_lo = desc_lo(a_off); o.b_lo = desc_lo(b_off); o.idesc = idesc_bf16(n) | (b_mn ? 1u << 16 : 0u); o.dcol = dcol;
-        o.nkt = static_cast<uint8_t>(nkt | ((signal >> 2) << 7) | (pair_wait ? kTfNktPairWait : 0));
+        o.nkt = static_cast<uint8_t>(nkt | ((signal >> 2) << 7) | (pair_wait ? kTfNktPairWait : 0) | (pair_free ? kTfNktPairFree : 0) |
+                                     (pair_wait_v ? kTfNktPairWaitV : 0));
         o.flags = static_cast<uint8_t>((acc ? kTfOpAcc : 0u) | (wait ? kTfOpWait : 0u) | (half_k ? kTfOpHalfK : 0u) | (b_mn ? kTfOpBMn : 0u) |
                                        kTfOpAttn | (static_cast<uint32_t>(signal & 3) << 4));
         ops.push_back(o);
@@ -311,10 +312,10 @@ static int emit_program(const MmfModelDesc& d, WeightMap& wm, const LayH& L, Bui
                     // P [rows][160 keys] = two 64-key k-tiles + one 32-key tail, V rows 128 bytes apart
                     b.smem_op(oQ, oK, 160, L.cS, 1, true, 0, 1, 1, false, true);          // S of head 0 (after the partner's K / V rows)
                     b.smem_op(oQ + 64, oK + 64, 160, L.cS, 1, true, 0, 1, 1);             // S of head 1 (head 0's scores are in registers)
-                    b.smem_op(oP, oVT, 32, 256, 2, false, 0, 1, 0, true);                 // O_h0: keys 0..127
+                    b.smem_op(oP, oVT, 32, 256, 2, false, 0, 1, 0, true, false, false, true);   // O_h0: keys 0..127 (after the partner's V rows)
                     b.smem_op(oP + 2 * kT, oVT + 128 * 128, 32, 256, 1, true, 1, 0, 4, true);   //       keys 128..159 -> done[3]
                     b.smem_op(oP, oVT + 64, 32, 288, 2, false, 0, 1, 0, true);            // O_h1
-                    b.smem_op(oP + 2 * kT, oVT + 128 * 128 + 64, 32, 288, 1, true, 1, 0, 1, true);
+                    b.smem_op(oP + 2 * kT, oVT + 128 * 128 + 64, 32, 288, 1, true, 1, 0, 1, true, false, true);
                 }
                 if (!(g == 1 && u == 1)) qkv(u == 1 ? 1 : g, u == 1 ? 0 : 1, 1);    // released as soon as both score tiles are in registers
                 b.ring_op(oO, rows_of(w[g].proj, 0, 128), u * 64, 1, static_cast<uint16_t>(g * 128), 1, 1, (g == 1 && u == 1) ? 1 : 3);   // 3: done[2] = oO may be rewritten
@@ -365,8 +366,8 @@ static int emit_program(const MmfModelDesc& d, WeightMap& wm, const LayH& L, Bui
                 b.smem_op(oQ, oVT, 64, 448, 2, false, 0, 1, 1, true);            // O = P V; V is [key][d] (MN-major B)
             } else {
                 b.smem_op(oQ, oK, 160, L.cS, 1, false, 0, 1, 1, false, true);            // S over 160 keys (after the partner's rows)
-                b.smem_op(oP, oVT, 64, L.cO64, 2, false, 0, 1, 0, true);                 // O: keys 0..127
-                b.smem_op(oP + 2 * kT, oVT + 128 * 128, 64, L.cO64, 1, true, 1, 0, 1, true);   //    keys 128..159
+                b.smem_op(oP, oVT, 64, L.cO64, 2, false, 0, 1, 0, true, false, false, true);   // O: keys 0..127 (after the partner's V rows)
+                b.smem_op(oP + 2 * kT, oVT + 128 * 128, 64, L.cO64, 1, true, 1, 0, 1, true, false, true);   //    keys 128..159
             }
             if (u < 3) qkv(u + 1, 1);                                      // released as soon as the score tile is in registers
             b.ring_op(oO, rows_of(w.proj, 0, 256), u * 64, 1, 0, 1, 1, u == 3 ? 1 : 3);      // N = 256; 3: done[2] = oO may be rewritten
@@ -675,12 +676,12 @@ int tftile_launch(TfTileModel* m, cudaStream_t s) {
         cudaFree(d_trace);
         if (FILE* f = fopen(trace_path, "w")) {
             const unsigned long long kClk = 0x00ffffffffffffffull;
-            static const char* kTag[] = {"", " [before a wait]", " [done0 arrived]", " [done1 arrived]", " [done2 arrived]", " [done3 arrived]"};
+            static const char* kTag[] = {"", " [before a wait]", " [done0 arrived]", " [done1 arrived]", " [done2 arrived]", " [done3 arrived]", " [kvfree arrived]"};
             for (int st = 0; st < 2; ++st)
                 for (int i = 0; i < 512 && hbuf[st * 512 + i]; ++i) {
                     const unsigned long long c = hbuf[st * 512 + i] & kClk, c0 = hbuf[st * 512] & kClk, cp = i ? hbuf[st * 512 + i - 1] & kClk : c;
                     const unsigned tag = static_cast<unsigned>(hbuf[st * 512 + i] >> 56);
-                    fprintf(f, "step %d mark %3d  +%llu cycles (total %llu)%s\n", st, i, c - cp, c - c0, tag < 6 ? kTag[tag] : "");
+                    fprintf(f, "step %d mark %3d  +%llu cycles (total %llu)%s\n", st, i, c - cp, c - c0, tag < 7 ? kTag[tag] : "");
                 }
             // when each of the first 128 MMA ops of timestep 1 was issued, relative to the step start
             for (int i = 0; i < 128; ++i)

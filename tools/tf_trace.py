@@ -10,7 +10,8 @@ model = sys.argv[1] if len(sys.argv) > 1 else "ParticleFormer"
 cfg = make_config(model, num_timesteps=4)
 sd = synthetic.make_state_dict(cfg, "wide", 0)
 nm = _abi.NativeModel(cfg, sd, torch.device("cuda:0"))
-src = synthetic.source_state(256).to("cuda:0")
+dense = len(sys.argv) > 2 and sys.argv[2] == "dense"          # dense: pair tiles only (every jet 150 particles)
+src = (synthetic.source_state(4, dense=True) if dense else synthetic.source_state(256)).to("cuda:0")
 ts, dt = time_grid(cfg)
 for _ in range(2):
     nm.generate(src.continuous, src.discrete, src.mask, ts, dt, _abi.step_options(cfg))
