@@ -130,6 +130,31 @@ int mmf_jet_observables(const float* x, const int64_t* k, const int64_t* mask, c
                         int32_t B, int32_t D, int32_t V, float* kin_out, int32_t* counts_out, int32_t device,
                         void* stream);
 
+/* ---- forward half of the training step (model/MMF.py:138-170).  The encoder call in the middle is
+ * mmf_encoder_forward (per-jet times); there are no backward kernels yet, so this is the loss, not a trainer. ----
+ *
+ * mmf_bridge_sample: the intermediate state of both bridges at per-jet times t (B,):
+ *   model/CFM.py:171-184   UniformFlow.sample            xt = t x1 + (1 - t) x0 + sigma z
+ *   model/MJB.py:197-257   RandomTelegraphBridge.sample  kt ~ Categorical(P), P(k) = p(k->k1; t,1) p(k0->k; 0,t) / p(k0->k1; 0,1),
+ *                                                        p(a->b; s,t) = 1/V + w (delta_ab - 1/V), w = exp(-V beta (t - s))
+ * z (B,D,3) normals and u (B,D) uniforms may be supplied (parity: the categorical draw is the inverse CDF of u in channel
+ * order) or NULL (Philox4x32-10 keyed on (seed, first_global_jet D + slot)).  Outputs xt (B,D,3) f32, kt (B,D) i64.  No masking,
+ * like the reference.  Out-of-range tokens raise the flag read by mmf_hybrid_step_status. */
+int mmf_bridge_sample(const float* x0, const float* x1, const int64_t* k0, const int64_t* k1, const float* t, float sigma, float beta,
+                      int32_t V, const float* z, const float* u, uint64_t seed, uint64_t first_global_jet, int32_t B, int32_t D,
+                      float* xt, int64_t* kt, int32_t device, void* stream);
+/* mmf_multitask_loss: model/MMF.py:152-168 + MultiTaskLoss :203-233 after the encoder returned vt (B,D,3), logits (B,D,V):
+ *   loss_mse[b] = sum_{d,c} mask (vt - (x1 - x0))^2 / max(n_b, 1)          (conditional drift of model/CFM.py:186-193)
+ *   loss_ce[b]  = sum_d mask CE(logits, k1; ignore_index 0) / max(n_b, 1)
+ *   mode 0 "sum": loss = mean(loss_mse + loss_ce);  mode 1 "time-weighted": (u1, u2) = uncertainty_net(time features of t),
+ *   loss = mean(0.5 (u1 + e^-u1 loss_mse) + 0.5 (u2 + e^-u2 loss_ce)); w_fc (E,E), b_fc (E), w_proj (2,E), b_proj (2): the
+ *   checkpoint's loss_combine.uncertainty_net.{c_fc,c_proj} (device pointers, fp32; ignored for mode 0).
+ * per_jet: device (2,B) scratch that receives loss_mse | loss_ce; out5: device float[5] = loss, mean loss_mse, mean loss_ce,
+ * mean w_mse, mean w_ce (what MultiModalFlowBridge.loss returns). */
+int mmf_multitask_loss(const float* vt, const float* logits, const float* x0, const float* x1, const int64_t* k1, const int64_t* mask,
+                       const float* t, int32_t B, int32_t D, int32_t V, int32_t mode, int32_t n_embd, const float* w_fc, const float* b_fc,
+                       const float* w_proj, const float* b_proj, float* per_jet, float* out5, int32_t device, void* stream);
+
 /* The generated sample as one narrow record per jet - the device-side half of FlowGeneratorCallback:
  *   utils/callbacks.py:52-56   sample.continuous = sample.continuous * std + mean     (mean, std: HOST float[3], NULL = identity)
  *   utils/callbacks.py:57      sample.apply_mask()                                    (padded slots zeroed)

@@ -61,6 +61,14 @@ int sample_record_bytes(int D);
 int launch_sample_pack(const float* x, const long long* k, const long long* mask, const float* mean, const float* std_, long long B,
                        int D, unsigned char* rec, cudaStream_t stream);
 int launch_sample_unpack(const unsigned char* rec, long long B, int D, float* x, long long* k, long long* mask, cudaStream_t stream);
+// forward half of the training step (kernels_train.cu)
+int launch_bridge_sample(const float* x0, const float* x1, const long long* k0, const long long* k1, const float* t, float sigma,
+                         float beta, int V, const float* z, const float* u, unsigned long long seed, unsigned long long slot0,
+                         long long B, int D, float* xt, long long* kt, int* err, cudaStream_t s);
+int launch_multitask_loss(const float* vt, const float* logits, const float* x0, const float* x1, const long long* k1,
+                          const long long* mask, int B, int D, int V, float* loss_mse, float* loss_ce, cudaStream_t s);
+int launch_loss_combine(const float* t, const float* loss_mse, const float* loss_ce, const float* w_fc, const float* b_fc,
+                        const float* w_pr, const float* b_pr, int E, int mode, int B, float* out5, cudaStream_t s);
 int launch_force_tokens(const unsigned char* forced, const int* row_slot, int rows, int* ks, cudaStream_t stream);
 int launch_embed_x(const float* xs, int rows, const float* w0, const float* b0, int E, int apply_gelu, bf16* out,
                    int ld_out, cudaStream_t stream);

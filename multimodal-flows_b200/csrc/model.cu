@@ -641,6 +641,18 @@ int generate_device(MmfModel* m, const float* x0, const int64_t* k0, const int64
 // =============================================================================================
 extern "C" {
 
+// out-of-range-token flag of the standalone step, one per device (the step has no model handle to hang it on)
+static int* g_step_flag[64] = {nullptr};
+static int step_flag(int device, int** out) {
+    MMF_REQUIRE(device >= 0 && device < 64, "device index out of range");
+    if (!g_step_flag[device]) {
+        MMF_CUDA_OK(cudaMalloc(&g_step_flag[device], sizeof(int)));
+        MMF_CUDA_OK(cudaMemset(g_step_flag[device], 0, sizeof(int)));
+    }
+    *out = g_step_flag[device];
+    return 0;
+}
+
 int mmf_abi_version(void) { return MMF_ABI_VERSION; }
 const char* mmf_last_error(void) { return g_last_error.c_str(); }
 
@@ -761,18 +773,6 @@ int mmf_encoder_forward(MmfModel* m, const float* x, const int64_t* k, const int
     return check_device_flags(m, s);
 }
 
-// out-of-range-token flag of the standalone step, one per device (the step has no model handle to hang it on)
-static int* g_step_flag[64] = {nullptr};
-static int step_flag(int device, int** out) {
-    MMF_REQUIRE(device >= 0 && device < 64, "device index out of range");
-    if (!g_step_flag[device]) {
-        MMF_CUDA_OK(cudaMalloc(&g_step_flag[device], sizeof(int)));
-        MMF_CUDA_OK(cudaMemset(g_step_flag[device], 0, sizeof(int)));
-    }
-    *out = g_step_flag[device];
-    return 0;
-}
-
 int mmf_hybrid_step_status(int32_t device, void* stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     MMF_CUDA_OK(cudaSetDevice(device));
@@ -851,6 +851,31 @@ int mmf_make_source(const float* mult_probs, int32_t B, int32_t D, int32_t V, ui
     }
     return launch_make_source(a, x0, reinterpret_cast<long long*>(k0), reinterpret_cast<long long*>(mask), n_out,
                               static_cast<cudaStream_t>(stream));
+}
+
+int mmf_bridge_sample(const float* x0, const float* x1, const int64_t* k0, const int64_t* k1, const float* t, float sigma, float beta,
+                      int32_t V, const float* z, const float* u, uint64_t seed, uint64_t first_global_jet, int32_t B, int32_t D,
+                      float* xt, int64_t* kt, int32_t device, void* stream) {
+    MMF_REQUIRE(x0 && x1 && k0 && k1 && t && xt && kt, "null argument");
+    MMF_REQUIRE(B >= 0 && D >= 1, "bad batch shape");
+    MMF_CUDA_OK(cudaSetDevice(device));
+    int* flag = nullptr;
+    MMF_TRY(step_flag(device, &flag));
+    return launch_bridge_sample(x0, x1, reinterpret_cast<const long long*>(k0), reinterpret_cast<const long long*>(k1), t, sigma, beta, V, z, u,
+                                seed, first_global_jet * static_cast<uint64_t>(D), B, D, xt, reinterpret_cast<long long*>(kt), flag,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int mmf_multitask_loss(const float* vt, const float* logits, const float* x0, const float* x1, const int64_t* k1, const int64_t* mask,
+                       const float* t, int32_t B, int32_t D, int32_t V, int32_t mode, int32_t n_embd, const float* w_fc, const float* b_fc,
+                       const float* w_proj, const float* b_proj, float* per_jet /* 2 B */, float* out5, int32_t device, void* stream) {
+    MMF_REQUIRE(vt && logits && x0 && x1 && k1 && mask && t && per_jet && out5, "null argument");
+    MMF_REQUIRE(B >= 0 && D >= 1 && (mode == 0 || mode == 1), "bad arguments");
+    MMF_CUDA_OK(cudaSetDevice(device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    MMF_TRY(launch_multitask_loss(vt, logits, x0, x1, reinterpret_cast<const long long*>(k1), reinterpret_cast<const long long*>(mask), B, D, V,
+                                  per_jet, per_jet + B, s));
+    return launch_loss_combine(t, per_jet, per_jet + B, w_fc, b_fc, w_proj, b_proj, n_embd, mode, B, out5, s);
 }
 
 int64_t mmf_sample_record_bytes(int32_t D) { return D >= 1 ? sample_record_bytes(D) : 0; }

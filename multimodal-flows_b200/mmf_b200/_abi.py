@@ -47,7 +47,7 @@ EXPORTS = [
     "mmf_abi_version", "mmf_last_error", "mmf_model_create", "mmf_model_destroy", "mmf_encoder_forward",
     "mmf_hybrid_step", "mmf_hybrid_step_status", "mmf_euler_step", "mmf_generate", "mmf_generate_n", "mmf_model_status",
     "mmf_generate_host", "mmf_launch_count", "mmf_jet_observables", "mmf_make_source",
-    "mmf_sample_record_bytes", "mmf_pack_sample", "mmf_unpack_sample",
+    "mmf_sample_record_bytes", "mmf_pack_sample", "mmf_unpack_sample", "mmf_bridge_sample", "mmf_multitask_loss",
     "mmf_dbg_gemm", "mmf_dbg_gemm_resln", "mmf_dbg_gemm_qkv", "mmf_dbg_attention", "mmf_dbg_ring_plan",
     "mmf_profile_enable", "mmf_profile_num_classes", "mmf_profile_class_name", "mmf_profile_read",
 ]
@@ -84,6 +84,10 @@ def lib() -> ctypes.CDLL:
     L.mmf_sample_record_bytes.restype = c_int64
     L.mmf_pack_sample.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p]
     L.mmf_unpack_sample.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
+    L.mmf_bridge_sample.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int32, c_void_p, c_void_p,
+                                    c_uint64, c_uint64, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p]
+    L.mmf_multitask_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
+                                     c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
     L.mmf_generate_n.argtypes = L.mmf_generate.argtypes
     L.mmf_model_status.argtypes = [c_void_p, c_void_p]
     L.mmf_hybrid_step_status.argtypes = [c_int32, c_void_p]
@@ -366,6 +370,42 @@ def unpack_sample(rec, D: int, discrete: bool = True):
     idx = rec.device.index if rec.device.index is not None else torch.cuda.current_device()
     check(lib().mmf_unpack_sample(ptr(rec), B, D, ptr(x), ptr(k), ptr(mask), idx, stream_handle(rec.device)))
     return x, k, mask
+
+
+def bridge_sample(x0, x1, k0, k1, t, sigma, beta, vocab_size, z=None, u=None, seed=0, first_global_jet=0):
+    """xt (B,D,3), kt (B,D,1) of the two bridges at per-jet times t (reference model/CFM.py:171-184, model/MJB.py:197-257)."""
+    assert x0.is_cuda
+    B, D = x0.shape[:2]
+    f = lambda a: a.contiguous().float()
+    i = lambda a: a.reshape(B, D).contiguous().long()
+    x0, x1, k0, k1, t = f(x0), f(x1), i(k0), i(k1), f(t)
+    z = None if z is None else f(z)
+    u = None if u is None else f(u)
+    xt = torch.empty_like(x0)
+    kt = torch.empty_like(k0)
+    idx = x0.device.index if x0.device.index is not None else torch.cuda.current_device()
+    check(lib().mmf_bridge_sample(ptr(x0), ptr(x1), ptr(k0), ptr(k1), ptr(t), float(sigma), float(beta), int(vocab_size), ptr(z), ptr(u),
+                                  int(seed), int(first_global_jet), B, D, ptr(xt), ptr(kt), idx, stream_handle(x0.device)))
+    return xt, kt.unsqueeze(-1)
+
+
+def multitask_loss(vt, logits, x0, x1, k1, mask, t, mode, n_embd=256, net=None):
+    """(loss, loss_mse, loss_ce, w_mse, w_ce) as 0-dim tensors + per-jet (loss_mse, loss_ce) (reference model/MMF.py:152-168, 203-233).
+    mode "sum" | "time-weighted"; net = (c_fc.weight, c_fc.bias, c_proj.weight, c_proj.bias) of loss_combine.uncertainty_net."""
+    B, D = x0.shape[:2]
+    V = logits.shape[-1]
+    f = lambda a: a.contiguous().float()
+    vt, logits, x0, x1, t = f(vt), f(logits), f(x0), f(x1), f(t)
+    k1 = k1.reshape(B, D).contiguous().long()
+    mask = mask.reshape(B, D).contiguous().long()
+    per_jet = torch.empty(2, B, device=x0.device, dtype=torch.float32)
+    out = torch.empty(5, device=x0.device, dtype=torch.float32)
+    m = {"sum": 0, "time-weighted": 1}[mode]
+    ws = [None] * 4 if net is None else [f(w) for w in net]
+    idx = x0.device.index if x0.device.index is not None else torch.cuda.current_device()
+    check(lib().mmf_multitask_loss(ptr(vt), ptr(logits), ptr(x0), ptr(x1), ptr(k1), ptr(mask), ptr(t), B, D, V, m, int(n_embd),
+                                   ptr(ws[0]), ptr(ws[1]), ptr(ws[2]), ptr(ws[3]), ptr(per_jet), ptr(out), idx, stream_handle(x0.device)))
+    return out, per_jet
 
 
 def euler_step(vt, x, dt):

@@ -9,7 +9,10 @@ SURVEY.md section 9).  Lightning is optional: when ``pytorch_lightning`` is impo
 derive from ``LightningModule`` so ``Trainer.predict`` drives them unchanged; otherwise they are
 plain ``nn.Module`` objects and ``load_from_checkpoint`` reads the ``.ckpt`` with ``torch.load``.
 
-Training (``loss``, ``MultiTaskLoss``, optimisers) is not part of the accelerated path yet.
+Training: ``MultiModalFlowBridge.loss`` / ``training_step`` / ``validation_step`` run the FORWARD half of the reference's
+training step (bridge sampling, encoder forward, masked MSE + CE, MultiTaskLoss) through the library
+(``mmf_bridge_sample``, ``mmf_encoder_forward``, ``mmf_multitask_loss``) with parity against ``MultiModalFlowBridge.loss``;
+the encoder has no backward kernels yet, so the returned loss carries no gradient (in progress).
 """
 from __future__ import annotations
 
@@ -84,6 +87,9 @@ class _GenerativeBase(_Base):
         obj = cls(config)
         sd = {k[len("model."):]: v for k, v in ckpt["state_dict"].items() if k.startswith("model.")}
         obj.model.load_state_dict(sd, strict=strict)
+        lc = {k[len("loss_combine."):]: v for k, v in ckpt["state_dict"].items() if k.startswith("loss_combine.")}
+        if lc and hasattr(obj, "loss_combine"):
+            obj.loss_combine.load_state_dict(lc, strict=strict)
         obj.on_load_checkpoint(ckpt)
         return obj
 
@@ -110,8 +116,88 @@ class _GenerativeBase(_Base):
         return off
 
 
+class MultiTaskLoss(nn.Module):
+    """Parameter shell of the reference's loss combiner (model/MMF.py:203-233): ``uncertainty_net`` = MLP(n_embd, n_embd, 2)
+    for "time-weighted" (``c_proj.bias`` starts at 0: balanced L = L_mse + L_ce), ``loss_weights`` for "weighted", nothing for
+    "sum".  Same state_dict keys as the reference (``loss_combine.uncertainty_net.c_fc.weight`` ...); the arithmetic runs in
+    ``mmf_multitask_loss``."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.mode = config.multitask_loss
+        E = config.n_embd
+        if self.mode == "weighted":
+            self.loss_weights = nn.Parameter(torch.tensor([0.0, 0.0]))
+        elif self.mode == "time-weighted":
+            net = nn.Module()
+            net.c_fc = nn.Linear(E, E)
+            net.c_proj = nn.Linear(E, 2)
+            nn.init.constant_(net.c_proj.bias, 0.0)
+            self.uncertainty_net = net
+        elif self.mode != "sum":
+            raise ValueError(f"unknown multitask_loss '{self.mode}'")
+
+    def net_tensors(self):
+        n = self.uncertainty_net
+        return n.c_fc.weight, n.c_fc.bias, n.c_proj.weight, n.c_proj.bias
+
+
 class MultiModalFlowBridge(_GenerativeBase):
     """Hybrid continuous/discrete sampler (Euler ODE + telegraph tau-leap)."""
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.loss_combine = MultiTaskLoss(self.config)
+
+    # ---- forward half of the training step (reference model/MMF.py:42-68, 138-170) ----------------------------------
+    @torch.no_grad()
+    def loss(self, batch: DataCoupling, time: Optional[torch.Tensor] = None, z: Optional[torch.Tensor] = None,
+             u: Optional[torch.Tensor] = None):
+        """(loss, loss_mse, loss_ce, w_mse, w_ce) exactly as the reference returns them.  ``time`` (B,), ``z`` (B,D,3) and
+        ``u`` (B,D) replace the reference's torch.rand / randn_like / Categorical.sample draws when given (parity tests);
+        otherwise time comes from torch's generator like the reference and the bridge noise from the library's Philox."""
+        cfg = self.config
+        dev = self.device
+        B, V, eps = len(batch), cfg.vocab_size, cfg.time_eps
+        if cfg.multitask_loss == "weighted":
+            raise NotImplementedError("multitask_loss='weighted' is not on the accelerated path (use 'time-weighted' or 'sum')")
+        if time is None:
+            time = eps + (1.0 - eps) * torch.rand(B, device=dev)
+        tgt, src = batch.target.to(dev), batch.source.to(dev) if batch.source is not None else TensorMultiModal()
+        if not src.has_continuous:                       # reference model/CFM.py:175-177
+            src.continuous = torch.randn_like(tgt.continuous) * tgt.mask
+        if not src.has_discrete:                         # reference model/MJB.py:201-203
+            src.discrete = torch.randint_like(tgt.discrete, 1, V) * tgt.mask
+        xt, kt = _abi.bridge_sample(src.continuous, tgt.continuous, src.discrete, tgt.discrete, time.to(dev), cfg.sigma, cfg.beta, V,
+                                    z=None if z is None else z.to(dev), u=None if u is None else u.to(dev), seed=self.seed,
+                                    first_global_jet=self._jet_cursor)
+        self._jet_cursor += B
+        state = TensorMultiModal(continuous=xt, discrete=kt, mask=tgt.mask, time=time.to(dev))
+        vt, logits = self.model(state)
+        net = self.loss_combine.net_tensors() if cfg.multitask_loss == "time-weighted" else None
+        out, _ = _abi.multitask_loss(vt, logits, src.continuous, tgt.continuous, tgt.discrete, tgt.mask, time.to(dev),
+                                     cfg.multitask_loss, cfg.n_embd, net)
+        if cfg.multitask_loss == "sum":
+            return out[0], out[1], out[2], None, None
+        return out[0], out[1], out[2], out[3], out[4]
+
+    def _log(self, name, value, **kw):
+        if value is not None and _Base is not nn.Module:      # pragma: no cover - Lightning only
+            self.log(name, value, **kw)
+
+    def training_step(self, batch: DataCoupling, batch_idx: int = 0):
+        loss, loss_mse, loss_ce, w_mse, w_ce = self.loss(batch)
+        for name, v in (("train_loss", loss), ("train_loss_ce", loss_ce), ("train_loss_mse", loss_mse), ("train_weight_mse", w_mse),
+                        ("train_weight_ce", w_ce)):
+            self._log(name, v, on_epoch=True, sync_dist=True, batch_size=len(batch))
+        return {"loss": loss}
+
+    def validation_step(self, batch: DataCoupling, batch_idx: int = 0):
+        loss, loss_mse, loss_ce, w_mse, w_ce = self.loss(batch)
+        for name, v in (("val_loss", loss), ("val_loss_ce", loss_ce), ("val_loss_mse", loss_mse), ("val_weight_mse", w_mse),
+                        ("val_weight_ce", w_ce)):
+            self._log(name, v, on_epoch=True, sync_dist=True, batch_size=len(batch))
+        return {"val_loss": loss}
 
     @torch.no_grad()
     def simulate_dynamics(self, batch: DataCoupling, u: Optional[torch.Tensor] = None,

@@ -311,6 +311,61 @@ def hybrid_euler_step(vt, logits, x, k, t, dt, u, *, beta=0.075, vocab_size=9, t
     return x + vt * dt, k_new, rates
 
 
+# --------------------------------------------------------------------------
+# forward half of the training step                 reference model/MMF.py:138-170
+# --------------------------------------------------------------------------
+def telegraph_conditional_probability(t_in, t_out, k_in, k_out, beta: float, vocab_size: int) -> torch.Tensor:
+    """p(k_in -> k_out; t_in, t_out) = 1/V + w (delta - 1/V), w = exp(-V beta (t_out - t_in))
+    (reference ``model/MJB.py:231-253`` with the constant thermostat); t_* are (B,) tensors or floats, k_* (B,D,*)."""
+    t_in = torch.as_tensor(t_in, dtype=torch.float32)
+    t_out = torch.as_tensor(t_out, dtype=torch.float32)
+    B = k_out.shape[0]
+    t_in = t_in.expand(B) if t_in.dim() == 0 else t_in
+    t_out = t_out.expand(B) if t_out.dim() == 0 else t_out
+    w = torch.exp(-vocab_size * beta * (t_out - t_in))
+    kron = (k_out == k_in).float()
+    return 1.0 / vocab_size + w[:, None, None] * ((-1.0 / vocab_size) + kron)
+
+
+def bridge_sample(x0, x1, k0, k1, t, z, u, *, sigma: float, beta: float, vocab_size: int):
+    """xt = t x1 + (1 - t) x0 + sigma z  (reference ``model/CFM.py:171-184``) and kt ~ Categorical(P) with
+    P(k) = p(k -> k1; t, 1) p(k0 -> k; 0, t) / p(k0 -> k1; 0, 1)  (``model/MJB.py:197-229``), the categorical draw by inverse
+    CDF of the supplied u (B,D).  Returns xt (B,D,3), kt (B,D,1)."""
+    tt = t[:, None, None]
+    xt = tt * x1 + (1.0 - tt) * x0
+    xt = xt + sigma * z
+    k = torch.arange(vocab_size).view(1, 1, -1).expand(k0.shape[0], k0.shape[1], -1).float()
+    p = (telegraph_conditional_probability(t, 1.0, k, k1, beta, vocab_size)
+         * telegraph_conditional_probability(0.0, t, k0, k, beta, vocab_size)
+         / telegraph_conditional_probability(0.0, 1.0, k0, k1, beta, vocab_size))
+    return xt, categorical_from_uniform(p, u).unsqueeze(-1)
+
+
+def multitask_loss(sd_loss: SD, cfg, vt, logits, x0, x1, k1, mask, t):
+    """Masked MSE + CE per jet and their combination (reference ``model/MMF.py:152-168``, ``MultiTaskLoss`` ``:203-233``).
+    ``sd_loss``: the ``loss_combine.*`` entries of the checkpoint without the prefix.  Returns (loss, mse, ce, w_mse, w_ce)."""
+    B, V = x0.shape[0], cfg.vocab_size
+    m = mask.to(vt.dtype)
+    mse = (F.mse_loss(vt, x1 - x0, reduction="none") * m).sum(dim=[1, 2]) / m.sum(dim=[1, 2]).clamp_min(1.0)
+    ce = F.cross_entropy(logits.reshape(-1, V), k1.reshape(-1), ignore_index=0, reduction="none").view(B, -1) * m.squeeze(-1)
+    ce = ce.sum(dim=1) / m.squeeze(-1).sum(dim=1).clamp_min(1.0)
+    if cfg.multitask_loss == "sum":
+        return (mse + ce).mean(), mse.mean(), ce.mean(), None, None
+    temb = timestep_embedding(t, cfg.n_embd)
+    h = F.gelu(F.linear(temb, sd_loss["uncertainty_net.c_fc.weight"], sd_loss["uncertainty_net.c_fc.bias"]))
+    u1, u2 = F.linear(h, sd_loss["uncertainty_net.c_proj.weight"], sd_loss["uncertainty_net.c_proj.bias"]).unbind(-1)
+    w1, w2 = torch.exp(-u1), torch.exp(-u2)
+    loss = 0.5 * (u1 + w1 * mse) + 0.5 * (u2 + w2 * ce)
+    return loss.mean(), mse.mean(), ce.mean(), w1.mean(), w2.mean()
+
+
+def training_loss(sd: SD, sd_loss: SD, cfg, x0, k0, x1, k1, mask, t, z, u):
+    """``MultiModalFlowBridge.loss`` with its three random draws supplied (time, bridge noise, categorical uniforms)."""
+    xt, kt = bridge_sample(x0, x1, k0, k1, t, z, u, sigma=cfg.sigma, beta=cfg.beta, vocab_size=cfg.vocab_size)
+    vt, logits = encoder_forward(sd, cfg, t, xt, kt, mask)
+    return multitask_loss(sd_loss, cfg, vt, logits, x0, x1, k1, mask, t) + (xt, kt)
+
+
 def step_uniforms(seed: int, first_global_jet: int, num_steps: int, B: int, D: int, V: int) -> torch.Tensor:
     """The in-kernel draws of the sampler, restated: u[step, b, d, v] of the library's counter-based generator
     (``philox_uniforms`` in csrc/mmf_common.cuh) - Philox4x32-10, key = seed, counter = (global slot lo, hi, step, v // 4),

@@ -129,11 +129,13 @@ def supplied_uniforms(u_per_step):
 
 
 @contextlib.contextmanager
-def supplied_categorical(u_per_call):
-    """Route ``Categorical(probs).sample()`` inside the reference's solvers through pre-drawn uniforms (one (B,D) tensor
-    per call, in order): inverse CDF in channel order on the normalised probabilities torch itself stores."""
+def supplied_categorical(u_per_call, module: str = "model.solvers"):
+    """Route ``Categorical(probs).sample()`` inside one module of the reference (``model.solvers`` or ``model.MJB``) through
+    pre-drawn uniforms (one (B,D) tensor per call, in order): inverse CDF in channel order on the normalised probabilities
+    torch itself stores."""
     install()
-    import model.solvers as ref_solvers                   # type: ignore
+    import importlib
+    ref_solvers = importlib.import_module(module)
     it = iter(u_per_call)
     real = ref_solvers.Categorical
 
@@ -151,3 +153,27 @@ def supplied_categorical(u_per_call):
         yield
     finally:
         ref_solvers.Categorical = real
+
+
+@contextlib.contextmanager
+def supplied_rand(time, z):
+    """``torch.rand`` -> the supplied per-jet uniforms behind ``time`` (model/MMF.py:146) and ``torch.randn_like`` -> the supplied
+    bridge noise (model/CFM.py:182), once each, for a reproducible ``MultiModalFlowBridge.loss``."""
+    real_rand, real_randn_like = torch.rand, torch.randn_like
+    used = {"rand": 0, "randn_like": 0}
+
+    def fake_rand(*size, **kw):
+        used["rand"] += 1
+        assert tuple(size) == tuple(time.shape) or (len(size) == 1 and tuple(size[0:1]) == tuple(time.shape)), size
+        return time.clone()
+
+    def fake_randn_like(x, **kw):
+        used["randn_like"] += 1
+        assert x.shape == z.shape, (x.shape, z.shape)
+        return z.clone()
+
+    torch.rand, torch.randn_like = fake_rand, fake_randn_like
+    try:
+        yield used
+    finally:
+        torch.rand, torch.randn_like = real_rand, real_randn_like

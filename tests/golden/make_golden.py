@@ -15,6 +15,7 @@ Fixtures written next to this file:
 
   encoder_<Model>_<flavor>.npz   one forward, per-jet times, ragged multiplicities
   step_cases.npz                 HybridSolver.tauleap_step on supplied (vt, logits, u), tie-free
+  loss_<Model>_<mode>.npz        MultiModalFlowBridge.loss with supplied time / bridge noise / categorical uniforms
   euler_step_cases.npz           HybridSolver.euler_step (categorical jump) on supplied (vt, logits, u), tie-free
   traj_<Model>.npz               full N-step simulate_dynamics with supplied uniforms
 """
@@ -264,6 +265,58 @@ def gen_euler_steps(ref):
     np.savez_compressed(os.path.join(HERE, "euler_step_cases.npz"), **out)
 
 
+def gen_loss(ref):
+    """MultiModalFlowBridge.loss (reference model/MMF.py:138-170) with its three draws supplied: time (torch.rand),
+    bridge noise z (torch.randn_like) and the categorical uniforms of RandomTelegraphBridge.sample."""
+    for model, mt in (("FusedParticleFormer", "time-weighted"), ("ParticleFormer", "time-weighted"), ("FusedParticleFormer", "sum")):
+        cfg = make_config(model, multitask_loss=mt, sigma=1e-3)
+        sd = synthetic.make_state_dict(cfg, flavor="wide", seed=13)
+        g = torch.Generator().manual_seed(400)
+        ns = [1, 9, 40, 77, 128, 150]
+        B, D, V, E = len(ns), 150, cfg.vocab_size, cfg.n_embd
+        mask = synthetic.prefix_masks(torch.tensor(ns), D)
+        x0 = torch.randn(B, D, 3, generator=g) * mask
+        k0 = torch.randint(1, V, (B, D, 1), generator=g) * mask
+        x1 = (torch.randn(B, D, 3, generator=g) * 1.5 + 0.3) * mask
+        k1 = torch.randint(1, V, (B, D, 1), generator=g) * mask
+        u01 = torch.rand(B, generator=g)
+        z = torch.randn(B, D, 3, generator=g)
+        sd_loss = {}
+        if mt == "time-weighted":
+            sd_loss = {"uncertainty_net.c_fc.weight": torch.randn(E, E, generator=g) * 0.05, "uncertainty_net.c_fc.bias": torch.randn(E, generator=g) * 0.05,
+                       "uncertainty_net.c_proj.weight": torch.randn(2, E, generator=g) * 0.2, "uncertainty_net.c_proj.bias": torch.randn(2, generator=g) * 0.3}
+        m = ref_model(ref, cfg, sd, "mmf")
+        m.loss_combine.load_state_dict(sd_loss, strict=True)
+        t = cfg.time_eps + (1.0 - cfg.time_eps) * u01
+        # categorical uniforms away from the cumulative thresholds of the bridge probabilities (evaluated in double)
+        kk = torch.arange(V).view(1, 1, -1).expand(B, D, -1).double()
+        def cp(ti, to, ki, ko):
+            w = torch.exp(-V * cfg.beta * (torch.as_tensor(to, dtype=torch.float64) - torch.as_tensor(ti, dtype=torch.float64)).expand(B))
+            return 1.0 / V + w[:, None, None] * ((-1.0 / V) + (ko == ki).double())
+        p = cp(t.double(), 1.0, kk, k1.double()) * cp(0.0, t.double(), k0.double(), kk) / cp(0.0, 1.0, k0.double(), k1.double())
+        cum = (p / p.sum(-1, keepdim=True)).cumsum(-1)
+        u = torch.rand(B, D, generator=g)
+        for _ in range(50):
+            bad = ((u.double().unsqueeze(-1) - cum).abs() < 2e-5).any(-1)
+            if not bad.any():
+                break
+            u = torch.where(bad, torch.rand(B, D, generator=g), u)
+        assert not bad.any()
+        batch = ref.DataCoupling(source=ref.TensorMultiModal(continuous=x0.clone(), discrete=k0.clone(), mask=mask),
+                                 target=ref.TensorMultiModal(continuous=x1.clone(), discrete=k1.clone(), mask=mask))
+        with torch.no_grad(), ref_harness.supplied_rand(u01, z) as used, ref_harness.supplied_categorical([u], module="model.MJB"):
+            out = m.loss(batch)
+        assert used == {"rand": 1, "randn_like": 1}, used
+        oo = orc.training_loss(sd, sd_loss, cfg, x0, k0, x1, k1, mask, t, z, u)
+        vals = [float(v) if v is not None else float("nan") for v in out]
+        ovals = [float(v) if v is not None else float("nan") for v in oo[:5]]
+        print(f"loss {model} {mt}: reference {vals}  oracle {ovals}")
+        np.savez_compressed(os.path.join(HERE, f"loss_{model}_{mt}.npz"), x0=x0.numpy(), k0=k0.numpy().astype(np.uint8), x1=x1.numpy(),
+                            k1=k1.numpy().astype(np.uint8), mask=mask.numpy(), u01=u01.numpy(), time=t.numpy(), z=z.numpy(), u=u.numpy(),
+                            xt=oo[5].numpy(), kt=oo[6].numpy().astype(np.uint8), out=np.array(vals, np.float32), weight_seed=13, sigma=np.float32(cfg.sigma),
+                            weight_checksum=synthetic.state_dict_checksum(sd), **{"net_" + k.replace(".", "_"): v.numpy() for k, v in sd_loss.items()})
+
+
 def gen_trajectories(ref):
     for model, N in (("FusedParticleFormer", 100), ("ParticleFormer", 100), ("EPiC", 100)):
         cfg = make_config(model, num_timesteps=N, temperature=1.0)
@@ -317,12 +370,14 @@ def gen_trajectories(ref):
 if __name__ == "__main__":
     torch.manual_seed(0)
     ref = ref_harness.modules()
-    which = sys.argv[1:] or ["encoders", "steps", "euler", "traj"]
+    which = sys.argv[1:] or ["encoders", "steps", "euler", "loss", "traj"]
     if "encoders" in which:
         gen_encoders(ref)
     if "steps" in which:
         gen_steps(ref)
     if "euler" in which:
         gen_euler_steps(ref)
+    if "loss" in which:
+        gen_loss(ref)
     if "traj" in which:
         gen_trajectories(ref)

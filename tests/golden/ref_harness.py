@@ -7,4 +7,4 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from oracle.ref_loader import *            # noqa: F401,F403,E402
-from oracle.ref_loader import REF_PKG, REF_ROOT, available, install, modules, supplied_categorical, supplied_uniforms   # noqa: F401,E402
+from oracle.ref_loader import REF_PKG, REF_ROOT, available, install, modules, supplied_categorical, supplied_rand, supplied_uniforms   # noqa: F401,E402
