@@ -41,11 +41,11 @@ constexpr int kCopySplit = MMF_COPY_SPLIT;   // bulk copies per weight-tile slic
 constexpr int kGoBars = 4;
 struct TfBars {
     uint64_t full[kBars], empty[kBars], done[4], go[kGoBars], go_attn, pfull[2], pempty[2];
-    // pair tiles: kfull / vfull - the partner's K / V rows of the current unit have landed in this CTA (one expect_tx arrival
-    // + the bytes of one bulk copy each, issued by the partner's attention issuer; S waits for K only, the V rows travel
-    // under the softmax); kvfree - the partner's MMAs of the current unit have finished reading ITS K / V buffers
-    // (tcgen05.commit multicast to this CTA): the next unit's rows may go there
-    uint64_t kfull, vfull, kvfree;
+    // pair tiles: kfull / vfull - the partner's K / V rows of a unit have landed in this CTA (one expect_tx arrival + the
+    // bytes of one bulk copy each, issued by the partner's attention issuer); kfree / vfree - the partner's MMAs have read ITS
+    // K / V buffers for the last time in the unit (tcgen05.commit multicast to this CTA): the next unit's rows may go there,
+    // and - since the partner's products ran - this CTA's own outgoing copy of the unit has long left its local rows
+    uint64_t kfull, vfull, kfree, vfree;
     uint32_t tmem_base;
 };
 
@@ -72,7 +72,7 @@ struct Epi {
     uint32_t gc;             // hand-offs to the weight-GEMM issuer so far (barrier gc % kGoBars, parity (gc / kGoBars) & 1)
     uint32_t kmask, kfull, kpart;   // 16-key groups of this thread's key half: attended by any row of the warp / in full by
                                     // every row / cut by a jet boundary of some row
-    uint32_t uc;                    // pair tiles: attention units done so far
+    uint32_t kc, vc;                // pair tiles: K / V rows of how many units staged so far
     unsigned long long* trace;   // clock stamps of CTA 0 / thread 0 for the first two timesteps (debugging aid) or null
     int mark_i, step;
 };
@@ -537,12 +537,30 @@ __device__ __forceinline__ void head_epilogue(Epi& e, int q, const float* bias, 
 }
 
 // one attention unit (64 q-columns = 64/HS heads) of the current block, epilogue side
+// pair tiles: q / k of a unit -> Q / K operand rows, then the hand-off that lets the attention issuer ship the K rows to the
+// partner.  Runs for the first unit of a block at its top, for every later unit under the last P V product of the unit
+// before it (its QKV accumulator is ready by then), so that the exchange - DSMEM moves ~17 B/clk, 10 KB take ~1200 cycles
+// each way - is over when the unit starts.  `G`: the parameter group of that unit (q | k bias at G[qoff], G[koff]).
+template <int HS>
+__device__ __forceinline__ void pair_stage_k(Epi& e, const float* bq, const float* bk, const float* qg, const float* qb, const float* kg,
+                                             const float* kb) {
+    wait_done(e, 1);                                  // QKV of that unit
+    // kfree of the previous exchange: the partner's score products ran, so this CTA's outgoing K copy left the rows long ago
+    if (e.kc > 0) { mark(e, 1); mbar_wait_cluster(&e.bars->kfree, (e.kc - 1) & 1); mark(e, 6); }
+    ++e.kc;
+    qk_epilogue<HS, true>(e, bq, bk, qg, qb, kg, kb);
+    go_attn(e);                                       // -> the issuer sends the K rows
+}
+
+// nbq ... nkb: the q / k parameters of the NEXT unit of the block (pair tiles stage its K rows ahead; unused otherwise)
 template <int HS, bool PAIR>
 __device__ __forceinline__ void attention_unit(Epi& e, bool first, bool more, const float* bq, const float* bk, const float* bv, const float* qg,
-                                               const float* qb, const float* kg, const float* kb, int lo, uint32_t span) {
+                                               const float* qb, const float* kg, const float* kb, int lo, uint32_t span,
+                                               const float* nbq = nullptr, const float* nbk = nullptr, const float* nqg = nullptr,
+                                               const float* nqb = nullptr, const float* nkg = nullptr, const float* nkb = nullptr) {
     using L = TfLay<PAIR>;
     const float scale = 1.4426950408889634f * rsqrtf(static_cast<float>(HS));
-    wait_done(e, 1);                                  // QKV of this unit (issued under the previous unit's epilogue)
+    if (!PAIR) wait_done(e, 1);                       // QKV of this unit (issued under the previous unit's epilogue)
     if (!PAIR) {
         qk_epilogue<HS, false>(e, bq, bk, qg, qb, kg, kb);
         go_attn(e);                                       // -> S
@@ -572,20 +590,19 @@ __device__ __forceinline__ void attention_unit(Epi& e, bool first, bool more, co
         }
     } else {
         // ---- pair tile: this CTA holds one half of a 129...160-particle jet; keys = own 80 rows | partner's 80 rows ----
-        // The epilogue only fills this CTA's own rows; the attention issuer ships them to the partner and waits for the
-        // partner's before it issues S (kvfull / kvfree, see the issuer loop).
-        // kvfree of the previous unit = the partner's MMAs ran, hence the outgoing copy of this CTA's previous rows was
-        // complete long ago: the rows may be overwritten (normally an immediate pass).
-        if (e.uc > 0) { mark(e, 1); mbar_wait_cluster(&e.bars->kvfree, (e.uc - 1) & 1); mark(e, 6); }
-        ++e.uc;
-        qk_epilogue<HS, true>(e, bq, bk, qg, qb, kg, kb);
+        // The epilogue only fills this CTA's own rows; the attention issuer ships them to the partner (K ahead of time, V at the
+        // start of the unit, arriving under the softmax) and waits for the partner's before S / P V (see the issuer loop).
+        if (first) pair_stage_k<HS>(e, bq, bk, qg, qb, kg, kb);
+        if (e.vc > 0) { mark(e, 1); mbar_wait_cluster(&e.bars->vfree, (e.vc - 1) & 1); mark(e, 6); }   // (as kfree, for the V rows)
+        ++e.vc;
         v_epilogue<HS, true>(e, bv);                      // (before S: its 160 columns cover the v accumulator)
-        go_attn(e);                                       // -> exchange of K / V rows, then S
+        go_attn(e);                                       // -> V rows to the partner, then S once the partner's K rows are here
         constexpr uint32_t cS = L::cS;
         if (HS == 64) {
             wait_done(e, 0);
             softmax_epilogue<true>(e, cS, scale, lo, span, 0, more);
             go_attn(e);                                       // -> P V (O in scratch [0,64))
+            if (more) pair_stage_k<HS>(e, nbq, nbk, nqg, nqb, nkg, nkb);   // next unit's q / k under this unit's P V
             wait_done(e, 0);
             if (!first) wait_done(e, 2);
             o_epilogue<64, true>(e, L::cO64, 0, 0);
@@ -605,6 +622,7 @@ __device__ __forceinline__ void attention_unit(Epi& e, bool first, bool more, co
             go_attn(e);                                       // -> P V of head 1
             if (!first) wait_done(e, 2);
             o_epilogue<32, true>(e, kScr, 0, 0);              // O of head 0 in scratch [0,32), under P V of head 1
+            if (more) pair_stage_k<HS>(e, nbq, nbk, nqg, nqb, nkg, nkb);   // next unit's q / k under P V of head 1
             wait_done(e, 0);                                  // O of head 1 in scratch [32,64)
             o_epilogue<32, true>(e, kScr + 32, 32, 1);
             go(e);
@@ -644,7 +662,8 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->pfull[i], 1); mbar_init(&bars->pempty[i], kEpi); }
         mbar_init(&bars->kfull, 1);                       // pair tiles (see TfBars)
         mbar_init(&bars->vfull, 1);
-        mbar_init(&bars->kvfree, 1);
+        mbar_init(&bars->kfree, 1);
+        mbar_init(&bars->vfree, 1);
         fence_mbar_init();
     }
     if (warp == 9) {
@@ -714,7 +733,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
         const bool attn_issuer = warp == 11;
         // All 32 lanes run the loop converged (op fields stay in uniform registers, the table sits in the constant bank);
         // one elected lane issues the asynchronous instructions.  Descriptors come precomputed from the host.
-        uint32_t pg = 0, gbase = 0, pk = 0;                   // hand-offs consumed so far; pair tiles: kvfull phases consumed
+        uint32_t pg = 0, gbase = 0, nK = 0, nV = 0;           // hand-offs consumed so far; pair tiles: K / V exchanges started
         const uint32_t base16 = smem_u32(arena) >> 4;
         const uint32_t ring16 = base16 + (L::oRing >> 4) + (1u << 16);
         constexpr uint64_t kDescHi = static_cast<uint64_t>(0x40004040u) << 32;   // SBO 1024 B | version 1 | SWIZZLE_128B
@@ -731,29 +750,39 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                     else mbar_wait(&bars->go[pg % kGoBars], (pg / kGoBars) & 1, static_cast<uint32_t>(i));
                     ++pg;
                 }
-                if (PAIR && (op.nkt & kTfNktPairWait)) {
-                    // Exchange of the unit's K / V rows (this CTA's epilogue has just stored rows [0, 80) of both operands):
-                    // once the partner's MMAs of the previous unit are done with ITS buffers (kvfree), copy my rows into its
-                    // rows [80, 160) - K first: S only waits for the partner's K rows (kfull); the V rows (DSMEM moves
-                    // ~17 B/clk, 10 KB take ~1000 cycles) arrive under the softmax and are waited for before P V (vfull).
-                    if (pk > 0) mbar_wait_cluster(&bars->kvfree, (pk - 1) & 1);
-                    if (elect_one()) {
-                        const uint32_t peer = crank ^ 1u;
-                        const uint32_t kbar = dsmem_addr(&bars->kfull, peer), vbar = dsmem_addr(&bars->vfull, peer);
-                        constexpr uint32_t kHalf = L::kRows * 128u;
-                        mbar_expect_tx_remote(kbar, kHalf);
-                        bulk_copy_to_peer(dsmem_addr(arena + L::oK + kHalf, peer), arena + L::oK, kHalf, kbar);
-                        mbar_expect_tx_remote(vbar, kHalf);
-                        bulk_copy_to_peer(dsmem_addr(arena + L::oVT + kHalf, peer), arena + L::oVT, kHalf, vbar);
+                const uint32_t pfl = PAIR ? (static_cast<uint32_t>(op.dcol) >> kTfPairShift) : 0u;
+                if (PAIR && pfl) {
+                    // K / V exchange of a pair tile.  The rows [0, 80) of this CTA's K (V) operand are byte-for-byte the rows
+                    // [80, 160) of the partner's, so each goes there as ONE 10 KB bulk copy whose bytes complete on the
+                    // partner's kfull (vfull); a copy may start once the partner's MMAs are done with that buffer (kfree / vfree).
+                    constexpr uint32_t kHalf = L::kRows * 128u;
+                    const uint32_t peer = crank ^ 1u;
+                    if (pfl & kTfPairSendK) {
+                        if (nK > 0) mbar_wait_cluster(&bars->kfree, (nK - 1) & 1);
+                        if (elect_one()) {
+                            const uint32_t kbar = dsmem_addr(&bars->kfull, peer);
+                            mbar_expect_tx_remote(kbar, kHalf);
+                            bulk_copy_to_peer(dsmem_addr(arena + L::oK + kHalf, peer), arena + L::oK, kHalf, kbar);
+                        }
+                        __syncwarp();
+                        ++nK;
                     }
-                    __syncwarp();
-                    mbar_wait_cluster(&bars->kfull, pk & 1);
-                    ++pk;
+                    if (pfl & kTfPairSendVWaitK) {
+                        if (nV > 0) mbar_wait_cluster(&bars->vfree, (nV - 1) & 1);
+                        if (elect_one()) {
+                            const uint32_t vbar = dsmem_addr(&bars->vfull, peer);
+                            mbar_expect_tx_remote(vbar, kHalf);
+                            bulk_copy_to_peer(dsmem_addr(arena + L::oVT + kHalf, peer), arena + L::oVT, kHalf, vbar);
+                        }
+                        __syncwarp();
+                        mbar_wait_cluster(&bars->kfull, nV & 1);          // the partner's K rows of this unit
+                        ++nV;
+                    }
+                    if (pfl & kTfPairWaitV) mbar_wait_cluster(&bars->vfull, (nV - 1) & 1);
                 }
-                if (PAIR && (op.nkt & kTfNktPairWaitV)) mbar_wait_cluster(&bars->vfull, (pk - 1) & 1);   // first P V of the unit
                 const bool ring = (fl & kTfOpRing) != 0;
                 uint32_t a_lo = op.a_lo + base16, b_lo = op.b_lo + base16, acc = fl & kTfOpAcc;
-                const uint32_t d = tmem_base + op.dcol;
+                const uint32_t d = tmem_base + (op.dcol & kTfDcolMask);
                 const uint32_t nkt = op.nkt & 0x07u, sig = ((fl >> 4) & 3u) | ((op.nkt & 0x80u) >> 5);
                 for (uint32_t kt = 0; kt < nkt; ++kt) {
                     const uint32_t g = gbase + ti;
@@ -782,8 +811,11 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                     b_lo += 8192 >> 4;
                     acc = 1u;
                 }
-                if (PAIR && (op.nkt & kTfNktPairFree)) {      // last product of the unit that reads K / V: tell the partner
-                    if (elect_one()) umma_commit_multicast(&bars->kvfree, static_cast<uint16_t>(1u << (crank ^ 1u)));
+                if (PAIR && (pfl & (kTfPairFreeK | kTfPairFreeV))) {      // last product of the unit that reads K (V): tell the partner
+                    if (elect_one()) {
+                        if (pfl & kTfPairFreeK) umma_commit_multicast(&bars->kfree, static_cast<uint16_t>(1u << (crank ^ 1u)));
+                        if (pfl & kTfPairFreeV) umma_commit_multicast(&bars->vfree, static_cast<uint16_t>(1u << (crank ^ 1u)));
+                    }
                     __syncwarp();
                 }
                 if (sig) {
@@ -798,7 +830,8 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
             }
         }
         // the partner's last kvfree commit lands in THIS CTA's shared memory: wait for it before anybody may leave
-        if (PAIR && attn_issuer && pk > 0) mbar_wait_cluster(&bars->kvfree, (pk - 1) & 1);
+        if (PAIR && attn_issuer && nK > 0) mbar_wait_cluster(&bars->kfree, (nK - 1) & 1);
+        if (PAIR && attn_issuer && nV > 0) mbar_wait_cluster(&bars->vfree, (nV - 1) & 1);
         __syncwarp();
     } else {
         // ---------------------------------------------------- epilogue warps ----------------------------------------
@@ -833,7 +866,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
             if (!__all_sync(0xffffffffu, in || out)) e.kpart |= 1u << g;
         }
 
-        e.uc = 0;
+        e.kc = 0; e.vc = 0;
         const int tb_row = a.per_jet_time ? meta->row_tb[r] : 0;
         const long long slot = a.row_slot[static_cast<size_t>(tile) * 128 + r];
         float* skipc = a.skip + (static_cast<size_t>(tile) * 256 + hf * 128) * 128 + r;    // + col * 128
@@ -953,8 +986,13 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 for (int g = 0; g < 2; ++g) {
                     const float* G = e.P + g * tfp::SA_GROUP;
                     for (int u = 0; u < 2; ++u)
+                    {
+                        const int ng = u == 1 ? 1 : g, nu = u ^ 1;          // the unit after (g, u): (g, 1) or (1, 0)
+                        const float* NG = e.P + ng * tfp::SA_GROUP;
                         attention_unit<32, PAIR>(e, g == 0 && u == 0, !(g == 1 && u == 1), G + tfp::SA_BQKV + u * 64, G + tfp::SA_BQKV + 128 + u * 64, G + tfp::SA_BQKV + 256 + u * 64,
-                                           G + tfp::SA_QG, G + tfp::SA_QB, G + tfp::SA_KG, G + tfp::SA_KB, att_lo, att_span);
+                                                 G + tfp::SA_QG, G + tfp::SA_QB, G + tfp::SA_KG, G + tfp::SA_KB, att_lo, att_span,
+                                                 NG + tfp::SA_BQKV + nu * 64, NG + tfp::SA_BQKV + 128 + nu * 64, NG + tfp::SA_QG, NG + tfp::SA_QB, NG + tfp::SA_KG, NG + tfp::SA_KB);
+                    }
                 }
                 wait_done(e, 0);                              // last projection of group 1 has landed
                 {
@@ -1007,7 +1045,9 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 const bool last = blk + 1 == a.n_main;
                 for (int u = 0; u < 4; ++u)
                     attention_unit<64, PAIR>(e, u == 0, u < 3, e.P + tfp::BA_BQKV + u * 64, e.P + tfp::BA_BQKV + 256 + u * 64, e.P + tfp::BA_BQKV + 512 + u * 64,
-                                       e.P + tfp::BA_QG, e.P + tfp::BA_QB, e.P + tfp::BA_KG, e.P + tfp::BA_KB, att_lo, att_span);
+                                       e.P + tfp::BA_QG, e.P + tfp::BA_QB, e.P + tfp::BA_KG, e.P + tfp::BA_KB, att_lo, att_span,
+                                       e.P + tfp::BA_BQKV + (u + 1) * 64, e.P + tfp::BA_BQKV + 256 + (u + 1) * 64, e.P + tfp::BA_QG, e.P + tfp::BA_QB,
+                                       e.P + tfp::BA_KG, e.P + tfp::BA_KB);
                 wait_done(e, 0);
                 {
                     const RowStat sum = resid_update(e, e.P + tfp::BA_BPROJ + hf * 128, nullptr, nullptr);

@@ -66,8 +66,8 @@ struct TfOp {
     uint32_t a_lo;          // (arena offset of A >> 4) | LBO field of the descriptor low word
     uint32_t b_lo;          // same for B when it lives in the arena (ignored for ring operands)
     uint32_t idesc;         // kind::f16 instruction descriptor (M = 128, N)
-    uint16_t dcol;          // TMEM column of D (relative to the allocation base)
-    uint8_t nkt;            // bits 0-2: k-tiles; bits 4-6: pair-tile hand-offs (kTfNktPair*); bit 7: third bit of the completion signal (signal 4 = commit -> done[3])
+    uint16_t dcol;          // bits 0-9: TMEM column of D (relative to the allocation base); bits 10-15: kTfPair* hand-offs
+    uint8_t nkt;            // bits 0-2: k-tiles (0: a pure hand-off op of a pair tile); bit 7: third bit of the completion signal (signal 4 = commit -> done[3])
     uint8_t flags;          // kTfOpAcc: the first MMA accumulates onto D; kTfOpWait: wait for the next "go" of the epilogue
                             // warps first; kTfOpRing: B from the weight ring; kTfOpHalfK: K = 32 (2 MMAs) instead of 64 (4);
                             // bits 4-5 (+ nkt bit 7): after the last k-tile 0 nothing, s = 1..4 commit -> done[s - 1];
@@ -78,9 +78,15 @@ struct TfOp {
 };
 static_assert(sizeof(TfOp) == 16, "TfOp is read with one 128-bit load");
 
-constexpr uint8_t kTfNktPairWait = 0x40;      // TfOp.nkt bit 6 (pair tiles): exchange the unit's K / V rows with the partner CTA first
-constexpr uint8_t kTfNktPairWaitV = 0x10;     // TfOp.nkt bit 4 (pair tiles): first P V of the unit - wait for the partner's V rows
-constexpr uint8_t kTfNktPairFree = 0x20;      // TfOp.nkt bit 5 (pair tiles): last product of the unit that reads K / V
+// Pair tiles: hand-offs of the K / V exchange between the two CTAs of a cluster, carried in the high bits of TfOp.dcol
+// (the TMEM column needs 9 bits).  All of them are executed by the attention-issuer warp around the op they sit on.
+constexpr uint32_t kTfDcolMask = 0x3ffu;
+constexpr uint32_t kTfPairShift = 10;
+constexpr uint32_t kTfPairSendK = 1u;        // before the op: (partner done with its K rows of the previous exchange) copy my K rows to it
+constexpr uint32_t kTfPairSendVWaitK = 2u;   // before the op: (partner done with its V rows) copy my V rows to it; wait for its K rows
+constexpr uint32_t kTfPairFreeK = 4u;        // after the op: commit -> partner's kfree (my MMAs have read K for the last time)
+constexpr uint32_t kTfPairWaitV = 8u;        // before the op: wait for the partner's V rows
+constexpr uint32_t kTfPairFreeV = 16u;       // after the op: commit -> partner's vfree
 
 constexpr int kTfMaxOps = 1024;
 struct TfOpTable {          // MMA ops of one timestep; passed to the kernel BY VALUE (constant bank -> uniform registers)

@@ -141,15 +141,17 @@ struct Builder {
     // both operands in the arena; B advances by 8 KB per k-tile
     // b_mn: B is MN-major (rows = K, N contiguous inside the 128-byte row) - bit 16 of the instruction descriptor
     void smem_op(uint32_t a_off, uint32_t b_off, int n, uint16_t dcol, int nkt, bool half_k, int acc, int wait, int signal, bool b_mn = false,
-                 bool pair_wait = false, bool pair_free = false, bool pair_wait_v = false) {
+                 uint32_t pair_flags = 0) {
         TfOp o{};
-        o.a_lo = desc_lo(a_off); o.b_lo = desc_lo(b_off); o.idesc = idesc_bf16(n) | (b_mn ? 1u << 16 : 0u); o.dcol = dcol;
-        o.nkt = static_cast<uint8_t>(nkt | ((signal >> 2) << 7) | (pair_wait ? kTfNktPairWait : 0) | (pair_free ? kTfNktPairFree : 0) |
-                                     (pair_wait_v ? kTfNktPairWaitV : 0));
+        o.a_lo = desc_lo(a_off); o.b_lo = desc_lo(b_off); o.idesc = idesc_bf16(n) | (b_mn ? 1u << 16 : 0u);
+        o.dcol = static_cast<uint16_t>(dcol | (pair_flags << kTfPairShift));
+        o.nkt = static_cast<uint8_t>(nkt | ((signal >> 2) << 7));
         o.flags = static_cast<uint8_t>((acc ? kTfOpAcc : 0u) | (wait ? kTfOpWait : 0u) | (half_k ? kTfOpHalfK : 0u) | (b_mn ? kTfOpBMn : 0u) |
                                        kTfOpAttn | (static_cast<uint32_t>(signal & 3) << 4));
         ops.push_back(o);
     }
+    // pair tiles: a pure hand-off of the attention issuer (no MMA): the K rows of a unit staged ahead of time
+    void pair_send_k() { smem_op(0, 0, 16, 0, 0, false, 0, 1, 0, false, kTfPairSendK); }
     bool plan_ring() {
         std::vector<int> kb(tiles.size());
         for (size_t i = 0; i < tiles.size(); ++i) kb[i] = static_cast<int>(tiles[i].x >> 24);
@@ -309,13 +311,17 @@ static int emit_program(const MmfModelDesc& d, WeightMap& wm, const LayH& L, Bui
                     b.smem_op(oQ, oVT + 64, 32, 288, 2, false, 0, 1, 1, true);   // O_h1: d columns 32..63 of the V rows
                 } else {
                     // pair tile: 160 keys, one head at a time on the score columns [320,480); O_h0 [256,288), O_h1 [288,320);
-                    // P [rows][160 keys] = two 64-key k-tiles + one 32-key tail, V rows 128 bytes apart
-                    b.smem_op(oQ, oK, 160, L.cS, 1, true, 0, 1, 1, false, true);          // S of head 0 (after the partner's K / V rows)
-                    b.smem_op(oQ + 64, oK + 64, 160, L.cS, 1, true, 0, 1, 1);             // S of head 1 (head 0's scores are in registers)
-                    b.smem_op(oP, oVT, 32, 256, 2, false, 0, 1, 0, true, false, false, true);   // O_h0: keys 0..127 (after the partner's V rows)
-                    b.smem_op(oP + 2 * kT, oVT + 128 * 128, 32, 256, 1, true, 1, 0, 4, true);   //       keys 128..159 -> done[3]
-                    b.smem_op(oP, oVT + 64, 32, 288, 2, false, 0, 1, 0, true);            // O_h1
-                    b.smem_op(oP + 2 * kT, oVT + 128 * 128 + 64, 32, 288, 1, true, 1, 0, 1, true, false, true);
+                    // P [rows][160 keys] = two 64-key k-tiles + one 32-key tail, V rows 128 bytes apart.  K / V exchange hand-offs:
+                    // K of the block's first unit is sent by its own hand-off op, K of every later unit right after this unit's
+                    // last P V hand-off (the epilogue stages it under that product).
+                    if (g == 0 && u == 0) b.pair_send_k();
+                    b.smem_op(oQ, oK, 160, L.cS, 1, true, 0, 1, 1, false, kTfPairSendVWaitK);          // S of head 0
+                    b.smem_op(oQ + 64, oK + 64, 160, L.cS, 1, true, 0, 1, 1, false, kTfPairFreeK);     // S of head 1 (head 0's scores are in registers)
+                    b.smem_op(oP, oVT, 32, 256, 2, false, 0, 1, 0, true, kTfPairWaitV);                // O_h0: keys 0..127
+                    b.smem_op(oP + 2 * kT, oVT + 128 * 128, 32, 256, 1, true, 1, 0, 4, true);          //       keys 128..159 -> done[3]
+                    b.smem_op(oP, oVT + 64, 32, 288, 2, false, 0, 1, 0, true);                         // O_h1
+                    b.smem_op(oP + 2 * kT, oVT + 128 * 128 + 64, 32, 288, 1, true, 1, 0, 1, true, kTfPairFreeV);
+                    if (!(g == 1 && u == 1)) b.pair_send_k();
                 }
                 if (!(g == 1 && u == 1)) qkv(u == 1 ? 1 : g, u == 1 ? 0 : 1, 1);    // released as soon as both score tiles are in registers
                 b.ring_op(oO, rows_of(w[g].proj, 0, 128), u * 64, 1, static_cast<uint16_t>(g * 128), 1, 1, (g == 1 && u == 1) ? 1 : 3);   // 3: done[2] = oO may be rewritten
@@ -365,9 +371,11 @@ static int emit_program(const MmfModelDesc& d, WeightMap& wm, const LayH& L, Bui
                 b.smem_op(oQ, oK, 128, 256, 1, false, 0, 1, 1);                  // S = Q K^T
                 b.smem_op(oQ, oVT, 64, 448, 2, false, 0, 1, 1, true);            // O = P V; V is [key][d] (MN-major B)
             } else {
-                b.smem_op(oQ, oK, 160, L.cS, 1, false, 0, 1, 1, false, true);            // S over 160 keys (after the partner's rows)
-                b.smem_op(oP, oVT, 64, L.cO64, 2, false, 0, 1, 0, true, false, false, true);   // O: keys 0..127 (after the partner's V rows)
-                b.smem_op(oP + 2 * kT, oVT + 128 * 128, 64, L.cO64, 1, true, 1, 0, 1, true, false, true);   //    keys 128..159
+                if (u == 0) b.pair_send_k();
+                b.smem_op(oQ, oK, 160, L.cS, 1, false, 0, 1, 1, false, kTfPairSendVWaitK | kTfPairFreeK);   // S over 160 keys
+                b.smem_op(oP, oVT, 64, L.cO64, 2, false, 0, 1, 0, true, kTfPairWaitV);                        // O: keys 0..127
+                b.smem_op(oP + 2 * kT, oVT + 128 * 128, 64, L.cO64, 1, true, 1, 0, 1, true, kTfPairFreeV);    //    keys 128..159
+                if (u < 3) b.pair_send_k();
             }
             if (u < 3) qkv(u + 1, 1);                                      // released as soon as the score tile is in registers
             b.ring_op(oO, rows_of(w.proj, 0, 256), u * 64, 1, 0, 1, 1, u == 3 ? 1 : 3);      // N = 256; 3: done[2] = oO may be rewritten
