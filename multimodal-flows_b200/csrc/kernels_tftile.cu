@@ -202,32 +202,15 @@ __device__ __forceinline__ void stage32(uint8_t* abase, int r, int col0, const f
 }
 
 // ---- residual-stream passes; every thread owns columns [hf*128, hf*128+128) of its row -----------------------
-// A tcgen05.ld of 32 columns + wait::ld is a ~235-cycle round trip (tools/ubench/tmem_rate.cu), as long as the arithmetic on
-// those 32 values; with two epilogue warps per scheduler it is only half hidden.  The four 32-column chunks of a pass are
-// therefore software-pipelined over two register buffers: the load of chunk c + 1 is in flight while chunk c is worked on.
-//   body(cc, v): v holds columns [cc*32, cc*32 + 32) of the thread's 128
-template <class F>
-__device__ __forceinline__ void tmem_pass4(uint32_t taddr0, F&& body) {
-    float a[32], b[32];
-    tmem_ld32(taddr0, a);
-    tmem_ld_wait();
-    tmem_ld32(taddr0 + 32, b);
-    body(0, a);
-    tmem_ld_wait();
-    tmem_ld32(taddr0 + 64, a);
-    body(1, b);
-    tmem_ld_wait();
-    tmem_ld32(taddr0 + 96, b);
-    body(2, a);
-    tmem_ld_wait();
-    body(3, b);
-}
-
 // v = resid + add0 (+ add1) (+ skip); stored back; returns the statistics of the thread's 128 columns
 __device__ __forceinline__ RowStat resid_update(Epi& e, const float* add0, const float* add1, const float* skipc) {
     RowStat st{0.f, 0.f, 0.f};
-    tmem_pass4(e.taddr + e.hf * 128, [&](int cc, float* v) {
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
         const int c0 = cc * 32;
+        float v[32];
+        tmem_ld32(e.taddr + e.hf * 128 + c0, v);
+        tmem_ld_wait();
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const float4 a = ldf4(add0 + c0 + 4 * u);
@@ -249,7 +232,7 @@ __device__ __forceinline__ RowStat resid_update(Epi& e, const float* add0, const
         if (cc == 0) st.c = v[0];
         stat_regs<32>(v, st);
         tmem_st32(e.taddr + e.hf * 128 + c0, v);
-    });
+    }
     tmem_st_wait();
     return st;
 }
@@ -277,9 +260,14 @@ __device__ __forceinline__ void ln_stats(Epi& e, const RowStat& st, int slot, fl
 // normalised row -> bf16 GEMM operand (Abuf)
 template <bool PAIR>
 __device__ __forceinline__ void ln_to_abuf(Epi& e, float mean, float rstd, const float* g, const float* b) {
-    const float2 nm = f2dup(-mean), rs = f2dup(rstd);
-    tmem_pass4(e.taddr + e.hf * 128, [&](int cc, float* v) {
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
         const int c0 = cc * 32;
+        float v[32];
+        tmem_ld32(e.taddr + e.hf * 128 + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        const float2 nm = f2dup(-mean), rs = f2dup(rstd);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const float4 gg = ldf4(g + c0 + 4 * u), bb = ldf4(b + c0 + 4 * u);
@@ -287,13 +275,17 @@ __device__ __forceinline__ void ln_to_abuf(Epi& e, float mean, float rstd, const
             MMF_SET2(v, 4 * u + 2, f2fma(f2mul(f2add(MMF_V2(v, 4 * u + 2), nm), rs), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w)));
         }
         stage32<PAIR>(e.arena + TfLay<PAIR>::oA, e.r, e.hf * 128 + c0, v);
-    });
+    }
 }
 // normalised row (+ post) -> back into the residual stream; returns the new row statistics (stream junction of ParticleFormer)
 __device__ __forceinline__ RowStat ln_to_resid(Epi& e, float mean, float rstd, const float* g, const float* b, const float* post) {
     RowStat st{0.f, 0.f, 0.f};
-    tmem_pass4(e.taddr + e.hf * 128, [&](int cc, float* v) {
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
         const int c0 = cc * 32;
+        float v[32];
+        tmem_ld32(e.taddr + e.hf * 128 + c0, v);
+        tmem_ld_wait();
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const float4 gg = ldf4(g + c0 + 4 * u), bb = ldf4(b + c0 + 4 * u), pp = ldf4(post + c0 + 4 * u);
@@ -305,7 +297,7 @@ __device__ __forceinline__ RowStat ln_to_resid(Epi& e, float mean, float rstd, c
         if (cc == 0) st.c = v[0];
         stat_regs<32>(v, st);
         tmem_st32(e.taddr + e.hf * 128 + c0, v);
-    });
+    }
     tmem_st_wait();
     return st;
 }
@@ -335,25 +327,16 @@ struct QkvCols {     // scratch columns of q|k and v (see the op emission in tft
 };
 // q and k: bias, per-head LayerNorm, bf16 -> the Q / K operand chunks.  The score product only needs these.
 // Pair tiles: k of row r is key r here and key 80 + r in the partner CTA (copied there by the attention issuer).
-// `pre` / `prew`: the accumulator columns already in registers (qkv_tmem_load: one TMEM round trip for q | k and v together)
-template <int HS, bool PAIR>
-__device__ __forceinline__ void qkv_tmem_load(Epi& e, float* v, float* w) {
-    tmem_ld32(e.taddr + QkvCols<HS, PAIR>::cQK + e.hf * 64, v);
-    tmem_ld32(e.taddr + QkvCols<HS, PAIR>::cQK + e.hf * 64 + 32, v + 32);
-    tmem_ld32(e.taddr + QkvCols<HS, PAIR>::cV + e.hf * 32, w);
-    tmem_ld_wait();
-}
+// `prew` (32 registers, optional): also fetch this thread's v columns, for a v_epilogue that must not touch TMEM any more
 template <int HS, bool PAIR>
 __device__ __forceinline__ void qk_epilogue(Epi& e, const float* bq, const float* bk, const float* qg, const float* qb,
-                                            const float* kg, const float* kb, float* pre = nullptr) {
+                                            const float* kg, const float* kb, float* prew = nullptr) {
     using L = TfLay<PAIR>;
-    float vloc[64];
-    float* v = pre ? pre : vloc;
-    if (!pre) {
-        tmem_ld32(e.taddr + QkvCols<HS, PAIR>::cQK + e.hf * 64, v);
-        tmem_ld32(e.taddr + QkvCols<HS, PAIR>::cQK + e.hf * 64 + 32, v + 32);
-        tmem_ld_wait();
-    }
+    float v[64];
+    tmem_ld32(e.taddr + QkvCols<HS, PAIR>::cQK + e.hf * 64, v);
+    tmem_ld32(e.taddr + QkvCols<HS, PAIR>::cQK + e.hf * 64 + 32, v + 32);
+    if (prew) tmem_ld32(e.taddr + QkvCols<HS, PAIR>::cV + e.hf * 32, prew);   // v leaves TMEM in the same round trip
+    tmem_ld_wait();
     const float* bias = e.hf ? bk : bq;
 #pragma unroll
     for (int i = 0; i < 64; i += 4) {
@@ -530,47 +513,6 @@ __device__ __forceinline__ void fc_epilogue(Epi& e, int q, const float* bias) {
     stage_row_bf16(e.arena + ((q & 1) ? L::oH1 : L::oH0) + e.hf * L::kChunk, e.r, v);
 }
 
-// The two hidden quarters (q0, q0 + 1) of one up-projection half, GELU(acc + bias) -> bf16 H0 | H1, with the four 32-column
-// TMEM loads of the thread software-pipelined over two register buffers (see tmem_pass4).  `bias`: the 512 biases of the
-// layer.  After quarter q0 the down-projection of that quarter is handed to the issuer; before H1 is rewritten (quarter 3)
-// the down-projection of quarter 1 must have read it (done[1], see emit_mlp).
-template <bool PAIR>
-__device__ __forceinline__ void fc_pair_epilogue(Epi& e, int q0, const float* bias) {
-    using L = TfLay<PAIR>;
-    const uint32_t c0 = kScr + e.hf * 64;                 // quarter q0 sits in the scratch half 0, q0 + 1 in half 1
-    const bool ok = row_ok<PAIR>(e.r);
-    auto half_row = [&](int q, int h, float* v) {         // 32 values -> units 4 h .. 4 h + 3 of the row in chunk hf of H(q & 1)
-        const float* bq = bias + q * 128 + e.hf * 64 + h * 32;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            const float4 a = ldf4(bq + i);
-            MMF_SET2(v, i, gelu_tile2(f2add(MMF_V2(v, i), make_float2(a.x, a.y))));
-            MMF_SET2(v, i + 2, gelu_tile2(f2add(MMF_V2(v, i + 2), make_float2(a.z, a.w))));
-        }
-        uint8_t* ch = e.arena + ((q & 1) ? L::oH1 : L::oH0) + e.hf * L::kChunk;
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            st_shared_v4(ch + sw128_offset(e.r, h * 4 + u), pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
-                         pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
-    };
-    float a[32], b[32];
-    tmem_ld32(e.taddr + c0, a);
-    tmem_ld_wait();
-    tmem_ld32(e.taddr + c0 + 32, b);
-    if (ok) half_row(q0, 0, a);
-    tmem_ld_wait();
-    tmem_ld32(e.taddr + c0 + 128, a);
-    if (ok) half_row(q0, 1, b);
-    go(e);                                                // -> down-projection of quarter q0
-    if (q0 + 1 == 3) wait_done(e, 1);
-    tmem_ld_wait();
-    tmem_ld32(e.taddr + c0 + 160, b);
-    if (ok) half_row(q0 + 1, 0, a);
-    tmem_ld_wait();
-    if (ok) half_row(q0 + 1, 1, b);
-    go(e);                                                // -> (next up-projection half and) down-projection of quarter q0 + 1
-}
-
 // head hidden quarter: GELU(acc + bias) dotted with NO output rows of W2 (row stride ld), accumulated into out[]
 template <int NO>
 __device__ __forceinline__ void head_epilogue(Epi& e, int q, const float* bias, const float* w2, int ld, float* out) {
@@ -625,14 +567,12 @@ __device__ __forceinline__ void attention_unit(Epi& e, bool first, bool more, co
     const float scale = 1.4426950408889634f * rsqrtf(static_cast<float>(HS));
     if (!PAIR) wait_done(e, 1);                       // QKV of this unit (issued under the previous unit's epilogue)
     if (!PAIR) {
-        // q | k and v leave TMEM in ONE round trip (a tcgen05.ld + wait::ld costs ~235 cycles whatever its width, and both
-        // warps of a scheduler would sit in it together); v must also be out before the score product, which in the 32-wide
-        // units writes over its columns
-        float qkr[64], vr[32];
-        qkv_tmem_load<HS, false>(e, qkr, vr);
-        qk_epilogue<HS, false>(e, bq, bk, qg, qb, kg, kb, qkr);
+        // 32-wide units: the score product of head 0 writes [256,384), over the v accumulator [320,384): v must be in
+        // registers before the hand-off (until round 2 it was read right after it - a race the timing happened to hide)
+        float vr[32];
+        qk_epilogue<HS, false>(e, bq, bk, qg, qb, kg, kb, HS == 32 ? vr : nullptr);
         go_attn(e);                                       // -> S
-        v_epilogue<HS, false>(e, bv, vr);                 // under the score MMA; P V is only issued after the next hand-off
+        v_epilogue<HS, false>(e, bv, HS == 32 ? vr : nullptr);   // under the score MMA; P V is only issued after the next hand-off
         if (HS == 64) {
             wait_done(e, 0);
             softmax_epilogue<false>(e, kScr, scale, lo, span, 0, more);   // (S in registers -> the QKV GEMM of the next unit)
@@ -1075,9 +1015,13 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 param_acquire(e);                             // MLP stage
                 for (int g = 0; g < 2; ++g) {
                     const float* G = e.P + g * tfp::SM_GROUP;
-                    for (int q = 0; q < 4; q += 2) {
-                        wait_done(e, 0);                      // an up-projection half (two quarters) has landed
-                        fc_pair_epilogue<PAIR>(e, q, G + tfp::SM_BFC);
+                    for (int q = 0; q < 4; ++q) {
+                        // up-projection halves land on done[0]; before H1 is rewritten (q = 3) the down-projection of
+                        // quarter 1 must have read it (done[1]) - see emit_mlp
+                        if (q == 0 || q == 2) wait_done(e, 0);
+                        if (q == 3) wait_done(e, 1);
+                        fc_epilogue<PAIR>(e, q, G + tfp::SM_BFC + q * 128);
+                        go(e);
                     }
                 }
                 wait_done(e, 0);                              // last down-projection of group 1
@@ -1122,9 +1066,11 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 }
                 param_release(e);
                 param_acquire(e);                             // MLP stage
-                for (int q = 0; q < 4; q += 2) {
-                    wait_done(e, 0);                          // an up-projection half (two quarters) has landed
-                    fc_pair_epilogue<PAIR>(e, q, e.P + tfp::BM_BFC);
+                for (int q = 0; q < 4; ++q) {
+                    if (q == 0 || q == 2) wait_done(e, 0);
+                    if (q == 3) wait_done(e, 1);
+                    fc_epilogue<PAIR>(e, q, e.P + tfp::BM_BFC + q * 128);
+                    go(e);
                 }
                 wait_done(e, 0);
                 {
