@@ -452,7 +452,7 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
 
-    cfg = make_config(args.model, num_timesteps=args.timesteps, temperature=args.temperature)
+    cfg = make_config(args.model, num_timesteps=args.timesteps, temperature=args.temperature, batch_size=args.batch)
     sd = synthetic.make_state_dict(cfg, flavor="wide", seed=0)
     epic = args.model == "EPiC"
     bridge = (ConditionalFlowMatching if epic else MultiModalFlowBridge)(cfg)
@@ -508,16 +508,16 @@ def main():
     value = world * B * args.steps / (total_ms * 1e-3)
 
     # ---- end-to-end through the drop-in API with pinned HOST buffers (H2D + D2H inside the timed region) ----
-    def e2e_step():
+    def e2e_step(i):
         batch = DataCoupling(source=src_host, target=TensorMultiModal())
-        out = bridge.predict_step(batch, 0)
+        out = bridge.predict_step(batch, i)              # (batch_idx -> global jet offset, as under Lightning's predict loop)
         return out
-    for _ in range(2):
-        e2e_step()
+    for i in range(2):
+        e2e_step(i)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        out = e2e_step()
+    for i in range(args.steps):
+        out = e2e_step(2 + i)
     torch.cuda.synchronize()
     e2e_t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:

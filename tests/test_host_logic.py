@@ -170,3 +170,26 @@ def test_weight_ring_plan_rejects_oversized_tiles():
     out = np.zeros(3, dtype=np.int32)
     p = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
     assert L.mmf_dbg_ring_plan(p(kb), 3, p(out), p(out.copy())) != 0
+
+
+def test_global_jet_offset_rules(monkeypatch):
+    """ADVICE r1: draws are keyed on the global jet index, so two calls must never share a range.  Single process: a cursor;
+    under a predict loop with a configured batch size: (batch_idx * world + rank) * batch_size; a multi-process run without
+    either information refuses instead of silently re-using draws."""
+    import torch
+    from mmf_b200.mmf import MultiModalFlowBridge
+    from mmf_b200.param_spec import make_config
+    b = MultiModalFlowBridge(make_config("FusedParticleFormer"))
+    assert [b._next_jet_offset(5), b._next_jet_offset(7), b._next_jet_offset(3)] == [0, 5, 12]
+    assert b._next_jet_offset(4, first_global_jet=99) == 99
+    c = MultiModalFlowBridge(make_config("FusedParticleFormer", batch_size=16))
+    assert c._next_jet_offset(16, batch_idx=3) == 48 and c._next_jet_offset(9, batch_idx=4) == 64      # short last batch
+    monkeypatch.setattr(torch.distributed, "is_initialized", lambda: True)
+    monkeypatch.setattr(torch.distributed, "get_rank", lambda: 1)
+    monkeypatch.setattr(torch.distributed, "get_world_size", lambda: 4)
+    assert c._next_jet_offset(16, batch_idx=2) == (2 * 4 + 1) * 16
+    import pytest
+    with pytest.raises(RuntimeError, match="global jet index"):
+        b._next_jet_offset(5)
+    with pytest.raises(RuntimeError, match="global jet index"):
+        c._next_jet_offset(32, batch_idx=0)                  # batch longer than the configured stride
