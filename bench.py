@@ -449,6 +449,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL_DEBUG=VERSION (the default of some launchers) prints "NCCL version ..." on STDOUT, next to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         torch.distributed.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
 

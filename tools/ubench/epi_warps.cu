@@ -1,0 +1,124 @@
+// Micro-benchmark (measurement aid): does the row-per-thread epilogue of the tile kernel run faster with four warps per
+// scheduler (thread = row x column QUARTER, 16 warps) than with two (row x column HALF, 8 warps)?  Three representative
+// phases over a [128 x 256] fp32 tile in TMEM: (0) residual update + LayerNorm statistics (ld, add, stats, st),
+// (1) LayerNorm normalise -> bf16 -> swizzled shared memory, (2) bias + GELU(tanh) -> bf16 -> shared memory.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o epi_warps epi_warps.cu && ./epi_warps
+#include <cstdio>
+#include "../../multimodal-flows_b200/csrc/mmf_ptx.cuh"
+#include "../../multimodal-flows_b200/csrc/mmf_tile.cuh"
+using namespace mmf;
+
+template <int NW>   // epilogue warps: 8 or 16
+__global__ void __launch_bounds__(NW * 32, 1) epi_kernel(int mode, int iters, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t tbase;
+    __shared__ __align__(16) float params[1024];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NC = 256 / (NW / 4);                    // columns per thread: 128 or 64
+    const int r = (warp & 3) * 32 + lane, cq = warp >> 2;
+    if (warp == 0) { tmem_alloc(&tbase, 512); tmem_relinquish(); }
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) params[i] = 0.001f * i;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t taddr = tbase + (static_cast<uint32_t>((warp & 3) * 32) << 16) + cq * NC;
+    {
+        float v[32];
+        for (int i = 0; i < 32; ++i) v[i] = 0.01f * (threadIdx.x + i);
+        for (int c = 0; c < NC; c += 32) tmem_st32(taddr + c, v);
+        tmem_st_wait();
+    }
+    __syncthreads();
+    const long long t0 = clock64();
+    float sink = 0.f;
+    for (int it = 0; it < iters; ++it) {
+        if (mode == 0) {
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < NC; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 a = *reinterpret_cast<const float4*>(params + cq * NC + c0 + 4 * u);
+                    MMF_SET2(v, 4 * u, f2add(MMF_V2(v, 4 * u), make_float2(a.x, a.y)));
+                    MMF_SET2(v, 4 * u + 2, f2add(MMF_V2(v, 4 * u + 2), make_float2(a.z, a.w)));
+                }
+                float2 a01 = f2dup(0.f), q01 = f2dup(0.f);
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) { a01 = f2add(a01, MMF_V2(v, i)); q01 = f2fma(MMF_V2(v, i), MMF_V2(v, i), q01); }
+                s1 += a01.x + a01.y; s2 += q01.x + q01.y;
+                tmem_st32(taddr + c0, v);
+            }
+            tmem_st_wait();
+            sink += s1 * 1e-9f + s2 * 1e-12f;
+        } else if (mode == 1) {
+            const float2 nm = f2dup(-0.5f), rs = f2dup(1.01f);
+#pragma unroll 1
+            for (int c0 = 0; c0 < NC; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 gg = *reinterpret_cast<const float4*>(params + cq * NC + c0 + 4 * u), bb = *reinterpret_cast<const float4*>(params + 512 + cq * NC / 2 + 4 * u);
+                    MMF_SET2(v, 4 * u, f2fma(f2mul(f2add(MMF_V2(v, 4 * u), nm), rs), make_float2(gg.x, gg.y), make_float2(bb.x, bb.y)));
+                    MMF_SET2(v, 4 * u + 2, f2fma(f2mul(f2add(MMF_V2(v, 4 * u + 2), nm), rs), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w)));
+                }
+                const int col0 = cq * NC + c0;
+                uint8_t* ch = smem + (col0 >> 6) * 16384;
+                const uint32_t u0 = (col0 & 63) >> 3;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    st_shared_v4(ch + sw128_offset(r, u0 + u), pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                                 pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+            }
+        } else {
+            // one MLP quarter = 128 columns: 8 warps -> 64 per thread (two loads, one wait); 16 warps -> 32 per thread
+            constexpr int NQ = NC / 2;
+            float v[NQ];
+            const int colq = (cq * NQ) & 127;
+            tmem_ld32(taddr - cq * NC + 256 - 256 + colq, v);
+            if (NQ == 64) tmem_ld32(taddr - cq * NC + colq + 32, v + 32);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < NQ; i += 4) {
+                const float4 a = *reinterpret_cast<const float4*>(params + colq + i);
+                MMF_SET2(v, i, gelu_tanh2(f2add(MMF_V2(v, i), make_float2(a.x, a.y))));
+                MMF_SET2(v, i + 2, gelu_tanh2(f2add(MMF_V2(v, i + 2), make_float2(a.z, a.w))));
+            }
+            uint8_t* ch = smem + (colq >> 6) * 16384;
+            const uint32_t u0 = (colq & 63) >> 3;
+#pragma unroll
+            for (int u = 0; u < NQ / 8; ++u)
+                st_shared_v4(ch + sw128_offset(r, u0 + u), pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                             pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(NW * 32) : "memory");      // the phases of the real kernel end in a barrier
+    }
+    const long long t1 = clock64();
+    __syncthreads();
+    if (threadIdx.x == 0) out[0] = t1 - t0;
+    if (sink == 12345.f) out[1] = 1;
+    if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+int main() {
+    long long* out; cudaMalloc(&out, 16);
+    const int iters = 2000;
+    cudaFuncSetAttribute(epi_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    cudaFuncSetAttribute(epi_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    const char* names[3] = {"resid update + stats (ld/add/stats/st, 256 cols)", "LN normalise -> bf16 smem (256 cols)", "bias + GELU -> bf16 smem (128 cols)"};
+    for (int mode = 0; mode < 3; ++mode) {
+        long long h8, h16;
+        epi_kernel<8><<<1, 256, 65536>>>(mode, iters, out);
+        if (cudaDeviceSynchronize() != cudaSuccess) { printf("fail %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
+        cudaMemcpy(&h8, out, 8, cudaMemcpyDeviceToHost);
+        epi_kernel<16><<<1, 512, 65536>>>(mode, iters, out);
+        if (cudaDeviceSynchronize() != cudaSuccess) { printf("fail %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
+        cudaMemcpy(&h16, out, 8, cudaMemcpyDeviceToHost);
+        printf("%-52s  8 warps %7.0f cycles   16 warps %7.0f cycles   speed-up %.2f\n", names[mode], double(h8) / iters, double(h16) / iters, double(h8) / double(h16));
+    }
+    return 0;
+}
