@@ -600,7 +600,12 @@ def main():
             dms = timed_generate(nm, dsrc.to(dev), ts, dt, cfg, 2, 2, flush, False)
             dn = dsrc.mask.squeeze(-1).sum(1)
             dtf = algorithmic_flops_per_timestep(args.model, dn) * args.timesteps / (dms * 1e-3) / 1e12
-            line["roofline_dense"] = {"bound": "tensor", "kernel": "tf_tile_kernel (pair tiles: one 150-particle jet per 2-CTA cluster)",
+            try:
+                with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                    dtraffic = json.load(f).get("tf_tile_kernel_pair", {}).get("dram_bytes_per_launch")
+            except (OSError, ValueError):
+                dtraffic = None
+            line["roofline_dense"] = {"bound": "tensor", "kernel": "tf_tile_kernel (pair tiles: one 150-particle jet per 2-CTA cluster)", "traffic": dtraffic,
                                       "workload": f"{args.model}, {B} jets of 150 particles x {args.timesteps} timesteps", "value": B / (dms * 1e-3),
                                       "unit_value": "jets/s", "ms_per_step": dms, "achieved": dtf, "peak": peaks["bf16_tflops_sustained"],
                                       "unit": "TFLOP/s", "frac": dtf / peaks["bf16_tflops_sustained"], "steps": 2, "warmup": 2}

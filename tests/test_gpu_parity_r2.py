@@ -329,3 +329,43 @@ def test_two_devices_in_one_process_if_present():
             torch.cuda.synchronize()
         outs.append((x.cpu(), k.cpu()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("name", ["FusedParticleFormer", "EPiC"])
+def test_edge_shapes_single_jet_short_D_and_empty_jets(name):
+    """Shapes the reference itself trips over or never sees: B = 1 (its bare `.squeeze()` breaks), a shorter
+    particle axis (D = 37), a batch whose jets are all empty (nothing to generate: zeros), and one particle in the whole batch."""
+    from mmf_b200 import _abi, synthetic
+    from mmf_b200.param_spec import make_config
+    from oracle import mmf_oracle as orc
+    epic = name == "EPiC"
+    for D, ns in ((150, [77]), (37, [37, 1, 20]), (150, [0, 0, 0]), (150, [0, 1, 0])):
+        cfg = make_config(name, num_timesteps=3, max_num_particles=D)
+        sd = synthetic.make_state_dict(cfg, flavor="wide", seed=1)
+        nm = _abi.NativeModel(cfg, sd, torch.device(DEV))
+        g = torch.Generator().manual_seed(17)
+        n = torch.tensor(ns)
+        B = len(ns)
+        mask = synthetic.prefix_masks(n, D)
+        x0 = torch.randn(B, D, 3, generator=g) * mask
+        k0 = torch.randint(1, 9, (B, D, 1), generator=g) * mask
+        ts, dt = orc.time_grid(cfg)
+        real = mask.bool().squeeze(-1)
+        if epic:
+            x, _, _ = nm.generate(x0.to(DEV), None, mask.to(DEV), ts, float(dt), None)
+        else:
+            u = synthetic.uniform_draws(3, B, D, 9, seed=18)
+            x, k, _ = nm.generate(x0.to(DEV), k0.to(DEV), mask.to(DEV), ts, float(dt), _abi.step_options(cfg), u=u.to(DEV))
+            assert (k.cpu()[~real] == 0).all()
+        torch.cuda.synchronize()
+        assert torch.isfinite(x).all() and (x.cpu()[~real] == 0).all()
+        if int(n.sum()) == 0:
+            assert (x == 0).all()
+            continue
+        keep = n > 0                                            # (EPiC's masked mean divides by zero for an empty jet in the reference)
+        if epic:
+            xo = orc.simulate_dynamics_cfm(sd, cfg, x0[keep], mask[keep])
+        else:
+            xo, ko, _ = orc.simulate_dynamics(sd, cfg, x0[keep], k0[keep], mask[keep], u=u[:, keep])
+            assert (k.cpu()[keep][real[keep]] == ko.squeeze(-1)[real[keep]]).float().mean() > 0.9
+        assert _rel(x.cpu()[keep], xo, real[keep]) < 2e-2, (name, D, ns)

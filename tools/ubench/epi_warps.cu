@@ -74,8 +74,84 @@ __global__ void __launch_bounds__(NW * 32, 1) epi_kernel(int mode, int iters, lo
                     st_shared_v4(ch + sw128_offset(r, u0 + u), pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
                                  pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
             }
+        } else if (mode == 3) {
+            // mode 1 with the TMEM loads software-pipelined over two register buffers (load of chunk c + 1 in flight during chunk c)
+            const float2 nm = f2dup(-0.5f), rs = f2dup(1.01f);
+            auto body = [&](int c0, float* v) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 gg = *reinterpret_cast<const float4*>(params + cq * NC + c0 + 4 * u), bb = *reinterpret_cast<const float4*>(params + 512 + cq * NC / 2 + 4 * u);
+                    MMF_SET2(v, 4 * u, f2fma(f2mul(f2add(MMF_V2(v, 4 * u), nm), rs), make_float2(gg.x, gg.y), make_float2(bb.x, bb.y)));
+                    MMF_SET2(v, 4 * u + 2, f2fma(f2mul(f2add(MMF_V2(v, 4 * u + 2), nm), rs), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w)));
+                }
+                const int col0 = cq * NC + c0;
+                uint8_t* ch = smem + (col0 >> 6) * 16384;
+                const uint32_t u0 = (col0 & 63) >> 3;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    st_shared_v4(ch + sw128_offset(r, u0 + u), pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                                 pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+            };
+            float a[32], b[32];
+            tmem_ld32(taddr, a);
+            tmem_ld_wait();
+            if (NC == 128) {
+                tmem_ld32(taddr + 32, b); body(0, a); tmem_ld_wait();
+                tmem_ld32(taddr + 64, a); body(32, b); tmem_ld_wait();
+                tmem_ld32(taddr + 96, b); body(64, a); tmem_ld_wait();
+                body(96, b);
+            } else {
+                tmem_ld32(taddr + 32, b); body(0, a); tmem_ld_wait();
+                body(32, b);
+            }
+        } else if (mode == 4) {
+            // mode 1 with ALL the thread's columns loaded up front (NC registers), one wait
+            const float2 nm = f2dup(-0.5f), rs = f2dup(1.01f);
+            float v[NC];
+#pragma unroll
+            for (int c0 = 0; c0 < NC; c0 += 32) tmem_ld32(taddr + c0, v + c0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c0 = 0; c0 < NC; c0 += 32) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 gg = *reinterpret_cast<const float4*>(params + cq * NC + c0 + 4 * u), bb = *reinterpret_cast<const float4*>(params + 512 + cq * NC / 2 + 4 * u);
+                    MMF_SET2(v, c0 + 4 * u, f2fma(f2mul(f2add(MMF_V2(v, c0 + 4 * u), nm), rs), make_float2(gg.x, gg.y), make_float2(bb.x, bb.y)));
+                    MMF_SET2(v, c0 + 4 * u + 2, f2fma(f2mul(f2add(MMF_V2(v, c0 + 4 * u + 2), nm), rs), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w)));
+                }
+                const int col0 = cq * NC + c0;
+                uint8_t* ch = smem + (col0 >> 6) * 16384;
+                const uint32_t u0 = (col0 & 63) >> 3;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    st_shared_v4(ch + sw128_offset(r, u0 + u), pack_bf16x2(v[c0 + 8 * u], v[c0 + 8 * u + 1]), pack_bf16x2(v[c0 + 8 * u + 2], v[c0 + 8 * u + 3]),
+                                 pack_bf16x2(v[c0 + 8 * u + 4], v[c0 + 8 * u + 5]), pack_bf16x2(v[c0 + 8 * u + 6], v[c0 + 8 * u + 7]));
+            }
+        } else if (mode == 5) {
+            // compute only (no TMEM traffic): the arithmetic + shared-memory stores of mode 1 on register data
+            const float2 nm = f2dup(-0.5f), rs = f2dup(1.01f);
+#pragma unroll 1
+            for (int c0 = 0; c0 < NC; c0 += 32) {
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = sink + i;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 gg = *reinterpret_cast<const float4*>(params + cq * NC + c0 + 4 * u), bb = *reinterpret_cast<const float4*>(params + 512 + cq * NC / 2 + 4 * u);
+                    MMF_SET2(v, 4 * u, f2fma(f2mul(f2add(MMF_V2(v, 4 * u), nm), rs), make_float2(gg.x, gg.y), make_float2(bb.x, bb.y)));
+                    MMF_SET2(v, 4 * u + 2, f2fma(f2mul(f2add(MMF_V2(v, 4 * u + 2), nm), rs), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w)));
+                }
+                const int col0 = cq * NC + c0;
+                uint8_t* ch = smem + (col0 >> 6) * 16384;
+                const uint32_t u0 = (col0 & 63) >> 3;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    st_shared_v4(ch + sw128_offset(r, u0 + u), pack_bf16x2(v[8 * u], v[8 * u + 1]), pack_bf16x2(v[8 * u + 2], v[8 * u + 3]),
+                                 pack_bf16x2(v[8 * u + 4], v[8 * u + 5]), pack_bf16x2(v[8 * u + 6], v[8 * u + 7]));
+                sink += v[3] * 1e-20f;
+            }
         } else {
-            // one MLP quarter = 128 columns: 8 warps -> 64 per thread (two loads, one wait); 16 warps -> 32 per thread
+            // (mode 2) one MLP quarter = 128 columns: 8 warps -> 64 per thread (two loads, one wait); 16 warps -> 32 per thread
             constexpr int NQ = NC / 2;
             float v[NQ];
             const int colq = (cq * NQ) & 127;
@@ -109,8 +185,9 @@ int main() {
     const int iters = 2000;
     cudaFuncSetAttribute(epi_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     cudaFuncSetAttribute(epi_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-    const char* names[3] = {"resid update + stats (ld/add/stats/st, 256 cols)", "LN normalise -> bf16 smem (256 cols)", "bias + GELU -> bf16 smem (128 cols)"};
-    for (int mode = 0; mode < 3; ++mode) {
+    const char* names[6] = {"resid update + stats (ld/add/stats/st, 256 cols)", "LN normalise -> bf16 smem (256 cols)", "bias + GELU -> bf16 smem (128 cols)",
+                            "LN normalise, TMEM loads double-buffered", "LN normalise, all columns loaded up front", "LN normalise, arithmetic + stores only"};
+    for (int mode : {0, 1, 3, 4, 5, 2}) {
         long long h8, h16;
         epi_kernel<8><<<1, 256, 65536>>>(mode, iters, out);
         if (cudaDeviceSynchronize() != cudaSuccess) { printf("fail %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
