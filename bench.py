@@ -449,9 +449,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL_DEBUG=VERSION (the default of some launchers) prints "NCCL version ..." on STDOUT, next to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # with NCCL_DEBUG set (VERSION and up) NCCL writes "NCCL version ..." to STDOUT, next to the one JSON line: keep
+        # whatever level the operator asked for, but send it to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.distributed.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
 
