@@ -609,6 +609,16 @@ def main():
                                       "workload": f"{args.model}, {B} jets of 150 particles x {args.timesteps} timesteps", "value": B / (dms * 1e-3),
                                       "unit_value": "jets/s", "ms_per_step": dms, "achieved": dtf, "peak": peaks["bf16_tflops_sustained"],
                                       "unit": "TFLOP/s", "frac": dtf / peaks["bf16_tflops_sustained"], "steps": 2, "warmup": 2}
+            # the same kernel with every SM busy (4096 jets = 1760 tiles = 11.9 waves of 148): what the design sustains per SM when
+            # the batch does not leave a quarter of the chip without a tile (256 jets = 110 tiles)
+            fsrc = synthetic.source_state(4096, cfg.max_num_particles, cfg.vocab_size, seed=1234)
+            fms = timed_generate(nm, fsrc.to(dev), ts, dt, cfg, 2, 1, flush, False)
+            ftf = algorithmic_flops_per_timestep(args.model, fsrc.mask.squeeze(-1).sum(1)) * args.timesteps / (fms * 1e-3) / 1e12
+            line["roofline_full_chip"] = {"bound": "tensor", "kernel": "tf_tile_kernel", "workload": f"{args.model}, 4096 AOJ-shaped jets x {args.timesteps} timesteps",
+                                          "value": 4096 / (fms * 1e-3), "unit_value": "jets/s", "ms_per_step": fms, "achieved": ftf,
+                                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ftf / peaks["bf16_tflops_sustained"],
+                                          "steps": 2, "warmup": 1}
+            del fsrc
         line["extra_models"] = extra_model_lines(args, peaks, dev, flush, rank)
     if not args.no_step_roofline and not epic:
         line["roofline_step_kernel"] = step_kernel_roofline(peaks, dev)
