@@ -253,3 +253,33 @@ def test_dense_batch_of_150_particle_jets_matches_oracle():
     assert nm.launches <= 2
     assert _rel(xg.cpu(), xo, real) < 2e-2
     assert (kg.cpu()[real] == ko.squeeze(-1)[real]).float().mean() > 0.96
+
+
+def test_other_vocabulary_runs_on_the_layered_kernels():
+    """Outside the tile kernels' envelope (vocab_size != 9) the model still runs natively - on the layered tcgen05 kernels, one
+    launch per layer - and matches the oracle: forward with per-jet times and a 3-step sampler, incl. a 140-particle jet."""
+    from mmf_b200 import _abi, synthetic
+    from oracle import mmf_oracle as orc
+    cfg, sd, nm = _model("FusedParticleFormer", num_timesteps=3, vocab_size=8)
+    g = torch.Generator().manual_seed(61)
+    n = torch.tensor([140, 12, 64, 128, 1, 77])
+    B = len(n)
+    mask = synthetic.prefix_masks(n, 150)
+    x0 = torch.randn(B, 150, 3, generator=g) * mask
+    k0 = torch.randint(1, 8, (B, 150, 1), generator=g) * mask
+    t = torch.rand(B, generator=g)
+    real = mask.bool().squeeze(-1)
+    l0 = nm.launches
+    va, la = nm.forward(x0.to(DEV), k0.to(DEV), mask.to(DEV), t.to(DEV))
+    torch.cuda.synchronize()
+    assert nm.launches - l0 > 20 and la.shape[-1] == 8          # one launch per layer (the tile path takes 2)
+    vr, lr = orc.encoder_forward(sd, cfg, t, x0, k0, mask)
+    assert _rel(va.cpu(), vr, real) < 2e-2 and _rel(la.cpu(), lr, real) < 2e-2
+    u = synthetic.uniform_draws(3, B, 150, 8, seed=62)
+    xo, ko, _ = orc.simulate_dynamics(sd, cfg, x0, k0, mask, u=u)
+    ts, dt = orc.time_grid(cfg)
+    xg, kg, _ = nm.generate(x0.to(DEV), k0.to(DEV), mask.to(DEV), ts, float(dt), _abi.step_options(cfg), u=u.to(DEV))
+    torch.cuda.synchronize()
+    assert _rel(xg.cpu(), xo, real) < 2e-2
+    assert (kg.cpu()[real] == ko.squeeze(-1)[real]).float().mean() > 0.96
+    assert int(kg.max()) < 8
