@@ -155,6 +155,11 @@ int mmf_multitask_loss(const float* vt, const float* logits, const float* x0, co
                        const float* t, int32_t B, int32_t D, int32_t V, int32_t mode, int32_t n_embd, const float* w_fc, const float* b_fc,
                        const float* w_proj, const float* b_proj, float* per_jet, float* out5, int32_t device, void* stream);
 
+/* EMA of the weights: what timm's ModelEmaV2.update does for every state_dict entry when the reference's
+ * EMACallback.on_train_batch_end fires (utils/callbacks.py:152-226):  ema <- decay * ema + (1 - decay) * p  on n fp32 values
+ * (device pointers), every operation rounded on its own like the torch expression, so the result is bit-identical. */
+int mmf_ema_update(float* ema, const float* p, double decay, int64_t n, int32_t device, void* stream);
+
 /* The generated sample as one narrow record per jet - the device-side half of FlowGeneratorCallback:
  *   utils/callbacks.py:52-56   sample.continuous = sample.continuous * std + mean     (mean, std: HOST float[3], NULL = identity)
  *   utils/callbacks.py:57      sample.apply_mask()                                    (padded slots zeroed)

@@ -160,7 +160,23 @@ __global__ void __launch_bounds__(256) loss_combine_kernel(const float* __restri
     }
 }
 
+// EMA of the weights as timm's ModelEmaV2.update does it for every state_dict entry (reference utils/callbacks.py:152-226,
+// on_train_batch_end): ema <- decay * ema + (1 - decay) * p, each operation rounded on its own like the torch expression
+__global__ void ema_update_kernel(float* __restrict__ ema, const float* __restrict__ p, float decay, float one_minus, long long n) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) ema[i] = det_add(det_mul(decay, ema[i]), det_mul(one_minus, p[i]));
+}
+
 }  // namespace
+
+int launch_ema_update(float* ema, const float* p, float decay, long long n, cudaStream_t s) {
+    if (n == 0) return 0;
+    // (1. - decay) is evaluated in double by Python and rounded to fp32 when it multiplies the tensor
+    const float one_minus = static_cast<float>(1.0 - static_cast<double>(decay));
+    ema_update_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(ema, p, decay, one_minus, n);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 
 int launch_bridge_sample(const float* x0, const float* x1, const long long* k0, const long long* k1, const float* t, float sigma,
                          float beta, int V, const float* z, const float* u, unsigned long long seed, unsigned long long slot0,

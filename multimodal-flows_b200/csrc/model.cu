@@ -878,6 +878,14 @@ int mmf_multitask_loss(const float* vt, const float* logits, const float* x0, co
     return launch_loss_combine(t, per_jet, per_jet + B, w_fc, b_fc, w_proj, b_proj, n_embd, mode, B, out5, s);
 }
 
+int mmf_ema_update(float* ema, const float* p, double decay, int64_t n, int32_t device, void* stream) {
+    MMF_REQUIRE(n >= 0 && decay >= 0.0 && decay <= 1.0, "bad arguments");
+    if (n == 0) return 0;
+    MMF_REQUIRE(ema && p, "null argument");
+    MMF_CUDA_OK(cudaSetDevice(device));
+    return launch_ema_update(ema, p, static_cast<float>(decay), n, static_cast<cudaStream_t>(stream));
+}
+
 int64_t mmf_sample_record_bytes(int32_t D) { return D >= 1 ? sample_record_bytes(D) : 0; }
 
 int mmf_pack_sample(const float* x, const int64_t* k, const int64_t* mask, const float* mean, const float* std_, int64_t B,

@@ -47,7 +47,7 @@ EXPORTS = [
     "mmf_abi_version", "mmf_last_error", "mmf_model_create", "mmf_model_destroy", "mmf_encoder_forward",
     "mmf_hybrid_step", "mmf_hybrid_step_status", "mmf_euler_step", "mmf_generate", "mmf_generate_n", "mmf_model_status",
     "mmf_generate_host", "mmf_launch_count", "mmf_jet_observables", "mmf_make_source",
-    "mmf_sample_record_bytes", "mmf_pack_sample", "mmf_unpack_sample", "mmf_bridge_sample", "mmf_multitask_loss",
+    "mmf_sample_record_bytes", "mmf_pack_sample", "mmf_unpack_sample", "mmf_bridge_sample", "mmf_multitask_loss", "mmf_ema_update",
     "mmf_dbg_gemm", "mmf_dbg_gemm_resln", "mmf_dbg_gemm_qkv", "mmf_dbg_attention", "mmf_dbg_ring_plan",
     "mmf_profile_enable", "mmf_profile_num_classes", "mmf_profile_class_name", "mmf_profile_read",
 ]
@@ -88,6 +88,7 @@ def lib() -> ctypes.CDLL:
                                     c_uint64, c_uint64, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p]
     L.mmf_multitask_loss.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                      c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
+    L.mmf_ema_update.argtypes = [c_void_p, c_void_p, ctypes.c_double, c_int64, c_int32, c_void_p]
     L.mmf_generate_n.argtypes = L.mmf_generate.argtypes
     L.mmf_model_status.argtypes = [c_void_p, c_void_p]
     L.mmf_hybrid_step_status.argtypes = [c_int32, c_void_p]
@@ -406,6 +407,14 @@ def multitask_loss(vt, logits, x0, x1, k1, mask, t, mode, n_embd=256, net=None):
     check(lib().mmf_multitask_loss(ptr(vt), ptr(logits), ptr(x0), ptr(x1), ptr(k1), ptr(mask), ptr(t), B, D, V, m, int(n_embd),
                                    ptr(ws[0]), ptr(ws[1]), ptr(ws[2]), ptr(ws[3]), ptr(per_jet), ptr(out), idx, stream_handle(x0.device)))
     return out, per_jet
+
+
+def ema_update(ema: torch.Tensor, p: torch.Tensor, decay: float) -> None:
+    """ema <- decay * ema + (1 - decay) * p in place (fp32, device), timm ModelEmaV2.update for one tensor."""
+    assert ema.is_cuda and ema.dtype == torch.float32 and ema.is_contiguous() and p.shape == ema.shape
+    p = p.detach().to(ema.device, torch.float32).contiguous()
+    idx = ema.device.index if ema.device.index is not None else torch.cuda.current_device()
+    check(lib().mmf_ema_update(ptr(ema), ptr(p), float(decay), ema.numel(), idx, stream_handle(ema.device)))
 
 
 def euler_step(vt, x, dt):
