@@ -169,11 +169,11 @@ __global__ void ema_update_kernel(float* __restrict__ ema, const float* __restri
 
 }  // namespace
 
-int launch_ema_update(float* ema, const float* p, float decay, long long n, cudaStream_t s) {
+int launch_ema_update(float* ema, const float* p, double decay, long long n, cudaStream_t s) {
     if (n == 0) return 0;
-    // (1. - decay) is evaluated in double by Python and rounded to fp32 when it multiplies the tensor
-    const float one_minus = static_cast<float>(1.0 - static_cast<double>(decay));
-    ema_update_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(ema, p, decay, one_minus, n);
+    // decay and (1. - decay) are Python doubles in the reference, each rounded to fp32 when it multiplies an fp32 tensor
+    const float one_minus = static_cast<float>(1.0 - decay);
+    ema_update_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(ema, p, static_cast<float>(decay), one_minus, n);
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -67,7 +67,7 @@ int launch_bridge_sample(const float* x0, const float* x1, const long long* k0, 
                          long long B, int D, float* xt, long long* kt, int* err, cudaStream_t s);
 int launch_multitask_loss(const float* vt, const float* logits, const float* x0, const float* x1, const long long* k1,
                           const long long* mask, int B, int D, int V, float* loss_mse, float* loss_ce, cudaStream_t s);
-int launch_ema_update(float* ema, const float* p, float decay, long long n, cudaStream_t s);
+int launch_ema_update(float* ema, const float* p, double decay, long long n, cudaStream_t s);
 int launch_loss_combine(const float* t, const float* loss_mse, const float* loss_ce, const float* w_fc, const float* b_fc,
                         const float* w_pr, const float* b_pr, int E, int mode, int B, float* out5, cudaStream_t s);
 int launch_force_tokens(const unsigned char* forced, const int* row_slot, int rows, int* ks, cudaStream_t stream);

@@ -883,7 +883,7 @@ int mmf_ema_update(float* ema, const float* p, double decay, int64_t n, int32_t 
     if (n == 0) return 0;
     MMF_REQUIRE(ema && p, "null argument");
     MMF_CUDA_OK(cudaSetDevice(device));
-    return launch_ema_update(ema, p, static_cast<float>(decay), n, static_cast<cudaStream_t>(stream));
+    return launch_ema_update(ema, p, decay, n, static_cast<cudaStream_t>(stream));
 }
 
 int64_t mmf_sample_record_bytes(int32_t D) { return D >= 1 ? sample_record_bytes(D) : 0; }
