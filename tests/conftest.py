@@ -26,3 +26,13 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(autouse=True)
+def _sync_device_after_each_gpu_test(request):
+    """Asynchronous kernel failures must be charged to the test that launched them, not to whichever test touches the device next."""
+    yield
+    if "gpu" in request.keywords:
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
