@@ -1,0 +1,193 @@
+// The tensor-core GEMM of the training step: one tcgen05 kernel serves the forward linears, the
+// data gradients and the weight gradients of every nn.Linear on the encoder path (reference networks/attention.py:44-45,
+// utils/models.py:15-17, networks/ParticleTransformers.py:28-53 under autograd).
+//
+//   C[M x N] (+)= A[M x K] * B[N x K]^T (+ bias[N])      A, B bf16 with K contiguous, fp32 accumulation in TMEM
+//
+//     forward      y  = x  W^T + b      A = x  [tokens, in]     B = W    [out, in]
+//     data grad    dx = dy W            A = dy [tokens, out]    B = W^T  [in, out]     (bf16 transposed copy of the weight)
+//     weight grad  dW = dy^T x          A = dy^T [out, tokens]  B = x^T  [in, tokens]  (K = tokens, split over blockIdx.z, the
+//                                                                                       partial tiles meet in a TMA reduce-add)
+//
+// One CTA = one 128 x 128 output tile: a TMA producer thread and an MMA issuer thread run a 4-stage ring of 128-byte-swizzled
+// [128 x 64] operand boxes; four epilogue warps move the accumulator TMEM -> registers -> swizzled shared memory and one thread
+// stores (or reduce-adds) the tile with TMA.  Tensor maps carry the exact extents, so ragged M / N / K edges are zero-filled on
+// load and clipped on store - no padding rules for the callers.
+#include "mmf_internal.h"
+#include "mmf_ptx.cuh"
+#include "mmf_tile.cuh"
+#include "mmf_train.h"
+
+namespace mmf {
+namespace {
+
+constexpr int kTrStages = 4;
+constexpr int kTrBox = kTileM * 128;             // one operand box: 128 rows x 128 B
+constexpr int kTrStage = 2 * kTrBox;             // A + B
+constexpr int kTrSmem = 1024 + kTrStages * kTrStage + 1024;
+
+struct TrGemmBars {
+    uint64_t full[kTrStages], empty[kTrStages], acc_full;
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(192, 1)
+tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const int N, const int kb_total,
+               const int kb_per_split) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    TrGemmBars* bars = reinterpret_cast<TrGemmBars*>(smem);
+    uint8_t* tiles = smem + 1024;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kTileM, n0 = blockIdx.y * 128;
+    const int kb0 = blockIdx.z * kb_per_split;
+    const int nkb = min(kb_per_split, kb_total - kb0);
+
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+    }
+    if (warp == 5) {
+        if (lane == 0) {
+            for (int i = 0; i < kTrStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+            mbar_init(&bars->acc_full, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(&bars->tmem_base, 128);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % kTrStages, it = i / kTrStages;
+                if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
+                mbar_expect_tx(&bars->full[s], kTrStage);
+                tma_load_2d(tiles + s * kTrStage, &tmA, &bars->full[s], (kb0 + i) * kBK, m0);
+                tma_load_2d(tiles + s * kTrStage + kTrBox, &tmB, &bars->full[s], (kb0 + i) * kBK, n0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kTileM, 128);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % kTrStages, it = i / kTrStages;
+                mbar_wait(&bars->full[s], it & 1);
+                tc_fence_after();
+                const uint64_t da = umma_desc_sw128(smem_u32(tiles + s * kTrStage));
+                const uint64_t db = umma_desc_sw128(smem_u32(tiles + s * kTrStage + kTrBox));
+#pragma unroll
+                for (int ks = 0; ks < kBK / 16; ++ks) umma_bf16(tmem_base, da + 2 * ks, db + 2 * ks, idesc, (i | ks) != 0 ? 1u : 0u);
+                umma_commit(&bars->empty[s]);
+            }
+            umma_commit(&bars->acc_full);
+        }
+        __syncwarp();
+    } else {
+        // epilogue: thread = accumulator row; the whole 128 x 128 tile is staged in the (now idle) operand ring
+        const int r = warp * 32 + lane;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+        const bool add_bias = bias != nullptr && (MODE != 2 || blockIdx.z == 0);
+        mbar_wait(&bars->acc_full, 0);
+        tc_fence_after();
+        if constexpr (MODE == 0) {
+            for (int cc = 0; cc < 2; ++cc) {
+                float v[64];
+                tmem_ld32(taddr + cc * 64, v);
+                tmem_ld32(taddr + cc * 64 + 32, v + 32);
+                tmem_ld_wait();
+                if (add_bias) {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) { const int col = n0 + cc * 64 + i; v[i] += col < N ? __ldg(bias + col) : 0.f; }
+                }
+                stage_row_bf16(tiles + cc * kTrBox, r, v);
+            }
+        } else {
+            for (int c = 0; c < 4; ++c) {
+                float v[32];
+                tmem_ld32(taddr + c * 32, v);
+                tmem_ld_wait();
+                if (add_bias) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { const int col = n0 + c * 32 + i; v[i] += col < N ? __ldg(bias + col) : 0.f; }
+                }
+                stage_row_f32(tiles + c * kTrBox, r, v);
+            }
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 128);
+        if (threadIdx.x == 0) {
+            if constexpr (MODE == 0) {
+                for (int cc = 0; cc < 2; ++cc) tma_store_2d(&tmC, tiles + cc * kTrBox, n0 + cc * 64, m0);
+            } else if constexpr (MODE == 1) {
+                for (int c = 0; c < 4; ++c) tma_store_2d(&tmC, tiles + c * kTrBox, n0 + c * 32, m0);
+            } else {
+                for (int c = 0; c < 4; ++c) tma_reduce_add_2d(&tmC, tiles + c * kTrBox, n0 + c * 32, m0);
+            }
+            tma_store_commit();
+            tma_store_wait_all();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, 128);
+}
+
+template <int MODE>
+int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const float* bias, int N, int kb_total,
+                int kb_per_split, dim3 grid, cudaStream_t s) {
+    static bool configured[64] = {false};                 // the attribute is per device
+    int dev = 0;
+    MMF_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        MMF_CUDA_OK(cudaFuncSetAttribute(tr_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrSmem));
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    tr_gemm_kernel<MODE><<<grid, 192, kTrSmem, s>>>(tmA, tmB, tmC, bias, N, kb_total, kb_per_split);
+    MMF_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int launch_tr_gemm(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N, int K,
+                   const float* bias, int mode, int ksplit, cudaStream_t s) {
+    MMF_REQUIRE(A && B && C, "gemm: null operand");
+    MMF_REQUIRE(mode >= 0 && mode <= 2, "gemm: mode is 0 (bf16 store), 1 (fp32 store) or 2 (fp32 reduce-add)");
+    if (M <= 0 || N <= 0) return 0;
+    MMF_REQUIRE(K > 0, "gemm: K must be positive");
+    const int kb_total = (K + kBK - 1) / kBK;
+    if (ksplit < 1 || mode != 2) ksplit = 1;
+    if (ksplit > kb_total) ksplit = kb_total;
+    const int per = (kb_total + ksplit - 1) / ksplit;
+    ksplit = (kb_total + per - 1) / per;                  // no empty split
+    CUtensorMap tmA, tmB, tmC;
+    if (make_tmap_2d(&tmA, A, 2, M, K, lda, 64, 128)) return 1;
+    if (make_tmap_2d(&tmB, B, 2, N, K, ldb, 64, 128)) return 1;
+    if (mode == 0) { if (make_tmap_2d(&tmC, C, 2, M, N, ldc, 64, 128)) return 1; }
+    else { if (make_tmap_2d(&tmC, C, 4, M, N, ldc, 32, 128)) return 1; }
+    const dim3 grid((M + kTileM - 1) / kTileM, (N + 127) / 128, ksplit);
+    switch (mode) {
+        case 0: return launch_mode<0>(tmA, tmB, tmC, bias, N, kb_total, per, grid, s);
+        case 1: return launch_mode<1>(tmA, tmB, tmC, bias, N, kb_total, per, grid, s);
+        default: return launch_mode<2>(tmA, tmB, tmC, bias, N, kb_total, per, grid, s);
+    }
+}
+
+}  // namespace mmf

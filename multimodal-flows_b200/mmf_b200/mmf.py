@@ -9,10 +9,12 @@ SURVEY.md section 9).  Lightning is optional: when ``pytorch_lightning`` is impo
 derive from ``LightningModule`` so ``Trainer.predict`` drives them unchanged; otherwise they are
 plain ``nn.Module`` objects and ``load_from_checkpoint`` reads the ``.ckpt`` with ``torch.load``.
 
-Training: ``MultiModalFlowBridge.loss`` / ``training_step`` / ``validation_step`` run the FORWARD half of the reference's
-training step (bridge sampling, encoder forward, masked MSE + CE, MultiTaskLoss) through the library
-(``mmf_bridge_sample``, ``mmf_encoder_forward``, ``mmf_multitask_loss``) with parity against ``MultiModalFlowBridge.loss``;
-the encoder has no backward kernels yet, so the returned loss carries no gradient (in progress).
+Training: ``MultiModalFlowBridge.loss`` / ``validation_step`` run the forward half of the reference's training step
+(bridge sampling, encoder forward, masked MSE + CE, MultiTaskLoss) through the library (``mmf_bridge_sample``,
+``mmf_encoder_forward``, ``mmf_multitask_loss``).  After ``configure_training()`` ``training_step`` runs the whole step on
+the device - forward, backward, DDP gradient average, norm clipping, Adam - through ``mmf_b200.training.TrainEngine``
+(``include/mmf_b200_train.h``); there is no torch autograd on the path, so under Lightning the module declares
+``automatic_optimization = False``.
 """
 from __future__ import annotations
 
@@ -185,8 +187,22 @@ class MultiModalFlowBridge(_GenerativeBase):
         if value is not None and _Base is not nn.Module:      # pragma: no cover - Lightning only
             self.log(name, value, **kw)
 
-    def training_step(self, batch: DataCoupling, batch_idx: int = 0):
-        loss, loss_mse, loss_ce, w_mse, w_ce = self.loss(batch)
+    def configure_training(self, lr: Optional[float] = None, max_norm: float = 1.0):
+        """Creates the device training engine (reference configure_optimizers model/MMF.py:77-78: Adam(lr=config.lr); Trainer
+        gradient_clip_val=1.0 scripts/train_mmf.py:166).  From here on the parameters live in the engine's flat buffers."""
+        from .training import TrainEngine
+        self.automatic_optimization = False                 # Lightning: the step owns backward and the optimiser
+        self._engine = TrainEngine(self, lr=lr, max_norm=max_norm)
+        return self._engine
+
+    def training_step(self, batch: DataCoupling, batch_idx: int = 0, lr: Optional[float] = None):
+        engine = getattr(self, "_engine", None)
+        if engine is not None:
+            out = engine.train_step(batch, lr=lr)
+            weighted = self.config.multitask_loss != "sum"
+            loss, loss_mse, loss_ce, w_mse, w_ce = out[0], out[1], out[2], out[3] if weighted else None, out[4] if weighted else None
+        else:
+            loss, loss_mse, loss_ce, w_mse, w_ce = self.loss(batch)
         for name, v in (("train_loss", loss), ("train_loss_ce", loss_ce), ("train_loss_mse", loss_mse), ("train_weight_mse", w_mse),
                         ("train_weight_ce", w_ce)):
             self._log(name, v, on_epoch=True, sync_dist=True, batch_size=len(batch))
