@@ -317,8 +317,8 @@ def hybrid_euler_step(vt, logits, x, k, t, dt, u, *, beta=0.075, vocab_size=9, t
 def telegraph_conditional_probability(t_in, t_out, k_in, k_out, beta: float, vocab_size: int) -> torch.Tensor:
     """p(k_in -> k_out; t_in, t_out) = 1/V + w (delta - 1/V), w = exp(-V beta (t_out - t_in))
     (reference ``model/MJB.py:231-253`` with the constant thermostat); t_* are (B,) tensors or floats, k_* (B,D,*)."""
-    t_in = torch.as_tensor(t_in, dtype=torch.float32)
-    t_out = torch.as_tensor(t_out, dtype=torch.float32)
+    t_in = torch.as_tensor(t_in, dtype=torch.float32, device=k_out.device)
+    t_out = torch.as_tensor(t_out, dtype=torch.float32, device=k_out.device)
     B = k_out.shape[0]
     t_in = t_in.expand(B) if t_in.dim() == 0 else t_in
     t_out = t_out.expand(B) if t_out.dim() == 0 else t_out
@@ -334,7 +334,7 @@ def bridge_sample(x0, x1, k0, k1, t, z, u, *, sigma: float, beta: float, vocab_s
     tt = t[:, None, None]
     xt = tt * x1 + (1.0 - tt) * x0
     xt = xt + sigma * z
-    k = torch.arange(vocab_size).view(1, 1, -1).expand(k0.shape[0], k0.shape[1], -1).float()
+    k = torch.arange(vocab_size, device=k0.device).view(1, 1, -1).expand(k0.shape[0], k0.shape[1], -1).float()
     p = (telegraph_conditional_probability(t, 1.0, k, k1, beta, vocab_size)
          * telegraph_conditional_probability(0.0, t, k0, k, beta, vocab_size)
          / telegraph_conditional_probability(0.0, 1.0, k0, k1, beta, vocab_size))
