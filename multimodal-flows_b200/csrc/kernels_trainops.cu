@@ -949,9 +949,9 @@ int launch_tr_qkln_bwd(bf16* dqkv, long long ldd, const bf16* qkv, long long ld,
 static int attn_smem_bytes(int hs, int n, int n_operands, bool with_delta) {
     return n_operands * n * (hs / 2 + 1) * 4 + n * (n + 1) * 4 + (with_delta ? n * 4 : 0);
 }
-template <typename K>
+template <int TAG, typename K>                            // TAG: one static table per kernel instantiation (the function TYPES coincide)
 static int attn_configure(K kernel, int bytes) {
-    static int configured[64] = {0};                       // per kernel instantiation and device: largest size opted in so far
+    static int configured[64] = {0};                       // per device: largest size opted in so far
     int dev = 0;
     MMF_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || configured[dev] < bytes) {
@@ -969,10 +969,10 @@ int launch_tr_attn_fwd(const bf16* qn, long long ldq, const bf16* kn, long long 
     const int bytes = attn_smem_bytes(hs, nmax, 3, false);
     const float scale = 1.0f / sqrtf(static_cast<float>(hs));
     if (hs == 32) {
-        if (attn_configure(tr_attn_fwd_kernel<32>, bytes)) return 1;
+        if (attn_configure<0>(tr_attn_fwd_kernel<32>, bytes)) return 1;
         tr_attn_fwd_kernel<32><<<dim3(B, H), 256, bytes, s>>>(qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, o, ldo, P);
     } else {
-        if (attn_configure(tr_attn_fwd_kernel<64>, bytes)) return 1;
+        if (attn_configure<1>(tr_attn_fwd_kernel<64>, bytes)) return 1;
         tr_attn_fwd_kernel<64><<<dim3(B, H), 256, bytes, s>>>(qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, o, ldo, P);
     }
     MMF_CUDA_OK(cudaGetLastError());
@@ -988,10 +988,10 @@ int launch_tr_attn_bwd(const bf16* dO, long long lddo, const bf16* o, long long 
     const int bytes = attn_smem_bytes(hs, nmax, 4, true);
     const float scale = 1.0f / sqrtf(static_cast<float>(hs));
     if (hs == 32) {
-        if (attn_configure(tr_attn_bwd_kernel<32>, bytes)) return 1;
+        if (attn_configure<2>(tr_attn_bwd_kernel<32>, bytes)) return 1;
         tr_attn_bwd_kernel<32><<<dim3(B, H), 256, bytes, s>>>(dO, lddo, o, ldo, P, qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, dqkv, ldd, C);
     } else {
-        if (attn_configure(tr_attn_bwd_kernel<64>, bytes)) return 1;
+        if (attn_configure<3>(tr_attn_bwd_kernel<64>, bytes)) return 1;
         tr_attn_bwd_kernel<64><<<dim3(B, H), 256, bytes, s>>>(dO, lddo, o, ldo, P, qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, dqkv, ldd, C);
     }
     MMF_CUDA_OK(cudaGetLastError());

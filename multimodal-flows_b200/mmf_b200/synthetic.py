@@ -56,6 +56,16 @@ def source_batch(num_jets: int, **kw) -> DataCoupling:
     return DataCoupling(source=source_state(num_jets, **kw), target=TensorMultiModal())
 
 
+def training_batch(num_jets: int, max_particles: int = 150, vocab_size: int = 9, seed: int = 1234, dense: bool = False) -> DataCoupling:
+    """(source, target) pair of a training step (reference utils/datasets.py:8-41): the source as the sampler draws it, a
+    synthetic "data" target on the same masks."""
+    src = source_state(num_jets, max_particles, vocab_size, dense=dense, seed=seed)
+    g = torch.Generator().manual_seed(seed + 7)
+    x1 = (torch.randn(num_jets, max_particles, 3, generator=g) * 1.5 + 0.3) * src.mask
+    k1 = torch.randint(1, vocab_size, (num_jets, max_particles, 1), generator=g) * src.mask
+    return DataCoupling(source=src, target=TensorMultiModal(time=None, continuous=x1, discrete=k1, mask=src.mask))
+
+
 def uniform_draws(num_steps: int, num_jets: int, max_particles: int = 150, vocab_size: int = 9,
                   seed: int = 1237) -> torch.Tensor:
     g = torch.Generator().manual_seed(seed)
