@@ -13,6 +13,8 @@ Contract (see the task description): `python bench.py --gpus N --steps K --warmu
   gpu_eager_baseline = the fp32 oracle port (plain torch, TF32 off) on the same GPU, whole batch, bounded timesteps
   extra_models = FusedParticleFormer / EPiC on one GPU; whole_run = source -> sampler -> records -> ONE collective, timed
               end to end on every rank (BASELINE configs #3 and #4)
+  training  = BASELINE config #5: the device training step (forward + backward + gradient all-reduce + clip + Adam) on every rank,
+              with the unmodified reference's own step on the host cores and fp32 eager torch on the same GPU beside it
 `--impl reference` times the reference's own CPU sampler as the reference arm (rank 0 only): every step is the whole batch
 for `--ref-sample-timesteps` timesteps, nothing is extrapolated over jets.
 """
@@ -25,6 +27,8 @@ import subprocess
 import sys
 import threading
 import time
+
+import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "multimodal-flows_b200"))
@@ -352,6 +356,124 @@ def whole_run_lines(args, dev, rank, world):
     return out
 
 
+def training_flops(model: str, n: torch.Tensor) -> float:
+    """Algorithmic FLOPs of one training step on real particles: forward + backward = 3 x forward
+    (every product appears once more for the data gradient and once for the weight gradient)."""
+    return 3.0 * algorithmic_flops_per_timestep(model, n)
+
+
+def training_lines(args, peaks, dev, rank, world):
+    """BASELINE config #5 on every rank: one step = bridge sampling + bf16 forward + backward + (N > 1: ONE all-reduce of the flat
+    gradient) + norm clipping + Adam on a batch of `--batch` AOJ-shaped jets, all inside the clock.  jets/s = jets of all ranks /
+    max-over-ranks CUDA-event time.  Rank 0 of a single-GPU run adds the unmodified reference's own training step on the host
+    cores and fp32 eager torch (autograd over the oracle port + torch.optim.Adam) on the same GPU."""
+    from mmf_b200 import synthetic
+    from mmf_b200.mmf import MultiModalFlowBridge
+    from mmf_b200.param_spec import make_config
+    out = {}
+    for name, steps in (("ParticleFormer", 8), ("FusedParticleFormer", 8)):
+        cfg = make_config(name, lr=1e-3, lr_final=1e-5, max_epochs=100, warmup_epochs=5)
+        sd = synthetic.make_state_dict(cfg, flavor="wide", seed=0)
+        bridge = MultiModalFlowBridge(cfg)
+        bridge.model.load_state_dict(sd, strict=True)
+        bridge = bridge.to(dev)
+        eng = bridge.configure_training(lr=cfg.lr)
+        batch = synthetic.training_batch(args.batch, cfg.max_num_particles, cfg.vocab_size, seed=1234 + 10 * rank)
+        batch.source, batch.target = batch.source.to(dev), batch.target.to(dev)
+        for _ in range(3):
+            eng.train_step(batch)
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        l0 = eng.ops.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            out5 = eng.train_step(batch)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        eng.check_tokens()
+        tmax = torch.tensor([e0.elapsed_time(e1) * 1e-3, wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(tmax, op=torch.distributed.ReduceOp.MAX)
+        sec = float(tmax[0]) / steps
+        fl = training_flops(name, torch.as_tensor(eng.last_plan.n))
+        tf = fl / sec / 1e12
+        out[name] = {"workload": f"{name} training step: MultiModalFlowBridge.loss ({cfg.multitask_loss}) forward + backward, gradient clip 1.0, Adam; "
+                                 f"{args.batch} AOJ-shaped jets per GPU, bf16 operands / fp32 accumulation, master weights and gradients fp32",
+                     "value": world * args.batch / sec, "unit": "jets/s", "ms_per_step": 1e3 * sec, "steps": steps, "warmup": 3,
+                     "wall_ms_per_step": 1e3 * float(tmax[1]) / steps, "gpu_launches_per_step": (eng.ops.launches - l0) / steps,
+                     "parameters": int(sum(int(np.prod(eng.shape[n])) for n in eng.names)), "loss_after": float(out5[0]),
+                     "collective": None if world == 1 else f"one all_reduce of the flat fp32 gradient ({4 * eng.total} bytes) per step, inside the timed region",
+                     "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                  "frac": tf / peaks["bf16_tflops_sustained"],
+                                  "note": "algorithmic FLOPs = 3 x the forward count of SURVEY 8(d) on real particles, whole step (all kernels)"}}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            out[name].update(training_baselines(args, cfg, sd, dev, name))
+        del eng, bridge
+    return out
+
+
+def training_baselines(args, cfg, sd, dev, name):
+    """The same training step (same batch, same Adam + clip) by (a) the UNMODIFIED reference on the host cores and (b) fp32 eager
+    torch on this GPU (autograd over oracle/mmf_oracle.py, TF32 off).  One measured step each after one warm-up step."""
+    from mmf_b200 import synthetic
+    from oracle import mmf_oracle as orc, ref_loader
+    res = {}
+    batch = synthetic.training_batch(args.batch, cfg.max_num_particles, cfg.vocab_size, seed=1234)
+    if ref_loader.available():
+        torch.set_num_threads(os.cpu_count() or 1)
+        ref = ref_loader.modules()
+        m = ref.MultiModalFlowBridge(cfg)
+        m.model.load_state_dict(sd, strict=True)
+        opt = m.configure_optimizers()["optimizer"]
+        mk = lambda t: ref.TensorMultiModal(continuous=t.continuous.clone(), discrete=t.discrete.clone(), mask=t.mask.clone())
+        secs = []
+        for _ in range(2):
+            b = ref.DataCoupling(source=mk(batch.source), target=mk(batch.target))
+            t0 = time.perf_counter()
+            opt.zero_grad()
+            loss = m.loss(b)[0]
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+            opt.step()
+            secs.append(time.perf_counter() - t0)
+        res["cpu_baseline"] = {"value": args.batch / secs[-1], "unit": "jets/s", "cores": os.cpu_count() or 1, "kind": "reference",
+                               "sample": f"the unmodified reference (oracle/_ref): MultiModalFlowBridge.loss + backward + clip_grad_norm_(1.0) + its own "
+                                         f"configure_optimizers() Adam step, torch fp32, one step on the whole batch of {args.batch} jets ({secs[-1]:.2f} s)"}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sdg = {k: torch.nn.Parameter(v.to(dev).clone()) for k, v in sd.items()}
+    E = cfg.n_embd
+    g = torch.Generator().manual_seed(3)
+    slg = {"uncertainty_net.c_fc.weight": torch.randn(E, E, generator=g) * 0.02, "uncertainty_net.c_fc.bias": torch.zeros(E),
+           "uncertainty_net.c_proj.weight": torch.randn(2, E, generator=g) * 0.02, "uncertainty_net.c_proj.bias": torch.zeros(2)}
+    slg = {k: torch.nn.Parameter(v.to(dev)) for k, v in slg.items()}
+    params = list(sdg.values()) + list(slg.values())
+    opt = torch.optim.Adam(params, lr=cfg.lr)
+    src, tgt = batch.source.to(dev), batch.target.to(dev)
+    B, D = src.continuous.shape[:2]
+    ms = []
+    for _ in range(3):
+        t = cfg.time_eps + (1.0 - cfg.time_eps) * torch.rand(B, device=dev)
+        z, u = torch.randn(B, D, 3, device=dev), torch.rand(B, D, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        opt.zero_grad()
+        loss = orc.training_loss(sdg, slg, cfg, src.continuous, src.discrete, tgt.continuous, tgt.discrete, src.mask, t, z, u)[0]
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    res["gpu_eager_baseline"] = {"value": args.batch / (min(ms[1:]) * 1e-3), "unit": "jets/s", "ms_per_step": min(ms[1:]),
+                                 "kind": "port on cuda (autograd over oracle/mmf_oracle.py + torch.optim.Adam + clip_grad_norm_, eager torch fp32, TF32 off)"}
+    return res
+
+
 def workload_name(args):
     return (f"{args.model} sampler, batch {args.batch} jets/GPU x {args.timesteps} timesteps, D=150, V=9, "
             + ("dense n=150" if args.dense else "AOJ-shaped n~clamp(round(55+18z),1,150)") + f", T={args.temperature}")
@@ -533,6 +655,7 @@ def main():
 
     # ---- whole runs with the single end-of-run collective INSIDE the clock (all ranks) -----------------------
     whole_run = None if args.no_extras else whole_run_lines(args, dev, rank, world)
+    training = None if (args.no_extras or epic) else training_lines(args, peaks, dev, rank, world)
 
     if rank != 0:
         if world > 1:
@@ -593,6 +716,8 @@ def main():
     }
     if whole_run is not None:
         line["whole_run"] = whole_run
+    if training is not None:
+        line["training"] = training
     if not args.no_extras:
         if not epic and not args.dense:
             # the dense worst case (every jet 150 particles -> CTA-pair tiles) on the same kernel, same timing rules

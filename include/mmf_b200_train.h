@@ -94,8 +94,9 @@ int mmf_tr_loss_fwd(const float* vt, const float* logits, const float* tgt, cons
  * out5 = batch means of (loss, l_mse, l_ce, w_mse, w_ce); gl1 / gl2 [B] = d loss / d l_mse, d l_ce; du [B, 2] = d loss / d u */
 int mmf_tr_loss_combine(const float* loss_mse, const float* loss_ce, const float* u, int32_t B, float* out5, float* gl1, float* gl2, float* du,
                         void* stream);
+/* d loss / d (vt, logits) per row; rows at and beyond jet_off[B] (a batch padded to a fixed row capacity M) get zeros */
 int mmf_tr_loss_bwd(const float* vt, const float* logits, const float* tgt, const int32_t* k1, const int32_t* row_jet, const int32_t* jet_off,
-                    const float* gl1, const float* gl2, int32_t M, int32_t V, float* dvt, float* dlog, void* stream);
+                    const float* gl1, const float* gl2, int32_t M, int32_t B, int32_t V, float* dvt, float* dlog, void* stream);
 /* out[0] = sum g^2 (the squared gradient norm of clip_grad_norm_) */
 int mmf_tr_sumsq(const float* g, int64_t n, float* out, void* stream);
 /* torch.optim.Adam step `step` (1-based) on flat buffers; the gradient is first multiplied by grad_scale and, when sumsq is

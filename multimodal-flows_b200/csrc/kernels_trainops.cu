@@ -766,10 +766,17 @@ __global__ void tr_loss_combine_kernel(const float* __restrict__ loss_mse, const
 template <int V>
 __global__ void tr_loss_bwd_kernel(const float* __restrict__ vt, const float* __restrict__ logits, const float* __restrict__ tgt,
                                    const int* __restrict__ k1, const int* __restrict__ row_jet, const int* __restrict__ jet_off,
-                                   const float* __restrict__ gl1, const float* __restrict__ gl2, int M, float* __restrict__ dvt,
+                                   const float* __restrict__ gl1, const float* __restrict__ gl2, int M, int B, float* __restrict__ dvt,
                                    float* __restrict__ dlog) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= M) return;
+    if (r >= jet_off[B]) {                              // rows beyond the last jet (a batch padded to a fixed row capacity)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dvt[r * 3 + c] = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) dlog[r * V + v] = 0.f;
+        return;
+    }
     const int b = row_jet[r];
     const float dn = fmaxf(static_cast<float>(jet_off[b + 1] - jet_off[b]), 1.0f);
     const float a1 = 2.0f * gl1[b] / dn, a2 = gl2[b] / dn;
@@ -1071,10 +1078,10 @@ int launch_tr_loss_combine(const float* loss_mse, const float* loss_ce, const fl
 }
 
 int launch_tr_loss_bwd(const float* vt, const float* logits, const float* tgt, const int* k1, const int* row_jet, const int* jet_off,
-                       const float* gl1, const float* gl2, int M, int V, float* dvt, float* dlog, cudaStream_t s) {
+                       const float* gl1, const float* gl2, int M, int B, int V, float* dvt, float* dlog, cudaStream_t s) {
     if (M <= 0) return 0;
     MMF_REQUIRE(V == 9, "the loss kernels are instantiated for vocab_size 9");
-    tr_loss_bwd_kernel<9><<<blocks_for(M, 256), 256, 0, s>>>(vt, logits, tgt, k1, row_jet, jet_off, gl1, gl2, M, dvt, dlog);
+    tr_loss_bwd_kernel<9><<<blocks_for(M, 256), 256, 0, s>>>(vt, logits, tgt, k1, row_jet, jet_off, gl1, gl2, M, B, dvt, dlog);
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }

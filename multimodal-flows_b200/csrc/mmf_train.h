@@ -85,7 +85,7 @@ int launch_tr_loss_fwd(const float* vt, const float* logits, const float* tgt, c
 int launch_tr_loss_combine(const float* loss_mse, const float* loss_ce, const float* u, int B, float* out5, float* gl1, float* gl2,
                            float* du, cudaStream_t s);
 int launch_tr_loss_bwd(const float* vt, const float* logits, const float* tgt, const int* k1, const int* row_jet, const int* jet_off,
-                       const float* gl1, const float* gl2, int M, int V, float* dvt, float* dlog, cudaStream_t s);
+                       const float* gl1, const float* gl2, int M, int B, int V, float* dvt, float* dlog, cudaStream_t s);
 
 int launch_tr_sumsq(const float* g, long long n, float* out, cudaStream_t s);
 // torch.optim.Adam (reference model/MMF.py:77-78) with Lightning's gradient_clip_val norm clipping (scripts/train_mmf.py:166) folded in

@@ -131,8 +131,8 @@ int mmf_tr_loss_combine(const float* loss_mse, const float* loss_ce, const float
     return launch_tr_loss_combine(loss_mse, loss_ce, u, B, out5, gl1, gl2, du, S_(stream));
 }
 int mmf_tr_loss_bwd(const float* vt, const float* logits, const float* tgt, const int32_t* k1, const int32_t* row_jet, const int32_t* jet_off,
-                    const float* gl1, const float* gl2, int32_t M, int32_t V, float* dvt, float* dlog, void* stream) {
-    return launch_tr_loss_bwd(vt, logits, tgt, k1, row_jet, jet_off, gl1, gl2, M, V, dvt, dlog, S_(stream));
+                    const float* gl1, const float* gl2, int32_t M, int32_t B, int32_t V, float* dvt, float* dlog, void* stream) {
+    return launch_tr_loss_bwd(vt, logits, tgt, k1, row_jet, jet_off, gl1, gl2, M, B, V, dvt, dlog, S_(stream));
 }
 
 int mmf_tr_sumsq(const float* g, int64_t n, float* out, void* stream) { return launch_tr_sumsq(g, n, out, S_(stream)); }

@@ -38,7 +38,7 @@ SIGNATURES = {
     "mmf_tr_head_bwd": [P, P, P, P, I64, I32, P, P, I32, I32, P, P, P, P, P, P],
     "mmf_tr_loss_fwd": [P, P, P, P, P, I32, I32, P, P, P],
     "mmf_tr_loss_combine": [P, P, P, I32, P, P, P, P, P],
-    "mmf_tr_loss_bwd": [P, P, P, P, P, P, P, P, I32, I32, P, P, P],
+    "mmf_tr_loss_bwd": [P, P, P, P, P, P, P, P, I32, I32, I32, P, P, P],
     "mmf_tr_sumsq": [P, I64, P, P],
     "mmf_tr_adam": [P, P, P, P, I64, F, F, F, F, I32, P, F, F, P, P],
 }
@@ -172,7 +172,8 @@ class Ops:
         _abi.check(self.L.mmf_tr_loss_combine(_p(loss_mse), _p(loss_ce), _p(u), loss_mse.shape[0], _p(out5), _p(gl1), _p(gl2), _p(du), self._s()))
 
     def loss_bwd(self, vt, logits, tgt, k1, row_jet, jet_off, gl1, gl2, V, dvt, dlog):
-        _abi.check(self.L.mmf_tr_loss_bwd(_p(vt), _p(logits), _p(tgt), _p(k1), _p(row_jet), _p(jet_off), _p(gl1), _p(gl2), vt.shape[0], V,
+        _abi.check(self.L.mmf_tr_loss_bwd(_p(vt), _p(logits), _p(tgt), _p(k1), _p(row_jet), _p(jet_off), _p(gl1), _p(gl2), vt.shape[0],
+                                          gl1.shape[0], V,
                                           _p(dvt), _p(dlog), self._s()))
 
     def sumsq(self, g, out):

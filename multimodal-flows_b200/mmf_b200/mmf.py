@@ -187,12 +187,12 @@ class MultiModalFlowBridge(_GenerativeBase):
         if value is not None and _Base is not nn.Module:      # pragma: no cover - Lightning only
             self.log(name, value, **kw)
 
-    def configure_training(self, lr: Optional[float] = None, max_norm: float = 1.0):
+    def configure_training(self, lr: Optional[float] = None, max_norm: float = 1.0, use_graphs: bool = True):
         """Creates the device training engine (reference configure_optimizers model/MMF.py:77-78: Adam(lr=config.lr); Trainer
         gradient_clip_val=1.0 scripts/train_mmf.py:166).  From here on the parameters live in the engine's flat buffers."""
         from .training import TrainEngine
         self.automatic_optimization = False                 # Lightning: the step owns backward and the optimiser
-        self._engine = TrainEngine(self, lr=lr, max_norm=max_norm)
+        self._engine = TrainEngine(self, lr=lr, max_norm=max_norm, use_graphs=use_graphs)
         return self._engine
 
     def training_step(self, batch: DataCoupling, batch_idx: int = 0, lr: Optional[float] = None):

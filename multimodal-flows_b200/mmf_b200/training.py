@@ -29,8 +29,9 @@ _ALIGN = 64                                      # elements: every parameter sta
 
 class _Plan:
     """Row maps of one batch, built on the host from the mask (any mask works; the reference's are prefix masks)."""
+    padded = False
 
-    def __init__(self, mask: torch.Tensor, device: torch.device):
+    def __init__(self, mask: torch.Tensor, device: torch.device, upload: bool = True):
         m = mask.detach().reshape(mask.shape[0], -1).to("cpu").numpy() != 0
         self.B, self.D = m.shape
         n = m.sum(1).astype(np.int64)
@@ -38,21 +39,52 @@ class _Plan:
         self.M = int(n.sum())
         self.nmax = int(n.max()) if self.B else 0
         self.Mp = (self.M + 63) // 64 * 64
-        jet_off = np.zeros(self.B + 1, np.int32)
-        np.cumsum(n, out=jet_off[1:])
-        p_off = np.zeros(self.B + 1, np.int64)
-        np.cumsum(n * n, out=p_off[1:])
-        self.sum_n2 = int(p_off[-1])
-        row_slot = np.flatnonzero(m.reshape(-1)).astype(np.int32)
-        row_jet = np.repeat(np.arange(self.B, dtype=np.int32), n)
+        self.h_jet_off = np.zeros(self.B + 1, np.int32)
+        np.cumsum(n, out=self.h_jet_off[1:])
+        self.h_p_off = np.zeros(self.B + 1, np.int64)
+        np.cumsum(n * n, out=self.h_p_off[1:])
+        self.sum_n2 = int(self.h_p_off[-1])
+        self.h_row_slot = np.flatnonzero(m.reshape(-1)).astype(np.int32)
+        self.h_row_jet = np.repeat(np.arange(self.B, dtype=np.int32), n)
         up = lambda a: torch.from_numpy(a).to(device, non_blocking=True)
-        self.jet_off, self.p_off, self.row_slot, self.row_jet = up(jet_off), up(p_off), up(row_slot), up(row_jet)
+        self.row_slot = up(self.h_row_slot)
+        if upload:
+            self.jet_off, self.p_off, self.row_jet = up(self.h_jet_off), up(self.h_p_off), up(self.h_row_jet)
+
+
+class _GraphSlot:
+    """Static buffers of one captured forward + backward program: a batch of B jets padded to `rows` packed rows.  Rows at and
+    beyond the last jet belong to no jet: attention never touches them, the loss gives them zero gradient, so they add
+    nothing to any parameter gradient - the same CUDA graph serves every batch of B jets with at most `rows` particles."""
+    padded = True
+
+    def __init__(self, B: int, D: int, rows: int, device: torch.device):
+        self.B, self.D, self.M, self.Mp, self.nmax, self.sum_n2 = B, D, rows, rows, D, B * D * D
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, device=device, dtype=dt)
+        self.jet_off, self.p_off, self.row_jet = z(B + 1, dt=torch.int32), z(B + 1, dt=torch.int64), z(rows, dt=torch.int32)
+        self.xs, self.tg, self.ks, self.k1p, self.t = z(rows, 3), z(rows, 3), z(rows, dt=torch.int32), z(rows, dt=torch.int32), z(B)
+        self.pin = [torch.zeros(B + 1, dtype=torch.int32).pin_memory(), torch.zeros(B + 1, dtype=torch.int64).pin_memory(),
+                    torch.zeros(rows, dtype=torch.int32).pin_memory()]
+        self.graph, self.out5, self.busy = None, None, None
+
+    def load(self, plan: _Plan):
+        if self.busy is not None:
+            self.busy.synchronize()                            # the previous upload still reads the pinned staging
+        self.pin[0].copy_(torch.from_numpy(plan.h_jet_off))
+        self.pin[1].copy_(torch.from_numpy(plan.h_p_off))
+        self.pin[2][: plan.M].copy_(torch.from_numpy(plan.h_row_jet))
+        self.jet_off.copy_(self.pin[0], non_blocking=True)
+        self.p_off.copy_(self.pin[1], non_blocking=True)
+        self.row_jet[: plan.M].copy_(self.pin[2][: plan.M], non_blocking=True)
+        self.busy = torch.cuda.Event()
+        self.busy.record()
 
 
 class TrainEngine:
     """fwd + bwd + optimiser for one ``MultiModalFlowBridge`` (its encoder and its ``MultiTaskLoss``)."""
 
-    def __init__(self, module, lr: Optional[float] = None, betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0, _ops=None):
+    def __init__(self, module, lr: Optional[float] = None, betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0,
+                 use_graphs: bool = False, _ops=None):
         """``_ops`` is a test seam (tests/mock_train_ops.py checks the sequencing below on the CPU); the product path has no
         default for it other than the library."""
         cfg = module.config
@@ -112,7 +144,8 @@ class TrainEngine:
         self._sumsq = torch.zeros(1, device=dev)
         self._err = torch.zeros(1, device=dev, dtype=torch.int32)
         self.refresh_operands()
-        self.last_grad_norm = None
+        self.use_graphs, self.graph_rows, self._slots = bool(use_graphs) and _ops is None, 1024, {}
+        self.last_plan = None
 
     # ---- parameter views -------------------------------------------------------------------------------------------------
     def _v(self, buf, name):
@@ -178,7 +211,8 @@ class TrainEngine:
                          self.p(pre + ".attn.k_layernorm.weight"), self.p(pre + ".attn.k_layernorm.bias"), s["qn"], s["kn"])
         else:
             s["qn"], s["kn"] = s["qkv"][:, :C], s["qkv"][:, C:2 * C]
-        s["o"], s["P"] = torch.empty(M, C, **bf), torch.empty(max(plan.sum_n2 * H, 1), **bf)
+        s["o"] = torch.zeros(M, C, **bf) if plan.padded else torch.empty(M, C, **bf)      # rows of no jet are never written
+        s["P"] = torch.empty(max(plan.sum_n2 * H, 1), **bf)
         ops.attn_fwd(s["qn"], s["kn"], s["qkv"][:, 2 * C:], plan.jet_off, plan.p_off, plan.B, H, hs, plan.nmax, s["o"], s["P"])
         y = torch.empty(M, C, device=dev)
         self._lin_fwd(s["o"], pre + ".attn.c_proj", y, 1)
@@ -208,7 +242,7 @@ class TrainEngine:
                    accumulate=True)
         do = torch.empty(M, C, **bf)
         self._lin_bwd(plan, G16, s["o"], pre + ".attn.c_proj", dx=do, dx_mode=0, dy_src=G)
-        dqkv = torch.empty(M, 3 * C, **bf)
+        dqkv = torch.zeros(M, 3 * C, **bf) if plan.padded else torch.empty(M, 3 * C, **bf)
         ops.attn_bwd(do, s["o"], s["P"], s["qn"], s["kn"], s["qkv"][:, 2 * C:], plan.jet_off, plan.p_off, plan.B, H, hs, plan.nmax, dqkv, C)
         if self.cfg.qk_layernorm:
             ops.qkln_bwd(dqkv, s["qkv"], C, H, self.p(pre + ".attn.q_layernorm.weight"), self.p(pre + ".attn.k_layernorm.weight"),
@@ -396,7 +430,7 @@ class TrainEngine:
         if time is None:
             time = eps + (1.0 - eps) * torch.rand(B, device=dev)
         time = time.to(dev, torch.float32).contiguous()
-        plan = _Plan(batch.target.mask, dev)
+        plan = _Plan(batch.target.mask, dev, upload=not self.use_graphs)
         tgt, src = batch.target.to(dev), batch.source.to(dev) if batch.source is not None else TensorMultiModal()
         if not src.has_continuous:                       # reference model/CFM.py:175-177
             src.continuous = torch.randn_like(tgt.continuous) * tgt.mask
@@ -406,27 +440,61 @@ class TrainEngine:
                                     z=None if z is None else z.to(dev), u=None if u is None else u.to(dev), seed=mod.seed,
                                     first_global_jet=mod._jet_cursor)
         mod._jet_cursor += B
-        M = plan.M
-        xs, tg = torch.empty(M, 3, device=dev), torch.empty(M, 3, device=dev)
-        ks, k1p = torch.empty(M, device=dev, dtype=torch.int32), torch.empty(M, device=dev, dtype=torch.int32)
+        self.last_plan = plan
+        if self.use_graphs:
+            rows = max(self.graph_rows, (plan.M + self.graph_rows - 1) // self.graph_rows * self.graph_rows)
+            key = (plan.B, plan.D, rows)
+            slot = self._slots.get(key)
+            if slot is None:
+                slot = self._slots[key] = _GraphSlot(plan.B, plan.D, rows, dev)
+            slot.load(plan)
+            slot.t.copy_(time)
+            xs, ks, tg, k1p, run = slot.xs, slot.ks, slot.tg, slot.k1p, slot
+        else:
+            M = plan.M
+            xs, tg = torch.empty(M, 3, device=dev), torch.empty(M, 3, device=dev)
+            ks, k1p = torch.empty(M, device=dev, dtype=torch.int32), torch.empty(M, device=dev, dtype=torch.int32)
+            run = plan
         self.ops.pack(xt.contiguous(), kt.contiguous(), src.continuous.contiguous(), tgt.continuous.contiguous(), tgt.discrete.contiguous(),
                       plan.row_slot, V, xs, ks, tg, k1p, self._err)
-        return plan, time, xs, ks, tg, k1p
+        return run, time, xs, ks, tg, k1p
 
-    def loss_and_grad(self, batch: DataCoupling, time=None, z=None, u=None, zero_grad: bool = True):
-        """One forward + backward pass.  Returns the reference's (loss, loss_mse, loss_ce, w_mse, w_ce) as a 5-vector on the
-        device; the gradients are in ``self.G`` (= every parameter's ``.grad``)."""
-        plan, t, xs, ks, tg, k1p = self._prepare(batch, time, z, u)
-        if zero_grad:
-            self.G.zero_()
+    def _fwd_bwd(self, plan, xs, ks, tg, k1p, t):
+        self.G.zero_()
         c = self._forward(plan, xs, ks, t)
         out5 = self._loss(plan, c, tg, k1p, t, True)
         self._backward(plan, c, xs, ks)
-        self.last_plan = plan
         return out5
 
-    def loss_only(self, batch: DataCoupling, time=None, z=None, u=None):
+    def loss_and_grad(self, batch: DataCoupling, time=None, z=None, u=None):
+        """One forward + backward pass.  Returns the reference's (loss, loss_mse, loss_ce, w_mse, w_ce) as a 5-vector on the
+        device; the gradients are in ``self.G`` (= every parameter's ``.grad``).  With ``use_graphs`` the ~600 kernel launches
+        of the pass are ONE CUDA graph per (jets, padded row count), captured on first use and replayed afterwards."""
         plan, t, xs, ks, tg, k1p = self._prepare(batch, time, z, u)
+        if not self.use_graphs:
+            return self._fwd_bwd(plan, xs, ks, tg, k1p, t)
+        slot = plan
+        if slot.graph is None:
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                 # eager warm-up off the capture: one-time attribute opt-ins, allocator
+                self._fwd_bwd(slot, xs, ks, tg, k1p, slot.t)
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                slot.out5 = self._fwd_bwd(slot, xs, ks, tg, k1p, slot.t)
+            slot.graph = graph
+        slot.graph.replay()
+        self.ops.launches += 1
+        return slot.out5
+
+    def loss_only(self, batch: DataCoupling, time=None, z=None, u=None):
+        graphs, self.use_graphs = self.use_graphs, False
+        try:
+            plan, t, xs, ks, tg, k1p = self._prepare(batch, time, z, u)
+        finally:
+            self.use_graphs = graphs
         c = self._forward(plan, xs, ks, t)
         return self._loss(plan, c, tg, k1p, t, False)
 

@@ -217,9 +217,10 @@ class MockOps:
     def loss_bwd(self, vt, logits, tgt, k1, row_jet, jet_off, gl1, gl2, V, dvt, dlog):
         n = (jet_off[1:] - jet_off[:-1]).float().clamp_min(1)
         rj = row_jet.long()
-        dvt.copy_((2 * gl1[rj] / n[rj])[:, None] * (vt - tgt))
+        real = (torch.arange(vt.shape[0]) < int(jet_off[-1]))[:, None]
+        dvt.copy_(torch.where(real, (2 * gl1[rj] / n[rj])[:, None] * (vt - tgt), torch.zeros_like(vt)))
         p = torch.softmax(logits, -1) - F.one_hot(k1.long(), V).float()
-        dlog.copy_(torch.where((k1 != 0)[:, None], (gl2[rj] / n[rj])[:, None] * p, torch.zeros_like(p)))
+        dlog.copy_(torch.where((k1 != 0)[:, None] & real, (gl2[rj] / n[rj])[:, None] * p, torch.zeros_like(p)))
 
     def sumsq(self, g, out):
         out.copy_((g.double() ** 2).sum().float().view(1))
