@@ -24,6 +24,10 @@ extern "C" {
  * replaces F.linear and its autograd (attention.py:44-45, utils/models.py:15-17). */
 int mmf_tr_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
                 const float* bias, int32_t mode, int32_t ksplit, void* stream);
+/* weight gradient of nn.Linear straight from the row-major activations: C[M x N] += A^T B with A = dy [K x M], B = x [K x N]
+ * (bf16, K = tokens; both are read as MN-major tcgen05 operands, so no transposed copy exists); K split over `ksplit` CTAs */
+int mmf_tr_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                   int32_t ksplit, void* stream);
 /* small fp32 product with general strides, C[m, n] = sum_k A[m sam + k sak] B[k sbk + n sbn] (+ bias[n]) (+ C):
  * the per-jet linears (time_expand ParticleTransformers.py:109, MultiTaskLoss.uncertainty_net MMF.py:212) and their gradients */
 int mmf_tr_sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t ldc, int32_t M,

@@ -6,11 +6,13 @@
 //
 //     forward      y  = x  W^T + b      A = x  [tokens, in]     B = W    [out, in]
 //     data grad    dx = dy W            A = dy [tokens, out]    B = W^T  [in, out]     (bf16 transposed copy of the weight)
-//     weight grad  dW = dy^T x          A = dy^T [out, tokens]  B = x^T  [in, tokens]  (K = tokens, split over blockIdx.z, the
-//                                                                                       partial tiles meet in a TMA reduce-add)
+//     weight grad  dW = dy^T x          A = dy [tokens, out]    B = x    [tokens, in]  both read as MN-MAJOR operands (no transposed
+//                                       copies exist anywhere); K = tokens, split over blockIdx.z, the partial tiles meet in a
+//                                       TMA reduce-add
 //
 // One CTA = one 128 x 128 output tile: a TMA producer thread and an MMA issuer thread run a 4-stage ring of 128-byte-swizzled
-// [128 x 64] operand boxes; four epilogue warps move the accumulator TMEM -> registers -> swizzled shared memory and one thread
+// [128 x 64] operand boxes (MN-major operands: two [64 tokens x 64 features] boxes each); the ring is as deep as the K loop is
+// long (2 ... 4 stages), so short-K products run three CTAs per SM and hide each other's prologue / epilogue; four epilogue warps move the accumulator TMEM -> registers -> swizzled shared memory and one thread
 // stores (or reduce-adds) the tile with TMA.  Tensor maps carry the exact extents, so ragged M / N / K edges are zero-filled on
 // load and clipped on store - no padding rules for the callers.
 #include "mmf_internal.h"
@@ -24,7 +26,19 @@ namespace {
 constexpr int kTrStages = 4;
 constexpr int kTrBox = kTileM * 128;             // one operand box: 128 rows x 128 B
 constexpr int kTrStage = 2 * kTrBox;             // A + B
-constexpr int kTrSmem = 1024 + kTrStages * kTrStage + 1024;
+constexpr int tr_smem_bytes(int stages) { return 1024 + stages * kTrStage + 1024; }
+
+// MN-major operand, 128-byte swizzle: [8 K-rows][64 elements] atoms of 1024 B; SBO = 1024 B between 8-row groups along K,
+// LBO = 8192 B between the two 64-element groups along M / N (two [64 x 64] TMA boxes side by side)
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(8192 >> 4) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
 
 struct TrGemmBars {
     uint64_t full[kTrStages], empty[kTrStages], acc_full;
@@ -37,11 +51,12 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
                  : "memory");
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(192, 1)
+// MODE 0: bf16 store, 1: fp32 store, 2: fp32 reduce-add; TN: A [K x M], B [K x N] row-major (MN-major operands)
+template <int MODE, bool TN>
+__global__ void __launch_bounds__(192, 3)
 tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const int N, const int kb_total,
-               const int kb_per_split) {
+               const int kb_per_split, const int stages) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     TrGemmBars* bars = reinterpret_cast<TrGemmBars*>(smem);
@@ -75,25 +90,35 @@ tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 4) {
         if (lane == 0) {
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % kTrStages, it = i / kTrStages;
+                const int s = i % stages, it = i / stages;
                 if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
                 mbar_expect_tx(&bars->full[s], kTrStage);
-                tma_load_2d(tiles + s * kTrStage, &tmA, &bars->full[s], (kb0 + i) * kBK, m0);
-                tma_load_2d(tiles + s * kTrStage + kTrBox, &tmB, &bars->full[s], (kb0 + i) * kBK, n0);
+                uint8_t* sa = tiles + s * kTrStage;
+                if constexpr (TN) {
+                    tma_load_2d(sa, &tmA, &bars->full[s], m0, (kb0 + i) * kBK);
+                    tma_load_2d(sa + kTrBox / 2, &tmA, &bars->full[s], m0 + 64, (kb0 + i) * kBK);
+                    tma_load_2d(sa + kTrBox, &tmB, &bars->full[s], n0, (kb0 + i) * kBK);
+                    tma_load_2d(sa + kTrBox + kTrBox / 2, &tmB, &bars->full[s], n0 + 64, (kb0 + i) * kBK);
+                } else {
+                    tma_load_2d(sa, &tmA, &bars->full[s], (kb0 + i) * kBK, m0);
+                    tma_load_2d(sa + kTrBox, &tmB, &bars->full[s], (kb0 + i) * kBK, n0);
+                }
             }
         }
         __syncwarp();
     } else if (warp == 5) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kTileM, 128);
+            constexpr uint32_t idesc = umma_idesc_bf16(kTileM, 128) | (TN ? (1u << 15) | (1u << 16) : 0u);   // bits 15 / 16: A / B MN-major
+            constexpr uint32_t kstep = TN ? (2048u >> 4) : 2u;          // K = 16: 16 rows of 128 B (MN-major) or 32 bytes (K-major)
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % kTrStages, it = i / kTrStages;
+                const int s = i % stages, it = i / stages;
                 mbar_wait(&bars->full[s], it & 1);
                 tc_fence_after();
-                const uint64_t da = umma_desc_sw128(smem_u32(tiles + s * kTrStage));
-                const uint64_t db = umma_desc_sw128(smem_u32(tiles + s * kTrStage + kTrBox));
+                const uint32_t aa = smem_u32(tiles + s * kTrStage), ab = aa + kTrBox;
+                const uint64_t da = TN ? umma_desc_sw128_mn(aa) : umma_desc_sw128(aa);
+                const uint64_t db = TN ? umma_desc_sw128_mn(ab) : umma_desc_sw128(ab);
 #pragma unroll
-                for (int ks = 0; ks < kBK / 16; ++ks) umma_bf16(tmem_base, da + 2 * ks, db + 2 * ks, idesc, (i | ks) != 0 ? 1u : 0u);
+                for (int ks = 0; ks < kBK / 16; ++ks) umma_bf16(tmem_base, da + kstep * ks, db + kstep * ks, idesc, (i | ks) != 0 ? 1u : 0u);
                 umma_commit(&bars->empty[s]);
             }
             umma_commit(&bars->acc_full);
@@ -107,16 +132,20 @@ tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&bars->acc_full, 0);
         tc_fence_after();
         if constexpr (MODE == 0) {
-            for (int cc = 0; cc < 2; ++cc) {
-                float v[64];
-                tmem_ld32(taddr + cc * 64, v);
-                tmem_ld32(taddr + cc * 64 + 32, v + 32);
+            for (int c = 0; c < 4; ++c) {
+                float v[32];
+                tmem_ld32(taddr + c * 32, v);
                 tmem_ld_wait();
                 if (add_bias) {
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) { const int col = n0 + cc * 64 + i; v[i] += col < N ? __ldg(bias + col) : 0.f; }
+                    for (int i = 0; i < 32; ++i) { const int col = n0 + c * 32 + i; v[i] += col < N ? __ldg(bias + col) : 0.f; }
                 }
-                stage_row_bf16(tiles + cc * kTrBox, r, v);
+                uint8_t* chunk = tiles + (c >> 1) * kTrBox;             // 64 bf16 columns per [128 x 128 B] staging chunk
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    st_shared_v4(chunk + sw128_offset(r, (c & 1) * 4 + u), pack_bf16x2(v[u * 8 + 0], v[u * 8 + 1]),
+                                 pack_bf16x2(v[u * 8 + 2], v[u * 8 + 3]), pack_bf16x2(v[u * 8 + 4], v[u * 8 + 5]),
+                                 pack_bf16x2(v[u * 8 + 6], v[u * 8 + 7]));
             }
         } else {
             for (int c = 0; c < 4; ++c) {
@@ -149,17 +178,19 @@ tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 5) tmem_dealloc(tmem_base, 128);
 }
 
-template <int MODE>
+template <int MODE, bool TN>
 int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const float* bias, int N, int kb_total,
                 int kb_per_split, dim3 grid, cudaStream_t s) {
     static bool configured[64] = {false};                 // the attribute is per device
     int dev = 0;
     MMF_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        MMF_CUDA_OK(cudaFuncSetAttribute(tr_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrSmem));
+        MMF_CUDA_OK(cudaFuncSetAttribute(tr_gemm_kernel<MODE, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem_bytes(kTrStages)));
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    tr_gemm_kernel<MODE><<<grid, 192, kTrSmem, s>>>(tmA, tmB, tmC, bias, N, kb_total, kb_per_split);
+    // the epilogue stages the whole output tile in the ring: two stages hold it (64 KB fp32)
+    const int stages = kb_per_split < 2 ? 2 : (kb_per_split > kTrStages ? kTrStages : kb_per_split);
+    tr_gemm_kernel<MODE, TN><<<grid, 192, tr_smem_bytes(stages), s>>>(tmA, tmB, tmC, bias, N, kb_total, kb_per_split, stages);
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -184,10 +215,29 @@ int launch_tr_gemm(const void* A, long long lda, const void* B, long long ldb, v
     else { if (make_tmap_2d(&tmC, C, 4, M, N, ldc, 32, 128)) return 1; }
     const dim3 grid((M + kTileM - 1) / kTileM, (N + 127) / 128, ksplit);
     switch (mode) {
-        case 0: return launch_mode<0>(tmA, tmB, tmC, bias, N, kb_total, per, grid, s);
-        case 1: return launch_mode<1>(tmA, tmB, tmC, bias, N, kb_total, per, grid, s);
-        default: return launch_mode<2>(tmA, tmB, tmC, bias, N, kb_total, per, grid, s);
+        case 0: return launch_mode<0, false>(tmA, tmB, tmC, bias, N, kb_total, per, grid, s);
+        case 1: return launch_mode<1, false>(tmA, tmB, tmC, bias, N, kb_total, per, grid, s);
+        default: return launch_mode<2, false>(tmA, tmB, tmC, bias, N, kb_total, per, grid, s);
     }
+}
+
+// C[M x N] += A^T B with A [K x M], B [K x N] row-major bf16 (the weight gradient dW += dy^T x straight from the row-major
+// activations: both operands MN-major); K split over `ksplit` CTAs per output tile, fp32 TMA reduce-add
+int launch_tr_gemm_tn(const void* A, long long lda, const void* B, long long ldb, float* C, long long ldc, int M, int N, int K, int ksplit,
+                      cudaStream_t s) {
+    MMF_REQUIRE(A && B && C, "gemm_tn: null operand");
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    const int kb_total = (K + kBK - 1) / kBK;
+    if (ksplit < 1) ksplit = 1;
+    if (ksplit > kb_total) ksplit = kb_total;
+    const int per = (kb_total + ksplit - 1) / ksplit;
+    ksplit = (kb_total + per - 1) / per;
+    CUtensorMap tmA, tmB, tmC;
+    if (make_tmap_2d(&tmA, A, 2, K, M, lda, 64, 64)) return 1;
+    if (make_tmap_2d(&tmB, B, 2, K, N, ldb, 64, 64)) return 1;
+    if (make_tmap_2d(&tmC, C, 4, M, N, ldc, 32, 128)) return 1;
+    const dim3 grid((M + kTileM - 1) / kTileM, (N + 127) / 128, ksplit);
+    return launch_mode<2, true>(tmA, tmB, tmC, nullptr, N, kb_total, per, grid, s);
 }
 
 }  // namespace mmf

@@ -10,6 +10,10 @@ namespace mmf {
 int launch_tr_gemm(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N, int K,
                    const float* bias, int mode, int ksplit, cudaStream_t s);
 
+// C[M x N] += A^T B, A [K x M], B [K x N] row-major bf16 (weight gradient from row-major activations, MN-major operands)
+int launch_tr_gemm_tn(const void* A, long long lda, const void* B, long long ldb, float* C, long long ldc, int M, int N, int K, int ksplit,
+                      cudaStream_t s);
+
 // small fp32 products on CUDA cores (per-jet operands: time_expand, uncertainty net): C = A B (+ bias) (+ C), general strides
 int launch_tr_sgemm(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C,
                     long long ldc, int M, int N, int K, const float* bias, int accumulate, cudaStream_t s);

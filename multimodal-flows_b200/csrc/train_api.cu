@@ -17,6 +17,11 @@ int mmf_tr_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
     return launch_tr_gemm(A, lda, B, ldb, C, ldc, M, N, K, bias, mode, ksplit, S_(stream));
 }
 
+int mmf_tr_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                   int32_t ksplit, void* stream) {
+    return launch_tr_gemm_tn(A, lda, B, ldb, C, ldc, M, N, K, ksplit, S_(stream));
+}
+
 int mmf_tr_sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t ldc, int32_t M,
                  int32_t N, int32_t K, const float* bias, int32_t accumulate, void* stream) {
     MMF_REQUIRE(A && B && C, "sgemm: null operand");

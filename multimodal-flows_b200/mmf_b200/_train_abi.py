@@ -15,6 +15,7 @@ P, I32, I64, F = c_void_p, c_int32, c_int64, c_float
 
 SIGNATURES = {
     "mmf_tr_gemm": [P, I64, P, I64, P, I64, I32, I32, I32, P, I32, I32, P],
+    "mmf_tr_gemm_tn": [P, I64, P, I64, P, I64, I32, I32, I32, I32, P],
     "mmf_tr_sgemm": [P, I64, I64, P, I64, I64, P, I64, I32, I32, I32, P, I32, P],
     "mmf_tr_cast_transpose": [P, I64, I32, I32, I32, P, I64, P, I64, P, P],
     "mmf_tr_weights_transpose": [P, P, P, I32, I32, P],
@@ -85,6 +86,13 @@ class Ops:
         N = B.shape[0]
         assert B.shape[1] == K and tuple(C.shape) == (M, N) and A.stride(1) == 1 and B.stride(1) == 1 and C.stride(1) == 1
         _abi.check(self.L.mmf_tr_gemm(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, N, K, _p(bias), mode, ksplit, self._s()))
+
+    # C[M,N] += A^T B, A [K,M], B [K,N] row-major bf16
+    def gemm_tn(self, A, B, C, ksplit=1):
+        K, M = A.shape
+        N = B.shape[1]
+        assert B.shape[0] == K and tuple(C.shape) == (M, N) and A.stride(1) == 1 and B.stride(1) == 1 and C.stride(1) == 1
+        _abi.check(self.L.mmf_tr_gemm_tn(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, N, K, ksplit, self._s()))
 
     def sgemm(self, A, sam, sak, B, sbk, sbn, C, M, N, K, bias=None, accumulate=False):
         _abi.check(self.L.mmf_tr_sgemm(_p(A), sam, sak, _p(B), sbk, sbn, _p(C), C.stride(0) if C.dim() > 1 else N, M, N, K, _p(bias),

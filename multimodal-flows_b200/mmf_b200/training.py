@@ -182,15 +182,16 @@ class TrainEngine:
         return max(1, min(kb // 4, max(1, 296 // tiles)))
 
     def _lin_bwd(self, plan, dy16, x16, name, dx=None, dx_mode=1, dy_src=None):
-        """dy16 [M, N] bf16 (contiguous enough for TMA), x16 [M, K] bf16.  dW += dy^T x, db += colsum(dy), dx = dy W."""
-        ops, M, Mp = self.ops, plan.M, plan.Mp
+        """dy16 [M, N], x16 [M, K] bf16 row-major (column slices allowed).  dW += dy^T x (both operands read MN-major by the
+        tensor cores: no transposed copies), db += colsum(dy), dx = dy W.  dy_src: fp32 source that is first cast into dy16."""
+        ops = self.ops
         N, K = self.shape[name + ".weight"]
-        dyT = torch.empty(N, Mp, device=self.device, dtype=torch.bfloat16)
-        xT = torch.empty(K, Mp, device=self.device, dtype=torch.bfloat16)
-        src = dy16 if dy_src is None else dy_src
-        ops.cast_transpose(src, out=None if dy_src is None else dy16, outT=dyT, colsum=self.g(name + ".bias"))
-        ops.cast_transpose(x16, outT=xT)
-        ops.gemm(dyT[:, :M], xT[:, :M], self.g(name + ".weight"), None, 2, self._ksplit(plan, N, K))
+        db = self.g(name + ".bias")
+        if dy_src is not None:
+            ops.cast_transpose(dy_src, out=dy16, colsum=db)
+        elif db is not None:
+            ops.cast_transpose(dy16, colsum=db)
+        ops.gemm_tn(dy16, x16, self.g(name + ".weight"), self._ksplit(plan, N, K))
         if dx is not None:
             ops.gemm(dy16, self.wT16(name + ".weight"), dx, None, dx_mode)
 

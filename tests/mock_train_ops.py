@@ -27,6 +27,9 @@ class MockOps:
         else:
             C.copy_(r.to(C.dtype))
 
+    def gemm_tn(self, A, B, C, ksplit=1):
+        C += _f(A).T @ _f(B)
+
     def sgemm(self, A, sam, sak, B, sbk, sbn, C, M, N, K, bias=None, accumulate=False):
         a = torch.as_strided(A, (M, K), (sam, sak))
         b = torch.as_strided(B, (K, N), (sbk, sbn))

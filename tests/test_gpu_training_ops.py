@@ -70,6 +70,19 @@ def test_gemm_reduce_add_split_k(ops, M, N, K, ks):
     assert rel(C, want) < 2e-5, rel(C, want)
 
 
+@pytest.mark.parametrize("M,N,K,ks", [(384, 128, 13819, 32), (128, 256, 1000, 4), (512, 128, 130, 1), (256, 512, 5000, 100), (128, 128, 64, 1)])
+def test_gemm_tn_weight_gradient_from_row_major_operands(ops, M, N, K, ks):
+    """dW += dy^T x with dy [tokens, out], x [tokens, in] as they lie in memory (MN-major tcgen05 operands), column slices included"""
+    g = torch.Generator(device=DEV).manual_seed(K + 1)
+    dy, x = bf(torch.randn(K, M + 128, device=DEV, generator=g)), bf(torch.randn(K, N + 64, device=DEV, generator=g))
+    dyv, xv = dy[:, 128:], x[:, :N]
+    C0 = torch.randn(M, N, device=DEV, generator=g)
+    C = C0.clone()
+    ops.gemm_tn(dyv, xv, C, ks)
+    want = C0 + dyv.float().T @ xv.float()
+    assert rel(C, want) < 2e-5, rel(C, want)
+
+
 @pytest.mark.parametrize("f32", [True, False])
 def test_cast_transpose_colsum(ops, f32):
     g = torch.Generator(device=DEV).manual_seed(1)
