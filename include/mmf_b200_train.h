@@ -69,13 +69,25 @@ int mmf_tr_qkln_fwd(const void* qkv, int64_t ld, int32_t M, int32_t C, int32_t H
                     const float* kb, void* qn, void* kn, int64_t ldn, void* stream);
 int mmf_tr_qkln_bwd(void* dqkv, int64_t ldd, const void* qkv, int64_t ld, int32_t M, int32_t C, int32_t H, const float* qg, const float* kg,
                     float* dqg, float* dqb, float* dkg, float* dkb, void* stream);
-/* masked self-attention of whole jets, scale 1/sqrt(hs) (attention.py:53-74); P (bf16, H * sum_b n_b^2 elements, jet b at
- * p_off[b] * H) is kept for the backward call, which writes dqn | dkn | dv into dqkv [M, 3C] */
+/* masked self-attention of whole jets, scale 1/sqrt(hs) (attention.py:53-74), two kernel families:
+ *  (1) tensor cores (tcgen05): work items = runs of consecutive whole jets with at most 128 rows in total, items[i] = (first row,
+ *      rows) as int32 pairs; *n_items (device) of the grid_items launched CTAs work, the rest exit (fixed grids under CUDA graphs).
+ *      The forward call keeps 2 floats per (row, head) in stats [M, H, 2]; the backward call recomputes the probabilities from
+ *      them and writes dqn | dkn | dv into dqkv [M, 3C].  Jets of more than 128 particles are not in any item: they take
+ *  (2) CUDA cores: one CTA per (jet, head) for the jets of MORE than min_n particles (min_n = 0: all jets); P (bf16,
+ *      H * sum n_b^2 elements, jet b at p_off[b] * H) is kept for the backward call. */
+int mmf_tr_attn_tc_fwd(const void* qn, int64_t ldq, const void* kn, int64_t ldk, const void* v, int64_t ldv, int32_t M, int32_t C, int32_t hs,
+                       const int32_t* items, const int32_t* n_items, int32_t grid_items, const int32_t* row_jet, const int32_t* jet_off,
+                       float* stats, void* o, int64_t ldo, void* stream);
+int mmf_tr_attn_tc_bwd(const void* dO, int64_t lddo, const void* qn, int64_t ldq, const void* kn, int64_t ldk, const void* v, int64_t ldv,
+                       int32_t M, int32_t C, int32_t hs, const int32_t* items, const int32_t* n_items, int32_t grid_items,
+                       const int32_t* row_jet, const int32_t* jet_off, const float* stats, void* dqkv, int64_t ldd, void* stream);
 int mmf_tr_attn_fwd(const void* qn, int64_t ldq, const void* kn, int64_t ldk, const void* v, int64_t ldv, const int32_t* jet_off,
-                    const int64_t* p_off, int32_t B, int32_t H, int32_t hs, int32_t nmax, void* o, int64_t ldo, void* P, void* stream);
+                    const int64_t* p_off, int32_t B, int32_t H, int32_t hs, int32_t nmax, int32_t min_n, void* o, int64_t ldo, void* P,
+                    void* stream);
 int mmf_tr_attn_bwd(const void* dO, int64_t lddo, const void* o, int64_t ldo, const void* P, const void* qn, int64_t ldq, const void* kn,
                     int64_t ldk, const void* v, int64_t ldv, const int32_t* jet_off, const int64_t* p_off, int32_t B, int32_t H, int32_t hs,
-                    int32_t nmax, void* dqkv, int64_t ldd, int32_t C, void* stream);
+                    int32_t nmax, int32_t min_n, void* dqkv, int64_t ldd, int32_t C, void* stream);
 /* exact-erf GELU (nn.GELU(), utils/models.py:16) on n contiguous elements (bf16, or fp32 if f32) and its gradient */
 int mmf_tr_gelu_fwd(const void* z, void* h, int64_t n, int32_t f32, void* stream);
 int mmf_tr_gelu_bwd(const void* dh, const void* z, void* dz, int64_t n, int32_t f32, void* stream);

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "mmf_b200", "libmmf_b200.so")
-SOURCES = ["kernels_tc.cu", "kernels_simt.cu", "kernels_train.cu", "kernels_traingemm.cu", "kernels_trainops.cu", "train_api.cu", "kernels_epic.cu", "epic_model.cu", "kernels_tftile.cu", "kernels_tftile.cu@trace",
+SOURCES = ["kernels_tc.cu", "kernels_simt.cu", "kernels_train.cu", "kernels_traingemm.cu", "kernels_trainops.cu", "kernels_trainattn.cu", "train_api.cu", "kernels_epic.cu", "epic_model.cu", "kernels_tftile.cu", "kernels_tftile.cu@trace",
            "tftile_model.cu", "model.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [*os.environ.get("MMF_EXTRA_NVCC", "").split(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -457,13 +457,13 @@ __device__ __forceinline__ float bf_elem(const uint32_t* row, int d) {
 template <int HS>
 __global__ void __launch_bounds__(256) tr_attn_fwd_kernel(const bf16* __restrict__ qn, long long ldq, const bf16* __restrict__ kn, long long ldk,
                                                           const bf16* __restrict__ v, long long ldv, const int* __restrict__ jet_off,
-                                                          const long long* __restrict__ p_off, int H, float scale, bf16* __restrict__ o,
-                                                          long long ldo, bf16* __restrict__ P) {
+                                                          const long long* __restrict__ p_off, int H, float scale, int min_n,
+                                                          bf16* __restrict__ o, long long ldo, bf16* __restrict__ P) {
     extern __shared__ uint32_t sm[];
     constexpr int PW = HS / 2 + 1;
     const int jet = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
     const int r0 = jet_off[jet], n = jet_off[jet + 1] - r0;
-    if (n <= 0) return;
+    if (n <= min_n) return;
     uint32_t* Qs = sm;
     uint32_t* Ks = Qs + n * PW;
     uint32_t* Vs = Ks + n * PW;
@@ -507,12 +507,12 @@ __global__ void __launch_bounds__(256) tr_attn_bwd_kernel(const bf16* __restrict
                                                           const bf16* __restrict__ P, const bf16* __restrict__ qn, long long ldq,
                                                           const bf16* __restrict__ kn, long long ldk, const bf16* __restrict__ v, long long ldv,
                                                           const int* __restrict__ jet_off, const long long* __restrict__ p_off, int H,
-                                                          float scale, bf16* __restrict__ dqkv, long long ldd, int C) {
+                                                          float scale, int min_n, bf16* __restrict__ dqkv, long long ldd, int C) {
     extern __shared__ uint32_t sm[];
     constexpr int PW = HS / 2 + 1;
     const int jet = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const int r0 = jet_off[jet], n = jet_off[jet + 1] - r0;
-    if (n <= 0) return;
+    if (n <= min_n) return;
     uint32_t* Qs = sm;
     uint32_t* Ks = Qs + n * PW;
     uint32_t* Vs = Ks + n * PW;
@@ -969,7 +969,7 @@ static int attn_configure(K kernel, int bytes) {
 }
 
 int launch_tr_attn_fwd(const bf16* qn, long long ldq, const bf16* kn, long long ldk, const bf16* v, long long ldv, const int* jet_off,
-                       const long long* p_off, int B, int H, int hs, int nmax, bf16* o, long long ldo, bf16* P, cudaStream_t s) {
+                       const long long* p_off, int B, int H, int hs, int nmax, int min_n, bf16* o, long long ldo, bf16* P, cudaStream_t s) {
     if (B <= 0 || nmax <= 0) return 0;
     MMF_REQUIRE(hs == 32 || hs == 64, "attention: head size 32 or 64");
     MMF_REQUIRE(nmax <= 176, "attention: jets of up to 176 particles");
@@ -977,10 +977,10 @@ int launch_tr_attn_fwd(const bf16* qn, long long ldq, const bf16* kn, long long 
     const float scale = 1.0f / sqrtf(static_cast<float>(hs));
     if (hs == 32) {
         if (attn_configure<0>(tr_attn_fwd_kernel<32>, bytes)) return 1;
-        tr_attn_fwd_kernel<32><<<dim3(B, H), 256, bytes, s>>>(qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, o, ldo, P);
+        tr_attn_fwd_kernel<32><<<dim3(B, H), 256, bytes, s>>>(qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, min_n, o, ldo, P);
     } else {
         if (attn_configure<1>(tr_attn_fwd_kernel<64>, bytes)) return 1;
-        tr_attn_fwd_kernel<64><<<dim3(B, H), 256, bytes, s>>>(qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, o, ldo, P);
+        tr_attn_fwd_kernel<64><<<dim3(B, H), 256, bytes, s>>>(qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, min_n, o, ldo, P);
     }
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
@@ -988,7 +988,7 @@ int launch_tr_attn_fwd(const bf16* qn, long long ldq, const bf16* kn, long long 
 
 int launch_tr_attn_bwd(const bf16* dO, long long lddo, const bf16* o, long long ldo, const bf16* P, const bf16* qn, long long ldq,
                        const bf16* kn, long long ldk, const bf16* v, long long ldv, const int* jet_off, const long long* p_off, int B, int H,
-                       int hs, int nmax, bf16* dqkv, long long ldd, int C, cudaStream_t s) {
+                       int hs, int nmax, int min_n, bf16* dqkv, long long ldd, int C, cudaStream_t s) {
     if (B <= 0 || nmax <= 0) return 0;
     MMF_REQUIRE(hs == 32 || hs == 64, "attention: head size 32 or 64");
     MMF_REQUIRE(nmax <= 176, "attention: jets of up to 176 particles");
@@ -996,10 +996,10 @@ int launch_tr_attn_bwd(const bf16* dO, long long lddo, const bf16* o, long long 
     const float scale = 1.0f / sqrtf(static_cast<float>(hs));
     if (hs == 32) {
         if (attn_configure<2>(tr_attn_bwd_kernel<32>, bytes)) return 1;
-        tr_attn_bwd_kernel<32><<<dim3(B, H), 256, bytes, s>>>(dO, lddo, o, ldo, P, qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, dqkv, ldd, C);
+        tr_attn_bwd_kernel<32><<<dim3(B, H), 256, bytes, s>>>(dO, lddo, o, ldo, P, qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, min_n, dqkv, ldd, C);
     } else {
         if (attn_configure<3>(tr_attn_bwd_kernel<64>, bytes)) return 1;
-        tr_attn_bwd_kernel<64><<<dim3(B, H), 256, bytes, s>>>(dO, lddo, o, ldo, P, qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, dqkv, ldd, C);
+        tr_attn_bwd_kernel<64><<<dim3(B, H), 256, bytes, s>>>(dO, lddo, o, ldo, P, qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, min_n, dqkv, ldd, C);
     }
     MMF_CUDA_OK(cudaGetLastError());
     return 0;

@@ -63,12 +63,31 @@ int launch_tr_qkln_fwd(const bf16* qkv, long long ld, int M, int C, int H, const
 int launch_tr_qkln_bwd(bf16* dqkv, long long ldd, const bf16* qkv, long long ld, int M, int C, int H, const float* qg, const float* kg,
                        float* dqg, float* dqb, float* dkg, float* dkb, cudaStream_t s);
 
-// masked self-attention of whole jets (reference attention.py:53-74): one CTA per (jet, head); P is kept for the backward pass
+// masked self-attention of whole jets (reference attention.py:53-74) on CUDA cores: one CTA per (jet, head); P is kept for the
+// backward pass; jets of at most min_n particles are skipped (they run on the tensor-core kernels below)
 int launch_tr_attn_fwd(const bf16* qn, long long ldq, const bf16* kn, long long ldk, const bf16* v, long long ldv, const int* jet_off,
-                       const long long* p_off, int B, int H, int hs, int nmax, bf16* o, long long ldo, bf16* P, cudaStream_t s);
+                       const long long* p_off, int B, int H, int hs, int nmax, int min_n, bf16* o, long long ldo, bf16* P, cudaStream_t s);
 int launch_tr_attn_bwd(const bf16* dO, long long lddo, const bf16* o, long long ldo, const bf16* P, const bf16* qn, long long ldq,
                        const bf16* kn, long long ldk, const bf16* v, long long ldv, const int* jet_off, const long long* p_off, int B,
-                       int H, int hs, int nmax, bf16* dqkv, long long ldd, int C, cudaStream_t s);
+                       int H, int hs, int nmax, int min_n, bf16* dqkv, long long ldd, int C, cudaStream_t s);
+
+// the same on tensor cores for tiles of whole jets with at most 128 rows in total (kernels_trainattn.cu); items[i] = (first row,
+// rows); CTAs with blockIdx.x >= *n_items exit (fixed launch grids under CUDA graphs); stats [M, H, 2] fp32 replaces P
+struct TrAttnTcArgs {
+    const int2* items;
+    const int* n_items;
+    const int* row_jet;
+    const int* jet_off;
+    float* stats;
+    bf16* o; long long ldo;          // forward output
+    bf16* dqkv; long long ldd;       // backward output: dq | dk | dv sections of width C
+    int H, C;
+    float scale, scale_log2e;
+};
+int launch_tr_attn_tc_fwd(const bf16* qn, long long ldq, const bf16* kn, long long ldk, const bf16* v, long long ldv, int M, int C, int hs,
+                          int grid_items, TrAttnTcArgs a, cudaStream_t s);
+int launch_tr_attn_tc_bwd(const bf16* dO, long long lddo, const bf16* qn, long long ldq, const bf16* kn, long long ldk, const bf16* v,
+                          long long ldv, int M, int C, int hs, int grid_items, TrAttnTcArgs a, cudaStream_t s);
 
 int launch_tr_gelu_fwd(const void* z, void* h, long long n, int f32, cudaStream_t s);
 int launch_tr_gelu_bwd(const void* dh, const void* z, void* dz, long long n, int f32, cudaStream_t s);

@@ -92,15 +92,35 @@ int mmf_tr_qkln_bwd(void* dqkv, int64_t ldd, const void* qkv, int64_t ld, int32_
 }
 
 int mmf_tr_attn_fwd(const void* qn, int64_t ldq, const void* kn, int64_t ldk, const void* v, int64_t ldv, const int32_t* jet_off,
-                    const int64_t* p_off, int32_t B, int32_t H, int32_t hs, int32_t nmax, void* o, int64_t ldo, void* P, void* stream) {
+                    const int64_t* p_off, int32_t B, int32_t H, int32_t hs, int32_t nmax, int32_t min_n, void* o, int64_t ldo, void* P,
+                    void* stream) {
     return launch_tr_attn_fwd(CBF(qn), ldq, CBF(kn), ldk, CBF(v), ldv, jet_off, reinterpret_cast<const long long*>(p_off), B, H, hs, nmax,
-                              BF(o), ldo, BF(P), S_(stream));
+                              min_n, BF(o), ldo, BF(P), S_(stream));
 }
 int mmf_tr_attn_bwd(const void* dO, int64_t lddo, const void* o, int64_t ldo, const void* P, const void* qn, int64_t ldq, const void* kn,
                     int64_t ldk, const void* v, int64_t ldv, const int32_t* jet_off, const int64_t* p_off, int32_t B, int32_t H, int32_t hs,
-                    int32_t nmax, void* dqkv, int64_t ldd, int32_t C, void* stream) {
+                    int32_t nmax, int32_t min_n, void* dqkv, int64_t ldd, int32_t C, void* stream) {
     return launch_tr_attn_bwd(CBF(dO), lddo, CBF(o), ldo, CBF(P), CBF(qn), ldq, CBF(kn), ldk, CBF(v), ldv, jet_off,
-                              reinterpret_cast<const long long*>(p_off), B, H, hs, nmax, BF(dqkv), ldd, C, S_(stream));
+                              reinterpret_cast<const long long*>(p_off), B, H, hs, nmax, min_n, BF(dqkv), ldd, C, S_(stream));
+}
+
+int mmf_tr_attn_tc_fwd(const void* qn, int64_t ldq, const void* kn, int64_t ldk, const void* v, int64_t ldv, int32_t M, int32_t C, int32_t hs,
+                       const int32_t* items, const int32_t* n_items, int32_t grid_items, const int32_t* row_jet, const int32_t* jet_off,
+                       float* stats, void* o, int64_t ldo, void* stream) {
+    MMF_REQUIRE(M == 0 || (qn && kn && v && items && n_items && row_jet && jet_off && stats && o), "attention: null argument");
+    TrAttnTcArgs a{};
+    a.items = reinterpret_cast<const int2*>(items); a.n_items = n_items; a.row_jet = row_jet; a.jet_off = jet_off; a.stats = stats;
+    a.o = BF(o); a.ldo = ldo;
+    return launch_tr_attn_tc_fwd(CBF(qn), ldq, CBF(kn), ldk, CBF(v), ldv, M, C, hs, grid_items, a, S_(stream));
+}
+int mmf_tr_attn_tc_bwd(const void* dO, int64_t lddo, const void* qn, int64_t ldq, const void* kn, int64_t ldk, const void* v, int64_t ldv,
+                       int32_t M, int32_t C, int32_t hs, const int32_t* items, const int32_t* n_items, int32_t grid_items,
+                       const int32_t* row_jet, const int32_t* jet_off, const float* stats, void* dqkv, int64_t ldd, void* stream) {
+    MMF_REQUIRE(M == 0 || (dO && qn && kn && v && items && n_items && row_jet && jet_off && stats && dqkv), "attention: null argument");
+    TrAttnTcArgs a{};
+    a.items = reinterpret_cast<const int2*>(items); a.n_items = n_items; a.row_jet = row_jet; a.jet_off = jet_off;
+    a.stats = const_cast<float*>(stats); a.dqkv = BF(dqkv); a.ldd = ldd;
+    return launch_tr_attn_tc_bwd(CBF(dO), lddo, CBF(qn), ldq, CBF(kn), ldk, CBF(v), ldv, M, C, hs, grid_items, a, S_(stream));
 }
 
 int mmf_tr_gelu_fwd(const void* z, void* h, int64_t n, int32_t f32, void* stream) { return launch_tr_gelu_fwd(z, h, n, f32, S_(stream)); }

@@ -29,8 +29,10 @@ SIGNATURES = {
     "mmf_tr_ln_bwd": [P, I64, P, I64, P, I64, P, P, P, I32, I32, P, I64, I32, P, P, P],
     "mmf_tr_qkln_fwd": [P, I64, I32, I32, I32, P, P, P, P, P, P, I64, P],
     "mmf_tr_qkln_bwd": [P, I64, P, I64, I32, I32, I32, P, P, P, P, P, P, P],
-    "mmf_tr_attn_fwd": [P, I64, P, I64, P, I64, P, P, I32, I32, I32, I32, P, I64, P, P],
-    "mmf_tr_attn_bwd": [P, I64, P, I64, P, P, I64, P, I64, P, I64, P, P, I32, I32, I32, I32, P, I64, I32, P],
+    "mmf_tr_attn_fwd": [P, I64, P, I64, P, I64, P, P, I32, I32, I32, I32, I32, P, I64, P, P],
+    "mmf_tr_attn_bwd": [P, I64, P, I64, P, P, I64, P, I64, P, I64, P, P, I32, I32, I32, I32, I32, P, I64, I32, P],
+    "mmf_tr_attn_tc_fwd": [P, I64, P, I64, P, I64, I32, I32, I32, P, P, I32, P, P, P, P, I64, P],
+    "mmf_tr_attn_tc_bwd": [P, I64, P, I64, P, I64, P, I64, I32, I32, I32, P, P, I32, P, P, P, P, I64, P],
     "mmf_tr_gelu_fwd": [P, P, I64, I32, P],
     "mmf_tr_gelu_bwd": [P, P, P, I64, I32, P],
     "mmf_tr_add": [P, I64, P, I64, P, I64, P, I64, P, I32, I32, P],
@@ -143,13 +145,26 @@ class Ops:
         _abi.check(self.L.mmf_tr_qkln_bwd(_p(dqkv), dqkv.stride(0), _p(qkv), qkv.stride(0), qkv.shape[0], C, H, _p(qg), _p(kg), _p(dqg),
                                           _p(dqb), _p(dkg), _p(dkb), self._s()))
 
-    def attn_fwd(self, qn, kn, v, jet_off, p_off, B, H, hs, nmax, o, P_):
+    def attn_fwd(self, qn, kn, v, jet_off, p_off, B, H, hs, nmax, o, P_, min_n=0):
         _abi.check(self.L.mmf_tr_attn_fwd(_p(qn), qn.stride(0), _p(kn), kn.stride(0), _p(v), v.stride(0), _p(jet_off), _p(p_off), B, H, hs,
-                                          nmax, _p(o), o.stride(0), _p(P_), self._s()))
+                                          nmax, min_n, _p(o), o.stride(0), _p(P_), self._s()))
 
-    def attn_bwd(self, dO, o, P_, qn, kn, v, jet_off, p_off, B, H, hs, nmax, dqkv, C):
+    def attn_bwd(self, dO, o, P_, qn, kn, v, jet_off, p_off, B, H, hs, nmax, dqkv, C, min_n=0):
         _abi.check(self.L.mmf_tr_attn_bwd(_p(dO), dO.stride(0), _p(o), o.stride(0), _p(P_), _p(qn), qn.stride(0), _p(kn), kn.stride(0),
-                                          _p(v), v.stride(0), _p(jet_off), _p(p_off), B, H, hs, nmax, _p(dqkv), dqkv.stride(0), C, self._s()))
+                                          _p(v), v.stride(0), _p(jet_off), _p(p_off), B, H, hs, nmax, min_n, _p(dqkv), dqkv.stride(0), C,
+                                          self._s()))
+
+    # tensor-core attention over items of whole jets (<= 128 rows each)
+    def attn_tc_fwd(self, qn, kn, v, hs, items, n_items, grid_items, row_jet, jet_off, stats, o):
+        M, C = qn.shape
+        _abi.check(self.L.mmf_tr_attn_tc_fwd(_p(qn), qn.stride(0), _p(kn), kn.stride(0), _p(v), v.stride(0), M, C, hs, _p(items), _p(n_items),
+                                             grid_items, _p(row_jet), _p(jet_off), _p(stats), _p(o), o.stride(0), self._s()))
+
+    def attn_tc_bwd(self, dO, qn, kn, v, hs, items, n_items, grid_items, row_jet, jet_off, stats, dqkv):
+        M, C = qn.shape
+        _abi.check(self.L.mmf_tr_attn_tc_bwd(_p(dO), dO.stride(0), _p(qn), qn.stride(0), _p(kn), kn.stride(0), _p(v), v.stride(0), M, C, hs,
+                                             _p(items), _p(n_items), grid_items, _p(row_jet), _p(jet_off), _p(stats), _p(dqkv),
+                                             dqkv.stride(0), self._s()))
 
     def gelu_fwd(self, z, h):
         assert z.is_contiguous() and h.is_contiguous()

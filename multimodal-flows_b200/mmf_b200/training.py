@@ -41,15 +41,38 @@ class _Plan:
         self.Mp = (self.M + 63) // 64 * 64
         self.h_jet_off = np.zeros(self.B + 1, np.int32)
         np.cumsum(n, out=self.h_jet_off[1:])
+        # tensor-core attention works on runs of consecutive whole jets with at most 128 rows; larger jets take the CUDA-core
+        # kernels (their probabilities are kept: p_off counts those jets only)
+        big = n > 128
+        self.has_big = bool(big.any())
         self.h_p_off = np.zeros(self.B + 1, np.int64)
-        np.cumsum(n * n, out=self.h_p_off[1:])
+        np.cumsum(np.where(big, n * n, 0), out=self.h_p_off[1:])
         self.sum_n2 = int(self.h_p_off[-1])
+        items, start, rows = [], 0, 0
+        for b in range(self.B):
+            nb = int(n[b])
+            if nb == 0:
+                continue
+            if nb > 128 or rows + nb > 128:
+                if rows:
+                    items.append((start, rows))
+                rows = 0
+            if nb <= 128:
+                if rows == 0:
+                    start = int(self.h_jet_off[b])
+                rows += nb
+        if rows:
+            items.append((start, rows))
+        self.h_items = np.asarray(items, np.int32).reshape(-1, 2)
+        self.grid_items = len(items)
         self.h_row_slot = np.flatnonzero(m.reshape(-1)).astype(np.int32)
         self.h_row_jet = np.repeat(np.arange(self.B, dtype=np.int32), n)
         up = lambda a: torch.from_numpy(a).to(device, non_blocking=True)
         self.row_slot = up(self.h_row_slot)
         if upload:
             self.jet_off, self.p_off, self.row_jet = up(self.h_jet_off), up(self.h_p_off), up(self.h_row_jet)
+            self.items = up(self.h_items if len(items) else np.zeros((1, 2), np.int32))
+            self.n_items = up(np.asarray([len(items)], np.int32))
 
 
 class _GraphSlot:
@@ -63,8 +86,10 @@ class _GraphSlot:
         z = lambda *s, dt=torch.float32: torch.zeros(*s, device=device, dtype=dt)
         self.jet_off, self.p_off, self.row_jet = z(B + 1, dt=torch.int32), z(B + 1, dt=torch.int64), z(rows, dt=torch.int32)
         self.xs, self.tg, self.ks, self.k1p, self.t = z(rows, 3), z(rows, 3), z(rows, dt=torch.int32), z(rows, dt=torch.int32), z(B)
+        self.items, self.n_items, self.grid_items, self.has_big = z(B, 2, dt=torch.int32), z(1, dt=torch.int32), B, True
         self.pin = [torch.zeros(B + 1, dtype=torch.int32).pin_memory(), torch.zeros(B + 1, dtype=torch.int64).pin_memory(),
-                    torch.zeros(rows, dtype=torch.int32).pin_memory()]
+                    torch.zeros(rows, dtype=torch.int32).pin_memory(), torch.zeros(B, 2, dtype=torch.int32).pin_memory(),
+                    torch.zeros(1, dtype=torch.int32).pin_memory()]
         self.graph, self.out5, self.busy = None, None, None
 
     def load(self, plan: _Plan):
@@ -73,6 +98,10 @@ class _GraphSlot:
         self.pin[0].copy_(torch.from_numpy(plan.h_jet_off))
         self.pin[1].copy_(torch.from_numpy(plan.h_p_off))
         self.pin[2][: plan.M].copy_(torch.from_numpy(plan.h_row_jet))
+        self.pin[3][: plan.grid_items].copy_(torch.from_numpy(plan.h_items))
+        self.pin[4][0] = plan.grid_items
+        self.items.copy_(self.pin[3], non_blocking=True)
+        self.n_items.copy_(self.pin[4], non_blocking=True)
         self.jet_off.copy_(self.pin[0], non_blocking=True)
         self.p_off.copy_(self.pin[1], non_blocking=True)
         self.row_jet[: plan.M].copy_(self.pin[2][: plan.M], non_blocking=True)
@@ -213,8 +242,12 @@ class TrainEngine:
         else:
             s["qn"], s["kn"] = s["qkv"][:, :C], s["qkv"][:, C:2 * C]
         s["o"] = torch.zeros(M, C, **bf) if plan.padded else torch.empty(M, C, **bf)      # rows of no jet are never written
-        s["P"] = torch.empty(max(plan.sum_n2 * H, 1), **bf)
-        ops.attn_fwd(s["qn"], s["kn"], s["qkv"][:, 2 * C:], plan.jet_off, plan.p_off, plan.B, H, hs, plan.nmax, s["o"], s["P"])
+        s["stats"] = torch.empty(M, H, 2, device=dev)
+        ops.attn_tc_fwd(s["qn"], s["kn"], s["qkv"][:, 2 * C:], hs, plan.items, plan.n_items, plan.grid_items, plan.row_jet, plan.jet_off,
+                        s["stats"], s["o"])
+        if plan.has_big:                                      # jets of 129 ... 150 particles: CUDA-core kernels, probabilities kept
+            s["P"] = torch.empty(max(plan.sum_n2 * H, 1), **bf)
+            ops.attn_fwd(s["qn"], s["kn"], s["qkv"][:, 2 * C:], plan.jet_off, plan.p_off, plan.B, H, hs, plan.nmax, s["o"], s["P"], min_n=128)
         y = torch.empty(M, C, device=dev)
         self._lin_fwd(s["o"], pre + ".attn.c_proj", y, 1)
         ops.add(R1, Rin, y)
@@ -244,7 +277,11 @@ class TrainEngine:
         do = torch.empty(M, C, **bf)
         self._lin_bwd(plan, G16, s["o"], pre + ".attn.c_proj", dx=do, dx_mode=0, dy_src=G)
         dqkv = torch.zeros(M, 3 * C, **bf) if plan.padded else torch.empty(M, 3 * C, **bf)
-        ops.attn_bwd(do, s["o"], s["P"], s["qn"], s["kn"], s["qkv"][:, 2 * C:], plan.jet_off, plan.p_off, plan.B, H, hs, plan.nmax, dqkv, C)
+        ops.attn_tc_bwd(do, s["qn"], s["kn"], s["qkv"][:, 2 * C:], hs, plan.items, plan.n_items, plan.grid_items, plan.row_jet, plan.jet_off,
+                        s["stats"], dqkv)
+        if plan.has_big:
+            ops.attn_bwd(do, s["o"], s["P"], s["qn"], s["kn"], s["qkv"][:, 2 * C:], plan.jet_off, plan.p_off, plan.B, H, hs, plan.nmax, dqkv, C,
+                         min_n=128)
         if self.cfg.qk_layernorm:
             ops.qkln_bwd(dqkv, s["qkv"], C, H, self.p(pre + ".attn.q_layernorm.weight"), self.p(pre + ".attn.k_layernorm.weight"),
                          self.g(pre + ".attn.q_layernorm.weight"), self.g(pre + ".attn.q_layernorm.bias"),

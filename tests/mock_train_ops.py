@@ -135,11 +135,43 @@ class MockOps:
     def _heads(self, t, r, n, H, hs):
         return _f(t[r]).view(n, H, hs).transpose(0, 1)
 
-    def attn_fwd(self, qn, kn, v, jet_off, p_off, B, H, hs, nmax, o, P_):
+    def attn_tc_fwd(self, qn, kn, v, hs, items, n_items, grid_items, row_jet, jet_off, stats, o):
+        H, c = qn.shape[1] // hs, math.log2(math.e) / math.sqrt(hs)
+        for r0, rows in items[: int(n_items[0])].tolist():
+            jets = sorted(set(row_jet[r0: r0 + rows].tolist()))
+            assert sum(int(jet_off[b + 1] - jet_off[b]) for b in jets) == rows <= 128 and int(jet_off[jets[0]]) == r0
+            for b in jets:
+                r = slice(int(jet_off[b]), int(jet_off[b + 1]))
+                n = r.stop - r.start
+                q, k, vv = self._heads(qn, r, n, H, hs), self._heads(kn, r, n, H, hs), self._heads(v, r, n, H, hs)
+                sc = q @ k.transpose(1, 2) * c
+                m = sc.max(-1, keepdim=True).values
+                e = torch.exp2(sc - m)
+                inv = 1.0 / e.sum(-1, keepdim=True)
+                o[r] = ((e * inv) @ vv).transpose(0, 1).reshape(n, H * hs).to(o.dtype)
+                stats[r, :, 0] = m[..., 0].T
+                stats[r, :, 1] = inv[..., 0].T
+
+    def attn_tc_bwd(self, dO, qn, kn, v, hs, items, n_items, grid_items, row_jet, jet_off, stats, dqkv):
+        C = qn.shape[1]
+        H, c = C // hs, math.log2(math.e) / math.sqrt(hs)
+        for r0, rows in items[: int(n_items[0])].tolist():
+            for b in sorted(set(row_jet[r0: r0 + rows].tolist())):
+                r = slice(int(jet_off[b]), int(jet_off[b + 1]))
+                n = r.stop - r.start
+                q, k, vv, do = (self._heads(t, r, n, H, hs) for t in (qn, kn, v, dO))
+                p = torch.exp2(q @ k.transpose(1, 2) * c - stats[r, :, 0].T[..., None]) * stats[r, :, 1].T[..., None]
+                dp = do @ vv.transpose(1, 2)
+                ds = p * (dp - (p * dp).sum(-1, keepdim=True)) / math.sqrt(hs)
+                pb, dsb = p.to(torch.bfloat16).float(), ds.to(torch.bfloat16).float()
+                for w, t in enumerate((dsb @ k, dsb.transpose(1, 2) @ q, pb.transpose(1, 2) @ do)):
+                    dqkv[r, w * C:(w + 1) * C] = t.transpose(0, 1).reshape(n, C).to(dqkv.dtype)
+
+    def attn_fwd(self, qn, kn, v, jet_off, p_off, B, H, hs, nmax, o, P_, min_n=0):
         for b in range(B):
             r0, r1 = int(jet_off[b]), int(jet_off[b + 1])
             n = r1 - r0
-            if n == 0:
+            if n <= min_n:
                 continue
             r = slice(r0, r1)
             q, k, vv = self._heads(qn, r, n, H, hs), self._heads(kn, r, n, H, hs), self._heads(v, r, n, H, hs)
@@ -148,11 +180,11 @@ class MockOps:
             base = int(p_off[b]) * H
             P_[base: base + H * n * n] = p.to(P_.dtype).flatten()
 
-    def attn_bwd(self, dO, o, P_, qn, kn, v, jet_off, p_off, B, H, hs, nmax, dqkv, C):
+    def attn_bwd(self, dO, o, P_, qn, kn, v, jet_off, p_off, B, H, hs, nmax, dqkv, C, min_n=0):
         for b in range(B):
             r0, r1 = int(jet_off[b]), int(jet_off[b + 1])
             n = r1 - r0
-            if n == 0:
+            if n <= min_n:
                 continue
             r = slice(r0, r1)
             q, k, vv, do, oo = (self._heads(t, r, n, H, hs) for t in (qn, kn, v, dO, o))

@@ -1,6 +1,7 @@
 """Operators of the training step (include/mmf_b200_train.h) one by one against plain fp32 torch on the same inputs.
 Tolerances: fp32 kernels 1e-5 relative; kernels with bf16 operands / outputs are compared with torch evaluated on the SAME
 bf16-rounded operands, so what remains is accumulation order and the bf16 rounding of the result (2^-8 relative)."""
+import numpy as np
 import pytest
 import torch
 
@@ -328,3 +329,40 @@ def test_weights_transpose_jobs(ops):
     ops.weights_transpose(P, PT, jobs, len(shapes), t0)
     for s, o in zip(shapes, offs):
         assert torch.equal(PT[o:o + s[0] * s[1]].view(s[1], s[0]), bf(P[o:o + s[0] * s[1]].view(s).T))
+
+
+@pytest.mark.parametrize("hs,H", [(32, 4), (64, 4)])
+def test_tensor_core_attention_forward_backward(ops, hs, H):
+    """tcgen05 attention over items of whole jets (block-diagonal inside a 128-row tile) against torch SDPA and its autograd,
+    jet by jet; a jet of more than 128 particles in the batch is left to the CUDA-core kernels (its rows are not touched)."""
+    from mmf_b200 import synthetic
+    from mmf_b200.training import _Plan
+    g = torch.Generator(device=DEV).manual_seed(hs + 1)
+    ns = [3, 100, 1, 64, 128, 17, 60, 50, 140, 2, 127, 5, 121]
+    plan = _Plan(synthetic.prefix_masks(torch.tensor(ns)), torch.device(DEV))
+    assert plan.has_big and plan.h_items.tolist() == [[0, 104], [104, 64], [168, 128], [296, 127], [563, 2], [565, 127], [692, 126]]
+    M, C = plan.M, hs * H
+    qn, kn = bf(torch.randn(M, C, device=DEV, generator=g)), bf(torch.randn(M, C, device=DEV, generator=g))
+    qkv = bf(torch.randn(M, 3 * C, device=DEV, generator=g))
+    v = qkv[:, 2 * C:]
+    o = torch.full((M, C), 7.0, device=DEV, dtype=torch.bfloat16)
+    stats = torch.zeros(M, H, 2, device=DEV)
+    ops.attn_tc_fwd(qn, kn, v, hs, plan.items, plan.n_items, plan.grid_items + 3, plan.row_jet, plan.jet_off, stats, o)
+    qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (qn, kn, v))
+    outs, off = [], plan.h_jet_off
+    for b, n in enumerate(ns):
+        r = slice(int(off[b]), int(off[b + 1]))
+        qq, kk, vv = (t[r].view(n, H, hs).transpose(0, 1) for t in (qf, kf, vf))
+        outs.append(torch.nn.functional.scaled_dot_product_attention(qq, kk, vv).transpose(0, 1).reshape(n, C))
+    want = torch.cat(outs)
+    small = torch.tensor(np.repeat(np.array(ns) <= 128, ns), device=DEV)
+    assert rel(o[small].float(), want[small]) < 4e-3, rel(o[small].float(), want[small])
+    assert bool((o[~small] == 7.0).all())
+    dO = bf(torch.randn(M, C, device=DEV, generator=g))
+    want.backward(dO.float())
+    dqkv = torch.full((M, 3 * C), 7.0, device=DEV, dtype=torch.bfloat16)
+    ops.attn_tc_bwd(dO, qn, kn, v, hs, plan.items, plan.n_items, plan.grid_items + 3, plan.row_jet, plan.jet_off, stats, dqkv)
+    assert bool((dqkv[~small] == 7.0).all())
+    for w, ref in enumerate((qf.grad, kf.grad, vf.grad)):
+        got = dqkv[:, w * C:(w + 1) * C][small].float()
+        assert rel(got, ref[small]) < 1.2e-2, (w, rel(got, ref[small]))

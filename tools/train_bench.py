@@ -16,7 +16,7 @@ cfg = make_config(model, lr=1e-3)
 bridge = MultiModalFlowBridge(cfg)
 bridge.model.load_state_dict(synthetic.make_state_dict(cfg, "wide", 0))
 bridge = bridge.to(dev)
-eng = bridge.configure_training(lr=1e-3)
+eng = bridge.configure_training(lr=1e-3, use_graphs=not (os.environ.get('MMF_TRAIN_EAGER') or os.environ.get('MMF_TRAIN_PROFILE')))
 batch = synthetic.training_batch(B)
 batch.source, batch.target = batch.source.to(dev), batch.target.to(dev)
 
@@ -53,6 +53,21 @@ fl = {"ParticleFormer": lambda n: 10630656 * n + 65536 + 11264 * n * n, "FusedPa
 flops = 3.0 * float(sum(fl(int(v)) for v in n))
 res = {"model": model, "jets": B, "rows": int(eng.last_plan.M), "ms_per_step": ms, "host_ms_per_step": 1e3 * t_host / steps, "jets_per_s": B / ms * 1e3,
        "launches_per_step": (eng.ops.launches - l0) / steps, "algorithmic_tflops": flops / ms / 1e9, "loss": float(out[0])}
+if eng.use_graphs:
+    slot = next(iter(eng._slots.values()))
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        slot.graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    res["graph_replay_ms"] = e0.elapsed_time(e1) / steps
+    e0.record()
+    for _ in range(steps):
+        eng.optimizer_step()
+    e1.record()
+    torch.cuda.synchronize()
+    res["optimizer_ms"] = e0.elapsed_time(e1) / steps
 if prof:
     res["ops_ms_per_step"] = {k: round(sum(a.elapsed_time(b) for a, b in v) / steps, 4) for k, v in sorted(prof.items())}
     res["ops_calls_per_step"] = {k: len(v) / steps for k, v in sorted(prof.items())}
