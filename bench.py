@@ -241,7 +241,7 @@ def run_reference_arm(args, rank):
     t0 = time.perf_counter()
     value, per_step, kind, sample = cpu_reference_measure(args, cfg, sd, args.steps, max(args.warmup, 0))
     wall = time.perf_counter() - t0
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": metric_name(args), "value": value, "unit": "jets/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -249,7 +249,7 @@ def run_reference_arm(args, rank):
                    "step": f"one step = the whole batch for {max(2, min(args.ref_sample_timesteps, args.timesteps))} of the {args.timesteps} timesteps (bounded sample)"},
         "cpu_baseline": {"value": value, "unit": "jets/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "jets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def timed_generate(nm, src_dev, ts, dt, cfg, steps, warmup, flush, epic):
@@ -548,8 +548,23 @@ def observables_roofline(peaks, dev):
             "jets_per_s": B / (ms * 1e-3)}
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's original stdout; everything else that writes to file descriptor 1 (NCCL prints
+    its version banner there from C code, whatever NCCL_DEBUG_FILE says) has been pointed at stderr by main()."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
     args = parse_args()
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.cpu_sample_jets <= 0:
         args.cpu_sample_jets = args.batch
     args.cpu_sample_timesteps = max(1, min(args.cpu_sample_timesteps, args.timesteps))
@@ -759,7 +774,7 @@ def main():
             rate, s_per_ts = cpu_port_rate(args, cfg, sd, args.batch, S, device=str(dev))
             line["gpu_eager_baseline"] = {"value": rate, "unit": "jets/s", "kind": "port on cuda (oracle/mmf_oracle.py, eager torch fp32, TF32 off)",
                                           "sample": f"the whole batch of {args.batch} jets x {S} timesteps ({s_per_ts * 1e3:.1f} ms/timestep), scaled to {args.timesteps} timesteps"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -106,3 +106,38 @@ def test_bridge_sample_philox_draws_have_the_right_law():
     assert float((freq - p.double()).abs().max()) < 4e-3
     xt2, kt2 = _abi.bridge_sample(x0, x1, k0, k1, t, 1.0, 0.075, V, seed=9, first_global_jet=17)
     assert torch.equal(xt2, xt) and torch.equal(kt2, kt)            # counter-based: reproducible
+
+
+@pytest.mark.parametrize("model,mode", [("FusedParticleFormer", "time-weighted"), ("FusedParticleFormer", "sum"), ("ParticleFormer", "time-weighted")])
+def test_oracle_autograd_matches_reference_gradient_golden(model, mode, golden_dir):
+    """tests/golden/grad_*.npz: norms and sampled entries of the gradients of the reference's own loss(batch)[0].backward()
+    (tests/golden/make_golden_grads.py).  Autograd over the oracle restatement must reproduce them - that autograd is what the GPU
+    tests hold the backward kernels to."""
+    from oracle import mmf_oracle as orc
+    g, cfg, sd, sd_loss, T = _load(golden_dir, model, mode)
+    gg = np.load(os.path.join(golden_dir, f"grad_{model}_{mode}.npz"))
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    slg = {k: v.clone().requires_grad_(True) for k, v in sd_loss.items()}
+    out = orc.training_loss(sdg, slg, cfg, T("x0"), T("k0").long(), T("x1"), T("k1").long(), T("mask"), T("time"), T("z"), T("u"))
+    out[0].backward()
+    grads = {"model." + k: v.grad for k, v in sdg.items()}
+    grads.update({"loss_combine." + k: v.grad for k, v in slg.items()})
+    names = [str(n) for n in gg["names"]]
+    assert sorted(names) == sorted(grads)
+    gnorm = sum(float(gg["norm:" + n.replace(".", "/")]) ** 2 for n in names) ** 0.5
+
+    def positions(name, numel):                      # the generator's seeded sample positions (FNV-1a of the name)
+        h = 2166136261
+        for ch in name.encode():
+            h = ((h ^ ch) * 16777619) & 0xFFFFFFFF
+        return np.random.default_rng(h % (2 ** 32)).integers(0, numel, size=min(48, numel))
+
+    for n in names:
+        a = grads[n].detach().double().flatten()
+        want_norm, want_val = float(gg["norm:" + n.replace(".", "/")]), torch.from_numpy(gg["val:" + n.replace(".", "/")]).double()
+        got_val = a[torch.from_numpy(positions(n, a.numel()))]
+        # fp32 autograd both sides; reductions in another order -> 1e-4 of the tensor's own scale (or of the whole gradient for
+        # the tensors whose gradient vanishes identically, e.g. the key-LayerNorm bias)
+        scale = max(want_norm, 1e-6 * gnorm)
+        assert abs(float(a.norm()) - want_norm) <= 2e-4 * scale, (n, float(a.norm()), want_norm)
+        assert float((got_val - want_val).abs().max()) <= 2e-4 * scale, (n, float((got_val - want_val).abs().max()), scale)
