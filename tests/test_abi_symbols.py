@@ -9,8 +9,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "mmf_b200.h")
 
 
-def _declared_functions():
-    src = open(HEADER).read()
+TRAIN_HEADER = os.path.join(ROOT, "include", "mmf_b200_train.h")
+
+
+def _declared_functions(header=HEADER):
+    src = open(header).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = re.findall(r"^\s*(?:const\s+)?[A-Za-z_][A-Za-z0-9_]*\s*\*?\s*(mmf_[a-z0-9_]+)\s*\(", src, flags=re.M)
     return sorted(set(names))
@@ -37,6 +40,15 @@ def test_library_exports_every_declared_symbol(built_lib):
         assert hasattr(lib, name), f"{name} is declared in include/mmf_b200.h but not exported"
     # and the Python binding knows about every one of them
     assert sorted(built_lib.EXPORTS) == _declared_functions()
+    # the training-step operators (include/mmf_b200_train.h): exported, bound with the right number of arguments
+    from mmf_b200 import _train_abi
+    declared = _declared_functions(TRAIN_HEADER)
+    assert declared == _train_abi.TRAIN_EXPORTS and len(declared) >= 29
+    src = re.sub(r"/\*.*?\*/", "", open(TRAIN_HEADER).read(), flags=re.S)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/mmf_b200_train.h but not exported"
+        args = re.search(name + r"\s*\((.*?)\)\s*;", src, flags=re.S).group(1)
+        assert len(_train_abi.SIGNATURES[name]) == len([a for a in args.split(",") if a.strip()]), name
 
 
 def test_abi_version_and_struct_layout(built_lib):
