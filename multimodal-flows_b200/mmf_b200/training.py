@@ -174,6 +174,7 @@ class TrainEngine:
         self._err = torch.zeros(1, device=dev, dtype=torch.int32)
         self.refresh_operands()
         self.use_graphs, self.graph_rows, self._slots = bool(use_graphs) and _ops is None, 1024, {}
+        self.concurrent, self._streams, self._wstreams, self._wused, self._keep = _ops is None, [], {}, set(), []
         self.last_plan = None
 
     # ---- parameter views -------------------------------------------------------------------------------------------------
@@ -201,6 +202,56 @@ class TrainEngine:
         self.ops.weights_transpose(self.P, self.PT16, self._jobs, self._n_jobs, self._n_tiles)
         self.module.model.refresh()
 
+    # ---- concurrency: independent chains on side streams (branches of the graph under capture) ------------------------------
+    def _branches(self, n):
+        eng = self
+
+        class _Br:
+            def __enter__(self):
+                self.on = eng.device.type == "cuda" and eng.concurrent
+                if self.on:
+                    self.cur = torch.cuda.current_stream(eng.device)
+                    while len(eng._streams) < n:
+                        eng._streams.append(torch.cuda.Stream(eng.device))
+                    for st in eng._streams[:n]:
+                        st.wait_stream(self.cur)
+                return self
+
+            def __call__(self, i):
+                import contextlib
+                return torch.cuda.stream(eng._streams[i]) if self.on else contextlib.nullcontext()
+
+            def __exit__(self, *exc):
+                if self.on:
+                    for st in eng._streams[:n]:
+                        self.cur.wait_stream(st)
+                return False
+        return _Br()
+
+    def _wgrad_side(self, fn, *tensors):
+        """Weight-gradient products feed nothing downstream: they run on a side stream next to the data-gradient chain and are
+        joined once at the end of the backward pass.  Their operands are kept alive until then."""
+        if self.device.type != "cuda" or not self.concurrent:
+            return fn()
+        cur = torch.cuda.current_stream(self.device)
+        key = cur.cuda_stream
+        st = self._wstreams.get(key)
+        if st is None:
+            st = self._wstreams[key] = torch.cuda.Stream(self.device)
+        self._wused.add(key)
+        self._keep.extend(tensors)
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            fn()
+
+    def _join_wgrad(self):
+        if self._wused:
+            cur = torch.cuda.current_stream(self.device)
+            for key in self._wused:
+                cur.wait_stream(self._wstreams[key])
+            self._wused.clear()
+        self._keep.clear()
+
     # ---- nn.Linear on packed rows ----------------------------------------------------------------------------------------
     def _lin_fwd(self, x16, name, out, mode):
         self.ops.gemm(x16, self.w16(name + ".weight"), out, self.p(name + ".bias"), mode)
@@ -218,9 +269,14 @@ class TrainEngine:
         db = self.g(name + ".bias")
         if dy_src is not None:
             ops.cast_transpose(dy_src, out=dy16, colsum=db)
-        elif db is not None:
-            ops.cast_transpose(dy16, colsum=db)
-        ops.gemm_tn(dy16, x16, self.g(name + ".weight"), self._ksplit(plan, N, K))
+            db = None
+        ks = self._ksplit(plan, N, K)
+
+        def wgrad():
+            if db is not None:
+                ops.cast_transpose(dy16, colsum=db)
+            ops.gemm_tn(dy16, x16, self.g(name + ".weight"), ks)
+        self._wgrad_side(wgrad, dy16, x16)
         if dx is not None:
             ops.gemm(dy16, self.wT16(name + ".weight"), dx, None, dx_mode)
 
@@ -274,8 +330,8 @@ class TrainEngine:
         self._lin_bwd(plan, dh, s["a2"], pre + ".ffw.c_fc", dx=da, dx_mode=1)
         ops.ln_bwd(da, s["R1"], s["m2"], s["r2"], self.p(pre + ".ln2.weight"), G, self.g(pre + ".ln2.weight"), self.g(pre + ".ln2.bias"),
                    accumulate=True)
-        do = torch.empty(M, C, **bf)
-        self._lin_bwd(plan, G16, s["o"], pre + ".attn.c_proj", dx=do, dx_mode=0, dy_src=G)
+        do, G16b = torch.empty(M, C, **bf), torch.empty(M, C, **bf)
+        self._lin_bwd(plan, G16b, s["o"], pre + ".attn.c_proj", dx=do, dx_mode=0, dy_src=G)
         dqkv = torch.zeros(M, 3 * C, **bf) if plan.padded else torch.empty(M, 3 * C, **bf)
         ops.attn_tc_bwd(do, s["qn"], s["kn"], s["qkv"][:, 2 * C:], hs, plan.items, plan.n_items, plan.grid_items, plan.row_jet, plan.jet_off,
                         s["stats"], dqkv)
@@ -322,12 +378,21 @@ class TrainEngine:
         c["skip"] = R
         blocks: List[dict] = []
         if self.pf:
-            for i in range(self.cfg.n_layer):
-                R1, R2 = f32(M, 256), f32(M, 256)
+            # the continuous and the discrete stream do not meet before ln2_x / ln2_y: two independent chains of blocks, run
+            # concurrently (two branches of the CUDA graph) - each one alone leaves most of the chip idle
+            Rs = [R] + [(f32(M, 256), f32(M, 256)) for _ in range(self.cfg.n_layer)]
+            chains = [[], []]
+            with self._branches(2) as br:
                 for gi, nm in enumerate(("blocks_x", "blocks_y")):
                     cols = slice(gi * h, (gi + 1) * h)
-                    blocks.append(self._block_fwd(plan, R[:, cols], R1[:, cols], R2[:, cols], f"{T}{nm}.{i}", temb[:, cols]))
-                R = R2
+                    with br(gi):
+                        Rin = R
+                        for i in range(self.cfg.n_layer):
+                            R1, R2 = Rs[i + 1]
+                            chains[gi].append(self._block_fwd(plan, Rin[:, cols], R1[:, cols], R2[:, cols], f"{T}{nm}.{i}", temb[:, cols]))
+                            Rin = R2
+            blocks = chains[0] + chains[1]
+            R = Rs[-1][1]
             # x = ln2_x(x + x_skip) | y = ln2_y(y + y_skip); z = cat + time_expand(temb)
             c["Rmid"] = R
             Z = f32(M, 256)
@@ -441,9 +506,11 @@ class TrainEngine:
                            self.g(T + nm + ".weight"), self.g(T + nm + ".bias"), add=c["skip"][:, cols])
             ops.add(Gskip, Gskip, G2)
             G = G2
-            for s in reversed(blocks[:ns]):
-                gi = 0 if ".blocks_x." in s["pre"] else 1
-                self._block_bwd(plan, s, G[:, gi * h:(gi + 1) * h])
+            with self._branches(2) as br:
+                for gi in range(2):
+                    with br(gi):
+                        for s in reversed(blocks[gi * (ns // 2):(gi + 1) * (ns // 2)]):
+                            self._block_bwd(plan, s, G[:, gi * h:(gi + 1) * h])
         else:
             for s in reversed(blocks):
                 self._block_bwd(plan, s, G)
@@ -460,6 +527,7 @@ class TrainEngine:
         self._lin_bwd(plan, du16[:, h:], c["g0"], T + "wye.2", dx=dg0, dx_mode=0, dy_src=du[:, h:])
         ops.embed_x_bwd(dh0, xs, self.p(T + "wxe.0.weight"), self.p(T + "wxe.0.bias"), self.g(T + "wxe.0.weight"), self.g(T + "wxe.0.bias"))
         ops.embed_y_bwd(dg0, ks, self.p(T + "wye.0.weight"), self.g(T + "wye.0.weight"))
+        self._join_wgrad()
 
     # ---- public API ---------------------------------------------------------------------------------------------------------
     def _prepare(self, batch: DataCoupling, time, z, u):
