@@ -70,7 +70,7 @@ tr_attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     uint8_t* Ks = Qs + kBox;
     uint8_t* Vs = Ks + kBox;
     uint8_t* Ps = Vs + kBox;                     // two boxes: keys [0,64) and [64,128)
-    if (static_cast<int>(blockIdx.x) >= *a.n_items) return;
+    if (static_cast<int>(blockIdx.x) >= *a.n_items) return;        // (n_items comes from a host copy, not from the previous kernel)
     const int2 item = a.items[blockIdx.x];
     const int row0 = item.x, nrows = item.y;
     const int col0 = blockIdx.y * 64;
@@ -87,6 +87,8 @@ tr_attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    grid_dep_wait();                             // PDL: the prologue above overlapped the previous kernel
+    grid_dep_launch();
     if (threadIdx.x == 0) {
         mbar_expect_tx(&bars->loaded, 3 * kBox);
         tma_load_2d(Qs, &tmQ, &bars->loaded, col0, row0);
@@ -209,6 +211,8 @@ tr_attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    grid_dep_wait();
+    grid_dep_launch();
     if (threadIdx.x == 0) {
         mbar_expect_tx(&bars->loaded, 4 * kBox);
         tma_load_2d(Qs, &tmQ, &bars->loaded, col0, row0);
@@ -345,10 +349,10 @@ int launch_tr_attn_tc_fwd(const bf16* qn, long long ldq, const bf16* kn, long lo
     const dim3 grid(grid_items, C / 64);
     if (hs == 32) {
         if (configure_once<0>(tr_attn_tc_fwd_kernel<32>, kFwdSmem)) return 1;
-        tr_attn_tc_fwd_kernel<32><<<grid, 128, kFwdSmem, s>>>(tq, tk, tv, a);
+        MMF_CUDA_OK(tr_launch(tr_attn_tc_fwd_kernel<32>, grid, dim3(128), kFwdSmem, s, tq, tk, tv, a));
     } else {
         if (configure_once<1>(tr_attn_tc_fwd_kernel<64>, kFwdSmem)) return 1;
-        tr_attn_tc_fwd_kernel<64><<<grid, 128, kFwdSmem, s>>>(tq, tk, tv, a);
+        MMF_CUDA_OK(tr_launch(tr_attn_tc_fwd_kernel<64>, grid, dim3(128), kFwdSmem, s, tq, tk, tv, a));
     }
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
@@ -367,10 +371,10 @@ int launch_tr_attn_tc_bwd(const bf16* dO, long long lddo, const bf16* qn, long l
     const dim3 grid(grid_items, C / 64);
     if (hs == 32) {
         if (configure_once<2>(tr_attn_tc_bwd_kernel<32>, kBwdSmem)) return 1;
-        tr_attn_tc_bwd_kernel<32><<<grid, 128, kBwdSmem, s>>>(tq, tk, tv, td, a);
+        MMF_CUDA_OK(tr_launch(tr_attn_tc_bwd_kernel<32>, grid, dim3(128), kBwdSmem, s, tq, tk, tv, td, a));
     } else {
         if (configure_once<3>(tr_attn_tc_bwd_kernel<64>, kBwdSmem)) return 1;
-        tr_attn_tc_bwd_kernel<64><<<grid, 128, kBwdSmem, s>>>(tq, tk, tv, td, a);
+        MMF_CUDA_OK(tr_launch(tr_attn_tc_bwd_kernel<64>, grid, dim3(128), kBwdSmem, s, tq, tk, tv, td, a));
     }
     MMF_CUDA_OK(cudaGetLastError());
     return 0;

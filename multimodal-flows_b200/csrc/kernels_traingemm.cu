@@ -23,7 +23,7 @@
 namespace mmf {
 namespace {
 
-constexpr int kTrStages = 4;
+constexpr int kTrStages = 3;              // 98 KB of operand ring at most: two CTAs per SM even for the long split-K loops
 constexpr int kTrBox = kTileM * 128;             // one operand box: 128 rows x 128 B
 constexpr int kTrStage = 2 * kTrBox;             // A + B
 constexpr int tr_smem_bytes(int stages) { return 1024 + stages * kTrStage + 1024; }
@@ -86,6 +86,8 @@ tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    grid_dep_wait();                 // PDL: everything above overlapped the previous kernel; its results are visible from here
+    grid_dep_launch();
 
     if (warp == 4) {
         if (lane == 0) {
@@ -190,8 +192,7 @@ int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     }
     // the epilogue stages the whole output tile in the ring: two stages hold it (64 KB fp32)
     const int stages = kb_per_split < 2 ? 2 : (kb_per_split > kTrStages ? kTrStages : kb_per_split);
-    tr_gemm_kernel<MODE, TN><<<grid, 192, tr_smem_bytes(stages), s>>>(tmA, tmB, tmC, bias, N, kb_total, kb_per_split, stages);
-    MMF_CUDA_OK(cudaGetLastError());
+    MMF_CUDA_OK(tr_launch(tr_gemm_kernel<MODE, TN>, grid, dim3(192), tr_smem_bytes(stages), s, tmA, tmB, tmC, bias, N, kb_total, kb_per_split, stages));
     return 0;
 }
 

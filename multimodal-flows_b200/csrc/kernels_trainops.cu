@@ -6,7 +6,9 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
+#include "mmf_ptx.cuh"
 #include "mmf_train.h"
 
 namespace mmf {
@@ -38,6 +40,8 @@ __device__ __forceinline__ float gelu_grad(float x) {
 __global__ void __launch_bounds__(256) tr_sgemm_kernel(const float* __restrict__ A, long long sam, long long sak, const float* __restrict__ B,
                                                        long long sbk, long long sbn, float* __restrict__ C, long long ldc, int M, int N,
                                                        int K, const float* __restrict__ bias, int accumulate) {
+    grid_dep_wait();
+    grid_dep_launch();
     __shared__ float As[16][17], Bs[16][17];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m = blockIdx.y * 16 + ty, n = blockIdx.x * 16 + tx;
@@ -63,6 +67,8 @@ template <bool F32>
 __global__ void __launch_bounds__(256) tr_cast_transpose_kernel(const void* __restrict__ in_, long long ld_in, int rows, int cols,
                                                                 bf16* __restrict__ out, long long ld_out, bf16* __restrict__ outT,
                                                                 long long ldT, float* __restrict__ colsum) {
+    grid_dep_wait();
+    grid_dep_launch();
     __shared__ float tile[32][33];
     __shared__ float part[8][32];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -101,6 +107,8 @@ __global__ void __launch_bounds__(256) tr_cast_transpose_kernel(const void* __re
 // all two-dimensional weights of the flat parameter buffer: bf16 transposed copies for the data-gradient GEMMs, one launch
 __global__ void __launch_bounds__(256) tr_weights_transpose_kernel(const float* __restrict__ p, bf16* __restrict__ pT,
                                                                    const TrTransposeJob* __restrict__ jobs, int n_jobs) {
+    grid_dep_wait();
+    grid_dep_launch();
     __shared__ float tile[32][33];
     int j = 0;
     while (j + 1 < n_jobs && jobs[j + 1].tile0 <= static_cast<int>(blockIdx.x)) ++j;
@@ -128,6 +136,8 @@ __global__ void tr_pack_kernel(const float* __restrict__ xt, const long long* __
                                const float* __restrict__ x1, const long long* __restrict__ k1, const int* __restrict__ row_slot, int M,
                                int V, float* __restrict__ xs, int* __restrict__ ks, float* __restrict__ tgt, int* __restrict__ k1p,
                                int* __restrict__ err) {
+    grid_dep_wait();
+    grid_dep_launch();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= M) return;
     const long long s = row_slot[r];
@@ -144,6 +154,8 @@ __global__ void tr_pack_kernel(const float* __restrict__ xt, const long long* __
 
 // transformer_timestep_embedding (reference utils/models.py:62-75); dup = 1 writes the row twice (x | y halves)
 __global__ void tr_time_embed_kernel(const float* __restrict__ t, int B, int dim, int dup, float* __restrict__ out, long long ld) {
+    grid_dep_wait();
+    grid_dep_launch();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * dim) return;
     const int b = i / dim, c = i % dim, half = dim / 2;
@@ -157,6 +169,8 @@ __global__ void tr_time_embed_kernel(const float* __restrict__ t, int B, int dim
 
 __global__ void tr_embed_x_fwd_kernel(const float* __restrict__ xs, int M, const float* __restrict__ w0, const float* __restrict__ b0,
                                       int E, bf16* __restrict__ h, long long ld) {
+    grid_dep_wait();
+    grid_dep_launch();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(M) * E) return;
     const int r = static_cast<int>(i / E), j = static_cast<int>(i % E);
@@ -168,6 +182,8 @@ __global__ void tr_embed_x_fwd_kernel(const float* __restrict__ xs, int M, const
 __global__ void tr_embed_x_bwd_kernel(const bf16* __restrict__ dh, long long ld, const float* __restrict__ xs, int M,
                                       const float* __restrict__ w0, const float* __restrict__ b0, int E, int rows_per_cta,
                                       float* __restrict__ dw0, float* __restrict__ db0) {
+    grid_dep_wait();
+    grid_dep_launch();
     const int j = threadIdx.x;
     if (j >= E) return;
     const int r_beg = blockIdx.x * rows_per_cta, r_end = min(M, r_beg + rows_per_cta);
@@ -184,6 +200,8 @@ __global__ void tr_embed_x_bwd_kernel(const bf16* __restrict__ dh, long long ld,
 
 __global__ void tr_embed_y_fwd_kernel(const int* __restrict__ ks, int M, const float* __restrict__ emb, int E, bf16* __restrict__ g,
                                       long long ld) {
+    grid_dep_wait();
+    grid_dep_launch();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= static_cast<long long>(M) * E) return;
     const int r = static_cast<int>(i / E), j = static_cast<int>(i % E);
@@ -193,6 +211,8 @@ __global__ void tr_embed_y_fwd_kernel(const int* __restrict__ ks, int M, const f
 template <int V>
 __global__ void tr_embed_y_bwd_kernel(const bf16* __restrict__ dg, long long ld, const int* __restrict__ ks, int M,
                                       const float* __restrict__ emb, int E, int rows_per_cta, float* __restrict__ demb) {
+    grid_dep_wait();
+    grid_dep_launch();
     const int j = threadIdx.x;
     if (j >= E) return;
     const int r_beg = blockIdx.x * rows_per_cta, r_end = min(M, r_beg + rows_per_cta);
@@ -213,6 +233,8 @@ __global__ void tr_embed_y_bwd_kernel(const bf16* __restrict__ dg, long long ld,
 // ------------------------------------------------------------------------------------------------ LayerNorm (warp per row)
 template <int C>
 __global__ void __launch_bounds__(256) tr_ln_fwd_kernel(const TrLnArgs a) {
+    grid_dep_wait();
+    grid_dep_launch();
     constexpr int NV = C / 128;                     // float4 per lane
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -257,6 +279,8 @@ __global__ void __launch_bounds__(256) tr_ln_fwd_kernel(const TrLnArgs a) {
 
 template <int C>
 __global__ void __launch_bounds__(256) tr_ln_bwd_kernel(const TrLnBwdArgs a) {
+    grid_dep_wait();
+    grid_dep_launch();
     constexpr int NV = C / 128;
     __shared__ float red[2][8][C];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -355,6 +379,8 @@ __global__ void __launch_bounds__(128) tr_qkln_fwd_kernel(const bf16* __restrict
                                                           const float* __restrict__ qg, const float* __restrict__ qb,
                                                           const float* __restrict__ kg, const float* __restrict__ kb,
                                                           bf16* __restrict__ qn, bf16* __restrict__ kn, long long ldn) {
+    grid_dep_wait();
+    grid_dep_launch();
     const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (idx >= static_cast<long long>(M) * 2 * H) return;
     const int head = static_cast<int>(idx % H), which = static_cast<int>((idx / H) % 2);
@@ -376,6 +402,8 @@ __global__ void __launch_bounds__(128) tr_qkln_bwd_kernel(bf16* __restrict__ dqk
                                                           int M, int C, int H, const float* __restrict__ qg, const float* __restrict__ kg,
                                                           float* __restrict__ dqg, float* __restrict__ dqb, float* __restrict__ dkg,
                                                           float* __restrict__ dkb) {
+    grid_dep_wait();
+    grid_dep_launch();
     const int which = blockIdx.y, lane = threadIdx.x & 31;
     const float* g = which ? kg : qg;
     float* dgam = which ? dkg : dqg;
@@ -459,6 +487,8 @@ __global__ void __launch_bounds__(256) tr_attn_fwd_kernel(const bf16* __restrict
                                                           const bf16* __restrict__ v, long long ldv, const int* __restrict__ jet_off,
                                                           const long long* __restrict__ p_off, int H, float scale, int min_n,
                                                           bf16* __restrict__ o, long long ldo, bf16* __restrict__ P) {
+    grid_dep_wait();
+    grid_dep_launch();
     extern __shared__ uint32_t sm[];
     constexpr int PW = HS / 2 + 1;
     const int jet = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
@@ -508,6 +538,8 @@ __global__ void __launch_bounds__(256) tr_attn_bwd_kernel(const bf16* __restrict
                                                           const bf16* __restrict__ kn, long long ldk, const bf16* __restrict__ v, long long ldv,
                                                           const int* __restrict__ jet_off, const long long* __restrict__ p_off, int H,
                                                           float scale, int min_n, bf16* __restrict__ dqkv, long long ldd, int C) {
+    grid_dep_wait();
+    grid_dep_launch();
     extern __shared__ uint32_t sm[];
     constexpr int PW = HS / 2 + 1;
     const int jet = blockIdx.x, h = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
@@ -565,6 +597,8 @@ __global__ void __launch_bounds__(256) tr_attn_bwd_kernel(const bf16* __restrict
 // ------------------------------------------------------------------------------------------------ element-wise
 template <bool F32>
 __global__ void tr_gelu_fwd_kernel(const void* __restrict__ z_, void* __restrict__ h_, long long n) {
+    grid_dep_wait();
+    grid_dep_launch();
     const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
     if (i >= n) return;
     if (F32) {
@@ -579,6 +613,8 @@ __global__ void tr_gelu_fwd_kernel(const void* __restrict__ z_, void* __restrict
 }
 template <bool F32>
 __global__ void tr_gelu_bwd_kernel(const void* __restrict__ dh_, const void* __restrict__ z_, void* __restrict__ dz_, long long n) {
+    grid_dep_wait();
+    grid_dep_launch();
     const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 2;
     if (i >= n) return;
     if (F32) {
@@ -595,6 +631,8 @@ __global__ void tr_gelu_bwd_kernel(const void* __restrict__ dh_, const void* __r
 
 __global__ void tr_add_kernel(float* __restrict__ out, long long ldo, const float* __restrict__ a, long long lda, const float* __restrict__ y,
                               long long ldy, const float* __restrict__ tadd, long long ldt, const int* __restrict__ row_jet, int M, int C) {
+    grid_dep_wait();
+    grid_dep_launch();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int cq = C / 4;
     if (i >= static_cast<long long>(M) * cq) return;
@@ -611,6 +649,8 @@ __global__ void tr_add_kernel(float* __restrict__ out, long long ldo, const floa
 
 __global__ void tr_jet_sum_kernel(const float* __restrict__ g, long long ld, const int* __restrict__ jet_off, int C, float* __restrict__ out,
                                   long long ldo, int accumulate) {
+    grid_dep_wait();
+    grid_dep_launch();
     const int b = blockIdx.x, c = threadIdx.x;
     if (c >= C) return;
     float s = 0.f;
@@ -625,6 +665,8 @@ template <int V>
 __global__ void __launch_bounds__(256) tr_head_fwd_kernel(const bf16* __restrict__ h, long long ldh, int I, const float* __restrict__ wx,
                                                           const float* __restrict__ bx, const float* __restrict__ wy,
                                                           const float* __restrict__ by, int M, float* __restrict__ vt, float* __restrict__ logits) {
+    grid_dep_wait();
+    grid_dep_launch();
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= M) return;
@@ -658,6 +700,8 @@ __global__ void __launch_bounds__(256) tr_head_bwd_kernel(const float* __restric
                                                           const float* __restrict__ wy, int M, int rows_per_cta, bf16* __restrict__ dz,
                                                           float* __restrict__ dwx, float* __restrict__ dbx, float* __restrict__ dwy,
                                                           float* __restrict__ dby) {
+    grid_dep_wait();
+    grid_dep_launch();
     __shared__ float sd[3 + V];
     const int tid = threadIdx.x;
     const int r_beg = blockIdx.x * rows_per_cta, r_end = min(M, r_beg + rows_per_cta);
@@ -708,6 +752,8 @@ template <int V>
 __global__ void tr_loss_fwd_kernel(const float* __restrict__ vt, const float* __restrict__ logits, const float* __restrict__ tgt,
                                    const int* __restrict__ k1, const int* __restrict__ jet_off, int B, float* __restrict__ loss_mse,
                                    float* __restrict__ loss_ce) {
+    grid_dep_wait();
+    grid_dep_launch();
     const int jet = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (jet >= B) return;
     float mse = 0.f, ce = 0.f;
@@ -738,6 +784,8 @@ __global__ void tr_loss_fwd_kernel(const float* __restrict__ vt, const float* __
 __global__ void tr_loss_combine_kernel(const float* __restrict__ loss_mse, const float* __restrict__ loss_ce, const float* __restrict__ u,
                                        int B, float* __restrict__ out5, float* __restrict__ gl1, float* __restrict__ gl2,
                                        float* __restrict__ du) {
+    grid_dep_wait();
+    grid_dep_launch();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const float inv = 1.0f / static_cast<float>(B);
     float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
@@ -768,6 +816,8 @@ __global__ void tr_loss_bwd_kernel(const float* __restrict__ vt, const float* __
                                    const int* __restrict__ k1, const int* __restrict__ row_jet, const int* __restrict__ jet_off,
                                    const float* __restrict__ gl1, const float* __restrict__ gl2, int M, int B, float* __restrict__ dvt,
                                    float* __restrict__ dlog) {
+    grid_dep_wait();
+    grid_dep_launch();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= M) return;
     if (r >= jet_off[B]) {                              // rows beyond the last jet (a batch padded to a fixed row capacity)
@@ -795,6 +845,8 @@ __global__ void tr_loss_bwd_kernel(const float* __restrict__ vt, const float* __
 
 // ------------------------------------------------------------------------------------------------ optimiser
 __global__ void __launch_bounds__(256) tr_sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+    grid_dep_wait();
+    grid_dep_launch();
     __shared__ float red[8];
     float s = 0.f;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -813,6 +865,8 @@ __global__ void __launch_bounds__(256) tr_sumsq_kernel(const float* __restrict__
 __global__ void tr_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
                                float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt, const float* __restrict__ sumsq,
                                float max_norm, float grad_scale, bf16* __restrict__ p16) {
+    grid_dep_wait();
+    grid_dep_launch();
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float coef = grad_scale;
@@ -835,10 +889,15 @@ inline unsigned blocks_for(long long n, int per) { return static_cast<unsigned>(
 }  // namespace
 
 // ================================================================================================== launchers
+bool tr_pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("MMF_TRAIN_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 int launch_tr_sgemm(const float* A, long long sam, long long sak, const float* B, long long sbk, long long sbn, float* C, long long ldc,
                     int M, int N, int K, const float* bias, int accumulate, cudaStream_t s) {
     if (M <= 0 || N <= 0) return 0;
-    tr_sgemm_kernel<<<dim3((N + 15) / 16, (M + 15) / 16), 256, 0, s>>>(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, accumulate);
+    MMF_CUDA_OK(tr_launch(tr_sgemm_kernel, dim3(dim3((N + 15) / 16, (M + 15) / 16)), dim3(256), 0, s, A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, accumulate));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -847,15 +906,15 @@ int launch_tr_cast_transpose(const void* in, long long ld_in, int in_f32, int ro
                              long long ldT, float* colsum, cudaStream_t s) {
     if (rows <= 0 || cols <= 0) return 0;
     const dim3 grid((rows + 31) / 32, (cols + 31) / 32);
-    if (in_f32) tr_cast_transpose_kernel<true><<<grid, 256, 0, s>>>(in, ld_in, rows, cols, out, ld_out, outT, ldT, colsum);
-    else tr_cast_transpose_kernel<false><<<grid, 256, 0, s>>>(in, ld_in, rows, cols, out, ld_out, outT, ldT, colsum);
+    if (in_f32) MMF_CUDA_OK(tr_launch(tr_cast_transpose_kernel<true>, dim3(grid), dim3(256), 0, s, in, ld_in, rows, cols, out, ld_out, outT, ldT, colsum));
+    else MMF_CUDA_OK(tr_launch(tr_cast_transpose_kernel<false>, dim3(grid), dim3(256), 0, s, in, ld_in, rows, cols, out, ld_out, outT, ldT, colsum));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 int launch_tr_weights_transpose(const float* p, bf16* pT, const TrTransposeJob* jobs_dev, int n_jobs, int n_tiles, cudaStream_t s) {
     if (n_jobs <= 0 || n_tiles <= 0) return 0;
-    tr_weights_transpose_kernel<<<n_tiles, 256, 0, s>>>(p, pT, jobs_dev, n_jobs);
+    MMF_CUDA_OK(tr_launch(tr_weights_transpose_kernel, dim3(n_tiles), dim3(256), 0, s, p, pT, jobs_dev, n_jobs));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -863,21 +922,21 @@ int launch_tr_weights_transpose(const float* p, bf16* pT, const TrTransposeJob* 
 int launch_tr_pack(const float* xt, const long long* kt, const float* x0, const float* x1, const long long* k1, const int* row_slot, int M,
                    int V, float* xs, int* ks, float* tgt, int* k1p, int* err, cudaStream_t s) {
     if (M <= 0) return 0;
-    tr_pack_kernel<<<blocks_for(M, 256), 256, 0, s>>>(xt, kt, x0, x1, k1, row_slot, M, V, xs, ks, tgt, k1p, err);
+    MMF_CUDA_OK(tr_launch(tr_pack_kernel, dim3(blocks_for(M, 256)), dim3(256), 0, s, xt, kt, x0, x1, k1, row_slot, M, V, xs, ks, tgt, k1p, err));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 int launch_tr_time_embed(const float* t, int B, int dim, int dup, float* out, long long ld, cudaStream_t s) {
     if (B <= 0) return 0;
-    tr_time_embed_kernel<<<blocks_for(static_cast<long long>(B) * dim, 256), 256, 0, s>>>(t, B, dim, dup, out, ld);
+    MMF_CUDA_OK(tr_launch(tr_time_embed_kernel, dim3(blocks_for(static_cast<long long>(B) * dim, 256)), dim3(256), 0, s, t, B, dim, dup, out, ld));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 int launch_tr_embed_x_fwd(const float* xs, int M, const float* w0, const float* b0, int E, bf16* h, long long ld, cudaStream_t s) {
     if (M <= 0) return 0;
-    tr_embed_x_fwd_kernel<<<blocks_for(static_cast<long long>(M) * E, 256), 256, 0, s>>>(xs, M, w0, b0, E, h, ld);
+    MMF_CUDA_OK(tr_launch(tr_embed_x_fwd_kernel, dim3(blocks_for(static_cast<long long>(M) * E, 256)), dim3(256), 0, s, xs, M, w0, b0, E, h, ld));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -887,7 +946,7 @@ int launch_tr_embed_x_bwd(const bf16* dh, long long ld, const float* xs, int M, 
     if (M <= 0) return 0;
     MMF_REQUIRE(E <= 1024, "embed_x_bwd: n_embd up to 1024");
     const int rpc = 64;
-    tr_embed_x_bwd_kernel<<<blocks_for(M, rpc), E, 0, s>>>(dh, ld, xs, M, w0, b0, E, rpc, dw0, db0);
+    MMF_CUDA_OK(tr_launch(tr_embed_x_bwd_kernel, dim3(blocks_for(M, rpc)), dim3(E), 0, s, dh, ld, xs, M, w0, b0, E, rpc, dw0, db0));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -895,7 +954,7 @@ int launch_tr_embed_x_bwd(const bf16* dh, long long ld, const float* xs, int M, 
 int launch_tr_embed_y_fwd(const int* ks, int M, const float* emb, int E, int V, bf16* g, long long ld, cudaStream_t s) {
     if (M <= 0) return 0;
     (void)V;
-    tr_embed_y_fwd_kernel<<<blocks_for(static_cast<long long>(M) * E, 256), 256, 0, s>>>(ks, M, emb, E, g, ld);
+    MMF_CUDA_OK(tr_launch(tr_embed_y_fwd_kernel, dim3(blocks_for(static_cast<long long>(M) * E, 256)), dim3(256), 0, s, ks, M, emb, E, g, ld));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -904,7 +963,7 @@ int launch_tr_embed_y_bwd(const bf16* dg, long long ld, const int* ks, int M, co
     if (M <= 0) return 0;
     MMF_REQUIRE(V == 9 && E <= 1024, "embed_y_bwd is instantiated for vocab_size 9");
     const int rpc = 64;
-    tr_embed_y_bwd_kernel<9><<<blocks_for(M, rpc), E, 0, s>>>(dg, ld, ks, M, emb, E, rpc, demb);
+    MMF_CUDA_OK(tr_launch(tr_embed_y_bwd_kernel<9>, dim3(blocks_for(M, rpc)), dim3(E), 0, s, dg, ld, ks, M, emb, E, rpc, demb));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -912,8 +971,8 @@ int launch_tr_embed_y_bwd(const bf16* dg, long long ld, const int* ks, int M, co
 int launch_tr_ln_fwd(const TrLnArgs& a, cudaStream_t s) {
     if (a.M <= 0) return 0;
     MMF_REQUIRE(a.C == 128 || a.C == 256, "layernorm: width 128 or 256");
-    if (a.C == 128) tr_ln_fwd_kernel<128><<<blocks_for(a.M, 8), 256, 0, s>>>(a);
-    else tr_ln_fwd_kernel<256><<<blocks_for(a.M, 8), 256, 0, s>>>(a);
+    if (a.C == 128) MMF_CUDA_OK(tr_launch(tr_ln_fwd_kernel<128>, dim3(blocks_for(a.M, 8)), dim3(256), 0, s, a));
+    else MMF_CUDA_OK(tr_launch(tr_ln_fwd_kernel<256>, dim3(blocks_for(a.M, 8)), dim3(256), 0, s, a));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -922,8 +981,8 @@ int launch_tr_ln_bwd(const TrLnBwdArgs& a, cudaStream_t s) {
     if (a.M <= 0) return 0;
     MMF_REQUIRE(a.C == 128 || a.C == 256, "layernorm: width 128 or 256");
     const unsigned grid = std::min<unsigned>(blocks_for(a.M, 8), 148 * 4);
-    if (a.C == 128) tr_ln_bwd_kernel<128><<<grid, 256, 0, s>>>(a);
-    else tr_ln_bwd_kernel<256><<<grid, 256, 0, s>>>(a);
+    if (a.C == 128) MMF_CUDA_OK(tr_launch(tr_ln_bwd_kernel<128>, dim3(grid), dim3(256), 0, s, a));
+    else MMF_CUDA_OK(tr_launch(tr_ln_bwd_kernel<256>, dim3(grid), dim3(256), 0, s, a));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -934,8 +993,8 @@ int launch_tr_qkln_fwd(const bf16* qkv, long long ld, int M, int C, int H, const
     const int hs = C / H;
     MMF_REQUIRE(hs == 32 || hs == 64, "q/k LayerNorm: head size 32 or 64");
     const unsigned grid = blocks_for(static_cast<long long>(M) * 2 * H, 128);
-    if (hs == 32) tr_qkln_fwd_kernel<32><<<grid, 128, 0, s>>>(qkv, ld, M, C, H, qg, qb, kg, kb, qn, kn, ldn);
-    else tr_qkln_fwd_kernel<64><<<grid, 128, 0, s>>>(qkv, ld, M, C, H, qg, qb, kg, kb, qn, kn, ldn);
+    if (hs == 32) MMF_CUDA_OK(tr_launch(tr_qkln_fwd_kernel<32>, dim3(grid), dim3(128), 0, s, qkv, ld, M, C, H, qg, qb, kg, kb, qn, kn, ldn));
+    else MMF_CUDA_OK(tr_launch(tr_qkln_fwd_kernel<64>, dim3(grid), dim3(128), 0, s, qkv, ld, M, C, H, qg, qb, kg, kb, qn, kn, ldn));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -947,8 +1006,8 @@ int launch_tr_qkln_bwd(bf16* dqkv, long long ldd, const bf16* qkv, long long ld,
     MMF_REQUIRE(hs == 32 || hs == 64, "q/k LayerNorm: head size 32 or 64");
     const long long chunks = (static_cast<long long>(M) * H + 31) / 32;
     const dim3 grid(static_cast<unsigned>(std::min<long long>((chunks + 3) / 4, 148 * 8)), 2);
-    if (hs == 32) tr_qkln_bwd_kernel<32><<<grid, 128, 0, s>>>(dqkv, ldd, qkv, ld, M, C, H, qg, kg, dqg, dqb, dkg, dkb);
-    else tr_qkln_bwd_kernel<64><<<grid, 128, 0, s>>>(dqkv, ldd, qkv, ld, M, C, H, qg, kg, dqg, dqb, dkg, dkb);
+    if (hs == 32) MMF_CUDA_OK(tr_launch(tr_qkln_bwd_kernel<32>, dim3(grid), dim3(128), 0, s, dqkv, ldd, qkv, ld, M, C, H, qg, kg, dqg, dqb, dkg, dkb));
+    else MMF_CUDA_OK(tr_launch(tr_qkln_bwd_kernel<64>, dim3(grid), dim3(128), 0, s, dqkv, ldd, qkv, ld, M, C, H, qg, kg, dqg, dqb, dkg, dkb));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -977,10 +1036,10 @@ int launch_tr_attn_fwd(const bf16* qn, long long ldq, const bf16* kn, long long 
     const float scale = 1.0f / sqrtf(static_cast<float>(hs));
     if (hs == 32) {
         if (attn_configure<0>(tr_attn_fwd_kernel<32>, bytes)) return 1;
-        tr_attn_fwd_kernel<32><<<dim3(B, H), 256, bytes, s>>>(qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, min_n, o, ldo, P);
+        MMF_CUDA_OK(tr_launch(tr_attn_fwd_kernel<32>, dim3(dim3(B, H)), dim3(256), bytes, s, qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, min_n, o, ldo, P));
     } else {
         if (attn_configure<1>(tr_attn_fwd_kernel<64>, bytes)) return 1;
-        tr_attn_fwd_kernel<64><<<dim3(B, H), 256, bytes, s>>>(qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, min_n, o, ldo, P);
+        MMF_CUDA_OK(tr_launch(tr_attn_fwd_kernel<64>, dim3(dim3(B, H)), dim3(256), bytes, s, qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, min_n, o, ldo, P));
     }
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
@@ -996,10 +1055,10 @@ int launch_tr_attn_bwd(const bf16* dO, long long lddo, const bf16* o, long long 
     const float scale = 1.0f / sqrtf(static_cast<float>(hs));
     if (hs == 32) {
         if (attn_configure<2>(tr_attn_bwd_kernel<32>, bytes)) return 1;
-        tr_attn_bwd_kernel<32><<<dim3(B, H), 256, bytes, s>>>(dO, lddo, o, ldo, P, qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, min_n, dqkv, ldd, C);
+        MMF_CUDA_OK(tr_launch(tr_attn_bwd_kernel<32>, dim3(dim3(B, H)), dim3(256), bytes, s, dO, lddo, o, ldo, P, qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, min_n, dqkv, ldd, C));
     } else {
         if (attn_configure<3>(tr_attn_bwd_kernel<64>, bytes)) return 1;
-        tr_attn_bwd_kernel<64><<<dim3(B, H), 256, bytes, s>>>(dO, lddo, o, ldo, P, qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, min_n, dqkv, ldd, C);
+        MMF_CUDA_OK(tr_launch(tr_attn_bwd_kernel<64>, dim3(dim3(B, H)), dim3(256), bytes, s, dO, lddo, o, ldo, P, qn, ldq, kn, ldk, v, ldv, jet_off, p_off, H, scale, min_n, dqkv, ldd, C));
     }
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
@@ -1008,8 +1067,8 @@ int launch_tr_attn_bwd(const bf16* dO, long long lddo, const bf16* o, long long 
 int launch_tr_gelu_fwd(const void* z, void* h, long long n, int f32, cudaStream_t s) {
     if (n <= 0) return 0;
     MMF_REQUIRE(f32 || n % 2 == 0, "gelu: bf16 arrays hold an even number of elements");
-    if (f32) tr_gelu_fwd_kernel<true><<<blocks_for((n + 1) / 2, 256), 256, 0, s>>>(z, h, n);
-    else tr_gelu_fwd_kernel<false><<<blocks_for(n / 2, 256), 256, 0, s>>>(z, h, n);
+    if (f32) MMF_CUDA_OK(tr_launch(tr_gelu_fwd_kernel<true>, dim3(blocks_for((n + 1) / 2, 256)), dim3(256), 0, s, z, h, n));
+    else MMF_CUDA_OK(tr_launch(tr_gelu_fwd_kernel<false>, dim3(blocks_for(n / 2, 256)), dim3(256), 0, s, z, h, n));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1017,8 +1076,8 @@ int launch_tr_gelu_fwd(const void* z, void* h, long long n, int f32, cudaStream_
 int launch_tr_gelu_bwd(const void* dh, const void* z, void* dz, long long n, int f32, cudaStream_t s) {
     if (n <= 0) return 0;
     MMF_REQUIRE(f32 || n % 2 == 0, "gelu: bf16 arrays hold an even number of elements");
-    if (f32) tr_gelu_bwd_kernel<true><<<blocks_for((n + 1) / 2, 256), 256, 0, s>>>(dh, z, dz, n);
-    else tr_gelu_bwd_kernel<false><<<blocks_for(n / 2, 256), 256, 0, s>>>(dh, z, dz, n);
+    if (f32) MMF_CUDA_OK(tr_launch(tr_gelu_bwd_kernel<true>, dim3(blocks_for((n + 1) / 2, 256)), dim3(256), 0, s, dh, z, dz, n));
+    else MMF_CUDA_OK(tr_launch(tr_gelu_bwd_kernel<false>, dim3(blocks_for(n / 2, 256)), dim3(256), 0, s, dh, z, dz, n));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1027,7 +1086,7 @@ int launch_tr_add(float* out, long long ldo, const float* a, long long lda, cons
                   const int* row_jet, int M, int C, cudaStream_t s) {
     if (M <= 0) return 0;
     MMF_REQUIRE(C % 4 == 0, "add: width must be a multiple of 4");
-    tr_add_kernel<<<blocks_for(static_cast<long long>(M) * (C / 4), 256), 256, 0, s>>>(out, ldo, a, lda, y, ldy, tadd, ldt, row_jet, M, C);
+    MMF_CUDA_OK(tr_launch(tr_add_kernel, dim3(blocks_for(static_cast<long long>(M) * (C / 4), 256)), dim3(256), 0, s, out, ldo, a, lda, y, ldy, tadd, ldt, row_jet, M, C));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1035,7 +1094,7 @@ int launch_tr_add(float* out, long long ldo, const float* a, long long lda, cons
 int launch_tr_jet_sum(const float* g, long long ld, const int* jet_off, int B, int C, float* out, long long ldo, int accumulate, cudaStream_t s) {
     if (B <= 0) return 0;
     MMF_REQUIRE(C <= 1024, "jet_sum: width up to 1024");
-    tr_jet_sum_kernel<<<B, C, 0, s>>>(g, ld, jet_off, C, out, ldo, accumulate);
+    MMF_CUDA_OK(tr_launch(tr_jet_sum_kernel, dim3(B), dim3(C), 0, s, g, ld, jet_off, C, out, ldo, accumulate));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1044,7 +1103,7 @@ int launch_tr_head_fwd(const bf16* h, long long ldh, int I, const float* wx, con
                        float* vt, float* logits, cudaStream_t s) {
     if (M <= 0) return 0;
     MMF_REQUIRE(V == 9 && I % 256 == 0, "head kernels are instantiated for vocab_size 9 and n_inner a multiple of 256");
-    tr_head_fwd_kernel<9><<<blocks_for(M, 8), 256, 0, s>>>(h, ldh, I, wx, bx, wy, by, M, vt, logits);
+    MMF_CUDA_OK(tr_launch(tr_head_fwd_kernel<9>, dim3(blocks_for(M, 8)), dim3(256), 0, s, h, ldh, I, wx, bx, wy, by, M, vt, logits));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1054,7 +1113,7 @@ int launch_tr_head_bwd(const float* dvt, const float* dlog, const bf16* h, const
     if (M <= 0) return 0;
     MMF_REQUIRE(V == 9 && I == 512, "head kernels are instantiated for vocab_size 9 and n_inner 512");
     const int rpc = 32;
-    tr_head_bwd_kernel<9, 2><<<blocks_for(M, rpc), 256, 0, s>>>(dvt, dlog, h, z, ldh, I, wx, wy, M, rpc, dz, dwx, dbx, dwy, dby);
+    MMF_CUDA_OK(tr_launch(tr_head_bwd_kernel<9, 2>, dim3(blocks_for(M, rpc)), dim3(256), 0, s, dvt, dlog, h, z, ldh, I, wx, wy, M, rpc, dz, dwx, dbx, dwy, dby));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1063,7 +1122,7 @@ int launch_tr_loss_fwd(const float* vt, const float* logits, const float* tgt, c
                        float* loss_mse, float* loss_ce, cudaStream_t s) {
     if (B <= 0) return 0;
     MMF_REQUIRE(V == 9, "the loss kernels are instantiated for vocab_size 9");
-    tr_loss_fwd_kernel<9><<<blocks_for(static_cast<long long>(B) * 32, 256), 256, 0, s>>>(vt, logits, tgt, k1, jet_off, B, loss_mse, loss_ce);
+    MMF_CUDA_OK(tr_launch(tr_loss_fwd_kernel<9>, dim3(blocks_for(static_cast<long long>(B) * 32, 256)), dim3(256), 0, s, vt, logits, tgt, k1, jet_off, B, loss_mse, loss_ce));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1072,7 +1131,7 @@ int launch_tr_loss_combine(const float* loss_mse, const float* loss_ce, const fl
                            cudaStream_t s) {
     MMF_CUDA_OK(cudaMemsetAsync(out5, 0, 5 * sizeof(float), s));
     if (B <= 0) return 0;
-    tr_loss_combine_kernel<<<blocks_for(B, 256), 256, 0, s>>>(loss_mse, loss_ce, u, B, out5, gl1, gl2, du);
+    MMF_CUDA_OK(tr_launch(tr_loss_combine_kernel, dim3(blocks_for(B, 256)), dim3(256), 0, s, loss_mse, loss_ce, u, B, out5, gl1, gl2, du));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1081,7 +1140,7 @@ int launch_tr_loss_bwd(const float* vt, const float* logits, const float* tgt, c
                        const float* gl1, const float* gl2, int M, int B, int V, float* dvt, float* dlog, cudaStream_t s) {
     if (M <= 0) return 0;
     MMF_REQUIRE(V == 9, "the loss kernels are instantiated for vocab_size 9");
-    tr_loss_bwd_kernel<9><<<blocks_for(M, 256), 256, 0, s>>>(vt, logits, tgt, k1, row_jet, jet_off, gl1, gl2, M, B, dvt, dlog);
+    MMF_CUDA_OK(tr_launch(tr_loss_bwd_kernel<9>, dim3(blocks_for(M, 256)), dim3(256), 0, s, vt, logits, tgt, k1, row_jet, jet_off, gl1, gl2, M, B, dvt, dlog));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1089,7 +1148,7 @@ int launch_tr_loss_bwd(const float* vt, const float* logits, const float* tgt, c
 int launch_tr_sumsq(const float* g, long long n, float* out, cudaStream_t s) {
     MMF_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float), s));
     if (n <= 0) return 0;
-    tr_sumsq_kernel<<<static_cast<unsigned>(std::min<long long>((n + 255) / 256, 148 * 8)), 256, 0, s>>>(g, n, out);
+    MMF_CUDA_OK(tr_launch(tr_sumsq_kernel, dim3(static_cast<unsigned>(std::min<long long>((n + 255) / 256, 148 * 8))), dim3(256), 0, s, g, n, out));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -1100,7 +1159,7 @@ int launch_tr_adam(float* p, const float* g, float* m, float* v, long long n, fl
     MMF_REQUIRE(step >= 1, "adam: steps count from 1");
     const float bc1 = 1.0f - static_cast<float>(pow(static_cast<double>(beta1), step));
     const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), step)));
-    tr_adam_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2_sqrt, sumsq, max_norm, grad_scale, p16);
+    MMF_CUDA_OK(tr_launch(tr_adam_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, s, p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2_sqrt, sumsq, max_norm, grad_scale, p16));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -6,6 +6,23 @@
 
 namespace mmf {
 
+// Programmatic dependent launch: every training kernel begins with griddepcontrol.wait (its predecessor in the stream has
+// completed and flushed) followed by griddepcontrol.launch_dependents (its successor may be scheduled now and run its own
+// prologue up to the wait), so launch latency and CTA ramp-up of kernel N + 1 hide under kernel N - also as programmatic
+// edges of the captured CUDA graph.  MMF_TRAIN_PDL=0 launches without the attribute (the two instructions are then no-ops).
+bool tr_pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t tr_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = tr_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // C[M x N] (+)= A[M x K] B[N x K]^T (+ bias); mode 0: bf16 store, 1: fp32 store, 2: fp32 reduce-add (K split over `ksplit` CTAs)
 int launch_tr_gemm(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N, int K,
                    const float* bias, int mode, int ksplit, cudaStream_t s);

@@ -537,7 +537,9 @@ class TrainEngine:
             time = eps + (1.0 - eps) * torch.rand(B, device=dev)
         time = time.to(dev, torch.float32).contiguous()
         plan = _Plan(batch.target.mask, dev, upload=not self.use_graphs)
-        tgt, src = batch.target.to(dev), batch.source.to(dev) if batch.source is not None else TensorMultiModal()
+        # host batches (a DataLoader's, ideally pinned) are copied without blocking; the plan above came from the host mask
+        up = lambda tm: tm._map(lambda x: x.to(dev, non_blocking=True))
+        tgt, src = up(batch.target), up(batch.source) if batch.source is not None else TensorMultiModal()
         if not src.has_continuous:                       # reference model/CFM.py:175-177
             src.continuous = torch.randn_like(tgt.continuous) * tgt.mask
         if not src.has_discrete:                         # reference model/MJB.py:201-203

@@ -18,7 +18,10 @@ bridge.model.load_state_dict(synthetic.make_state_dict(cfg, "wide", 0))
 bridge = bridge.to(dev)
 eng = bridge.configure_training(lr=1e-3, use_graphs=not (os.environ.get('MMF_TRAIN_EAGER') or os.environ.get('MMF_TRAIN_PROFILE')))
 batch = synthetic.training_batch(B)
-batch.source, batch.target = batch.source.to(dev), batch.target.to(dev)
+if os.environ.get("MMF_TRAIN_DEVICE_BATCH"):
+    batch.source, batch.target = batch.source.to(dev), batch.target.to(dev)
+else:                                   # the DataLoader's view: a pinned host batch, copied to the device inside the step
+    batch.source, batch.target = batch.source.pin_memory(), batch.target.pin_memory()
 
 prof = {}
 if os.environ.get("MMF_TRAIN_PROFILE"):
