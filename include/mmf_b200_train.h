@@ -20,10 +20,13 @@ extern "C" {
 
 /* nn.Linear forward / data gradient / weight gradient on tensor cores (tcgen05, fp32 accumulation):
  *   C[M x N] (+)= A[M x K] B[N x K]^T (+ bias[N]); A, B bf16 with K contiguous (lda, ldb multiples of 8, 16-byte aligned bases).
- *   mode 0: C bf16;  mode 1: C fp32;  mode 2: C fp32 += (TMA reduce-add; K is split over `ksplit` CTAs, bias added once).
+ *   mode 0: C bf16;  mode 1: C fp32;  mode 2: C fp32 += (TMA reduce-add; K is split over `ksplit` CTAs, bias added once);
+ *   mode 3: C bf16 and aux = GELU(C) bf16 (MLP.c_fc + nn.GELU in one pass, utils/models.py:15-16);
+ *   mode 4: C = bf16(product * GELU'(aux)), aux = the bf16 pre-activations (data gradient of MLP.c_proj through the GELU).
+ * aux [M x N] bf16 with row pitch ldaux (modes 3, 4; else null).
  * replaces F.linear and its autograd (attention.py:44-45, utils/models.py:15-17). */
 int mmf_tr_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
-                const float* bias, int32_t mode, int32_t ksplit, void* stream);
+                const float* bias, int32_t mode, int32_t ksplit, void* aux, int64_t ldaux, void* stream);
 /* weight gradient of nn.Linear straight from the row-major activations: C[M x N] += A^T B with A = dy [K x M], B = x [K x N]
  * (bf16, K = tokens; both are read as MN-major tcgen05 operands, so no transposed copy exists); K split over `ksplit` CTAs */
 int mmf_tr_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
@@ -59,10 +62,11 @@ int mmf_tr_embed_y_bwd(const void* dg_bf16, int64_t ld, const int32_t* ks, int32
 int mmf_tr_ln_fwd(const float* x, int64_t ldx, const float* add, int64_t lda, const float* g, const float* b, const float* tadd,
                   int64_t ldt, const int32_t* row_jet, int32_t M, int32_t C, void* out_bf16, int64_t ld16, float* out_f32, int64_t ld32,
                   float* mean, float* rstd, void* stream);
-/* dx (+)= dLN/dx, dg += , db += (atomic) */
+/* dx (+)= dLN/dx, dg += , db += (atomic); optionally the final dx also leaves as bf16 (dx_bf16, the operand of the next linear's
+ * gradient products) and its column sums are added to dxsum [C] (that linear's bias gradient) */
 int mmf_tr_ln_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* add, int64_t lda, const float* mean,
                   const float* rstd, const float* g, int32_t M, int32_t C, float* dx, int64_t lddx, int32_t accumulate, float* dg, float* db,
-                  void* stream);
+                  void* dx_bf16, int64_t ld16, float* dxsum, void* stream);
 /* per-head LayerNorm of q and k (attention.py:62-64): qkv bf16 [M, 3C] -> qn, kn bf16 [M, C]; the backward call turns
  * dqkv[:, 0:2C] (gradients of qn | kn) into the gradients of q | k in place */
 int mmf_tr_qkln_fwd(const void* qkv, int64_t ld, int32_t M, int32_t C, int32_t H, const float* qg, const float* qb, const float* kg,

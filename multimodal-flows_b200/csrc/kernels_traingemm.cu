@@ -41,9 +41,21 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
 }
 
 struct TrGemmBars {
-    uint64_t full[kTrStages], empty[kTrStages], acc_full;
+    uint64_t full[kTrStages], empty[kTrStages], acc_full, aux_full;
     uint32_t tmem_base;
 };
+
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_exact(float x) {
+    return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ void stage_bf16_32(uint8_t* chunk, int r, int half, const float* v) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        st_shared_v4(chunk + sw128_offset(r, half * 4 + u), pack_bf16x2(v[u * 8 + 0], v[u * 8 + 1]), pack_bf16x2(v[u * 8 + 2], v[u * 8 + 3]),
+                     pack_bf16x2(v[u * 8 + 4], v[u * 8 + 5]), pack_bf16x2(v[u * 8 + 6], v[u * 8 + 7]));
+}
 
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
     asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
@@ -51,12 +63,13 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
                  : "memory");
 }
 
-// MODE 0: bf16 store, 1: fp32 store, 2: fp32 reduce-add; TN: A [K x M], B [K x N] row-major (MN-major operands)
+// MODE 0: bf16 store, 1: fp32 store, 2: fp32 reduce-add, 3: bf16 store of z AND of GELU(z) (second output through tmD),
+// 4: bf16 store of acc * GELU'(z), z tile loaded through tmD; TN: A [K x M], B [K x N] row-major (MN-major operands)
 template <int MODE, bool TN>
 __global__ void __launch_bounds__(192, 3)
 tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const int N, const int kb_total,
-               const int kb_per_split, const int stages) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, const float* __restrict__ bias,
+               const int N, const int kb_total, const int kb_per_split, const int stages) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     TrGemmBars* bars = reinterpret_cast<TrGemmBars*>(smem);
@@ -71,11 +84,13 @@ tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         tma_prefetch_desc(&tmC);
+        if (MODE >= 3) tma_prefetch_desc(&tmD);
     }
     if (warp == 5) {
         if (lane == 0) {
             for (int i = 0; i < kTrStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
             mbar_init(&bars->acc_full, 1);
+            mbar_init(&bars->aux_full, 1);
             fence_mbar_init();
         }
         __syncwarp();
@@ -89,8 +104,14 @@ tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     grid_dep_wait();                 // PDL: everything above overlapped the previous kernel; its results are visible from here
     grid_dep_launch();
 
+    uint8_t* aux = tiles + stages * kTrStage;                 // MODE 4: the [128 x 128] bf16 tile of pre-activations
     if (warp == 4) {
         if (lane == 0) {
+            if constexpr (MODE == 4) {
+                mbar_expect_tx(&bars->aux_full, kTrStage);
+                tma_load_2d(aux, &tmD, &bars->aux_full, n0, m0);
+                tma_load_2d(aux + kTrBox, &tmD, &bars->aux_full, n0 + 64, m0);
+            }
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % stages, it = i / stages;
                 if (it > 0) mbar_wait(&bars->empty[s], (it - 1) & 1);
@@ -133,7 +154,8 @@ tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool add_bias = bias != nullptr && (MODE != 2 || blockIdx.z == 0);
         mbar_wait(&bars->acc_full, 0);
         tc_fence_after();
-        if constexpr (MODE == 0) {
+        if constexpr (MODE == 0 || MODE == 3 || MODE == 4) {
+            if constexpr (MODE == 4) mbar_wait(&bars->aux_full, 0);
             for (int c = 0; c < 4; ++c) {
                 float v[32];
                 tmem_ld32(taddr + c * 32, v);
@@ -142,12 +164,25 @@ tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int i = 0; i < 32; ++i) { const int col = n0 + c * 32 + i; v[i] += col < N ? __ldg(bias + col) : 0.f; }
                 }
-                uint8_t* chunk = tiles + (c >> 1) * kTrBox;             // 64 bf16 columns per [128 x 128 B] staging chunk
+                if constexpr (MODE == 4) {                              // dz = dh GELU'(z)
+                    const uint8_t* zc = aux + (c >> 1) * kTrBox;
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    st_shared_v4(chunk + sw128_offset(r, (c & 1) * 4 + u), pack_bf16x2(v[u * 8 + 0], v[u * 8 + 1]),
-                                 pack_bf16x2(v[u * 8 + 2], v[u * 8 + 3]), pack_bf16x2(v[u * 8 + 4], v[u * 8 + 5]),
-                                 pack_bf16x2(v[u * 8 + 6], v[u * 8 + 7]));
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 w = ld_shared_f4(zc + sw128_offset(r, (c & 1) * 4 + u));
+                        const uint32_t ww[4] = {__float_as_uint(w.x), __float_as_uint(w.y), __float_as_uint(w.z), __float_as_uint(w.w)};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            v[u * 8 + 2 * e] *= gelu_grad_exact(__uint_as_float(ww[e] << 16));
+                            v[u * 8 + 2 * e + 1] *= gelu_grad_exact(__uint_as_float(ww[e] & 0xffff0000u));
+                        }
+                    }
+                }
+                stage_bf16_32(tiles + (c >> 1) * kTrBox, r, c & 1, v);   // 64 bf16 columns per [128 x 128 B] staging chunk
+                if constexpr (MODE == 3) {                              // h = GELU(z) of the bf16 z the backward pass will read
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = gelu_exact(bf16_round(v[i]));
+                    stage_bf16_32(tiles + (2 + (c >> 1)) * kTrBox, r, c & 1, v);
+                }
             }
         } else {
             for (int c = 0; c < 4; ++c) {
@@ -164,8 +199,10 @@ tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_proxy_async();
         named_bar_sync(1, 128);
         if (threadIdx.x == 0) {
-            if constexpr (MODE == 0) {
+            if constexpr (MODE == 0 || MODE == 3 || MODE == 4) {
                 for (int cc = 0; cc < 2; ++cc) tma_store_2d(&tmC, tiles + cc * kTrBox, n0 + cc * 64, m0);
+                if constexpr (MODE == 3)
+                    for (int cc = 0; cc < 2; ++cc) tma_store_2d(&tmD, tiles + (2 + cc) * kTrBox, n0 + cc * 64, m0);
             } else if constexpr (MODE == 1) {
                 for (int c = 0; c < 4; ++c) tma_store_2d(&tmC, tiles + c * kTrBox, n0 + c * 32, m0);
             } else {
@@ -181,27 +218,29 @@ tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int MODE, bool TN>
-int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const float* bias, int N, int kb_total,
-                int kb_per_split, dim3 grid, cudaStream_t s) {
+int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmD, const float* bias, int N,
+                int kb_total, int kb_per_split, dim3 grid, cudaStream_t s) {
     static bool configured[64] = {false};                 // the attribute is per device
     int dev = 0;
     MMF_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        MMF_CUDA_OK(cudaFuncSetAttribute(tr_gemm_kernel<MODE, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem_bytes(kTrStages)));
+        MMF_CUDA_OK(cudaFuncSetAttribute(tr_gemm_kernel<MODE, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, tr_smem_bytes(kTrStages + 1)));
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     // the epilogue stages the whole output tile in the ring: two stages hold it (64 KB fp32)
     const int stages = kb_per_split < 2 ? 2 : (kb_per_split > kTrStages ? kTrStages : kb_per_split);
-    MMF_CUDA_OK(tr_launch(tr_gemm_kernel<MODE, TN>, grid, dim3(192), tr_smem_bytes(stages), s, tmA, tmB, tmC, bias, N, kb_total, kb_per_split, stages));
+    const int smem = tr_smem_bytes(stages + (MODE == 4 ? 1 : 0));           // + the pre-activation tile
+    MMF_CUDA_OK(tr_launch(tr_gemm_kernel<MODE, TN>, grid, dim3(192), smem, s, tmA, tmB, tmC, tmD, bias, N, kb_total, kb_per_split, stages));
     return 0;
 }
 
 }  // namespace
 
 int launch_tr_gemm(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N, int K,
-                   const float* bias, int mode, int ksplit, cudaStream_t s) {
+                   const float* bias, int mode, int ksplit, void* aux, long long ldaux, cudaStream_t s) {
     MMF_REQUIRE(A && B && C, "gemm: null operand");
-    MMF_REQUIRE(mode >= 0 && mode <= 2, "gemm: mode is 0 (bf16 store), 1 (fp32 store) or 2 (fp32 reduce-add)");
+    MMF_REQUIRE(mode >= 0 && mode <= 4, "gemm: mode is 0 (bf16), 1 (fp32), 2 (fp32 reduce-add), 3 (bf16 + GELU copy), 4 (bf16 times GELU'(aux))");
+    MMF_REQUIRE(mode < 3 || aux, "gemm: modes 3 and 4 need the auxiliary [M x N] bf16 tensor");
     if (M <= 0 || N <= 0) return 0;
     MMF_REQUIRE(K > 0, "gemm: K must be positive");
     const int kb_total = (K + kBK - 1) / kBK;
@@ -209,16 +248,20 @@ int launch_tr_gemm(const void* A, long long lda, const void* B, long long ldb, v
     if (ksplit > kb_total) ksplit = kb_total;
     const int per = (kb_total + ksplit - 1) / ksplit;
     ksplit = (kb_total + per - 1) / per;                  // no empty split
-    CUtensorMap tmA, tmB, tmC;
+    CUtensorMap tmA, tmB, tmC, tmD;
     if (make_tmap_2d(&tmA, A, 2, M, K, lda, 64, 128)) return 1;
     if (make_tmap_2d(&tmB, B, 2, N, K, ldb, 64, 128)) return 1;
-    if (mode == 0) { if (make_tmap_2d(&tmC, C, 2, M, N, ldc, 64, 128)) return 1; }
+    if (mode == 0 || mode >= 3) { if (make_tmap_2d(&tmC, C, 2, M, N, ldc, 64, 128)) return 1; }
     else { if (make_tmap_2d(&tmC, C, 4, M, N, ldc, 32, 128)) return 1; }
+    tmD = tmC;
+    if (mode >= 3 && make_tmap_2d(&tmD, aux, 2, M, N, ldaux, 64, 128)) return 1;
     const dim3 grid((M + kTileM - 1) / kTileM, (N + 127) / 128, ksplit);
     switch (mode) {
-        case 0: return launch_mode<0, false>(tmA, tmB, tmC, bias, N, kb_total, per, grid, s);
-        case 1: return launch_mode<1, false>(tmA, tmB, tmC, bias, N, kb_total, per, grid, s);
-        default: return launch_mode<2, false>(tmA, tmB, tmC, bias, N, kb_total, per, grid, s);
+        case 0: return launch_mode<0, false>(tmA, tmB, tmC, tmD, bias, N, kb_total, per, grid, s);
+        case 1: return launch_mode<1, false>(tmA, tmB, tmC, tmD, bias, N, kb_total, per, grid, s);
+        case 2: return launch_mode<2, false>(tmA, tmB, tmC, tmD, bias, N, kb_total, per, grid, s);
+        case 3: return launch_mode<3, false>(tmA, tmB, tmC, tmD, bias, N, kb_total, per, grid, s);
+        default: return launch_mode<4, false>(tmA, tmB, tmC, tmD, bias, N, kb_total, per, grid, s);
     }
 }
 
@@ -238,7 +281,7 @@ int launch_tr_gemm_tn(const void* A, long long lda, const void* B, long long ldb
     if (make_tmap_2d(&tmB, B, 2, K, N, ldb, 64, 64)) return 1;
     if (make_tmap_2d(&tmC, C, 4, M, N, ldc, 32, 128)) return 1;
     const dim3 grid((M + kTileM - 1) / kTileM, (N + 127) / 128, ksplit);
-    return launch_mode<2, true>(tmA, tmB, tmC, nullptr, N, kb_total, per, grid, s);
+    return launch_mode<2, true>(tmA, tmB, tmC, tmC, nullptr, N, kb_total, per, grid, s);
 }
 
 }  // namespace mmf

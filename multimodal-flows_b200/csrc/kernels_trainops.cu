@@ -282,11 +282,11 @@ __global__ void __launch_bounds__(256) tr_ln_bwd_kernel(const TrLnBwdArgs a) {
     grid_dep_wait();
     grid_dep_launch();
     constexpr int NV = C / 128;
-    __shared__ float red[2][8][C];
+    __shared__ float red[3][8][C];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float accg[NV * 4], accb[NV * 4];
+    float accg[NV * 4], accb[NV * 4], accx[NV * 4];
 #pragma unroll
-    for (int i = 0; i < NV * 4; ++i) { accg[i] = 0.f; accb[i] = 0.f; }
+    for (int i = 0; i < NV * 4; ++i) { accg[i] = 0.f; accb[i] = 0.f; accx[i] = 0.f; }
     for (int r = blockIdx.x * 8 + warp; r < a.M; r += gridDim.x * 8) {
         const float mean = a.mean[r], rstd = a.rstd[r];
         float xh[NV * 4], dxh[NV * 4];
@@ -325,6 +325,9 @@ __global__ void __launch_bounds__(256) tr_ln_bwd_kernel(const TrLnBwdArgs a) {
             float4* dst = reinterpret_cast<float4*>(a.dx + r * a.lddx + c);
             if (a.accumulate) { const float4 o = *dst; d.x += o.x; d.y += o.y; d.z += o.z; d.w += o.w; }
             *dst = d;
+            // the new gradient as the bf16 operand of the next linear's products, and its column sums (that linear's bias gradient)
+            if (a.dx16) *reinterpret_cast<uint2*>(a.dx16 + r * a.ld16 + c) = make_uint2(pack2(d.x, d.y), pack2(d.z, d.w));
+            accx[q * 4] += d.x; accx[q * 4 + 1] += d.y; accx[q * 4 + 2] += d.z; accx[q * 4 + 3] += d.w;
         }
     }
 #pragma unroll
@@ -333,14 +336,16 @@ __global__ void __launch_bounds__(256) tr_ln_bwd_kernel(const TrLnBwdArgs a) {
         for (int e = 0; e < 4; ++e) {
             red[0][warp][q * 128 + lane * 4 + e] = accg[q * 4 + e];
             red[1][warp][q * 128 + lane * 4 + e] = accb[q * 4 + e];
+            red[2][warp][q * 128 + lane * 4 + e] = accx[q * 4 + e];
         }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += 256) {
-        float sg = 0.f, sb = 0.f;
+        float sg = 0.f, sb = 0.f, sx = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { sg += red[0][w][c]; sb += red[1][w][c]; }
+        for (int w = 0; w < 8; ++w) { sg += red[0][w][c]; sb += red[1][w][c]; sx += red[2][w][c]; }
         atomicAdd(a.dg + c, sg);
         if (a.db) atomicAdd(a.db + c, sb);
+        if (a.dxsum) atomicAdd(a.dxsum + c, sx);
     }
 }
 

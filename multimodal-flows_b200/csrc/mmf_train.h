@@ -23,9 +23,10 @@ inline cudaError_t tr_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-// C[M x N] (+)= A[M x K] B[N x K]^T (+ bias); mode 0: bf16 store, 1: fp32 store, 2: fp32 reduce-add (K split over `ksplit` CTAs)
+// C[M x N] (+)= A[M x K] B[N x K]^T (+ bias); mode 0: bf16 store, 1: fp32 store, 2: fp32 reduce-add (K split over `ksplit` CTAs),
+// 3: bf16 store + aux = GELU(C) (bf16), 4: bf16 store of the product times GELU'(aux) (aux: bf16 pre-activations)
 int launch_tr_gemm(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N, int K,
-                   const float* bias, int mode, int ksplit, cudaStream_t s);
+                   const float* bias, int mode, int ksplit, void* aux, long long ldaux, cudaStream_t s);
 
 // C[M x N] += A^T B, A [K x M], B [K x N] row-major bf16 (weight gradient from row-major activations, MN-major operands)
 int launch_tr_gemm_tn(const void* A, long long lda, const void* B, long long ldb, float* C, long long ldc, int M, int N, int K, int ksplit,
@@ -71,6 +72,8 @@ struct TrLnBwdArgs {
     int M, C;
     float* dx; long long lddx; int accumulate;
     float *dg, *db;                          // atomically accumulated (db may be null)
+    bf16* dx16; long long ld16;              // optional: bf16 copy of the final dx (operand of the next linear's products)
+    float* dxsum;                            // optional: += column sums of the final dx (that linear's bias gradient)
 };
 int launch_tr_ln_bwd(const TrLnBwdArgs& a, cudaStream_t s);
 

@@ -13,8 +13,8 @@ using namespace mmf;
 extern "C" {
 
 int mmf_tr_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
-                const float* bias, int32_t mode, int32_t ksplit, void* stream) {
-    return launch_tr_gemm(A, lda, B, ldb, C, ldc, M, N, K, bias, mode, ksplit, S_(stream));
+                const float* bias, int32_t mode, int32_t ksplit, void* aux, int64_t ldaux, void* stream) {
+    return launch_tr_gemm(A, lda, B, ldb, C, ldc, M, N, K, bias, mode, ksplit, aux, ldaux, S_(stream));
 }
 
 int mmf_tr_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
@@ -76,9 +76,9 @@ int mmf_tr_ln_fwd(const float* x, int64_t ldx, const float* add, int64_t lda, co
 }
 int mmf_tr_ln_bwd(const float* dy, int64_t lddy, const float* x, int64_t ldx, const float* add, int64_t lda, const float* mean,
                   const float* rstd, const float* g, int32_t M, int32_t C, float* dx, int64_t lddx, int32_t accumulate, float* dg, float* db,
-                  void* stream) {
+                  void* dx_bf16, int64_t ld16, float* dxsum, void* stream) {
     MMF_REQUIRE(M == 0 || (dy && x && mean && rstd && g && dx && dg), "layernorm backward: null argument");
-    TrLnBwdArgs a{dy, lddy, x, ldx, add, lda, mean, rstd, g, M, C, dx, lddx, accumulate, dg, db};
+    TrLnBwdArgs a{dy, lddy, x, ldx, add, lda, mean, rstd, g, M, C, dx, lddx, accumulate, dg, db, BF(dx_bf16), ld16, dxsum};
     return launch_tr_ln_bwd(a, S_(stream));
 }
 

@@ -14,7 +14,7 @@ from . import _abi
 P, I32, I64, F = c_void_p, c_int32, c_int64, c_float
 
 SIGNATURES = {
-    "mmf_tr_gemm": [P, I64, P, I64, P, I64, I32, I32, I32, P, I32, I32, P],
+    "mmf_tr_gemm": [P, I64, P, I64, P, I64, I32, I32, I32, P, I32, I32, P, I64, P],
     "mmf_tr_gemm_tn": [P, I64, P, I64, P, I64, I32, I32, I32, I32, P],
     "mmf_tr_sgemm": [P, I64, I64, P, I64, I64, P, I64, I32, I32, I32, P, I32, P],
     "mmf_tr_cast_transpose": [P, I64, I32, I32, I32, P, I64, P, I64, P, P],
@@ -26,7 +26,7 @@ SIGNATURES = {
     "mmf_tr_embed_y_fwd": [P, I32, P, I32, I32, P, I64, P],
     "mmf_tr_embed_y_bwd": [P, I64, P, I32, P, I32, I32, P, P],
     "mmf_tr_ln_fwd": [P, I64, P, I64, P, P, P, I64, P, I32, I32, P, I64, P, I64, P, P, P],
-    "mmf_tr_ln_bwd": [P, I64, P, I64, P, I64, P, P, P, I32, I32, P, I64, I32, P, P, P],
+    "mmf_tr_ln_bwd": [P, I64, P, I64, P, I64, P, P, P, I32, I32, P, I64, I32, P, P, P, I64, P, P],
     "mmf_tr_qkln_fwd": [P, I64, I32, I32, I32, P, P, P, P, P, P, I64, P],
     "mmf_tr_qkln_bwd": [P, I64, P, I64, I32, I32, I32, P, P, P, P, P, P, P],
     "mmf_tr_attn_fwd": [P, I64, P, I64, P, I64, P, P, I32, I32, I32, I32, I32, P, I64, P, P],
@@ -83,11 +83,13 @@ class Ops:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     # C[M,N] (+)= A[M,K] B[N,K]^T (+ bias)
-    def gemm(self, A, B, C, bias=None, mode=0, ksplit=1):
+    def gemm(self, A, B, C, bias=None, mode=0, ksplit=1, aux=None):
         M, K = A.shape
         N = B.shape[0]
         assert B.shape[1] == K and tuple(C.shape) == (M, N) and A.stride(1) == 1 and B.stride(1) == 1 and C.stride(1) == 1
-        _abi.check(self.L.mmf_tr_gemm(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, N, K, _p(bias), mode, ksplit, self._s()))
+        assert (mode >= 3) == (aux is not None) and (aux is None or (tuple(aux.shape) == (M, N) and aux.stride(1) == 1))
+        _abi.check(self.L.mmf_tr_gemm(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, N, K, _p(bias), mode, ksplit, _p(aux),
+                                      _ld(aux), self._s()))
 
     # C[M,N] += A^T B, A [K,M], B [K,N] row-major bf16
     def gemm_tn(self, A, B, C, ksplit=1):
@@ -132,10 +134,10 @@ class Ops:
         _abi.check(self.L.mmf_tr_ln_fwd(_p(x), x.stride(0), _p(add), _ld(add), _p(g), _p(b), _p(tadd), _ld(tadd), _p(row_jet), M, C,
                                         _p(out16), _ld(out16), _p(out32), _ld(out32), _p(mean), _p(rstd), self._s()))
 
-    def ln_bwd(self, dy, x, mean, rstd, g, dx, dg, db, add=None, accumulate=False):
+    def ln_bwd(self, dy, x, mean, rstd, g, dx, dg, db, add=None, accumulate=False, dx16=None, dxsum=None):
         M, C = x.shape
         _abi.check(self.L.mmf_tr_ln_bwd(_p(dy), dy.stride(0), _p(x), x.stride(0), _p(add), _ld(add), _p(mean), _p(rstd), _p(g), M, C,
-                                        _p(dx), dx.stride(0), int(accumulate), _p(dg), _p(db), self._s()))
+                                        _p(dx), dx.stride(0), int(accumulate), _p(dg), _p(db), _p(dx16), _ld(dx16), _p(dxsum), self._s()))
 
     def qkln_fwd(self, qkv, C, H, qg, qb, kg, kb, qn, kn):
         _abi.check(self.L.mmf_tr_qkln_fwd(_p(qkv), qkv.stride(0), qkv.shape[0], C, H, _p(qg), _p(qb), _p(kg), _p(kb), _p(qn), _p(kn),

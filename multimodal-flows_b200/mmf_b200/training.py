@@ -253,20 +253,21 @@ class TrainEngine:
         self._keep.clear()
 
     # ---- nn.Linear on packed rows ----------------------------------------------------------------------------------------
-    def _lin_fwd(self, x16, name, out, mode):
-        self.ops.gemm(x16, self.w16(name + ".weight"), out, self.p(name + ".bias"), mode)
+    def _lin_fwd(self, x16, name, out, mode, aux=None):
+        self.ops.gemm(x16, self.w16(name + ".weight"), out, self.p(name + ".bias"), mode, aux=aux)
 
     def _ksplit(self, plan, n_out, n_in):
         tiles = ((n_out + 127) // 128) * ((n_in + 127) // 128)
         kb = (plan.M + 63) // 64
         return max(1, min(kb // 4, max(1, 296 // tiles)))
 
-    def _lin_bwd(self, plan, dy16, x16, name, dx=None, dx_mode=1, dy_src=None):
+    def _lin_bwd(self, plan, dy16, x16, name, dx=None, dx_mode=1, dy_src=None, bias_done=False, aux=None):
         """dy16 [M, N], x16 [M, K] bf16 row-major (column slices allowed).  dW += dy^T x (both operands read MN-major by the
-        tensor cores: no transposed copies), db += colsum(dy), dx = dy W.  dy_src: fp32 source that is first cast into dy16."""
+        tensor cores: no transposed copies), db += colsum(dy) unless the producer of dy16 already added it (bias_done), dx = dy W
+        (dx_mode 4: times GELU'(aux), the data gradient straight through the activation).  dy_src: fp32 source first cast into dy16."""
         ops = self.ops
         N, K = self.shape[name + ".weight"]
-        db = self.g(name + ".bias")
+        db = None if bias_done else self.g(name + ".bias")
         if dy_src is not None:
             ops.cast_transpose(dy_src, out=dy16, colsum=db)
             db = None
@@ -278,7 +279,7 @@ class TrainEngine:
             ops.gemm_tn(dy16, x16, self.g(name + ".weight"), ks)
         self._wgrad_side(wgrad, dy16, x16)
         if dx is not None:
-            ops.gemm(dy16, self.wT16(name + ".weight"), dx, None, dx_mode)
+            ops.gemm(dy16, self.wT16(name + ".weight"), dx, None, dx_mode, aux=aux)
 
     # ---- one SelfAttnBlock (reference networks/attention.py:23-26) on columns of the 256-wide residual buffers ------------
     def _block_fwd(self, plan, Rin, R1, R2, pre, tadd):
@@ -310,28 +311,30 @@ class TrainEngine:
         s["a2"], s["m2"], s["r2"] = torch.empty(M, C, **bf), torch.empty(M, device=dev), torch.empty(M, device=dev)
         ops.ln_fwd(R1, self.p(pre + ".ln2.weight"), self.p(pre + ".ln2.bias"), s["m2"], s["r2"], out16=s["a2"])
         s["z"], s["hh"] = torch.empty(M, I, **bf), torch.empty(M, I, **bf)
-        self._lin_fwd(s["a2"], pre + ".ffw.c_fc", s["z"], 0)
-        ops.gelu_fwd(s["z"], s["hh"])
+        self._lin_fwd(s["a2"], pre + ".ffw.c_fc", s["z"], 3, aux=s["hh"])      # z and GELU(z) leave the same epilogue
         self._lin_fwd(s["hh"], pre + ".ffw.c_proj", y, 1)
         ops.add(R2, R1, y, tadd, plan.row_jet)
         return s
 
-    def _block_bwd(self, plan, s, G):
-        """G [M, C] fp32: gradient w.r.t. the block's output on entry, w.r.t. its input on exit."""
+    def _block_bwd(self, plan, s, G, g16=None, nxt=None):
+        """G [M, C] fp32: gradient w.r.t. the block's output on entry, w.r.t. its input on exit.  g16: its bf16 copy when the
+        producer of G already made one (and added its column sums to ffw.c_proj.bias); nxt = (bf16 buffer, bias gradient) that
+        the last LayerNorm backward of this block fills for the block processed next."""
         ops, dev, M = self.ops, self.device, plan.M
         C, pre, H, I = s["C"], s["pre"], self.H, self.I
         hs = C // H
         bf = dict(device=dev, dtype=torch.bfloat16)
-        G16 = torch.empty(M, C, **bf)
-        dh = torch.empty(M, I, **bf)
-        self._lin_bwd(plan, G16, s["hh"], pre + ".ffw.c_proj", dx=dh, dx_mode=0, dy_src=G)
-        ops.gelu_bwd(dh, s["z"], dh)
+        dz = torch.empty(M, I, **bf)
+        if g16 is None:
+            self._lin_bwd(plan, torch.empty(M, C, **bf), s["hh"], pre + ".ffw.c_proj", dx=dz, dx_mode=4, dy_src=G, aux=s["z"])
+        else:
+            self._lin_bwd(plan, g16, s["hh"], pre + ".ffw.c_proj", dx=dz, dx_mode=4, bias_done=True, aux=s["z"])
         da = torch.empty(M, C, device=dev)
-        self._lin_bwd(plan, dh, s["a2"], pre + ".ffw.c_fc", dx=da, dx_mode=1)
-        ops.ln_bwd(da, s["R1"], s["m2"], s["r2"], self.p(pre + ".ln2.weight"), G, self.g(pre + ".ln2.weight"), self.g(pre + ".ln2.bias"),
-                   accumulate=True)
+        self._lin_bwd(plan, dz, s["a2"], pre + ".ffw.c_fc", dx=da, dx_mode=1)
         do, G16b = torch.empty(M, C, **bf), torch.empty(M, C, **bf)
-        self._lin_bwd(plan, G16b, s["o"], pre + ".attn.c_proj", dx=do, dx_mode=0, dy_src=G)
+        ops.ln_bwd(da, s["R1"], s["m2"], s["r2"], self.p(pre + ".ln2.weight"), G, self.g(pre + ".ln2.weight"), self.g(pre + ".ln2.bias"),
+                   accumulate=True, dx16=G16b, dxsum=self.g(pre + ".attn.c_proj.bias"))
+        self._lin_bwd(plan, G16b, s["o"], pre + ".attn.c_proj", dx=do, dx_mode=0, bias_done=True)
         dqkv = torch.zeros(M, 3 * C, **bf) if plan.padded else torch.empty(M, 3 * C, **bf)
         ops.attn_tc_bwd(do, s["qn"], s["kn"], s["qkv"][:, 2 * C:], hs, plan.items, plan.n_items, plan.grid_items, plan.row_jet, plan.jet_off,
                         s["stats"], dqkv)
@@ -344,7 +347,19 @@ class TrainEngine:
                          self.g(pre + ".attn.k_layernorm.weight"), self.g(pre + ".attn.k_layernorm.bias"))
         self._lin_bwd(plan, dqkv, s["a1"], pre + ".attn.c_attn", dx=da, dx_mode=1)
         ops.ln_bwd(da, s["Rin"], s["m1"], s["r1"], self.p(pre + ".ln1.weight"), G, self.g(pre + ".ln1.weight"), self.g(pre + ".ln1.bias"),
-                   accumulate=True)
+                   accumulate=True, dx16=None if nxt is None else nxt[0], dxsum=None if nxt is None else nxt[1])
+
+    def _chain_bwd(self, plan, chain, G, g16, before=None):
+        """Backward through a chain of blocks (last block first); g16 = bf16 copy of G for the first one processed."""
+        order = list(reversed(chain))
+        for i, s in enumerate(order):
+            if before is not None:
+                before()
+            nxt = None
+            if i + 1 < len(order):
+                nxt = (torch.empty(plan.M, s["C"], device=self.device, dtype=torch.bfloat16), self.g(order[i + 1]["pre"] + ".ffw.c_proj.bias"))
+            self._block_bwd(plan, s, G, g16, nxt)
+            g16 = None if nxt is None else nxt[0]
 
     # ---- encoder forward on packed rows (reference ParticleTransformers.py:62-122 / 177-210) ------------------------------
     def _forward(self, plan, xs, ks, t):
@@ -478,42 +493,46 @@ class TrainEngine:
         dxf = f32(M, 256)
         for gi, nm in enumerate(("head_x.0", "head_y.0")):
             self._lin_bwd(plan, dzh[:, gi * I:(gi + 1) * I], c["xf"][:, gi * h:(gi + 1) * h], T + nm, dx=dxf[:, gi * h:(gi + 1) * h], dx_mode=1)
-        # final LayerNorm(s): d/d(z + skip) goes to the residual stream and to the skip connection alike
+        # final LayerNorm(s): d/d(z + skip) goes to the residual stream and to the skip connection alike; the same kernels hand the
+        # first block of the backward chain its bf16 operand and bias column sums
         G, R = f32(M, 256), c["Rlast"]
+        blocks, ns = c["blocks"], c["n_stream_blocks"]
+        main = blocks[ns:]
+        g16 = torch.empty(M, 256, **bf)
+        last_bias = self.g(main[-1]["pre"] + ".ffw.c_proj.bias")
         if self.pf:
             for gi, nm in enumerate(("ln3_x", "ln3_y")):
                 cols = slice(gi * h, (gi + 1) * h)
                 ops.ln_bwd(dxf[:, cols], R[:, cols], c["fm"][gi], c["fr"][gi], self.p(T + nm + ".weight"), G[:, cols], self.g(T + nm + ".weight"),
-                           self.g(T + nm + ".bias"), add=c["skip"][:, cols])
+                           self.g(T + nm + ".bias"), add=c["skip"][:, cols], dx16=g16[:, cols], dxsum=None if last_bias is None else last_bias[cols])
         else:
-            ops.ln_bwd(dxf, R, c["fm"][0], c["fr"][0], self.p(T + "ln2.weight"), G, self.g(T + "ln2.weight"), self.g(T + "ln2.bias"), add=c["skip"])
+            ops.ln_bwd(dxf, R, c["fm"][0], c["fr"][0], self.p(T + "ln2.weight"), G, self.g(T + "ln2.weight"), self.g(T + "ln2.bias"), add=c["skip"],
+                       dx16=g16, dxsum=last_bias)
         Gskip = f32(M, 256)
         ops.add(Gskip, G)
-        blocks, ns = c["blocks"], c["n_stream_blocks"]
         if self.pf:
             dt2 = torch.zeros(B, E, device=dev)
-            for s in reversed(blocks[ns:]):
-                ops.jet_sum(G, plan.jet_off, B, dt2, accumulate=True)
-                self._block_bwd(plan, s, G)
+            self._chain_bwd(plan, main, G, g16, before=lambda: ops.jet_sum(G, plan.jet_off, B, dt2, accumulate=True))
             ops.jet_sum(G, plan.jet_off, B, dt2, accumulate=True)
             w = T + "time_expand."
             ops.sgemm(dt2, 1, E, c["temb"], 256, 1, self.g(w + "weight"), E, h, B, accumulate=True)
             ops.cast_transpose(dt2, colsum=self.g(w + "bias"))
             G2 = f32(M, 256)
+            chains = [blocks[: ns // 2], blocks[ns // 2: ns]]
+            g16s = [torch.empty(M, h, **bf), torch.empty(M, h, **bf)]
             for gi, nm in enumerate(("ln2_x", "ln2_y")):
                 cols = slice(gi * h, (gi + 1) * h)
                 ops.ln_bwd(G[:, cols], c["Rmid"][:, cols], c["mm"][gi], c["mr"][gi], self.p(T + nm + ".weight"), G2[:, cols],
-                           self.g(T + nm + ".weight"), self.g(T + nm + ".bias"), add=c["skip"][:, cols])
+                           self.g(T + nm + ".weight"), self.g(T + nm + ".bias"), add=c["skip"][:, cols], dx16=g16s[gi],
+                           dxsum=self.g(chains[gi][-1]["pre"] + ".ffw.c_proj.bias"))
             ops.add(Gskip, Gskip, G2)
             G = G2
             with self._branches(2) as br:
                 for gi in range(2):
                     with br(gi):
-                        for s in reversed(blocks[gi * (ns // 2):(gi + 1) * (ns // 2)]):
-                            self._block_bwd(plan, s, G[:, gi * h:(gi + 1) * h])
+                        self._chain_bwd(plan, chains[gi], G[:, gi * h:(gi + 1) * h], g16s[gi])
         else:
-            for s in reversed(blocks):
-                self._block_bwd(plan, s, G)
+            self._chain_bwd(plan, main, G, g16)
         ops.add(G, G, Gskip)
         # embeddings
         du = f32(M, 256)

@@ -18,12 +18,18 @@ class MockOps:
     def __init__(self):
         self.launches = 0
 
-    def gemm(self, A, B, C, bias=None, mode=0, ksplit=1):
+    def gemm(self, A, B, C, bias=None, mode=0, ksplit=1, aux=None):
         r = _f(A) @ _f(B).T
         if bias is not None:
             r = r + bias
         if mode == 2:
             C += r
+        elif mode == 3:
+            C.copy_(r.to(C.dtype))
+            aux.copy_(F.gelu(_f(C)).to(aux.dtype))
+        elif mode == 4:
+            zz = _f(aux).clone().requires_grad_(True)
+            C.copy_(torch.autograd.grad(F.gelu(zz), zz, r)[0].to(C.dtype))
         else:
             C.copy_(r.to(C.dtype))
 
@@ -99,7 +105,7 @@ class MockOps:
         if out16 is not None:
             out16.copy_(y.to(torch.bfloat16))
 
-    def ln_bwd(self, dy, x, mean, rstd, g, dx, dg, db, add=None, accumulate=False):
+    def ln_bwd(self, dy, x, mean, rstd, g, dx, dg, db, add=None, accumulate=False, dx16=None, dxsum=None):
         v = x + add if add is not None else x
         xh = (v - mean[:, None]) * rstd[:, None]
         dxh = dy * g
@@ -111,6 +117,10 @@ class MockOps:
         dg += (dy * xh).sum(0)
         if db is not None:
             db += dy.sum(0)
+        if dx16 is not None:
+            dx16.copy_(dx.to(torch.bfloat16))
+        if dxsum is not None:
+            dxsum += dx.sum(0)
 
     def qkln_fwd(self, qkv, C, H, qg, qb, kg, kb, qn, kn):
         M, hs = qkv.shape[0], C // H

@@ -48,6 +48,26 @@ def test_gemm_store_modes(ops, M, N, K, mode):
     assert rel(C.float(), want) < (4e-3 if mode == 0 else 2e-6), rel(C.float(), want)
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 512, 128), (13819, 512, 256), (1000, 256, 512)])
+def test_gemm_gelu_epilogues(ops, M, N, K):
+    """mode 3: z = x W^T + b and h = GELU(z) from one epilogue (h is the GELU of the bf16 z the backward pass reads);
+    mode 4: dz = (dh W) * GELU'(z) with the z tile loaded next to the accumulator"""
+    g = torch.Generator(device=DEV).manual_seed(M + K)
+    A, B = bf(torch.randn(M, K, device=DEV, generator=g)), bf(torch.randn(N, K, device=DEV, generator=g) * 0.1)
+    bias = torch.randn(N, device=DEV, generator=g)
+    z, h = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16), torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, B, z, bias, 3, aux=h)
+    want = A.float() @ B.float().T + bias
+    assert rel(z.float(), want) < 4e-3
+    assert rel(h.float(), torch.nn.functional.gelu(z.float())) < 3e-3
+    zin = bf(torch.randn(M, N, device=DEV, generator=g) * 1.5)
+    dz = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, B, dz, None, 4, aux=zin)
+    zz = zin.float().clone().requires_grad_(True)
+    torch.nn.functional.gelu(zz).backward(A.float() @ B.float().T)
+    assert rel(dz.float(), zz.grad) < 4e-3, rel(dz.float(), zz.grad)
+
+
 def test_gemm_strided_views_and_no_bias(ops):
     g = torch.Generator(device=DEV).manual_seed(5)
     big_a, big_c = bf(torch.randn(500, 256, device=DEV, generator=g)), torch.zeros(500, 1024, device=DEV, dtype=torch.bfloat16)
@@ -128,9 +148,12 @@ def test_layernorm_forward_backward(ops, C):
     y.backward(dy)
     dx0 = torch.randn(M, 256, device=DEV, generator=g)
     dx, dg, db = dx0.clone(), torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
-    ops.ln_bwd(dy, xv, mean, rstd, gam, dx[:, :C], dg, db, add=av, accumulate=True)
+    dx16, dxsum = torch.zeros(M, 256, device=DEV, dtype=torch.bfloat16), torch.ones(C, device=DEV)
+    ops.ln_bwd(dy, xv, mean, rstd, gam, dx[:, :C], dg, db, add=av, accumulate=True, dx16=dx16[:, 256 - C:], dxsum=dxsum)
     assert rel(dx[:, :C] - dx0[:, :C], xs.grad) < 1e-5 and torch.equal(dx[:, C:], dx0[:, C:])
     assert rel(dg, gp.grad) < 1e-5 and rel(db, bp.grad) < 1e-5
+    # the hand-off to the next linear: bf16 copy of the accumulated gradient and its column sums
+    assert torch.equal(dx16[:, 256 - C:], bf(dx[:, :C])) and rel(dxsum, 1.0 + dx[:, :C].sum(0)) < 1e-5
 
 
 @pytest.mark.parametrize("C,H", [(128, 4), (256, 4)])
