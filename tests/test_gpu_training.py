@@ -155,3 +155,56 @@ def test_cuda_graph_replay_equals_eager_launches(golden_dir):
         assert rel < 1e-4, (i, rel)                                      # atomics order differs, nothing else
     eager.optimizer_step(); graph.optimizer_step()
     assert float((eager.P - graph.P).abs().max()) < 1e-5
+
+
+def _random_case(cfg, ns, seed):
+    from mmf_b200 import synthetic
+    from mmf_b200.tensorclass import DataCoupling, TensorMultiModal
+    g = torch.Generator().manual_seed(seed)
+    B, D, V = len(ns), cfg.max_num_particles, cfg.vocab_size
+    mask = synthetic.prefix_masks(torch.tensor(ns), D)
+    x0 = torch.randn(B, D, 3, generator=g) * mask
+    k0 = torch.randint(1, V, (B, D, 1), generator=g) * mask
+    x1 = (torch.randn(B, D, 3, generator=g) * 1.5 + 0.3) * mask
+    k1 = torch.randint(0, V, (B, D, 1), generator=g) * mask          # token 0 among the targets: ignore_index
+    t, z, u = torch.rand(B, generator=g) * 0.98 + 0.01, torch.randn(B, D, 3, generator=g), torch.rand(B, D, generator=g)
+    batch = DataCoupling(source=TensorMultiModal(continuous=x0, discrete=k0, mask=mask), target=TensorMultiModal(continuous=x1, discrete=k1, mask=mask))
+    return batch, (x0, k0, x1, k1, mask, t, z, u)
+
+
+@pytest.mark.parametrize("model,ns,overrides,graphs", [
+    ("FusedParticleFormer", [0, 1, 150, 37, 0, 129, 128, 2], {}, False),            # empty jets, single particles, CUDA-core attention jets
+    ("FusedParticleFormer", [0, 1, 150, 37, 0, 129, 128, 2], {}, True),
+    ("ParticleFormer", [77], {}, True),                                            # B = 1 (the reference's .squeeze() breaks there)
+    ("ParticleFormer", [150, 150, 150], dict(multitask_loss="sum"), False),        # dense: every jet on the CUDA-core attention path
+    ("FusedParticleFormer", [5, 60, 131], dict(bias=False, qk_layernorm=False), True),
+])
+def test_edge_shapes_and_optional_parameters(model, ns, overrides, graphs):
+    from mmf_b200 import synthetic
+    from mmf_b200.mmf import MultiModalFlowBridge
+    from mmf_b200.param_spec import make_config
+    from mmf_b200.training import TrainEngine
+    from oracle import mmf_oracle as orc
+    cfg = make_config(model, sigma=1e-3, lr=1e-3, n_layer=2, n_layer_fused=2, **overrides)
+    sd = synthetic.make_state_dict(cfg, flavor="wide", seed=21)
+    bridge = MultiModalFlowBridge(cfg)
+    bridge.model.load_state_dict(sd)
+    sd_loss = {k: v.detach().clone() for k, v in bridge.loss_combine.state_dict().items()}
+    bridge = bridge.to(DEV)
+    eng = TrainEngine(bridge, lr=1e-3, use_graphs=graphs)
+    batch, (x0, k0, x1, k1, mask, t, z, u) = _random_case(cfg, ns, seed=len(ns))
+    out5 = eng.loss_and_grad(batch, time=t, z=z, u=u)
+    if graphs:
+        out5 = eng.loss_and_grad(batch, time=t, z=z, u=u)                # and once more as a replay
+    eng.check_tokens()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sdg = {k: v.to(DEV).clone().requires_grad_(True) for k, v in sd.items()}
+    slg = {k: v.to(DEV).clone().requires_grad_(True) for k, v in sd_loss.items()}
+    d = lambda x: x.to(DEV)
+    want = orc.training_loss(sdg, slg, cfg, d(x0), d(k0), d(x1), d(k1), d(mask), d(t), d(z), d(u))
+    want[0].backward()
+    assert abs(float(out5[0]) - float(want[0].detach())) <= 3e-2 * abs(float(want[0].detach())), (float(out5[0]), float(want[0].detach()))
+    grads = {"model." + k: v.grad for k, v in sdg.items()}
+    grads.update({"loss_combine." + k: v.grad for k, v in slg.items()})
+    gcos, grel, _ = compare_gradients(eng, grads, verbose=f"{model} {ns} {overrides} graphs={graphs}")
+    assert gcos > 0.995 and grel < 5e-2

@@ -114,3 +114,33 @@ def test_ddp_gradient_average_over_gloo(golden_dir):
     (_, l0, s0, p0), (_, l1, s1, p1) = got
     assert np.allclose(s0, l0 + l1) and np.array_equal(s0, s1)       # one all-reduce of the flat buffer
     assert np.array_equal(p0, p1)                                       # identical replicas after the step (grad_scale = 1 / world)
+
+
+@pytest.mark.parametrize("overrides", [dict(bias=False), dict(qk_layernorm=False), dict(bias=False, qk_layernorm=False, multitask_loss="sum")])
+def test_program_handles_optional_parameters(overrides, golden_dir):
+    """config.bias = False (no Linear / block-LayerNorm biases) and config.qk_layernorm = False (reference attention.py:32-51): the
+    program skips exactly the operators whose parameters do not exist."""
+    from mmf_b200 import synthetic
+    from mmf_b200.mmf import MultiModalFlowBridge
+    from mmf_b200.param_spec import make_config
+    from mmf_b200.training import TrainEngine
+    from oracle import mmf_oracle as orc
+    g = np.load(os.path.join(golden_dir, "loss_FusedParticleFormer_time-weighted.npz"))
+    cfg = make_config("FusedParticleFormer", sigma=float(g["sigma"]), lr=1e-3, n_layer=2, **overrides)
+    sd = synthetic.make_state_dict(cfg, flavor="wide", seed=3)
+    bridge = MultiModalFlowBridge(cfg)
+    bridge.model.load_state_dict(sd)
+    sd_loss = {k: v.detach().clone() for k, v in bridge.loss_combine.state_dict().items()}
+    eng = TrainEngine(bridge, lr=1e-3, _ops=MockOps())
+    sel = [1, 2]
+    T = lambda n, long=False: (torch.from_numpy(g[n]).long() if long else torch.from_numpy(g[n]))[sel]
+    out5 = _run(eng, cfg, T)
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    slg = {k: v.clone().requires_grad_(True) for k, v in sd_loss.items()}
+    want = orc.training_loss(sdg, slg, cfg, T("x0"), T("k0", True), T("x1"), T("k1", True), T("mask"), T("time"), T("z"), T("u"))
+    want[0].backward()
+    grads = {"model." + k: v.grad for k, v in sdg.items()}
+    grads.update({"loss_combine." + k: v.grad for k, v in slg.items()})
+    assert abs(float(out5[0]) - float(want[0].detach())) < 3e-2 * abs(float(want[0].detach()))
+    gcos, grel, _ = compare_gradients(eng, grads)
+    assert gcos > 0.995 and grel < 5e-2
