@@ -22,11 +22,14 @@ extern "C" {
  *   C[M x N] (+)= A[M x K] B[N x K]^T (+ bias[N]); A, B bf16 with K contiguous (lda, ldb multiples of 8, 16-byte aligned bases).
  *   mode 0: C bf16;  mode 1: C fp32;  mode 2: C fp32 += (TMA reduce-add; K is split over `ksplit` CTAs, bias added once);
  *   mode 3: C bf16 and aux = GELU(C) bf16 (MLP.c_fc + nn.GELU in one pass, utils/models.py:15-16);
- *   mode 4: C = bf16(product * GELU'(aux)), aux = the bf16 pre-activations (data gradient of MLP.c_proj through the GELU).
- * aux [M x N] bf16 with row pitch ldaux (modes 3, 4; else null).
+ *   mode 4: C = bf16(product * GELU'(aux)), aux = the bf16 pre-activations (data gradient of MLP.c_proj through the GELU);
+ *   mode 5: C fp32 = resid + product + bias (+ tadd[row_jet[row]]): `x = x + attn(...)` / `x = x + ffw(...)` (+ time embedding)
+ *           of SelfAttnBlock (attention.py:24-25, ParticleTransformers.py:88-89) written out of place by the projection.
+ * aux [M x N] bf16 with row pitch ldaux (modes 3, 4; else null); resid [M x N] fp32 / tadd / row_jet (mode 5; else null).
  * replaces F.linear and its autograd (attention.py:44-45, utils/models.py:15-17). */
 int mmf_tr_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
-                const float* bias, int32_t mode, int32_t ksplit, void* aux, int64_t ldaux, void* stream);
+                const float* bias, int32_t mode, int32_t ksplit, void* aux, int64_t ldaux, const float* resid, int64_t ldr, const float* tadd,
+                int64_t ldt, const int32_t* row_jet, void* stream);
 /* weight gradient of nn.Linear straight from the row-major activations: C[M x N] += A^T B with A = dy [K x M], B = x [K x N]
  * (bf16, K = tokens; both are read as MN-major tcgen05 operands, so no transposed copy exists); K split over `ksplit` CTAs */
 int mmf_tr_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,

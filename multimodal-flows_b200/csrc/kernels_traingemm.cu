@@ -64,12 +64,13 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
 }
 
 // MODE 0: bf16 store, 1: fp32 store, 2: fp32 reduce-add, 3: bf16 store of z AND of GELU(z) (second output through tmD),
-// 4: bf16 store of acc * GELU'(z), z tile loaded through tmD; TN: A [K x M], B [K x N] row-major (MN-major operands)
+// 4: bf16 store of acc * GELU'(z), z tile loaded through tmD, 5: fp32 store of resid + acc + bias (+ tadd[row_jet]): the residual
+// stream written out of place by the projection itself; TN: A [K x M], B [K x N] row-major (MN-major operands)
 template <int MODE, bool TN>
 __global__ void __launch_bounds__(192, 3)
 tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD, const float* __restrict__ bias,
-               const int N, const int kb_total, const int kb_per_split, const int stages) {
+               const int N, const int kb_total, const int kb_per_split, const int stages, const TrGemmResid rs) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     TrGemmBars* bars = reinterpret_cast<TrGemmBars*>(smem);
@@ -193,6 +194,19 @@ tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int i = 0; i < 32; ++i) { const int col = n0 + c * 32 + i; v[i] += col < N ? __ldg(bias + col) : 0.f; }
                 }
+                if constexpr (MODE == 5) {
+                    const int row = m0 + r;
+                    if (row < rs.M) {                                   // (rows beyond M are clipped by the store)
+                        const float4* rp = reinterpret_cast<const float4*>(rs.resid + row * rs.ldr + n0 + c * 32);
+                        const float4* tp = rs.tadd ? reinterpret_cast<const float4*>(rs.tadd + static_cast<long long>(rs.row_jet ? rs.row_jet[row] : 0) * rs.ldt + n0 + c * 32) : nullptr;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const float4 a4 = rp[u];
+                            v[u * 4] += a4.x; v[u * 4 + 1] += a4.y; v[u * 4 + 2] += a4.z; v[u * 4 + 3] += a4.w;
+                            if (tp) { const float4 t4 = __ldg(tp + u); v[u * 4] += t4.x; v[u * 4 + 1] += t4.y; v[u * 4 + 2] += t4.z; v[u * 4 + 3] += t4.w; }
+                        }
+                    }
+                }
                 stage_row_f32(tiles + c * kTrBox, r, v);
             }
         }
@@ -203,7 +217,7 @@ tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int cc = 0; cc < 2; ++cc) tma_store_2d(&tmC, tiles + cc * kTrBox, n0 + cc * 64, m0);
                 if constexpr (MODE == 3)
                     for (int cc = 0; cc < 2; ++cc) tma_store_2d(&tmD, tiles + (2 + cc) * kTrBox, n0 + cc * 64, m0);
-            } else if constexpr (MODE == 1) {
+            } else if constexpr (MODE == 1 || MODE == 5) {
                 for (int c = 0; c < 4; ++c) tma_store_2d(&tmC, tiles + c * kTrBox, n0 + c * 32, m0);
             } else {
                 for (int c = 0; c < 4; ++c) tma_reduce_add_2d(&tmC, tiles + c * kTrBox, n0 + c * 32, m0);
@@ -219,7 +233,7 @@ tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 template <int MODE, bool TN>
 int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmD, const float* bias, int N,
-                int kb_total, int kb_per_split, dim3 grid, cudaStream_t s) {
+                int kb_total, int kb_per_split, dim3 grid, cudaStream_t s, const TrGemmResid& rs = TrGemmResid{}) {
     static bool configured[64] = {false};                 // the attribute is per device
     int dev = 0;
     MMF_CUDA_OK(cudaGetDevice(&dev));
@@ -230,17 +244,18 @@ int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     // the epilogue stages the whole output tile in the ring: two stages hold it (64 KB fp32)
     const int stages = kb_per_split < 2 ? 2 : (kb_per_split > kTrStages ? kTrStages : kb_per_split);
     const int smem = tr_smem_bytes(stages + (MODE == 4 ? 1 : 0));           // + the pre-activation tile
-    MMF_CUDA_OK(tr_launch(tr_gemm_kernel<MODE, TN>, grid, dim3(192), smem, s, tmA, tmB, tmC, tmD, bias, N, kb_total, kb_per_split, stages));
+    MMF_CUDA_OK(tr_launch(tr_gemm_kernel<MODE, TN>, grid, dim3(192), smem, s, tmA, tmB, tmC, tmD, bias, N, kb_total, kb_per_split, stages, rs));
     return 0;
 }
 
 }  // namespace
 
 int launch_tr_gemm(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N, int K,
-                   const float* bias, int mode, int ksplit, void* aux, long long ldaux, cudaStream_t s) {
+                   const float* bias, int mode, int ksplit, void* aux, long long ldaux, const TrGemmResid* resid, cudaStream_t s) {
     MMF_REQUIRE(A && B && C, "gemm: null operand");
-    MMF_REQUIRE(mode >= 0 && mode <= 4, "gemm: mode is 0 (bf16), 1 (fp32), 2 (fp32 reduce-add), 3 (bf16 + GELU copy), 4 (bf16 times GELU'(aux))");
-    MMF_REQUIRE(mode < 3 || aux, "gemm: modes 3 and 4 need the auxiliary [M x N] bf16 tensor");
+    MMF_REQUIRE(mode >= 0 && mode <= 5, "gemm: mode is 0 (bf16), 1 (fp32), 2 (fp32 reduce-add), 3 (bf16 + GELU copy), 4 (bf16 times GELU'(aux)), 5 (fp32 residual + product)");
+    MMF_REQUIRE((mode != 3 && mode != 4) || aux, "gemm: modes 3 and 4 need the auxiliary [M x N] bf16 tensor");
+    MMF_REQUIRE(mode != 5 || (resid && resid->resid && N % 128 == 0), "gemm: mode 5 needs the residual input and N a multiple of 128");
     if (M <= 0 || N <= 0) return 0;
     MMF_REQUIRE(K > 0, "gemm: K must be positive");
     const int kb_total = (K + kBK - 1) / kBK;
@@ -251,17 +266,22 @@ int launch_tr_gemm(const void* A, long long lda, const void* B, long long ldb, v
     CUtensorMap tmA, tmB, tmC, tmD;
     if (make_tmap_2d(&tmA, A, 2, M, K, lda, 64, 128)) return 1;
     if (make_tmap_2d(&tmB, B, 2, N, K, ldb, 64, 128)) return 1;
-    if (mode == 0 || mode >= 3) { if (make_tmap_2d(&tmC, C, 2, M, N, ldc, 64, 128)) return 1; }
+    if (mode == 0 || mode == 3 || mode == 4) { if (make_tmap_2d(&tmC, C, 2, M, N, ldc, 64, 128)) return 1; }
     else { if (make_tmap_2d(&tmC, C, 4, M, N, ldc, 32, 128)) return 1; }
     tmD = tmC;
-    if (mode >= 3 && make_tmap_2d(&tmD, aux, 2, M, N, ldaux, 64, 128)) return 1;
+    if ((mode == 3 || mode == 4) && make_tmap_2d(&tmD, aux, 2, M, N, ldaux, 64, 128)) return 1;
     const dim3 grid((M + kTileM - 1) / kTileM, (N + 127) / 128, ksplit);
     switch (mode) {
         case 0: return launch_mode<0, false>(tmA, tmB, tmC, tmD, bias, N, kb_total, per, grid, s);
         case 1: return launch_mode<1, false>(tmA, tmB, tmC, tmD, bias, N, kb_total, per, grid, s);
         case 2: return launch_mode<2, false>(tmA, tmB, tmC, tmD, bias, N, kb_total, per, grid, s);
         case 3: return launch_mode<3, false>(tmA, tmB, tmC, tmD, bias, N, kb_total, per, grid, s);
-        default: return launch_mode<4, false>(tmA, tmB, tmC, tmD, bias, N, kb_total, per, grid, s);
+        case 4: return launch_mode<4, false>(tmA, tmB, tmC, tmD, bias, N, kb_total, per, grid, s);
+        default: {
+            TrGemmResid rs = *resid;
+            rs.M = M;
+            return launch_mode<5, false>(tmA, tmB, tmC, tmD, bias, N, kb_total, per, grid, s, rs);
+        }
     }
 }
 

@@ -24,9 +24,16 @@ inline cudaError_t tr_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, si
 }
 
 // C[M x N] (+)= A[M x K] B[N x K]^T (+ bias); mode 0: bf16 store, 1: fp32 store, 2: fp32 reduce-add (K split over `ksplit` CTAs),
-// 3: bf16 store + aux = GELU(C) (bf16), 4: bf16 store of the product times GELU'(aux) (aux: bf16 pre-activations)
+// 3: bf16 store + aux = GELU(C) (bf16), 4: bf16 store of the product times GELU'(aux) (aux: bf16 pre-activations),
+// 5: fp32 store of resid + product + bias (+ tadd[row_jet]) - the residual stream written out of place by the projection
+struct TrGemmResid {
+    const float* resid; long long ldr;       // [M x N] fp32 input of the residual connection
+    const float* tadd; long long ldt;        // optional per-jet row (time embedding)
+    const int* row_jet;
+    int M;
+};
 int launch_tr_gemm(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N, int K,
-                   const float* bias, int mode, int ksplit, void* aux, long long ldaux, cudaStream_t s);
+                   const float* bias, int mode, int ksplit, void* aux, long long ldaux, const TrGemmResid* resid, cudaStream_t s);
 
 // C[M x N] += A^T B, A [K x M], B [K x N] row-major bf16 (weight gradient from row-major activations, MN-major operands)
 int launch_tr_gemm_tn(const void* A, long long lda, const void* B, long long ldb, float* C, long long ldc, int M, int N, int K, int ksplit,

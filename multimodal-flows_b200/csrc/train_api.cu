@@ -13,8 +13,10 @@ using namespace mmf;
 extern "C" {
 
 int mmf_tr_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
-                const float* bias, int32_t mode, int32_t ksplit, void* aux, int64_t ldaux, void* stream) {
-    return launch_tr_gemm(A, lda, B, ldb, C, ldc, M, N, K, bias, mode, ksplit, aux, ldaux, S_(stream));
+                const float* bias, int32_t mode, int32_t ksplit, void* aux, int64_t ldaux, const float* resid, int64_t ldr, const float* tadd,
+                int64_t ldt, const int32_t* row_jet, void* stream) {
+    const TrGemmResid rs{resid, ldr, tadd, ldt, row_jet, M};
+    return launch_tr_gemm(A, lda, B, ldb, C, ldc, M, N, K, bias, mode, ksplit, aux, ldaux, &rs, S_(stream));
 }
 
 int mmf_tr_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,

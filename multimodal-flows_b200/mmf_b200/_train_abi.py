@@ -14,7 +14,7 @@ from . import _abi
 P, I32, I64, F = c_void_p, c_int32, c_int64, c_float
 
 SIGNATURES = {
-    "mmf_tr_gemm": [P, I64, P, I64, P, I64, I32, I32, I32, P, I32, I32, P, I64, P],
+    "mmf_tr_gemm": [P, I64, P, I64, P, I64, I32, I32, I32, P, I32, I32, P, I64, P, I64, P, I64, P, P],
     "mmf_tr_gemm_tn": [P, I64, P, I64, P, I64, I32, I32, I32, I32, P],
     "mmf_tr_sgemm": [P, I64, I64, P, I64, I64, P, I64, I32, I32, I32, P, I32, P],
     "mmf_tr_cast_transpose": [P, I64, I32, I32, I32, P, I64, P, I64, P, P],
@@ -83,13 +83,14 @@ class Ops:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     # C[M,N] (+)= A[M,K] B[N,K]^T (+ bias)
-    def gemm(self, A, B, C, bias=None, mode=0, ksplit=1, aux=None):
+    def gemm(self, A, B, C, bias=None, mode=0, ksplit=1, aux=None, resid=None, tadd=None, row_jet=None):
         M, K = A.shape
         N = B.shape[0]
         assert B.shape[1] == K and tuple(C.shape) == (M, N) and A.stride(1) == 1 and B.stride(1) == 1 and C.stride(1) == 1
-        assert (mode >= 3) == (aux is not None) and (aux is None or (tuple(aux.shape) == (M, N) and aux.stride(1) == 1))
+        assert (mode in (3, 4)) == (aux is not None) and (aux is None or (tuple(aux.shape) == (M, N) and aux.stride(1) == 1))
+        assert (mode == 5) == (resid is not None) and (resid is None or tuple(resid.shape) == (M, N))
         _abi.check(self.L.mmf_tr_gemm(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, N, K, _p(bias), mode, ksplit, _p(aux),
-                                      _ld(aux), self._s()))
+                                      _ld(aux), _p(resid), _ld(resid), _p(tadd), _ld(tadd), _p(row_jet), self._s()))
 
     # C[M,N] += A^T B, A [K,M], B [K,N] row-major bf16
     def gemm_tn(self, A, B, C, ksplit=1):

@@ -81,12 +81,14 @@ class _GraphSlot:
     nothing to any parameter gradient - the same CUDA graph serves every batch of B jets with at most `rows` particles."""
     padded = True
 
-    def __init__(self, B: int, D: int, rows: int, device: torch.device):
-        self.B, self.D, self.M, self.Mp, self.nmax, self.sum_n2 = B, D, rows, rows, D, B * D * D
+    def __init__(self, B: int, D: int, rows: int, has_big: bool, device: torch.device):
+        # has_big: the graph holds the CUDA-core attention launches for jets of more than 128 particles (and their probability
+        # buffers, sized for the worst case); batches without such jets replay a graph without them
+        self.B, self.D, self.M, self.Mp, self.nmax, self.sum_n2 = B, D, rows, rows, D, (B * D * D if has_big else 0)
         z = lambda *s, dt=torch.float32: torch.zeros(*s, device=device, dtype=dt)
         self.jet_off, self.p_off, self.row_jet = z(B + 1, dt=torch.int32), z(B + 1, dt=torch.int64), z(rows, dt=torch.int32)
         self.xs, self.tg, self.ks, self.k1p, self.t = z(rows, 3), z(rows, 3), z(rows, dt=torch.int32), z(rows, dt=torch.int32), z(B)
-        self.items, self.n_items, self.grid_items, self.has_big = z(B, 2, dt=torch.int32), z(1, dt=torch.int32), B, True
+        self.items, self.n_items, self.grid_items, self.has_big = z(B, 2, dt=torch.int32), z(1, dt=torch.int32), B, bool(has_big)
         self.pin = [torch.zeros(B + 1, dtype=torch.int32).pin_memory(), torch.zeros(B + 1, dtype=torch.int64).pin_memory(),
                     torch.zeros(rows, dtype=torch.int32).pin_memory(), torch.zeros(B, 2, dtype=torch.int32).pin_memory(),
                     torch.zeros(1, dtype=torch.int32).pin_memory()]
@@ -253,8 +255,8 @@ class TrainEngine:
         self._keep.clear()
 
     # ---- nn.Linear on packed rows ----------------------------------------------------------------------------------------
-    def _lin_fwd(self, x16, name, out, mode, aux=None):
-        self.ops.gemm(x16, self.w16(name + ".weight"), out, self.p(name + ".bias"), mode, aux=aux)
+    def _lin_fwd(self, x16, name, out, mode, aux=None, resid=None, tadd=None, row_jet=None):
+        self.ops.gemm(x16, self.w16(name + ".weight"), out, self.p(name + ".bias"), mode, aux=aux, resid=resid, tadd=tadd, row_jet=row_jet)
 
     def _ksplit(self, plan, n_out, n_in):
         tiles = ((n_out + 127) // 128) * ((n_in + 127) // 128)
@@ -305,15 +307,12 @@ class TrainEngine:
         if plan.has_big:                                      # jets of 129 ... 150 particles: CUDA-core kernels, probabilities kept
             s["P"] = torch.empty(max(plan.sum_n2 * H, 1), **bf)
             ops.attn_fwd(s["qn"], s["kn"], s["qkv"][:, 2 * C:], plan.jet_off, plan.p_off, plan.B, H, hs, plan.nmax, s["o"], s["P"], min_n=128)
-        y = torch.empty(M, C, device=dev)
-        self._lin_fwd(s["o"], pre + ".attn.c_proj", y, 1)
-        ops.add(R1, Rin, y)
+        self._lin_fwd(s["o"], pre + ".attn.c_proj", R1, 5, resid=Rin)           # x = x + attn(ln1(x)), written out of place
         s["a2"], s["m2"], s["r2"] = torch.empty(M, C, **bf), torch.empty(M, device=dev), torch.empty(M, device=dev)
         ops.ln_fwd(R1, self.p(pre + ".ln2.weight"), self.p(pre + ".ln2.bias"), s["m2"], s["r2"], out16=s["a2"])
         s["z"], s["hh"] = torch.empty(M, I, **bf), torch.empty(M, I, **bf)
         self._lin_fwd(s["a2"], pre + ".ffw.c_fc", s["z"], 3, aux=s["hh"])      # z and GELU(z) leave the same epilogue
-        self._lin_fwd(s["hh"], pre + ".ffw.c_proj", y, 1)
-        ops.add(R2, R1, y, tadd, plan.row_jet)
+        self._lin_fwd(s["hh"], pre + ".ffw.c_proj", R2, 5, resid=R1, tadd=tadd, row_jet=plan.row_jet)   # x = x + ffw(ln2(x)) + time embedding
         return s
 
     def _block_bwd(self, plan, s, G, g16=None, nxt=None):
@@ -570,10 +569,10 @@ class TrainEngine:
         self.last_plan = plan
         if self.use_graphs:
             rows = max(self.graph_rows, (plan.M + self.graph_rows - 1) // self.graph_rows * self.graph_rows)
-            key = (plan.B, plan.D, rows)
+            key = (plan.B, plan.D, rows, plan.has_big)
             slot = self._slots.get(key)
             if slot is None:
-                slot = self._slots[key] = _GraphSlot(plan.B, plan.D, rows, dev)
+                slot = self._slots[key] = _GraphSlot(plan.B, plan.D, rows, plan.has_big, dev)
             slot.load(plan)
             slot.t.copy_(time)
             xs, ks, tg, k1p, run = slot.xs, slot.ks, slot.tg, slot.k1p, slot

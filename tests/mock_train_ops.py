@@ -18,7 +18,7 @@ class MockOps:
     def __init__(self):
         self.launches = 0
 
-    def gemm(self, A, B, C, bias=None, mode=0, ksplit=1, aux=None):
+    def gemm(self, A, B, C, bias=None, mode=0, ksplit=1, aux=None, resid=None, tadd=None, row_jet=None):
         r = _f(A) @ _f(B).T
         if bias is not None:
             r = r + bias
@@ -30,6 +30,11 @@ class MockOps:
         elif mode == 4:
             zz = _f(aux).clone().requires_grad_(True)
             C.copy_(torch.autograd.grad(F.gelu(zz), zz, r)[0].to(C.dtype))
+        elif mode == 5:
+            r = r + resid
+            if tadd is not None:
+                r = r + tadd[row_jet.long()]
+            C.copy_(r)
         else:
             C.copy_(r.to(C.dtype))
 

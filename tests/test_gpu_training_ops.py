@@ -68,6 +68,20 @@ def test_gemm_gelu_epilogues(ops, M, N, K):
     assert rel(dz.float(), zz.grad) < 4e-3, rel(dz.float(), zz.grad)
 
 
+def test_gemm_residual_epilogue(ops):
+    """mode 5: out = resid + x W^T + b + tadd[row_jet], out of place, on column slices of 256-wide fp32 buffers"""
+    g = torch.Generator(device=DEV).manual_seed(11)
+    off, _, row_jet, M, _ = jets([5, 1, 150, 44, 77])
+    A, W, bias = bf(torch.randn(M, 512, device=DEV, generator=g)), bf(torch.randn(128, 512, device=DEV, generator=g) * 0.1), torch.randn(128, device=DEV, generator=g)
+    R, tadd = torch.randn(M, 256, device=DEV, generator=g), torch.randn(5, 256, device=DEV, generator=g)
+    out = torch.zeros(M, 256, device=DEV)
+    ops.gemm(A, W, out[:, 128:], bias, 5, resid=R[:, 128:], tadd=tadd[:, 128:], row_jet=row_jet)
+    want = R[:, 128:] + A.float() @ W.float().T + bias + tadd[row_jet.long()][:, 128:]
+    assert rel(out[:, 128:], want) < 2e-6 and float(out[:, :128].abs().max()) == 0.0
+    ops.gemm(A, W, out[:, :128], None, 5, resid=R[:, :128])
+    assert rel(out[:, :128], R[:, :128] + A.float() @ W.float().T) < 2e-6
+
+
 def test_gemm_strided_views_and_no_bias(ops):
     g = torch.Generator(device=DEV).manual_seed(5)
     big_a, big_c = bf(torch.randn(500, 256, device=DEV, generator=g)), torch.zeros(500, 1024, device=DEV, dtype=torch.bfloat16)
