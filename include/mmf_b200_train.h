@@ -30,6 +30,10 @@ extern "C" {
 int mmf_tr_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
                 const float* bias, int32_t mode, int32_t ksplit, void* aux, int64_t ldaux, const float* resid, int64_t ldr, const float* tadd,
                 int64_t ldt, const int32_t* row_jet, void* stream);
+/* SelfAttention.c_attn with the per-head LayerNorm of q and k in its epilogue (attention.py:57-64): qkv [M x 3C] bf16 (kept for the
+ * backward pass) and the normalised q | k as qkn [M x 2C] bf16; A [M x K] bf16, W [3C x K] bf16, bias [3C] or null */
+int mmf_tr_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* qkv, int64_t ldq, void* qkn, int64_t ldn,
+                    int32_t M, int32_t C, int32_t K, int32_t H, const float* qg, const float* qb, const float* kg, const float* kb, void* stream);
 /* weight gradient of nn.Linear straight from the row-major activations: C[M x N] += A^T B with A = dy [K x M], B = x [K x N]
  * (bf16, K = tokens; both are read as MN-major tcgen05 operands, so no transposed copy exists); K split over `ksplit` CTAs */
 int mmf_tr_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,

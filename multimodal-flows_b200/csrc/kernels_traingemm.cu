@@ -50,6 +50,19 @@ __device__ __forceinline__ float gelu_grad_exact(float x) {
     return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+template <int N>
+__device__ __forceinline__ void head_layernorm(float* v, const float* g, const float* b) {     // reference utils/models.py:36-37, eps 1e-5
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) s += v[i];
+    const float mean = s * (1.0f / N);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(q * (1.0f / N) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = fmaf((v[i] - mean) * rstd, __ldg(g + i), b ? __ldg(b + i) : 0.f);
+}
 __device__ __forceinline__ void stage_bf16_32(uint8_t* chunk, int r, int half, const float* v) {
 #pragma unroll
     for (int u = 0; u < 4; ++u)
@@ -65,7 +78,8 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
 
 // MODE 0: bf16 store, 1: fp32 store, 2: fp32 reduce-add, 3: bf16 store of z AND of GELU(z) (second output through tmD),
 // 4: bf16 store of acc * GELU'(z), z tile loaded through tmD, 5: fp32 store of resid + acc + bias (+ tadd[row_jet]): the residual
-// stream written out of place by the projection itself; TN: A [K x M], B [K x N] row-major (MN-major operands)
+// stream written out of place by the projection itself, 6: c_attn: bf16 store of q | k | v AND of the per-head LayerNorm of the q
+// and k sections (through tmD, a [M x 2C] buffer); TN: A [K x M], B [K x N] row-major (MN-major operands)
 template <int MODE, bool TN>
 __global__ void __launch_bounds__(192, 3)
 tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -155,7 +169,31 @@ tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool add_bias = bias != nullptr && (MODE != 2 || blockIdx.z == 0);
         mbar_wait(&bars->acc_full, 0);
         tc_fence_after();
-        if constexpr (MODE == 0 || MODE == 3 || MODE == 4) {
+        if constexpr (MODE == 6) {
+            const int sect = n0 / rs.C;                                 // 0: q, 1: k, 2: v (C is a multiple of the 128-column tile)
+            const float* hg = sect == 0 ? rs.qg : rs.kg;
+            const float* hb = sect == 0 ? rs.qb : rs.kb;
+            for (int cc = 0; cc < 2; ++cc) {
+                float v[64];
+                tmem_ld32(taddr + cc * 64, v);
+                tmem_ld32(taddr + cc * 64 + 32, v + 32);
+                tmem_ld_wait();
+                if (add_bias) {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) v[i] += __ldg(bias + n0 + cc * 64 + i);
+                }
+                stage_bf16_32(tiles + cc * kTrBox, r, 0, v);
+                stage_bf16_32(tiles + cc * kTrBox, r, 1, v + 32);
+                if (sect < 2) {                                          // LayerNorm over each head of the bf16 values the backward pass reads
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) v[i] = bf16_round(v[i]);
+                    if (rs.hs == 32) { head_layernorm<32>(v, hg, hb); head_layernorm<32>(v + 32, hg, hb); }
+                    else head_layernorm<64>(v, hg, hb);
+                    stage_bf16_32(tiles + (2 + cc) * kTrBox, r, 0, v);
+                    stage_bf16_32(tiles + (2 + cc) * kTrBox, r, 1, v + 32);
+                }
+            }
+        } else if constexpr (MODE == 0 || MODE == 3 || MODE == 4) {
             if constexpr (MODE == 4) mbar_wait(&bars->aux_full, 0);
             for (int c = 0; c < 4; ++c) {
                 float v[32];
@@ -213,9 +251,9 @@ tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         fence_proxy_async();
         named_bar_sync(1, 128);
         if (threadIdx.x == 0) {
-            if constexpr (MODE == 0 || MODE == 3 || MODE == 4) {
+            if constexpr (MODE == 0 || MODE == 3 || MODE == 4 || MODE == 6) {
                 for (int cc = 0; cc < 2; ++cc) tma_store_2d(&tmC, tiles + cc * kTrBox, n0 + cc * 64, m0);
-                if constexpr (MODE == 3)
+                if (MODE == 3 || (MODE == 6 && n0 < 2 * rs.C))
                     for (int cc = 0; cc < 2; ++cc) tma_store_2d(&tmD, tiles + (2 + cc) * kTrBox, n0 + cc * 64, m0);
             } else if constexpr (MODE == 1 || MODE == 5) {
                 for (int c = 0; c < 4; ++c) tma_store_2d(&tmC, tiles + c * kTrBox, n0 + c * 32, m0);
@@ -283,6 +321,23 @@ int launch_tr_gemm(const void* A, long long lda, const void* B, long long ldb, v
             return launch_mode<5, false>(tmA, tmB, tmC, tmD, bias, N, kb_total, per, grid, s, rs);
         }
     }
+}
+
+// SelfAttention.c_attn + q / k LayerNorm (reference attention.py:57-64): qkv [M x 3C] bf16 and the normalised q | k [M x 2C] bf16
+int launch_tr_gemm_qkv(const void* A, long long lda, const void* W, long long ldw, const float* bias, void* qkv, long long ldq, void* qkn,
+                       long long ldn, int M, int C, int K, int hs, const float* qg, const float* qb, const float* kg, const float* kb,
+                       cudaStream_t s) {
+    MMF_REQUIRE(A && W && qkv && qkn && qg && kg, "gemm_qkv: null argument");
+    MMF_REQUIRE(C % 128 == 0 && (hs == 32 || hs == 64), "gemm_qkv: width a multiple of 128, head size 32 or 64");
+    if (M <= 0) return 0;
+    const int kb_total = (K + kBK - 1) / kBK;
+    CUtensorMap tmA, tmB, tmC, tmD;
+    if (make_tmap_2d(&tmA, A, 2, M, K, lda, 64, 128) || make_tmap_2d(&tmB, W, 2, 3 * C, K, ldw, 64, 128) ||
+        make_tmap_2d(&tmC, qkv, 2, M, 3 * C, ldq, 64, 128) || make_tmap_2d(&tmD, qkn, 2, M, 2 * C, ldn, 64, 128)) return 1;
+    TrGemmResid rs{};
+    rs.M = M; rs.C = C; rs.hs = hs; rs.qg = qg; rs.qb = qb; rs.kg = kg; rs.kb = kb;
+    const dim3 grid((M + kTileM - 1) / kTileM, 3 * C / 128, 1);
+    return launch_mode<6, false>(tmA, tmB, tmC, tmD, bias, 3 * C, kb_total, kb_total, grid, s, rs);
 }
 
 // C[M x N] += A^T B with A [K x M], B [K x N] row-major bf16 (the weight gradient dW += dy^T x straight from the row-major

@@ -31,7 +31,13 @@ struct TrGemmResid {
     const float* tadd; long long ldt;        // optional per-jet row (time embedding)
     const int* row_jet;
     int M;
+    // mode 6 (c_attn + per-head LayerNorm of q and k)
+    int C, hs;
+    const float *qg, *qb, *kg, *kb;
 };
+int launch_tr_gemm_qkv(const void* A, long long lda, const void* W, long long ldw, const float* bias, void* qkv, long long ldq, void* qkn,
+                       long long ldn, int M, int C, int K, int hs, const float* qg, const float* qb, const float* kg, const float* kb,
+                       cudaStream_t s);
 int launch_tr_gemm(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N, int K,
                    const float* bias, int mode, int ksplit, void* aux, long long ldaux, const TrGemmResid* resid, cudaStream_t s);
 

@@ -15,8 +15,15 @@ extern "C" {
 int mmf_tr_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
                 const float* bias, int32_t mode, int32_t ksplit, void* aux, int64_t ldaux, const float* resid, int64_t ldr, const float* tadd,
                 int64_t ldt, const int32_t* row_jet, void* stream) {
-    const TrGemmResid rs{resid, ldr, tadd, ldt, row_jet, M};
+    TrGemmResid rs{};
+    rs.resid = resid; rs.ldr = ldr; rs.tadd = tadd; rs.ldt = ldt; rs.row_jet = row_jet; rs.M = M;
     return launch_tr_gemm(A, lda, B, ldb, C, ldc, M, N, K, bias, mode, ksplit, aux, ldaux, &rs, S_(stream));
+}
+
+int mmf_tr_gemm_qkv(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* qkv, int64_t ldq, void* qkn, int64_t ldn,
+                    int32_t M, int32_t C, int32_t K, int32_t H, const float* qg, const float* qb, const float* kg, const float* kb, void* stream) {
+    MMF_REQUIRE(H > 0 && C % H == 0, "gemm_qkv: bad head count");
+    return launch_tr_gemm_qkv(A, lda, W, ldw, bias, qkv, ldq, qkn, ldn, M, C, K, C / H, qg, qb, kg, kb, S_(stream));
 }
 
 int mmf_tr_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,

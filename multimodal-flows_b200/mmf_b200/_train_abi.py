@@ -15,6 +15,7 @@ P, I32, I64, F = c_void_p, c_int32, c_int64, c_float
 
 SIGNATURES = {
     "mmf_tr_gemm": [P, I64, P, I64, P, I64, I32, I32, I32, P, I32, I32, P, I64, P, I64, P, I64, P, P],
+    "mmf_tr_gemm_qkv": [P, I64, P, I64, P, P, I64, P, I64, I32, I32, I32, I32, P, P, P, P, P],
     "mmf_tr_gemm_tn": [P, I64, P, I64, P, I64, I32, I32, I32, I32, P],
     "mmf_tr_sgemm": [P, I64, I64, P, I64, I64, P, I64, I32, I32, I32, P, I32, P],
     "mmf_tr_cast_transpose": [P, I64, I32, I32, I32, P, I64, P, I64, P, P],
@@ -91,6 +92,14 @@ class Ops:
         assert (mode == 5) == (resid is not None) and (resid is None or tuple(resid.shape) == (M, N))
         _abi.check(self.L.mmf_tr_gemm(_p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, N, K, _p(bias), mode, ksplit, _p(aux),
                                       _ld(aux), _p(resid), _ld(resid), _p(tadd), _ld(tadd), _p(row_jet), self._s()))
+
+    # qkv = A W^T + b [M,3C]; qkn = per-head LayerNorm of its q | k sections [M,2C]
+    def gemm_qkv(self, A, W, bias, qkv, qkn, H, qg, qb, kg, kb):
+        M, K = A.shape
+        C = W.shape[0] // 3
+        assert tuple(qkv.shape) == (M, 3 * C) and tuple(qkn.shape) == (M, 2 * C) and W.shape[1] == K
+        _abi.check(self.L.mmf_tr_gemm_qkv(_p(A), A.stride(0), _p(W), W.stride(0), _p(bias), _p(qkv), qkv.stride(0), _p(qkn), qkn.stride(0),
+                                          M, C, K, H, _p(qg), _p(qb), _p(kg), _p(kb), self._s()))
 
     # C[M,N] += A^T B, A [K,M], B [K,N] row-major bf16
     def gemm_tn(self, A, B, C, ksplit=1):

@@ -293,12 +293,14 @@ class TrainEngine:
         s["a1"], s["m1"], s["r1"] = torch.empty(M, C, **bf), torch.empty(M, device=dev), torch.empty(M, device=dev)
         ops.ln_fwd(Rin, self.p(pre + ".ln1.weight"), self.p(pre + ".ln1.bias"), s["m1"], s["r1"], out16=s["a1"])
         s["qkv"] = torch.empty(M, 3 * C, **bf)
-        self._lin_fwd(s["a1"], pre + ".attn.c_attn", s["qkv"], 0)
-        if self.cfg.qk_layernorm:
-            s["qn"], s["kn"] = torch.empty(M, C, **bf), torch.empty(M, C, **bf)
-            ops.qkln_fwd(s["qkv"], C, H, self.p(pre + ".attn.q_layernorm.weight"), self.p(pre + ".attn.q_layernorm.bias"),
-                         self.p(pre + ".attn.k_layernorm.weight"), self.p(pre + ".attn.k_layernorm.bias"), s["qn"], s["kn"])
+        if self.cfg.qk_layernorm:                              # c_attn with the q / k LayerNorm in its epilogue
+            qkn = torch.empty(M, 2 * C, **bf)
+            ops.gemm_qkv(s["a1"], self.w16(pre + ".attn.c_attn.weight"), self.p(pre + ".attn.c_attn.bias"), s["qkv"], qkn, H,
+                         self.p(pre + ".attn.q_layernorm.weight"), self.p(pre + ".attn.q_layernorm.bias"),
+                         self.p(pre + ".attn.k_layernorm.weight"), self.p(pre + ".attn.k_layernorm.bias"))
+            s["qn"], s["kn"] = qkn[:, :C], qkn[:, C:]
         else:
+            self._lin_fwd(s["a1"], pre + ".attn.c_attn", s["qkv"], 0)
             s["qn"], s["kn"] = s["qkv"][:, :C], s["qkv"][:, C:2 * C]
         s["o"] = torch.zeros(M, C, **bf) if plan.padded else torch.empty(M, C, **bf)      # rows of no jet are never written
         s["stats"] = torch.empty(M, H, 2, device=dev)

@@ -38,6 +38,11 @@ class MockOps:
         else:
             C.copy_(r.to(C.dtype))
 
+    def gemm_qkv(self, A, W, bias, qkv, qkn, H, qg, qb, kg, kb):
+        self.gemm(A, W, qkv, bias, 0)
+        C = W.shape[0] // 3
+        self.qkln_fwd(qkv, C, H, qg, qb, kg, kb, qkn[:, :C], qkn[:, C:])
+
     def gemm_tn(self, A, B, C, ksplit=1):
         C += _f(A).T @ _f(B)
 

@@ -68,6 +68,25 @@ def test_gemm_gelu_epilogues(ops, M, N, K):
     assert rel(dz.float(), zz.grad) < 4e-3, rel(dz.float(), zz.grad)
 
 
+@pytest.mark.parametrize("C,H", [(128, 4), (256, 4)])
+def test_gemm_qkv_with_head_layernorm_epilogue(ops, C, H):
+    """c_attn + q / k LayerNorm in one kernel: qkv as the plain bf16 product, qkn = LayerNorm over each head of those bf16 values"""
+    g = torch.Generator(device=DEV).manual_seed(C + 3)
+    M, hs = 1000, C // H
+    A, W, bias = bf(torch.randn(M, C, device=DEV, generator=g)), bf(torch.randn(3 * C, C, device=DEV, generator=g) * 0.2), torch.randn(3 * C, device=DEV, generator=g)
+    qg, qb, kg, kb = (torch.rand(hs, device=DEV, generator=g) + 0.5 for _ in range(4))
+    qkv, qkn = torch.zeros(M, 3 * C, device=DEV, dtype=torch.bfloat16), torch.zeros(M, 2 * C, device=DEV, dtype=torch.bfloat16)
+    ops.gemm_qkv(A, W, bias, qkv, qkn, H, qg, qb, kg, kb)
+    want = A.float() @ W.float().T + bias
+    assert rel(qkv.float(), want) < 4e-3
+    ln = lambda x, gam, bet: torch.nn.functional.layer_norm(x.float().view(M, H, hs), (hs,), gam, bet, 1e-5).reshape(M, C)
+    assert rel(qkn[:, :C].float(), ln(qkv[:, :C], qg, qb)) < 4e-3 and rel(qkn[:, C:].float(), ln(qkv[:, C:2 * C], kg, kb)) < 4e-3
+    # and it equals the two-kernel path bit for bit on the stored bf16 values
+    qn2, kn2 = torch.empty(M, C, device=DEV, dtype=torch.bfloat16), torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    ops.qkln_fwd(qkv, C, H, qg, qb, kg, kb, qn2, kn2)
+    assert rel(qkn[:, :C].float(), qn2.float()) < 1e-3 and rel(qkn[:, C:].float(), kn2.float()) < 1e-3
+
+
 def test_gemm_residual_epilogue(ops):
     """mode 5: out = resid + x W^T + b + tadd[row_jet], out of place, on column slices of 256-wide fp32 buffers"""
     g = torch.Generator(device=DEV).manual_seed(11)
