@@ -175,7 +175,7 @@ class TrainEngine:
         self._sumsq = torch.zeros(1, device=dev)
         self._err = torch.zeros(1, device=dev, dtype=torch.int32)
         self.refresh_operands()
-        self.use_graphs, self.graph_rows, self._slots = bool(use_graphs) and _ops is None, 1024, {}
+        self.use_graphs, self.graph_rows, self._slots, self.max_graphs = bool(use_graphs) and _ops is None, 1024, {}, 6
         self.concurrent, self._streams, self._wstreams, self._wused, self._keep = _ops is None, [], {}, set(), []
         self.last_plan = None
 
@@ -572,9 +572,12 @@ class TrainEngine:
         if self.use_graphs:
             rows = max(self.graph_rows, (plan.M + self.graph_rows - 1) // self.graph_rows * self.graph_rows)
             key = (plan.B, plan.D, rows, plan.has_big)
-            slot = self._slots.get(key)
+            slot = self._slots.pop(key, None)
             if slot is None:
-                slot = self._slots[key] = _GraphSlot(plan.B, plan.D, rows, plan.has_big, dev)
+                while len(self._slots) >= self.max_graphs:      # every graph owns ~1 GB of activations: keep the most recent few
+                    self._slots.pop(next(iter(self._slots)))
+                slot = _GraphSlot(plan.B, plan.D, rows, plan.has_big, dev)
+            self._slots[key] = slot                             # (re-inserted last: the dict is the LRU order)
             slot.load(plan)
             slot.t.copy_(time)
             xs, ks, tg, k1p, run = slot.xs, slot.ks, slot.tg, slot.k1p, slot

@@ -208,3 +208,29 @@ def test_edge_shapes_and_optional_parameters(model, ns, overrides, graphs):
     grads.update({"loss_combine." + k: v.grad for k, v in slg.items()})
     gcos, grel, _ = compare_gradients(eng, grads, verbose=f"{model} {ns} {overrides} graphs={graphs}")
     assert gcos > 0.995 and grel < 5e-2
+
+
+def test_graph_cache_eviction_and_reloaded_weights(golden_dir):
+    """At most `max_graphs` captured programs are kept (least recently used goes first); after load_state_dict + refresh_operands
+    the engine computes with the new weights."""
+    from mmf_b200 import synthetic
+    from mmf_b200.training import TrainEngine
+    g, cfg, sd, sd_loss, T = _fixture(golden_dir, "FusedParticleFormer", "sum")
+    bridge = _bridge(cfg, sd, sd_loss)
+    eng = TrainEngine(bridge, lr=1e-3, use_graphs=True)
+    eng.graph_rows, eng.max_graphs = 256, 2
+    eager = TrainEngine(_bridge(cfg, sd, sd_loss), lr=1e-3)
+    gen = torch.Generator().manual_seed(3)
+    for B in (4, 12, 4, 20, 12):
+        b = synthetic.training_batch(B, seed=40 + B)
+        t, z, u = torch.rand(B, generator=gen), torch.randn(B, 150, 3, generator=gen), torch.rand(B, 150, generator=gen)
+        a, c = eager.loss_and_grad(b, time=t, z=z, u=u), eng.loss_and_grad(b, time=t, z=z, u=u)
+        assert len(eng._slots) <= 2
+        assert torch.allclose(a, c, rtol=1e-5, atol=1e-6) and float((eager.G - eng.G).norm() / eager.G.norm()) < 1e-4
+    sd2 = synthetic.make_state_dict(cfg, flavor="wide", seed=77)
+    bridge.model.load_state_dict(sd2)
+    eng.refresh_operands()
+    fresh = TrainEngine(_bridge(cfg, sd2, sd_loss), lr=1e-3)
+    b = synthetic.training_batch(12, seed=52)
+    t, z, u = torch.rand(12, generator=gen), torch.randn(12, 150, 3, generator=gen), torch.rand(12, 150, generator=gen)
+    assert torch.allclose(eng.loss_and_grad(b, time=t, z=z, u=u), fresh.loss_and_grad(b, time=t, z=z, u=u), rtol=1e-5, atol=1e-6)
