@@ -261,7 +261,7 @@ tr_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int c = 0; c < 4; ++c) tma_reduce_add_2d(&tmC, tiles + c * kTrBox, n0 + c * 32, m0);
             }
             tma_store_commit();
-            tma_store_wait_all();
+            tma_store_wait_read<0>();        // the staging memory must outlive the reads; the writes are complete at grid end
         }
     }
     tc_fence_before();

@@ -690,36 +690,43 @@ __global__ void tr_jet_sum_kernel(const float* __restrict__ g, long long ld, con
 }
 
 // ------------------------------------------------------------------------------------------------ output projections
-// vt = hx Wx^T + bx, logits = hy Wy^T + by; h = [hx | hy] bf16 [M, 2 I]; warp per row
+// vt = hx Wx^T + bx, logits = hy Wy^T + by; h = [hx | hy] bf16 [M, 2 I].  The (3 + V) x I weights sit in shared memory; a warp
+// walks rows (grid-stride), lane l owns features 128 j + 4 l .. + 3 (8-byte loads of h, conflict-free float4 loads of W).
 template <int V>
 __global__ void __launch_bounds__(256) tr_head_fwd_kernel(const bf16* __restrict__ h, long long ldh, int I, const float* __restrict__ wx,
                                                           const float* __restrict__ bx, const float* __restrict__ wy,
                                                           const float* __restrict__ by, int M, float* __restrict__ vt, float* __restrict__ logits) {
     grid_dep_wait();
     grid_dep_launch();
-    const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (r >= M) return;
-    float ax[3] = {0.f, 0.f, 0.f}, ay[V];
+    extern __shared__ float4 head_w[];                 // [(3 + V)][I / 4]
+    const int lane = threadIdx.x & 31, I4 = I / 4;
+    for (int i = threadIdx.x; i < (3 + V) * I4; i += 256)
+        head_w[i] = i < 3 * I4 ? reinterpret_cast<const float4*>(wx)[i] : reinterpret_cast<const float4*>(wy)[i - 3 * I4];
+    __syncthreads();
+    for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < M; r += gridDim.x * 8) {
+        float ax[3] = {0.f, 0.f, 0.f}, ay[V];
 #pragma unroll
-    for (int c = 0; c < V; ++c) ay[c] = 0.f;
-    for (int i0 = lane * 8; i0 < I; i0 += 256) {
-        float hx[8], hy[8];
-        load_head<8>(h + r * ldh + i0, hx);
-        load_head<8>(h + r * ldh + I + i0, hy);
+        for (int c = 0; c < V; ++c) ay[c] = 0.f;
+        for (int j = 0; j < I / 128; ++j) {
+            const int i4 = j * 32 + lane;
+            const uint2 ux = *reinterpret_cast<const uint2*>(h + r * ldh + 4 * i4), uy = *reinterpret_cast<const uint2*>(h + r * ldh + I + 4 * i4);
+            const float hx[4] = {bflo(ux.x), bfhi(ux.x), bflo(ux.y), bfhi(ux.y)}, hy[4] = {bflo(uy.x), bfhi(uy.x), bflo(uy.y), bfhi(uy.y)};
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+            for (int c = 0; c < 3; ++c) {
+                const float4 w = head_w[c * I4 + i4];
+                ax[c] = fmaf(hx[0], w.x, fmaf(hx[1], w.y, fmaf(hx[2], w.z, fmaf(hx[3], w.w, ax[c]))));
+            }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) ax[c] = fmaf(hx[e], __ldg(wx + c * I + i0 + e), ax[c]);
+            for (int c = 0; c < V; ++c) {
+                const float4 w = head_w[(3 + c) * I4 + i4];
+                ay[c] = fmaf(hy[0], w.x, fmaf(hy[1], w.y, fmaf(hy[2], w.z, fmaf(hy[3], w.w, ay[c]))));
+            }
+        }
 #pragma unroll
-        for (int c = 0; c < V; ++c)
+        for (int c = 0; c < 3; ++c) { const float s = warp_sum(ax[c]); if (lane == 0) vt[r * 3 + c] = s + bx[c]; }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) ay[c] = fmaf(hy[e], __ldg(wy + c * I + i0 + e), ay[c]);
+        for (int c = 0; c < V; ++c) { const float s = warp_sum(ay[c]); if (lane == 0) logits[r * V + c] = s + by[c]; }
     }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { const float s = warp_sum(ax[c]); if (lane == 0) vt[r * 3 + c] = s + bx[c]; }
-#pragma unroll
-    for (int c = 0; c < V; ++c) { const float s = warp_sum(ay[c]); if (lane == 0) logits[r * V + c] = s + by[c]; }
 }
 
 // thread = hidden unit i of both heads (I / 256 each), CTA = a run of rows:
@@ -1132,8 +1139,9 @@ int launch_tr_jet_sum(const float* g, long long ld, const int* jet_off, int B, i
 int launch_tr_head_fwd(const bf16* h, long long ldh, int I, const float* wx, const float* bx, const float* wy, const float* by, int V, int M,
                        float* vt, float* logits, cudaStream_t s) {
     if (M <= 0) return 0;
-    MMF_REQUIRE(V == 9 && I % 256 == 0, "head kernels are instantiated for vocab_size 9 and n_inner a multiple of 256");
-    MMF_CUDA_OK(tr_launch(tr_head_fwd_kernel<9>, dim3(blocks_for(M, 8)), dim3(256), 0, s, h, ldh, I, wx, bx, wy, by, M, vt, logits));
+    MMF_REQUIRE(V == 9 && I % 128 == 0 && I <= 768, "head kernels are instantiated for vocab_size 9 and n_inner a multiple of 128 up to 768");
+    const unsigned grid = std::min<unsigned>(blocks_for(M, 8), 148 * 2);
+    MMF_CUDA_OK(tr_launch(tr_head_fwd_kernel<9>, dim3(grid), dim3(256), static_cast<size_t>(12) * I * 4, s, h, ldh, I, wx, bx, wy, by, M, vt, logits));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }
