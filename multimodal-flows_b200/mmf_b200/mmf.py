@@ -162,7 +162,8 @@ class MultiModalFlowBridge(_GenerativeBase):
         dev = self.device
         B, V, eps = len(batch), cfg.vocab_size, cfg.time_eps
         if cfg.multitask_loss == "weighted":
-            raise NotImplementedError("multitask_loss='weighted' is not on the accelerated path (use 'time-weighted' or 'sum')")
+            raise NotImplementedError("loss() covers 'time-weighted' and 'sum'; multitask_loss='weighted' runs through configure_training() "
+                                      "(training_step / validation_step)")
         if time is None:
             time = eps + (1.0 - eps) * torch.rand(B, device=dev)
         tgt, src = batch.target.to(dev), batch.source.to(dev) if batch.source is not None else TensorMultiModal()
@@ -209,7 +210,13 @@ class MultiModalFlowBridge(_GenerativeBase):
         return {"loss": loss}
 
     def validation_step(self, batch: DataCoupling, batch_idx: int = 0):
-        loss, loss_mse, loss_ce, w_mse, w_ce = self.loss(batch)
+        engine = getattr(self, "_engine", None)
+        if engine is not None:                              # the training engine's forward (any multitask_loss mode), no gradients
+            out = engine.loss_only(batch)
+            weighted = self.config.multitask_loss != "sum"
+            loss, loss_mse, loss_ce, w_mse, w_ce = out[0], out[1], out[2], out[3] if weighted else None, out[4] if weighted else None
+        else:
+            loss, loss_mse, loss_ce, w_mse, w_ce = self.loss(batch)
         for name, v in (("val_loss", loss), ("val_loss_ce", loss_ce), ("val_loss_mse", loss_mse), ("val_weight_mse", w_mse),
                         ("val_weight_ce", w_ce)):
             self._log(name, v, on_epoch=True, sync_dist=True, batch_size=len(batch))

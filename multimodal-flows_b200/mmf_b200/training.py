@@ -121,8 +121,8 @@ class TrainEngine:
         cfg = module.config
         if cfg.model not in ("ParticleFormer", "FusedParticleFormer"):
             raise NotImplementedError("the training step covers ParticleFormer and FusedParticleFormer")
-        if cfg.multitask_loss not in ("sum", "time-weighted"):
-            raise NotImplementedError("multitask_loss='weighted' is not on the accelerated path (use 'time-weighted' or 'sum')")
+        if cfg.multitask_loss not in ("sum", "weighted", "time-weighted"):
+            raise ValueError(f"unknown multitask_loss '{cfg.multitask_loss}'")
         if getattr(cfg, "dropout", 0.0):
             raise NotImplementedError("dropout > 0 is not supported (the reference trains with dropout 0.0, scripts/train_mmf.py:55)")
         dev = next(module.parameters()).device
@@ -172,7 +172,7 @@ class TrainEngine:
             rec[i] = j
         self._jobs = torch.from_numpy(rec.view(np.uint8).copy()).to(dev)
         self._n_jobs, self._n_tiles = len(jobs), tile0
-        self._sumsq = torch.zeros(1, device=dev)
+        self._sumsq, self._ones = torch.zeros(1, device=dev), None
         self._err = torch.zeros(1, device=dev, dtype=torch.int32)
         self.refresh_operands()
         self.use_graphs, self.graph_rows, self._slots, self.max_graphs = bool(use_graphs) and _ops is None, 1024, {}, 6
@@ -454,6 +454,11 @@ class TrainEngine:
         l1, l2 = f32(B), f32(B)
         ops.loss_fwd(c["vt"], c["logits"], tgt, k1p, plan.jet_off, B, self.V, l1, l2)
         u = None
+        if self.cfg.multitask_loss == "weighted":             # u[b, :] = loss_weights for every jet (reference model/MMF.py:219-223)
+            if self._ones is None or self._ones.shape[0] < B:
+                self._ones = torch.ones(max(B, 256), device=dev)
+            u = f32(B, 2)
+            ops.sgemm(self._ones, 1, 0, self.p("loss_combine.loss_weights"), 0, 1, u, B, 2, 1)
         if self.cfg.multitask_loss == "time-weighted":
             N = "loss_combine.uncertainty_net."
             c["ue"], c["ua"], c["uh"], u = f32(B, E), f32(B, E), f32(B, E), f32(B, 2)
@@ -476,8 +481,10 @@ class TrainEngine:
         T = "model.transformer."
         bf = dict(device=dev, dtype=torch.bfloat16)
         f32 = lambda *s: torch.empty(*s, device=dev)
+        if c["du"] is not None and self.cfg.multitask_loss == "weighted":
+            ops.cast_transpose(c["du"], colsum=self.g("loss_combine.loss_weights"))
         # uncertainty net
-        if c["du"] is not None:
+        if c["du"] is not None and self.cfg.multitask_loss == "time-weighted":
             N = "loss_combine.uncertainty_net."
             du = c["du"]
             ops.sgemm(du, 1, 2, c["uh"], E, 1, self.g(N + "c_proj.weight"), 2, E, B, accumulate=True)

@@ -351,6 +351,11 @@ def multitask_loss(sd_loss: SD, cfg, vt, logits, x0, x1, k1, mask, t):
     ce = ce.sum(dim=1) / m.squeeze(-1).sum(dim=1).clamp_min(1.0)
     if cfg.multitask_loss == "sum":
         return (mse + ce).mean(), mse.mean(), ce.mean(), None, None
+    if cfg.multitask_loss == "weighted":                      # reference model/MMF.py:219-223: two learned log-variances
+        u1, u2 = sd_loss["loss_weights"].unbind(-1)
+        w1, w2 = torch.exp(-u1), torch.exp(-u2)
+        loss = 0.5 * (u1 + w1 * mse) + 0.5 * (u2 + w2 * ce)
+        return loss.mean(), mse.mean(), ce.mean(), w1.mean(), w2.mean()
     temb = timestep_embedding(t, cfg.n_embd)
     h = F.gelu(F.linear(temb, sd_loss["uncertainty_net.c_fc.weight"], sd_loss["uncertainty_net.c_fc.bias"]))
     u1, u2 = F.linear(h, sd_loss["uncertainty_net.c_proj.weight"], sd_loss["uncertainty_net.c_proj.bias"]).unbind(-1)

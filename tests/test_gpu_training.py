@@ -178,6 +178,7 @@ def _random_case(cfg, ns, seed):
     ("ParticleFormer", [77], {}, True),                                            # B = 1 (the reference's .squeeze() breaks there)
     ("ParticleFormer", [150, 150, 150], dict(multitask_loss="sum"), False),        # dense: every jet on the CUDA-core attention path
     ("FusedParticleFormer", [5, 60, 131], dict(bias=False, qk_layernorm=False), True),
+    ("FusedParticleFormer", [40, 8, 99, 128], dict(multitask_loss="weighted"), True),   # MultiTaskLoss with two learned log-variances
 ])
 def test_edge_shapes_and_optional_parameters(model, ns, overrides, graphs):
     from mmf_b200 import synthetic
@@ -189,6 +190,8 @@ def test_edge_shapes_and_optional_parameters(model, ns, overrides, graphs):
     sd = synthetic.make_state_dict(cfg, flavor="wide", seed=21)
     bridge = MultiModalFlowBridge(cfg)
     bridge.model.load_state_dict(sd)
+    if cfg.multitask_loss == "weighted":
+        bridge.loss_combine.load_state_dict({"loss_weights": torch.tensor([0.3, -0.2])})
     sd_loss = {k: v.detach().clone() for k, v in bridge.loss_combine.state_dict().items()}
     bridge = bridge.to(DEV)
     eng = TrainEngine(bridge, lr=1e-3, use_graphs=graphs)

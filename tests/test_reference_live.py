@@ -59,3 +59,31 @@ def test_sampler_matches_live_reference_with_supplied_uniforms():
     real = mask.bool().squeeze(-1)
     assert torch.allclose(xo[real], tgt.continuous[real], rtol=1e-4, atol=1e-5)
     assert (ko[real] == tgt.discrete[real]).float().mean() > 0.995
+
+
+def test_weighted_multitask_loss_matches_live_reference():
+    """MultiTaskLoss 'weighted' (reference model/MMF.py:219-223) has no committed golden: the oracle branch is held to the live
+    reference here (loss value and the gradient of the two learned log-variances)."""
+    ref = ref_harness.modules()
+    cfg = make_config("FusedParticleFormer", multitask_loss="weighted", n_layer=1)
+    loss_ref = ref.MultiTaskLoss(cfg) if hasattr(ref, "MultiTaskLoss") else __import__("model.MMF", fromlist=["MultiTaskLoss"]).MultiTaskLoss(cfg)
+    with torch.no_grad():
+        loss_ref.loss_weights.copy_(torch.tensor([0.3, -0.2]))
+    g = torch.Generator().manual_seed(5)
+    B, D, V = 4, 150, 9
+    mask = synthetic.prefix_masks(torch.tensor([3, 50, 150, 1]), D)
+    vt, logits = torch.randn(B, D, 3, generator=g), torch.randn(B, D, V, generator=g)
+    x0, x1 = torch.randn(B, D, 3, generator=g) * mask, torch.randn(B, D, 3, generator=g) * mask
+    k1 = torch.randint(0, V, (B, D, 1), generator=g) * mask
+    m = mask.float()
+    mse = ((vt - (x1 - x0)) ** 2 * m).sum(dim=[1, 2]) / m.sum(dim=[1, 2]).clamp_min(1.0)
+    ce = torch.nn.functional.cross_entropy(logits.view(-1, V), k1.view(-1), ignore_index=0, reduction="none").view(B, -1) * m.squeeze(-1)
+    ce = ce.sum(1) / m.squeeze(-1).sum(1).clamp_min(1.0)
+    want = loss_ref(mse, ce, None)
+    want[0].backward()
+    w = torch.tensor([0.3, -0.2], requires_grad=True)
+    got = orc.multitask_loss({"loss_weights": w}, cfg, vt, logits, x0, x1, k1, mask, torch.rand(B, generator=g))
+    got[0].backward()
+    for a, b in zip(got, want):
+        assert torch.allclose(a, b.detach(), rtol=1e-6, atol=1e-7)
+    assert torch.allclose(w.grad, loss_ref.loss_weights.grad, rtol=1e-5, atol=1e-7)

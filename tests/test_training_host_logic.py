@@ -116,7 +116,8 @@ def test_ddp_gradient_average_over_gloo(golden_dir):
     assert np.array_equal(p0, p1)                                       # identical replicas after the step (grad_scale = 1 / world)
 
 
-@pytest.mark.parametrize("overrides", [dict(bias=False), dict(qk_layernorm=False), dict(bias=False, qk_layernorm=False, multitask_loss="sum")])
+@pytest.mark.parametrize("overrides", [dict(bias=False), dict(qk_layernorm=False), dict(bias=False, qk_layernorm=False, multitask_loss="sum"),
+                                       dict(multitask_loss="weighted")])
 def test_program_handles_optional_parameters(overrides, golden_dir):
     """config.bias = False (no Linear / block-LayerNorm biases) and config.qk_layernorm = False (reference attention.py:32-51): the
     program skips exactly the operators whose parameters do not exist."""
@@ -130,6 +131,8 @@ def test_program_handles_optional_parameters(overrides, golden_dir):
     sd = synthetic.make_state_dict(cfg, flavor="wide", seed=3)
     bridge = MultiModalFlowBridge(cfg)
     bridge.model.load_state_dict(sd)
+    if cfg.multitask_loss == "weighted":
+        bridge.loss_combine.load_state_dict({"loss_weights": torch.tensor([0.3, -0.2])})
     sd_loss = {k: v.detach().clone() for k, v in bridge.loss_combine.state_dict().items()}
     eng = TrainEngine(bridge, lr=1e-3, _ops=MockOps())
     sel = [1, 2]
