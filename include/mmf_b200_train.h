@@ -53,8 +53,9 @@ int mmf_tr_weights_transpose(const float* params, void* paramsT_bf16, const void
 /* gather of the real particles of a training batch: xs = xt, ks = kt, tgt = x1 - x0 (CFM.py:186-193), k1p = k1; err as in mmf_b200.h */
 int mmf_tr_pack(const float* xt, const int64_t* kt, const float* x0, const float* x1, const int64_t* k1, const int32_t* row_slot, int32_t M,
                 int32_t V, float* xs, int32_t* ks, float* tgt, int32_t* k1p, int32_t* err, void* stream);
-/* transformer_timestep_embedding (utils/models.py:62-75): out[b, 0:dim]; dup != 0 repeats it in out[b, dim:2 dim] */
-int mmf_tr_time_embed(const float* t, int32_t B, int32_t dim, int32_t dup, float* out, int64_t ld, void* stream);
+/* transformer_timestep_embedding (utils/models.py:62-75) of t[perm[b]] (perm null: t[b]) into out[b, 0:dim]; dup != 0 repeats it
+ * in out[b, dim:2 dim].  perm: packed jet -> jet of the batch (the planner packs jets into attention tiles in its own order) */
+int mmf_tr_time_embed(const float* t, const int32_t* perm, int32_t B, int32_t dim, int32_t dup, float* out, int64_t ld, void* stream);
 /* wxe.0 + GELU (ParticleTransformers.py:28-30) and its gradient (dh = gradient w.r.t. the GELU output, bf16) */
 int mmf_tr_embed_x_fwd(const float* xs, int32_t M, const float* w0, const float* b0, int32_t E, void* h_bf16, int64_t ld, void* stream);
 int mmf_tr_embed_x_bwd(const void* dh_bf16, int64_t ld, const float* xs, int32_t M, const float* w0, const float* b0, int32_t E,

@@ -153,7 +153,8 @@ __global__ void tr_pack_kernel(const float* __restrict__ xt, const long long* __
 }
 
 // transformer_timestep_embedding (reference utils/models.py:62-75); dup = 1 writes the row twice (x | y halves)
-__global__ void tr_time_embed_kernel(const float* __restrict__ t, int B, int dim, int dup, float* __restrict__ out, long long ld) {
+__global__ void tr_time_embed_kernel(const float* __restrict__ t, const int* __restrict__ perm, int B, int dim, int dup, float* __restrict__ out,
+                                     long long ld) {
     grid_dep_wait();
     grid_dep_launch();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -161,7 +162,7 @@ __global__ void tr_time_embed_kernel(const float* __restrict__ t, int B, int dim
     const int b = i / dim, c = i % dim, half = dim / 2;
     const float scale = logf(10000.0f) / static_cast<float>(half - 1);
     const int j = c < half ? c : c - half;
-    const float a = t[b] * expf(static_cast<float>(j) * -scale);
+    const float a = t[perm ? perm[b] : b] * expf(static_cast<float>(j) * -scale);     // row b = packed jet b = jet perm[b] of the batch
     const float v = c < half ? sinf(a) : cosf(a);
     out[b * ld + c] = v;
     if (dup) out[b * ld + dim + c] = v;
@@ -964,9 +965,9 @@ int launch_tr_pack(const float* xt, const long long* kt, const float* x0, const 
     return 0;
 }
 
-int launch_tr_time_embed(const float* t, int B, int dim, int dup, float* out, long long ld, cudaStream_t s) {
+int launch_tr_time_embed(const float* t, const int* perm, int B, int dim, int dup, float* out, long long ld, cudaStream_t s) {
     if (B <= 0) return 0;
-    MMF_CUDA_OK(tr_launch(tr_time_embed_kernel, dim3(blocks_for(static_cast<long long>(B) * dim, 256)), dim3(256), 0, s, t, B, dim, dup, out, ld));
+    MMF_CUDA_OK(tr_launch(tr_time_embed_kernel, dim3(blocks_for(static_cast<long long>(B) * dim, 256)), dim3(256), 0, s, t, perm, B, dim, dup, out, ld));
     MMF_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -58,7 +58,7 @@ int launch_tr_weights_transpose(const float* p, bf16* pT, const TrTransposeJob* 
 
 int launch_tr_pack(const float* xt, const long long* kt, const float* x0, const float* x1, const long long* k1, const int* row_slot,
                    int M, int V, float* xs, int* ks, float* tgt, int* k1p, int* err, cudaStream_t s);
-int launch_tr_time_embed(const float* t, int B, int dim, int dup, float* out, long long ld, cudaStream_t s);
+int launch_tr_time_embed(const float* t, const int* perm, int B, int dim, int dup, float* out, long long ld, cudaStream_t s);
 int launch_tr_embed_x_fwd(const float* xs, int M, const float* w0, const float* b0, int E, bf16* h, long long ld, cudaStream_t s);
 int launch_tr_embed_x_bwd(const bf16* dh, long long ld, const float* xs, int M, const float* w0, const float* b0, int E, float* dw0,
                           float* db0, cudaStream_t s);

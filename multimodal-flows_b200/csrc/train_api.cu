@@ -56,9 +56,9 @@ int mmf_tr_pack(const float* xt, const int64_t* kt, const float* x0, const float
                           tgt, k1p, err, S_(stream));
 }
 
-int mmf_tr_time_embed(const float* t, int32_t B, int32_t dim, int32_t dup, float* out, int64_t ld, void* stream) {
+int mmf_tr_time_embed(const float* t, const int32_t* perm, int32_t B, int32_t dim, int32_t dup, float* out, int64_t ld, void* stream) {
     MMF_REQUIRE(t && out && dim >= 4 && dim % 2 == 0, "time_embed: bad argument");
-    return launch_tr_time_embed(t, B, dim, dup, out, ld, S_(stream));
+    return launch_tr_time_embed(t, perm, B, dim, dup, out, ld, S_(stream));
 }
 
 int mmf_tr_embed_x_fwd(const float* xs, int32_t M, const float* w0, const float* b0, int32_t E, void* h_bf16, int64_t ld, void* stream) {

@@ -21,7 +21,7 @@ SIGNATURES = {
     "mmf_tr_cast_transpose": [P, I64, I32, I32, I32, P, I64, P, I64, P, P],
     "mmf_tr_weights_transpose": [P, P, P, I32, I32, P],
     "mmf_tr_pack": [P, P, P, P, P, P, I32, I32, P, P, P, P, P, P],
-    "mmf_tr_time_embed": [P, I32, I32, I32, P, I64, P],
+    "mmf_tr_time_embed": [P, P, I32, I32, I32, P, I64, P],
     "mmf_tr_embed_x_fwd": [P, I32, P, P, I32, P, I64, P],
     "mmf_tr_embed_x_bwd": [P, I64, P, I32, P, P, I32, P, P, P],
     "mmf_tr_embed_y_fwd": [P, I32, P, I32, I32, P, I64, P],
@@ -124,8 +124,8 @@ class Ops:
         _abi.check(self.L.mmf_tr_pack(_p(xt), _p(kt), _p(x0), _p(x1), _p(k1), _p(row_slot), row_slot.shape[0], V, _p(xs), _p(ks), _p(tgt),
                                       _p(k1p), _p(err), self._s()))
 
-    def time_embed(self, t, dim, dup, out):
-        _abi.check(self.L.mmf_tr_time_embed(_p(t), t.shape[0], dim, int(dup), _p(out), out.stride(0), self._s()))
+    def time_embed(self, t, dim, dup, out, perm=None):
+        _abi.check(self.L.mmf_tr_time_embed(_p(t), _p(perm), t.shape[0], dim, int(dup), _p(out), out.stride(0), self._s()))
 
     def embed_x_fwd(self, xs, w0, b0, h):
         _abi.check(self.L.mmf_tr_embed_x_fwd(_p(xs), xs.shape[0], _p(w0), _p(b0), w0.shape[0], _p(h), h.stride(0), self._s()))

@@ -28,10 +28,17 @@ _ALIGN = 64                                      # elements: every parameter sta
 
 
 class _Plan:
-    """Row maps of one batch, built on the host from the mask (any mask works; the reference's are prefix masks)."""
+    """Row maps of one batch, built on the host from the mask (any mask works; the reference's are prefix masks).
+
+    The packed order of the jets is the planner's choice (nothing downstream depends on it: the step returns batch means and
+    parameter gradients): jets of at most 128 particles are packed best-fit-decreasing into tiles of at most 128 rows - the work
+    items of the tensor-core attention kernels - and laid out tile after tile; jets of 129 ... 150 particles follow (CUDA-core
+    attention kernels, their probabilities are kept: p_off counts those jets only), empty jets last.  perm[p] = index in the batch
+    of packed jet p (the per-jet time is read through it)."""
     padded = False
 
     def __init__(self, mask: torch.Tensor, device: torch.device, upload: bool = True):
+        import bisect
         m = mask.detach().reshape(mask.shape[0], -1).to("cpu").numpy() != 0
         self.B, self.D = m.shape
         n = m.sum(1).astype(np.int64)
@@ -39,38 +46,43 @@ class _Plan:
         self.M = int(n.sum())
         self.nmax = int(n.max()) if self.B else 0
         self.Mp = (self.M + 63) // 64 * 64
+        bins, free = [], []                                   # free: sorted (remaining rows, bin)
+        for b in sorted((int(b) for b in np.flatnonzero((n > 0) & (n <= 128))), key=lambda b: -int(n[b])):
+            nb = int(n[b])
+            i = bisect.bisect_left(free, (nb, -1))
+            if i < len(free):
+                rem, bi = free.pop(i)
+                bins[bi].append(b)
+            else:
+                rem, bi = 128, len(bins)
+                bins.append([b])
+            bisect.insort(free, (rem - nb, bi))
+        order = [b for jets in bins for b in jets] + [int(b) for b in np.flatnonzero(n > 128)] + [int(b) for b in np.flatnonzero(n == 0)]
+        self.h_perm = np.asarray(order, np.int32)
+        npk = n[self.h_perm] if self.B else n
+        self.n_packed = npk
         self.h_jet_off = np.zeros(self.B + 1, np.int32)
-        np.cumsum(n, out=self.h_jet_off[1:])
-        # tensor-core attention works on runs of consecutive whole jets with at most 128 rows; larger jets take the CUDA-core
-        # kernels (their probabilities are kept: p_off counts those jets only)
-        big = n > 128
+        np.cumsum(npk, out=self.h_jet_off[1:])
+        big = npk > 128
         self.has_big = bool(big.any())
         self.h_p_off = np.zeros(self.B + 1, np.int64)
-        np.cumsum(np.where(big, n * n, 0), out=self.h_p_off[1:])
+        np.cumsum(np.where(big, npk * npk, 0), out=self.h_p_off[1:])
         self.sum_n2 = int(self.h_p_off[-1])
-        items, start, rows = [], 0, 0
-        for b in range(self.B):
-            nb = int(n[b])
-            if nb == 0:
-                continue
-            if nb > 128 or rows + nb > 128:
-                if rows:
-                    items.append((start, rows))
-                rows = 0
-            if nb <= 128:
-                if rows == 0:
-                    start = int(self.h_jet_off[b])
-                rows += nb
-        if rows:
-            items.append((start, rows))
+        items, row = [], 0
+        for jets in bins:
+            rows = int(sum(int(n[b]) for b in jets))
+            items.append((row, rows))
+            row += rows
         self.h_items = np.asarray(items, np.int32).reshape(-1, 2)
         self.grid_items = len(items)
-        self.h_row_slot = np.flatnonzero(m.reshape(-1)).astype(np.int32)
-        self.h_row_jet = np.repeat(np.arange(self.B, dtype=np.int32), n)
+        pm = m[self.h_perm] if self.B else m                  # masks in packed jet order
+        pj, pd = np.nonzero(pm)
+        self.h_row_slot = (self.h_perm[pj].astype(np.int64) * self.D + pd).astype(np.int32)
+        self.h_row_jet = pj.astype(np.int32)
         up = lambda a: torch.from_numpy(a).to(device, non_blocking=True)
         self.row_slot = up(self.h_row_slot)
         if upload:
-            self.jet_off, self.p_off, self.row_jet = up(self.h_jet_off), up(self.h_p_off), up(self.h_row_jet)
+            self.jet_off, self.p_off, self.row_jet, self.perm = up(self.h_jet_off), up(self.h_p_off), up(self.h_row_jet), up(self.h_perm)
             self.items = up(self.h_items if len(items) else np.zeros((1, 2), np.int32))
             self.n_items = up(np.asarray([len(items)], np.int32))
 
@@ -89,9 +101,10 @@ class _GraphSlot:
         self.jet_off, self.p_off, self.row_jet = z(B + 1, dt=torch.int32), z(B + 1, dt=torch.int64), z(rows, dt=torch.int32)
         self.xs, self.tg, self.ks, self.k1p, self.t = z(rows, 3), z(rows, 3), z(rows, dt=torch.int32), z(rows, dt=torch.int32), z(B)
         self.items, self.n_items, self.grid_items, self.has_big = z(B, 2, dt=torch.int32), z(1, dt=torch.int32), B, bool(has_big)
+        self.perm = z(B, dt=torch.int32)
         self.pin = [torch.zeros(B + 1, dtype=torch.int32).pin_memory(), torch.zeros(B + 1, dtype=torch.int64).pin_memory(),
                     torch.zeros(rows, dtype=torch.int32).pin_memory(), torch.zeros(B, 2, dtype=torch.int32).pin_memory(),
-                    torch.zeros(1, dtype=torch.int32).pin_memory()]
+                    torch.zeros(1, dtype=torch.int32).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()]
         self.graph, self.out5, self.busy = None, None, None
 
     def load(self, plan: _Plan):
@@ -102,6 +115,8 @@ class _GraphSlot:
         self.pin[2][: plan.M].copy_(torch.from_numpy(plan.h_row_jet))
         self.pin[3][: plan.grid_items].copy_(torch.from_numpy(plan.h_items))
         self.pin[4][0] = plan.grid_items
+        self.pin[5].copy_(torch.from_numpy(plan.h_perm))
+        self.perm.copy_(self.pin[5], non_blocking=True)
         self.items.copy_(self.pin[3], non_blocking=True)
         self.n_items.copy_(self.pin[4], non_blocking=True)
         self.jet_off.copy_(self.pin[0], non_blocking=True)
@@ -372,7 +387,7 @@ class TrainEngine:
         c = {}
         # time embeddings: ParticleFormer adds the same 128-wide row to both streams, the fused encoder one 256-wide row
         temb = f32(B, 256)
-        ops.time_embed(t, h if self.pf else E, self.pf, temb)
+        ops.time_embed(t, h if self.pf else E, self.pf, temb, perm=plan.perm)
         c["temb"] = temb
         if self.pf:
             c["temb2"] = f32(B, E)
@@ -462,7 +477,7 @@ class TrainEngine:
         if self.cfg.multitask_loss == "time-weighted":
             N = "loss_combine.uncertainty_net."
             c["ue"], c["ua"], c["uh"], u = f32(B, E), f32(B, E), f32(B, E), f32(B, 2)
-            ops.time_embed(t, E, False, c["ue"])
+            ops.time_embed(t, E, False, c["ue"], perm=plan.perm)
             ops.sgemm(c["ue"], E, 1, self.p(N + "c_fc.weight"), 1, E, c["ua"], B, E, E, bias=self.p(N + "c_fc.bias"))
             ops.gelu_fwd(c["ua"], c["uh"])
             ops.sgemm(c["uh"], E, 1, self.p(N + "c_proj.weight"), 1, E, u, B, 2, E, bias=self.p(N + "c_proj.bias"))

@@ -75,7 +75,9 @@ class MockOps:
             src = params[int(j["src"]): int(j["src"]) + n].view(int(j["rows"]), int(j["cols"]))
             paramsT[int(j["dst"]): int(j["dst"]) + n] = src.T.contiguous().to(torch.bfloat16).flatten()
 
-    def time_embed(self, t, dim, dup, out):
+    def time_embed(self, t, dim, dup, out, perm=None):
+        if perm is not None:
+            t = t[perm.long()]
         half = dim // 2
         f = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1)))
         e = t[:, None] * f[None]

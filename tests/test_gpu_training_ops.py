@@ -277,6 +277,9 @@ def test_gelu_add_jetsum_time_embed(ops):
     ops.time_embed(t, 128, True, emb)
     ref = orc.timestep_embedding(t.cpu(), 128).to(DEV)
     assert torch.allclose(emb[:, :128], ref, atol=2e-6) and torch.equal(emb[:, 128:], emb[:, :128])
+    perm = torch.tensor([3, 0, 8, 1, 2, 7, 6, 5, 4], device=DEV, dtype=torch.int32)
+    ops.time_embed(t, 128, False, emb, perm=perm)
+    assert torch.allclose(emb[:, :128], ref[perm.long()], atol=2e-6)
 
 
 def test_embeddings_forward_backward(ops):
@@ -396,7 +399,10 @@ def test_tensor_core_attention_forward_backward(ops, hs, H):
     g = torch.Generator(device=DEV).manual_seed(hs + 1)
     ns = [3, 100, 1, 64, 128, 17, 60, 50, 140, 2, 127, 5, 121]
     plan = _Plan(synthetic.prefix_masks(torch.tensor(ns)), torch.device(DEV))
-    assert plan.has_big and plan.h_items.tolist() == [[0, 104], [104, 64], [168, 128], [296, 127], [563, 2], [565, 127], [692, 126]]
+    # best-fit decreasing: 128 | 127 + 1 | 121 + 5 + 2 | 100 + 17 | 64 + 60 + 3 | 50, then the 140-particle jet
+    assert plan.has_big and plan.h_items[:, 1].tolist() == [128, 128, 128, 117, 127, 50] and plan.n_packed[-1] == 140
+    assert sorted(plan.h_perm.tolist()) == list(range(len(ns)))
+    ns = [int(v) for v in plan.n_packed]                          # from here on: the packed order
     M, C = plan.M, hs * H
     qn, kn = bf(torch.randn(M, C, device=DEV, generator=g)), bf(torch.randn(M, C, device=DEV, generator=g))
     qkv = bf(torch.randn(M, 3 * C, device=DEV, generator=g))
