@@ -189,6 +189,10 @@ class TrainEngine:
         self._n_jobs, self._n_tiles = len(jobs), tile0
         self._sumsq, self._ones = torch.zeros(1, device=dev), None
         self._err = torch.zeros(1, device=dev, dtype=torch.int32)
+        if _ops is None and torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            # what DistributedDataParallel does at construction: every replica starts from rank 0's parameters (the randomly
+            # initialised uncertainty net of MultiTaskLoss differs from process to process otherwise)
+            torch.distributed.broadcast(self.P, src=0)
         self.refresh_operands()
         self.use_graphs, self.graph_rows, self._slots, self.max_graphs = bool(use_graphs) and _ops is None, 1024, {}, 6
         self.concurrent, self._streams, self._wstreams, self._wused, self._keep = _ops is None, [], {}, set(), []

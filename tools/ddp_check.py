@@ -20,7 +20,8 @@ def make():
     b = MultiModalFlowBridge(cfg)
     b.model.load_state_dict(sd)
     return b.to(dev)
-eng = TrainEngine(make(), lr=1e-3, use_graphs=True)
+eng = TrainEngine(make(), lr=1e-3, use_graphs=True)      # broadcasts rank 0's parameters (the loss net is randomly initialised per process)
+P_start = eng.P.clone()
 B, steps = 32, 4
 gen = torch.Generator().manual_seed(5)
 draws = [[(torch.rand(B, generator=gen), torch.randn(B, 150, 3, generator=gen), torch.rand(B, 150, generator=gen)) for _ in range(world)] for _ in range(steps)]
@@ -37,8 +38,10 @@ ok_replicas = all(torch.equal(gathered[0], g) for g in gathered)
 msg = ""
 if rank == 0:
     dist_backup = torch.distributed.is_initialized
+    torch.distributed.is_initialized = lambda: False          # the solo engine must neither broadcast nor all-reduce
     solo = TrainEngine(make(), lr=1e-3, use_graphs=False)
-    torch.distributed.is_initialized = lambda: False          # the solo engine must not all-reduce
+    solo.P.copy_(P_start)
+    solo.refresh_operands()
     try:
         for s in range(steps):
             acc = torch.zeros_like(solo.G)
