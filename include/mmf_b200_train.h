@@ -125,7 +125,8 @@ int mmf_tr_loss_combine(const float* loss_mse, const float* loss_ce, const float
 /* d loss / d (vt, logits) per row; rows at and beyond jet_off[B] (a batch padded to a fixed row capacity M) get zeros */
 int mmf_tr_loss_bwd(const float* vt, const float* logits, const float* tgt, const int32_t* k1, const int32_t* row_jet, const int32_t* jet_off,
                     const float* gl1, const float* gl2, int32_t M, int32_t B, int32_t V, float* dvt, float* dlog, void* stream);
-/* out[0] = sum g^2 (the squared gradient norm of clip_grad_norm_) */
+/* out[0] = sum g^2 (the squared gradient norm of clip_grad_norm_); `out` points to 2048 floats (out[1..] holds per-block partial
+ * sums of a two-stage, fixed-order - hence bit-reproducible - reduction: data-parallel replicas compute identical clip coefficients) */
 int mmf_tr_sumsq(const float* g, int64_t n, float* out, void* stream);
 /* torch.optim.Adam step `step` (1-based) on flat buffers; the gradient is first multiplied by grad_scale and, when sumsq is
  * given and max_norm > 0, by min(1, max_norm / (grad_scale sqrt(sumsq) + 1e-6)); p16 (optional) receives the bf16 copy */

@@ -882,7 +882,7 @@ __global__ void tr_loss_bwd_kernel(const float* __restrict__ vt, const float* __
 }
 
 // ------------------------------------------------------------------------------------------------ optimiser
-__global__ void __launch_bounds__(256) tr_sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) tr_sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ partial) {
     grid_dep_wait();
     grid_dep_launch();
     __shared__ float red[8];
@@ -896,8 +896,24 @@ __global__ void __launch_bounds__(256) tr_sumsq_kernel(const float* __restrict__
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) t += red[w];
-        atomicAdd(out, t);
+        partial[blockIdx.x] = t;
     }
+}
+// second stage, one block, fixed order: the result is bit-reproducible (replicas of a data-parallel run compute the same clip
+// coefficient from the same all-reduced gradient and stay bit-identical)
+__global__ void __launch_bounds__(256) tr_sumsq_final_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+    grid_dep_wait();
+    grid_dep_launch();
+    __shared__ float red[256];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o >= 1; o >>= 1) {
+        if (static_cast<int>(threadIdx.x) < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
 }
 
 __global__ void tr_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
@@ -1185,10 +1201,10 @@ int launch_tr_loss_bwd(const float* vt, const float* logits, const float* tgt, c
 }
 
 int launch_tr_sumsq(const float* g, long long n, float* out, cudaStream_t s) {
-    MMF_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float), s));
-    if (n <= 0) return 0;
-    MMF_CUDA_OK(tr_launch(tr_sumsq_kernel, dim3(static_cast<unsigned>(std::min<long long>((n + 255) / 256, 148 * 8))), dim3(256), 0, s, g, n, out));
-    MMF_CUDA_OK(cudaGetLastError());
+    // out[0] = result, out[1 .. kSumsqScratch) = per-block partial sums
+    const int blocks = n <= 0 ? 0 : static_cast<int>(std::min<long long>((n + 255) / 256, kSumsqScratch - 1));
+    if (blocks > 0) MMF_CUDA_OK(tr_launch(tr_sumsq_kernel, dim3(blocks), dim3(256), 0, s, g, n, out + 1));
+    MMF_CUDA_OK(tr_launch(tr_sumsq_final_kernel, dim3(1), dim3(256), 0, s, static_cast<const float*>(out + 1), blocks, out));
     return 0;
 }
 

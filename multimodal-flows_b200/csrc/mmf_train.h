@@ -143,6 +143,7 @@ int launch_tr_loss_combine(const float* loss_mse, const float* loss_ce, const fl
 int launch_tr_loss_bwd(const float* vt, const float* logits, const float* tgt, const int* k1, const int* row_jet, const int* jet_off,
                        const float* gl1, const float* gl2, int M, int B, int V, float* dvt, float* dlog, cudaStream_t s);
 
+constexpr int kSumsqScratch = 2048;      // floats behind `out`: out[0] the result, the rest per-block partial sums
 int launch_tr_sumsq(const float* g, long long n, float* out, cudaStream_t s);
 // torch.optim.Adam (reference model/MMF.py:77-78) with Lightning's gradient_clip_val norm clipping (scripts/train_mmf.py:166) folded in
 int launch_tr_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, int step,

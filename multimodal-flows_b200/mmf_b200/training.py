@@ -187,7 +187,7 @@ class TrainEngine:
             rec[i] = j
         self._jobs = torch.from_numpy(rec.view(np.uint8).copy()).to(dev)
         self._n_jobs, self._n_tiles = len(jobs), tile0
-        self._sumsq, self._ones = torch.zeros(1, device=dev), None
+        self._sumsq, self._ones = torch.zeros(2048, device=dev), None       # [0] the squared gradient norm, the rest scratch
         self._err = torch.zeros(1, device=dev, dtype=torch.int32)
         if _ops is None and torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
             # what DistributedDataParallel does at construction: every replica starts from rank 0's parameters (the randomly
@@ -680,7 +680,7 @@ class TrainEngine:
 
     def grad_norm(self) -> float:
         self.ops.sumsq(self.G, self._sumsq)
-        return float(self._sumsq.sqrt())
+        return float(self._sumsq[0].sqrt())
 
     def check_tokens(self):
         if int(self._err.item()):

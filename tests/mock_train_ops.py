@@ -280,12 +280,12 @@ class MockOps:
         dlog.copy_(torch.where((k1 != 0)[:, None] & real, (gl2[rj] / n[rj])[:, None] * p, torch.zeros_like(p)))
 
     def sumsq(self, g, out):
-        out.copy_((g.double() ** 2).sum().float().view(1))
+        out[0] = (g.double() ** 2).sum().float()
 
     def adam(self, p, g, m, v, lr, beta1, beta2, eps, step, sumsq=None, max_norm=0.0, grad_scale=1.0, p16=None):
         coef = grad_scale
         if sumsq is not None and max_norm > 0:
-            coef *= min(1.0, max_norm / (float(sumsq.sqrt()) * grad_scale + 1e-6))
+            coef *= min(1.0, max_norm / (float(sumsq[0].sqrt()) * grad_scale + 1e-6))
         gi = g * coef
         m.mul_(beta1).add_(gi, alpha=1 - beta1)
         v.mul_(beta2).addcmul_(gi, gi, value=1 - beta2)
