@@ -290,6 +290,7 @@ int launch_mode(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
 
 int launch_tr_gemm(const void* A, long long lda, const void* B, long long ldb, void* C, long long ldc, int M, int N, int K,
                    const float* bias, int mode, int ksplit, void* aux, long long ldaux, const TrGemmResid* resid, cudaStream_t s) {
+    if (M <= 0 || N <= 0) return 0;                      // an empty batch: nothing to do (empty torch tensors have null pointers)
     MMF_REQUIRE(A && B && C, "gemm: null operand");
     MMF_REQUIRE(mode >= 0 && mode <= 5, "gemm: mode is 0 (bf16), 1 (fp32), 2 (fp32 reduce-add), 3 (bf16 + GELU copy), 4 (bf16 times GELU'(aux)), 5 (fp32 residual + product)");
     MMF_REQUIRE((mode != 3 && mode != 4) || aux, "gemm: modes 3 and 4 need the auxiliary [M x N] bf16 tensor");
@@ -327,9 +328,9 @@ int launch_tr_gemm(const void* A, long long lda, const void* B, long long ldb, v
 int launch_tr_gemm_qkv(const void* A, long long lda, const void* W, long long ldw, const float* bias, void* qkv, long long ldq, void* qkn,
                        long long ldn, int M, int C, int K, int hs, const float* qg, const float* qb, const float* kg, const float* kb,
                        cudaStream_t s) {
+    if (M <= 0) return 0;
     MMF_REQUIRE(A && W && qkv && qkn && qg && kg, "gemm_qkv: null argument");
     MMF_REQUIRE(C % 128 == 0 && (hs == 32 || hs == 64), "gemm_qkv: width a multiple of 128, head size 32 or 64");
-    if (M <= 0) return 0;
     const int kb_total = (K + kBK - 1) / kBK;
     CUtensorMap tmA, tmB, tmC, tmD;
     if (make_tmap_2d(&tmA, A, 2, M, K, lda, 64, 128) || make_tmap_2d(&tmB, W, 2, 3 * C, K, ldw, 64, 128) ||
@@ -344,8 +345,8 @@ int launch_tr_gemm_qkv(const void* A, long long lda, const void* W, long long ld
 // activations: both operands MN-major); K split over `ksplit` CTAs per output tile, fp32 TMA reduce-add
 int launch_tr_gemm_tn(const void* A, long long lda, const void* B, long long ldb, float* C, long long ldc, int M, int N, int K, int ksplit,
                       cudaStream_t s) {
-    MMF_REQUIRE(A && B && C, "gemm_tn: null operand");
     if (M <= 0 || N <= 0 || K <= 0) return 0;
+    MMF_REQUIRE(A && B && C, "gemm_tn: null operand");
     const int kb_total = (K + kBK - 1) / kBK;
     if (ksplit < 1) ksplit = 1;
     if (ksplit > kb_total) ksplit = kb_total;

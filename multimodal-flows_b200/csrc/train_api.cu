@@ -33,12 +33,14 @@ int mmf_tr_gemm_tn(const void* A, int64_t lda, const void* B, int64_t ldb, float
 
 int mmf_tr_sgemm(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn, float* C, int64_t ldc, int32_t M,
                  int32_t N, int32_t K, const float* bias, int32_t accumulate, void* stream) {
+    if (M <= 0 || N <= 0) return 0;
     MMF_REQUIRE(A && B && C, "sgemm: null operand");
     return launch_tr_sgemm(A, sam, sak, B, sbk, sbn, C, ldc, M, N, K, bias, accumulate, S_(stream));
 }
 
 int mmf_tr_cast_transpose(const void* in, int64_t ld_in, int32_t in_f32, int32_t rows, int32_t cols, void* out_bf16, int64_t ld_out,
                           void* outT_bf16, int64_t ldT, float* colsum, void* stream) {
+    if (rows <= 0 || cols <= 0) return 0;
     MMF_REQUIRE(in, "cast_transpose: null input");
     return launch_tr_cast_transpose(in, ld_in, in_f32, rows, cols, BF(out_bf16), ld_out, BF(outT_bf16), ldT, colsum, S_(stream));
 }

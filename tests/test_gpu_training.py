@@ -237,3 +237,21 @@ def test_graph_cache_eviction_and_reloaded_weights(golden_dir):
     b = synthetic.training_batch(12, seed=52)
     t, z, u = torch.rand(12, generator=gen), torch.randn(12, 150, 3, generator=gen), torch.rand(12, 150, generator=gen)
     assert torch.allclose(eng.loss_and_grad(b, time=t, z=z, u=u), fresh.loss_and_grad(b, time=t, z=z, u=u), rtol=1e-5, atol=1e-6)
+
+
+def test_degenerate_batches():
+    """A batch whose jets are all empty (nothing to pack) and a batch of single-particle jets run through the whole step."""
+    from mmf_b200 import synthetic
+    from mmf_b200.mmf import MultiModalFlowBridge
+    from mmf_b200.param_spec import make_config
+    from mmf_b200.training import TrainEngine
+    cfg = make_config("ParticleFormer", sigma=1e-3, lr=1e-3, n_layer=1, n_layer_fused=1)
+    bridge = MultiModalFlowBridge(cfg)
+    bridge.model.load_state_dict(synthetic.make_state_dict(cfg, flavor="wide", seed=2))
+    eng = TrainEngine(bridge.to(DEV), lr=1e-3)
+    batch, (x0, k0, x1, k1, mask, t, z, u) = _random_case(cfg, [0, 0, 0], seed=1)
+    out5 = eng.train_step(batch, time=t, z=z, u=u)
+    assert float(out5[1]) == 0.0 and float(out5[2]) == 0.0 and bool(torch.isfinite(eng.P).all())       # empty jets: losses 0 (clamp_min(1))
+    batch, (x0, k0, x1, k1, mask, t, z, u) = _random_case(cfg, [1, 1, 1, 1, 1], seed=2)
+    out5 = eng.train_step(batch, time=t, z=z, u=u)
+    assert bool(torch.isfinite(out5).all()) and bool(torch.isfinite(eng.P).all()) and float(eng.G.abs().max()) > 0
