@@ -9,7 +9,8 @@
 //              Only the row statistics (max * scale * log2e, 1 / sum) are kept for the backward pass: 8 bytes per (row, head).
 //   backward   S = Q K^T and dP = dO V^T again on the tensor cores; P and dS = P (dP - sum_j P dP) * scale are rebuilt row by
 //              row (the row sum uses the very P that multiplies it, so sum_j dS_ij = 0 holds to fp32 rounding); then
-//              dV = P^T dO, dQ = dS K, dK = dS^T Q.
+//              dQ = dS K, dK = dS^T Q, dV = P^T dO.  P and dS take turns in one pair of shared-memory boxes and the gradients
+//              reuse the accumulator columns of dP, so two CTAs fit on an SM (96 KB, 256 TMEM columns each).
 //
 // No operand is ever transposed in memory: V, K, Q and dO are read as MN-major B operands ([rows = contraction index][64
 // features]) where the contraction runs over particles, P and dS as MN-major A operands for the "transposed" products.
@@ -26,7 +27,7 @@ constexpr int kBox = kTileM * 128;               // [128 rows][128 B] = 16 KB: o
 constexpr uint32_t kRowStep16 = 2048u >> 4;      // 16 rows of 128 B: one K = 16 step of an MN-major operand
 
 struct AttnTcBars {
-    uint64_t loaded, mma_a, mma_b;
+    uint64_t loaded, mma_a, mma_b, mma_c;
     uint32_t tmem_base;
 };
 
@@ -179,8 +180,13 @@ tr_attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------ backward
+// Two CTAs share an SM (96 KB of shared memory, 256 TMEM columns each): P and dS take turns in ONE pair of boxes and the
+// gradients land in the accumulator columns of dP once that is consumed.  Per head:
+//   S = Q K^T -> [0,128), dP = dO V^T -> [128,256)          | rows: delta = sum_j P dP, dS -> boxes
+//   dQ = dS K -> [128,192), dK = dS^T Q -> [192,256)        | rows: store dQ, dK; P (from S, still intact) -> boxes
+//   dV = P^T dO -> [128,192)                                | rows: store dV
 template <int HS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 2)
 tr_attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmD, const TrAttnTcArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -190,23 +196,21 @@ tr_attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     uint8_t* Ks = Qs + kBox;
     uint8_t* Vs = Ks + kBox;
     uint8_t* Ds = Vs + kBox;                     // dO
-    uint8_t* Ps = Ds + kBox;                     // P:  two boxes of 64 keys
-    uint8_t* Ss = Ps + 2 * kBox;                 // dS: two boxes of 64 keys
-    if (static_cast<int>(blockIdx.x) >= *a.n_items) return;
+    uint8_t* Xs = Ds + kBox;                     // dS, then P: two boxes of 64 keys
+    if (static_cast<int>(blockIdx.x) >= *a.n_items) return;        // (n_items comes from a host copy, not from the previous kernel)
     const int2 item = a.items[blockIdx.x];
     const int row0 = item.x, nrows = item.y;
     const int col0 = blockIdx.y * 64;
     const int warp = threadIdx.x >> 5, r = threadIdx.x;
     constexpr int NH = 64 / HS, KS = HS / 16;
-    // TMEM columns: S [0,128)  dP [128,256)  dV [256,320)  dQ [320,384)  dK [384,448)
-    constexpr uint32_t cS = 0, cP = 128, cV = 256, cQ = 320, cK = 384;
+    constexpr uint32_t cS = 0, cP = 128, cQ = 128, cK = 192, cV = 128;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmD);
-        mbar_init(&bars->loaded, 1); mbar_init(&bars->mma_a, 1); mbar_init(&bars->mma_b, 1);
+        mbar_init(&bars->loaded, 1); mbar_init(&bars->mma_a, 1); mbar_init(&bars->mma_b, 1); mbar_init(&bars->mma_c, 1);
         fence_mbar_init();
     }
-    if (warp == 0) { __syncwarp(); tmem_alloc(&bars->tmem_base, 512); tmem_relinquish(); }
+    if (warp == 0) { __syncwarp(); tmem_alloc(&bars->tmem_base, 256); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -224,6 +228,19 @@ tr_attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     row_segment(a, row0, r, nrows, &kb, &ke);
     const bool valid = r < nrows;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    auto store_out = [&](uint32_t col, int w, int h) {        // dq | dk | dv sections of dqkv; row r is a query (dq) or a key (dk, dv)
+        float v[HS];
+#pragma unroll
+        for (int c = 0; c < HS / 32; ++c) tmem_ld32(taddr + col + h * HS + c * 32, v + c * 32);
+        tmem_ld_wait();
+        if (valid) {
+            uint4* dst = reinterpret_cast<uint4*>(a.dqkv + static_cast<long long>(row0 + r) * a.ldd + w * a.C + col0 + h * HS);
+#pragma unroll
+            for (int u = 0; u < HS / 8; ++u)
+                dst[u] = make_uint4(pack_bf16x2(v[u * 8 + 0], v[u * 8 + 1]), pack_bf16x2(v[u * 8 + 2], v[u * 8 + 3]),
+                                    pack_bf16x2(v[u * 8 + 4], v[u * 8 + 5]), pack_bf16x2(v[u * 8 + 6], v[u * 8 + 7]));
+        }
+    };
 
     for (int h = 0; h < NH; ++h) {
         if (threadIdx.x == 0) {
@@ -244,7 +261,7 @@ tr_attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (valid) st = *(reinterpret_cast<const float2*>(a.stats) + (static_cast<long long>(row0 + r) * a.H + blockIdx.y * NH + h));
         mbar_wait(&bars->mma_a, h & 1);
         tc_fence_after();
-        // delta = sum_j P_ij dP_ij with the P that is used below
+        // delta = sum_j P_ij dP_ij with the P that multiplies it below
         float delta = 0.f;
         for (int c = 0; c < 4; ++c) {
             float s[32], dp[32];
@@ -267,23 +284,18 @@ tr_attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             for (int j = 0; j < 32; ++j) {
                 const int col = c * 32 + j;
                 const float p = (col >= kb && col < ke) ? exp2f(fmaf(s[j], a.scale_log2e, -st.x)) * st.y : 0.f;
-                s[j] = p;
                 dp[j] = p * (dp[j] - delta) * a.scale;
             }
-            store_bf16_row32(Ps + (c >> 1) * kBox, r, c & 1, s);
-            store_bf16_row32(Ss + (c >> 1) * kBox, r, c & 1, dp);
+            store_bf16_row32(Xs + (c >> 1) * kBox, r, c & 1, dp);
         }
         fence_proxy_async();
         tc_fence_before();
-        __syncthreads();
+        __syncthreads();                         // dS is in the boxes, dP is consumed: its columns take dQ and dK
         if (threadIdx.x == 0) {
             tc_fence_after();
-            // dV = P^T dO, dK = dS^T Q: A MN-major ([query rows][keys], two boxes of 64 keys), B MN-major ([query rows][64 features])
+            // dK = dS^T Q: A MN-major ([query rows][keys], two boxes of 64 keys), B MN-major ([query rows][64 features])
             constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64) | kAMn | kBMn;
-            const uint64_t ap = desc_mn(smem_u32(Ps), kBox), as = desc_mn(smem_u32(Ss), kBox);
-            const uint64_t bd = umma_desc_sw128(smem_u32(Ds)), bq = umma_desc_sw128(smem_u32(Qs));
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) umma_bf16(tmem_base + cV, ap + kRowStep16 * kk, bd + kRowStep16 * kk, idesc_t, kk != 0 ? 1u : 0u);
+            const uint64_t as = desc_mn(smem_u32(Xs), kBox), bq = umma_desc_sw128(smem_u32(Qs));
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) umma_bf16(tmem_base + cK, as + kRowStep16 * kk, bq + kRowStep16 * kk, idesc_t, kk != 0 ? 1u : 0u);
             // dQ = dS K: A K-major (keys contiguous), B = K MN-major ([key rows][64 features])
@@ -291,37 +303,51 @@ tr_attn_tc_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             const uint64_t bk = umma_desc_sw128(smem_u32(Ks));
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
-                const uint64_t da = umma_desc_sw128(smem_u32(Ss + (kk >> 2) * kBox)) + 2 * (kk & 3);
+                const uint64_t da = umma_desc_sw128(smem_u32(Xs + (kk >> 2) * kBox)) + 2 * (kk & 3);
                 umma_bf16(tmem_base + cQ, da, bk + kRowStep16 * kk, idesc_q, kk != 0 ? 1u : 0u);
             }
             umma_commit(&bars->mma_b);
         }
         __syncwarp();
-        mbar_wait(&bars->mma_b, h & 1);
+        mbar_wait(&bars->mma_b, h & 1);           // the products have read dS: the boxes are free for P
         tc_fence_after();
-#pragma unroll
-        for (int w = 0; w < 3; ++w) {            // dq | dk | dv sections of dqkv; row r is a query (dq) or a key (dk, dv) of the item
-            const uint32_t col = (w == 0 ? cQ : (w == 1 ? cK : cV)) + h * HS;
-            float v[HS];
-#pragma unroll
-            for (int c = 0; c < HS / 32; ++c) tmem_ld32(taddr + col + c * 32, v + c * 32);
+        store_out(cQ, 0, h);
+        store_out(cK, 1, h);
+        for (int c = 0; c < 4; ++c) {            // P again, from the scores that still sit in [0,128)
+            float s[32];
+            tmem_ld32(taddr + cS + c * 32, s);
             tmem_ld_wait();
-            if (valid) {
-                uint4* dst = reinterpret_cast<uint4*>(a.dqkv + static_cast<long long>(row0 + r) * a.ldd + w * a.C + col0 + h * HS);
 #pragma unroll
-                for (int u = 0; u < HS / 8; ++u)
-                    dst[u] = make_uint4(pack_bf16x2(v[u * 8 + 0], v[u * 8 + 1]), pack_bf16x2(v[u * 8 + 2], v[u * 8 + 3]),
-                                        pack_bf16x2(v[u * 8 + 4], v[u * 8 + 5]), pack_bf16x2(v[u * 8 + 6], v[u * 8 + 7]));
+            for (int j = 0; j < 32; ++j) {
+                const int col = c * 32 + j;
+                s[j] = (col >= kb && col < ke) ? exp2f(fmaf(s[j], a.scale_log2e, -st.x)) * st.y : 0.f;
             }
+            store_bf16_row32(Xs + (c >> 1) * kBox, r, c & 1, s);
         }
+        fence_proxy_async();
         tc_fence_before();
-        __syncthreads();
+        __syncthreads();                         // P is in the boxes, dQ / dK have left their columns
+        if (threadIdx.x == 0) {
+            tc_fence_after();
+            // dV = P^T dO: A MN-major, B MN-major
+            constexpr uint32_t idesc_t = umma_idesc_bf16(128, 64) | kAMn | kBMn;
+            const uint64_t ap = desc_mn(smem_u32(Xs), kBox), bd = umma_desc_sw128(smem_u32(Ds));
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) umma_bf16(tmem_base + cV, ap + kRowStep16 * kk, bd + kRowStep16 * kk, idesc_t, kk != 0 ? 1u : 0u);
+            umma_commit(&bars->mma_c);
+        }
+        __syncwarp();
+        mbar_wait(&bars->mma_c, h & 1);
+        tc_fence_after();
+        store_out(cV, 2, h);
+        tc_fence_before();
+        __syncthreads();                         // the next head's S / dP overwrite the columns, its dS the boxes
     }
-    if (warp == 0) tmem_dealloc(tmem_base, 512);
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 constexpr int kFwdSmem = 1024 + 5 * kBox + 1024;
-constexpr int kBwdSmem = 1024 + 8 * kBox + 1024;
+constexpr int kBwdSmem = 1024 + 6 * kBox + 1024;      // 98 KB: two CTAs per SM
 
 template <int TAG, typename K>
 int configure_once(K kernel, int bytes) {
