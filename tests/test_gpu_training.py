@@ -255,3 +255,39 @@ def test_degenerate_batches():
     batch, (x0, k0, x1, k1, mask, t, z, u) = _random_case(cfg, [1, 1, 1, 1, 1], seed=2)
     out5 = eng.train_step(batch, time=t, z=z, u=u)
     assert bool(torch.isfinite(out5).all()) and bool(torch.isfinite(eng.P).all()) and float(eng.G.abs().max()) > 0
+
+
+def test_config5_full_size_step_against_fp32_autograd():
+    """BASELINE config #5 at its own size: ParticleFormer, 256 AOJ-shaped jets (13 819 particles, 109 attention tiles), time-weighted
+    loss, through the CUDA graph - loss and whole gradient against fp32 autograd over the oracle on the same draws."""
+    from mmf_b200 import synthetic
+    from mmf_b200.mmf import MultiModalFlowBridge
+    from mmf_b200.param_spec import make_config
+    from mmf_b200.training import TrainEngine
+    from oracle import mmf_oracle as orc
+    cfg = make_config("ParticleFormer", sigma=1e-3, lr=5e-4)
+    sd = synthetic.make_state_dict(cfg, flavor="wide", seed=0)
+    bridge = MultiModalFlowBridge(cfg)
+    bridge.model.load_state_dict(sd)
+    sd_loss = {k: v.detach().clone() for k, v in bridge.loss_combine.state_dict().items()}
+    eng = TrainEngine(bridge.to(DEV), lr=5e-4, use_graphs=True)
+    B = 256
+    batch = synthetic.training_batch(B, seed=1234)
+    assert int(batch.target.mask.sum()) == 13819
+    g = torch.Generator().manual_seed(9)
+    t, z, u = cfg.time_eps + (1 - cfg.time_eps) * torch.rand(B, generator=g), torch.randn(B, 150, 3, generator=g), torch.rand(B, 150, generator=g)
+    eng.loss_and_grad(batch, time=t, z=z, u=u)
+    out5 = eng.loss_and_grad(batch, time=t, z=z, u=u)                    # the replay
+    assert eng.last_plan.grid_items == 109
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sdg = {k: v.to(DEV).clone().requires_grad_(True) for k, v in sd.items()}
+    slg = {k: v.to(DEV).clone().requires_grad_(True) for k, v in sd_loss.items()}
+    d = lambda x: x.to(DEV)
+    want = orc.training_loss(sdg, slg, cfg, d(batch.source.continuous), d(batch.source.discrete), d(batch.target.continuous), d(batch.target.discrete),
+                             d(batch.target.mask), d(t), d(z), d(u))
+    want[0].backward()
+    assert abs(float(out5[0]) - float(want[0].detach())) <= 3e-2 * abs(float(want[0].detach()))
+    grads = {"model." + k: v.grad for k, v in sdg.items()}
+    grads.update({"loss_combine." + k: v.grad for k, v in slg.items()})
+    gcos, grel, _ = compare_gradients(eng, grads, verbose="config #5, 256 jets")
+    assert gcos > 0.999 and grel < 3e-2
