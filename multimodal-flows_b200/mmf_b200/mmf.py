@@ -211,7 +211,8 @@ class MultiModalFlowBridge(_GenerativeBase):
 
     def validation_step(self, batch: DataCoupling, batch_idx: int = 0):
         engine = getattr(self, "_engine", None)
-        if engine is not None:                              # the training engine's forward (any multitask_loss mode), no gradients
+        if engine is not None and self.model is engine.model_ref:   # (an EMA module swapped in by EMACallback validates through loss())
+            # the training engine's forward (any multitask_loss mode), no gradients
             out = engine.loss_only(batch)
             weighted = self.config.multitask_loss != "sum"
             loss, loss_mse, loss_ce, w_mse, w_ce = out[0], out[1], out[2], out[3] if weighted else None, out[4] if weighted else None

@@ -144,6 +144,7 @@ class TrainEngine:
         if _ops is None and dev.type != "cuda":
             raise RuntimeError("the training step runs through libmmf_b200.so on a CUDA device (there is no CPU fallback)")
         self.module, self.cfg, self.device = module, cfg, dev
+        self.model_ref = module.model                        # the encoder whose parameters live in the flat buffers
         self.ops = _ops if _ops is not None else Ops(dev)
         self.lr = float(lr if lr is not None else getattr(cfg, "lr", 1e-3))
         self.betas, self.eps, self.max_norm = betas, eps, float(max_norm)

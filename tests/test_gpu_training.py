@@ -291,3 +291,48 @@ def test_config5_full_size_step_against_fp32_autograd():
     grads.update({"loss_combine." + k: v.grad for k, v in slg.items()})
     gcos, grel, _ = compare_gradients(eng, grads, verbose="config #5, 256 jets")
     assert gcos > 0.999 and grel < 3e-2
+
+
+def test_train_ema_checkpoint_sample_cycle(tmp_path):
+    """The reference's life cycle on the device path: training steps with EMACallback -> validation on the EMA weights -> a
+    Lightning-layout checkpoint (state_dict + ema_state_dict) -> load_from_checkpoint -> use_ema_weights -> predict_step."""
+    from mmf_b200 import synthetic
+    from mmf_b200.callbacks import EMACallback
+    from mmf_b200.mmf import MultiModalFlowBridge
+    from mmf_b200.param_spec import make_config
+    cfg = make_config("FusedParticleFormer", n_layer=2, num_timesteps=4, sigma=1e-3, lr=2e-3, use_ema_weights=True, ema_decay=0.9, seed=3)
+    sd0 = synthetic.make_state_dict(cfg, flavor="wide", seed=6)
+    bridge = MultiModalFlowBridge(cfg)
+    bridge.model.load_state_dict(sd0)
+    bridge = bridge.to(DEV)
+    bridge.configure_training(lr=cfg.lr)
+    cb = EMACallback(cfg)
+    cb.on_fit_start(None, bridge)
+    batch = synthetic.training_batch(16, seed=77)
+    losses = []
+    for _ in range(6):
+        losses.append(float(bridge.training_step(batch)["loss"]))
+        cb.on_train_batch_end(None, bridge)
+    key = "transformer.blocks.0.ffw.c_fc.weight"
+    trained = bridge.model.state_dict()[key].detach().cpu()
+    ema = cb.ema_model.module.state_dict()[key].detach().cpu()
+    assert not torch.equal(trained, sd0[key]) and not torch.equal(ema, sd0[key]) and not torch.equal(ema, trained)
+    # EMA after 6 updates from the same start lies between the start and the trained weights
+    assert float((ema - sd0[key]).norm()) < float((trained - sd0[key]).norm())
+    cb.on_validation_epoch_start(None, bridge)
+    assert bridge.model is cb.ema_model.module
+    v_ema = float(bridge.validation_step(batch)["val_loss"])
+    cb.on_validation_epoch_end(None, bridge)
+    v_trained = float(bridge.validation_step(batch)["val_loss"])
+    assert np.isfinite(v_ema) and np.isfinite(v_trained) and v_ema != v_trained
+    ckpt = synthetic.to_checkpoint(cfg, {k: v.detach().cpu() for k, v in bridge.model.state_dict().items()}, ema=cb.state_dict()["ema_state_dict"])
+    ckpt["state_dict"].update({"loss_combine." + k: v.detach().cpu() for k, v in bridge.loss_combine.state_dict().items()})
+    path = str(tmp_path / "last.ckpt")
+    torch.save(ckpt, path)
+    loaded = MultiModalFlowBridge.load_from_checkpoint(path, map_location="cpu", config=cfg).to(DEV)
+    assert torch.equal(loaded.model.state_dict()[key].cpu(), trained)
+    assert loaded.use_ema_weights() and torch.equal(loaded.model.state_dict()[key].cpu(), ema)
+    src = synthetic.source_batch(8, seed=5)
+    out = loaded.predict_step(src, batch_idx=0)
+    real = src.source.mask.bool().squeeze(-1)
+    assert bool(torch.isfinite(out.continuous).all()) and int(out.discrete[real].min()) >= 0 and int(out.discrete[real].max()) < cfg.vocab_size
