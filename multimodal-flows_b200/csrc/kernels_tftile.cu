@@ -73,6 +73,7 @@ struct Epi {
     uint32_t kmask, kfull, kpart;   // 16-key groups of this thread's key half: attended by any row of the warp / in full by
                                     // every row / cut by a jet boundary of some row
     uint32_t kc, vc;                // pair tiles: K / V rows of how many units staged so far
+    uint32_t nomax;                 // scores are bounded (TfLaunch.softmax_nomax): the softmax needs no row maximum
     unsigned long long* trace;   // clock stamps of CTA 0 / thread 0 for the first two timesteps (debugging aid) or null
     int mark_i, step;
 };
@@ -257,9 +258,12 @@ __device__ __forceinline__ void ln_stats(Epi& e, const RowStat& st, int slot, fl
         rstd = rsqrtf(m2 * (1.0f / 128.0f) + 1e-5f);
     }
 }
-// normalised row -> bf16 GEMM operand (Abuf)
+// normalised row -> bf16 GEMM operand (Abuf).  The affine part of every LayerNorm that feeds a linear layer is folded into
+// that layer on the host (W' = W diag(g), b' = b + W beta: tftile_model.cu fold_ln), so the operand is (v - mean) rstd itself:
+// one packed fma per two elements and no parameter loads.
 template <bool PAIR>
-__device__ __forceinline__ void ln_to_abuf(Epi& e, float mean, float rstd, const float* g, const float* b) {
+__device__ __forceinline__ void ln_to_abuf(Epi& e, float mean, float rstd) {
+    const float2 rs = f2dup(rstd), nmrs = f2dup(-mean * rstd);
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
         const int c0 = cc * 32;
@@ -267,13 +271,7 @@ __device__ __forceinline__ void ln_to_abuf(Epi& e, float mean, float rstd, const
         tmem_ld32(e.taddr + e.hf * 128 + c0, v);
         tmem_ld_wait();
 #pragma unroll
-        const float2 nm = f2dup(-mean), rs = f2dup(rstd);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const float4 gg = ldf4(g + c0 + 4 * u), bb = ldf4(b + c0 + 4 * u);
-            MMF_SET2(v, 4 * u, f2fma(f2mul(f2add(MMF_V2(v, 4 * u), nm), rs), make_float2(gg.x, gg.y), make_float2(bb.x, bb.y)));
-            MMF_SET2(v, 4 * u + 2, f2fma(f2mul(f2add(MMF_V2(v, 4 * u + 2), nm), rs), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w)));
-        }
+        for (int i = 0; i < 32; i += 2) MMF_SET2(v, i, f2fma(MMF_V2(v, i), rs, nmrs));
         stage32<PAIR>(e.arena + TfLay<PAIR>::oA, e.r, e.hf * 128 + c0, v);
     }
 }
@@ -412,7 +410,6 @@ __device__ __forceinline__ float softmax_probs(Epi& e, uint32_t scol, float scal
     // all-in or all-out and one per-lane predicate covers the 16 keys.
     asm volatile("" : "+r"(lo), "+r"(span));
     const int hi = lo + static_cast<int>(span);
-    float mx = -INFINITY;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         if (km & (1u << g)) {
@@ -424,14 +421,24 @@ __device__ __forceinline__ float softmax_probs(Epi& e, uint32_t scol, float scal
 #pragma unroll
                 for (int j = 16 * g; j < 16 * g + 16; ++j) s[j] = in ? s[j] : -INFINITY;
             }
-            mx = fmaxf(mx, max_regs<16>(s + 16 * g));
         }
     }
-    float* red = e.misc + mRed + slot * 256;
-    red[e.hf * 128 + e.r] = mx;
-    epi_bar();
-    mx = fmaxf(mx, red[(e.hf ^ 1) * 128 + e.r]);
-    const float msc = (mx == -INFINITY) ? 0.f : mx * scale_log2e;
+    // The row maximum only guards the exponentials against overflow; softmax itself is shift-invariant.  q and k are
+    // per-head LayerNorm outputs, so |q.k| <= (max|g_q| sqrt(HS) + |b_q|)(max|g_k| sqrt(HS) + |b_k|): when the host finds that
+    // bound (in the units of the exponent) small for every block of the checkpoint (e.nomax, CTA-uniform), the maximum, its
+    // exchange between the two halves of a row and the barrier are skipped and the exponent is taken of the raw score.
+    float msc = 0.f;
+    if (!e.nomax) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+            if (km & (1u << g)) mx = fmaxf(mx, max_regs<16>(s + 16 * g));
+        float* red = e.misc + mRed + slot * 256;
+        red[e.hf * 128 + e.r] = mx;
+        epi_bar();
+        mx = fmaxf(mx, red[(e.hf ^ 1) * 128 + e.r]);
+        msc = (mx == -INFINITY) ? 0.f : mx * scale_log2e;
+    }
     float sum = 0.f;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
@@ -865,6 +872,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
         const int att_lo = seg_b - hf * NK;
         const uint32_t att_span = static_cast<uint32_t>(seg_e - seg_b);
         e.kmask = 0; e.kfull = 0; e.kpart = 0;
+        e.nomax = a.softmax_nomax ? 1u : 0u;
 #pragma unroll
         for (int g = 0; g < NK / 16; ++g) {
             const int k0 = hf * NK + 16 * g;
@@ -980,7 +988,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 tmem_st_wait();
                 float mean, rstd;
                 if (pf) ln_stats<false>(e, sum, 0, mean, rstd); else ln_stats<true>(e, sum, 0, mean, rstd);
-                ln_to_abuf<PAIR>(e, mean, rstd, PB + tfp::EB_LNN_G + hf * 128, PB + tfp::EB_LNN_B + hf * 128);
+                ln_to_abuf<PAIR>(e, mean, rstd);
                 go(e);
             }
             param_release(e);
@@ -1008,7 +1016,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                     const RowStat sum = resid_update(e, G + tfp::SA_BPROJ, nullptr, nullptr);
                     float mean, rstd;
                     ln_stats<false>(e, sum, 0, mean, rstd);
-                    ln_to_abuf<PAIR>(e, mean, rstd, G + tfp::SA_LN2G, G + tfp::SA_LN2B);
+                    ln_to_abuf<PAIR>(e, mean, rstd);
                     go(e);
                 }
                 param_release(e);
@@ -1031,7 +1039,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                         const RowStat sum = resid_update(e, G + tfp::SM_BP2, tb1, nullptr);
                         float mean, rstd;
                         ln_stats<false>(e, sum, 0, mean, rstd);
-                        ln_to_abuf<PAIR>(e, mean, rstd, e.P + tfp::SM_LNN_G + hf * 128, e.P + tfp::SM_LNN_B + hf * 128);
+                        ln_to_abuf<PAIR>(e, mean, rstd);
                     } else {
                         // stream junction: x = ln2_x(x + x_skip) | y = ln2_y(y + y_skip); z = cat(x, y) + time_expand(temb)
                         const RowStat sum = resid_update(e, G + tfp::SM_BP2, tb1, skipc);
@@ -1039,7 +1047,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                         ln_stats<false>(e, sum, 0, mean, rstd);
                         const RowStat sum2 = ln_to_resid(e, mean, rstd, e.P + tfp::SM_LNN_G + hf * 128, e.P + tfp::SM_LNN_B + hf * 128, tb2);
                         ln_stats<true>(e, sum2, 1, mean, rstd);
-                        ln_to_abuf<PAIR>(e, mean, rstd, e.P + tfp::SM_LN2ND_G + hf * 128, e.P + tfp::SM_LN2ND_B + hf * 128);
+                        ln_to_abuf<PAIR>(e, mean, rstd);
                     }
                     go(e);
                 }
@@ -1061,7 +1069,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                     const RowStat sum = resid_update(e, e.P + tfp::BA_BPROJ + hf * 128, nullptr, nullptr);
                     float mean, rstd;
                     ln_stats<true>(e, sum, 0, mean, rstd);
-                    ln_to_abuf<PAIR>(e, mean, rstd, e.P + tfp::BA_LN2G + hf * 128, e.P + tfp::BA_LN2B + hf * 128);
+                    ln_to_abuf<PAIR>(e, mean, rstd);
                     go(e);
                 }
                 param_release(e);
@@ -1079,7 +1087,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                     const RowStat sum = resid_update(e, e.P + tfp::BM_BP2 + hf * 128, tb2, last ? skipc : nullptr);
                     float mean, rstd;
                     if (last && pf) ln_stats<false>(e, sum, 0, mean, rstd); else ln_stats<true>(e, sum, 0, mean, rstd);
-                    ln_to_abuf<PAIR>(e, mean, rstd, e.P + tfp::BM_LNN_G + hf * 128, e.P + tfp::BM_LNN_B + hf * 128);
+                    ln_to_abuf<PAIR>(e, mean, rstd);
                     go(e);
                 }
                 param_release(e);

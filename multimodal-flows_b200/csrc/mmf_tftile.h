@@ -142,6 +142,7 @@ struct TfLaunch {
     const float* temb;      // [*][512]: time embedding (256) | time_expand(temb) (256, ParticleFormer)
     int per_jet_time;
     int nsteps;
+    int softmax_nomax;      // 1: the checkpoint's q / k LayerNorm parameters bound every score, the softmax skips the row maximum
     TfStepCfg st;
     float* x_out;           // padded (B,D,3) final state     (sampler)
     long long* k_out;       // padded (B,D) final tokens      (sampler)

@@ -32,6 +32,7 @@ struct TfTileModel {
     cudaStream_t side = nullptr;                         // pair tiles run beside the plain ones (fork / join with events)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int cluster = 2;                                     // CTAs sharing one weight stream (MMF_TILE_CLUSTER = 1 | 2 | 4)
+    int softmax_nomax = 0;                               // every score of the checkpoint is bounded: softmax without the row maximum
     PinnedStage stage;                                   // per-call tables on their way to the device
     ~TfTileModel() {
         stage.release();
@@ -186,10 +187,37 @@ void put(float* dst, const std::vector<float>& src) { std::copy(src.begin(), src
 
 float gelu_h(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-struct BlockW { Mat attn, proj, fc, p2; };
+// The affine part of a LayerNorm that feeds a linear layer moves into that layer (fp re-association only):
+//   W (g * xhat + beta) + b = (W diag(g)) xhat + (b + W beta)
+// so the kernel's normalise pass writes xhat itself (ln_to_abuf).  `bias` (in / out): the layer's bias; g / beta: [W.cols].
+void fold_ln(Mat& W, std::vector<float>& bias, const std::vector<float>& g, const std::vector<float>& beta) {
+    for (int o = 0; o < W.rows; ++o) {
+        float* w = W.w.data() + static_cast<size_t>(o) * W.cols;
+        double acc = 0.0;
+        for (int i = 0; i < W.cols; ++i) { acc += static_cast<double>(w[i]) * beta[i]; w[i] *= g[i]; }
+        bias[o] += static_cast<float>(acc);
+    }
+}
+
+// upper bound of |q . k| * log2(e) / sqrt(hs) for per-head LayerNorm outputs q, k (|xhat|_2 <= sqrt(hs)), bf16 rounding included
+double score_bound(WeightMap& wm, const std::string& p, int hs) {
+    auto side = [&](const std::string& n) {
+        const std::vector<float> g = wm.get(p + ".attn." + n + ".weight", hs), b = wm.get(p + ".attn." + n + ".bias", hs, -1, true);
+        double gm = 0.0, b2 = 0.0;
+        for (int i = 0; i < hs; ++i) { gm = std::max(gm, static_cast<double>(std::fabs(g[i]))); b2 += static_cast<double>(b[i]) * b[i]; }
+        return 1.01 * (gm * std::sqrt(static_cast<double>(hs)) + std::sqrt(b2));
+    };
+    return side("q_layernorm") * side("k_layernorm") * 1.4426950408889634 / std::sqrt(static_cast<double>(hs));
+}
+
+struct BlockW { Mat attn, proj, fc, p2; std::vector<float> b_attn, b_fc; };   // c_attn / c_fc carry ln1 / ln2 (fold_ln)
 BlockW load_block(WeightMap& wm, const std::string& p, int C, int I) {
-    return BlockW{mat(wm, p + ".attn.c_attn.weight", 3 * C, C), mat(wm, p + ".attn.c_proj.weight", C, C),
-                  mat(wm, p + ".ffw.c_fc.weight", I, C), mat(wm, p + ".ffw.c_proj.weight", C, I)};
+    BlockW w{mat(wm, p + ".attn.c_attn.weight", 3 * C, C), mat(wm, p + ".attn.c_proj.weight", C, C),
+             mat(wm, p + ".ffw.c_fc.weight", I, C), mat(wm, p + ".ffw.c_proj.weight", C, I),
+             wm.get(p + ".attn.c_attn.bias", 3 * C, -1, true), wm.get(p + ".ffw.c_fc.bias", I, -1, true)};
+    fold_ln(w.attn, w.b_attn, wm.get(p + ".ln1.weight", C), wm.get(p + ".ln1.bias", C, -1, true));
+    fold_ln(w.fc, w.b_fc, wm.get(p + ".ln2.weight", C), wm.get(p + ".ln2.bias", C, -1, true));
+    return w;
 }
 
 // MLP of one group.  The up-projection runs as two N = 256 halves over the whole scratch (one MMA instruction per K = 16
@@ -214,7 +242,7 @@ void emit_mlp(Builder& b, const LayH& L, const BlockW& w, int C, int a_chunk0, u
 // The per-timestep program of one tile kind: MMA ops, weight stream (consumption order) and parameter blobs.  Both kinds
 // consume the SAME weight tiles in the SAME order (the pair program differs only in operand addresses, scratch columns and
 // the attention products), so the stream, ring plan and blobs of the plain program serve both.
-static int emit_program(const MmfModelDesc& d, WeightMap& wm, const LayH& L, Builder& b, int* n_blobs) {
+static int emit_program(const MmfModelDesc& d, WeightMap& wm, const LayH& L, Builder& b, int* n_blobs, double* score_max) {
     const bool pf = d.arch == MMF_ARCH_PARTICLEFORMER;
     const int E = d.n_embd, h = E / 2, I = d.n_inner, V = d.vocab_size;
     const std::string t = "transformer.";
@@ -264,12 +292,13 @@ static int emit_program(const MmfModelDesc& d, WeightMap& wm, const LayH& L, Bui
     for (int i = 0; i < n_stream; ++i) {
         const std::string px[2] = {t + "blocks_x." + std::to_string(i), t + "blocks_y." + std::to_string(i)};
         BlockW w[2] = {load_block(wm, px[0], h, I), load_block(wm, px[1], h, I)};
+        *score_max = std::max(*score_max, std::max(score_bound(wm, px[0], 32), score_bound(wm, px[1], 32)));
         const bool last = i + 1 == n_stream;
         {
             float* P = b.blob(blob_idx);                 // attention stage (prefetched by the previous stage)
             for (int g = 0; g < 2; ++g) {
                 float* G = P + g * tfp::SA_GROUP;
-                put(G + tfp::SA_BQKV, wm.get(px[g] + ".attn.c_attn.bias", 3 * h, -1, true));
+                put(G + tfp::SA_BQKV, w[g].b_attn);
                 put(G + tfp::SA_QG, wm.get(px[g] + ".attn.q_layernorm.weight", 32)); put(G + tfp::SA_QB, wm.get(px[g] + ".attn.q_layernorm.bias", 32, -1, true));
                 put(G + tfp::SA_KG, wm.get(px[g] + ".attn.k_layernorm.weight", 32)); put(G + tfp::SA_KB, wm.get(px[g] + ".attn.k_layernorm.bias", 32, -1, true));
                 put(G + tfp::SA_BPROJ, wm.get(px[g] + ".attn.c_proj.bias", h, -1, true));
@@ -278,7 +307,7 @@ static int emit_program(const MmfModelDesc& d, WeightMap& wm, const LayH& L, Bui
             P = b.blob(blob_idx + 1);                    // MLP stage
             for (int g = 0; g < 2; ++g) {
                 float* G = P + g * tfp::SM_GROUP;
-                put(G + tfp::SM_BFC, wm.get(px[g] + ".ffw.c_fc.bias", I, -1, true));
+                put(G + tfp::SM_BFC, w[g].b_fc);
                 put(G + tfp::SM_BP2, wm.get(px[g] + ".ffw.c_proj.bias", h, -1, true));
             }
             const std::string nx = last ? t + "ln2_x" : t + "blocks_x." + std::to_string(i + 1) + ".ln1";
@@ -334,16 +363,17 @@ static int emit_program(const MmfModelDesc& d, WeightMap& wm, const LayH& L, Bui
     for (int j = 0; j < n_main; ++j) {
         const std::string p = t + (pf ? "blocks_fuse." : "blocks.") + std::to_string(j);
         const BlockW w = load_block(wm, p, E, I);
+        *score_max = std::max(*score_max, score_bound(wm, p, 64));
         const bool last = j + 1 == n_main;
         {
             float* P = b.blob(blob_idx);                 // attention stage
-            put(P + tfp::BA_BQKV, wm.get(p + ".attn.c_attn.bias", 3 * E, -1, true));
+            put(P + tfp::BA_BQKV, w.b_attn);
             put(P + tfp::BA_QG, wm.get(p + ".attn.q_layernorm.weight", 64)); put(P + tfp::BA_QB, wm.get(p + ".attn.q_layernorm.bias", 64, -1, true));
             put(P + tfp::BA_KG, wm.get(p + ".attn.k_layernorm.weight", 64)); put(P + tfp::BA_KB, wm.get(p + ".attn.k_layernorm.bias", 64, -1, true));
             put(P + tfp::BA_BPROJ, wm.get(p + ".attn.c_proj.bias", E, -1, true));
             put(P + tfp::BA_LN2G, wm.get(p + ".ln2.weight", E)); put(P + tfp::BA_LN2B, wm.get(p + ".ln2.bias", E, -1, true));
             P = b.blob(blob_idx + 1);                    // MLP stage
-            put(P + tfp::BM_BFC, wm.get(p + ".ffw.c_fc.bias", I, -1, true));
+            put(P + tfp::BM_BFC, w.b_fc);
             put(P + tfp::BM_BP2, wm.get(p + ".ffw.c_proj.bias", E, -1, true));
             if (!last) {
                 const std::string nx = t + (pf ? "blocks_fuse." : "blocks.") + std::to_string(j + 1) + ".ln1";
@@ -386,9 +416,22 @@ static int emit_program(const MmfModelDesc& d, WeightMap& wm, const LayH& L, Bui
 
     // ---------------- heads: Linear(128,512) + GELU on tensor cores, Linear(512, 3 | V) on CUDA cores
     {
-        const Mat hx = mat(wm, t + "head_x.0.weight", I, h), hy = mat(wm, t + "head_y.0.weight", I, h);
-        const std::vector<float> bx0 = wm.get(t + "head_x.0.bias", I), by0 = wm.get(t + "head_y.0.bias", I),
-                                 wx2 = wm.get(t + "head_x.2.weight", 3, I), bx2 = wm.get(t + "head_x.2.bias", 3),
+        Mat hx = mat(wm, t + "head_x.0.weight", I, h), hy = mat(wm, t + "head_y.0.weight", I, h);
+        std::vector<float> bx0 = wm.get(t + "head_x.0.bias", I), by0 = wm.get(t + "head_y.0.bias", I);
+        {   // the last LayerNorm (ParticleFormer ln3_x | ln3_y, fused encoder ln2 = columns [0,128) | [128,256)) folds into the heads
+            std::vector<float> gx, bx, gy, by;
+            if (pf) {
+                gx = wm.get(t + "ln3_x.weight", h); bx = wm.get(t + "ln3_x.bias", h, -1, true);
+                gy = wm.get(t + "ln3_y.weight", h); by = wm.get(t + "ln3_y.bias", h, -1, true);
+            } else {
+                const std::vector<float> g2 = wm.get(t + "ln2.weight", E), b2 = wm.get(t + "ln2.bias", E, -1, true);
+                gx.assign(g2.begin(), g2.begin() + h); bx.assign(b2.begin(), b2.begin() + h);
+                gy.assign(g2.begin() + h, g2.end()); by.assign(b2.begin() + h, b2.end());
+            }
+            fold_ln(hx, bx0, gx, bx);
+            fold_ln(hy, by0, gy, by);
+        }
+        const std::vector<float> wx2 = wm.get(t + "head_x.2.weight", 3, I), bx2 = wm.get(t + "head_x.2.bias", 3),
                                  wy2 = wm.get(t + "head_y.2.weight", V, I), by2 = wm.get(t + "head_y.2.bias", V);
         float* P = b.blob(blob_idx);
         put(P + tfp::HX_BIAS, bx0); put(P + tfp::HX_W2, wx2); put(P + tfp::HX_B2, bx2);
@@ -422,8 +465,14 @@ int tftile_create(const MmfModelDesc& d, WeightMap& wm, TfTileModel** out) {
     m->desc = d;
     Builder b, bp;
     int blob_idx = 0, blob_idx_pair = 0;
-    MMF_TRY_RC(emit_program(d, wm, make_lay<false>(), b, &blob_idx));
-    MMF_TRY_RC(emit_program(d, wm, make_lay<true>(), bp, &blob_idx_pair));
+    double score_max = 0.0;
+    MMF_TRY_RC(emit_program(d, wm, make_lay<false>(), b, &blob_idx, &score_max));
+    MMF_TRY_RC(emit_program(d, wm, make_lay<true>(), bp, &blob_idx_pair, &score_max));
+    // |score| log2(e) / sqrt(hs) <= 64 for every block: 2^(+-64) and sums of 160 such terms are far inside fp32 / bf16 range, so
+    // the softmax needs no row maximum (kernels_tftile.cu softmax_probs).  MMF_TILE_SOFTMAX_MAX=1 keeps the maximum (tests).
+    const char* force_max = getenv("MMF_TILE_SOFTMAX_MAX");
+    m->softmax_nomax = (score_max <= 64.0 && !(force_max && force_max[0] == '1')) ? 1 : 0;
+    if (getenv("MMF_TILE_DEBUG")) fprintf(stderr, "tile kernel: score bound %.2f (log2 units), softmax %s the row maximum\n", score_max, m->softmax_nomax ? "without" : "with");
     MMF_REQUIRE(bp.tiles.size() == b.tiles.size() && bp.stream == b.stream && blob_idx_pair == blob_idx,
                 "tile kernel: the pair program must consume the weight stream of the plain program");
     if (pf) {
@@ -622,7 +671,7 @@ int tftile_prepare(TfTileModel* m, const TfRunArgs& r, std::vector<unsigned char
     a.arch = d.arch; a.n_stream = pf ? d.n_layer : 0; a.n_main = pf ? d.n_layer_fused : d.n_layer; a.vocab = d.vocab_size;
     a.optab = m->optab.get(); a.prodtab = m->prodtab.get(); a.n_ops = m->n_ops; a.n_prod = m->n_prod; a.n_blobs = m->n_blobs; a.wstream = m->d_wstream; a.params = m->d_params; a.meta = m->d_meta; a.tile0 = 0;
     a.xs0 = m->d_xs0; a.ks0 = m->d_ks0; a.row_slot = m->d_row_slot; a.skip = m->d_skip; a.temb = m->d_temb;
-    a.per_jet_time = r.per_jet_time ? 1 : 0; a.nsteps = r.nsteps;
+    a.per_jet_time = r.per_jet_time ? 1 : 0; a.nsteps = r.nsteps; a.softmax_nomax = m->softmax_nomax;
     if (r.opts) {
         a.st.sp = StepParams{r.opts->temperature, r.dt, r.opts->beta, r.opts->top_p, r.opts->top_k, d.vocab_size};
         a.st.seed = r.opts->seed;
