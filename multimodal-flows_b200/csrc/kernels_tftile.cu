@@ -15,7 +15,12 @@
 #ifndef MMF_TILE_TRACE
 #define MMF_TILE_TRACE 0
 #endif
-#define MMF_WAIT_DIAG MMF_TILE_TRACE
+// -DMMF_PROD_DIAG=1 (MMF_EXTRA_NVCC of build.py): the PRODUCTION kernel with the time-out records of mbar_wait; the process
+// prints them when it exits (debugging aid for a launch that trapped: which warp waited for which barrier).
+#ifndef MMF_PROD_DIAG
+#define MMF_PROD_DIAG 0
+#endif
+#define MMF_WAIT_DIAG (MMF_TILE_TRACE || MMF_PROD_DIAG)
 #include "mmf_ptx.cuh"
 #include "mmf_tftile.h"
 #include "mmf_tile.cuh"
@@ -40,7 +45,7 @@ constexpr int kCopySplit = MMF_COPY_SPLIT;   // bulk copies per weight-tile slic
 // while the attention issuer keeps the epilogue going), so one barrier could complete two phases unobserved.
 constexpr int kGoBars = 4;
 struct TfBars {
-    uint64_t full[kBars], empty[kBars], done[4], go[kGoBars], go_attn, pfull[2], pempty[2];
+    uint64_t full[kBars], empty[kBars], done[4], go[kGoBars], go_attn[kGoBars], pfull[2], pempty[2];
     // pair tiles: kfull / vfull - the partner's K / V rows of a unit have landed in this CTA (one expect_tx arrival + the
     // bytes of one bulk copy each, issued by the partner's attention issuer); kfree / vfree - the partner's MMAs have read ITS
     // K / V buffers for the last time in the unit (tcgen05.commit multicast to this CTA): the next unit's rows may go there,
@@ -70,6 +75,7 @@ struct Epi {
     int r, hf, tid;
     uint32_t pd0, pd1, pd2, pd3, pc;
     uint32_t gc;             // hand-offs to the weight-GEMM issuer so far (barrier gc % kGoBars, parity (gc / kGoBars) & 1)
+    uint32_t ac;             // hand-offs to the attention issuer so far (same rotation over go_attn[])
     uint32_t kmask, kfull, kpart;   // 16-key groups of this thread's key half: attended by any row of the warp / in full by
                                     // every row / cut by a jet boundary of some row
     uint32_t kc, vc;                // pair tiles: K / V rows of how many units staged so far
@@ -114,7 +120,12 @@ __device__ __forceinline__ void go_attn(Epi& e, bool also_gemm = false) {
     mark(e);
     fence_proxy_async();
     tc_fence_before();
-    mbar_arrive(&e.bars->go_attn);
+    // Rotating barriers, as for `go`: the pair-tile program hands the attention issuer two ops in a row without an MMA result
+    // in between (the K rows of a unit, then its V rows + score product; P V, then the next unit's K rows).  With ONE barrier
+    // an issuer warp that woke up late - cold instruction cache in the first launches of a process - found it two phases on
+    // and waited for ever: an intermittent dead-lock of the pair tiles in 5 ... 15 % of fresh processes (tools/tile_stress.py).
+    mbar_arrive(&e.bars->go_attn[e.ac % kGoBars]);
+    ++e.ac;
     if (also_gemm) { mbar_arrive(&e.bars->go[e.gc % kGoBars]); ++e.gc; }
 }
 // blob `ahead` stages past the oldest one still held (0 or 1: two slots)
@@ -307,12 +318,12 @@ __device__ __forceinline__ void ln_regs(float* v, const float* g, const float* b
     const float q = sqdev_regs<N>(v, mean);
     const float rstd = rsqrtf(q * (1.0f / N) + 1e-5f);
 #pragma unroll
-    const float2 nm = f2dup(-mean), rs = f2dup(rstd);
+    const float2 rs = f2dup(rstd), nmrs = f2dup(-mean * rstd);
 #pragma unroll
     for (int i = 0; i < N; i += 4) {
         const float4 gg = ldf4(g + i), bb = ldf4(b + i);
-        MMF_SET2(v, i, f2fma(f2mul(f2add(MMF_V2(v, i), nm), rs), make_float2(gg.x, gg.y), make_float2(bb.x, bb.y)));
-        MMF_SET2(v, i + 2, f2fma(f2mul(f2add(MMF_V2(v, i + 2), nm), rs), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w)));
+        MMF_SET2(v, i, f2fma(f2fma(MMF_V2(v, i), rs, nmrs), make_float2(gg.x, gg.y), make_float2(bb.x, bb.y)));
+        MMF_SET2(v, i + 2, f2fma(f2fma(MMF_V2(v, i + 2), rs, nmrs), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w)));
     }
 }
 
@@ -355,7 +366,7 @@ __device__ __forceinline__ void qk_epilogue(Epi& e, const float* bq, const float
 // v: bias, bf16 -> V[key = r][d] (row r of a [keys][128 B] swizzled chunk: the MN-major B operand of P V, so no transpose);
 // runs under the score MMA (plain tiles) / before it (pair tiles: the 160 score columns cover the v accumulator)
 template <int HS, bool PAIR>
-__device__ __forceinline__ void v_epilogue(Epi& e, const float* bv, float* prew = nullptr) {
+__device__ __forceinline__ void v_epilogue(Epi& e, float* prew = nullptr) {
     using L = TfLay<PAIR>;
     float wloc[32];
     float* w = prew ? prew : wloc;
@@ -363,12 +374,8 @@ __device__ __forceinline__ void v_epilogue(Epi& e, const float* bv, float* prew 
         tmem_ld32(e.taddr + QkvCols<HS, PAIR>::cV + e.hf * 32, w);
         tmem_ld_wait();
     }
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-        const float4 b = ldf4(bv + e.hf * 32 + i);
-        MMF_SET2(w, i, f2add(MMF_V2(w, i), make_float2(b.x, b.y)));
-        MMF_SET2(w, i + 2, f2add(MMF_V2(w, i + 2), make_float2(b.z, b.w)));
-    }
+    // (no bias: the probabilities of a row sum to one, so P (V + b_v) = P V + b_v and b_v travels through the projection
+    // into its bias on the host - tftile_model.cu fold_v_bias)
     if (!row_ok<PAIR>(e.r)) return;
     uint8_t* vb = e.arena + L::oVT;
 #pragma unroll
@@ -389,7 +396,7 @@ __device__ __forceinline__ void v_epilogue(Epi& e, const float* bv, float* prew 
 // it reads only Abuf and the ring, no shared memory written by this epilogue, hence no proxy fence).
 // Key j of this thread is valid iff (unsigned)(j - lo) < span (plain: the row's jet; pair: the real rows of that CTA).
 template <int NK>
-__device__ __forceinline__ float softmax_probs(Epi& e, uint32_t scol, float scale_log2e, int lo, uint32_t span, int slot, float* s,
+__device__ __forceinline__ float softmax_probs(Epi& e, uint32_t scol, int lo, uint32_t span, int slot, float* s,
                                                bool release_gemm = false) {
     constexpr int NG = NK / 16;
     const uint32_t km = e.kmask;
@@ -437,16 +444,23 @@ __device__ __forceinline__ float softmax_probs(Epi& e, uint32_t scol, float scal
         red[e.hf * 128 + e.r] = mx;
         epi_bar();
         mx = fmaxf(mx, red[(e.hf ^ 1) * 128 + e.r]);
-        msc = (mx == -INFINITY) ? 0.f : mx * scale_log2e;
+        msc = (mx == -INFINITY) ? 0.f : mx;
     }
+    // The scores arrive in the units of the exponent: log2(e) / sqrt(HS) is folded into the affine part of the q LayerNorm on
+    // the host (tftile_model.cu), so without the maximum the exponential is taken of the accumulator as it is.
     float sum = 0.f;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
         if (km & (1u << g)) {
+            if (e.nomax) {
 #pragma unroll
-            for (int j = 16 * g; j < 16 * g + 16; j += 2) {
-                const float2 a = f2fma(MMF_V2(s, j), f2dup(scale_log2e), f2dup(-msc));
-                s[j] = ex2_approx(a.x); s[j + 1] = ex2_approx(a.y);
+                for (int j = 16 * g; j < 16 * g + 16; ++j) s[j] = ex2_approx(s[j]);
+            } else {
+#pragma unroll
+                for (int j = 16 * g; j < 16 * g + 16; j += 2) {
+                    const float2 a = f2add(MMF_V2(s, j), f2dup(-msc));
+                    s[j] = ex2_approx(a.x); s[j + 1] = ex2_approx(a.y);
+                }
             }
             sum += sum_regs<16>(s + 16 * g);
         } else {
@@ -473,9 +487,9 @@ __device__ __forceinline__ void softmax_store(Epi& e, int slot, const float* s, 
     e.misc[mSum + slot * 256 + e.hf * 128 + e.r] = sum;
 }
 template <bool PAIR>
-__device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, float scale_log2e, int lo, uint32_t span, int slot, bool release_gemm = false) {
+__device__ __forceinline__ void softmax_epilogue(Epi& e, uint32_t scol, int lo, uint32_t span, int slot, bool release_gemm = false) {
     float s[PAIR ? 80 : 64];
-    const float sum = softmax_probs<PAIR ? 80 : 64>(e, scol, scale_log2e, lo, span, slot, s, release_gemm);
+    const float sum = softmax_probs<PAIR ? 80 : 64>(e, scol, lo, span, slot, s, release_gemm);
     softmax_store<PAIR>(e, slot, s, sum);
 }
 
@@ -501,7 +515,8 @@ __device__ __forceinline__ void o_epilogue(Epi& e, uint32_t ocol, int ucol, int 
                      pack_bf16x2(o[8 * u + 4], o[8 * u + 5]), pack_bf16x2(o[8 * u + 6], o[8 * u + 7]));
 }
 
-// MLP hidden quarter q in scratch half (q&1): GELU(acc + bias) -> bf16 H(q&1); `bias` points at the quarter's 128 values
+// MLP hidden quarter q in scratch half (q&1): 2 GELU(acc + bias) -> bf16 H(q&1) (the down-projection weights carry the 0.5,
+// tftile_model.cu); `bias` points at the quarter's 128 values
 template <bool PAIR>
 __device__ __forceinline__ void fc_epilogue(Epi& e, int q, const float* bias) {
     using L = TfLay<PAIR>;
@@ -514,8 +529,8 @@ __device__ __forceinline__ void fc_epilogue(Epi& e, int q, const float* bias) {
 #pragma unroll
     for (int i = 0; i < 64; i += 4) {
         const float4 a = ldf4(bias + e.hf * 64 + i);
-        MMF_SET2(v, i, gelu_tile2(f2add(MMF_V2(v, i), make_float2(a.x, a.y))));
-        MMF_SET2(v, i + 2, gelu_tile2(f2add(MMF_V2(v, i + 2), make_float2(a.z, a.w))));
+        MMF_SET2(v, i, gelu2x_tile2(f2add(MMF_V2(v, i), make_float2(a.x, a.y))));
+        MMF_SET2(v, i + 2, gelu2x_tile2(f2add(MMF_V2(v, i + 2), make_float2(a.z, a.w))));
     }
     stage_row_bf16(e.arena + ((q & 1) ? L::oH1 : L::oH0) + e.hf * L::kChunk, e.r, v);
 }
@@ -531,8 +546,8 @@ __device__ __forceinline__ void head_epilogue(Epi& e, int q, const float* bias, 
 #pragma unroll
     for (int i = 0; i < 64; i += 4) {
         const float4 a = ldf4(bias + e.hf * 64 + i);
-        MMF_SET2(v, i, gelu_tile2(f2add(MMF_V2(v, i), make_float2(a.x, a.y))));
-        MMF_SET2(v, i + 2, gelu_tile2(f2add(MMF_V2(v, i + 2), make_float2(a.z, a.w))));
+        MMF_SET2(v, i, gelu2x_tile2(f2add(MMF_V2(v, i), make_float2(a.x, a.y))));
+        MMF_SET2(v, i + 2, gelu2x_tile2(f2add(MMF_V2(v, i + 2), make_float2(a.z, a.w))));
     }
 #pragma unroll
     for (int o = 0; o < NO; ++o) {
@@ -571,7 +586,6 @@ __device__ __forceinline__ void attention_unit(Epi& e, bool first, bool more, co
                                                const float* nbq = nullptr, const float* nbk = nullptr, const float* nqg = nullptr,
                                                const float* nqb = nullptr, const float* nkg = nullptr, const float* nkb = nullptr) {
     using L = TfLay<PAIR>;
-    const float scale = 1.4426950408889634f * rsqrtf(static_cast<float>(HS));
     if (!PAIR) wait_done(e, 1);                       // QKV of this unit (issued under the previous unit's epilogue)
     if (!PAIR) {
         // 32-wide units: the score product of head 0 writes [256,384), over the v accumulator [320,384): v must be in
@@ -579,10 +593,10 @@ __device__ __forceinline__ void attention_unit(Epi& e, bool first, bool more, co
         float vr[32];
         qk_epilogue<HS, false>(e, bq, bk, qg, qb, kg, kb, HS == 32 ? vr : nullptr);
         go_attn(e);                                       // -> S
-        v_epilogue<HS, false>(e, bv, HS == 32 ? vr : nullptr);   // under the score MMA; P V is only issued after the next hand-off
+        v_epilogue<HS, false>(e, HS == 32 ? vr : nullptr);   // under the score MMA; P V is only issued after the next hand-off
         if (HS == 64) {
             wait_done(e, 0);
-            softmax_epilogue<false>(e, kScr, scale, lo, span, 0, more);   // (S in registers -> the QKV GEMM of the next unit)
+            softmax_epilogue<false>(e, kScr, lo, span, 0, more);   // (S in registers -> the QKV GEMM of the next unit)
             go_attn(e);                                       // -> P V
             wait_done(e, 0);
             if (!first) wait_done(e, 2);                      // the previous unit's projection (other issuer warp) has read oO
@@ -590,10 +604,10 @@ __device__ __forceinline__ void attention_unit(Epi& e, bool first, bool more, co
             go(e);                                            // -> projection
         } else {
             wait_done(e, 0);                                  // both heads' scores: [256,384) and [384,512)
-            softmax_epilogue<false>(e, kScr, scale, lo, span, 0);
+            softmax_epilogue<false>(e, kScr, lo, span, 0);
             go_attn(e);                                       // -> P V of head 0
             float s[64];                                      // head 1's probabilities are computed under that product ...
-            const float sum = softmax_probs<64>(e, kScr + 128, scale, lo, span, 1, s, more);   // (both S in registers -> next QKV GEMM)
+            const float sum = softmax_probs<64>(e, kScr + 128, lo, span, 1, s, more);   // (both S in registers -> next QKV GEMM)
             wait_done(e, 3);                                  // ... and stored once it has finished reading head 0's
             softmax_store<false>(e, 1, s, sum);
             go_attn(e);                                       // -> P V of head 1
@@ -610,12 +624,12 @@ __device__ __forceinline__ void attention_unit(Epi& e, bool first, bool more, co
         if (first) pair_stage_k<HS>(e, bq, bk, qg, qb, kg, kb);
         if (e.vc > 0) { mark(e, 1); mbar_wait_cluster(&e.bars->vfree, (e.vc - 1) & 1); mark(e, 6); }   // (as kfree, for the V rows)
         ++e.vc;
-        v_epilogue<HS, true>(e, bv);                      // (before S: its 160 columns cover the v accumulator)
+        v_epilogue<HS, true>(e);                      // (before S: its 160 columns cover the v accumulator)
         go_attn(e);                                       // -> V rows to the partner, then S once the partner's K rows are here
         constexpr uint32_t cS = L::cS;
         if (HS == 64) {
             wait_done(e, 0);
-            softmax_epilogue<true>(e, cS, scale, lo, span, 0, more);
+            softmax_epilogue<true>(e, cS, lo, span, 0, more);
             go_attn(e);                                       // -> P V (O in scratch [0,64))
             if (more) pair_stage_k<HS>(e, nbq, nbk, nqg, nqb, nkg, nkb);   // next unit's q / k under this unit's P V
             wait_done(e, 0);
@@ -626,12 +640,12 @@ __device__ __forceinline__ void attention_unit(Epi& e, bool first, bool more, co
             // the two heads take turns on the score columns: S0, softmax 0, then S1 under the P store of head 0
             wait_done(e, 0);                                  // S of head 0
             float s[80];
-            float sum = softmax_probs<80>(e, cS, scale, lo, span, 0, s);
+            float sum = softmax_probs<80>(e, cS, lo, span, 0, s);
             go_attn(e);                                       // S0 in registers -> S of head 1 may overwrite its columns
             softmax_store<true>(e, 0, s, sum);                // (P is free: the previous unit's P V products were waited for)
             go_attn(e);                                       // -> P V of head 0 (done[3])
             wait_done(e, 0);                                  // S of head 1
-            sum = softmax_probs<80>(e, cS, scale, lo, span, 1, s, more);   // (all scores in registers -> next QKV GEMM)
+            sum = softmax_probs<80>(e, cS, lo, span, 1, s, more);   // (all scores in registers -> next QKV GEMM)
             wait_done(e, 3);                                  // P V of head 0 has read P
             softmax_store<true>(e, 1, s, sum);
             go_attn(e);                                       // -> P V of head 1
@@ -673,7 +687,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
         mbar_init(&bars->done[2], 1);
         mbar_init(&bars->done[3], 1);
         for (int i = 0; i < kGoBars; ++i) mbar_init(&bars->go[i], kEpi);
-        mbar_init(&bars->go_attn, kEpi);
+        for (int i = 0; i < kGoBars; ++i) mbar_init(&bars->go_attn[i], kEpi);
         for (int i = 0; i < 2; ++i) { mbar_init(&bars->pfull[i], 1); mbar_init(&bars->pempty[i], kEpi); }
         mbar_init(&bars->kfull, 1);                       // pair tiles (see TfBars)
         mbar_init(&bars->vfull, 1);
@@ -761,7 +775,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 const uint32_t fl = op.flags;
                 if (((fl & kTfOpAttn) != 0) != attn_issuer) continue;       // the other issuer's op (attention ops never touch the ring)
                 if (fl & kTfOpWait) {
-                    if (attn_issuer) mbar_wait(&bars->go_attn, pg & 1, static_cast<uint32_t>(i));
+                    if (attn_issuer) mbar_wait(&bars->go_attn[pg % kGoBars], (pg / kGoBars) & 1, static_cast<uint32_t>(i));
                     else mbar_wait(&bars->go[pg % kGoBars], (pg / kGoBars) & 1, static_cast<uint32_t>(i));
                     ++pg;
                 }
@@ -854,7 +868,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
         e.arena = arena; e.pbuf = pbuf; e.misc = misc; e.bars = bars; e.P = pbuf;
         e.r = (warp & 3) * 32 + lane; e.hf = warp >> 2; e.tid = tid;
         e.taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-        e.pd0 = 0; e.pd1 = 0; e.pd2 = 0; e.pd3 = 0; e.pc = 0; e.gc = 0;
+        e.pd0 = 0; e.pd1 = 0; e.pd2 = 0; e.pd3 = 0; e.pc = 0; e.gc = 0; e.ac = 0;
         const int r = e.r, hf = e.hf;
         const int nrows = meta->nrows;
         float* s_xs = misc + mXs;
@@ -1208,7 +1222,30 @@ int launch_tf_tiles_trace(const TfLaunch& a, int n_tiles, int cluster, bool pair
 #else
 int tf_tile_smem_bytes() { return smem_bytes<false>(); }
 
+#if MMF_PROD_DIAG
+static unsigned long long* g_diag_host = nullptr;
+static void diag_dump() {
+    if (!g_diag_host || !g_diag_host[0]) return;
+    const unsigned n = static_cast<unsigned>(g_diag_host[0]);
+    fprintf(stderr, "tile kernel (production build): %u timed-out barrier waits\n", n);
+    for (unsigned i = 0; i < n && i < 62; ++i) {
+        const unsigned long long v = g_diag_host[1 + i];
+        fprintf(stderr, "  cta %llu barrier smem+0x%llx parity %llu warp %llu lane0 tag %llu\n", (v >> 12) & 0xffff, (v >> 32) & 0xffff, (v >> 28) & 1, (v & 0xfff) >> 5, v >> 48);
+    }
+}
+#endif
+
 int launch_tf_tiles(const TfLaunch& a, int n_tiles, int cluster, bool pair, cudaStream_t stream) {
+#if MMF_PROD_DIAG
+    if (!g_diag_host) {
+        unsigned long long* dptr = nullptr;
+        MMF_CUDA_OK(cudaHostAlloc(&g_diag_host, 64 * 8, cudaHostAllocMapped));
+        memset(g_diag_host, 0, 64 * 8);
+        MMF_CUDA_OK(cudaHostGetDevicePointer(&dptr, g_diag_host, 0));
+        MMF_CUDA_OK(cudaMemcpyToSymbol(mmf_dbg_sink, &dptr, sizeof(dptr)));
+        atexit(diag_dump);
+    }
+#endif
 #endif
     if (n_tiles == 0) return 0;
     MMF_REQUIRE(a.vocab == 9, "the tile kernel is instantiated for vocab_size 9");

@@ -184,12 +184,28 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
         : "memory");
     return ok != 0;
 }
+// Bounded like mbar_wait, by the SM's own cycle counter (~4 s at 2 GHz).  NOT by %globaltimer: that clock is re-based by
+// the driver (it tracks host time), and in the first launches of a fresh process a wait that straddled such a step read
+// "more than 4 s" and trapped a healthy kernel - an intermittent "unspecified launch failure" of the pair tiles (the only
+// users of this wait) in 5 ... 15 % of fresh processes, found with tools/tile_stress.py.
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait_cluster(bar, parity)) return;
-    const uint64_t t0 = globaltimer_ns();
+    const long long c0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try_wait_cluster(bar, parity)) {
-        if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 4000000000ull) __trap();
+        if ((++spins & 0x3ff) == 0 && clock64() - c0 > 8000000000ll) {
+#if MMF_WAIT_DIAG
+            if (mmf_dbg_sink && (threadIdx.x & 31) == 0) {      // tag 0x7777: a cluster-scope wait
+                const unsigned int slot = atomicAdd(reinterpret_cast<unsigned int*>(mmf_dbg_sink), 1u);
+                if (slot < 62) {
+                    mmf_dbg_sink[1 + slot] = (0x7777ull << 48) | (static_cast<unsigned long long>(smem_u32(bar) & 0xffffu) << 32) |
+                                             (static_cast<unsigned long long>(parity) << 28) | (static_cast<unsigned long long>(blockIdx.x) << 12) | threadIdx.x;
+                    __threadfence_system();
+                }
+            }
+#endif
+            __trap();
+        }
     }
 }
 

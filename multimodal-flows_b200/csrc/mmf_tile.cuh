@@ -61,6 +61,20 @@ __device__ __forceinline__ float2 gelu_tile2(float2 x) { return make_float2(gelu
 #else
 __device__ __forceinline__ float2 gelu_tile2(float2 x) { return gelu_tanh2(x); }
 #endif
+// 2 GELU(x) = x + x tanh(..): four packed instructions + two MUFU.TANH.  For activations whose consumer is a linear layer: the
+// factor 0.5 moves into that layer's weights on the host, exactly (a power of two).
+__device__ __forceinline__ float2 gelu2x_tanh2(float2 x) {
+    const float2 u = f2mul(x, f2fma(f2mul(x, x), f2dup(0.0356774081f), f2dup(0.7978845608f)));
+    float2 t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+    return f2fma(x, t, x);
+}
+#ifdef MMF_TILE_GELU_EXACT
+__device__ __forceinline__ float2 gelu2x_tile2(float2 x) { return make_float2(2.0f * gelu_erf(x.x), 2.0f * gelu_erf(x.y)); }
+#else
+__device__ __forceinline__ float2 gelu2x_tile2(float2 x) { return gelu2x_tanh2(x); }
+#endif
 #ifdef MMF_TILE_GELU_EXACT
 __device__ __forceinline__ float gelu_tile(float x) { return gelu_erf(x); }
 #else

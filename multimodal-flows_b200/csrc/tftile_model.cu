@@ -210,13 +210,27 @@ double score_bound(WeightMap& wm, const std::string& p, int hs) {
     return side("q_layernorm") * side("k_layernorm") * 1.4426950408889634 / std::sqrt(static_cast<double>(hs));
 }
 
-struct BlockW { Mat attn, proj, fc, p2; std::vector<float> b_attn, b_fc; };   // c_attn / c_fc carry ln1 / ln2 (fold_ln)
-BlockW load_block(WeightMap& wm, const std::string& p, int C, int I) {
+// c_attn / c_fc carry ln1 / ln2 (fold_ln); the v bias travels through the attention (the probabilities of a row sum to one:
+// P (V + b_v) = P V + b_v) and the projection into the projection bias: b_proj' = b_proj + W_proj b_v.  The kernel adds no v bias.
+// q_g / q_b: the affine part of the q LayerNorm times log2(e) / sqrt(hs) - the scores leave the tensor core in the units of
+// the softmax exponent.
+struct BlockW { Mat attn, proj, fc, p2; std::vector<float> b_attn, b_fc, b_proj, q_g, q_b; };
+BlockW load_block(WeightMap& wm, const std::string& p, int C, int I, int hs) {
     BlockW w{mat(wm, p + ".attn.c_attn.weight", 3 * C, C), mat(wm, p + ".attn.c_proj.weight", C, C),
              mat(wm, p + ".ffw.c_fc.weight", I, C), mat(wm, p + ".ffw.c_proj.weight", C, I),
-             wm.get(p + ".attn.c_attn.bias", 3 * C, -1, true), wm.get(p + ".ffw.c_fc.bias", I, -1, true)};
+             wm.get(p + ".attn.c_attn.bias", 3 * C, -1, true), wm.get(p + ".ffw.c_fc.bias", I, -1, true),
+             wm.get(p + ".attn.c_proj.bias", C, -1, true), wm.get(p + ".attn.q_layernorm.weight", hs),
+             wm.get(p + ".attn.q_layernorm.bias", hs, -1, true)};
     fold_ln(w.attn, w.b_attn, wm.get(p + ".ln1.weight", C), wm.get(p + ".ln1.bias", C, -1, true));
     fold_ln(w.fc, w.b_fc, wm.get(p + ".ln2.weight", C), wm.get(p + ".ln2.bias", C, -1, true));
+    for (int o = 0; o < C; ++o) {
+        double acc = 0.0;
+        for (int i = 0; i < C; ++i) acc += static_cast<double>(w.proj.row(o)[i]) * w.b_attn[2 * C + i];
+        w.b_proj[o] += static_cast<float>(acc);
+    }
+    const float c = static_cast<float>(1.4426950408889634 / std::sqrt(static_cast<double>(hs)));
+    for (int i = 0; i < hs; ++i) { w.q_g[i] *= c; w.q_b[i] *= c; }
+    for (float& x : w.p2.w) x *= 0.5f;                 // the kernel's MLP epilogue produces 2 GELU (one multiply less per pair)
     return w;
 }
 
@@ -291,7 +305,7 @@ static int emit_program(const MmfModelDesc& d, WeightMap& wm, const LayH& L, Bui
     // ---------------- stream blocks (ParticleFormer): groups x | y, C = 128, head size 32, units = head pairs
     for (int i = 0; i < n_stream; ++i) {
         const std::string px[2] = {t + "blocks_x." + std::to_string(i), t + "blocks_y." + std::to_string(i)};
-        BlockW w[2] = {load_block(wm, px[0], h, I), load_block(wm, px[1], h, I)};
+        BlockW w[2] = {load_block(wm, px[0], h, I, 32), load_block(wm, px[1], h, I, 32)};
         *score_max = std::max(*score_max, std::max(score_bound(wm, px[0], 32), score_bound(wm, px[1], 32)));
         const bool last = i + 1 == n_stream;
         {
@@ -299,9 +313,9 @@ static int emit_program(const MmfModelDesc& d, WeightMap& wm, const LayH& L, Bui
             for (int g = 0; g < 2; ++g) {
                 float* G = P + g * tfp::SA_GROUP;
                 put(G + tfp::SA_BQKV, w[g].b_attn);
-                put(G + tfp::SA_QG, wm.get(px[g] + ".attn.q_layernorm.weight", 32)); put(G + tfp::SA_QB, wm.get(px[g] + ".attn.q_layernorm.bias", 32, -1, true));
+                put(G + tfp::SA_QG, w[g].q_g); put(G + tfp::SA_QB, w[g].q_b);
                 put(G + tfp::SA_KG, wm.get(px[g] + ".attn.k_layernorm.weight", 32)); put(G + tfp::SA_KB, wm.get(px[g] + ".attn.k_layernorm.bias", 32, -1, true));
-                put(G + tfp::SA_BPROJ, wm.get(px[g] + ".attn.c_proj.bias", h, -1, true));
+                put(G + tfp::SA_BPROJ, w[g].b_proj);
                 put(G + tfp::SA_LN2G, wm.get(px[g] + ".ln2.weight", h)); put(G + tfp::SA_LN2B, wm.get(px[g] + ".ln2.bias", h, -1, true));
             }
             P = b.blob(blob_idx + 1);                    // MLP stage
@@ -362,15 +376,15 @@ static int emit_program(const MmfModelDesc& d, WeightMap& wm, const LayH& L, Bui
     // ---------------- main blocks: C = 256, head size 64, units = heads
     for (int j = 0; j < n_main; ++j) {
         const std::string p = t + (pf ? "blocks_fuse." : "blocks.") + std::to_string(j);
-        const BlockW w = load_block(wm, p, E, I);
+        const BlockW w = load_block(wm, p, E, I, 64);
         *score_max = std::max(*score_max, score_bound(wm, p, 64));
         const bool last = j + 1 == n_main;
         {
             float* P = b.blob(blob_idx);                 // attention stage
             put(P + tfp::BA_BQKV, w.b_attn);
-            put(P + tfp::BA_QG, wm.get(p + ".attn.q_layernorm.weight", 64)); put(P + tfp::BA_QB, wm.get(p + ".attn.q_layernorm.bias", 64, -1, true));
+            put(P + tfp::BA_QG, w.q_g); put(P + tfp::BA_QB, w.q_b);
             put(P + tfp::BA_KG, wm.get(p + ".attn.k_layernorm.weight", 64)); put(P + tfp::BA_KB, wm.get(p + ".attn.k_layernorm.bias", 64, -1, true));
-            put(P + tfp::BA_BPROJ, wm.get(p + ".attn.c_proj.bias", E, -1, true));
+            put(P + tfp::BA_BPROJ, w.b_proj);
             put(P + tfp::BA_LN2G, wm.get(p + ".ln2.weight", E)); put(P + tfp::BA_LN2B, wm.get(p + ".ln2.bias", E, -1, true));
             P = b.blob(blob_idx + 1);                    // MLP stage
             put(P + tfp::BM_BFC, w.b_fc);
@@ -431,8 +445,10 @@ static int emit_program(const MmfModelDesc& d, WeightMap& wm, const LayH& L, Bui
             fold_ln(hx, bx0, gx, bx);
             fold_ln(hy, by0, gy, by);
         }
-        const std::vector<float> wx2 = wm.get(t + "head_x.2.weight", 3, I), bx2 = wm.get(t + "head_x.2.bias", 3),
-                                 wy2 = wm.get(t + "head_y.2.weight", V, I), by2 = wm.get(t + "head_y.2.bias", V);
+        std::vector<float> wx2 = wm.get(t + "head_x.2.weight", 3, I), wy2 = wm.get(t + "head_y.2.weight", V, I);
+        const std::vector<float> bx2 = wm.get(t + "head_x.2.bias", 3), by2 = wm.get(t + "head_y.2.bias", V);
+        for (float& x : wx2) x *= 0.5f;                // the head epilogue produces 2 GELU as well
+        for (float& x : wy2) x *= 0.5f;
         float* P = b.blob(blob_idx);
         put(P + tfp::HX_BIAS, bx0); put(P + tfp::HX_W2, wx2); put(P + tfp::HX_B2, bx2);
         for (int q = 0; q < 4; ++q) {
