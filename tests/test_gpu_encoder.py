@@ -58,6 +58,33 @@ def test_encoder_forward_matches_reference_golden(model, flavor, golden_dir):
 
 
 @pytest.mark.parametrize("model", ["FusedParticleFormer", "ParticleFormer"])
+def test_encoder_forward_softmax_with_row_maximum(model, golden_dir, monkeypatch):
+    """The tile kernel skips the softmax's row maximum when the checkpoint's q / k LayerNorm parameters bound every score
+    (true for the test weights); MMF_TILE_SOFTMAX_MAX=1, read when the model is created, keeps the maximum - the path a
+    checkpoint over the bound takes.  Same golden, same tolerances; the two modes agree to bf16 rounding."""
+    g = np.load(os.path.join(golden_dir, f"encoder_{model}_wide.npz"))
+    dev = torch.device("cuda:0")
+    T = lambda n: torch.from_numpy(g[n]).to(dev)
+    outs = []
+    for force in ("1", None):
+        if force:
+            monkeypatch.setenv("MMF_TILE_SOFTMAX_MAX", force)
+        else:
+            monkeypatch.delenv("MMF_TILE_SOFTMAX_MAX", raising=False)
+        cfg, sd, nm, synthetic = _setup(model, "wide", int(g["weight_seed"]))
+        vt, logits = nm.forward(T("continuous"), T("discrete"), T("mask"), T("time"))
+        torch.cuda.synchronize()
+        outs.append((vt.clone(), logits.clone()))
+        nm.close()
+    real = T("mask").bool().squeeze(-1)
+    e_vt, e_lg = _errs(outs[0][0], T("vt"), real), _errs(outs[0][1], T("logits"), real)
+    assert e_vt[0] < REL_L2 and e_vt[1] < MAX_ABS and e_lg[0] < REL_L2 and e_lg[1] < MAX_ABS, (e_vt, e_lg)
+    d_vt, d_lg = _errs(outs[0][0], outs[1][0], real), _errs(outs[0][1], outs[1][1], real)
+    print(f"{model}: with vs without the row maximum: vt rel {d_vt[0]:.2e}, logits rel {d_lg[0]:.2e}")
+    assert d_vt[0] < 1e-2 and d_lg[0] < 1e-2, (d_vt, d_lg)
+
+
+@pytest.mark.parametrize("model", ["FusedParticleFormer", "ParticleFormer"])
 def test_generate_teacher_forced_matches_reference_trajectory(model, golden_dir):
     """Full N=100 loop with the reference's token trajectory forced after each step: x_N within tolerance."""
     from mmf_b200 import _abi
