@@ -329,7 +329,8 @@ __device__ __forceinline__ void ln_regs(float* v, const float* g, const float* b
 
 // ---- attention epilogues -----------------------------------------------------------------------------------------
 // QKV of one 64-column unit sits in scratch (q | k | v, 64 columns each).  hf 0: q and v[0,32); hf 1: k and v[32,64).
-// bq/bk/bv point at the unit's 64 bias values; qg.. are the per-head LayerNorm parameters ([HS]).
+// bq/bk point at the unit's 64 bias values (the v bias lives in the projection bias, tftile_model.cu); qg.. are the per-head
+// LayerNorm parameters ([HS]).
 template <int HS, bool PAIR>
 struct QkvCols {     // scratch columns of q|k and v (see the op emission in tftile_model.cu)
     static constexpr uint32_t cQK = HS == 64 ? TfLay<PAIR>::cQkv64 : kScr + 128, cV = HS == 64 ? TfLay<PAIR>::cQkv64 + 128 : kScr + 64;
@@ -363,7 +364,7 @@ __device__ __forceinline__ void qk_epilogue(Epi& e, const float* bq, const float
         stage_row_bf16(e.arena + (e.hf ? L::oK : L::oQ), e.r, v);
     }
 }
-// v: bias, bf16 -> V[key = r][d] (row r of a [keys][128 B] swizzled chunk: the MN-major B operand of P V, so no transpose);
+// v: bf16 -> V[key = r][d] (row r of a [keys][128 B] swizzled chunk: the MN-major B operand of P V, so no transpose);
 // runs under the score MMA (plain tiles) / before it (pair tiles: the 160 score columns cover the v accumulator)
 template <int HS, bool PAIR>
 __device__ __forceinline__ void v_epilogue(Epi& e, float* prew = nullptr) {
@@ -581,7 +582,7 @@ __device__ __forceinline__ void pair_stage_k(Epi& e, const float* bq, const floa
 
 // nbq ... nkb: the q / k parameters of the NEXT unit of the block (pair tiles stage its K rows ahead; unused otherwise)
 template <int HS, bool PAIR>
-__device__ __forceinline__ void attention_unit(Epi& e, bool first, bool more, const float* bq, const float* bk, const float* bv, const float* qg,
+__device__ __forceinline__ void attention_unit(Epi& e, bool first, bool more, const float* bq, const float* bk, const float* qg,
                                                const float* qb, const float* kg, const float* kb, int lo, uint32_t span,
                                                const float* nbq = nullptr, const float* nbk = nullptr, const float* nqg = nullptr,
                                                const float* nqb = nullptr, const float* nkg = nullptr, const float* nkb = nullptr) {
@@ -1019,7 +1020,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                     {
                         const int ng = u == 1 ? 1 : g, nu = u ^ 1;          // the unit after (g, u): (g, 1) or (1, 0)
                         const float* NG = e.P + ng * tfp::SA_GROUP;
-                        attention_unit<32, PAIR>(e, g == 0 && u == 0, !(g == 1 && u == 1), G + tfp::SA_BQKV + u * 64, G + tfp::SA_BQKV + 128 + u * 64, G + tfp::SA_BQKV + 256 + u * 64,
+                        attention_unit<32, PAIR>(e, g == 0 && u == 0, !(g == 1 && u == 1), G + tfp::SA_BQKV + u * 64, G + tfp::SA_BQKV + 128 + u * 64,
                                                  G + tfp::SA_QG, G + tfp::SA_QB, G + tfp::SA_KG, G + tfp::SA_KB, att_lo, att_span,
                                                  NG + tfp::SA_BQKV + nu * 64, NG + tfp::SA_BQKV + 128 + nu * 64, NG + tfp::SA_QG, NG + tfp::SA_QB, NG + tfp::SA_KG, NG + tfp::SA_KB);
                     }
@@ -1074,7 +1075,7 @@ __global__ void __launch_bounds__(kThreads, 1) tf_tile_kernel(const __grid_const
                 param_acquire(e);                             // attention stage
                 const bool last = blk + 1 == a.n_main;
                 for (int u = 0; u < 4; ++u)
-                    attention_unit<64, PAIR>(e, u == 0, u < 3, e.P + tfp::BA_BQKV + u * 64, e.P + tfp::BA_BQKV + 256 + u * 64, e.P + tfp::BA_BQKV + 512 + u * 64,
+                    attention_unit<64, PAIR>(e, u == 0, u < 3, e.P + tfp::BA_BQKV + u * 64, e.P + tfp::BA_BQKV + 256 + u * 64,
                                        e.P + tfp::BA_QG, e.P + tfp::BA_QB, e.P + tfp::BA_KG, e.P + tfp::BA_KB, att_lo, att_span,
                                        e.P + tfp::BA_BQKV + (u + 1) * 64, e.P + tfp::BA_BQKV + 256 + (u + 1) * 64, e.P + tfp::BA_QG, e.P + tfp::BA_QB,
                                        e.P + tfp::BA_KG, e.P + tfp::BA_KB);
