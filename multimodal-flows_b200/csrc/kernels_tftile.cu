@@ -327,6 +327,25 @@ __device__ __forceinline__ void ln_regs(float* v, const float* g, const float* b
     }
 }
 
+// The same for rows whose mean is zero by construction: LayerNorm over a head does not see a constant added to the head's
+// outputs, so the host centres the q / k rows (and biases) of c_attn per head (tftile_model.cu centre_heads) and the sum of a
+// head's pre-activations vanishes up to the bf16 rounding of the centred weights (~2e-4 of the row's standard deviation).
+// Variance = mean of squares, no mean pass: three packed instructions per pair instead of five.
+template <int N>
+__device__ __forceinline__ void ln_regs_centred(float* v, const float* g, const float* b) {
+    float2 q01 = f2dup(0.f), q23 = f2dup(0.f);
+#pragma unroll
+    for (int i = 0; i < N; i += 4) { q01 = f2fma(MMF_V2(v, i), MMF_V2(v, i), q01); q23 = f2fma(MMF_V2(v, i + 2), MMF_V2(v, i + 2), q23); }
+    const float q = (q01.x + q01.y) + (q23.x + q23.y);
+    const float2 rs = f2dup(rsqrtf(q * (1.0f / N) + 1e-5f));
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+        const float4 gg = ldf4(g + i), bb = ldf4(b + i);
+        MMF_SET2(v, i, f2fma(f2mul(MMF_V2(v, i), rs), make_float2(gg.x, gg.y), make_float2(bb.x, bb.y)));
+        MMF_SET2(v, i + 2, f2fma(f2mul(MMF_V2(v, i + 2), rs), make_float2(gg.z, gg.w), make_float2(bb.z, bb.w)));
+    }
+}
+
 // ---- attention epilogues -----------------------------------------------------------------------------------------
 // QKV of one 64-column unit sits in scratch (q | k | v, 64 columns each).  hf 0: q and v[0,32); hf 1: k and v[32,64).
 // bq/bk point at the unit's 64 bias values (the v bias lives in the projection bias, tftile_model.cu); qg.. are the per-head
@@ -357,8 +376,8 @@ __device__ __forceinline__ void qk_epilogue(Epi& e, const float* bq, const float
     const float* g = e.hf ? kg : qg;
     const float* b = e.hf ? kb : qb;
     if (g) {
-        if (HS == 64) ln_regs<64>(v, g, b);
-        else { ln_regs<32>(v, g, b); ln_regs<32>(v + 32, g, b); }
+        if (HS == 64) ln_regs_centred<64>(v, g, b);
+        else { ln_regs_centred<32>(v, g, b); ln_regs_centred<32>(v + 32, g, b); }
     }
     if (row_ok<PAIR>(e.r)) {
         stage_row_bf16(e.arena + (e.hf ? L::oK : L::oQ), e.r, v);

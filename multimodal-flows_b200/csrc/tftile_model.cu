@@ -223,6 +223,22 @@ BlockW load_block(WeightMap& wm, const std::string& p, int C, int I, int hs) {
              wm.get(p + ".attn.q_layernorm.bias", hs, -1, true)};
     fold_ln(w.attn, w.b_attn, wm.get(p + ".ln1.weight", C), wm.get(p + ".ln1.bias", C, -1, true));
     fold_ln(w.fc, w.b_fc, wm.get(p + ".ln2.weight", C), wm.get(p + ".ln2.bias", C, -1, true));
+    // q and k rows centred per head: the per-head LayerNorm that follows does not see a constant added to all hs outputs of a
+    // head, and with centred rows (and biases) the head's pre-activations sum to zero - the kernel's LayerNorm skips the mean
+    // (ln_regs_centred in kernels_tftile.cu)
+    for (int part = 0; part < 2; ++part)
+        for (int r0 = part * C; r0 < (part + 1) * C; r0 += hs) {
+            for (int i = 0; i < C; ++i) {
+                double m = 0.0;
+                for (int r = r0; r < r0 + hs; ++r) m += w.attn.w[static_cast<size_t>(r) * C + i];
+                m /= hs;
+                for (int r = r0; r < r0 + hs; ++r) w.attn.w[static_cast<size_t>(r) * C + i] -= static_cast<float>(m);
+            }
+            double mb = 0.0;
+            for (int r = r0; r < r0 + hs; ++r) mb += w.b_attn[r];
+            mb /= hs;
+            for (int r = r0; r < r0 + hs; ++r) w.b_attn[r] -= static_cast<float>(mb);
+        }
     for (int o = 0; o < C; ++o) {
         double acc = 0.0;
         for (int i = 0; i < C; ++i) acc += static_cast<double>(w.proj.row(o)[i]) * w.b_attn[2 * C + i];

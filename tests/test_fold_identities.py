@@ -63,3 +63,19 @@ def test_half_of_gelu_moves_into_the_next_weights_exactly():
     ref = h.double() @ W.double().T
     folded = (2.0 * h).double() @ (W.float() * 0.5).double().T
     assert torch.allclose(ref, folded, rtol=1e-12, atol=1e-9)
+
+
+def test_centred_head_rows_make_the_per_head_layernorm_mean_free():
+    """LN over a head ignores a constant added to all of the head's outputs: with the head's rows of W (and biases) centred the
+    pre-activations sum to zero, and LN = y * rsqrt(mean(y^2) + eps) * g + b equals the LN of the un-centred projection."""
+    g = torch.Generator().manual_seed(4)
+    hs, C = 64, 256
+    x = torch.randn(50, C, generator=g, dtype=torch.float64)
+    W, b = torch.randn(hs, C, generator=g, dtype=torch.float64) + 0.7, torch.randn(hs, generator=g, dtype=torch.float64) + 2.0
+    gam, beta = torch.randn(hs, generator=g, dtype=torch.float64), torch.randn(hs, generator=g, dtype=torch.float64)
+    ref = _ln(x @ W.T + b) * gam + beta
+    Wc, bc = W - W.mean(0, keepdim=True), b - b.mean()
+    y = x @ Wc.T + bc
+    assert float(y.sum(-1).abs().max()) < 1e-9
+    out = y * torch.rsqrt((y * y).mean(-1, keepdim=True) + 1e-5) * gam + beta
+    assert torch.allclose(ref, out, rtol=1e-10, atol=1e-10)
